@@ -1,0 +1,214 @@
+// stem_pool.cu — the two HBM-bound backbone helpers around the tcgen05 convolutions:
+//   * stem convolution (3 input channels) fused with prep_images and the NCHW fp32 -> NHWC fp16
+//     relayout  (reference: utils.py:8-19 + first conv of backbone.py:88-99 / 115-132 / 44);
+//   * NHWC fp16 max pooling (reference: nn.MaxPool2d inside vgg16.features / resnet18.maxpool,
+//     F.max_pool2d at backbone.py:50,56).
+#include <cfloat>
+
+#include "din_common.cuh"
+
+namespace {
+
+constexpr int kStemTileH = 4;    // output rows per CTA
+constexpr int kStemTileW = 64;   // output cols per CTA
+constexpr int kStemThreads = 256;
+
+// One CTA = 4 x 64 output pixels x c_out channels.  Warp w: output row (w & 3), channel half (w >> 2);
+// lane l: pixels l and l + 32 of that row.  The (prep'd, zero-padded) input patch and the whole filter
+// bank live in shared memory; weight reads are warp-uniform broadcasts.
+template <int CPT>  // output channels per thread (c_out = 2 * CPT)
+__global__ void __launch_bounds__(kStemThreads)
+stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                 __half* __restrict__ y, int h, int wd, int oh, int ow, int kh, int kw, int stride, int pad,
+                 int relu, int prep) {
+  extern __shared__ float smem_f[];
+  const int c_out = 2 * CPT;
+  const int K = 3 * kh * kw;
+  const int in_th = (kStemTileH - 1) * stride + kh;
+  const int in_tw = (kStemTileW - 1) * stride + kw;
+  const int in_tw_p = in_tw | 1;  // odd row pitch: fewer bank conflicts for strided reads
+  float* ws = smem_f;                       // [K][c_out]
+  float* xs = smem_f + K * c_out;           // [3][in_th][in_tw_p]
+
+  const int img = blockIdx.z;
+  const int oy0 = blockIdx.y * kStemTileH;
+  const int ox0 = blockIdx.x * kStemTileW;
+
+  // weights: OIHW [c_out][3][kh][kw] -> ws[(c*kh + ky)*kw + kx][o]
+  for (int i = threadIdx.x; i < K * c_out; i += kStemThreads) {
+    const int o = i / K;
+    const int k = i - o * K;
+    ws[k * c_out + o] = w[i];
+  }
+  const int iy0 = oy0 * stride - pad;
+  const int ix0 = ox0 * stride - pad;
+  const float* xi = x + static_cast<size_t>(img) * 3 * h * wd;
+  for (int i = threadIdx.x; i < 3 * in_th * in_tw; i += kStemThreads) {
+    const int c = i / (in_th * in_tw);
+    const int r = i - c * (in_th * in_tw);
+    const int yy = r / in_tw;
+    const int xx = r - yy * in_tw;
+    const int gy = iy0 + yy, gx = ix0 + xx;
+    float v = 0.0f;
+    if (gy >= 0 && gy < h && gx >= 0 && gx < wd) {
+      v = __ldg(xi + (static_cast<size_t>(c) * h + gy) * wd + gx);
+      // prep_images, same three roundings as the reference (utils.py:14-17): div, sub, mul
+      if (prep) v = __fmul_rn(__fsub_rn(__fdiv_rn(v, 255.0f), 0.5f), 2.0f);
+    }
+    xs[(c * in_th + yy) * in_tw_p + xx] = v;
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = warp & 3;
+  const int half_id = warp >> 2;
+  float acc0[CPT], acc1[CPT];
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) {
+    const float b = bias ? __ldg(bias + half_id * CPT + j) : 0.0f;
+    acc0[j] = b;
+    acc1[j] = b;
+  }
+  const float* wbase = ws + half_id * CPT;
+  for (int c = 0; c < 3; ++c) {
+    for (int ky = 0; ky < kh; ++ky) {
+      const float* xrow = xs + (c * in_th + row * stride + ky) * in_tw_p;
+      for (int kx = 0; kx < kw; ++kx) {
+        const float a0 = xrow[lane * stride + kx];
+        const float a1 = xrow[(lane + 32) * stride + kx];
+        const float4* wv = reinterpret_cast<const float4*>(wbase + ((c * kh + ky) * kw + kx) * c_out);
+#pragma unroll
+        for (int j = 0; j < CPT / 4; ++j) {
+          const float4 t = wv[j];
+          acc0[4 * j + 0] = fmaf(a0, t.x, acc0[4 * j + 0]);
+          acc0[4 * j + 1] = fmaf(a0, t.y, acc0[4 * j + 1]);
+          acc0[4 * j + 2] = fmaf(a0, t.z, acc0[4 * j + 2]);
+          acc0[4 * j + 3] = fmaf(a0, t.w, acc0[4 * j + 3]);
+          acc1[4 * j + 0] = fmaf(a1, t.x, acc1[4 * j + 0]);
+          acc1[4 * j + 1] = fmaf(a1, t.y, acc1[4 * j + 1]);
+          acc1[4 * j + 2] = fmaf(a1, t.z, acc1[4 * j + 2]);
+          acc1[4 * j + 3] = fmaf(a1, t.w, acc1[4 * j + 3]);
+        }
+      }
+    }
+  }
+  const int oy = oy0 + row;
+  if (oy >= oh) return;
+#pragma unroll
+  for (int pxi = 0; pxi < 2; ++pxi) {
+    const int ox = ox0 + lane + 32 * pxi;
+    if (ox >= ow) continue;
+    const float* a = pxi ? acc1 : acc0;
+    __half* yp = y + ((static_cast<size_t>(img) * oh + oy) * ow + ox) * c_out + half_id * CPT;
+#pragma unroll
+    for (int j = 0; j < CPT; j += 8) {
+      uint4 o;
+      __half2* h2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float v0 = a[j + 2 * e], v1 = a[j + 2 * e + 1];
+        if (relu) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
+        h2[e] = __floats2half2_rn(v0, v1);
+      }
+      *reinterpret_cast<uint4*>(yp + j) = o;
+    }
+  }
+}
+
+// 8 channels (one 16-byte vector) of one output pixel per thread.
+__global__ void __launch_bounds__(256)
+maxpool_nhwc_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n, int h, int w, int c8, int oh,
+                    int ow, int k, int stride, int pad) {
+  const size_t total = static_cast<size_t>(n) * oh * ow * c8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % c8);
+    size_t t = i / c8;
+    const int ox = static_cast<int>(t % ow);
+    t /= ow;
+    const int oy = static_cast<int>(t % oh);
+    const int img = static_cast<int>(t / oh);
+    const __half2 ninf = __float2half2_rn(-65504.0f);
+    __half2 m[4] = {ninf, ninf, ninf, ninf};
+    bool any = false;
+    for (int ky = 0; ky < k; ++ky) {
+      const int iy = oy * stride - pad + ky;
+      if (iy < 0 || iy >= h) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int ix = ox * stride - pad + kx;
+        if (ix < 0 || ix >= w) continue;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x) + ((static_cast<size_t>(img) * h + iy) * w + ix) * c8 + cv);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+        if (!any) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) m[e] = h2[e];
+          any = true;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) m[e] = __hmax2(m[e], h2[e]);
+        }
+      }
+    }
+    uint4 o;
+    __half2* oh2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) oh2[e] = m[e];
+    reinterpret_cast<uint4*>(y)[i] = o;
+  }
+}
+
+}  // namespace
+
+extern "C" int din_stem_conv_nchw_f32(const float* x, const float* w, const float* bias, void* y, int n, int h,
+                                      int w_in, int c_out, int kh, int kw, int stride, int pad, int relu, int prep,
+                                      void* stream) {
+  DIN_CHECK_ARG(x && w && y, "din_stem_conv_nchw_f32: null pointer");
+  DIN_CHECK_ARG(n > 0 && h > 0 && w_in > 0, "din_stem_conv_nchw_f32: bad extent n=%d h=%d w=%d", n, h, w_in);
+  DIN_CHECK_ARG(c_out == 64 || c_out == 32, "din_stem_conv_nchw_f32: c_out=%d unsupported (32 or 64)", c_out);
+  DIN_CHECK_ARG(kh >= 1 && kw >= 1 && kh * kw <= 49, "din_stem_conv_nchw_f32: bad filter %dx%d", kh, kw);
+  DIN_CHECK_ARG(stride >= 1 && stride <= 2 && pad >= 0, "din_stem_conv_nchw_f32: bad stride/pad");
+  DIN_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 15) == 0, "din_stem_conv_nchw_f32: y must be 16-byte aligned");
+  DIN_CHECK_ARG(n <= 65535, "din_stem_conv_nchw_f32: n=%d exceeds grid.z", n);
+  const int oh = (h + 2 * pad - kh) / stride + 1;
+  const int ow = (w_in + 2 * pad - kw) / stride + 1;
+  DIN_CHECK_ARG(oh > 0 && ow > 0, "din_stem_conv_nchw_f32: empty output");
+  const int K = 3 * kh * kw;
+  const int in_th = (kStemTileH - 1) * stride + kh;
+  const int in_tw_p = ((kStemTileW - 1) * stride + kw) | 1;
+  const size_t smem = (static_cast<size_t>(K) * c_out + 3 * in_th * in_tw_p) * sizeof(float);
+  dim3 grid((ow + kStemTileW - 1) / kStemTileW, (oh + kStemTileH - 1) / kStemTileH, n);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c_out == 64) {
+    DIN_CHECK_CUDA(cudaFuncSetAttribute(stem_conv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+    stem_conv_kernel<32><<<grid, kStemThreads, smem, st>>>(x, w, bias, static_cast<__half*>(y), h, w_in, oh, ow,
+                                                           kh, kw, stride, pad, relu, prep);
+  } else {
+    DIN_CHECK_CUDA(cudaFuncSetAttribute(stem_conv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+    stem_conv_kernel<16><<<grid, kStemThreads, smem, st>>>(x, w, bias, static_cast<__half*>(y), h, w_in, oh, ow,
+                                                           kh, kw, stride, pad, relu, prep);
+  }
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
+extern "C" int din_maxpool2d_nhwc_f16(const void* x, void* y, int n, int h, int w, int c, int k, int stride,
+                                      int pad, void* stream) {
+  DIN_CHECK_ARG(x && y, "din_maxpool2d_nhwc_f16: null pointer");
+  DIN_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0,
+                "din_maxpool2d_nhwc_f16: bad shape n=%d h=%d w=%d c=%d (c must be a multiple of 8)", n, h, w, c);
+  DIN_CHECK_ARG(k >= 1 && stride >= 1 && pad >= 0 && pad < k, "din_maxpool2d_nhwc_f16: bad window");
+  DIN_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+                "din_maxpool2d_nhwc_f16: pointers must be 16-byte aligned");
+  const int oh = (h + 2 * pad - k) / stride + 1;
+  const int ow = (w + 2 * pad - k) / stride + 1;
+  DIN_CHECK_ARG(oh > 0 && ow > 0, "din_maxpool2d_nhwc_f16: empty output");
+  const size_t total = static_cast<size_t>(n) * oh * ow * (c / 8);
+  const int sms = din_num_sms();
+  const int grid = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(sms > 0 ? sms : 148) * 16));
+  maxpool_nhwc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), static_cast<__half*>(y), n, h, w, c / 8, oh, ow, k, stride, pad);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}

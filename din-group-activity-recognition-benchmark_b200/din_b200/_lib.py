@@ -1,0 +1,61 @@
+"""ctypes binding of the C ABI in include/din_sm100.h (one prototype per exported symbol)."""
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libdin_sm100.so")
+
+DIN_OK = 0
+
+
+class DinError(RuntimeError):
+    pass
+
+
+class DinConvDesc(C.Structure):
+    _fields_ = [(name, C.c_int32) for name in (
+        "n", "h", "w", "c_in", "x_c_stride", "c_out", "y_c_stride", "kh", "kw", "stride",
+        "pad_h", "pad_w", "relu", "out_f32")]
+
+
+_vp, _i, _fp = C.c_void_p, C.c_int, C.c_void_p  # float* is passed as a raw address too
+
+# name -> (restype, argtypes).  tests/test_abi.py checks this table against include/din_sm100.h.
+PROTOTYPES = {
+    "din_abi_version": (C.c_int, []),
+    "din_last_error_string": (C.c_char_p, []),
+    "din_device_sm_count": (C.c_int, []),
+    "din_stem_conv_nchw_f32": (C.c_int, [_fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "din_conv2d_nhwc_f16": (C.c_int, [C.POINTER(DinConvDesc), _vp, _vp, _fp, _vp, _vp, _vp]),
+    "din_pack_conv_weight_f16": (C.c_int, [_fp, _fp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "din_maxpool2d_nhwc_f16": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load():
+    """Load libdin_sm100.so (built in-tree by __graft_entry__.build()). Fails loudly if absent."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise DinError(
+                    f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(there is no CPU fallback for the DIN hot path)")
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in PROTOTYPES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != DIN_OK:
+        msg = load().din_last_error_string().decode("utf-8", "replace")
+        raise DinError(f"{what or 'libdin_sm100'} failed (code {rc}): {msg}")
+    return rc

@@ -1,0 +1,114 @@
+"""tcgen05 implicit-GEMM convolution vs a plain PyTorch fp32 reference of the same op (GPU).
+
+Both sides see the SAME fp16-rounded operands, so the only difference is fp32 accumulation order:
+tolerance 2e-3 * max|ref| on the fp16 output (one fp16 ulp of the largest value is 9.8e-4).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_conv(x_nhwc_h, w_oihw_h, bias, stride, pad, relu, residual=None):
+    x = x_nhwc_h.float().permute(0, 3, 1, 2)
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        y = F.conv2d(x, w_oihw_h.float(), bias, stride=stride, padding=pad)
+        torch.backends.cuda.matmul.allow_tf32 = old
+    if residual is not None:
+        y = y + residual.float().permute(0, 3, 1, 2)
+    if relu:
+        y = F.relu(y)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+CASES = [
+    # n, h, w, cin, cout, k, stride, pad, relu
+    (1, 8, 16, 64, 64, 1, 1, 0, False),      # one tile, one K step, single tap
+    (1, 8, 16, 64, 64, 3, 1, 1, False),      # 3x3, halo zero-fill on all sides
+    (2, 45, 80, 128, 128, 3, 1, 1, True),    # ragged tiles (45 rows), BN=128
+    (1, 90, 160, 256, 256, 3, 1, 1, True),   # BN=256
+    (1, 22, 40, 512, 512, 3, 1, 1, True),    # two N tiles, deep K (72 steps)
+    (3, 36, 64, 64, 128, 3, 2, 1, True),     # stride 2 (ResNet downsampling 3x3)
+    (2, 36, 64, 64, 128, 1, 2, 0, False),    # stride-2 1x1 (ResNet shortcut)
+    (1, 23, 40, 192, 320, 1, 1, 0, True),    # cout not a multiple of BN, cin = 3 blocks
+    (1, 17, 29, 128, 192, (1, 7), 1, (0, 3), True),   # Inception 1x7
+    (1, 17, 29, 128, 192, (7, 1), 1, (3, 0), True),   # Inception 7x1
+    (1, 720, 1280, 64, 64, 3, 1, 1, True),   # VGG conv1_2 at full size (7200 tiles, persistent loop)
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(c) for c in CASES])
+def test_conv_matches_torch(cuda, case):
+    from din_b200 import ops
+    n, h, w, cin, cout, k, stride, pad, relu = case
+    kh, kw = (k, k) if isinstance(k, int) else k
+    ph, pw = (pad, pad) if isinstance(pad, int) else pad
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    x = (torch.randn(n, h, w, cin, generator=g) * 1.0).to(cuda).half()
+    wt = (torch.randn(cout, cin, kh, kw, generator=g) * (2.0 / (cin * kh * kw)) ** 0.5).to(cuda)
+    bias = torch.randn(cout, generator=g).to(cuda)
+    wp = ops.pack_conv_weight(wt)
+    assert wp.shape == (cout, kh, kw, cin)
+    # the packed weight is exactly the fp16 rounding of the OIHW weight, tap-major
+    torch.testing.assert_close(wp.float(), wt.half().float().permute(0, 2, 3, 1), rtol=0, atol=0)
+    y = ops.conv2d_nhwc(x, wp, bias, stride=stride, pad=(ph, pw), relu=relu)
+    torch.cuda.synchronize()
+    ref = _ref_conv(x, wt.half(), bias, stride, (ph, pw), relu)
+    assert y.shape == ref.shape
+    err = (y.float() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2e-3 * scale, f"max abs err {err} vs scale {scale}"
+
+
+def test_conv_f32_out_residual_and_channel_slices(cuda):
+    from din_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(7)
+    n, h, w = 2, 23, 40
+    xbuf = torch.randn(n, h, w, 192, generator=g).to(cuda).half()      # conv reads channels [64,192)
+    wt = (torch.randn(72, 128, 3, 3, generator=g) * 0.03).to(cuda)
+    bias = torch.randn(72, generator=g).to(cuda)
+    res = torch.randn(n, h, w, 200, generator=g).to(cuda).half()
+    out = torch.zeros(n, h, w, 200, device=cuda, dtype=torch.float16)  # conv writes channels [64,136)
+    wp = ops.pack_conv_weight(wt)
+    ops.conv2d_nhwc(xbuf, wp, bias, stride=1, pad=(1, 1), relu=True, residual=res, out=out,
+                    c_in=128, x_c_offset=64, y_c_offset=64)
+    ref = _ref_conv(xbuf[..., 64:192].contiguous(), wt.half(), bias, 1, (1, 1), True,
+                    residual=res[..., 64:136].contiguous())
+    torch.cuda.synchronize()
+    assert (out[..., :64] == 0).all() and (out[..., 136:] == 0).all()   # neighbours untouched
+    err = (out[..., 64:136].float() - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item()
+    # fp32 output (the fc_emb GEMM shape: rows x K -> 1024), tighter tolerance
+    a = torch.randn(1, 1, 360, 1280, generator=g).to(cuda).half()
+    wl = (torch.randn(1024, 1280, 1, 1, generator=g) * 0.03).to(cuda)
+    bl = torch.randn(1024, generator=g).to(cuda)
+    y = ops.conv2d_nhwc(a, ops.pack_conv_weight(wl), bl, out_f32=True)
+    ref = a.float().reshape(360, 1280) @ wl.half().float().reshape(1024, 1280).t() + bl
+    torch.cuda.synchronize()
+    err = (y.reshape(360, 1024) - ref).abs().max().item()
+    assert err <= 2e-5 * max(1.0, ref.abs().max().item()) * 10, err
+
+
+def test_stem_and_pool(cuda):
+    from din_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x = torch.randint(0, 256, (2, 3, 70, 150), generator=g).float().to(cuda)
+    for (co, k, s, p) in [(64, 3, 1, 1), (64, 7, 2, 3), (32, 3, 2, 0)]:
+        wt = (torch.randn(co, 3, k, k, generator=g) * 0.1).to(cuda)
+        b = torch.randn(co, generator=g).to(cuda)
+        y = ops.stem_conv(x, wt, b, stride=s, pad=p, relu=True, prep=True)
+        xp = ((x / 255.0) - 0.5) * 2.0
+        ref = F.relu(F.conv2d(xp, wt, b, stride=s, padding=p)).permute(0, 2, 3, 1)
+        torch.cuda.synchronize()
+        assert y.shape == ref.shape
+        err = (y.float() - ref).abs().max().item()
+        assert err <= 1e-3 * ref.abs().max().item() + 1e-3, (co, k, s, p, err)
+    t = torch.randn(2, 45, 81, 64, generator=g).to(cuda).half()
+    for (k, s, p) in [(2, 2, 0), (3, 2, 1), (3, 2, 0)]:
+        y = ops.maxpool2d_nhwc(t, k, s, p)
+        ref = F.max_pool2d(t.float().permute(0, 3, 1, 2), k, s, p).permute(0, 2, 3, 1)
+        torch.cuda.synchronize()
+        assert torch.equal(y.float(), ref), (k, s, p)
