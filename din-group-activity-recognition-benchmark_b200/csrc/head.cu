@@ -1,0 +1,536 @@
+// head.cu — everything after the backbone: RoIAlign, embedding LayerNorm, the lite branch, the fused
+// Dynamic Relation / Dynamic Walk step, fusion LayerNorm and the group read-out.  All fp32 except the
+// RoIAlign input/output (fp16 feature map in, fp16 fc_emb operand out).
+//
+// Reference call sites:
+//   RoIAlign                  infer_model.py:178-181 (external longcw/RoIAlign.pytorch crop_and_resize)
+//   nl_emb_1 + ReLU           infer_model.py:185-186
+//   point_conv/point_ln       infer_model.py:188-193
+//   Dynamic_Person_Inference  infer_module/dynamic_infer_module.py:121-151, 184-282, 344-404
+//   fusion + dpi_nl           infer_model.py:203-216 (volleyball), :1298-1301 (collective)
+//   read-out                  infer_model.py:224-232 (volleyball), :1311-1313 (collective)
+#include <cfloat>
+
+#include "din_common.cuh"
+
+namespace {
+
+using namespace din;
+
+// ================================================================================================
+// RoIAlign (crop_and_resize, one bilinear sample per bin, zero extrapolation)
+// ================================================================================================
+// One warp per (box, bin); lanes sweep the channel dimension 8 fp16 at a time (16-byte vectors), so
+// every global access is a fully coalesced 512-byte warp transaction on the NHWC map.  The output row
+// of box m is [bin][channel] — the K-order the packed fc_emb weight uses — so RoIAlign's result is
+// directly the A operand of the embedding GEMM.
+__global__ void __launch_bounds__(256)
+roi_align_kernel(const __half* __restrict__ fm, const float* __restrict__ boxes, const int* __restrict__ box_ind,
+                 __half* __restrict__ out, int n_img, int H, int W, int D, int fm_c_stride, int M, int crop_h,
+                 int crop_w) {
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int bins = crop_h * crop_w;
+  if (warp_global >= M * bins) return;
+  const int m = warp_global / bins;
+  const int bin = warp_global - m * bins;
+  const int iy = bin / crop_w;
+  const int ix = bin - iy * crop_w;
+
+  const float x1 = __ldg(boxes + 4 * m + 0), y1 = __ldg(boxes + 4 * m + 1);
+  const float x2 = __ldg(boxes + 4 * m + 2), y2 = __ldg(boxes + 4 * m + 3);
+  const int b = __ldg(box_ind + m);
+  // RoIAlign.forward (transform_fpcoor=True): same fp32 op order as the published implementation, no
+  // FMA contraction, so floor()/validity decisions agree with the CPU restatement.
+  const float Wm1 = static_cast<float>(W - 1), Hm1 = static_cast<float>(H - 1);
+  const float spacing_w = __fdiv_rn(__fsub_rn(x2, x1), static_cast<float>(crop_w));
+  const float spacing_h = __fdiv_rn(__fsub_rn(y2, y1), static_cast<float>(crop_h));
+  const float nx0 = __fdiv_rn(__fsub_rn(__fadd_rn(x1, __fdiv_rn(spacing_w, 2.0f)), 0.5f), Wm1);
+  const float ny0 = __fdiv_rn(__fsub_rn(__fadd_rn(y1, __fdiv_rn(spacing_h, 2.0f)), 0.5f), Hm1);
+  const float nw = __fdiv_rn(__fmul_rn(spacing_w, static_cast<float>(crop_w - 1)), Wm1);
+  const float nh = __fdiv_rn(__fmul_rn(spacing_h, static_cast<float>(crop_h - 1)), Hm1);
+  const float by1 = ny0, bx1 = nx0, by2 = __fadd_rn(ny0, nh), bx2 = __fadd_rn(nx0, nw);
+  // crop_and_resize
+  const float height_scale = __fdiv_rn(__fmul_rn(__fsub_rn(by2, by1), Hm1), static_cast<float>(crop_h - 1));
+  const float width_scale = __fdiv_rn(__fmul_rn(__fsub_rn(bx2, bx1), Wm1), static_cast<float>(crop_w - 1));
+  const float in_y = __fadd_rn(__fmul_rn(by1, Hm1), __fmul_rn(static_cast<float>(iy), height_scale));
+  const float in_x = __fadd_rn(__fmul_rn(bx1, Wm1), __fmul_rn(static_cast<float>(ix), width_scale));
+
+  __half* op = out + (static_cast<size_t>(m) * bins + bin) * D;
+  const bool ok = (b >= 0) && (b < n_img) && (in_y >= 0.0f) && (in_y <= Hm1) && (in_x >= 0.0f) && (in_x <= Wm1);
+  if (!ok) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (int c = lane * 8; c < D; c += 256) *reinterpret_cast<uint4*>(op + c) = z;
+    return;
+  }
+  const int top = static_cast<int>(floorf(in_y)), bot = static_cast<int>(ceilf(in_y));
+  const int left = static_cast<int>(floorf(in_x)), right = static_cast<int>(ceilf(in_x));
+  const float yl = in_y - static_cast<float>(top);
+  const float xl = in_x - static_cast<float>(left);
+  const __half* base = fm + static_cast<size_t>(b) * H * W * fm_c_stride;
+  const __half* ptl = base + (static_cast<size_t>(top) * W + left) * fm_c_stride;
+  const __half* ptr = base + (static_cast<size_t>(top) * W + right) * fm_c_stride;
+  const __half* pbl = base + (static_cast<size_t>(bot) * W + left) * fm_c_stride;
+  const __half* pbr = base + (static_cast<size_t>(bot) * W + right) * fm_c_stride;
+  for (int c = lane * 8; c < D; c += 256) {
+    const uint4 vtl = __ldg(reinterpret_cast<const uint4*>(ptl + c));
+    const uint4 vtr = __ldg(reinterpret_cast<const uint4*>(ptr + c));
+    const uint4 vbl = __ldg(reinterpret_cast<const uint4*>(pbl + c));
+    const uint4 vbr = __ldg(reinterpret_cast<const uint4*>(pbr + c));
+    const __half2* htl = reinterpret_cast<const __half2*>(&vtl);
+    const __half2* htr = reinterpret_cast<const __half2*>(&vtr);
+    const __half2* hbl = reinterpret_cast<const __half2*>(&vbl);
+    const __half2* hbr = reinterpret_cast<const __half2*>(&vbr);
+    uint4 o;
+    __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 tl = __half22float2(htl[e]), tr = __half22float2(htr[e]);
+      const float2 bl = __half22float2(hbl[e]), br = __half22float2(hbr[e]);
+      const float t0 = tl.x + (tr.x - tl.x) * xl, t1 = tl.y + (tr.y - tl.y) * xl;
+      const float b0 = bl.x + (br.x - bl.x) * xl, b1 = bl.y + (br.y - bl.y) * xl;
+      ho[e] = __floats2half2_rn(t0 + (b0 - t0) * yl, t1 + (b1 - t1) * yl);
+    }
+    *reinterpret_cast<uint4*>(op + c) = o;
+  }
+}
+
+// ================================================================================================
+// block-wide sum helper
+// ================================================================================================
+template <int kThreads>
+__device__ __forceinline__ float block_sum(float v, float* red /* >= 33 floats */) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();  // protect `red` from the previous use
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    float t = lane < (kThreads / 32) ? red[lane] : 0.0f;
+    t = warp_sum(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+// ================================================================================================
+// LayerNorm over strided groups, with optional pre-add, ReLU and post-add
+//   y = [relu]( LN(x (+ pre)) * gamma + beta ) (+ post)
+// One CTA per group.  A group is `rows` x `cols` elements, element (r, c) at
+//   base(g) + r*row_stride + c,   base(g) = (g / n_inner)*outer_stride + (g % n_inner)*inner_stride,
+// gamma/beta indexed r*cols + c.  Covers nl_emb_1 (rows=1, one group per person), point_ln / dpi_nl
+// / hier_LN (one group per clip, rows=1, cols=T*N*C) and Collective's LayerNorm([T, C]) over the
+// [N, T, C] permutation of a [T, N, C] tensor (rows=T, row_stride=N*C, inner_stride=C).
+// Two passes over L2-resident data (mean, then centred variance), biased variance as torch.
+// ================================================================================================
+constexpr int kLnThreads = 512;
+
+__global__ void __launch_bounds__(kLnThreads)
+group_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ pre, const float* __restrict__ post,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y,
+                       int n_inner, long long outer_stride, long long inner_stride, int rows,
+                       long long row_stride, int cols, float eps, int relu, const int* __restrict__ n_valid) {
+  __shared__ float red[33];
+  const int g = blockIdx.x;
+  const int go = g / n_inner, gi = g - go * n_inner;
+  if (n_valid != nullptr && gi >= __ldg(n_valid + go)) return;  // padded actor (Collective)
+  const size_t base = static_cast<size_t>(go) * outer_stride + static_cast<size_t>(gi) * inner_stride;
+  const int cols4 = cols >> 2;
+  const int total4 = rows * cols4;
+  float s = 0.0f;
+  for (int i = threadIdx.x; i < total4; i += kLnThreads) {
+    const int r = i / cols4, c4 = i - r * cols4;
+    const size_t off = base + static_cast<size_t>(r) * row_stride + 4 * c4;
+    float4 v = __ldg(reinterpret_cast<const float4*>(x + off));
+    if (pre != nullptr) {
+      const float4 p = __ldg(reinterpret_cast<const float4*>(pre + off));
+      v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+    }
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  const float n_el = static_cast<float>(rows) * static_cast<float>(cols);
+  const float mean = block_sum<kLnThreads>(s, red) / n_el;
+  float q = 0.0f;
+  for (int i = threadIdx.x; i < total4; i += kLnThreads) {
+    const int r = i / cols4, c4 = i - r * cols4;
+    const size_t off = base + static_cast<size_t>(r) * row_stride + 4 * c4;
+    float4 v = __ldg(reinterpret_cast<const float4*>(x + off));
+    if (pre != nullptr) {
+      const float4 p = __ldg(reinterpret_cast<const float4*>(pre + off));
+      v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+    }
+    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+    q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+  }
+  const float var = block_sum<kLnThreads>(q, red) / n_el;
+  const float rstd = rsqrtf(var + eps);
+  for (int i = threadIdx.x; i < total4; i += kLnThreads) {
+    const int r = i / cols4, c4 = i - r * cols4;
+    const size_t off = base + static_cast<size_t>(r) * row_stride + 4 * c4;
+    float4 v = __ldg(reinterpret_cast<const float4*>(x + off));
+    if (pre != nullptr) {
+      const float4 p = __ldg(reinterpret_cast<const float4*>(pre + off));
+      v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+    }
+    const size_t goff = static_cast<size_t>(r) * cols + 4 * c4;
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + goff));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + goff));
+    float4 o;
+    o.x = (v.x - mean) * rstd * ga.x + be.x;
+    o.y = (v.y - mean) * rstd * ga.y + be.y;
+    o.z = (v.z - mean) * rstd * ga.z + be.z;
+    o.w = (v.w - mean) * rstd * ga.w + be.w;
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    if (post != nullptr) {
+      const float4 p = __ldg(reinterpret_cast<const float4*>(post + off));
+      o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+    }
+    *reinterpret_cast<float4*>(y + off) = o;
+  }
+}
+
+// ================================================================================================
+// fp32 linear:  y[M,N] = x[M,K] · w[N,K]^T (+ bias) (ReLU)      (point_conv, hidden_weight)
+// 64x64 tile, K step 16, 256 threads x (4x4) outputs, operands staged transposed in shared memory.
+// ================================================================================================
+constexpr int kLinBM = 64, kLinBN = 64, kLinBK = 16;
+
+__global__ void __launch_bounds__(256)
+linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                  float* __restrict__ y, int M, int N, int K, int relu, int accumulate) {
+  __shared__ float xs[kLinBK][kLinBM + 4];
+  __shared__ float ws[kLinBK][kLinBN + 4];
+  const int m0 = blockIdx.y * kLinBM, n0 = blockIdx.x * kLinBN;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  const int lr = threadIdx.x >> 2;        // 0..63: tile row loaded by this thread
+  const int lk = (threadIdx.x & 3) * 4;   // 0,4,8,12
+  for (int k0 = 0; k0 < K; k0 += kLinBK) {
+    float4 xv = make_float4(0, 0, 0, 0), wv = make_float4(0, 0, 0, 0);
+    if (m0 + lr < M) xv = __ldg(reinterpret_cast<const float4*>(x + static_cast<size_t>(m0 + lr) * K + k0 + lk));
+    if (n0 + lr < N) wv = __ldg(reinterpret_cast<const float4*>(w + static_cast<size_t>(n0 + lr) * K + k0 + lk));
+    __syncthreads();
+    xs[lk + 0][lr] = xv.x; xs[lk + 1][lr] = xv.y; xs[lk + 2][lr] = xv.z; xs[lk + 3][lr] = xv.w;
+    ws[lk + 0][lr] = wv.x; ws[lk + 1][lr] = wv.y; ws[lk + 2][lr] = wv.z; ws[lk + 3][lr] = wv.w;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kLinBK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&xs[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&ws[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (bias ? __ldg(bias + n) : 0.0f);
+      if (relu) v = fmaxf(v, 0.0f);
+      if (accumulate) v += y[static_cast<size_t>(m) * N + n];
+      y[static_cast<size_t>(m) * N + n] = v;
+    }
+  }
+}
+
+// ================================================================================================
+// Dynamic Relation + Dynamic Walk for one sampling ratio (dynamic_infer_ratio, :184-282), fused:
+//   phase 1  offsets/relation logits = the two small convs over the T x N grid (p_conv, scale_conv):
+//            one CTA per (clip, frame) keeps the kt input rows it needs in shared memory and streams
+//            the tap-major weight [tap][3k²][C] once, reused across all N actors of the frame;
+//   phase 2  per actor (one warp each): softmax over the k² taps with __shfl-free uniform math,
+//            sample positions p = grid + tap + offset, detached floor, clamp-then-weight bilinear
+//            blend of 4 corners gathered from the zero-padded clip, relation-weighted sum over taps;
+//   y[b,t,n,:] (+)= coef * result      (coef = 1/len(ratios) or beta[r]; accumulate for ratios > first)
+// Nothing but x is read from HBM and nothing but y is written: the 4 x [B,T,N,k²,C] gathers and the
+// ~40 elementwise temporaries of the reference never exist.
+// ================================================================================================
+constexpr int kDinThreads = 256;
+constexpr int kDinWarps = kDinThreads / 32;
+constexpr int kDinMaxN = 16;     // actors per frame (12 Volleyball, 13 Collective)
+constexpr int kDinMaxK2 = 9;     // taps
+constexpr int kDinMaxOutPerWarp = 4;  // ceil(27 / 8)
+
+__global__ void __launch_bounds__(kDinThreads)
+dynamic_infer_kernel(const float* __restrict__ x, const float* __restrict__ w_tap, const float* __restrict__ b_cat,
+                     float* __restrict__ y, int T, int N, int C, int kt, int kn, int ratio, int scale_factor,
+                     const float* __restrict__ coef_ptr, float coef_scalar, int accumulate,
+                     const int* __restrict__ n_valid) {
+  extern __shared__ float smem_f[];
+  const int b = blockIdx.x / T;
+  const int t = blockIdx.x - b * T;
+  const int Nb = n_valid ? min(__ldg(n_valid + b), N) : N;  // real actors of this clip
+  const int k2 = kt * kn;
+  const int n_out = scale_factor ? 3 * k2 : 2 * k2;
+  const int pt = (kt - 1) / 2 * ratio, pl = (kn - 1) / 2 * ratio;
+  const int dy0 = -(((kt - 1) * ratio + 1) / 2);  // == python -(field-1)//2 for field = (k-1)*ratio+1
+  const int dx0 = -(((kn - 1) * ratio + 1) / 2);
+  float* xs = smem_f;                               // [kt][N][C] input rows t + dy (zero outside the clip)
+  float* conv_s = smem_f + static_cast<size_t>(kt) * N * C;   // [N][n_out]
+  const float* xb = x + static_cast<size_t>(b) * T * N * C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C4 = C >> 2;
+
+  // ---- stage the kt rows
+  for (int i = threadIdx.x; i < kt * N * C4; i += kDinThreads) {
+    const int c4 = i % C4;
+    const int rn = i / C4;
+    const int n = rn % N;
+    const int ky = rn / N;
+    const int tt = t + dy0 + ky * ratio;
+    float4 v = make_float4(0, 0, 0, 0);
+    if (tt >= 0 && tt < T && n < Nb) v = __ldg(reinterpret_cast<const float4*>(xb + (static_cast<size_t>(tt) * N + n) * C) + c4);
+    reinterpret_cast<float4*>(xs)[i] = v;
+  }
+  __syncthreads();
+
+  // ---- phase 1: conv outputs.  warp w owns outputs o = w, w+8, ...; lanes sweep channels.
+  {
+    float acc[kDinMaxOutPerWarp][kDinMaxN];
+#pragma unroll
+    for (int a = 0; a < kDinMaxOutPerWarp; ++a)
+#pragma unroll
+      for (int n = 0; n < kDinMaxN; ++n) acc[a][n] = 0.0f;
+    for (int ky = 0; ky < kt; ++ky) {
+      for (int kx = 0; kx < kn; ++kx) {
+        const int tap = ky * kn + kx;
+        const int dx = dx0 + kx * ratio;
+        const float* wt = w_tap + static_cast<size_t>(tap) * n_out * C;
+        const float* xrow = xs + static_cast<size_t>(ky) * N * C;
+        for (int c4 = lane; c4 < C4; c4 += 32) {
+          float4 wv[kDinMaxOutPerWarp];
+#pragma unroll
+          for (int a = 0; a < kDinMaxOutPerWarp; ++a) {
+            const int o = warp + a * kDinWarps;
+            wv[a] = (o < n_out) ? __ldg(reinterpret_cast<const float4*>(wt + static_cast<size_t>(o) * C) + c4)
+                                : make_float4(0, 0, 0, 0);
+          }
+#pragma unroll
+          for (int n = 0; n < kDinMaxN; ++n) {
+            const int nn = n + dx;
+            if (n < Nb && nn >= 0 && nn < Nb) {
+              const float4 xv = reinterpret_cast<const float4*>(xrow + static_cast<size_t>(nn) * C)[c4];
+#pragma unroll
+              for (int a = 0; a < kDinMaxOutPerWarp; ++a) {
+                acc[a][n] = fmaf(wv[a].x, xv.x, acc[a][n]);
+                acc[a][n] = fmaf(wv[a].y, xv.y, acc[a][n]);
+                acc[a][n] = fmaf(wv[a].z, xv.z, acc[a][n]);
+                acc[a][n] = fmaf(wv[a].w, xv.w, acc[a][n]);
+              }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < kDinMaxOutPerWarp; ++a) {
+      const int o = warp + a * kDinWarps;
+#pragma unroll
+      for (int n = 0; n < kDinMaxN; ++n) {
+        const float v = warp_sum(acc[a][n]);
+        if (lane == 0 && o < n_out && n < Nb) conv_s[n * n_out + o] = v + __ldg(b_cat + o);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: one warp per actor
+  const float coef = coef_ptr ? __ldg(coef_ptr) : coef_scalar;
+  const int Hp = T + 2 * pt, Wp = N + 2 * pl;   // padded extents; with n_valid the clip is [T, Nb]
+  const int Wp_b = Nb + 2 * pl;
+  for (int n = warp; n < Nb; n += kDinWarps) {
+    const float* cs = conv_s + n * n_out;
+    // relation weights: softmax over taps (uniform across the warp)
+    float rel[kDinMaxK2];
+    if (scale_factor) {
+      float mx = -FLT_MAX;
+      for (int k = 0; k < k2; ++k) mx = fmaxf(mx, cs[2 * k2 + k]);
+      float den = 0.0f;
+      for (int k = 0; k < k2; ++k) { rel[k] = expf(cs[2 * k2 + k] - mx); den += rel[k]; }
+      for (int k = 0; k < k2; ++k) rel[k] = rel[k] / den;
+    } else {
+      for (int k = 0; k < k2; ++k) rel[k] = 1.0f / static_cast<float>(k2);
+    }
+    (void)Wp;
+    float* yp = y + ((static_cast<size_t>(b) * T + t) * N + n) * C;
+    for (int c4 = lane; c4 < C4; c4 += 32) {
+      float4 o = make_float4(0, 0, 0, 0);
+      for (int ky = 0; ky < kt; ++ky) {
+        for (int kx = 0; kx < kn; ++kx) {
+          const int k = ky * kn + kx;
+          float py = static_cast<float>(pt + t + dy0 + ky * ratio) + cs[k];
+          float px = static_cast<float>(pl + n + dx0 + kx * ratio) + cs[k2 + k];
+          float ly = floorf(py), lx = floorf(px);
+          float ry = ly + 1.0f, rx = lx + 1.0f;
+          const float my = static_cast<float>(Hp - 1), mxx = static_cast<float>(Wp_b - 1);
+          ly = fminf(fmaxf(ly, 0.0f), my); ry = fminf(fmaxf(ry, 0.0f), my); py = fminf(fmaxf(py, 0.0f), my);
+          lx = fminf(fmaxf(lx, 0.0f), mxx); rx = fminf(fmaxf(rx, 0.0f), mxx); px = fminf(fmaxf(px, 0.0f), mxx);
+          const float wly = 1.0f - fabsf(py - ly), wry = 1.0f - fabsf(py - ry);
+          const float wlx = 1.0f - fabsf(px - lx), wrx = 1.0f - fabsf(px - rx);
+          const int ily = static_cast<int>(ly) - pt, iry = static_cast<int>(ry) - pt;
+          const int ilx = static_cast<int>(lx) - pl, irx = static_cast<int>(rx) - pl;
+          auto fetch = [&](int ty, int tx) -> float4 {
+            if (ty < 0 || ty >= T || tx < 0 || tx >= Nb) return make_float4(0, 0, 0, 0);
+            return __ldg(reinterpret_cast<const float4*>(xb + (static_cast<size_t>(ty) * N + tx) * C) + c4);
+          };
+          const float4 lt = fetch(ily, ilx), rb = fetch(iry, irx), lb = fetch(iry, ilx), rt = fetch(ily, irx);
+          const float wlt = wly * wlx, wrb = wry * wrx, wlb = wry * wlx, wrt = wly * wrx;
+          // reference order: lt + rb + lb + rt, then * relation, summed over taps (:255-258, :278)
+          const float fx = ((lt.x * wlt + rb.x * wrb) + lb.x * wlb) + rt.x * wrt;
+          const float fy = ((lt.y * wlt + rb.y * wrb) + lb.y * wlb) + rt.y * wrt;
+          const float fz = ((lt.z * wlt + rb.z * wrb) + lb.z * wlb) + rt.z * wrt;
+          const float fw = ((lt.w * wlt + rb.w * wrb) + lb.w * wlb) + rt.w * wrt;
+          o.x += fx * rel[k]; o.y += fy * rel[k]; o.z += fz * rel[k]; o.w += fw * rel[k];
+        }
+      }
+      float4* dst = reinterpret_cast<float4*>(yp) + c4;
+      if (accumulate) {
+        const float4 prev = *dst;
+        o.x = prev.x + coef * o.x; o.y = prev.y + coef * o.y; o.z = prev.z + coef * o.z; o.w = prev.w + coef * o.w;
+      } else {
+        o.x *= coef; o.y *= coef; o.z *= coef; o.w *= coef;
+      }
+      *dst = o;
+    }
+  }
+}
+
+// ================================================================================================
+// read-out: max over actors -> fc_activities -> mean over frames     (one CTA per clip)
+// ================================================================================================
+constexpr int kRoThreads = 256;
+
+__global__ void __launch_bounds__(kRoThreads)
+readout_kernel(const float* __restrict__ s, const float* __restrict__ w, const float* __restrict__ bias,
+               float* __restrict__ logits, int T, int N, int C, int A, const int* __restrict__ n_valid) {
+  extern __shared__ float pooled[];  // [C]
+  __shared__ float score[64];        // A <= 64 running sum over frames
+  const int b = blockIdx.x;
+  const int Nb = n_valid ? min(__ldg(n_valid + b), N) : N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < 64) score[threadIdx.x] = 0.0f;
+  for (int t = 0; t < T; ++t) {
+    __syncthreads();
+    const float* st = s + (static_cast<size_t>(b) * T + t) * N * C;
+    for (int c = threadIdx.x; c < C; c += kRoThreads) {
+      float m = -FLT_MAX;
+      for (int n = 0; n < Nb; ++n) m = fmaxf(m, __ldg(st + static_cast<size_t>(n) * C + c));
+      pooled[c] = m;
+    }
+    __syncthreads();
+    for (int a = warp; a < A; a += kRoThreads / 32) {
+      float d = 0.0f;
+      for (int c = lane; c < C; c += 32) d = fmaf(pooled[c], __ldg(w + static_cast<size_t>(a) * C + c), d);
+      d = warp_sum(d);
+      if (lane == 0) score[a] += d + __ldg(bias + a);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < A) logits[static_cast<size_t>(b) * A + threadIdx.x] = score[threadIdx.x] / static_cast<float>(T);
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" int din_roi_align_nhwc_f16(const void* fm, const float* boxes, const int32_t* box_ind, void* out,
+                                      int n_img, int h, int w, int d, int fm_c_stride, int m, int crop_h,
+                                      int crop_w, void* stream) {
+  DIN_CHECK_ARG(fm && boxes && box_ind && out, "din_roi_align_nhwc_f16: null pointer");
+  DIN_CHECK_ARG(n_img > 0 && h > 1 && w > 1 && m > 0, "din_roi_align_nhwc_f16: bad extent n=%d h=%d w=%d m=%d",
+                n_img, h, w, m);
+  DIN_CHECK_ARG(d > 0 && d % 8 == 0 && fm_c_stride >= d && fm_c_stride % 8 == 0,
+                "din_roi_align_nhwc_f16: d=%d / fm_c_stride=%d must be multiples of 8", d, fm_c_stride);
+  DIN_CHECK_ARG(crop_h > 1 && crop_w > 1, "din_roi_align_nhwc_f16: crop must be > 1");
+  DIN_CHECK_ARG((reinterpret_cast<uintptr_t>(fm) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                "din_roi_align_nhwc_f16: pointers must be 16-byte aligned");
+  const long long warps = static_cast<long long>(m) * crop_h * crop_w;
+  const int grid = static_cast<int>((warps + 7) / 8);
+  roi_align_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(fm), boxes, box_ind, static_cast<__half*>(out), n_img, h, w, d, fm_c_stride, m,
+      crop_h, crop_w);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
+extern "C" int din_group_layernorm_f32(const float* x, const float* pre, const float* post, const float* gamma,
+                                       const float* beta, float* y, int n_outer, int n_inner,
+                                       long long outer_stride, long long inner_stride, int rows,
+                                       long long row_stride, int cols, float eps, int relu,
+                                       const int32_t* n_valid, void* stream) {
+  DIN_CHECK_ARG(x && gamma && beta && y, "din_group_layernorm_f32: null pointer");
+  DIN_CHECK_ARG(n_outer > 0 && n_inner > 0 && rows > 0 && cols > 0 && cols % 4 == 0,
+                "din_group_layernorm_f32: bad shape outer=%d inner=%d rows=%d cols=%d (cols %% 4 == 0)", n_outer,
+                n_inner, rows, cols);
+  DIN_CHECK_ARG(outer_stride % 4 == 0 && inner_stride % 4 == 0 && row_stride % 4 == 0,
+                "din_group_layernorm_f32: strides must be multiples of 4 elements");
+  DIN_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
+                  reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(post) |
+                  reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0,
+                "din_group_layernorm_f32: pointers must be 16-byte aligned");
+  group_layernorm_kernel<<<n_outer * n_inner, kLnThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, pre, post, gamma, beta, y, n_inner, outer_stride, inner_stride, rows, row_stride, cols, eps, relu, n_valid);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
+extern "C" int din_linear_f32(const float* x, const float* w, const float* bias, float* y, int m, int n, int k,
+                              int relu, int accumulate, void* stream) {
+  DIN_CHECK_ARG(x && w && y, "din_linear_f32: null pointer");
+  DIN_CHECK_ARG(m > 0 && n > 0 && k > 0 && k % 16 == 0, "din_linear_f32: bad shape m=%d n=%d k=%d (k %% 16 == 0)", m,
+                n, k);
+  DIN_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15) == 0,
+                "din_linear_f32: x and w must be 16-byte aligned");
+  dim3 grid((n + kLinBN - 1) / kLinBN, (m + kLinBM - 1) / kLinBM);
+  linear_f32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, w, bias, y, m, n, k, relu, accumulate);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
+extern "C" int din_dynamic_infer_f32(const float* x, const float* w_tap, const float* b_cat, float* y, int b, int t,
+                                     int n, int c, int kt, int kn, int ratio, int scale_factor,
+                                     const float* coef_ptr, float coef_scalar, int accumulate,
+                                     const int32_t* n_valid, void* stream) {
+  DIN_CHECK_ARG(x && w_tap && b_cat && y, "din_dynamic_infer_f32: null pointer");
+  DIN_CHECK_ARG(b > 0 && t > 0 && n > 0 && n <= kDinMaxN, "din_dynamic_infer_f32: bad extent b=%d t=%d n=%d (n <= %d)",
+                b, t, n, kDinMaxN);
+  DIN_CHECK_ARG(c > 0 && c % 4 == 0, "din_dynamic_infer_f32: c=%d must be a multiple of 4", c);
+  DIN_CHECK_ARG(kt >= 1 && kn >= 1 && kt * kn <= kDinMaxK2 && (kt & 1) && (kn & 1),
+                "din_dynamic_infer_f32: kernel %dx%d unsupported (odd, <= %d taps)", kt, kn, kDinMaxK2);
+  DIN_CHECK_ARG(ratio >= 1, "din_dynamic_infer_f32: ratio=%d", ratio);
+  const int n_out = (scale_factor ? 3 : 2) * kt * kn;
+  DIN_CHECK_ARG(n_out <= kDinMaxOutPerWarp * kDinWarps, "din_dynamic_infer_f32: too many conv outputs");
+  DIN_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
+                  reinterpret_cast<uintptr_t>(w_tap)) & 15) == 0,
+                "din_dynamic_infer_f32: pointers must be 16-byte aligned");
+  const size_t smem = (static_cast<size_t>(kt) * n * c + static_cast<size_t>(n) * n_out) * sizeof(float);
+  DIN_CHECK_ARG(smem <= 220 * 1024, "din_dynamic_infer_f32: kt*n*c too large for shared memory (%zu bytes)", smem);
+  DIN_CHECK_CUDA(cudaFuncSetAttribute(dynamic_infer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+  dynamic_infer_kernel<<<b * t, kDinThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      x, w_tap, b_cat, y, t, n, c, kt, kn, ratio, scale_factor, coef_ptr, coef_scalar, accumulate, n_valid);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
+extern "C" int din_readout_f32(const float* s, const float* w, const float* bias, float* logits, int b, int t,
+                               int n, int c, int a, const int32_t* n_valid, void* stream) {
+  DIN_CHECK_ARG(s && w && bias && logits, "din_readout_f32: null pointer");
+  DIN_CHECK_ARG(b > 0 && t > 0 && n > 0 && c > 0 && a > 0 && a <= 64,
+                "din_readout_f32: bad shape b=%d t=%d n=%d c=%d a=%d (a <= 64)", b, t, n, c, a);
+  const size_t smem = static_cast<size_t>(c) * sizeof(float);
+  DIN_CHECK_ARG(smem <= 48 * 1024, "din_readout_f32: c=%d too large", c);
+  readout_kernel<<<b, kRoThreads, smem, static_cast<cudaStream_t>(stream)>>>(s, w, bias, logits, t, n, c, a, n_valid);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}

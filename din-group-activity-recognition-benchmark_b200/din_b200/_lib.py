@@ -19,7 +19,7 @@ class DinConvDesc(C.Structure):
         "pad_h", "pad_w", "relu", "out_f32")]
 
 
-_vp, _i, _fp = C.c_void_p, C.c_int, C.c_void_p  # float* is passed as a raw address too
+_vp, _i, _fp, _ll = C.c_void_p, C.c_int, C.c_void_p, C.c_longlong  # float* is passed as a raw address
 
 # name -> (restype, argtypes).  tests/test_abi.py checks this table against include/din_sm100.h.
 PROTOTYPES = {
@@ -30,6 +30,13 @@ PROTOTYPES = {
     "din_conv2d_nhwc_f16": (C.c_int, [C.POINTER(DinConvDesc), _vp, _vp, _fp, _vp, _vp, _vp]),
     "din_pack_conv_weight_f16": (C.c_int, [_fp, _fp, _vp, _i, _i, _i, _i, _i, _vp]),
     "din_maxpool2d_nhwc_f16": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "din_roi_align_nhwc_f16": (C.c_int, [_vp, _fp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "din_group_layernorm_f32": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _ll, _ll, _i, _ll, _i,
+                                          C.c_float, _i, _vp, _vp]),
+    "din_linear_f32": (C.c_int, [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _vp]),
+    "din_dynamic_infer_f32": (C.c_int, [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _fp, C.c_float,
+                                        _i, _vp, _vp]),
+    "din_readout_f32": (C.c_int, [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 
 _lock = threading.Lock()

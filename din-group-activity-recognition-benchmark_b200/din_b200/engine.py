@@ -1,0 +1,279 @@
+"""engine.py — the DIN stage-2 forward plan on one B200.
+
+Host-side orchestration only: it packs the model's weights into the layouts the kernels want (once per
+weight version), owns the activation workspaces, and issues the kernel sequence through the C ABI
+(`ops.py`).  No arithmetic happens in Python/torch here.
+
+Data layout in HBM
+  images        fp32 NCHW [B*T, 3, H, W]        raw 0..255, as the reference's loader produces them
+  activations   fp16 NHWC, two ping-pong slabs sized for the largest layer of one frame chunk
+  feature map   fp16 NHWC [B*T, OH, OW, D]      all frames (0.9 MB / frame for VGG-16)
+  crops         fp16 [B*T*N, 25, D]             RoIAlign output == A operand of the embedding GEMM
+  person feats  fp32 [B, T, N, C]               everything after the embedding GEMM
+
+Reference path restated (infer_model.py:141-234 / 1226-1319): prep -> backbone -> RoIAlign -> fc_emb_1 ->
+nl_emb_1 -> ReLU -> (point_conv -> point_ln -> ReLU) -> DPI -> fuse + dpi_nl -> max_N -> fc_activities
+-> mean_T.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+def _fold_bn(conv_w, bn):
+    """conv weight + BatchNorm (eval: running statistics) -> (weight, per-channel scale, bias)."""
+    scale = bn["weight"] / torch.sqrt(bn["running_var"] + bn["eps"])
+    bias = bn["bias"] - bn["running_mean"] * scale
+    return conv_w, scale.contiguous(), bias.contiguous()
+
+
+class _Conv:
+    """One tcgen05 convolution of the plan (weights packed fp16 [co][kh][kw][ci], fp32 bias)."""
+
+    def __init__(self, w, bias, scale=None, stride=1, pad=(0, 0), relu=True):
+        self.w = ops.pack_conv_weight(w.contiguous(), scale)
+        self.bias = None if bias is None else bias.contiguous().float()
+        self.stride, self.pad, self.relu = stride, pad, relu
+        self.c_out, self.kh, self.kw, self.c_in = self.w.shape
+
+    def __call__(self, x, out=None, residual=None, **kw):
+        return ops.conv2d_nhwc(x, self.w, self.bias, stride=self.stride, pad=self.pad, relu=self.relu,
+                               residual=residual, out=out, **kw)
+
+
+class _Stem:
+    def __init__(self, w, bias, scale=None, stride=1, pad=0):
+        if scale is not None:
+            w = w * scale.view(-1, 1, 1, 1)       # one-time weight prep (BN folding), not on the hot path
+        self.w, self.bias, self.stride, self.pad = w.contiguous().float(), bias.contiguous().float(), stride, pad
+
+    def __call__(self, images):
+        return ops.stem_conv(images, self.w, self.bias, stride=self.stride, pad=self.pad, relu=True, prep=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# backbones: each returns the NHWC fp16 feature map [frames, OH, OW, D] for a chunk of frames
+# ------------------------------------------------------------------------------------------------
+class VGG16Plan:
+    """torchvision vgg16().features (backbone.py:88-99): 13 x (3x3 conv + ReLU), 5 x maxpool 2x2."""
+    CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512, "M"]
+
+    def __init__(self, sd, prefix="backbone.features."):
+        self.layers = []
+        idx = 0
+        first = True
+        for v in self.CFG:
+            if v == "M":
+                self.layers.append("M")
+                idx += 1
+                continue
+            w, b = sd[f"{prefix}{idx}.weight"], sd[f"{prefix}{idx}.bias"]
+            if first:
+                self.layers.append(_Stem(w, b, stride=1, pad=1))
+                first = False
+            else:
+                self.layers.append(_Conv(w, b, stride=1, pad=(1, 1), relu=True))
+            idx += 2
+        self.out_channels = 512
+
+    def __call__(self, images):
+        x = images
+        for layer in self.layers:
+            x = ops.maxpool2d_nhwc(x, 2, 2, 0) if layer == "M" else layer(x)
+        return x
+
+
+class Res18Plan:
+    """torchvision resnet18 up to layer4 (backbone.py:115-132), eval-mode BN folded into the convs."""
+
+    def __init__(self, sd, prefix="backbone.features."):
+        def bn(p):
+            return {k: sd[f"{p}.{k}"] for k in ("weight", "bias", "running_mean", "running_var")} | {"eps": 1e-5}
+
+        w, s, b = _fold_bn(sd[prefix + "0.weight"], bn(prefix + "1"))
+        self.stem = _Stem(w, b, scale=s, stride=2, pad=3)
+        self.blocks = []
+        chans = [64, 128, 256, 512]
+        for li, c in enumerate(chans):
+            for bi in range(2):
+                p = f"{prefix}{4 + li}.{bi}."
+                stride = 2 if (li > 0 and bi == 0) else 1
+                w1, s1, b1 = _fold_bn(sd[p + "conv1.weight"], bn(p + "bn1"))
+                w2, s2, b2 = _fold_bn(sd[p + "conv2.weight"], bn(p + "bn2"))
+                conv1 = _Conv(w1, b1, s1, stride=stride, pad=(1, 1), relu=True)
+                conv2 = _Conv(w2, b2, s2, stride=1, pad=(1, 1), relu=True)   # ReLU after the residual add
+                down = None
+                if (p + "downsample.0.weight") in sd:
+                    wd, sdn, bd = _fold_bn(sd[p + "downsample.0.weight"], bn(p + "downsample.1"))
+                    down = _Conv(wd, bd, sdn, stride=stride, pad=(0, 0), relu=False)
+                self.blocks.append((conv1, conv2, down))
+        self.out_channels = 512
+
+    def __call__(self, images):
+        x = self.stem(images)
+        x = ops.maxpool2d_nhwc(x, 3, 2, 1)
+        for conv1, conv2, down in self.blocks:
+            identity = x if down is None else down(x)
+            y = conv1(x)
+            x = conv2(y, residual=identity)
+        return x
+
+
+def build_backbone_plan(name, sd):
+    if name == "vgg16":
+        return VGG16Plan(sd)
+    if name == "res18":
+        return Res18Plan(sd)
+    if name == "inv3":
+        from .inception import Inv3Plan
+        return Inv3Plan(sd)
+    raise ValueError(f"backbone {name!r} is outside the hot-path scope (vgg16 / res18 / inv3)")
+
+
+# ------------------------------------------------------------------------------------------------
+# Dynamic inference module weights
+# ------------------------------------------------------------------------------------------------
+class DPIWeights:
+    """One Dynamic_Person_Inference (dynamic_infer_module.py:14-151) in kernel layout."""
+
+    def __init__(self, sd, prefix, kernel, ratios, scale_factor, beta_factor):
+        self.kernel, self.ratios = tuple(kernel), list(ratios)
+        self.scale_factor, self.beta_factor = bool(scale_factor), bool(beta_factor)
+        self.taps = {}
+        for r in self.ratios:
+            self.taps[r] = ops.pack_din_weights(
+                sd[f"{prefix}p_conv.{r}.weight"], sd[f"{prefix}p_conv.{r}.bias"],
+                sd[f"{prefix}scale_conv.{r}.weight"] if scale_factor else None,
+                sd[f"{prefix}scale_conv.{r}.bias"] if scale_factor else None)
+        self.hidden = sd[f"{prefix}hidden_weight.weight"].contiguous().float()
+        self.beta = sd[f"{prefix}beta"].contiguous().float() if beta_factor else None
+
+    def __call__(self, x, out=None, accumulate=False, n_valid=None, tmp=None):
+        """x [B,T,N,C] -> hidden_weight( mean_r / sum_r beta_r * DIN_r(x) );  out (+)= result."""
+        if tmp is None:
+            tmp = torch.zeros_like(x) if n_valid is not None else torch.empty_like(x)
+        for i, r in enumerate(self.ratios):
+            w_tap, b_cat = self.taps[r]
+            if self.beta_factor:
+                ops.dynamic_infer(x, w_tap, b_cat, self.kernel, r, scale_factor=self.scale_factor, out=tmp,
+                                  coef_ptr=self.beta.data_ptr() + 4 * i, accumulate=i > 0, n_valid=n_valid)
+            else:
+                ops.dynamic_infer(x, w_tap, b_cat, self.kernel, r, scale_factor=self.scale_factor, out=tmp,
+                                  coef=1.0 / len(self.ratios), accumulate=i > 0, n_valid=n_valid)
+        return ops.linear_f32(tmp, self.hidden, None, out=out, accumulate=accumulate)
+
+
+# ------------------------------------------------------------------------------------------------
+# the whole path
+# ------------------------------------------------------------------------------------------------
+class DinEngine:
+    """Forward plan for Dynamic_volleyball / Dynamic_collective built from a reference-named state_dict."""
+
+    def __init__(self, cfg, state_dict, device, dataset="volleyball", frames_per_chunk=16):
+        self.cfg, self.dataset, self.device = cfg, dataset, torch.device(device)
+        self.frames_per_chunk = frames_per_chunk
+        sd = {k: v.detach().to(self.device, torch.float32) if v.is_floating_point() else v.detach().to(self.device)
+              for k, v in state_dict.items()}
+        self.T, self.N = cfg.num_frames, cfg.num_boxes
+        self.D, self.K = cfg.emb_features, cfg.crop_size[0]
+        self.NFB = cfg.num_features_boxes
+        self.C = cfg.lite_dim if cfg.lite_dim else self.NFB
+        self.backbone_name = cfg.backbone
+        self.backbone = build_backbone_plan(cfg.backbone, sd)
+
+        # fc_emb_1: the reference flattens crops as (d, ky, kx) (infer_model.py:181); RoIAlign here emits
+        # (ky, kx, d), so permute the weight's columns once.  Public parameter stays [NFB, K*K*D].
+        w = sd["fc_emb_1.weight"].view(self.NFB, self.D, self.K * self.K).permute(0, 2, 1).contiguous()
+        self.fc_emb = _Conv(w.view(self.NFB, self.K * self.K * self.D, 1, 1), sd["fc_emb_1.bias"], relu=False)
+        self.nl_emb = (sd["nl_emb_1.weight"].contiguous(), sd["nl_emb_1.bias"].contiguous())
+        if cfg.lite_dim:
+            pw = sd["point_conv.weight"]
+            self.point_w = pw.reshape(pw.shape[0], pw.shape[1]).contiguous()
+            self.point_b = sd["point_conv.bias"].contiguous()
+            self.point_ln = (sd["point_ln.weight"].contiguous(), sd["point_ln.bias"].contiguous())
+        self.hier = bool(getattr(cfg, "hierarchical_inference", False)) and dataset == "volleyball"
+        sf, bf, ratios = cfg.scale_factor, cfg.beta_factor, cfg.sampling_ratio
+        if dataset == "collective":
+            self.dpis = [DPIWeights(sd, "DPI.", tuple(cfg.ST_kernel_size), ratios, sf, bf)]
+        elif self.hier:
+            k1, k2 = cfg.ST_kernel_size
+            self.dpis = [DPIWeights(sd, "DPI.DPI_1.", k1, ratios, sf, bf),
+                         DPIWeights(sd, "DPI.DPI_2.", k2, ratios, sf, bf)]
+            self.hier_ln = (sd["DPI.hier_LN.weight"].contiguous(), sd["DPI.hier_LN.bias"].contiguous())
+        else:
+            self.dpis = [DPIWeights(sd, f"DPI.DIMlist.{i}.", cfg.ST_kernel_size[i], ratios, sf, bf)
+                         for i in range(cfg.num_DIM)]
+        self.dpi_nl = (sd["dpi_nl.weight"].contiguous(), sd["dpi_nl.bias"].contiguous())
+        self.fc_act = (sd["fc_activities.weight"].contiguous(), sd["fc_activities.bias"].contiguous())
+        self._idx_cache = {}
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _box_idx(self, n_frames, n_boxes):
+        key = (n_frames, n_boxes)
+        if key not in self._idx_cache:                # infer_model.py:155-157, built once per shape
+            self._idx_cache[key] = torch.arange(n_frames, dtype=torch.int32, device=self.device) \
+                .repeat_interleave(n_boxes).contiguous()
+        return self._idx_cache[key]
+
+    def features(self, images_flat):
+        """[F,3,H,W] fp32 raw -> NHWC fp16 [F,OH,OW,D] (prep_images + backbone), chunked over frames."""
+        F_ = images_flat.shape[0]
+        outs = []
+        for f0 in range(0, F_, self.frames_per_chunk):
+            outs.append(self.backbone(images_flat[f0:f0 + self.frames_per_chunk]))
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+
+    def embed(self, fm, boxes_flat, B, T, N):
+        """RoIAlign -> fc_emb_1 -> nl_emb_1 -> ReLU -> (lite branch).  Returns fp32 [B,T,N,C]."""
+        M = B * T * N
+        crops = ops.roi_align_nhwc(fm, boxes_flat, self._box_idx(B * T, N), self.K, self.K, d=self.D)
+        emb = self.fc_emb(crops.view(1, 1, M, self.K * self.K * self.D), out_f32=True).view(M, self.NFB)
+        x = ops.group_layernorm(emb, *self.nl_emb, n_outer=M, outer_stride=self.NFB, cols=self.NFB, relu=True)
+        if self.cfg.lite_dim:
+            y = ops.linear_f32(x, self.point_w, self.point_b)
+            g = T * N * self.C
+            x = ops.group_layernorm(y, *self.point_ln, n_outer=B, outer_stride=g, cols=g, relu=True)
+        return x.view(B, T, N, self.C)
+
+    # -- forwards --------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_volleyball(self, images, boxes):
+        B, T = images.shape[:2]
+        N = self.N
+        H, W = images.shape[-2:]
+        fm = self.features(images.reshape(B * T, 3, H, W))
+        OH, OW = self.cfg.out_size
+        assert fm.shape[1:3] == (OH, OW), (tuple(fm.shape), self.cfg.out_size)          # infer_model.py:165
+        x = self.embed(fm, boxes.reshape(B * T * N, 4).contiguous().float(), B, T, N)
+        g_sz = T * N * self.C
+        if self.hier:
+            y1 = self.dpis[0](x)
+            y1 = ops.group_layernorm(y1, *self.hier_ln, n_outer=B, outer_stride=g_sz, cols=g_sz, relu=True)
+            g = self.dpis[1](y1)
+        else:
+            g = None
+            for i, dpi in enumerate(self.dpis):
+                g = dpi(x, out=g, accumulate=i > 0)
+        if self.backbone_name == "res18":                                               # :203-209
+            s = ops.group_layernorm(g, *self.dpi_nl, n_outer=B, outer_stride=g_sz, cols=g_sz, relu=True, post=x)
+        else:                                                                           # :210-216
+            s = ops.group_layernorm(g, *self.dpi_nl, n_outer=B, outer_stride=g_sz, cols=g_sz, relu=True, pre=x)
+        return ops.readout(s, *self.fc_act)
+
+    @torch.no_grad()
+    def forward_collective(self, images, boxes, bboxes_num):
+        B, T = images.shape[:2]
+        N = self.N                                                                      # MAX_N
+        H, W = images.shape[-2:]
+        fm = self.features(images.reshape(B * T, 3, H, W))
+        x = self.embed(fm, boxes.reshape(B * T * N, 4).contiguous().float(), B, T, N)
+        n_valid = bboxes_num.reshape(B, T)[:, 0].to(torch.int32).contiguous()           # :1289
+        g = self.dpis[0](x, n_valid=n_valid)
+        # (g + x) -> [N, T, C] -> LayerNorm([T, C]) -> ReLU  (:1298-1301): one group per (clip, actor)
+        s = torch.zeros_like(g)
+        ops.group_layernorm(g, *self.dpi_nl, n_outer=B, n_inner=N, outer_stride=T * N * self.C,
+                            inner_stride=self.C, rows=T, row_stride=N * self.C, cols=self.C, relu=True, pre=x,
+                            n_valid=n_valid, out=s)
+        return ops.readout(s, *self.fc_act, n_valid=n_valid)

@@ -102,3 +102,92 @@ def maxpool2d_nhwc(x, k, stride, pad=0):
     check(_lib.load().din_maxpool2d_nhwc_f16(_p(x), _p(y), n, h, w, c, k, stride, pad, _stream()),
           "din_maxpool2d_nhwc_f16")
     return y
+
+
+# ---------------------------------------------------------------------------------------------
+# person-level head
+# ---------------------------------------------------------------------------------------------
+def roi_align_nhwc(fm, boxes, box_ind, crop_h, crop_w, d=None, out=None):
+    """fm [n_img,h,w,Cs] fp16 NHWC; boxes [m,4] fp32; box_ind [m] int32 -> [m, crop_h*crop_w, d] fp16."""
+    _need(fm, torch.float16, "fm")
+    _need(boxes, torch.float32, "boxes")
+    _need(box_ind, torch.int32, "box_ind")
+    n_img, h, w, cs = fm.shape
+    d = cs if d is None else d
+    m = boxes.shape[0]
+    if out is None:
+        out = torch.empty((m, crop_h * crop_w, d), dtype=torch.float16, device=fm.device)
+    check(_lib.load().din_roi_align_nhwc_f16(_p(fm), _p(boxes), _p(box_ind), _p(out), n_img, h, w, d, cs, m,
+                                             crop_h, crop_w, _stream()), "din_roi_align_nhwc_f16")
+    return out
+
+
+def group_layernorm(x, gamma, beta, *, n_outer, n_inner=1, outer_stride, inner_stride=0, rows=1, row_stride=0,
+                    cols, pre=None, post=None, relu=False, eps=1e-5, n_valid=None, out=None):
+    _need(x, torch.float32, "x")
+    _need(gamma, torch.float32, "gamma")
+    _need(beta, torch.float32, "beta")
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.load().din_group_layernorm_f32(_p(x), _p(pre), _p(post), _p(gamma), _p(beta), _p(out), n_outer,
+                                              n_inner, outer_stride, inner_stride, rows, row_stride, cols,
+                                              float(eps), int(relu), _p(n_valid), _stream()),
+          "din_group_layernorm_f32")
+    return out
+
+
+def linear_f32(x, w, bias=None, *, relu=False, out=None, accumulate=False):
+    """x [..., k] fp32, w [n, k] fp32 -> [..., n]."""
+    _need(x, torch.float32, "x")
+    _need(w, torch.float32, "w")
+    k = x.shape[-1]
+    n = w.shape[0]
+    m = x.numel() // k
+    if out is None:
+        assert not accumulate
+        out = torch.empty(x.shape[:-1] + (n,), dtype=torch.float32, device=x.device)
+    check(_lib.load().din_linear_f32(_p(x), _p(w), _p(bias), _p(out), m, n, k, int(relu), int(accumulate),
+                                     _stream()), "din_linear_f32")
+    return out
+
+
+def pack_din_weights(p_w, p_b, s_w=None, s_b=None):
+    """OIHW p_conv [2k2,C,kt,kn] (+ scale_conv [k2,C,kt,kn]) -> tap-major [kt*kn][n_out][C], bias [n_out].
+    Pure layout change (done once per weight update, not on the hot path)."""
+    ws = [p_w] + ([s_w] if s_w is not None else [])
+    bs = [p_b] + ([s_b] if s_b is not None else [])
+    w = torch.cat(ws, dim=0)                                   # [n_out, C, kt, kn]
+    n_out, c, kt, kn = w.shape
+    w_tap = w.permute(2, 3, 0, 1).reshape(kt * kn, n_out, c).contiguous().float()
+    return w_tap, torch.cat(bs, dim=0).contiguous().float()
+
+
+def dynamic_infer(x, w_tap, b_cat, kernel, ratio, *, scale_factor=True, out=None, coef=1.0, coef_ptr=None,
+                  accumulate=False, n_valid=None):
+    """x [b,t,n,c] fp32 -> y [b,t,n,c]; y = coef*DIN_ratio(x) (or += when accumulate)."""
+    _need(x, torch.float32, "x")
+    _need(w_tap, torch.float32, "w_tap")
+    _need(b_cat, torch.float32, "b_cat")
+    b, t, n, c = x.shape
+    kt, kn = kernel
+    if out is None:
+        assert not accumulate
+        # actors beyond n_valid are never written: start from zeros so they are well defined
+        out = torch.zeros_like(x) if n_valid is not None else torch.empty_like(x)
+    check(_lib.load().din_dynamic_infer_f32(_p(x), _p(w_tap), _p(b_cat), _p(out), b, t, n, c, kt, kn, ratio,
+                                            int(scale_factor), C.c_void_p(coef_ptr or 0), float(coef),
+                                            int(accumulate), _p(n_valid), _stream()), "din_dynamic_infer_f32")
+    return out
+
+
+def readout(s, w, bias, n_valid=None):
+    """s [b,t,n,c] fp32 -> logits [b,a] = mean_t fc(max_n s)."""
+    _need(s, torch.float32, "s")
+    _need(w, torch.float32, "w")
+    _need(bias, torch.float32, "bias")
+    b, t, n, c = s.shape
+    a = w.shape[0]
+    out = torch.empty((b, a), dtype=torch.float32, device=s.device)
+    check(_lib.load().din_readout_f32(_p(s), _p(w), _p(bias), _p(out), b, t, n, c, a, _p(n_valid), _stream()),
+          "din_readout_f32")
+    return out

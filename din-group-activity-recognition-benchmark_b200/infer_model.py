@@ -1,0 +1,156 @@
+"""Drop-in for the DIN models of `infer_model` (reference infer_model.py:15-234, 1135-1319).
+
+`Dynamic_volleyball(cfg)` / `Dynamic_collective(cfg)` keep the reference's constructor contract, module
+tree and state_dict key names/shapes, `loadmodel`, and `forward(batch) -> {'activities'}`,
+so `scripts/train_volleyball_stage2_dynamic.py`'s model registry resolves and stage-1 / stage-2
+checkpoints load unchanged.  forward() runs the sm_100a plan (din_b200/engine.py); torch modules below
+are parameter containers and are never called.
+
+Scope: evaluation / inference forward (no autograd through the CUDA path yet).
+"""
+import collections
+
+import torch
+import torch.nn as nn
+
+from backbone.backbone import MyInception_v3, MyRes18, MyVGG16
+from din_b200.engine import DinEngine
+from infer_module.dynamic_infer_module import (Dynamic_Person_Inference, Hierarchical_Dynamic_Inference,
+                                               Multi_Dynamic_Inference)
+from roi_align.roi_align import RoIAlign
+from utils import print_log
+
+
+def _make_backbone(cfg):
+    if cfg.backbone == "inv3":
+        return MyInception_v3(transform_input=False, pretrained=True)
+    if cfg.backbone == "vgg16":
+        return MyVGG16(pretrained=True)
+    if cfg.backbone == "res18":
+        return MyRes18(pretrained=True)
+    raise NotImplementedError(f"backbone {cfg.backbone!r} is outside the DIN hot-path scope")
+
+
+class _DinModel(nn.Module):
+    _dataset = None
+
+    def _common_init(self, cfg, person_mat_shape, ln_shape):
+        self.cfg = cfg
+        T, N = cfg.num_frames, cfg.num_boxes
+        D, K, NFB = cfg.emb_features, cfg.crop_size[0], cfg.num_features_boxes
+        self.backbone = _make_backbone(cfg)
+        if not cfg.train_backbone:
+            for p in self.backbone.parameters():
+                p.requires_grad = False
+        self.roi_align = RoIAlign(*cfg.crop_size)
+        self.fc_emb_1 = nn.Linear(K * K * D, NFB)
+        self.nl_emb_1 = nn.LayerNorm([NFB])
+        in_dim = cfg.lite_dim if cfg.lite_dim else NFB
+        print_log(cfg.log_path, ("Activate" if cfg.lite_dim else "Deactivate") + " lite model inference.")
+        kw = dict(in_dim=in_dim, person_mat_shape=person_mat_shape, stride=cfg.stride,
+                  kernel_size=cfg.ST_kernel_size, dynamic_sampling=cfg.dynamic_sampling,
+                  sampling_ratio=cfg.sampling_ratio, group=cfg.group, scale_factor=cfg.scale_factor,
+                  beta_factor=cfg.beta_factor, parallel_inference=cfg.parallel_inference, cfg=cfg)
+        if cfg.hierarchical_inference:
+            self.DPI = Hierarchical_Dynamic_Inference(**kw)
+        elif self._dataset == "volleyball":
+            self.DPI = Multi_Dynamic_Inference(num_DIM=cfg.num_DIM, **kw)
+        else:
+            self.DPI = Dynamic_Person_Inference(**kw)
+        print_log(cfg.log_path, "Hierarchical Inference : " + str(cfg.hierarchical_inference))
+        self.dpi_nl = nn.LayerNorm(ln_shape(T, N, in_dim))
+        self.dropout_global = nn.Dropout(p=cfg.train_dropout_prob)
+        if cfg.lite_dim:
+            self.point_conv = nn.Conv2d(NFB, in_dim, kernel_size=1, stride=1)
+            self.point_ln = nn.LayerNorm([T, N, in_dim])
+        self.fc_activities = nn.Linear(in_dim, cfg.num_activities)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.kaiming_normal_(m.weight)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+        self._engine, self._engine_key = None, None
+
+    # -- reference API ---------------------------------------------------------------------------
+    def loadmodel(self, filepath):
+        state = torch.load(filepath)
+        self.backbone.load_state_dict(state["backbone_state_dict"])
+        self.fc_emb_1.load_state_dict(state["fc_emb_state_dict"])
+        print("Load model states from: ", filepath)
+
+    def loadpart(self, pretrained_state_dict, model, prefix):
+        own = model.state_dict()
+        picked = collections.OrderedDict((k.replace(prefix, ""), v) for k, v in pretrained_state_dict.items()
+                                         if k.replace(prefix, "") in own)
+        own.update(picked)
+        model.load_state_dict(own)
+        print(str(len(picked)) + " parameters loaded for " + prefix)
+
+    # -- plan management -------------------------------------------------------------------------
+    def engine(self):
+        tensors = list(self.state_dict().values())
+        key = (str(tensors[0].device),) + tuple((t.data_ptr(), t._version) for t in tensors)
+        if self._engine_key != key:
+            dev = tensors[0].device
+            if dev.type != "cuda":
+                raise RuntimeError("the DIN hot path runs on sm_100a only: move the model to a CUDA device "
+                                   "(there is no CPU fallback)")
+            with torch.cuda.device(dev):
+                self._engine = DinEngine(self.cfg, self.state_dict(), dev, dataset=self._dataset)
+            self._engine_key = key
+        return self._engine
+
+    def _check_mode(self):
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError(
+                "the sm_100a DIN path is forward-only in this release: use model.eval() and/or "
+                "torch.no_grad() (backward kernels: SURVEY.md §8f)")
+
+
+class Dynamic_volleyball(_DinModel):
+    """reference infer_model.py:15-234."""
+    _dataset = "volleyball"
+
+    def __init__(self, cfg):
+        super().__init__()
+        self._common_init(cfg, (10, 12), lambda T, N, C: [T, N, C])     # person_mat_shape hard-coded :77
+
+    def forward(self, batch_data):
+        images_in, boxes_in = batch_data
+        self._check_mode()
+        with torch.cuda.device(images_in.device):
+            scores = self.engine().forward_volleyball(images_in.float(), boxes_in.float())
+        return {"activities": scores}
+
+
+class Dynamic_collective(_DinModel):
+    """reference infer_model.py:1135-1319 (variable actor count per clip, one launch instead of a loop)."""
+    _dataset = "collective"
+
+    def __init__(self, cfg):
+        super().__init__()
+        self._common_init(cfg, (cfg.num_frames, cfg.num_boxes), lambda T, N, C: [T, C])
+
+    def forward(self, batch_data):
+        images_in, boxes_in, bboxes_num_in = batch_data
+        self._check_mode()
+        with torch.cuda.device(images_in.device):
+            scores = self.engine().forward_collective(images_in.float(), boxes_in.float(), bboxes_num_in)
+        return {"activities": scores}
+
+
+def _out_of_scope(name):
+    class _Stub(nn.Module):
+        def __init__(self, *a, **k):
+            raise NotImplementedError(f"{name} is outside the DIN stage-2 hot-path scope (SURVEY.md §2 #13/#14)")
+    _Stub.__name__ = name
+    return _Stub
+
+
+# names the reference trainer's registry resolves at import time (train_net_dynamic.py:66-73)
+Dynamic_TCE_volleyball = _out_of_scope("Dynamic_TCE_volleyball")
+PCTDM_volleyball = _out_of_scope("PCTDM_volleyball")
+HiGCIN_volleyball = _out_of_scope("HiGCIN_volleyball")
+AT_volleyball = _out_of_scope("AT_volleyball")
+ARG_volleyball = _out_of_scope("ARG_volleyball")
+SACRF_BiUTE_volleyball = _out_of_scope("SACRF_BiUTE_volleyball")

@@ -108,6 +108,77 @@ DIN_API int din_pack_conv_weight_f16(const float* w_oihw, const float* scale, vo
 DIN_API int din_maxpool2d_nhwc_f16(const void* x, void* y, int n, int h, int w, int c, int k, int stride, int pad,
                            void* stream);
 
+/* ---- person-level head --------------------------------------------------------------------- */
+
+/*
+ * RoIAlign = TF crop_and_resize with longcw/RoIAlign.pytorch's box transform (transform_fpcoor=True,
+ * extrapolation_value=0): one bilinear sample per output bin, zero where the sample point leaves
+ * [0,h-1] x [0,w-1].
+ * Replaces: roi_align.roi_align.RoIAlign(crop_h, crop_w)(featuremap, boxes, box_ind), the reference's one
+ *   native extension (infer_model.py:3,48,178-181; Dockerfile:6-8).
+ * fm      : fp16 NHWC [n_img, h, w, fm_c_stride], channels [0, d) are read
+ * boxes   : fp32 [m, 4] = (x1, y1, x2, y2) in feature-map units (volleyball.py:249-251)
+ * box_ind : int32 [m] frame index of each box (boxes with an index outside [0, n_img) produce zeros)
+ * out     : fp16 [m][crop_h*crop_w][d]  -- bin-major, channel-minor: the K order of the packed fc_emb_1
+ *           weight, so `out` is the A operand of the embedding GEMM without a transpose
+ *           (the reference flattens (d, ky, kx), infer_model.py:181; the caller permutes fc_emb_1's
+ *           columns once at load time instead).
+ */
+DIN_API int din_roi_align_nhwc_f16(const void* fm, const float* boxes, const int32_t* box_ind, void* out,
+                                   int n_img, int h, int w, int d, int fm_c_stride, int m, int crop_h,
+                                   int crop_w, void* stream);
+
+/*
+ * LayerNorm over strided groups with optional pre-add, ReLU, post-add:
+ *     y = [relu]( LN(x (+ pre)) * gamma + beta ) (+ post)           (fp32, biased variance, eps inside sqrt)
+ * group g in [0, n_outer*n_inner): base = (g / n_inner)*outer_stride + (g % n_inner)*inner_stride;
+ * element (r, c), r < rows, c < cols, lives at base + r*row_stride + c; gamma/beta at r*cols + c.
+ * n_valid (int32 [n_outer], may be NULL): groups with (g % n_inner) >= n_valid[g / n_inner] are skipped.
+ * Replaces: nl_emb_1 (+ReLU) infer_model.py:185-186; point_ln (+ReLU) :191-192; dpi_nl fusion :203-216;
+ *   hier_LN dynamic_infer_module.py:493-494; Collective LayerNorm([T, C]) infer_model.py:1298-1301.
+ */
+DIN_API int din_group_layernorm_f32(const float* x, const float* pre, const float* post, const float* gamma,
+                                    const float* beta, float* y, int n_outer, int n_inner,
+                                    long long outer_stride, long long inner_stride, int rows,
+                                    long long row_stride, int cols, float eps, int relu,
+                                    const int32_t* n_valid, void* stream);
+
+/*
+ * y[m, n] (+)= x[m, k] . w[n, k]^T (+ bias[n]) (ReLU), fp32 (k a multiple of 16).  accumulate != 0 adds
+ * to the existing y (the sum over parallel DIMs, dynamic_infer_module.py:441); ReLU applies to the new term.
+ * Replaces: point_conv 1x1 (infer_model.py:189-190), hidden_weight (dynamic_infer_module.py:149).
+ */
+DIN_API int din_linear_f32(const float* x, const float* w, const float* bias, float* y, int m, int n, int k,
+                           int relu, int accumulate, void* stream);
+
+/*
+ * Dynamic Relation + Dynamic Walk for one sampling ratio, fused (affinity convs -> softmax over the
+ * kt x kn neighbourhood -> dynamic-walk bilinear sampling -> relation-weighted aggregation).
+ * Replaces: Dynamic_Person_Inference.dynamic_infer_ratio and helpers
+ *   (infer_module/dynamic_infer_module.py:184-282, 344-404) plus the ratio mean / beta sum (:142-147).
+ * x      : fp32 [b, t, n, c]
+ * w_tap  : fp32 [kt*kn][n_out][c], n_out = 2*kt*kn (+ kt*kn if scale_factor): p_conv rows first (T-axis
+ *          offsets, then N-axis offsets), then scale_conv rows; tap-major repack of the OIHW weights
+ * b_cat  : fp32 [n_out]
+ * y      : fp32 [b, t, n, c];  y = coef * out   or, if accumulate, y += coef * out
+ * coef   : *coef_ptr if coef_ptr != NULL (e.g. &beta[r], device memory) else coef_scalar (1/len(ratios))
+ * n_valid: int32 [b] real actors per clip (Collective: infer_model.py:1289), NULL = n everywhere; actors
+ *          >= n_valid[b] are neither read nor written and the zero padding starts right after them.
+ * scale_factor == 0 -> plain mean over the taps (:280).  kt, kn odd, kt*kn <= 9, n <= 16.
+ */
+DIN_API int din_dynamic_infer_f32(const float* x, const float* w_tap, const float* b_cat, float* y, int b, int t,
+                                  int n, int c, int kt, int kn, int ratio, int scale_factor,
+                                  const float* coef_ptr, float coef_scalar, int accumulate,
+                                  const int32_t* n_valid, void* stream);
+
+/*
+ * Group read-out: max over actors -> fc_activities -> mean over frames.
+ * Replaces: infer_model.py:224-232 (Volleyball) and :1311-1313 (Collective, with n_valid).
+ * s [b, t, n, c] fp32, w [a, c], bias [a] -> logits [b, a].   a <= 64.
+ */
+DIN_API int din_readout_f32(const float* s, const float* w, const float* bias, float* logits, int b, int t,
+                            int n, int c, int a, const int32_t* n_valid, void* stream);
+
 #ifdef __cplusplus
 } /* extern "C" */
 #endif

@@ -1,0 +1,81 @@
+"""End-to-end logits parity: the drop-in models (CUDA path) vs the CPU oracle on identical seeded weights
+and inputs.  Tolerance (north_star): max|Δ| <= 1e-3 * max|ref| — the backbone runs fp16 operands with
+fp32 accumulation, the head fp32."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+def _run_case(cuda, pc, B, seed=0):
+    import din_oracle as O
+    import infer_model as IM
+    from config import Config
+    bb = O.build_backbone(pc.backbone)
+    sd = O.make_state_dict(pc, seed=seed, backbone=bb)
+    O.load_backbone(bb, sd)
+    batch = O.make_inputs(pc, B, seed=seed)
+    if pc.dataset == "collective":
+        ref = O.collective_forward(bb, sd, pc, *batch)
+    else:
+        ref = O.volleyball_forward(bb, sd, pc, *batch)
+    cfg = Config(pc.dataset)
+    cfg.log_path = None
+    for k in ("backbone", "image_size", "out_size", "emb_features", "num_frames", "num_boxes", "crop_size",
+              "num_features_boxes", "num_activities", "lite_dim", "ST_kernel_size", "scale_factor", "beta_factor",
+              "hierarchical_inference", "num_DIM"):
+        setattr(cfg, k, getattr(pc, k))
+    cfg.sampling_ratio = list(pc.sampling_ratio)
+    cfg.num_features_gcn = pc.num_features_boxes
+    model = (IM.Dynamic_collective if pc.dataset == "collective" else IM.Dynamic_volleyball)(cfg)
+    missing = model.load_state_dict(sd, strict=True)
+    model = model.to(cuda).eval()
+    with torch.no_grad():
+        out = model(tuple(t.to(cuda) for t in batch))["activities"]
+    torch.cuda.synchronize()
+    assert out.shape == ref.shape
+    err = (out.cpu() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print(f"\n[e2e] {pc.backbone} {pc.dataset} B={B} T={pc.num_frames}: max|Δ|={err:.3e} max|ref|={scale:.3f} "
+          f"rel={err / scale:.2e}")
+    assert err <= TOL * scale, f"max|Δ| {err:.3e} > {TOL} * max|ref| {scale:.3e}"
+    return out, ref
+
+
+def _pc(backbone, hw, **kw):
+    import din_oracle as O
+    return O.PathConfig(backbone=backbone, image_size=hw, out_size=O.backbone_out_size(backbone, *hw), **kw)
+
+
+def test_vgg16_lite_small(cuda):
+    _run_case(cuda, _pc("vgg16", (96, 160), num_frames=3, num_boxes=4), B=2)
+
+
+def test_res18_lite_small(cuda):
+    _run_case(cuda, _pc("res18", (96, 160), num_frames=3, num_boxes=4), B=2)
+
+
+def test_vgg16_full_two_ratios_beta(cuda):
+    _run_case(cuda, _pc("vgg16", (96, 160), num_frames=4, num_boxes=5, lite_dim=None, sampling_ratio=(1, 3),
+                        beta_factor=True), B=2)
+
+
+def test_vgg16_parallel_fields(cuda):
+    _run_case(cuda, _pc("vgg16", (96, 160), num_frames=4, num_boxes=5, ST_kernel_size=[(1, 3), (3, 1)], num_DIM=2), B=2)
+
+
+def test_vgg16_hierarchical(cuda):
+    _run_case(cuda, _pc("vgg16", (64, 96), num_frames=10, num_boxes=12, lite_dim=None,
+                        ST_kernel_size=[(1, 3), (3, 1)], hierarchical_inference=True), B=1)
+
+
+def test_collective_res18(cuda):
+    _run_case(cuda, _pc("res18", (96, 144), dataset="collective", num_frames=3, num_boxes=13, lite_dim=None,
+                        ST_kernel_size=(3, 3), num_activities=4), B=3)
+
+
+def test_config1_vgg16_720p(cuda):
+    """BASELINE config 1: VGG-16, lite 128, B=1, T=3, N=12 at 720x1280 (the reference's CPU-runnable case)."""
+    _run_case(cuda, _pc("vgg16", (720, 1280), num_frames=3, num_boxes=12), B=1)
