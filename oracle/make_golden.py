@@ -1,0 +1,82 @@
+"""make_golden.py — generates tests/golden/*.pt from the REFERENCE's own classes.  TEST INFRASTRUCTURE.
+
+Run in the authoring container (needs /root/reference):   python oracle/make_golden.py
+Each fixture stores the PathConfig, batch size and seed (weights and inputs are regenerated from the seed
+by din_oracle.make_state_dict / make_inputs, with float64 checksums recorded to detect RNG drift) and the
+logits the reference model (infer_model.Dynamic_volleyball / Dynamic_collective, patched per
+ref_harness.py where it crashes as shipped) produced.  Module-level fixtures store full tensors.
+"""
+import dataclasses
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import din_oracle as O  # noqa: E402
+import ref_harness as R  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def checksum(tensors):
+    return float(sum(t.double().abs().sum() for t in tensors if t.is_floating_point()))
+
+
+def model_cases():
+    def pc(backbone, hw, **kw):
+        return O.PathConfig(backbone=backbone, image_size=hw, out_size=O.backbone_out_size(backbone, *hw), **kw)
+    return {
+        "vgg16_lite": (pc("vgg16", (96, 160), num_frames=3, num_boxes=4), 2),
+        "res18_lite": (pc("res18", (96, 160), num_frames=3, num_boxes=4), 2),
+        "vgg16_full_r13_beta": (pc("vgg16", (96, 160), num_frames=4, num_boxes=5, lite_dim=None,
+                                   sampling_ratio=(1, 3), beta_factor=True), 2),
+        "vgg16_parallel_fields": (pc("vgg16", (96, 160), num_frames=4, num_boxes=5,
+                                     ST_kernel_size=[(1, 3), (3, 1)], num_DIM=2), 2),
+        "vgg16_hierarchical": (pc("vgg16", (64, 96), num_frames=10, num_boxes=12, lite_dim=None,
+                                  ST_kernel_size=[(1, 3), (3, 1)], hierarchical_inference=True), 1),
+        "inv3_full": (pc("inv3", (139, 203), emb_features=1056, num_frames=2, num_boxes=4, lite_dim=None), 2),
+        "collective_res18": (pc("res18", (96, 144), dataset="collective", num_frames=3, num_boxes=13,
+                                lite_dim=None, ST_kernel_size=(3, 3), num_activities=4), 3),
+    }
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    for name, (pc, B) in model_cases().items():
+        bb = O.build_backbone(pc.backbone)
+        sd = O.make_state_dict(pc, seed=0, backbone=bb)
+        batch = O.make_inputs(pc, B, seed=0)
+        logits = R.ref_forward(pc, sd, *batch)
+        torch.save({"config": dataclasses.asdict(pc), "B": B, "seed": 0, "logits_ref": logits,
+                    "weights_checksum": checksum(sd.values()), "inputs_checksum": checksum(batch)},
+                   os.path.join(OUT, f"model_{name}.pt"))
+        print(name, logits[0, :4].tolist())
+    # module-level: the reference Dynamic_Person_Inference with randomised p_conv / scale_conv
+    g = torch.Generator().manual_seed(42)
+    for name, (kernel, ratios, T, N, beta) in {
+        "dpi_k33_r1": ((3, 3), [1], 4, 5, False),
+        "dpi_k33_r13_beta": ((3, 3), [1, 3], 10, 12, True),
+        "dpi_k13_r1": ((1, 3), [1], 4, 5, False),
+        "dpi_k31_r2": ((3, 1), [2], 4, 5, False),
+    }.items():
+        C = 32
+        m = R.ref_dpi_module(C, kernel, ratios, scale_factor=True, beta_factor=beta)
+        with torch.no_grad():
+            for n, p in m.named_parameters():
+                if "p_conv" in n or "scale_conv" in n:
+                    p.copy_(torch.randn(p.shape, generator=g) * (0.02 if n.endswith("weight") else 1.5))
+                elif n == "beta":
+                    p.copy_(torch.rand(p.shape, generator=g) + 0.5)
+        x = torch.randn(2, T, N, C, generator=g)
+        with torch.no_grad():
+            y, mad = m(x)
+        torch.save({"kernel": kernel, "ratios": ratios, "beta": beta, "x": x, "y": y,
+                    "state_dict": {k: v.clone() for k, v in m.state_dict().items()}},
+                   os.path.join(OUT, f"module_{name}.pt"))
+        print(name, tuple(y.shape))
+
+
+if __name__ == "__main__":
+    main()

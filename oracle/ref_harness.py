@@ -52,7 +52,11 @@ def _isolated_import():
         del sys.modules[k]
     sys.modules.update(_ref_modules)
     saved_path = list(sys.path)
-    sys.path[:0] = [_SHIMS, REF_ROOT]
+    # The reference's infer_module/ and backbone/ have no __init__.py (namespace packages); a regular
+    # package of the same name anywhere on sys.path would win, so this repo's drop-in package directory
+    # is taken off the path while reference modules are being imported.
+    pkg = os.path.join(os.path.dirname(_HERE), "din-group-activity-recognition-benchmark_b200")
+    sys.path[:] = [_SHIMS, REF_ROOT] + [p for p in sys.path if os.path.abspath(p or ".") != pkg]
     import torchvision.models as tvm
     orig = {}
 
