@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py — clips/s of the DIN stage-2 forward on synthetic Volleyball-shaped input.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one forward of the hot path (prep -> VGG-16 -> RoIAlign -> embedding -> Dynamic Relation /
+Dynamic Walk -> read-out) over one batch of B clips per GPU.  Prints ONE JSON line (rank 0):
+  value      clips/s, whole job, inputs already resident in HBM (CUDA events, barrier + sync both sides,
+             max over ranks)
+  e2e        the same metric through the public API `model((images, boxes))` with HOST (pinned) inputs:
+             every step's host->device copy and the device->host read of its logits are inside the timed
+             region (copies are double-buffered on a side stream so they overlap the previous step)
+  roofline   the dominant kernel (the tcgen05 implicit-GEMM convolution): algorithmic FLOPs of its launches
+             / their CUDA-event durations, against the measured bf16 tensor peak in MEASURED_PEAKS.json
+  cpu_baseline  the CPU port of the reference path (oracle/, torch-CPU fp32, all host cores) on a bounded
+             sample of the same workload
+`--impl reference` times that CPU implementation alone, on the same config / metric.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "din-group-activity-recognition-benchmark_b200")
+for p in (PKG, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "clips_per_sec"
+UNIT = "clips/s"
+
+# workload name -> (PathConfig kwargs, clips per GPU, algorithmic GFLOP per clip [SURVEY.md §8d, BASELINE.md §2])
+WORKLOADS = {
+    # the reference's own stage-2 recipe (scripts/train_volleyball_stage2_dynamic.py): the configuration the
+    # metric "clips/sec (Volleyball T=10 N=12 720p)" is quoted on
+    "volleyball_vgg16_lite128_T10_N12_720p": (
+        dict(backbone="vgg16", image_size=(720, 1280), out_size=(22, 40), emb_features=512, num_frames=10,
+             num_boxes=12, lite_dim=128, ST_kernel_size=[(3, 3)], sampling_ratio=(1,)), 8, 5640.7),
+    "volleyball_res18_lite128_T10_N12_720p": (
+        dict(backbone="res18", image_size=(720, 1280), out_size=(23, 40), emb_features=512, num_frames=10,
+             num_boxes=12, lite_dim=128, ST_kernel_size=[(3, 3)], sampling_ratio=(1,)), 32, 672.8),
+}
+DEFAULT_WORKLOAD = "volleyball_vgg16_lite128_T10_N12_720p"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"tflops_sustained": d["bf16_tflops_sustained"], "tflops_burst": d["bf16_tflops"],
+                "hbm_gbs": d["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops_sustained": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+        return False
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        busy = [v for v in sm if v > 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_model(pc, device):
+    import torch
+    import din_oracle as O
+    import infer_model as IM
+    from config import Config
+    bb = O.build_backbone(pc.backbone)
+    sd = O.make_state_dict(pc, seed=0, backbone=bb)     # random-init weights of the reference architecture
+    cfg = Config(pc.dataset)
+    cfg.log_path = None
+    for k in ("backbone", "image_size", "out_size", "emb_features", "num_frames", "num_boxes", "crop_size",
+              "num_features_boxes", "num_activities", "lite_dim", "ST_kernel_size", "scale_factor", "beta_factor",
+              "hierarchical_inference", "num_DIM"):
+        setattr(cfg, k, getattr(pc, k))
+    cfg.sampling_ratio = list(pc.sampling_ratio)
+    import contextlib
+    import io
+    import warnings
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = (IM.Dynamic_collective if pc.dataset == "collective" else IM.Dynamic_volleyball)(cfg)
+    model.load_state_dict(sd)
+    return model.to(device).eval(), sd, bb
+
+
+def cpu_reference_clips_per_s(pc, sd, bb, budget_s, steps=1, warmup=0):
+    """Times the CPU port of the reference path (oracle/din_oracle.py) with all host threads.
+    A step is one clip (B=1); if (steps+warmup) clips would exceed `budget_s`, the clip is cut to the first
+    `t_s` frames and the result is scaled by t_s/T (the backbone is >= 97 % of the CPU time and linear in
+    frames).  Returns (clips/s, cores, sample description, seconds per step)."""
+    import torch
+    import din_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    O.load_backbone(bb, sd)
+    T = pc.num_frames
+    images, boxes = O.make_inputs(pc, 1, seed=0)
+    # probe: one frame through the backbone
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        bb(O.prep_images(images[0, :1]))
+    t_frame = time.perf_counter() - t0
+    t_s = T
+    if (steps + warmup) * T * t_frame > budget_s:
+        t_s = max(1, int(budget_s / ((steps + warmup) * t_frame)))
+        t_s = min(t_s, T)
+    import dataclasses
+    pcs = dataclasses.replace(pc, num_frames=t_s)
+    if t_s != T:
+        sds = dict(sd)
+        for k in ("dpi_nl.weight", "dpi_nl.bias", "point_ln.weight", "point_ln.bias"):
+            if k in sds:
+                sds[k] = sds[k][:t_s].contiguous()
+    else:
+        sds = sd
+    im, bx = images[:, :t_s].contiguous(), boxes[:, :t_s].contiguous()
+    for _ in range(warmup):
+        O.volleyball_forward(bb, sds, pcs, im, bx)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.volleyball_forward(bb, sds, pcs, im, bx)
+    dt = (time.perf_counter() - t0) / steps
+    clips_per_s = (t_s / T) / dt
+    sample = (f"{steps} step(s) x 1 clip x {t_s}/{T} frames at {pc.image_size[0]}x{pc.image_size[1]}, N={pc.num_boxes}; "
+              f"oracle port (torch-CPU fp32, oneDNN), {torch.get_num_threads()} threads"
+              + ("" if t_s == T else "; clips/s scaled by frames/T"))
+    return clips_per_s, torch.get_num_threads(), sample, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--clips-per-gpu", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=25.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    import torch
+    import din_oracle as O
+    kw, clips_per_gpu, gflop_per_clip = WORKLOADS[args.workload]
+    if args.clips_per_gpu:
+        clips_per_gpu = args.clips_per_gpu
+    pc = O.PathConfig(**kw)
+    config = {"workload": args.workload, "backbone": pc.backbone, "clips_per_gpu": clips_per_gpu,
+              "global_clips_per_step": clips_per_gpu * world, "frames": pc.num_frames, "actors": pc.num_boxes,
+              "image": list(pc.image_size), "parallelism": f"dp{world} (clips sharded, no forward collective)",
+              "l2": "inputs (%.0f MB/step/GPU) larger than L2, no explicit flush" %
+                    (clips_per_gpu * pc.num_frames * 3 * pc.image_size[0] * pc.image_size[1] * 4 / 1e6)}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        bb = O.build_backbone(pc.backbone)
+        sd = O.make_state_dict(pc, seed=0, backbone=bb)
+        v, cores, sample, dt = cpu_reference_clips_per_s(pc, sd, bb, budget_s=200.0, steps=max(1, args.steps),
+                                                         warmup=args.warmup)
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(config, clips_per_gpu=1, global_clips_per_step=1, parallelism="cpu"),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return
+
+    # ------------------------------------------------------------------ our arm (B200)
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the hot path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from din_b200 import ops
+
+    model, sd, bb = build_model(pc, dev)
+    B, T, N = clips_per_gpu, pc.num_frames, pc.num_boxes
+    H, W = pc.image_size
+    images_h, boxes_h = O.make_inputs(pc, 1, seed=rank)          # boxes pattern from the oracle generator
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    images_d = torch.randint(0, 256, (B, T, 3, H, W), generator=g, device=dev, dtype=torch.int32).float()
+    boxes_d = boxes_h.repeat(B, 1, 1, 1).to(dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        with torch.no_grad():
+            return model((images_d, boxes_d))["activities"]
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ops.LAUNCHES
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            out = step()
+        e1.record()
+        barrier()
+    launches = ops.LAUNCHES - launches0
+    ms = e0.elapsed_time(e1)
+    assert torch.isfinite(out).all()
+
+    # ---- end to end through the public API with host inputs
+    e2e = None
+    if not args.no_e2e:
+        img_host = torch.empty((B, T, 3, H, W), dtype=torch.float32).pin_memory()
+        img_host.copy_(images_d)
+        box_host = boxes_d.cpu().pin_memory()
+        bufs = [(torch.empty_like(images_d), torch.empty_like(boxes_d)) for _ in range(2)]
+        out_host = torch.empty((B, pc.num_activities), dtype=torch.float32).pin_memory()
+        copy_stream = torch.cuda.Stream(device=dev)
+        main_stream = torch.cuda.current_stream()
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+
+        def issue_copy(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[i % 2])          # the buffer's previous consumer has finished
+                bufs[i % 2][0].copy_(img_host, non_blocking=True)
+                bufs[i % 2][1].copy_(box_host, non_blocking=True)
+                ready[i % 2].record(copy_stream)
+
+        def run_e2e(n):
+            for f in freed:
+                f.record(main_stream)
+            issue_copy(0)
+            for i in range(n):
+                if i + 1 < n:
+                    issue_copy(i + 1)                          # overlaps with step i's kernels
+                main_stream.wait_event(ready[i % 2])
+                with torch.no_grad():
+                    o = model(bufs[i % 2])["activities"]
+                freed[i % 2].record(main_stream)
+                out_host.copy_(o, non_blocking=True)           # D2H read of the step's result
+            torch.cuda.synchronize()
+
+        run_e2e(2)
+        barrier()
+        t0 = time.perf_counter()
+        e2e0, e2e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2e0.record()
+        run_e2e(args.steps)
+        e2e1.record()
+        barrier()
+        ms_e2e = e2e0.elapsed_time(e2e1)
+        wall_e2e = (time.perf_counter() - t0) * 1e3
+        e2e = {"ms": ms_e2e, "wall_ms": wall_e2e, "h2d": img_host.numel() * 4 + box_host.numel() * 4, "d2h": out_host.numel() * 4}
+
+    # ---- roofline of the dominant kernel: one extra (untimed) step with per-launch CUDA events
+    ops.RECORDER = []
+    step()
+    torch.cuda.synchronize()
+    rec, ops.RECORDER = ops.RECORDER, None
+    conv = [(n, f, b, a.elapsed_time(z)) for (n, f, b, a, z) in rec if n.startswith("conv")]
+    all_ms = sum(a.elapsed_time(z) for (_, _, _, a, z) in rec)
+    conv_ms = sum(t for *_, t in conv)
+    conv_flops = sum(f for _, f, _, _ in conv)
+    per_layer = {}
+    for n, f, b, t in conv:
+        e = per_layer.setdefault(n, [0, 0.0, 0])
+        e[0] += f; e[1] += t; e[2] += 1
+    other = {}
+    for (n, f, b, a, z) in rec:
+        if not n.startswith("conv"):
+            k = n.split("_")[0].split("@")[0]
+            other[k] = other.get(k, 0.0) + a.elapsed_time(z)
+
+    if dist is not None:
+        t = torch.tensor([ms, e2e["ms"] if e2e else 0.0], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        if e2e:
+            e2e["ms"] = float(t[1])
+        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt[0])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = _peaks()
+    total_clips = B * world * args.steps
+    value = total_clips / (ms / 1e3)
+    achieved = conv_flops / (conv_ms / 1e3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (backbone), f32 (head)",
+        "data": "synthetic", "config": config,
+        "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, all launches of a step)",
+                     "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["tflops_sustained"], "traffic": traffic,
+                     "peak_source": peaks["source"] + ", sustained bf16 (= fp16 rate)",
+                     "flops_per_step": conv_flops, "kernel_ms_per_step": conv_ms,
+                     "kernel_share_of_step": conv_ms / all_ms,
+                     "whole_path_tflops": value * gflop_per_clip / 1e3,
+                     "whole_path_frac": value * gflop_per_clip / 1e3 / world / peaks["tflops_sustained"],
+                     "other_kernels_ms": {k: round(v, 3) for k, v in sorted(other.items())},
+                     "per_layer_tflops": {n: round(f / (t / 1e3) / 1e12, 1) for n, (f, t, c) in per_layer.items()}},
+        "clocks": clocks.summary(),
+        "gpu_launches": launches,
+    }
+    if e2e:
+        line["e2e"] = {"value": total_clips / (e2e["ms"] / 1e3), "unit": UNIT,
+                       "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"]}
+    if world == 1 and not args.no_cpu_baseline:
+        v, cores, sample, _ = cpu_reference_clips_per_s(pc, sd, bb, budget_s=args.cpu_budget_s)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

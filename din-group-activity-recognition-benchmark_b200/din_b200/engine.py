@@ -78,11 +78,18 @@ class VGG16Plan:
             idx += 2
         self.out_channels = 512
 
-    def __call__(self, images):
+    def __call__(self, images, out=None):
         x = images
-        for layer in self.layers:
-            x = ops.maxpool2d_nhwc(x, 2, 2, 0) if layer == "M" else layer(x)
+        last = len(self.layers) - 1
+        for i, layer in enumerate(self.layers):
+            if layer == "M":
+                x = ops.maxpool2d_nhwc(x, 2, 2, 0, out=out if i == last else None)
+            else:
+                x = layer(x)
         return x
+
+    def out_shape(self, h, w):
+        return h // 32, w // 32, 512
 
 
 class Res18Plan:
@@ -111,14 +118,23 @@ class Res18Plan:
                 self.blocks.append((conv1, conv2, down))
         self.out_channels = 512
 
-    def __call__(self, images):
+    def __call__(self, images, out=None):
         x = self.stem(images)
         x = ops.maxpool2d_nhwc(x, 3, 2, 1)
-        for conv1, conv2, down in self.blocks:
+        last = len(self.blocks) - 1
+        for i, (conv1, conv2, down) in enumerate(self.blocks):
             identity = x if down is None else down(x)
             y = conv1(x)
-            x = conv2(y, residual=identity)
+            x = conv2(y, residual=identity, out=out if i == last else None)
         return x
+
+    def out_shape(self, h, w):
+        def c(v, k, s, p):
+            return (v + 2 * p - k) // s + 1
+        h, w = c(h, 7, 2, 3), c(w, 7, 2, 3)
+        for _ in range(4):
+            h, w = c(h, 3, 2, 1), c(w, 3, 2, 1)
+        return h, w, 512
 
 
 def build_backbone_plan(name, sd):
@@ -219,11 +235,13 @@ class DinEngine:
 
     def features(self, images_flat):
         """[F,3,H,W] fp32 raw -> NHWC fp16 [F,OH,OW,D] (prep_images + backbone), chunked over frames."""
-        F_ = images_flat.shape[0]
-        outs = []
+        F_, _, H, W = images_flat.shape
+        oh, ow, d = self.backbone.out_shape(H, W)
+        fm = torch.empty((F_, oh, ow, d), dtype=torch.float16, device=images_flat.device)
         for f0 in range(0, F_, self.frames_per_chunk):
-            outs.append(self.backbone(images_flat[f0:f0 + self.frames_per_chunk]))
-        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+            f1 = min(F_, f0 + self.frames_per_chunk)
+            self.backbone(images_flat[f0:f1], out=fm[f0:f1])      # last layer writes its slice in place
+        return fm
 
     def embed(self, fm, boxes_flat, B, T, N):
         """RoIAlign -> fc_emb_1 -> nl_emb_1 -> ReLU -> (lite branch).  Returns fp32 [B,T,N,C]."""

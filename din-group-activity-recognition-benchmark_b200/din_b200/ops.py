@@ -11,8 +11,35 @@ from . import _lib
 from ._lib import DinConvDesc, check
 
 
+LAUNCHES = 0      # kernels launched through this module (each C-ABI compute call launches exactly one)
+RECORDER = None   # optional list: bench.py's profiling pass appends (name, flops, bytes, ev_start, ev_end)
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _launch:
+    """Counts the launch and, when a recorder is installed, brackets it with CUDA events on the launching
+    (current) stream."""
+
+    def __init__(self, name, flops=0, nbytes=0):
+        self.name, self.flops, self.nbytes = name, flops, nbytes
+
+    def __enter__(self):
+        global LAUNCHES
+        LAUNCHES += 1
+        if RECORDER is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if RECORDER is not None:
+            self.e1.record()
+            RECORDER.append((self.name, self.flops, self.nbytes, self.e0, self.e1))
+        return False
 
 
 def _p(t):
@@ -69,8 +96,11 @@ def conv2d_nhwc(x, w_packed, bias=None, *, stride=1, pad=(0, 0), relu=False, res
         rp = C.c_void_p(residual.data_ptr() + 2 * y_c_offset)
     if bias is not None:
         _need(bias, torch.float32, "bias")
-    check(_lib.load().din_conv2d_nhwc_f16(C.byref(d), xp, _p(w_packed), _p(bias), rp, yp, _stream()),
-          "din_conv2d_nhwc_f16")
+    flops = 2 * n * oh * ow * co * kh * kw * ci
+    nbytes = 2 * n * h * w * ci + 2 * co * kh * kw * ci + esz_y * n * oh * ow * co
+    with _launch(f"conv{kh}x{kw}s{stride}_{ci}->{co}@{oh}x{ow}", flops, nbytes):
+        check(_lib.load().din_conv2d_nhwc_f16(C.byref(d), xp, _p(w_packed), _p(bias), rp, yp, _stream()),
+              "din_conv2d_nhwc_f16")
     return out
 
 
@@ -87,20 +117,25 @@ def stem_conv(x_nchw, w_oihw, bias, *, stride=1, pad=0, relu=True, prep=True):
     y = torch.empty((n, oh, ow, co), dtype=torch.float16, device=x_nchw.device)
     if bias is not None:
         _need(bias, torch.float32, "bias")
-    check(_lib.load().din_stem_conv_nchw_f32(_p(x_nchw), _p(w_oihw), _p(bias), _p(y), n, h, w, co, kh, kw,
-                                             stride, pad, int(relu), int(prep), _stream()),
-          "din_stem_conv_nchw_f32")
+    with _launch(f"stem{kh}x{kw}s{stride}_3->{co}@{oh}x{ow}", 2 * n * oh * ow * co * kh * kw * 3,
+                 4 * n * 3 * h * w + 2 * n * oh * ow * co):
+        check(_lib.load().din_stem_conv_nchw_f32(_p(x_nchw), _p(w_oihw), _p(bias), _p(y), n, h, w, co, kh, kw,
+                                                 stride, pad, int(relu), int(prep), _stream()),
+              "din_stem_conv_nchw_f32")
     return y
 
 
-def maxpool2d_nhwc(x, k, stride, pad=0):
+def maxpool2d_nhwc(x, k, stride, pad=0, out=None):
     _need(x, torch.float16, "x")
     n, h, w, c = x.shape
     oh = (h + 2 * pad - k) // stride + 1
     ow = (w + 2 * pad - k) // stride + 1
-    y = torch.empty((n, oh, ow, c), dtype=torch.float16, device=x.device)
-    check(_lib.load().din_maxpool2d_nhwc_f16(_p(x), _p(y), n, h, w, c, k, stride, pad, _stream()),
-          "din_maxpool2d_nhwc_f16")
+    y = torch.empty((n, oh, ow, c), dtype=torch.float16, device=x.device) if out is None else out
+    _need(y, torch.float16, "out")
+    assert tuple(y.shape) == (n, oh, ow, c)
+    with _launch(f"maxpool{k}s{stride}_{c}@{oh}x{ow}", 0, 2 * n * c * (h * w + oh * ow)):
+        check(_lib.load().din_maxpool2d_nhwc_f16(_p(x), _p(y), n, h, w, c, k, stride, pad, _stream()),
+              "din_maxpool2d_nhwc_f16")
     return y
 
 
@@ -117,8 +152,9 @@ def roi_align_nhwc(fm, boxes, box_ind, crop_h, crop_w, d=None, out=None):
     m = boxes.shape[0]
     if out is None:
         out = torch.empty((m, crop_h * crop_w, d), dtype=torch.float16, device=fm.device)
-    check(_lib.load().din_roi_align_nhwc_f16(_p(fm), _p(boxes), _p(box_ind), _p(out), n_img, h, w, d, cs, m,
-                                             crop_h, crop_w, _stream()), "din_roi_align_nhwc_f16")
+    with _launch("roi_align", 0, 2 * n_img * h * w * d + 2 * m * crop_h * crop_w * d):
+        check(_lib.load().din_roi_align_nhwc_f16(_p(fm), _p(boxes), _p(box_ind), _p(out), n_img, h, w, d, cs, m,
+                                                 crop_h, crop_w, _stream()), "din_roi_align_nhwc_f16")
     return out
 
 
@@ -129,10 +165,11 @@ def group_layernorm(x, gamma, beta, *, n_outer, n_inner=1, outer_stride, inner_s
     _need(beta, torch.float32, "beta")
     if out is None:
         out = torch.empty_like(x)
-    check(_lib.load().din_group_layernorm_f32(_p(x), _p(pre), _p(post), _p(gamma), _p(beta), _p(out), n_outer,
-                                              n_inner, outer_stride, inner_stride, rows, row_stride, cols,
-                                              float(eps), int(relu), _p(n_valid), _stream()),
-          "din_group_layernorm_f32")
+    with _launch("group_layernorm", 0, 8 * n_outer * n_inner * rows * cols):
+        check(_lib.load().din_group_layernorm_f32(_p(x), _p(pre), _p(post), _p(gamma), _p(beta), _p(out), n_outer,
+                                                  n_inner, outer_stride, inner_stride, rows, row_stride, cols,
+                                                  float(eps), int(relu), _p(n_valid), _stream()),
+              "din_group_layernorm_f32")
     return out
 
 
@@ -146,8 +183,9 @@ def linear_f32(x, w, bias=None, *, relu=False, out=None, accumulate=False):
     if out is None:
         assert not accumulate
         out = torch.empty(x.shape[:-1] + (n,), dtype=torch.float32, device=x.device)
-    check(_lib.load().din_linear_f32(_p(x), _p(w), _p(bias), _p(out), m, n, k, int(relu), int(accumulate),
-                                     _stream()), "din_linear_f32")
+    with _launch(f"linear_f32_{k}->{n}", 2 * m * n * k, 4 * (m * k + n * k + m * n)):
+        check(_lib.load().din_linear_f32(_p(x), _p(w), _p(bias), _p(out), m, n, k, int(relu), int(accumulate),
+                                         _stream()), "din_linear_f32")
     return out
 
 
@@ -174,9 +212,11 @@ def dynamic_infer(x, w_tap, b_cat, kernel, ratio, *, scale_factor=True, out=None
         assert not accumulate
         # actors beyond n_valid are never written: start from zeros so they are well defined
         out = torch.zeros_like(x) if n_valid is not None else torch.empty_like(x)
-    check(_lib.load().din_dynamic_infer_f32(_p(x), _p(w_tap), _p(b_cat), _p(out), b, t, n, c, kt, kn, ratio,
-                                            int(scale_factor), C.c_void_p(coef_ptr or 0), float(coef),
-                                            int(accumulate), _p(n_valid), _stream()), "din_dynamic_infer_f32")
+    with _launch(f"dynamic_infer_k{kt}x{kn}_r{ratio}_c{c}", 2 * b * t * n * w_tap.shape[1] * kt * kn * c,
+                 8 * b * t * n * c + 4 * w_tap.numel()):
+        check(_lib.load().din_dynamic_infer_f32(_p(x), _p(w_tap), _p(b_cat), _p(out), b, t, n, c, kt, kn, ratio,
+                                                int(scale_factor), C.c_void_p(coef_ptr or 0), float(coef),
+                                                int(accumulate), _p(n_valid), _stream()), "din_dynamic_infer_f32")
     return out
 
 
@@ -188,6 +228,7 @@ def readout(s, w, bias, n_valid=None):
     b, t, n, c = s.shape
     a = w.shape[0]
     out = torch.empty((b, a), dtype=torch.float32, device=s.device)
-    check(_lib.load().din_readout_f32(_p(s), _p(w), _p(bias), _p(out), b, t, n, c, a, _p(n_valid), _stream()),
-          "din_readout_f32")
+    with _launch("readout", 0, 4 * b * t * n * c):
+        check(_lib.load().din_readout_f32(_p(s), _p(w), _p(bias), _p(out), b, t, n, c, a, _p(n_valid), _stream()),
+              "din_readout_f32")
     return out
