@@ -5,17 +5,29 @@
 // (infer_model.py:50,184; cuBLAS sgemm there).
 //
 // Formulation.  Output tile = 128 output pixels (a th x tw patch of one image, th*tw = 128) x BN
-// output channels.  K runs over (filter tap, 64-channel block).  For one K step
-//   A = the th x tw x 64ch input patch shifted by the tap offset.  Activations are NHWC fp16, so this
-//       is ONE 4-D TMA box {64ch, tw, th, 1}; out-of-image elements are zero-filled by the TMA unit,
-//       which *is* the convolution's zero padding; stride-2 convs use the tensor map's element
-//       strides.  With 64 fp16 = 128 B per pixel and SWIZZLE_128B the box lands exactly in the
-//       K-major SW128 layout tcgen05.mma consumes: no im2col buffer ever exists.
-//   B = BN rows x 64 columns of the packed weight [c_out][tap][c_in] (K-major): one 2-D TMA box.
-// A persistent, warp-specialised CTA per SM: warp 0 = TMA producer, warp 1 = MMA issuer (one lane),
-// warps 2..5 = epilogue (TMEM -> registers -> bias / residual / ReLU -> global).  The fp32
-// accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop of
-// tile i+1.
+// output channels; fp32 accumulator in TMEM; K runs over (64-channel block, filter tap).  Activations
+// are NHWC fp16: 64 channels = 128 bytes per pixel = one SWIZZLE_128B row, so a TMA box of pixels lands
+// directly in the K-major SW128 layout tcgen05.mma consumes — no im2col buffer ever exists, and the
+// TMA unit's out-of-bounds zero fill *is* the convolution's zero padding.
+//
+// Two A-operand modes:
+//   HALO (stride-1 filters larger than 1x1): per 64-channel block ONE TMA box brings the tile's whole
+//        input halo (th+kh-1) x (tw+kw-1) pixels into shared memory, and all kh*kw taps are served from
+//        it by UMMA descriptors whose start address is shifted by (ky*pitch + kx) pixel rows (tw = 8, so
+//        every 8-row core group of the tile is one halo row segment and the group stride SBO = pitch
+//        rows).  A-operand L2->SM traffic drops by kh*kw*th*tw / ((th+kh-1)*(tw+kw-1)) = 6.4x for 3x3 —
+//        ncu showed that traffic (not the tensor pipe) bounding the tap-per-load formulation at ~7 TB/s.
+//   TAP  (1x1 filters, stride-2 filters, the dense GEMM): one box {64ch, tw, th} per (tap, block),
+//        shifted by the tap offset; stride 2 uses the tensor map's element strides.
+// B = BN rows x 64 columns of the packed weight [c_out][tap][c_in] (K-major): one 2-D TMA box per
+// (block, tap), on its own ring so weights stream while a halo is reused.
+//
+// A persistent, warp-specialised CTA per SM (256 threads): warp 0 = A producer, warp 2 = B producer,
+// warp 1 = MMA issuer (one lane; tcgen05.commit frees smem stages / publishes the accumulator),
+// warps 4..7 = epilogue (TMEM -> registers -> bias / residual / ReLU / 2x2 max-pool -> global).  The
+// accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <cstdlib>
+
 #include "din_common.cuh"
 
 namespace {
@@ -23,16 +35,25 @@ namespace {
 using namespace din;
 
 struct ConvKParams {
-  int oh, ow;
+  int oh, ow;                 // conv output extent (before the optional fused pool)
   int c_out, y_c_stride;
   int tiles_x, tiles_per_img;
   int n_tiles_n;
   int num_tiles;
   int th, tw, tw_log2;
   int kh, kw, stride, pad_h, pad_w;
-  int n_cblk;  // c_in / 64
+  int n_cblk;                 // c_in / 64
   int c_in;
-  int relu, out_f32;
+  int relu, out_f32, pool2;
+  // A-operand staging
+  int halo;                   // 1: HALO mode, 0: TAP mode
+  int halo_rows;              // th + kh - 1
+  int pitch_rows;             // smem rows between consecutive halo rows (tw+kw-1, or 16 when padded)
+  int per_row_loads;          // 1: one TMA box per halo row (padded pitch); 0: one box per halo
+  int use_base_offset;        // descriptor base_offset = (start >> 7) & 7
+  int a_stage_bytes, n_a_stages, n_b_stages;
+  int tb;                     // filter taps per B stage (HALO mode; 1 in TAP mode)
+  uint32_t a_tx_bytes;
   const float* bias;
   const __half* residual;
   void* y;
@@ -40,62 +61,90 @@ struct ConvKParams {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;                    // fp16 elements per K step = one 128-byte swizzle row
-constexpr int kABytes = kBM * kBK * 2;     // 16 KB
-constexpr int kNumThreads = 192;
+constexpr int kNumThreads = 256;
+constexpr int kSmemBudget = 200 * 1024;    // operand rings; barriers and alignment slack come on top
+constexpr int kMaxStages = 16;
 
-template <int BN>
-struct ConvCfg {
-  static constexpr int kBBytes = BN * kBK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (192 * 1024) / kStageBytes;  // 4 / 6 / 8 stages for BN = 256 / 128 / 64
-  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-};
+constexpr int kEpiPitch = 80;             // bytes per pixel row in the epilogue transpose scratch (64 + 16 pad)
+constexpr int kEpiScratch = 32 * kEpiPitch;  // per epilogue warp
+
+// UMMA smem descriptor (K-major, SWIZZLE_128B), split so the issue loop only touches the low word:
+//   lo = start address >> 4 | LBO(=1) << 16          hi = SBO >> 4 | version 1 << 14 | SWIZZLE_128B << 29
+// The hardware applies the 128B swizzle on absolute shared-memory address bits (probed on B200:
+// tools/probe_conv.py), so a start address shifted by whole 128-byte rows — and an 8-row group stride
+// (SBO) that is not a multiple of 1024 — address a sub-window of a larger TMA-written halo correctly
+// with base_offset = 0.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
+  return static_cast<uint64_t>(lo) | (static_cast<uint64_t>(hi) << 32);
+}
 
 template <int BN>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const ConvKParams p) {
-  using Cfg = ConvCfg<BN>;
+  constexpr int kBBytes = BN * kBK * 2;
+  constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* tmem_full = empty_bar + Cfg::kStages;
+  uint8_t* smem_a = smem;
+  const int b_stage_bytes = p.tb * kBBytes;
+  uint8_t* smem_b = smem + p.n_a_stages * p.a_stage_bytes;
+  uint8_t* epi_scratch = smem_b + p.n_b_stages * b_stage_bytes;                 // 4 warps x 2560 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_scratch + 4 * kEpiScratch);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + kMaxStages;
+  uint64_t* b_full = a_empty + kMaxStages;
+  uint64_t* b_empty = b_full + kMaxStages;
+  uint64_t* tmem_full = b_empty + kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint32_t* tap_off = tmem_ptr_smem + 4;      // [kh*kw] A-descriptor start offsets (16-byte units), HALO mode
+  float* bias_s = reinterpret_cast<float*>(tap_off + 64);   // [n_tiles_n * BN] bias (0 beyond c_out / no bias)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int taps = p.kh * p.kw;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 128);
-    }
+    for (int s = 0; s < p.n_a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < p.n_b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
+  if (warp == 3) {
+    for (int t = lane; t < taps; t += 32) {
+      const int ky = t / p.kw, kx = t - ky * p.kw;
+      tap_off[t] = p.halo ? static_cast<uint32_t>(ky * p.pitch_rows + kx) * (128u >> 4) : 0u;
+    }
+  }
+  if (warp >= 4) {
+    // the epilogue's bias lives in shared memory: broadcast LDS instead of eight serialised global loads
+    // per 32-column chunk (ncu: those loads' latency was the epilogue's critical path)
+    for (int c = threadIdx.x - 128; c < p.n_tiles_n * BN; c += 128)
+      bias_s[c] = (p.bias != nullptr && c < p.c_out) ? __ldg(p.bias + c) : 0.0f;
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr_smem);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int k_iters = p.kh * p.kw * p.n_cblk;
+  const int taps_per_a = p.halo ? taps : 1;            // taps served by one A stage
+  const int a_groups = p.halo ? p.n_cblk : taps * p.n_cblk;
+  const int b_groups = (taps_per_a + p.tb - 1) / p.tb;  // B stages consumed per A stage
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (one lane)
+    // ------------------------------------------------------------------ A producer (one lane)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles_n;
         const int mt = tile / p.n_tiles_n;
         const int img = mt / p.tiles_per_img;
         const int r = mt - img * p.tiles_per_img;
@@ -103,60 +152,114 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int txi = r - tyi * p.tiles_x;
         const int ix0 = txi * p.tw * p.stride - p.pad_w;
         const int iy0 = tyi * p.th * p.stride - p.pad_h;
-        const int n0 = nt * BN;
-        for (int ky = 0; ky < p.kh; ++ky) {
-          for (int kx = 0; kx < p.kw; ++kx) {
-            const int kbase = (ky * p.kw + kx) * p.c_in;
-            for (int cb = 0; cb < p.n_cblk; ++cb) {
-              mbar_wait(&empty_bar[stage], phase ^ 1u);
-              uint8_t* sa = smem + stage * Cfg::kStageBytes;
-              uint8_t* sb = sa + kABytes;
-              mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-              tma_load_4d(sa, &tmap_a, &full_bar[stage], cb * kBK, ix0 + kx, iy0 + ky, img);
-              tma_load_2d(sb, &tmap_b, &full_bar[stage], kbase + cb * kBK, n0);
-              if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
-            }
+        for (int g = 0; g < a_groups; ++g) {
+          mbar_wait(&a_empty[stage], phase ^ 1u);
+          uint8_t* sa = smem_a + stage * p.a_stage_bytes;
+          mbar_arrive_expect_tx(&a_full[stage], p.a_tx_bytes);
+          if (p.halo) {
+            tma_load_4d(sa, &tmap_a, &a_full[stage], g * kBK, ix0, iy0, img);
+          } else {
+            const int tap = g / p.n_cblk;
+            const int cb = g - tap * p.n_cblk;
+            const int ky = tap / p.kw, kx = tap - ky * p.kw;
+            tma_load_4d(sa, &tmap_a, &a_full[stage], cb * kBK, ix0 + kx, iy0 + ky, img);
+          }
+          if (++stage == p.n_a_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ B producer (one lane)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.n_tiles_n) * BN;
+        for (int g = 0; g < a_groups; ++g) {
+          // HALO: g = channel block, taps stream in groups of tb.  TAP: g = tap * n_cblk + cb, one tap.
+          const int kbase = p.halo ? g * kBK : ((g / p.n_cblk) * p.c_in + (g % p.n_cblk) * kBK);
+          for (int bg = 0; bg < b_groups; ++bg) {
+            const int t0 = bg * p.tb;
+            const int nt = min(p.tb, taps_per_a - t0);
+            mbar_wait(&b_empty[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&b_full[stage], static_cast<uint32_t>(nt) * kBBytes);
+            uint8_t* sb = smem_b + stage * b_stage_bytes;
+            for (int tt = 0; tt < nt; ++tt)
+              tma_load_2d(sb + tt * kBBytes, &tmap_b, &b_full[stage], kbase + (t0 + tt) * p.c_in, n0);
+            if (++stage == p.n_b_stages) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (lane 0 issues)
-    constexpr uint32_t idesc = umma_idesc_f16_f32(kBM, BN);
-    int stage = 0;
-    uint32_t phase = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1u;
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
-      tc_fence_after_sync();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-      for (int kit = 0; kit < k_iters; ++kit) {
-        mbar_wait(&full_bar[stage], phase);
+    // ------------------------------------------------------------------ MMA issuer: ONE thread.
+    // The loop is latency-bound on this thread's instruction stream (ncu: the producers wait on empty
+    // slots, this warp never waits for data), so everything invariant is hoisted and each barrier
+    // round-trip covers tb taps x 4 MMAs.
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16_f32(kBM, BN);
+      const uint32_t a_hi = desc_hi(p.halo ? static_cast<uint32_t>(p.pitch_rows) * 128u : 1024u);
+      const uint32_t b_hi = desc_hi(1024u);
+      const uint32_t a_lo0 = desc_lo(smem_u32(smem_a));
+      const uint32_t b_lo0 = desc_lo(smem_u32(smem_b));
+      const uint32_t a_step = static_cast<uint32_t>(p.a_stage_bytes) >> 4;
+      const uint32_t b_step = static_cast<uint32_t>(b_stage_bytes) >> 4;
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1u) ^ 1u);
         tc_fence_after_sync();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint64_t adesc = umma_desc_k_sw128(sa);
-          const uint64_t bdesc = umma_desc_k_sw128(sa + kABytes);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        uint32_t accum = 0;
+        for (int g = 0; g < a_groups; ++g) {
+          mbar_wait(&a_full[sa], pa);
+          const uint32_t a_lo = a_lo0 + sa * a_step;
+          int t = 0;
+          for (int bg = 0; bg < b_groups; ++bg) {
+            const int nt = min(p.tb, taps_per_a - t);
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after_sync();
+            uint32_t b_lo = b_lo0 + sb * b_step;
+            for (int tt = 0; tt < nt; ++tt, ++t, b_lo += (kBBytes >> 4)) {
+              const uint32_t al = a_lo + tap_off[t];
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
-            umma_f16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kit | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < kBK / 16; ++k) {   // +32 bytes (2 x 16-byte units) per K=16 slice
+                umma_f16_ss(d_tmem, desc64(al + 2u * k, a_hi), desc64(b_lo + 2u * k, b_hi), idesc, accum);
+                accum = 1;
+              }
+            }
+            umma_commit(&b_empty[sb]);  // frees the weight slot when these MMAs retire
+            if (++sb == p.n_b_stages) { sb = 0; pb ^= 1u; }
           }
-          umma_commit(&empty_bar[stage]);                       // frees the smem slot when the MMAs retire
-          if (kit == k_iters - 1) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+          umma_commit(&a_empty[sa]);                             // halo / tap tile fully consumed
+          if (g == a_groups - 1) umma_commit(&tmem_full[acc]);   // accumulator complete -> epilogue
+          if (++sa == p.n_a_stages) { sa = 0; pa ^= 1u; }
         }
-        __syncwarp();
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else {
+  } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (4 warps, 128 lanes)
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    const int m = q * 32 + lane;
-    const int ty = m >> p.tw_log2;
-    const int tx = m & (p.tw - 1);
+    uint8_t* scratch = epi_scratch + q * kEpiScratch;
+    // Store side of the transpose: after the scratch round-trip, lane l writes 16-byte unit (l & 3) of
+    // pixel slot (l >> 2) + 8*k (k = 0..3) — i.e. four lanes write one pixel's 64 contiguous bytes, so
+    // every global store instruction covers full 32-byte sectors (no partial-sector read-modify-write).
+    // With the fused pool only 8 lanes of the warp hold a pooled pixel: one store instruction.
+    const int unit = lane & 3;
+    int src_lane[4];   // which lane's (= which tile pixel's) row this lane stores in round k
+    int n_rounds;
+    if (p.pool2) {
+      const int i = lane >> 2, half_tw = p.tw >> 1;
+      src_lane[0] = (i / half_tw) * 2 * p.tw + (i % half_tw) * 2;
+      src_lane[1] = src_lane[2] = src_lane[3] = 0;
+      n_rounds = 1;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) src_lane[k] = (lane >> 2) + 8 * k;
+      n_rounds = 4;
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -167,76 +270,115 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int r = mt - img * p.tiles_per_img;
       const int tyi = r / p.tiles_x;
       const int txi = r - tyi * p.tiles_x;
-      const int oy = tyi * p.th + ty;
-      const int ox = txi * p.tw + tx;
-      const bool valid = (oy < p.oh) && (ox < p.ow);
       const int n0 = nt * BN;
-      const size_t pix = (static_cast<size_t>(img) * p.oh + oy) * p.ow + ox;
+      // own pixel (residual / fp32 path) and the pixels this lane stores after the transpose
+      const int m_own = q * 32 + lane;
+      const int oy_own = tyi * p.th + (m_own >> p.tw_log2), ox_own = txi * p.tw + (m_own & (p.tw - 1));
+      const bool valid_own = (oy_own < p.oh) && (ox_own < p.ow);
+      const size_t pix_own = (static_cast<size_t>(img) * p.oh + oy_own) * p.ow + ox_own;
+      size_t st_pix[4];
+      bool st_valid[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int m = q * 32 + src_lane[k];
+        const int oy = tyi * p.th + (m >> p.tw_log2), ox = txi * p.tw + (m & (p.tw - 1));
+        if (p.pool2) {
+          const int poh = p.oh >> 1, pow_ = p.ow >> 1;
+          st_valid[k] = (k == 0) && ((oy >> 1) < poh) && ((ox >> 1) < pow_);
+          st_pix[k] = (static_cast<size_t>(img) * poh + (oy >> 1)) * pow_ + (ox >> 1);
+        } else {
+          st_valid[k] = (oy < p.oh) && (ox < p.ow);
+          st_pix[k] = (static_cast<size_t>(img) * p.oh + oy) * p.ow + ox;
+        }
+      }
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(taddr, v);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr + c0, v);
         tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (c0 + 32 < BN) tmem_ld_32x32b_x32(taddr + c0 + 32, v);   // prefetch the next chunk's accumulators
         const int col0 = n0 + c0;
-        if (valid && col0 < p.c_out) {
-          float f[32];
+        if (col0 >= p.c_out) continue;   // warp-uniform
+        {
+          const float4* bs = reinterpret_cast<const float4*>(bias_s + col0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (col0 + j < p.c_out) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-              }
-            }
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = bs[j];
+            f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
           }
-          const size_t off = pix * p.y_c_stride + col0;
-          if (p.residual != nullptr) {
+        }
+        if (p.residual != nullptr && valid_own) {
+          const __half* rp = p.residual + pix_own * p.y_c_stride + col0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (col0 + j < p.c_out) {
-                const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.residual + off + j));
-                const __half2* h2 = reinterpret_cast<const __half2*>(&rr);
+          for (int j = 0; j < 32; j += 8) {
+            if (col0 + j < p.c_out) {
+              const uint4 rr = __ldg(reinterpret_cast<const uint4*>(rp + j));
+              const __half2* h2 = reinterpret_cast<const __half2*>(&rr);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 t2 = __half22float2(h2[e]);
-                  f[j + 2 * e] += t2.x;
-                  f[j + 2 * e + 1] += t2.y;
-                }
-              }
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-          }
-          if (p.out_f32) {
-            float* yp = reinterpret_cast<float*>(p.y) + off;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (col0 + j < p.c_out) {
-                *reinterpret_cast<float4*>(yp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-              }
-            }
-          } else {
-            __half* yp = reinterpret_cast<__half*>(p.y) + off;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (col0 + j < p.c_out) {
-                uint4 o;
-                __half2* h2 = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(f[j + 2 * e], f[j + 2 * e + 1]);
-                *reinterpret_cast<uint4*>(yp + j) = o;
+              for (int e = 0; e < 4; ++e) {
+                const float2 t2 = __half22float2(h2[e]);
+                f[j + 2 * e] += t2.x;
+                f[j + 2 * e + 1] += t2.y;
               }
             }
           }
         }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+        }
+        if (p.out_f32) {
+          if (valid_own) {
+            float* yp = reinterpret_cast<float*>(p.y) + pix_own * p.y_c_stride + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (col0 + j < p.c_out)
+                *reinterpret_cast<float4*>(yp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            }
+          }
+          continue;
+        }
+        __half2 h[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) h[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+        if (p.pool2) {
+          // 2x2 window = lanes {m, m^1, m^tw, m^tw^1}: all inside this warp because tw <= 16.
+          // max commutes with the (monotonic) fp16 rounding, so pooling the rounded values is exact.
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            uint32_t u = *reinterpret_cast<uint32_t*>(&h[e]);
+            uint32_t o1 = __shfl_xor_sync(0xffffffffu, u, 1);
+            h[e] = __hmax2(h[e], *reinterpret_cast<__half2*>(&o1));
+            u = *reinterpret_cast<uint32_t*>(&h[e]);
+            uint32_t o2 = __shfl_xor_sync(0xffffffffu, u, p.tw);
+            h[e] = __hmax2(h[e], *reinterpret_cast<__half2*>(&o2));
+          }
+        }
+        // transpose through the warp's scratch: 80-byte row pitch makes both sides bank-conflict free
+        {
+          uint4* wr = reinterpret_cast<uint4*>(scratch + lane * kEpiPitch);
+#pragma unroll
+          for (int u4 = 0; u4 < 4; ++u4) wr[u4] = *reinterpret_cast<uint4*>(&h[4 * u4]);
+        }
+        __syncwarp();
+        if (col0 + unit * 8 < p.c_out) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (k < n_rounds && st_valid[k]) {
+              const uint4 o = *reinterpret_cast<const uint4*>(scratch + src_lane[k] * kEpiPitch + unit * 16);
+              __half* yp = reinterpret_cast<__half*>(p.y) + st_pix[k] * p.y_c_stride + col0 + unit * 8;
+              *reinterpret_cast<uint4*>(yp) = o;
+            }
+          }
+        }
+        __syncwarp();
       }
       tc_fence_before_sync();
       mbar_arrive(&tmem_empty[acc]);
@@ -247,22 +389,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   __syncthreads();
   if (warp == 1) {
     tc_fence_after_sync();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 
 template <int BN>
-int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvKParams& p, int grid, cudaStream_t st) {
-  using Cfg = ConvCfg<BN>;
+int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvKParams& p, int grid, size_t smem,
+                cudaStream_t st) {
   static thread_local int attr_dev = -1;
   int dev = 0;
   DIN_CHECK_CUDA(cudaGetDevice(&dev));
   if (attr_dev != dev) {
     DIN_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        Cfg::kSmemBytes));
+                                        kSmemBudget + 4 * kEpiScratch + 4096 + 8192));
     attr_dev = dev;
   }
-  conv_igemm_kernel<BN><<<grid, kNumThreads, Cfg::kSmemBytes, st>>>(ta, tb, p);
+  conv_igemm_kernel<BN><<<grid, kNumThreads, smem, st>>>(ta, tb, p);
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;
 }
@@ -283,6 +425,13 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, const float* __r
     }
     out[i] = __float2half_rn(v);
   }
+}
+
+// Debug switch for GPU A/B runs: DIN_CONV_VARIANT bit2 (=4) forces TAP mode for every filter.
+// Unset = production default (HALO mode for stride-1 filters larger than 1x1).
+int conv_variant() {
+  const char* e = std::getenv("DIN_CONV_VARIANT");
+  return e ? std::atoi(e) : -1;
 }
 
 }  // namespace
@@ -311,8 +460,8 @@ extern "C" int din_conv2d_nhwc_f16(const DinConvDesc* d, const void* x, const vo
                 d->c_in);
   DIN_CHECK_ARG(d->x_c_stride >= d->c_in && d->x_c_stride % 8 == 0,
                 "din_conv2d_nhwc_f16: x_c_stride=%d must be >= c_in and a multiple of 8", d->x_c_stride);
-  DIN_CHECK_ARG(d->c_out > 0 && d->c_out % 8 == 0, "din_conv2d_nhwc_f16: c_out=%d must be a multiple of 8",
-                d->c_out);
+  DIN_CHECK_ARG(d->c_out > 0 && d->c_out % 8 == 0 && d->c_out <= 2048,
+                "din_conv2d_nhwc_f16: c_out=%d must be a multiple of 8 and <= 2048", d->c_out);
   DIN_CHECK_ARG(d->y_c_stride >= d->c_out && d->y_c_stride % 8 == 0,
                 "din_conv2d_nhwc_f16: y_c_stride=%d must be >= c_out and a multiple of 8", d->y_c_stride);
   DIN_CHECK_ARG(d->kh >= 1 && d->kw >= 1 && d->kh * d->kw <= 49, "din_conv2d_nhwc_f16: bad filter %dx%d", d->kh,
@@ -324,25 +473,37 @@ extern "C" int din_conv2d_nhwc_f16(const DinConvDesc* d, const void* x, const vo
                     (reinterpret_cast<uintptr_t>(residual) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(bias) & 15) == 0,
                 "din_conv2d_nhwc_f16: pointers must be 16-byte aligned");
+  DIN_CHECK_ARG(!(d->pool2 && (d->out_f32 || residual)),
+                "din_conv2d_nhwc_f16: pool2 cannot be combined with out_f32 or a residual");
   const int oh = (d->h + 2 * d->pad_h - d->kh) / d->stride + 1;
   const int ow = (d->w + 2 * d->pad_w - d->kw) / d->stride + 1;
   DIN_CHECK_ARG(oh > 0 && ow > 0, "din_conv2d_nhwc_f16: empty output %dx%d", oh, ow);
+  DIN_CHECK_ARG(!d->pool2 || (oh >= 2 && ow >= 2), "din_conv2d_nhwc_f16: pool2 needs an output of at least 2x2");
 
-  // output tile geometry: th x tw = 128 pixels, fewest tiles wins, wider rows break ties
-  int best_tw = 128, best_tiles = INT32_MAX;
-  for (int tw = 128; tw >= 8; tw >>= 1) {
-    const int th = 128 / tw;
-    const int tiles = ((ow + tw - 1) / tw) * ((oh + th - 1) / th);
-    if (tiles < best_tiles) { best_tiles = tiles; best_tw = tw; }
-  }
+  const int variant = conv_variant();
+  const bool force_tap = variant >= 0 && (variant & 4);
+  const bool halo = !force_tap && d->stride == 1 && (d->kh * d->kw > 1) && d->kw <= 9 && d->kh <= 9;
+
   ConvKParams p{};
   p.oh = oh; p.ow = ow;
   p.c_out = d->c_out; p.y_c_stride = d->y_c_stride;
-  p.tw = best_tw; p.th = 128 / best_tw;
+  if (halo) {
+    p.tw = 8;   // each 8-row UMMA core group = one halo row segment -> constant group stride (SBO)
+  } else {
+    // fewest tiles wins, wider rows break ties; the fused pool needs its 2x2 window inside one warp
+    int best_tw = 128, best_tiles = INT32_MAX;
+    for (int tw = d->pool2 ? 16 : 128; tw >= 8; tw >>= 1) {
+      const int th = 128 / tw;
+      const int tiles = ((ow + tw - 1) / tw) * ((oh + th - 1) / th);
+      if (tiles < best_tiles) { best_tiles = tiles; best_tw = tw; }
+    }
+    p.tw = best_tw;
+  }
+  p.th = 128 / p.tw;
   p.tw_log2 = 0;
   while ((1 << p.tw_log2) < p.tw) ++p.tw_log2;
   p.tiles_x = (ow + p.tw - 1) / p.tw;
-  p.tiles_per_img = best_tiles;
+  p.tiles_per_img = p.tiles_x * ((oh + p.th - 1) / p.th);
   const int bn = d->c_out > 128 ? 256 : (d->c_out > 64 ? 128 : 64);
   p.n_tiles_n = (d->c_out + bn - 1) / bn;
   const long long total_tiles = static_cast<long long>(d->n) * p.tiles_per_img * p.n_tiles_n;
@@ -350,8 +511,52 @@ extern "C" int din_conv2d_nhwc_f16(const DinConvDesc* d, const void* x, const vo
   p.num_tiles = static_cast<int>(total_tiles);
   p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad_h = d->pad_h; p.pad_w = d->pad_w;
   p.c_in = d->c_in; p.n_cblk = d->c_in / kBK;
-  p.relu = d->relu; p.out_f32 = d->out_f32;
+  p.relu = d->relu; p.out_f32 = d->out_f32; p.pool2 = d->pool2;
   p.bias = bias; p.residual = static_cast<const __half*>(residual); p.y = y;
+
+  // A staging geometry
+  uint32_t box_w, box_h;
+  p.halo = halo ? 1 : 0;
+  if (halo) {
+    const int halo_w = p.tw + d->kw - 1;
+    p.halo_rows = p.th + d->kh - 1;
+    p.per_row_loads = 0;
+    p.use_base_offset = 0;
+    p.pitch_rows = halo_w;
+    p.a_stage_bytes = ((p.halo_rows * p.pitch_rows * 128) + 1023) & ~1023;
+    p.a_tx_bytes = static_cast<uint32_t>(halo_w) * p.halo_rows * 128u;
+    box_w = static_cast<uint32_t>(halo_w);
+    box_h = p.per_row_loads ? 1u : static_cast<uint32_t>(p.halo_rows);
+  } else {
+    p.halo_rows = p.th; p.pitch_rows = p.tw; p.per_row_loads = 0; p.use_base_offset = 0;
+    p.a_stage_bytes = kBM * 128;
+    p.a_tx_bytes = kBM * 128;
+    box_w = static_cast<uint32_t>((p.tw - 1) * d->stride + 1);
+    box_h = static_cast<uint32_t>((p.th - 1) * d->stride + 1);
+  }
+  DIN_CHECK_ARG(box_w <= 256 && box_h <= 256, "din_conv2d_nhwc_f16: TMA box too large");
+  const int b_bytes = bn * kBK * 2;
+  if (halo) {
+    // several taps per weight stage: fewer barrier round-trips per MMA for the narrow-N layers
+    p.tb = 40960 / b_bytes;
+    if (p.tb < 1) p.tb = 1;
+    if (p.tb > d->kh * d->kw) p.tb = d->kh * d->kw;
+    p.n_a_stages = 2;
+    p.n_b_stages = (kSmemBudget - p.n_a_stages * p.a_stage_bytes) / (p.tb * b_bytes);
+  } else {
+    p.tb = 1;
+    const int pairs = kSmemBudget / (p.a_stage_bytes + b_bytes);
+    p.n_a_stages = pairs;
+    p.n_b_stages = pairs;
+  }
+  if (p.n_a_stages > kMaxStages) p.n_a_stages = kMaxStages;
+  if (p.n_b_stages > kMaxStages) p.n_b_stages = kMaxStages;
+  DIN_CHECK_ARG(p.n_a_stages >= 2 && p.n_b_stages >= 2, "din_conv2d_nhwc_f16: filter %dx%d does not fit shared memory",
+                d->kh, d->kw);
+  const size_t smem = static_cast<size_t>(p.n_a_stages) * p.a_stage_bytes +
+                      static_cast<size_t>(p.n_b_stages) * p.tb * b_bytes + 4 * kEpiScratch + 1024 /*align*/ +
+                      (4 * kMaxStages + 4) * 8 + 16 + 64 * 4 /*tap offsets*/ +
+                      static_cast<size_t>(p.n_tiles_n) * bn * 4 /*bias*/;
 
   CUtensorMap ta, tb;
   {
@@ -359,8 +564,7 @@ extern "C" int din_conv2d_nhwc_f16(const DinConvDesc* d, const void* x, const vo
                               static_cast<uint64_t>(d->h), static_cast<uint64_t>(d->n)};
     const uint64_t cs = static_cast<uint64_t>(d->x_c_stride) * 2;
     const uint64_t strides[4] = {2, cs, cs * d->w, cs * d->w * d->h};
-    const uint32_t box[4] = {static_cast<uint32_t>(kBK), static_cast<uint32_t>((p.tw - 1) * d->stride + 1),
-                             static_cast<uint32_t>((p.th - 1) * d->stride + 1), 1};
+    const uint32_t box[4] = {static_cast<uint32_t>(kBK), box_w, box_h, 1};
     const uint32_t es[4] = {1, static_cast<uint32_t>(d->stride), static_cast<uint32_t>(d->stride), 1};
     int rc = din_encode_tmap(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, box,
                              es, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -381,8 +585,8 @@ extern "C" int din_conv2d_nhwc_f16(const DinConvDesc* d, const void* x, const vo
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (bn) {
-    case 256: return launch_conv<256>(ta, tb, p, grid, st);
-    case 128: return launch_conv<128>(ta, tb, p, grid, st);
-    default: return launch_conv<64>(ta, tb, p, grid, st);
+    case 256: return launch_conv<256>(ta, tb, p, grid, smem, st);
+    case 128: return launch_conv<128>(ta, tb, p, grid, smem, st);
+    default: return launch_conv<64>(ta, tb, p, grid, smem, st);
   }
 }

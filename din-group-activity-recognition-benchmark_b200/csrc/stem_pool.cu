@@ -4,6 +4,7 @@
 //   * NHWC fp16 max pooling (reference: nn.MaxPool2d inside vgg16.features / resnet18.maxpool,
 //     F.max_pool2d at backbone.py:50,56).
 #include <cfloat>
+#include <cstdlib>
 
 #include "din_common.cuh"
 
@@ -172,12 +173,18 @@ extern "C" int din_stem_conv_nchw_f32(const float* x, const float* w, const floa
   const int oh = (h + 2 * pad - kh) / stride + 1;
   const int ow = (w_in + 2 * pad - kw) / stride + 1;
   DIN_CHECK_ARG(oh > 0 && ow > 0, "din_stem_conv_nchw_f32: empty output");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    // production path: im2col-in-smem + tcgen05.mma (stem_tc.cu).  DIN_STEM_SIMT=1 selects the CUDA-core
+    // direct convolution below (kept for A/B measurements only).
+    const char* e = std::getenv("DIN_STEM_SIMT");
+    if (!(e && e[0] == '1')) return din_stem_tc_launch(x, w, bias, y, n, h, w_in, c_out, kh, kw, stride, pad, relu, prep, st);
+  }
   const int K = 3 * kh * kw;
   const int in_th = (kStemTileH - 1) * stride + kh;
   const int in_tw_p = ((kStemTileW - 1) * stride + kw) | 1;
   const size_t smem = (static_cast<size_t>(K) * c_out + 3 * in_th * in_tw_p) * sizeof(float);
   dim3 grid((ow + kStemTileW - 1) / kStemTileW, (oh + kStemTileH - 1) / kStemTileH, n);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (c_out == 64) {
     DIN_CHECK_CUDA(cudaFuncSetAttribute(stem_conv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem)));

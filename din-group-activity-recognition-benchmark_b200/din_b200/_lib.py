@@ -16,7 +16,7 @@ class DinError(RuntimeError):
 class DinConvDesc(C.Structure):
     _fields_ = [(name, C.c_int32) for name in (
         "n", "h", "w", "c_in", "x_c_stride", "c_out", "y_c_stride", "kh", "kw", "stride",
-        "pad_h", "pad_w", "relu", "out_f32")]
+        "pad_h", "pad_w", "relu", "out_f32", "pool2")]
 
 
 _vp, _i, _fp, _ll = C.c_void_p, C.c_int, C.c_void_p, C.c_longlong  # float* is passed as a raw address

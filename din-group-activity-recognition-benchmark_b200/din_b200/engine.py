@@ -32,15 +32,15 @@ def _fold_bn(conv_w, bn):
 class _Conv:
     """One tcgen05 convolution of the plan (weights packed fp16 [co][kh][kw][ci], fp32 bias)."""
 
-    def __init__(self, w, bias, scale=None, stride=1, pad=(0, 0), relu=True):
+    def __init__(self, w, bias, scale=None, stride=1, pad=(0, 0), relu=True, pool2=False):
         self.w = ops.pack_conv_weight(w.contiguous(), scale)
         self.bias = None if bias is None else bias.contiguous().float()
-        self.stride, self.pad, self.relu = stride, pad, relu
+        self.stride, self.pad, self.relu, self.pool2 = stride, pad, relu, pool2
         self.c_out, self.kh, self.kw, self.c_in = self.w.shape
 
     def __call__(self, x, out=None, residual=None, **kw):
         return ops.conv2d_nhwc(x, self.w, self.bias, stride=self.stride, pad=self.pad, relu=self.relu,
-                               residual=residual, out=out, **kw)
+                               residual=residual, out=out, pool2=self.pool2, **kw)
 
 
 class _Stem:
@@ -63,18 +63,16 @@ class VGG16Plan:
     def __init__(self, sd, prefix="backbone.features."):
         self.layers = []
         idx = 0
-        first = True
-        for v in self.CFG:
+        for i, v in enumerate(self.CFG):
             if v == "M":
-                self.layers.append("M")
-                idx += 1
+                idx += 1        # the 2x2 max-pool is fused into the preceding conv's epilogue
                 continue
             w, b = sd[f"{prefix}{idx}.weight"], sd[f"{prefix}{idx}.bias"]
-            if first:
+            pool = i + 1 < len(self.CFG) and self.CFG[i + 1] == "M"
+            if not self.layers:
                 self.layers.append(_Stem(w, b, stride=1, pad=1))
-                first = False
             else:
-                self.layers.append(_Conv(w, b, stride=1, pad=(1, 1), relu=True))
+                self.layers.append(_Conv(w, b, stride=1, pad=(1, 1), relu=True, pool2=pool))
             idx += 2
         self.out_channels = 512
 
@@ -82,10 +80,7 @@ class VGG16Plan:
         x = images
         last = len(self.layers) - 1
         for i, layer in enumerate(self.layers):
-            if layer == "M":
-                x = ops.maxpool2d_nhwc(x, 2, 2, 0, out=out if i == last else None)
-            else:
-                x = layer(x)
+            x = layer(x, out=out) if i == last else layer(x)
         return x
 
     def out_shape(self, h, w):

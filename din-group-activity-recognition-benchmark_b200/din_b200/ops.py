@@ -66,7 +66,7 @@ def pack_conv_weight(w_oihw, scale=None, c_in_padded=None):
 
 
 def conv2d_nhwc(x, w_packed, bias=None, *, stride=1, pad=(0, 0), relu=False, residual=None, out=None,
-                out_f32=False, c_in=None, x_c_offset=0, y_c_offset=0, c_out=None):
+                out_f32=False, c_in=None, x_c_offset=0, y_c_offset=0, c_out=None, pool2=False):
     """x: [n,h,w,Cx] fp16 NHWC (the conv reads channels [x_c_offset, x_c_offset+c_in)).
     w_packed: [c_out, kh, kw, c_in] fp16.  Returns / fills `out` [n,oh,ow,Cy] at channel offset y_c_offset."""
     _need(x, torch.float16, "x")
@@ -79,13 +79,14 @@ def conv2d_nhwc(x, w_packed, bias=None, *, stride=1, pad=(0, 0), relu=False, res
     ph, pw = pad
     oh = (h + 2 * ph - kh) // stride + 1
     ow = (w + 2 * pw - kw) // stride + 1
+    yh, yw = (oh // 2, ow // 2) if pool2 else (oh, ow)
     if out is None:
-        out = torch.empty((n, oh, ow, co), dtype=torch.float32 if out_f32 else torch.float16, device=x.device)
+        out = torch.empty((n, yh, yw, co), dtype=torch.float32 if out_f32 else torch.float16, device=x.device)
     _need(out, torch.float32 if out_f32 else torch.float16, "out")
-    assert out.shape[:3] == (n, oh, ow), (out.shape, (n, oh, ow))
+    assert out.shape[:3] == (n, yh, yw), (out.shape, (n, yh, yw))
     cy = out.shape[3]
     d = DinConvDesc(n=n, h=h, w=w, c_in=c_in, x_c_stride=cx, c_out=co, y_c_stride=cy, kh=kh, kw=kw,
-                    stride=stride, pad_h=ph, pad_w=pw, relu=int(relu), out_f32=int(out_f32))
+                    stride=stride, pad_h=ph, pad_w=pw, relu=int(relu), out_f32=int(out_f32), pool2=int(pool2))
     esz_y = 4 if out_f32 else 2
     xp = C.c_void_p(x.data_ptr() + 2 * x_c_offset)
     yp = C.c_void_p(out.data_ptr() + esz_y * y_c_offset)
@@ -97,8 +98,8 @@ def conv2d_nhwc(x, w_packed, bias=None, *, stride=1, pad=(0, 0), relu=False, res
     if bias is not None:
         _need(bias, torch.float32, "bias")
     flops = 2 * n * oh * ow * co * kh * kw * ci
-    nbytes = 2 * n * h * w * ci + 2 * co * kh * kw * ci + esz_y * n * oh * ow * co
-    with _launch(f"conv{kh}x{kw}s{stride}_{ci}->{co}@{oh}x{ow}", flops, nbytes):
+    nbytes = 2 * n * h * w * ci + 2 * co * kh * kw * ci + esz_y * n * yh * yw * co
+    with _launch(f"conv{kh}x{kw}s{stride}_{ci}->{co}@{oh}x{ow}" + ("+pool" if pool2 else ""), flops, nbytes):
         check(_lib.load().din_conv2d_nhwc_f16(C.byref(d), xp, _p(w_packed), _p(bias), rp, yp, _stream()),
               "din_conv2d_nhwc_f16")
     return out

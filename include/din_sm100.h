@@ -83,6 +83,7 @@ typedef struct DinConvDesc {
   int32_t pad_h, pad_w;     /* zero padding */
   int32_t relu;             /* fuse ReLU */
   int32_t out_f32;          /* 0: y is fp16, 1: y is fp32 */
+  int32_t pool2;            /* fuse MaxPool2d(2,2) after (bias, ReLU): y is [n, oh/2, ow/2, ...] (fp16, no residual) */
 } DinConvDesc;
 
 /*
@@ -91,6 +92,7 @@ typedef struct DinConvDesc {
  * bias     : fp32 [c_out] or NULL
  * residual : fp16, same indexing as y with y_c_stride, added before ReLU; or NULL
  * y        : fp16 or fp32 (out_f32), element (img, oy, ox, co) at y[((img*oh + oy)*ow + ox)*y_c_stride + co]
+ *            (with pool2: oh, ow are the pooled extents floor(oh/2), floor(ow/2), as nn.MaxPool2d(2,2))
  */
 DIN_API int din_conv2d_nhwc_f16(const DinConvDesc* desc, const void* x, const void* w_packed, const float* bias,
                         const void* residual, void* y, void* stream);
