@@ -133,7 +133,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  // broadcast through a shuffle so the compiler knows the TMEM base is warp-uniform (UTCHMMA / LDTM take it
+  // from a uniform register)
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
 
   const int taps_per_a = p.halo ? taps : 1;            // taps served by one A stage
   const int a_groups = p.halo ? p.n_cblk : taps * p.n_cblk;
@@ -192,11 +194,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer: ONE thread.
-    // The loop is latency-bound on this thread's instruction stream (ncu: the producers wait on empty
-    // slots, this warp never waits for data), so everything invariant is hoisted and each barrier
-    // round-trip covers tb taps x 4 MMAs.
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer.
+    // The whole warp walks the loops so every counter / address stays warp-uniform (UTCHMMA takes its
+    // descriptors, TMEM address and predicate from UNIFORM registers; anything the compiler cannot prove
+    // uniform costs an ELECT / R2UR.BROADCAST waterfall per MMA — measured ~100 cycles each, which bounded
+    // the N=64/128 layers).  One elected lane issues the MMAs and the commits.
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc = umma_idesc_f16_f32(kBM, BN);
       const uint32_t a_hi = desc_hi(p.halo ? static_cast<uint32_t>(p.pitch_rows) * 128u : 1024u);
       const uint32_t b_hi = desc_hi(1024u);
@@ -204,6 +208,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const uint32_t b_lo0 = desc_lo(smem_u32(smem_b));
       const uint32_t a_step = static_cast<uint32_t>(p.a_stage_bytes) >> 4;
       const uint32_t b_step = static_cast<uint32_t>(b_stage_bytes) >> 4;
+      const uint32_t pitch8 = p.halo ? static_cast<uint32_t>(p.pitch_rows) * 8u : 0u;   // 16-byte units per halo row
+      const uint32_t kx8 = p.halo ? 8u : 0u;
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
@@ -216,25 +222,31 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         for (int g = 0; g < a_groups; ++g) {
           mbar_wait(&a_full[sa], pa);
           const uint32_t a_lo = a_lo0 + sa * a_step;
-          int t = 0;
+          int t = 0, kx = 0;
+          uint32_t row_off = 0, tap_off = 0;     // uniform: (ky*pitch + kx) * 8
           for (int bg = 0; bg < b_groups; ++bg) {
             const int nt = min(p.tb, taps_per_a - t);
             mbar_wait(&b_full[sb], pb);
             tc_fence_after_sync();
             uint32_t b_lo = b_lo0 + sb * b_step;
             for (int tt = 0; tt < nt; ++tt, ++t, b_lo += (kBBytes >> 4)) {
-              const uint32_t al = a_lo + tap_off[t];
+              const uint32_t al = a_lo + tap_off;
+              if (leader) {
 #pragma unroll
-              for (int k = 0; k < kBK / 16; ++k) {   // +32 bytes (2 x 16-byte units) per K=16 slice
-                umma_f16_ss(d_tmem, desc64(al + 2u * k, a_hi), desc64(b_lo + 2u * k, b_hi), idesc, accum);
-                accum = 1;
+                for (int k = 0; k < kBK / 16; ++k)   // +32 bytes (2 x 16-byte units) per K=16 slice
+                  umma_f16_ss(d_tmem, desc64(al + 2u * k, a_hi), desc64(b_lo + 2u * k, b_hi), idesc,
+                              (k == 0) ? accum : 1u);
               }
+              accum = 1;
+              if (++kx == p.kw) { kx = 0; row_off += pitch8; tap_off = row_off; } else { tap_off += kx8; }
             }
-            umma_commit(&b_empty[sb]);  // frees the weight slot when these MMAs retire
+            if (leader) umma_commit(&b_empty[sb]);  // frees the weight slot when these MMAs retire
             if (++sb == p.n_b_stages) { sb = 0; pb ^= 1u; }
           }
-          umma_commit(&a_empty[sa]);                             // halo / tap tile fully consumed
-          if (g == a_groups - 1) umma_commit(&tmem_full[acc]);   // accumulator complete -> epilogue
+          if (leader) {
+            umma_commit(&a_empty[sa]);                             // halo / tap tile fully consumed
+            if (g == a_groups - 1) umma_commit(&tmem_full[acc]);   // accumulator complete -> epilogue
+          }
           if (++sa == p.n_a_stages) { sa = 0; pa ^= 1u; }
         }
       }

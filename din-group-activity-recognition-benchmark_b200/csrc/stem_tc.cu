@@ -30,6 +30,8 @@ struct StemParams {
   int n, h, w_in, oh, ow, c_out, kh, kw, stride, pad, relu, prep;
   int k_real, k_pad;
   int strips_per_row;     // ceil(ow / 128)
+  int patch_w;            // input columns one strip needs: 127*stride + kw
+  int patch_pitch;        // patch_w rounded up to odd (bank spread for strided reads)
   int num_tiles;          // n * oh * strips_per_row
 };
 
@@ -61,10 +63,11 @@ stem_tc_kernel(const StemParams p) {
   uint8_t* a_s = smem;                                // 16 groups
   uint8_t* b_s = a_s + 16 * sbo;                      // COUT/8 groups
   uint8_t* scratch = b_s + (COUT / 8) * sbo;          // 4 warps x 32 x 80 B
-  int* koff = reinterpret_cast<int*>(scratch + 4 * 32 * kEpiPitch);   // [k_pad] packed (c, ky, kx) or -1
+  int* koff = reinterpret_cast<int*>(scratch + 4 * 32 * kEpiPitch);   // [k_pad] offset into the patch, or -1
   float* bias_s = reinterpret_cast<float*>(koff + kStemMaxK);         // [COUT]
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(bias_s + 64);
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  float* patch = reinterpret_cast<float*>(tmem_ptr_smem + 4);         // [3][kh][patch_pitch] prep'd input rows
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -75,7 +78,7 @@ stem_tc_kernel(const StemParams p) {
       const int c = k / (p.kh * p.kw);
       const int r = k - c * p.kh * p.kw;
       const int ky = r / p.kw, kx = r - ky * p.kw;
-      v = (c << 16) | (ky << 8) | kx;
+      v = (c * p.kh + ky) * p.patch_pitch + kx;
     }
     koff[k] = v;
   }
@@ -100,7 +103,7 @@ stem_tc_kernel(const StemParams p) {
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);   // warp-uniform for UTCHMMA / LDTM
   const uint32_t idesc = umma_idesc_f16_f32(128, COUT);
   const size_t plane = static_cast<size_t>(p.h) * p.w_in;
 
@@ -112,41 +115,59 @@ stem_tc_kernel(const StemParams p) {
     const int img = row / p.oh;
     const int ox = strip * 128 + tid;
     const float* xi = p.x + static_cast<size_t>(img) * 3 * plane;
-    const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
+    const int iy0 = oy * p.stride - p.pad;
+    (void)ox;
 
-    // ---- im2col row of this thread's pixel -> A tile
-    for (int kc = 0; kc < p.k_pad / 8; ++kc) {
-      __align__(16) __half hv[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int ko = koff[kc * 8 + e];
+    // ---- stage the strip's input patch: coalesced along x, prep_images applied once per input element,
+    //      zero where the convolution pads
+    {
+      const int rows = 3 * p.kh;
+      const int gx0 = strip * 128 * p.stride - p.pad;
+      for (int i = tid; i < rows * p.patch_w; i += kStemThreads) {
+        const int rr = i / p.patch_w, px = i - rr * p.patch_w;
+        const int c = rr / p.kh, ky = rr - c * p.kh;
+        const int gy = iy0 + ky, gx = gx0 + px;
         float v = 0.0f;
-        if (ko >= 0 && ox < p.ow) {
-          const int c = ko >> 16, ky = (ko >> 8) & 0xff, kx = ko & 0xff;
-          const int gy = iy0 + ky, gx = ix0 + kx;
-          if (gy >= 0 && gy < p.h && gx >= 0 && gx < p.w_in) {
-            v = __ldg(xi + c * plane + static_cast<size_t>(gy) * p.w_in + gx);
-            // prep_images, the reference's three roundings (utils.py:14-17): div, sub, mul
-            if (p.prep) v = __fmul_rn(__fsub_rn(__fdiv_rn(v, 255.0f), 0.5f), 2.0f);
-          }
+        if (gy >= 0 && gy < p.h && gx >= 0 && gx < p.w_in) {
+          v = __ldg(xi + c * plane + static_cast<size_t>(gy) * p.w_in + gx);
+          // prep_images (utils.py:14-17): (x/255 - 0.5)*2; the product by 1/255 differs from the division by
+          // at most 1 ulp(fp32), far below the fp16 rounding applied next
+          if (p.prep) v = (v * (1.0f / 255.0f) - 0.5f) * 2.0f;
         }
-        hv[e] = __float2half_rn(v);
+        patch[rr * p.patch_pitch + px] = v;
       }
-      *reinterpret_cast<uint4*>(a_s + canon_off(tid, kc, sbo)) = *reinterpret_cast<const uint4*>(hv);
+    }
+    __syncthreads();
+    // ---- im2col row of this thread's pixel -> A tile (canonical UMMA layout)
+    {
+      const float* prow = patch + tid * p.stride;
+      for (int kc = 0; kc < p.k_pad / 8; ++kc) {
+        __align__(16) __half hv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int ko = koff[kc * 8 + e];
+          hv[e] = __float2half_rn(ko >= 0 ? prow[ko] : 0.0f);
+        }
+        *reinterpret_cast<uint4*>(a_s + canon_off(tid, kc, sbo)) = *reinterpret_cast<const uint4*>(hv);
+      }
     }
     fence_proxy_async_smem();
     __syncthreads();
 
-    // ---- MMA: one thread, K_pad/16 instructions; each consumes two adjacent 16-byte K chunks
-    if (tid == 0) {
+    // ---- MMA: warp 0 walks the loop uniformly, one elected lane issues K_pad/16 instructions; each consumes
+    //      two adjacent 16-byte K chunks
+    if (warp == 0) {
       tc_fence_after_sync();
       const uint32_t a_addr = smem_u32(a_s), b_addr = smem_u32(b_s);
-      for (int ks = 0; ks < p.k_pad / 16; ++ks) {
-        const uint64_t ad = desc_noswz(a_addr + ks * 256, 128, sbo);
-        const uint64_t bd = desc_noswz(b_addr + ks * 256, 128, sbo);
-        umma_f16_ss(tmem_base, ad, bd, idesc, ks > 0 ? 1u : 0u);
+      if (elect_one()) {
+        for (int ks = 0; ks < p.k_pad / 16; ++ks) {
+          const uint64_t ad = desc_noswz(a_addr + ks * 256, 128, sbo);
+          const uint64_t bd = desc_noswz(b_addr + ks * 256, 128, sbo);
+          umma_f16_ss(tmem_base, ad, bd, idesc, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(mma_bar);
       }
-      umma_commit(mma_bar);
+      __syncwarp();
     }
     mbar_wait(mma_bar, phase);
     phase ^= 1u;
@@ -210,11 +231,14 @@ int din_stem_tc_launch(const float* x, const float* w, const float* bias, void* 
   p.k_real = 3 * kh * kw;
   p.k_pad = (p.k_real + 15) / 16 * 16;
   p.strips_per_row = (p.ow + 127) / 128;
+  p.patch_w = 127 * stride + kw;
+  p.patch_pitch = p.patch_w | 1;
   const long long tiles = static_cast<long long>(n) * p.oh * p.strips_per_row;
   if (tiles >= INT32_MAX) return din_set_error(DIN_ERR_INVALID_ARG, "din_stem_conv_nchw_f32: too many tiles");
   p.num_tiles = static_cast<int>(tiles);
   const int sbo = p.k_pad * 16;
-  const size_t smem = 128 + static_cast<size_t>(16 + c_out / 8) * sbo + 4 * 32 * kEpiPitch + kStemMaxK * 4 + 64 * 4 + 32;
+  const size_t smem = 128 + static_cast<size_t>(16 + c_out / 8) * sbo + 4 * 32 * kEpiPitch + kStemMaxK * 4 + 64 * 4 + 32 +
+                      static_cast<size_t>(3) * kh * p.patch_pitch * 4;
   const int sms = din_num_sms();
   int per_sm = static_cast<int>((200 * 1024) / smem);
   const int tmem_limit = 512 / (c_out < 32 ? 32 : c_out);
