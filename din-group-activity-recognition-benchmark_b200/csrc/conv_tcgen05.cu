@@ -22,9 +22,9 @@
 // B = BN rows x 64 columns of the packed weight [c_out][tap][c_in] (K-major): one 2-D TMA box per
 // (block, tap), on its own ring so weights stream while a halo is reused.
 //
-// A persistent, warp-specialised CTA per SM (256 threads): warp 0 = A producer, warp 2 = B producer,
+// A persistent, warp-specialised CTA per SM (384 threads): warp 0 = A producer, warp 2 = B producer,
 // warp 1 = MMA issuer (one lane; tcgen05.commit frees smem stages / publishes the accumulator),
-// warps 4..7 = epilogue (TMEM -> registers -> bias / residual / ReLU / 2x2 max-pool -> global).  The
+// warps 4..11 = epilogue (TMEM -> registers -> bias / residual / ReLU / 2x2 max-pool -> global).  The
 // accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
 #include <cstdlib>
 
@@ -34,7 +34,26 @@ namespace {
 
 using namespace din;
 
+// Division by a runtime constant without the ~100-cycle integer-divide sequence (Granlund-Montgomery,
+// round-up variant): q = (umulhi(x, mul) + x) >> shr, exact for x < 2^31.
+struct FastDiv {
+  uint32_t mul, shr, d;
+};
+__host__ inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  uint32_t l = 0;
+  while ((1u << l) < d) ++l;
+  f.shr = l;
+  f.mul = static_cast<uint32_t>(((static_cast<uint64_t>(1) << 32) * ((static_cast<uint64_t>(1) << l) - d)) / d + 1);
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t x, const FastDiv& f) {
+  return (__umulhi(x, f.mul) + x) >> f.shr;
+}
+
 struct ConvKParams {
+  FastDiv fd_ntn, fd_tpi, fd_tx;   // n_tiles_n, tiles_per_img, tiles_x
   int oh, ow;                 // conv output extent (before the optional fused pool)
   int c_out, y_c_stride;
   int tiles_x, tiles_per_img;
@@ -61,8 +80,9 @@ struct ConvKParams {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;                    // fp16 elements per K step = one 128-byte swizzle row
-constexpr int kNumThreads = 256;
-constexpr int kSmemBudget = 200 * 1024;    // operand rings; barriers and alignment slack come on top
+constexpr int kNumThreads = 384;            // 4 role warps + 8 epilogue warps
+constexpr int kNumEpiWarps = 8;
+constexpr int kSmemBudget = 192 * 1024;    // operand rings; barriers and alignment slack come on top
 constexpr int kMaxStages = 16;
 
 constexpr int kEpiPitch = 80;             // bytes per pixel row in the epilogue transpose scratch (64 + 16 pad)
@@ -93,8 +113,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint8_t* smem_a = smem;
   const int b_stage_bytes = p.tb * kBBytes;
   uint8_t* smem_b = smem + p.n_a_stages * p.a_stage_bytes;
-  uint8_t* epi_scratch = smem_b + p.n_b_stages * b_stage_bytes;                 // 4 warps x 2560 B
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_scratch + 4 * kEpiScratch);
+  uint8_t* epi_scratch = smem_b + p.n_b_stages * b_stage_bytes;                 // 8 warps x 2560 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_scratch + kNumEpiWarps * kEpiScratch);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kMaxStages;
   uint64_t* b_full = a_empty + kMaxStages;
@@ -114,7 +134,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < p.n_a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < p.n_b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 32 * kNumEpiWarps); }
     fence_mbar_init();
   }
   if (warp == 3) {
@@ -126,7 +146,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (warp >= 4) {
     // the epilogue's bias lives in shared memory: broadcast LDS instead of eight serialised global loads
     // per 32-column chunk (ncu: those loads' latency was the epilogue's critical path)
-    for (int c = threadIdx.x - 128; c < p.n_tiles_n * BN; c += 128)
+    for (int c = threadIdx.x - 128; c < p.n_tiles_n * BN; c += 32 * kNumEpiWarps)
       bias_s[c] = (p.bias != nullptr && c < p.c_out) ? __ldg(p.bias + c) : 0.0f;
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr_smem);
@@ -147,10 +167,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles_n;
-        const int img = mt / p.tiles_per_img;
+        const int mt = fdiv(tile, p.fd_ntn);
+        const int img = fdiv(mt, p.fd_tpi);
         const int r = mt - img * p.tiles_per_img;
-        const int tyi = r / p.tiles_x;
+        const int tyi = fdiv(r, p.fd_tx);
         const int txi = r - tyi * p.tiles_x;
         const int ix0 = txi * p.tw * p.stride - p.pad_w;
         const int iy0 = tyi * p.th * p.stride - p.pad_h;
@@ -176,7 +196,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int n0 = (tile % p.n_tiles_n) * BN;
+        const int n0 = (tile - static_cast<int>(fdiv(tile, p.fd_ntn)) * p.n_tiles_n) * BN;
         for (int g = 0; g < a_groups; ++g) {
           // HALO: g = channel block, taps stream in groups of tb.  TAP: g = tap * n_cblk + cb, one tap.
           const int kbase = p.halo ? g * kBK : ((g / p.n_cblk) * p.c_in + (g % p.n_cblk) * kBK);
@@ -252,9 +272,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue (4 warps, 128 lanes)
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    uint8_t* scratch = epi_scratch + q * kEpiScratch;
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    // warp e = warp - 4: TMEM lane quadrant q = e & 3 (a warp may only touch lanes 32*(warp%4)..+31), and
+    // the two warps of a quadrant split the tile's 32-column chunks (even / odd) between them.
+    const int q = warp & 3;
+    const int chunk_sel = (warp - 4) >> 2;
+    uint8_t* scratch = epi_scratch + (warp - 4) * kEpiScratch;
     // Store side of the transpose: after the scratch round-trip, lane l writes 16-byte unit (l & 3) of
     // pixel slot (l >> 2) + 8*k (k = 0..3) — i.e. four lanes write one pixel's 64 contiguous bytes, so
     // every global store instruction covers full 32-byte sectors (no partial-sector read-modify-write).
@@ -276,11 +299,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
-      const int nt = tile % p.n_tiles_n;
-      const int mt = tile / p.n_tiles_n;
-      const int img = mt / p.tiles_per_img;
+      const int mt = fdiv(tile, p.fd_ntn);
+      const int nt = tile - mt * p.n_tiles_n;
+      const int img = fdiv(mt, p.fd_tpi);
       const int r = mt - img * p.tiles_per_img;
-      const int tyi = r / p.tiles_x;
+      const int tyi = fdiv(r, p.fd_tx);
       const int txi = r - tyi * p.tiles_x;
       const int n0 = nt * BN;
       // own pixel (residual / fp32 path) and the pixels this lane stores after the transpose
@@ -308,14 +331,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
       uint32_t v[32];
-      tmem_ld_32x32b_x32(taddr, v);
+      tmem_ld_32x32b_x32(taddr + 32 * chunk_sel, v);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 32 * chunk_sel; c0 < BN; c0 += 64) {
         tmem_ld_wait();
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (c0 + 32 < BN) tmem_ld_32x32b_x32(taddr + c0 + 32, v);   // prefetch the next chunk's accumulators
+        if (c0 + 64 < BN) tmem_ld_32x32b_x32(taddr + c0 + 64, v);   // prefetch this warp's next chunk
         const int col0 = n0 + c0;
         if (col0 >= p.c_out) continue;   // warp-uniform
         {
@@ -413,7 +436,7 @@ int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvKParams&
   DIN_CHECK_CUDA(cudaGetDevice(&dev));
   if (attr_dev != dev) {
     DIN_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kSmemBudget + 4 * kEpiScratch + 4096 + 8192));
+                                        kSmemBudget + kNumEpiWarps * kEpiScratch + 4096 + 8192));
     attr_dev = dev;
   }
   conv_igemm_kernel<BN><<<grid, kNumThreads, smem, st>>>(ta, tb, p);
@@ -524,6 +547,7 @@ extern "C" int din_conv2d_nhwc_f16(const DinConvDesc* d, const void* x, const vo
   p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad_h = d->pad_h; p.pad_w = d->pad_w;
   p.c_in = d->c_in; p.n_cblk = d->c_in / kBK;
   p.relu = d->relu; p.out_f32 = d->out_f32; p.pool2 = d->pool2;
+  p.fd_ntn = make_fastdiv(p.n_tiles_n); p.fd_tpi = make_fastdiv(p.tiles_per_img); p.fd_tx = make_fastdiv(p.tiles_x);
   p.bias = bias; p.residual = static_cast<const __half*>(residual); p.y = y;
 
   // A staging geometry
@@ -566,7 +590,7 @@ extern "C" int din_conv2d_nhwc_f16(const DinConvDesc* d, const void* x, const vo
   DIN_CHECK_ARG(p.n_a_stages >= 2 && p.n_b_stages >= 2, "din_conv2d_nhwc_f16: filter %dx%d does not fit shared memory",
                 d->kh, d->kw);
   const size_t smem = static_cast<size_t>(p.n_a_stages) * p.a_stage_bytes +
-                      static_cast<size_t>(p.n_b_stages) * p.tb * b_bytes + 4 * kEpiScratch + 1024 /*align*/ +
+                      static_cast<size_t>(p.n_b_stages) * p.tb * b_bytes + kNumEpiWarps * kEpiScratch + 1024 /*align*/ +
                       (4 * kMaxStages + 4) * 8 + 16 + 64 * 4 /*tap offsets*/ +
                       static_cast<size_t>(p.n_tiles_n) * bn * 4 /*bias*/;
 

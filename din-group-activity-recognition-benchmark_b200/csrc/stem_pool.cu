@@ -175,10 +175,14 @@ extern "C" int din_stem_conv_nchw_f32(const float* x, const float* w, const floa
   DIN_CHECK_ARG(oh > 0 && ow > 0, "din_stem_conv_nchw_f32: empty output");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   {
-    // production path: im2col-in-smem + tcgen05.mma (stem_tc.cu).  DIN_STEM_SIMT=1 selects the CUDA-core
-    // direct convolution below (kept for A/B measurements only).
+    // production path: im2col-in-smem + tcgen05.mma (stem_tc.cu) for the three backbone stems.  Other
+    // filter geometries (and DIN_STEM_SIMT=1, for A/B measurements) use the generic CUDA-core direct
+    // convolution below — still a CUDA kernel of this library, not a fallback to another backend.
     const char* e = std::getenv("DIN_STEM_SIMT");
-    if (!(e && e[0] == '1')) return din_stem_tc_launch(x, w, bias, y, n, h, w_in, c_out, kh, kw, stride, pad, relu, prep, st);
+    if (!(e && e[0] == '1')) {
+      const int rc = din_stem_tc_launch(x, w, bias, y, n, h, w_in, c_out, kh, kw, stride, pad, relu, prep, st);
+      if (rc != DIN_ERR_UNSUPPORTED) return rc;
+    }
   }
   const int K = 3 * kh * kw;
   const int in_th = (kStemTileH - 1) * stride + kh;

@@ -5,16 +5,19 @@
 //
 // The layer is HBM-bound (VGG: 11 MB fp32 in, 118 MB fp16 out per frame, 3.2 GFLOP) but as a CUDA-core
 // direct conv it cost 14.5 ms of a 61 ms step.  Here K = 3*kh*kw (27 / 147) is padded to a multiple of 16
-// and each CTA turns a strip of 128 output pixels into one M=128 UMMA tile:
-//   * 128 threads = 128 pixels: each thread gathers its K input values from the NCHW fp32 image (coalesced
-//     along x), applies prep_images with the reference's three roundings, converts to fp16 and writes its
-//     row of the A tile straight into the canonical no-swizzle K-major UMMA layout (8x16-byte core
-//     matrices; LBO = 128 B between K chunks, SBO = K_pad*16 B between 8-row groups);
+// and each CTA turns a strip of 128 output pixels of one image row into one M=128 UMMA tile:
+//   * the strip's input patch (3 x kh rows x (127*stride + kw) columns) is staged in shared memory with
+//     coalesced loads, all in flight at once, prep_images applied once per input element, the value that
+//     preps to 0 where the convolution pads;
+//   * 128 threads = 128 pixels: each thread converts its K patch values to fp16 and writes its row of the
+//     A tile straight into the canonical no-swizzle K-major UMMA layout (8 x 16-byte core matrices;
+//     LBO = 128 B between K chunks, SBO = K_pad*16 B between 8-row groups); filter geometry is a template
+//     parameter so every offset is an immediate (runtime divisions made the first version 5x slower);
 //   * the weights (BN scale folded) are laid out the same way once per CTA;
-//   * one thread issues K_pad/16 tcgen05.mma (M=128, N=c_out, fp32 accumulate in TMEM);
+//   * one elected lane issues K_pad/16 tcgen05.mma (M=128, N=c_out, fp32 accumulate in TMEM);
 //   * the same 128 threads read the accumulator back (tcgen05.ld), add bias, ReLU, convert, transpose
 //     through shared memory and write NHWC fp16 with full-sector stores.
-// Persistent CTAs (several per SM, 64 TMEM columns each) hide the per-tile latency chain.
+// Persistent CTAs (several per SM, <= 64 TMEM columns each) hide the per-tile latency chain.
 #include "din_common.cuh"
 
 namespace {
@@ -22,21 +25,33 @@ namespace {
 using namespace din;
 
 constexpr int kStemThreads = 128;
-constexpr int kStemMaxK = 160;           // 7x7x3 = 147 -> 160
 constexpr int kEpiPitch = 80;            // bytes per pixel row in the store-transpose scratch
 
 struct StemParams {
   const float* x; const float* w; const float* bias; __half* y;
-  int n, h, w_in, oh, ow, c_out, kh, kw, stride, pad, relu, prep;
-  int k_real, k_pad;
+  int n, h, w_in, oh, ow, pad, relu, prep;
   int strips_per_row;     // ceil(ow / 128)
-  int patch_w;            // input columns one strip needs: 127*stride + kw
-  int patch_pitch;        // patch_w rounded up to odd (bank spread for strided reads)
   int num_tiles;          // n * oh * strips_per_row
+  uint32_t fd_mul, fd_shr;  // fast division by strips_per_row
+  uint32_t fo_mul, fo_shr;  // fast division by oh
 };
 
-// canonical no-swizzle K-major layout: element (row r, k) of an [rows x k_pad] operand
-__device__ __forceinline__ uint32_t canon_off(int r, int kc /*16-byte chunk*/, int sbo_bytes) {
+template <int COUT, int KH, int KW, int STRIDE>
+struct StemCfg {
+  static constexpr int kReal = 3 * KH * KW;
+  static constexpr int kPad = (kReal + 15) / 16 * 16;
+  static constexpr int kSbo = kPad * 16;                      // bytes between 8-row groups
+  static constexpr int kPatchW = 127 * STRIDE + KW;
+  static constexpr int kPitch = kPatchW | 1;                  // odd pitch: bank spread for strided reads
+  static constexpr int kRows = 3 * KH;
+  static constexpr int kLoadsPerRow = (kPatchW + kStemThreads - 1) / kStemThreads;
+  static constexpr int kTmemCols = COUT < 32 ? 32 : COUT;
+  static constexpr size_t kSmem = 128 + static_cast<size_t>(16 + COUT / 8) * kSbo + 4 * 32 * kEpiPitch + 64 * 4 + 32 +
+                                  static_cast<size_t>(kRows) * kPitch * 4;
+};
+
+// canonical no-swizzle K-major layout: 16-byte chunk kc of row r of an [rows x k_pad] operand
+__device__ __forceinline__ uint32_t canon_off(int r, int kc, int sbo_bytes) {
   return static_cast<uint32_t>((r >> 3) * sbo_bytes + kc * 128 + (r & 7) * 16);
 }
 
@@ -49,120 +64,127 @@ __device__ __forceinline__ uint64_t desc_noswz(uint32_t addr, uint32_t lbo_bytes
   return d;
 }
 
-__device__ __forceinline__ void tmem_ld_32x32b_x32_stem(uint32_t taddr, uint32_t (&v)[32]) {
-  tmem_ld_32x32b_x32(taddr, v);
-}
-
-template <int COUT>  // 64 or 32
+template <int COUT, int KH, int KW, int STRIDE>
 __global__ void __launch_bounds__(kStemThreads)
 stem_tc_kernel(const StemParams p) {
-  constexpr int kTmemCols = COUT < 32 ? 32 : COUT;
+  using Cfg = StemCfg<COUT, KH, KW, STRIDE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  const int sbo = p.k_pad * 16;                       // bytes between 8-row groups
-  uint8_t* a_s = smem;                                // 16 groups
-  uint8_t* b_s = a_s + 16 * sbo;                      // COUT/8 groups
-  uint8_t* scratch = b_s + (COUT / 8) * sbo;          // 4 warps x 32 x 80 B
-  int* koff = reinterpret_cast<int*>(scratch + 4 * 32 * kEpiPitch);   // [k_pad] offset into the patch, or -1
-  float* bias_s = reinterpret_cast<float*>(koff + kStemMaxK);         // [COUT]
+  uint8_t* a_s = smem;                                      // 16 row groups
+  uint8_t* b_s = a_s + 16 * Cfg::kSbo;                      // COUT/8 row groups
+  uint8_t* scratch = b_s + (COUT / 8) * Cfg::kSbo;          // 4 warps x 32 x 80 B
+  float* bias_s = reinterpret_cast<float*>(scratch + 4 * 32 * kEpiPitch);   // [COUT]
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(bias_s + 64);
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(mma_bar + 1);
-  float* patch = reinterpret_cast<float*>(tmem_ptr_smem + 4);         // [3][kh][patch_pitch] prep'd input rows
+  float* patch = reinterpret_cast<float*>(tmem_ptr_smem + 4);               // [3*KH][kPitch] prep'd input rows
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  // ---- one-time setup: tap table, weights in UMMA layout, bias, barrier, TMEM
-  for (int k = tid; k < p.k_pad; k += kStemThreads) {
-    int v = -1;
-    if (k < p.k_real) {
-      const int c = k / (p.kh * p.kw);
-      const int r = k - c * p.kh * p.kw;
-      const int ky = r / p.kw, kx = r - ky * p.kw;
-      v = (c * p.kh + ky) * p.patch_pitch + kx;
-    }
-    koff[k] = v;
-  }
-  for (int i = tid; i < COUT * (p.k_pad / 8); i += kStemThreads) {
-    const int o = i / (p.k_pad / 8), kc = i - o * (p.k_pad / 8);
+  // ---- one-time setup: weights in UMMA layout, bias, barrier, TMEM
+  for (int i = tid; i < COUT * (Cfg::kPad / 8); i += kStemThreads) {
+    const int o = i / (Cfg::kPad / 8), kc = i % (Cfg::kPad / 8);
     __align__(16) __half hv[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int k = kc * 8 + e;
       // OIHW [c_out][3][kh][kw] flattened == [c_out][k] with k = (c*kh + ky)*kw + kx
-      hv[e] = __float2half_rn(k < p.k_real ? __ldg(p.w + static_cast<size_t>(o) * p.k_real + k) : 0.0f);
+      hv[e] = __float2half_rn(k < Cfg::kReal ? __ldg(p.w + static_cast<size_t>(o) * Cfg::kReal + k) : 0.0f);
     }
-    *reinterpret_cast<uint4*>(b_s + canon_off(o, kc, sbo)) = *reinterpret_cast<const uint4*>(hv);
+    *reinterpret_cast<uint4*>(b_s + canon_off(o, kc, Cfg::kSbo)) = *reinterpret_cast<const uint4*>(hv);
   }
   if (tid < COUT) bias_s[tid] = p.bias ? __ldg(p.bias + tid) : 0.0f;
   if (tid == 0) {
     mbar_init(mma_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc<kTmemCols>(tmem_ptr_smem);
+  if (warp == 0) tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
   fence_proxy_async_smem();       // generic-proxy smem writes (b_s) -> visible to the tensor core (async proxy)
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);   // warp-uniform for UTCHMMA / LDTM
-  const uint32_t idesc = umma_idesc_f16_f32(128, COUT);
+  constexpr uint32_t idesc = umma_idesc_f16_f32(128, COUT);
   const size_t plane = static_cast<size_t>(p.h) * p.w_in;
+  const float pad_val = p.prep ? 127.5f : 0.0f;                               // preps to exactly 0
 
   uint32_t phase = 0;
   for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-    const int strip = tile % p.strips_per_row;
-    const int row = tile / p.strips_per_row;
-    const int oy = row % p.oh;
-    const int img = row / p.oh;
-    const int ox = strip * 128 + tid;
+    const int row = (__umulhi(tile, p.fd_mul) + tile) >> p.fd_shr;            // tile / strips_per_row
+    const int strip = tile - row * p.strips_per_row;
+    const int img = (__umulhi(row, p.fo_mul) + row) >> p.fo_shr;              // row / oh
+    const int oy = row - img * p.oh;
     const float* xi = p.x + static_cast<size_t>(img) * 3 * plane;
-    const int iy0 = oy * p.stride - p.pad;
-    (void)ox;
+    const int iy0 = oy * STRIDE - p.pad;
+    const int gx0 = strip * 128 * STRIDE - p.pad;
 
-    // ---- stage the strip's input patch: coalesced along x, prep_images applied once per input element,
-    //      zero where the convolution pads
+    // ---- stage the strip's input patch (all loads issued before the first use)
     {
-      const int rows = 3 * p.kh;
-      const int gx0 = strip * 128 * p.stride - p.pad;
-      for (int i = tid; i < rows * p.patch_w; i += kStemThreads) {
-        const int rr = i / p.patch_w, px = i - rr * p.patch_w;
-        const int c = rr / p.kh, ky = rr - c * p.kh;
-        const int gy = iy0 + ky, gx = gx0 + px;
-        float v = 0.0f;
-        if (gy >= 0 && gy < p.h && gx >= 0 && gx < p.w_in) {
-          v = __ldg(xi + c * plane + static_cast<size_t>(gy) * p.w_in + gx);
-          // prep_images (utils.py:14-17): (x/255 - 0.5)*2; the product by 1/255 differs from the division by
-          // at most 1 ulp(fp32), far below the fp16 rounding applied next
-          if (p.prep) v = (v * (1.0f / 255.0f) - 0.5f) * 2.0f;
+      float v[Cfg::kRows][Cfg::kLoadsPerRow];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int ky = 0; ky < KH; ++ky) {
+          const int gy = iy0 + ky;
+          const bool row_ok = gy >= 0 && gy < p.h;
+          const float* src = xi + c * plane + static_cast<size_t>(row_ok ? gy : 0) * p.w_in;
+#pragma unroll
+          for (int u = 0; u < Cfg::kLoadsPerRow; ++u) {
+            const int px = tid + u * kStemThreads;
+            const int gx = gx0 + px;
+            v[c * KH + ky][u] = (row_ok && px < Cfg::kPatchW && gx >= 0 && gx < p.w_in) ? __ldg(src + gx) : pad_val;
+          }
         }
-        patch[rr * p.patch_pitch + px] = v;
+      }
+#pragma unroll
+      for (int r = 0; r < Cfg::kRows; ++r) {
+#pragma unroll
+        for (int u = 0; u < Cfg::kLoadsPerRow; ++u) {
+          const int px = tid + u * kStemThreads;
+          // prep_images (utils.py:14-17): (x/255 - 0.5)*2; the product by 1/255 differs from the division
+          // by at most 1 ulp(fp32), far below the fp16 rounding applied next
+          if (px < Cfg::kPatchW)
+            patch[r * Cfg::kPitch + px] = p.prep ? (v[r][u] * (1.0f / 255.0f) - 0.5f) * 2.0f : v[r][u];
+        }
       }
     }
     __syncthreads();
-    // ---- im2col row of this thread's pixel -> A tile (canonical UMMA layout)
+    // ---- im2col row of this thread's pixel -> A tile (canonical UMMA layout); all offsets are immediates
     {
-      const float* prow = patch + tid * p.stride;
-      for (int kc = 0; kc < p.k_pad / 8; ++kc) {
-        __align__(16) __half hv[8];
+      const float* prow = patch + tid * STRIDE;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int ko = koff[kc * 8 + e];
-          hv[e] = __float2half_rn(ko >= 0 ? prow[ko] : 0.0f);
+      for (int kc = 0; kc < Cfg::kPad / 8; ++kc) {
+        __align__(16) __half2 hv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float f[2];
+#pragma unroll
+          for (int z = 0; z < 2; ++z) {
+            const int k = kc * 8 + 2 * e + z;
+            if (k < Cfg::kReal) {
+              const int c = k / (KH * KW), r = k % (KH * KW);
+              f[z] = prow[(c * KH + r / KW) * Cfg::kPitch + r % KW];
+            } else {
+              f[z] = 0.0f;
+            }
+          }
+          hv[e] = __floats2half2_rn(f[0], f[1]);
         }
-        *reinterpret_cast<uint4*>(a_s + canon_off(tid, kc, sbo)) = *reinterpret_cast<const uint4*>(hv);
+        *reinterpret_cast<uint4*>(a_s + canon_off(tid, kc, Cfg::kSbo)) = *reinterpret_cast<const uint4*>(hv);
       }
     }
     fence_proxy_async_smem();
     __syncthreads();
 
-    // ---- MMA: warp 0 walks the loop uniformly, one elected lane issues K_pad/16 instructions; each consumes
-    //      two adjacent 16-byte K chunks
+    // ---- MMA: warp 0, one elected lane issues K_pad/16 instructions; each consumes two adjacent 16-byte
+    //      K chunks (descriptors are warp-uniform)
     if (warp == 0) {
       tc_fence_after_sync();
       const uint32_t a_addr = smem_u32(a_s), b_addr = smem_u32(b_s);
       if (elect_one()) {
-        for (int ks = 0; ks < p.k_pad / 16; ++ks) {
-          const uint64_t ad = desc_noswz(a_addr + ks * 256, 128, sbo);
-          const uint64_t bd = desc_noswz(b_addr + ks * 256, 128, sbo);
+#pragma unroll
+        for (int ks = 0; ks < Cfg::kPad / 16; ++ks) {
+          const uint64_t ad = desc_noswz(a_addr + ks * 256, 128, Cfg::kSbo);
+          const uint64_t bd = desc_noswz(b_addr + ks * 256, 128, Cfg::kSbo);
           umma_f16_ss(tmem_base, ad, bd, idesc, ks > 0 ? 1u : 0u);
         }
         umma_commit(mma_bar);
@@ -177,10 +199,11 @@ stem_tc_kernel(const StemParams p) {
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
     uint8_t* sc = scratch + warp * 32 * kEpiPitch;
     const int unit = lane & 3;
-#pragma unroll 1
+    __half* yrow = p.y + ((static_cast<size_t>(img) * p.oh + oy) * p.ow) * COUT;
+#pragma unroll
     for (int c0 = 0; c0 < COUT; c0 += 32) {
       uint32_t v[32];
-      tmem_ld_32x32b_x32_stem(taddr + c0, v);
+      tmem_ld_32x32b_x32(taddr + c0, v);
       tmem_ld_wait();
       __half2 hh[16];
 #pragma unroll
@@ -200,26 +223,52 @@ stem_tc_kernel(const StemParams p) {
         const int sx = strip * 128 + warp * 32 + src;
         if (sx < p.ow) {
           const uint4 o = *reinterpret_cast<const uint4*>(sc + src * kEpiPitch + unit * 16);
-          __half* yp = p.y + ((static_cast<size_t>(img) * p.oh + oy) * p.ow + sx) * COUT + c0 + unit * 8;
-          *reinterpret_cast<uint4*>(yp) = o;
+          *reinterpret_cast<uint4*>(yrow + static_cast<size_t>(sx) * COUT + c0 + unit * 8) = o;
         }
       }
       __syncwarp();
     }
     tc_fence_before_sync();
-    __syncthreads();     // every warp has drained TMEM and a_s may be rebuilt
+    __syncthreads();     // every warp has drained TMEM; a_s and the patch may be rebuilt
   }
 
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) {
     tc_fence_after_sync();
-    tmem_dealloc<kTmemCols>(tmem_base);
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
+}
+
+void fastdiv(uint32_t d, uint32_t* mul, uint32_t* shr) {
+  uint32_t l = 0;
+  while ((1u << l) < d) ++l;
+  *shr = l;
+  *mul = static_cast<uint32_t>(((static_cast<uint64_t>(1) << 32) * ((static_cast<uint64_t>(1) << l) - d)) / d + 1);
+}
+
+template <int COUT, int KH, int KW, int STRIDE>
+int launch(StemParams& p, cudaStream_t st) {
+  using Cfg = StemCfg<COUT, KH, KW, STRIDE>;
+  const int sms = din_num_sms();
+  int per_sm = static_cast<int>((200 * 1024) / Cfg::kSmem);
+  const int tmem_limit = 512 / Cfg::kTmemCols;
+  if (per_sm > tmem_limit) per_sm = tmem_limit;
+  if (per_sm > 8) per_sm = 8;
+  if (per_sm < 1) per_sm = 1;
+  long long grid = static_cast<long long>(sms > 0 ? sms : 148) * per_sm;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  DIN_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel<COUT, KH, KW, STRIDE>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Cfg::kSmem)));
+  stem_tc_kernel<COUT, KH, KW, STRIDE><<<static_cast<int>(grid), kStemThreads, Cfg::kSmem, st>>>(p);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
 }
 
 }  // namespace
 
+// Returns DIN_ERR_UNSUPPORTED for filter geometries without a tensor-core instantiation (the caller then
+// uses the generic CUDA-core kernel in stem_pool.cu).
 int din_stem_tc_launch(const float* x, const float* w, const float* bias, void* y, int n, int h, int w_in,
                        int c_out, int kh, int kw, int stride, int pad, int relu, int prep, cudaStream_t st) {
   StemParams p{};
@@ -227,35 +276,15 @@ int din_stem_tc_launch(const float* x, const float* w, const float* bias, void* 
   p.n = n; p.h = h; p.w_in = w_in;
   p.oh = (h + 2 * pad - kh) / stride + 1;
   p.ow = (w_in + 2 * pad - kw) / stride + 1;
-  p.c_out = c_out; p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad; p.relu = relu; p.prep = prep;
-  p.k_real = 3 * kh * kw;
-  p.k_pad = (p.k_real + 15) / 16 * 16;
+  p.pad = pad; p.relu = relu; p.prep = prep;
   p.strips_per_row = (p.ow + 127) / 128;
-  p.patch_w = 127 * stride + kw;
-  p.patch_pitch = p.patch_w | 1;
   const long long tiles = static_cast<long long>(n) * p.oh * p.strips_per_row;
   if (tiles >= INT32_MAX) return din_set_error(DIN_ERR_INVALID_ARG, "din_stem_conv_nchw_f32: too many tiles");
   p.num_tiles = static_cast<int>(tiles);
-  const int sbo = p.k_pad * 16;
-  const size_t smem = 128 + static_cast<size_t>(16 + c_out / 8) * sbo + 4 * 32 * kEpiPitch + kStemMaxK * 4 + 64 * 4 + 32 +
-                      static_cast<size_t>(3) * kh * p.patch_pitch * 4;
-  const int sms = din_num_sms();
-  int per_sm = static_cast<int>((200 * 1024) / smem);
-  const int tmem_limit = 512 / (c_out < 32 ? 32 : c_out);
-  if (per_sm > tmem_limit) per_sm = tmem_limit;
-  if (per_sm > 8) per_sm = 8;
-  if (per_sm < 1) per_sm = 1;
-  long long grid = static_cast<long long>(sms > 0 ? sms : 148) * per_sm;
-  if (grid > tiles) grid = tiles;
-  if (c_out == 64) {
-    DIN_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(smem)));
-    stem_tc_kernel<64><<<static_cast<int>(grid), kStemThreads, smem, st>>>(p);
-  } else {
-    DIN_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(smem)));
-    stem_tc_kernel<32><<<static_cast<int>(grid), kStemThreads, smem, st>>>(p);
-  }
-  DIN_CHECK_CUDA(cudaGetLastError());
-  return DIN_OK;
+  fastdiv(static_cast<uint32_t>(p.strips_per_row), &p.fd_mul, &p.fd_shr);
+  fastdiv(static_cast<uint32_t>(p.oh), &p.fo_mul, &p.fo_shr);
+  if (c_out == 64 && kh == 3 && kw == 3 && stride == 1) return launch<64, 3, 3, 1>(p, st);   // VGG-16
+  if (c_out == 64 && kh == 7 && kw == 7 && stride == 2) return launch<64, 7, 7, 2>(p, st);   // ResNet-18
+  if (c_out == 32 && kh == 3 && kw == 3 && stride == 2) return launch<32, 3, 3, 2>(p, st);   // Inception-v3
+  return DIN_ERR_UNSUPPORTED;
 }

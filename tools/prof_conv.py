@@ -1,4 +1,4 @@
-"""Three representative VGG-16 conv launches for ncu (conv1_2+pool, conv3_1, conv4_2)."""
+"""Representative launches for ncu: VGG stem, conv1_2+pool, conv2_1, conv4_2."""
 import os
 import sys
 
@@ -10,7 +10,13 @@ from din_b200 import ops  # noqa: E402
 
 dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(0)
-CASES = [(4, 720, 1280, 64, 64, True), (8, 180, 320, 128, 256, False), (8, 90, 160, 512, 512, False)]
+img = torch.randint(0, 256, (4, 3, 720, 1280), generator=g).float().to(dev)
+w0 = (torch.randn(64, 3, 3, 3, generator=g) * 0.2).to(dev)
+b0 = torch.randn(64, generator=g).to(dev)
+for _ in range(3):
+    y0 = ops.stem_conv(img, w0, b0, stride=1, pad=1)
+torch.cuda.synchronize()
+CASES = [(4, 720, 1280, 64, 64, True), (8, 360, 640, 64, 128, False), (8, 90, 160, 512, 512, False)]
 for (n, h, w, ci, co, pool) in CASES:
     x = torch.randn(n, h, w, ci, generator=g).to(dev).half()
     wt = (torch.randn(co, ci, 3, 3, generator=g) * (2.0 / (ci * 9)) ** 0.5).to(dev)
