@@ -88,7 +88,9 @@ class MyInception_v3(_PlanBackbone):
 
     def forward(self, x):
         raw = ((x / 2.0) + 0.5) * 255.0
-        return [f.permute(0, 3, 1, 2).float() for f in self.forward_nhwc(raw)]
+        fm = self.forward_nhwc(raw)                       # multiscale map; channels [0, 288) = Mixed_5d
+        out1 = self._plan().last_out1                     # Mixed_6e before the upsample
+        return [fm[..., :288].permute(0, 3, 1, 2).float(), out1.permute(0, 3, 1, 2).float()]
 
 
 def _out_of_scope(name):

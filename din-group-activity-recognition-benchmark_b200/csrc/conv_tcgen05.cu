@@ -491,7 +491,7 @@ extern "C" int din_conv2d_nhwc_f16(const DinConvDesc* d, const void* x, const vo
   DIN_CHECK_ARG(d && x && w_packed && y, "din_conv2d_nhwc_f16: null pointer");
   DIN_CHECK_ARG(d->n > 0 && d->h > 0 && d->w > 0, "din_conv2d_nhwc_f16: bad extent n=%d h=%d w=%d", d->n, d->h,
                 d->w);
-  DIN_CHECK_ARG(d->c_in > 0 && d->c_in % kBK == 0, "din_conv2d_nhwc_f16: c_in=%d must be a multiple of 64",
+  DIN_CHECK_ARG(d->c_in > 0 && d->c_in % 8 == 0, "din_conv2d_nhwc_f16: c_in=%d must be a multiple of 8",
                 d->c_in);
   DIN_CHECK_ARG(d->x_c_stride >= d->c_in && d->x_c_stride % 8 == 0,
                 "din_conv2d_nhwc_f16: x_c_stride=%d must be >= c_in and a multiple of 8", d->x_c_stride);
@@ -539,13 +539,25 @@ extern "C" int din_conv2d_nhwc_f16(const DinConvDesc* d, const void* x, const vo
   while ((1 << p.tw_log2) < p.tw) ++p.tw_log2;
   p.tiles_x = (ow + p.tw - 1) / p.tw;
   p.tiles_per_img = p.tiles_x * ((oh + p.th - 1) / p.th);
-  const int bn = d->c_out > 128 ? 256 : (d->c_out > 64 ? 128 : 64);
+  // N tile: the variant that wastes the fewest MMA columns; ties go to the wider tile
+  int bn = 256;
+  {
+    const int cand[5] = {256, 192, 128, 96, 64};
+    int best_cost = INT32_MAX;
+    for (int i = 0; i < 5; ++i) {
+      const int cost = ((d->c_out + cand[i] - 1) / cand[i]) * cand[i];
+      if (cost < best_cost) { best_cost = cost; bn = cand[i]; }
+    }
+  }
   p.n_tiles_n = (d->c_out + bn - 1) / bn;
   const long long total_tiles = static_cast<long long>(d->n) * p.tiles_per_img * p.n_tiles_n;
   DIN_CHECK_ARG(total_tiles < INT32_MAX, "din_conv2d_nhwc_f16: too many tiles");
   p.num_tiles = static_cast<int>(total_tiles);
   p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad_h = d->pad_h; p.pad_w = d->pad_w;
-  p.c_in = d->c_in; p.n_cblk = d->c_in / kBK;
+  // K is blocked by 64 channels; a partial last block is zero-filled by the TMA unit on the activation side
+  // (tensor-map extent = the real c_in) and by the packed weight's zero columns on the weight side
+  p.n_cblk = (d->c_in + kBK - 1) / kBK;
+  p.c_in = p.n_cblk * kBK;
   p.relu = d->relu; p.out_f32 = d->out_f32; p.pool2 = d->pool2;
   p.fd_ntn = make_fastdiv(p.n_tiles_n); p.fd_tpi = make_fastdiv(p.tiles_per_img); p.fd_tx = make_fastdiv(p.tiles_x);
   p.bias = bias; p.residual = static_cast<const __half*>(residual); p.y = y;
@@ -607,7 +619,7 @@ extern "C" int din_conv2d_nhwc_f16(const DinConvDesc* d, const void* x, const vo
     if (rc != DIN_OK) return rc;
   }
   {
-    const uint64_t ktot = static_cast<uint64_t>(d->kh) * d->kw * d->c_in;
+    const uint64_t ktot = static_cast<uint64_t>(d->kh) * d->kw * p.c_in;   // packed with the padded c_in
     const uint64_t dims[2] = {ktot, static_cast<uint64_t>(d->c_out)};
     const uint64_t strides[2] = {2, ktot * 2};
     const uint32_t box[2] = {static_cast<uint32_t>(kBK), static_cast<uint32_t>(bn)};
@@ -622,7 +634,9 @@ extern "C" int din_conv2d_nhwc_f16(const DinConvDesc* d, const void* x, const vo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (bn) {
     case 256: return launch_conv<256>(ta, tb, p, grid, smem, st);
+    case 192: return launch_conv<192>(ta, tb, p, grid, smem, st);
     case 128: return launch_conv<128>(ta, tb, p, grid, smem, st);
+    case 96: return launch_conv<96>(ta, tb, p, grid, smem, st);
     default: return launch_conv<64>(ta, tb, p, grid, smem, st);
   }
 }

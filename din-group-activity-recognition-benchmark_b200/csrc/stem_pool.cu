@@ -116,10 +116,12 @@ stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const
   }
 }
 
-// 8 channels (one 16-byte vector) of one output pixel per thread.
-__global__ void __launch_bounds__(256)
-maxpool_nhwc_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n, int h, int w, int c8, int oh,
-                    int ow, int k, int stride, int pad) {
+// 8 channels (one 16-byte vector) of one output pixel per thread.  AVG = 0: max pooling (padding never
+// wins); AVG = 1: average pooling with count_include_pad=True (torch's default, what torchvision's
+// Inception blocks use): always divides by k*k.
+template <int AVG>
+__global__ void pool_nhwc_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n, int h, int w, int c8, int xs8,
+                 int ys8, int oh, int ow, int k, int stride, int pad) {
   const size_t total = static_cast<size_t>(n) * oh * ow * c8;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -129,32 +131,75 @@ maxpool_nhwc_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n,
     t /= ow;
     const int oy = static_cast<int>(t % oh);
     const int img = static_cast<int>(t / oh);
-    const __half2 ninf = __float2half2_rn(-65504.0f);
-    __half2 m[4] = {ninf, ninf, ninf, ninf};
-    bool any = false;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = AVG ? 0.0f : -FLT_MAX;
     for (int ky = 0; ky < k; ++ky) {
       const int iy = oy * stride - pad + ky;
       if (iy < 0 || iy >= h) continue;
       for (int kx = 0; kx < k; ++kx) {
         const int ix = ox * stride - pad + kx;
         if (ix < 0 || ix >= w) continue;
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x) + ((static_cast<size_t>(img) * h + iy) * w + ix) * c8 + cv);
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x) + ((static_cast<size_t>(img) * h + iy) * w + ix) * xs8 + cv);
         const __half2* h2 = reinterpret_cast<const __half2*>(&v);
-        if (!any) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) m[e] = h2[e];
-          any = true;
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) m[e] = __hmax2(m[e], h2[e]);
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h2[e]);
+          if (AVG) { acc[2 * e] += f.x; acc[2 * e + 1] += f.y; }
+          else { acc[2 * e] = fmaxf(acc[2 * e], f.x); acc[2 * e + 1] = fmaxf(acc[2 * e + 1], f.y); }
         }
       }
     }
     uint4 o;
     __half2* oh2 = reinterpret_cast<__half2*>(&o);
+    const float sc = AVG ? 1.0f / static_cast<float>(k * k) : 1.0f;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) oh2[e] = m[e];
-    reinterpret_cast<uint4*>(y)[i] = o;
+    for (int e = 0; e < 4; ++e) oh2[e] = __floats2half2_rn(acc[2 * e] * sc, acc[2 * e + 1] * sc);
+    reinterpret_cast<uint4*>(y)[((static_cast<size_t>(img) * oh + oy) * ow + ox) * ys8 + cv] = o;
+  }
+}
+
+// Bilinear resize, align_corners=True (F.interpolate at infer_model.py:169), NHWC fp16, 8 channels/thread.
+__global__ void __launch_bounds__(256)
+upsample_bilinear_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n, int h, int w, int c8,
+                         int xs8, int ys8, int oh, int ow) {
+  const size_t total = static_cast<size_t>(n) * oh * ow * c8;
+  // torch: scale = (in - 1) / (out - 1) for align_corners=True (0 when out == 1)
+  const float sy = oh > 1 ? static_cast<float>(h - 1) / static_cast<float>(oh - 1) : 0.0f;
+  const float sx = ow > 1 ? static_cast<float>(w - 1) / static_cast<float>(ow - 1) : 0.0f;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % c8);
+    size_t t = i / c8;
+    const int ox = static_cast<int>(t % ow);
+    t /= ow;
+    const int oy = static_cast<int>(t % oh);
+    const int img = static_cast<int>(t / oh);
+    const float fy = sy * static_cast<float>(oy), fx = sx * static_cast<float>(ox);
+    const int y0 = min(static_cast<int>(fy), h - 1), x0 = min(static_cast<int>(fx), w - 1);
+    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+    const float ly = fy - static_cast<float>(y0), lx = fx - static_cast<float>(x0);
+    const uint4* base = reinterpret_cast<const uint4*>(x) + static_cast<size_t>(img) * h * w * xs8 + cv;
+    const uint4 v00 = __ldg(base + (static_cast<size_t>(y0) * w + x0) * xs8);
+    const uint4 v01 = __ldg(base + (static_cast<size_t>(y0) * w + x1) * xs8);
+    const uint4 v10 = __ldg(base + (static_cast<size_t>(y1) * w + x0) * xs8);
+    const uint4 v11 = __ldg(base + (static_cast<size_t>(y1) * w + x1) * xs8);
+    const __half2* a = reinterpret_cast<const __half2*>(&v00);
+    const __half2* b = reinterpret_cast<const __half2*>(&v01);
+    const __half2* c = reinterpret_cast<const __half2*>(&v10);
+    const __half2* d = reinterpret_cast<const __half2*>(&v11);
+    uint4 o;
+    __half2* oh2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 fa = __half22float2(a[e]), fb = __half22float2(b[e]);
+      const float2 fc = __half22float2(c[e]), fd = __half22float2(d[e]);
+      // torch's upsample_bilinear2d: (1-ly)*((1-lx)*a + lx*b) + ly*((1-lx)*c + lx*d)
+      const float r0 = (1.0f - ly) * ((1.0f - lx) * fa.x + lx * fb.x) + ly * ((1.0f - lx) * fc.x + lx * fd.x);
+      const float r1 = (1.0f - ly) * ((1.0f - lx) * fa.y + lx * fb.y) + ly * ((1.0f - lx) * fc.y + lx * fd.y);
+      oh2[e] = __floats2half2_rn(r0, r1);
+    }
+    reinterpret_cast<uint4*>(y)[((static_cast<size_t>(img) * oh + oy) * ow + ox) * ys8 + cv] = o;
   }
 }
 
@@ -204,22 +249,57 @@ extern "C" int din_stem_conv_nchw_f32(const float* x, const float* w, const floa
   return DIN_OK;
 }
 
-extern "C" int din_maxpool2d_nhwc_f16(const void* x, void* y, int n, int h, int w, int c, int k, int stride,
-                                      int pad, void* stream) {
-  DIN_CHECK_ARG(x && y, "din_maxpool2d_nhwc_f16: null pointer");
+static int pool_common(const char* who, int avg, const void* x, void* y, int n, int h, int w, int c, int x_c_stride,
+                       int y_c_stride, int k, int stride, int pad, void* stream) {
+  DIN_CHECK_ARG(x && y, "%s: null pointer", who);
   DIN_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0,
-                "din_maxpool2d_nhwc_f16: bad shape n=%d h=%d w=%d c=%d (c must be a multiple of 8)", n, h, w, c);
-  DIN_CHECK_ARG(k >= 1 && stride >= 1 && pad >= 0 && pad < k, "din_maxpool2d_nhwc_f16: bad window");
+                "%s: bad shape n=%d h=%d w=%d c=%d (c must be a multiple of 8)", who, n, h, w, c);
+  DIN_CHECK_ARG(x_c_stride >= c && y_c_stride >= c && x_c_stride % 8 == 0 && y_c_stride % 8 == 0,
+                "%s: channel strides %d / %d must be >= c and multiples of 8", who, x_c_stride, y_c_stride);
+  DIN_CHECK_ARG(k >= 1 && stride >= 1 && pad >= 0 && pad < k, "%s: bad window", who);
   DIN_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
-                "din_maxpool2d_nhwc_f16: pointers must be 16-byte aligned");
+                "%s: pointers must be 16-byte aligned", who);
   const int oh = (h + 2 * pad - k) / stride + 1;
   const int ow = (w + 2 * pad - k) / stride + 1;
-  DIN_CHECK_ARG(oh > 0 && ow > 0, "din_maxpool2d_nhwc_f16: empty output");
+  DIN_CHECK_ARG(oh > 0 && ow > 0, "%s: empty output", who);
   const size_t total = static_cast<size_t>(n) * oh * ow * (c / 8);
   const int sms = din_num_sms();
   const int grid = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(sms > 0 ? sms : 148) * 16));
-  maxpool_nhwc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(x), static_cast<__half*>(y), n, h, w, c / 8, oh, ow, k, stride, pad);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (avg)
+    pool_nhwc_kernel<1><<<grid, 256, 0, st>>>(static_cast<const __half*>(x), static_cast<__half*>(y), n, h, w, c / 8,
+                                              x_c_stride / 8, y_c_stride / 8, oh, ow, k, stride, pad);
+  else
+    pool_nhwc_kernel<0><<<grid, 256, 0, st>>>(static_cast<const __half*>(x), static_cast<__half*>(y), n, h, w, c / 8,
+                                              x_c_stride / 8, y_c_stride / 8, oh, ow, k, stride, pad);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
+extern "C" int din_maxpool2d_nhwc_f16(const void* x, void* y, int n, int h, int w, int c, int x_c_stride,
+                                      int y_c_stride, int k, int stride, int pad, void* stream) {
+  return pool_common("din_maxpool2d_nhwc_f16", 0, x, y, n, h, w, c, x_c_stride, y_c_stride, k, stride, pad, stream);
+}
+
+extern "C" int din_avgpool2d_nhwc_f16(const void* x, void* y, int n, int h, int w, int c, int x_c_stride,
+                                      int y_c_stride, int k, int stride, int pad, void* stream) {
+  return pool_common("din_avgpool2d_nhwc_f16", 1, x, y, n, h, w, c, x_c_stride, y_c_stride, k, stride, pad, stream);
+}
+
+extern "C" int din_upsample_bilinear_nhwc_f16(const void* x, void* y, int n, int h, int w, int c, int x_c_stride,
+                                              int y_c_stride, int oh, int ow, void* stream) {
+  DIN_CHECK_ARG(x && y, "din_upsample_bilinear_nhwc_f16: null pointer");
+  DIN_CHECK_ARG(n > 0 && h > 0 && w > 0 && oh > 0 && ow > 0 && c > 0 && c % 8 == 0,
+                "din_upsample_bilinear_nhwc_f16: bad shape n=%d h=%d w=%d c=%d -> %dx%d", n, h, w, c, oh, ow);
+  DIN_CHECK_ARG(x_c_stride >= c && y_c_stride >= c && x_c_stride % 8 == 0 && y_c_stride % 8 == 0,
+                "din_upsample_bilinear_nhwc_f16: channel strides must be >= c and multiples of 8");
+  DIN_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+                "din_upsample_bilinear_nhwc_f16: pointers must be 16-byte aligned");
+  const size_t total = static_cast<size_t>(n) * oh * ow * (c / 8);
+  const int sms = din_num_sms();
+  const int grid = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(sms > 0 ? sms : 148) * 16));
+  upsample_bilinear_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), static_cast<__half*>(y), n, h, w, c / 8, x_c_stride / 8, y_c_stride / 8, oh, ow);
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;
 }

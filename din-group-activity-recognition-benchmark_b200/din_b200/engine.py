@@ -36,9 +36,11 @@ class _Conv:
         self.w = ops.pack_conv_weight(w.contiguous(), scale)
         self.bias = None if bias is None else bias.contiguous().float()
         self.stride, self.pad, self.relu, self.pool2 = stride, pad, relu, pool2
-        self.c_out, self.kh, self.kw, self.c_in = self.w.shape
+        self.c_out, self.kh, self.kw, self.c_in_padded = self.w.shape
+        self.c_in = w.shape[1]
 
     def __call__(self, x, out=None, residual=None, **kw):
+        kw.setdefault("c_in", self.c_in)
         return ops.conv2d_nhwc(x, self.w, self.bias, stride=self.stride, pad=self.pad, relu=self.relu,
                                residual=residual, out=out, pool2=self.pool2, **kw)
 
@@ -196,8 +198,13 @@ class DinEngine:
 
         # fc_emb_1: the reference flattens crops as (d, ky, kx) (infer_model.py:181); RoIAlign here emits
         # (ky, kx, d), so permute the weight's columns once.  Public parameter stays [NFB, K*K*D].
-        w = sd["fc_emb_1.weight"].view(self.NFB, self.D, self.K * self.K).permute(0, 2, 1).contiguous()
-        self.fc_emb = _Conv(w.view(self.NFB, self.K * self.K * self.D, 1, 1), sd["fc_emb_1.bias"], relu=False)
+        # The feature map's channel stride may exceed D (Inception: 1056 -> 1088, pad channels are zero), and
+        # RoIAlign crops that stride, so the weight gets matching zero columns.
+        self.D_stride = (self.D + 63) // 64 * 64
+        w = sd["fc_emb_1.weight"].view(self.NFB, self.D, self.K * self.K).permute(0, 2, 1)
+        wp = torch.zeros((self.NFB, self.K * self.K, self.D_stride), dtype=torch.float32, device=self.device)
+        wp[:, :, :self.D] = w
+        self.fc_emb = _Conv(wp.view(self.NFB, self.K * self.K * self.D_stride, 1, 1), sd["fc_emb_1.bias"], relu=False)
         self.nl_emb = (sd["nl_emb_1.weight"].contiguous(), sd["nl_emb_1.bias"].contiguous())
         if cfg.lite_dim:
             pw = sd["point_conv.weight"]
@@ -219,6 +226,7 @@ class DinEngine:
         self.dpi_nl = (sd["dpi_nl.weight"].contiguous(), sd["dpi_nl.bias"].contiguous())
         self.fc_act = (sd["fc_activities.weight"].contiguous(), sd["fc_activities.bias"].contiguous())
         self._idx_cache = {}
+        self._fm_cache = None
 
     # -- helpers ---------------------------------------------------------------------------------
     def _box_idx(self, n_frames, n_boxes):
@@ -232,7 +240,12 @@ class DinEngine:
         """[F,3,H,W] fp32 raw -> NHWC fp16 [F,OH,OW,D] (prep_images + backbone), chunked over frames."""
         F_, _, H, W = images_flat.shape
         oh, ow, d = self.backbone.out_shape(H, W)
-        fm = torch.empty((F_, oh, ow, d), dtype=torch.float16, device=images_flat.device)
+        assert d == self.D_stride, (d, self.D_stride)
+        key = (F_, oh, ow, d)
+        if self._fm_cache is None or self._fm_cache[0] != key:
+            # zero-initialised once: pad channels beyond D are never written and must stay finite (zero)
+            self._fm_cache = (key, torch.zeros(key, dtype=torch.float16, device=images_flat.device))
+        fm = self._fm_cache[1]
         for f0 in range(0, F_, self.frames_per_chunk):
             f1 = min(F_, f0 + self.frames_per_chunk)
             self.backbone(images_flat[f0:f1], out=fm[f0:f1])      # last layer writes its slice in place
@@ -241,8 +254,8 @@ class DinEngine:
     def embed(self, fm, boxes_flat, B, T, N):
         """RoIAlign -> fc_emb_1 -> nl_emb_1 -> ReLU -> (lite branch).  Returns fp32 [B,T,N,C]."""
         M = B * T * N
-        crops = ops.roi_align_nhwc(fm, boxes_flat, self._box_idx(B * T, N), self.K, self.K, d=self.D)
-        emb = self.fc_emb(crops.view(1, 1, M, self.K * self.K * self.D), out_f32=True).view(M, self.NFB)
+        crops = ops.roi_align_nhwc(fm, boxes_flat, self._box_idx(B * T, N), self.K, self.K, d=self.D_stride)
+        emb = self.fc_emb(crops.view(1, 1, M, self.K * self.K * self.D_stride), out_f32=True).view(M, self.NFB)
         x = ops.group_layernorm(emb, *self.nl_emb, n_outer=M, outer_stride=self.NFB, cols=self.NFB, relu=True)
         if self.cfg.lite_dim:
             y = ops.linear_f32(x, self.point_w, self.point_b)

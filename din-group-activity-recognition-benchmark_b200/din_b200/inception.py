@@ -1,0 +1,143 @@
+"""inception.py — the truncated Inception-v3 backbone plan (reference backbone/backbone.py:10-85) plus the
+multiscale build of infer_model.py:165-172, on NHWC fp16.
+
+torchvision's BasicConv2d = Conv2d(bias=False) + BatchNorm2d(eps=1e-3) + ReLU: BN (eval statistics) is
+folded into the packed weights' scale and the epilogue bias.  Every branch convolution writes its output
+channels directly at its offset of the block's concat buffer (`y_c_offset` / `y_c_stride` of the conv ABI),
+so `torch.cat` never runs; Mixed_5d writes into channels [0, 288) of the multiscale map and Mixed_6e's
+768 channels are bilinearly upsampled (align_corners=True) into channels [288, 1056) of the same map.
+Channel counts that are not multiples of 64 (32, 48, 80, 96, 160, 288) need no padded buffers: the conv's
+TMA tensor map is given the real channel extent and zero-fills the rest of the last 64-channel K block.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .engine import _Conv, _Stem, _fold_bn
+
+D_OUT = 288 + 768            # cfg.emb_features for inv3 (config.py:41)
+D_STRIDE = (D_OUT + 63) // 64 * 64   # 1088: channel stride of the multiscale map (pad channels stay zero)
+
+
+def _c(v, k, s, p=0):
+    return (v + 2 * p - k) // s + 1
+
+
+class _BasicConv:
+    def __init__(self, sd, name, stride=1, pad=(0, 0)):
+        bn = {k: sd[f"{name}.bn.{k}"] for k in ("weight", "bias", "running_mean", "running_var")}
+        bn["eps"] = 1e-3
+        w, s, b = _fold_bn(sd[f"{name}.conv.weight"], bn)
+        self.conv = _Conv(w, b, s, stride=stride, pad=pad, relu=True)
+        self.c_in, self.c_out = w.shape[1], w.shape[0]
+
+    def __call__(self, x, out=None, x_c_offset=0, y_c_offset=0):
+        return self.conv(x, out=out, c_in=self.c_in, x_c_offset=x_c_offset, y_c_offset=y_c_offset)
+
+
+class _InceptionA:   # Mixed_5b/5c/5d
+    def __init__(self, sd, p):
+        self.b1 = _BasicConv(sd, p + "branch1x1")
+        self.b5_1 = _BasicConv(sd, p + "branch5x5_1")
+        self.b5_2 = _BasicConv(sd, p + "branch5x5_2", pad=(2, 2))
+        self.d1 = _BasicConv(sd, p + "branch3x3dbl_1")
+        self.d2 = _BasicConv(sd, p + "branch3x3dbl_2", pad=(1, 1))
+        self.d3 = _BasicConv(sd, p + "branch3x3dbl_3", pad=(1, 1))
+        self.bp = _BasicConv(sd, p + "branch_pool")
+        self.c_in = self.b1.c_in
+        self.c_out = 64 + 64 + 96 + self.bp.c_out
+
+    def __call__(self, x, out):
+        self.b1(x, out=out, y_c_offset=0)
+        self.b5_2(self.b5_1(x), out=out, y_c_offset=64)
+        self.d3(self.d2(self.d1(x)), out=out, y_c_offset=128)
+        self.bp(ops.avgpool2d_nhwc(x, 3, 1, 1, c=self.c_in), out=out, y_c_offset=224)
+        return out
+
+
+class _InceptionB:   # Mixed_6a
+    def __init__(self, sd, p):
+        self.b3 = _BasicConv(sd, p + "branch3x3", stride=2)
+        self.d1 = _BasicConv(sd, p + "branch3x3dbl_1")
+        self.d2 = _BasicConv(sd, p + "branch3x3dbl_2", pad=(1, 1))
+        self.d3 = _BasicConv(sd, p + "branch3x3dbl_3", stride=2)
+        self.c_in = self.b3.c_in
+
+    def __call__(self, x, out):
+        self.b3(x, out=out, y_c_offset=0)
+        self.d3(self.d2(self.d1(x)), out=out, y_c_offset=384)
+        ops.maxpool2d_nhwc(x, 3, 2, 0, out=out, c=self.c_in, y_c_offset=480)
+        return out
+
+
+class _InceptionC:   # Mixed_6b..6e
+    def __init__(self, sd, p):
+        self.b1 = _BasicConv(sd, p + "branch1x1")
+        self.s1 = _BasicConv(sd, p + "branch7x7_1")
+        self.s2 = _BasicConv(sd, p + "branch7x7_2", pad=(0, 3))
+        self.s3 = _BasicConv(sd, p + "branch7x7_3", pad=(3, 0))
+        self.d1 = _BasicConv(sd, p + "branch7x7dbl_1")
+        self.d2 = _BasicConv(sd, p + "branch7x7dbl_2", pad=(3, 0))
+        self.d3 = _BasicConv(sd, p + "branch7x7dbl_3", pad=(0, 3))
+        self.d4 = _BasicConv(sd, p + "branch7x7dbl_4", pad=(3, 0))
+        self.d5 = _BasicConv(sd, p + "branch7x7dbl_5", pad=(0, 3))
+        self.bp = _BasicConv(sd, p + "branch_pool")
+
+    def __call__(self, x, out):
+        self.b1(x, out=out, y_c_offset=0)
+        self.s3(self.s2(self.s1(x)), out=out, y_c_offset=192)
+        self.d5(self.d4(self.d3(self.d2(self.d1(x)))), out=out, y_c_offset=384)
+        self.bp(ops.avgpool2d_nhwc(x, 3, 1, 1), out=out, y_c_offset=576)
+        return out
+
+
+class Inv3Plan:
+    def __init__(self, sd, prefix="backbone."):
+        bn = {k: sd[f"{prefix}Conv2d_1a_3x3.bn.{k}"] for k in ("weight", "bias", "running_mean", "running_var")}
+        bn["eps"] = 1e-3
+        w, s, b = _fold_bn(sd[prefix + "Conv2d_1a_3x3.conv.weight"], bn)
+        self.stem = _Stem(w, b, scale=s, stride=2, pad=0)
+        self.c2a = _BasicConv(sd, prefix + "Conv2d_2a_3x3")
+        self.c2b = _BasicConv(sd, prefix + "Conv2d_2b_3x3", pad=(1, 1))
+        self.c3b = _BasicConv(sd, prefix + "Conv2d_3b_1x1")
+        self.c4a = _BasicConv(sd, prefix + "Conv2d_4a_3x3")
+        self.m5b = _InceptionA(sd, prefix + "Mixed_5b.")
+        self.m5c = _InceptionA(sd, prefix + "Mixed_5c.")
+        self.m5d = _InceptionA(sd, prefix + "Mixed_5d.")
+        self.m6a = _InceptionB(sd, prefix + "Mixed_6a.")
+        self.m6 = [_InceptionC(sd, prefix + f"Mixed_6{c}.") for c in "bcde"]
+        self.last_out1 = None
+
+    def out_shape(self, h, w):
+        h, w = _c(h, 3, 2), _c(w, 3, 2)      # 1a
+        h, w = _c(h, 3, 1), _c(w, 3, 1)      # 2a   (2b keeps the size)
+        h, w = _c(h, 3, 2), _c(w, 3, 2)      # max-pool
+        h, w = _c(h, 3, 1), _c(w, 3, 1)      # 4a   (3b is 1x1)
+        h, w = _c(h, 3, 2), _c(w, 3, 2)      # max-pool
+        return h, w, D_STRIDE
+
+    def __call__(self, images, out=None):
+        """raw fp32 NCHW frames -> multiscale map [F, OH, OW, 1088] (channels [0,1056) valid, rest untouched)."""
+        F_, _, H, W = images.shape
+        oh, ow, _ = self.out_shape(H, W)
+        dev = images.device
+        if out is None:
+            out = torch.zeros((F_, oh, ow, D_STRIDE), dtype=torch.float16, device=dev)
+        x = self.stem(images)
+        x = self.c2b(self.c2a(x))
+        x = ops.maxpool2d_nhwc(x, 3, 2, 0)
+        x = self.c4a(self.c3b(x))
+        x = ops.maxpool2d_nhwc(x, 3, 2, 0)                                        # [F, oh, ow, 192]
+        e = lambda c, hh=oh, ww=ow: torch.empty((F_, hh, ww, c), dtype=torch.float16, device=dev)  # noqa: E731
+        x = self.m5b(x, e(256))
+        x = self.m5c(x, e(288))
+        self.m5d(x, out)                                                          # channels [0, 288) of the map
+        h2, w2 = _c(oh, 3, 2), _c(ow, 3, 2)
+        # Mixed_6a reads channels [0, 288) of the map in place (c_in = 288 < its channel stride)
+        y = self.m6a(out, e(768, h2, w2))
+        for blk in self.m6:
+            y = blk(y, e(768, h2, w2))
+        self.last_out1 = y
+        ops.upsample_bilinear_nhwc(y, oh, ow, out=out, c=768, y_c_offset=288)    # F.interpolate + cat
+        return out

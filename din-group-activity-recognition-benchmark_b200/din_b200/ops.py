@@ -56,7 +56,7 @@ def pack_conv_weight(w_oihw, scale=None, c_in_padded=None):
     """OIHW fp32 -> packed fp16 [c_out][kh][kw][c_in_padded] (optionally folding a per-channel scale)."""
     _need(w_oihw, torch.float32, "w_oihw")
     co, ci, kh, kw = w_oihw.shape
-    cip = ci if c_in_padded is None else c_in_padded
+    cip = (ci + 63) // 64 * 64 if c_in_padded is None else c_in_padded
     if scale is not None:
         _need(scale, torch.float32, "scale")
     out = torch.empty((co, kh, kw, cip), dtype=torch.float16, device=w_oihw.device)
@@ -72,10 +72,10 @@ def conv2d_nhwc(x, w_packed, bias=None, *, stride=1, pad=(0, 0), relu=False, res
     _need(x, torch.float16, "x")
     _need(w_packed, torch.float16, "w_packed")
     n, h, w, cx = x.shape
-    co, kh, kw, ci = w_packed.shape
+    co, kh, kw, ci = w_packed.shape          # ci = c_in rounded up to a multiple of 64 (zero columns)
     if c_in is None:
-        c_in = ci
-    assert c_in == ci, (c_in, ci)
+        c_in = min(ci, cx - x_c_offset)
+    assert (c_in + 63) // 64 * 64 == ci and x_c_offset + c_in <= cx, (c_in, ci, cx, x_c_offset)
     ph, pw = pad
     oh = (h + 2 * ph - kh) // stride + 1
     ow = (w + 2 * pw - kw) // stride + 1
@@ -85,6 +85,7 @@ def conv2d_nhwc(x, w_packed, bias=None, *, stride=1, pad=(0, 0), relu=False, res
     _need(out, torch.float32 if out_f32 else torch.float16, "out")
     assert out.shape[:3] == (n, yh, yw), (out.shape, (n, yh, yw))
     cy = out.shape[3]
+    assert y_c_offset + co <= cy, (y_c_offset, co, cy)
     d = DinConvDesc(n=n, h=h, w=w, c_in=c_in, x_c_stride=cx, c_out=co, y_c_stride=cy, kh=kh, kw=kw,
                     stride=stride, pad_h=ph, pad_w=pw, relu=int(relu), out_f32=int(out_f32), pool2=int(pool2))
     esz_y = 4 if out_f32 else 2
@@ -97,9 +98,9 @@ def conv2d_nhwc(x, w_packed, bias=None, *, stride=1, pad=(0, 0), relu=False, res
         rp = C.c_void_p(residual.data_ptr() + 2 * y_c_offset)
     if bias is not None:
         _need(bias, torch.float32, "bias")
-    flops = 2 * n * oh * ow * co * kh * kw * ci
-    nbytes = 2 * n * h * w * ci + 2 * co * kh * kw * ci + esz_y * n * yh * yw * co
-    with _launch(f"conv{kh}x{kw}s{stride}_{ci}->{co}@{oh}x{ow}" + ("+pool" if pool2 else ""), flops, nbytes):
+    flops = 2 * n * oh * ow * co * kh * kw * c_in       # algorithmic: the real c_in, not the K padding
+    nbytes = 2 * n * h * w * c_in + 2 * co * kh * kw * ci + esz_y * n * yh * yw * co
+    with _launch(f"conv{kh}x{kw}s{stride}_{c_in}->{co}@{oh}x{ow}" + ("+pool" if pool2 else ""), flops, nbytes):
         check(_lib.load().din_conv2d_nhwc_f16(C.byref(d), xp, _p(w_packed), _p(bias), rp, yp, _stream()),
               "din_conv2d_nhwc_f16")
     return out
@@ -126,17 +127,44 @@ def stem_conv(x_nchw, w_oihw, bias, *, stride=1, pad=0, relu=True, prep=True):
     return y
 
 
-def maxpool2d_nhwc(x, k, stride, pad=0, out=None):
+def _pool(fn_name, x, k, stride, pad, out, c, x_c_offset, y_c_offset):
     _need(x, torch.float16, "x")
-    n, h, w, c = x.shape
+    n, h, w, cx = x.shape
+    c = cx - x_c_offset if c is None else c
     oh = (h + 2 * pad - k) // stride + 1
     ow = (w + 2 * pad - k) // stride + 1
     y = torch.empty((n, oh, ow, c), dtype=torch.float16, device=x.device) if out is None else out
     _need(y, torch.float16, "out")
-    assert tuple(y.shape) == (n, oh, ow, c)
-    with _launch(f"maxpool{k}s{stride}_{c}@{oh}x{ow}", 0, 2 * n * c * (h * w + oh * ow)):
-        check(_lib.load().din_maxpool2d_nhwc_f16(_p(x), _p(y), n, h, w, c, k, stride, pad, _stream()),
-              "din_maxpool2d_nhwc_f16")
+    assert tuple(y.shape[:3]) == (n, oh, ow) and y_c_offset + c <= y.shape[3] and x_c_offset + c <= cx
+    xp = C.c_void_p(x.data_ptr() + 2 * x_c_offset)
+    yp = C.c_void_p(y.data_ptr() + 2 * y_c_offset)
+    with _launch(f"{fn_name[4:11]}{k}s{stride}_{c}@{oh}x{ow}", 0, 2 * n * c * (h * w + oh * ow)):
+        check(getattr(_lib.load(), fn_name)(xp, yp, n, h, w, c, cx, y.shape[3], k, stride, pad, _stream()), fn_name)
+    return y
+
+
+def maxpool2d_nhwc(x, k, stride, pad=0, out=None, c=None, x_c_offset=0, y_c_offset=0):
+    return _pool("din_maxpool2d_nhwc_f16", x, k, stride, pad, out, c, x_c_offset, y_c_offset)
+
+
+def avgpool2d_nhwc(x, k, stride, pad=0, out=None, c=None, x_c_offset=0, y_c_offset=0):
+    """count_include_pad=True (torch default)."""
+    return _pool("din_avgpool2d_nhwc_f16", x, k, stride, pad, out, c, x_c_offset, y_c_offset)
+
+
+def upsample_bilinear_nhwc(x, oh, ow, out=None, c=None, x_c_offset=0, y_c_offset=0):
+    """align_corners=True bilinear resize of channels [x_c_offset, x_c_offset+c) into out[..., y_c_offset:]."""
+    _need(x, torch.float16, "x")
+    n, h, w, cx = x.shape
+    c = cx - x_c_offset if c is None else c
+    y = torch.empty((n, oh, ow, c), dtype=torch.float16, device=x.device) if out is None else out
+    _need(y, torch.float16, "out")
+    assert tuple(y.shape[:3]) == (n, oh, ow) and y_c_offset + c <= y.shape[3]
+    xp = C.c_void_p(x.data_ptr() + 2 * x_c_offset)
+    yp = C.c_void_p(y.data_ptr() + 2 * y_c_offset)
+    with _launch(f"upsample_{c}@{oh}x{ow}", 0, 2 * n * c * (h * w + oh * ow)):
+        check(_lib.load().din_upsample_bilinear_nhwc_f16(xp, yp, n, h, w, c, cx, y.shape[3], oh, ow, _stream()),
+              "din_upsample_bilinear_nhwc_f16")
     return y
 
 

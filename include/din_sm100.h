@@ -74,7 +74,8 @@ DIN_API int din_stem_conv_nchw_f32(const float* x, const float* w, const float* 
  */
 typedef struct DinConvDesc {
   int32_t n, h, w;          /* input spatial extent (NHWC) */
-  int32_t c_in;             /* input channels used by this conv; multiple of 64 */
+  int32_t c_in;             /* input channels used by this conv; multiple of 8 (K is processed in blocks of 64:
+                               a partial last block is zero-filled by the TMA unit) */
   int32_t x_c_stride;       /* channel count of the buffer x lives in (>= c_in; x may be a channel slice) */
   int32_t c_out;            /* output channels; multiple of 8 */
   int32_t y_c_stride;       /* channel count of the buffer y lives in (>= c_out; concat-by-offset writes) */
@@ -88,7 +89,8 @@ typedef struct DinConvDesc {
 
 /*
  * x        : fp16, element (img, yy, xx, c) at x[((img*h + yy)*w + xx)*x_c_stride + c]; 16-byte aligned
- * w_packed : fp16 [c_out][kh][kw][c_in] (K-major rows; see din_pack_conv_weight_f16); 16-byte aligned
+ * w_packed : fp16 [c_out][kh][kw][c_in_padded], c_in_padded = c_in rounded up to 64, zero columns beyond c_in
+ *            (K-major rows; see din_pack_conv_weight_f16); 16-byte aligned
  * bias     : fp32 [c_out] or NULL
  * residual : fp16, same indexing as y with y_c_stride, added before ReLU; or NULL
  * y        : fp16 or fp32 (out_f32), element (img, oy, ox, co) at y[((img*oh + oy)*ow + ox)*y_c_stride + co]
@@ -104,11 +106,25 @@ DIN_API int din_pack_conv_weight_f16(const float* w_oihw, const float* scale, vo
                              int c_in_padded, int kh, int kw, void* stream);
 
 /*
- * Max pooling, NHWC fp16.  Replaces nn.MaxPool2d(2,2) in vgg16.features, resnet18.maxpool (3,2,1),
- * F.max_pool2d(3,2) at backbone.py:50,56.  Padding elements never win (-inf), as in torch.
+ * Max / average pooling, NHWC fp16, over channels [0, c) of buffers with x_c_stride / y_c_stride channels
+ * (so a pool can read a channel slice and write straight into a concat buffer).
+ * Replaces nn.MaxPool2d(2,2) in vgg16.features (normally fused into the conv epilogue, see pool2),
+ * resnet18.maxpool (3,2,1), F.max_pool2d(3,2) at backbone.py:50,56 and in Inception's Mixed_6a, and
+ * F.avg_pool2d(3,1,1) of the Inception blocks' pool branches (count_include_pad=True: divides by k*k).
+ * Max pooling: padding elements never win, as in torch.
  */
-DIN_API int din_maxpool2d_nhwc_f16(const void* x, void* y, int n, int h, int w, int c, int k, int stride, int pad,
-                           void* stream);
+DIN_API int din_maxpool2d_nhwc_f16(const void* x, void* y, int n, int h, int w, int c, int x_c_stride,
+                                   int y_c_stride, int k, int stride, int pad, void* stream);
+DIN_API int din_avgpool2d_nhwc_f16(const void* x, void* y, int n, int h, int w, int c, int x_c_stride,
+                                   int y_c_stride, int k, int stride, int pad, void* stream);
+
+/*
+ * Bilinear resize with align_corners=True, NHWC fp16, [n,h,w,c] -> [n,oh,ow,c] (channel-strided buffers).
+ * Replaces F.interpolate(features, size=(OH,OW), mode='bilinear', align_corners=True) (infer_model.py:169)
+ * and, by writing at a channel offset of the multiscale map, the torch.cat at infer_model.py:172.
+ */
+DIN_API int din_upsample_bilinear_nhwc_f16(const void* x, void* y, int n, int h, int w, int c, int x_c_stride,
+                                           int y_c_stride, int oh, int ow, void* stream);
 
 /* ---- person-level head --------------------------------------------------------------------- */
 

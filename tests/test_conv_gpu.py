@@ -37,6 +37,11 @@ CASES = [
     (1, 17, 29, 128, 192, (1, 7), 1, (0, 3), True),   # Inception 1x7
     (1, 17, 29, 128, 192, (7, 1), 1, (3, 0), True),   # Inception 7x1
     (1, 720, 1280, 64, 64, 3, 1, 1, True),   # VGG conv1_2 at full size (7200 tiles, persistent loop)
+    (1, 35, 35, 48, 64, 5, 1, 2, True),      # Inception 5x5, c_in = 48: partial K block zero-filled by TMA
+    (1, 30, 40, 80, 192, 3, 1, 0, True),     # Inception Conv2d_4a: c_in = 80, no padding, BN = 192 tile
+    (2, 17, 17, 160, 96, (7, 1), 1, (3, 0), True),   # c_in = 160, BN = 96 tile
+    (1, 35, 35, 288, 384, 3, 2, 0, True),    # Mixed_6a: stride 2, pad 0, 288 -> 384 (two BN = 192 tiles)
+    (1, 37, 37, 32, 32, 3, 1, 0, True),      # Conv2d_2a: 32 -> 32
 ]
 
 
@@ -51,9 +56,10 @@ def test_conv_matches_torch(cuda, case):
     wt = (torch.randn(cout, cin, kh, kw, generator=g) * (2.0 / (cin * kh * kw)) ** 0.5).to(cuda)
     bias = torch.randn(cout, generator=g).to(cuda)
     wp = ops.pack_conv_weight(wt)
-    assert wp.shape == (cout, kh, kw, cin)
-    # the packed weight is exactly the fp16 rounding of the OIHW weight, tap-major
-    torch.testing.assert_close(wp.float(), wt.half().float().permute(0, 2, 3, 1), rtol=0, atol=0)
+    assert wp.shape == (cout, kh, kw, (cin + 63) // 64 * 64)
+    # the packed weight is exactly the fp16 rounding of the OIHW weight, tap-major, zero K padding
+    torch.testing.assert_close(wp[..., :cin].float(), wt.half().float().permute(0, 2, 3, 1), rtol=0, atol=0)
+    assert (wp[..., cin:] == 0).all()
     y = ops.conv2d_nhwc(x, wp, bias, stride=stride, pad=(ph, pw), relu=relu)
     torch.cuda.synchronize()
     ref = _ref_conv(x, wt.half(), bias, stride, (ph, pw), relu)
@@ -112,3 +118,16 @@ def test_stem_and_pool(cuda):
         ref = F.max_pool2d(t.float().permute(0, 3, 1, 2), k, s, p).permute(0, 2, 3, 1)
         torch.cuda.synchronize()
         assert torch.equal(y.float(), ref), (k, s, p)
+    # channel-sliced pools writing into a concat buffer (Inception Mixed_6a), average pool, bilinear upsample
+    out = torch.zeros(2, 22, 40, 96, device=cuda, dtype=torch.float16)
+    ops.maxpool2d_nhwc(t, 3, 2, 0, out=out, c=48, x_c_offset=8, y_c_offset=40)
+    ref = F.max_pool2d(t[..., 8:56].float().permute(0, 3, 1, 2), 3, 2).permute(0, 2, 3, 1)
+    assert torch.equal(out[..., 40:88].float(), ref) and (out[..., :40] == 0).all() and (out[..., 88:] == 0).all()
+    y = ops.avgpool2d_nhwc(t, 3, 1, 1)
+    ref = F.avg_pool2d(t.float().permute(0, 3, 1, 2), 3, 1, 1).permute(0, 2, 3, 1)
+    assert (y.float() - ref).abs().max().item() <= 2e-3
+    up = torch.zeros(2, 91, 163, 80, device=cuda, dtype=torch.float16)
+    ops.upsample_bilinear_nhwc(t, 91, 163, out=up, c=64, y_c_offset=16)
+    ref = F.interpolate(t.float().permute(0, 3, 1, 2), size=(91, 163), mode="bilinear", align_corners=True)
+    assert (up[..., 16:].float() - ref.permute(0, 2, 3, 1)).abs().max().item() <= 4e-3
+    assert (up[..., :16] == 0).all()

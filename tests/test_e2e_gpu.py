@@ -71,6 +71,12 @@ def test_vgg16_hierarchical(cuda):
                         ST_kernel_size=[(1, 3), (3, 1)], hierarchical_inference=True), B=1)
 
 
+def test_inception_v3_multiscale(cuda):
+    """BASELINE config 2's backbone (patched oracle, bug I): Inception-v3 to Mixed_6e, bilinear upsample,
+    channel concat to D = 1056, C = 1024."""
+    _run_case(cuda, _pc("inv3", (139, 203), emb_features=1056, num_frames=2, num_boxes=4, lite_dim=None), B=2)
+
+
 def test_collective_res18(cuda):
     _run_case(cuda, _pc("res18", (96, 144), dataset="collective", num_frames=3, num_boxes=13, lite_dim=None,
                         ST_kernel_size=(3, 3), num_activities=4), B=3)
