@@ -16,7 +16,7 @@ class DinError(RuntimeError):
 class DinConvDesc(C.Structure):
     _fields_ = [(name, C.c_int32) for name in (
         "n", "h", "w", "c_in", "x_c_stride", "c_out", "y_c_stride", "kh", "kw", "stride",
-        "pad_h", "pad_w", "relu", "out_f32", "pool2")]
+        "pad_h", "pad_w", "relu", "out_f32", "pool2", "w_split")]
 
 
 _vp, _i, _fp, _ll = C.c_void_p, C.c_int, C.c_void_p, C.c_longlong  # float* is passed as a raw address
@@ -28,7 +28,7 @@ PROTOTYPES = {
     "din_device_sm_count": (C.c_int, []),
     "din_stem_conv_nchw_f32": (C.c_int, [_fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_conv2d_nhwc_f16": (C.c_int, [C.POINTER(DinConvDesc), _vp, _vp, _fp, _vp, _vp, _vp]),
-    "din_pack_conv_weight_f16": (C.c_int, [_fp, _fp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "din_pack_conv_weight_f16": (C.c_int, [_fp, _fp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "din_maxpool2d_nhwc_f16": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_avgpool2d_nhwc_f16": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_upsample_bilinear_nhwc_f16": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

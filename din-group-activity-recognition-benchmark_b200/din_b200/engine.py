@@ -32,11 +32,11 @@ def _fold_bn(conv_w, bn):
 class _Conv:
     """One tcgen05 convolution of the plan (weights packed fp16 [co][kh][kw][ci], fp32 bias)."""
 
-    def __init__(self, w, bias, scale=None, stride=1, pad=(0, 0), relu=True, pool2=False):
-        self.w = ops.pack_conv_weight(w.contiguous(), scale)
+    def __init__(self, w, bias, scale=None, stride=1, pad=(0, 0), relu=True, pool2=False, split=1):
+        self.w = ops.pack_conv_weight(w.contiguous(), scale, split=split)
         self.bias = None if bias is None else bias.contiguous().float()
         self.stride, self.pad, self.relu, self.pool2 = stride, pad, relu, pool2
-        self.c_out, self.kh, self.kw, self.c_in_padded = self.w.shape
+        self.c_out, self.c_in_padded = self.w.shape[0], self.w.shape[-1]
         self.c_in = w.shape[1]
 
     def __call__(self, x, out=None, residual=None, **kw):
@@ -204,7 +204,8 @@ class DinEngine:
         w = sd["fc_emb_1.weight"].view(self.NFB, self.D, self.K * self.K).permute(0, 2, 1)
         wp = torch.zeros((self.NFB, self.K * self.K, self.D_stride), dtype=torch.float32, device=self.device)
         wp[:, :, :self.D] = w
-        self.fc_emb = _Conv(wp.view(self.NFB, self.K * self.K * self.D_stride, 1, 1), sd["fc_emb_1.bias"], relu=False)
+        self.fc_emb = _Conv(wp.view(self.NFB, self.K * self.K * self.D_stride, 1, 1), sd["fc_emb_1.bias"], relu=False,
+                            split=2 if cfg.backbone == "inv3" else 1)
         self.nl_emb = (sd["nl_emb_1.weight"].contiguous(), sd["nl_emb_1.bias"].contiguous())
         if cfg.lite_dim:
             pw = sd["point_conv.weight"]

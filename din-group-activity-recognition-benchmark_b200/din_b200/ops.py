@@ -52,16 +52,18 @@ def _need(t, dtype, name):
                             f"{getattr(t, 'dtype', type(t))} on {getattr(t, 'device', '?')}")
 
 
-def pack_conv_weight(w_oihw, scale=None, c_in_padded=None):
-    """OIHW fp32 -> packed fp16 [c_out][kh][kw][c_in_padded] (optionally folding a per-channel scale)."""
+def pack_conv_weight(w_oihw, scale=None, c_in_padded=None, split=1):
+    """OIHW fp32 -> packed fp16 [c_out][kh][kw][c_in_padded] (optionally folding a per-channel scale);
+    split=2 -> [c_out][2][kh][kw][c_in_padded] (hi, lo parts)."""
     _need(w_oihw, torch.float32, "w_oihw")
     co, ci, kh, kw = w_oihw.shape
     cip = (ci + 63) // 64 * 64 if c_in_padded is None else c_in_padded
     if scale is not None:
         _need(scale, torch.float32, "scale")
-    out = torch.empty((co, kh, kw, cip), dtype=torch.float16, device=w_oihw.device)
-    check(_lib.load().din_pack_conv_weight_f16(_p(w_oihw), _p(scale), _p(out), co, ci, cip, kh, kw, _stream()),
-          "din_pack_conv_weight_f16")
+    shape = (co, kh, kw, cip) if split == 1 else (co, 2, kh, kw, cip)
+    out = torch.empty(shape, dtype=torch.float16, device=w_oihw.device)
+    check(_lib.load().din_pack_conv_weight_f16(_p(w_oihw), _p(scale), _p(out), co, ci, cip, kh, kw, split,
+                                               _stream()), "din_pack_conv_weight_f16")
     return out
 
 
@@ -72,7 +74,9 @@ def conv2d_nhwc(x, w_packed, bias=None, *, stride=1, pad=(0, 0), relu=False, res
     _need(x, torch.float16, "x")
     _need(w_packed, torch.float16, "w_packed")
     n, h, w, cx = x.shape
-    co, kh, kw, ci = w_packed.shape          # ci = c_in rounded up to a multiple of 64 (zero columns)
+    split = 2 if w_packed.dim() == 5 else 1
+    co, kh, kw, ci = w_packed.shape[0], w_packed.shape[-3], w_packed.shape[-2], w_packed.shape[-1]
+    # ci = c_in rounded up to a multiple of 64 (zero columns)
     if c_in is None:
         c_in = min(ci, cx - x_c_offset)
     assert (c_in + 63) // 64 * 64 == ci and x_c_offset + c_in <= cx, (c_in, ci, cx, x_c_offset)
@@ -87,7 +91,8 @@ def conv2d_nhwc(x, w_packed, bias=None, *, stride=1, pad=(0, 0), relu=False, res
     cy = out.shape[3]
     assert y_c_offset + co <= cy, (y_c_offset, co, cy)
     d = DinConvDesc(n=n, h=h, w=w, c_in=c_in, x_c_stride=cx, c_out=co, y_c_stride=cy, kh=kh, kw=kw,
-                    stride=stride, pad_h=ph, pad_w=pw, relu=int(relu), out_f32=int(out_f32), pool2=int(pool2))
+                    stride=stride, pad_h=ph, pad_w=pw, relu=int(relu), out_f32=int(out_f32), pool2=int(pool2),
+                    w_split=split)
     esz_y = 4 if out_f32 else 2
     xp = C.c_void_p(x.data_ptr() + 2 * x_c_offset)
     yp = C.c_void_p(out.data_ptr() + esz_y * y_c_offset)

@@ -85,6 +85,8 @@ typedef struct DinConvDesc {
   int32_t relu;             /* fuse ReLU */
   int32_t out_f32;          /* 0: y is fp16, 1: y is fp32 */
   int32_t pool2;            /* fuse MaxPool2d(2,2) after (bias, ReLU): y is [n, oh/2, ow/2, ...] (fp16, no residual) */
+  int32_t w_split;          /* 0/1: w_packed holds one fp16 part; 2: hi and lo fp16 parts ([c_out][2][kh][kw][c_in_padded]),
+                               both accumulated in the same TMEM tile (weights effectively exact, 2x tensor work) */
 } DinConvDesc;
 
 /*
@@ -101,9 +103,12 @@ DIN_API int din_conv2d_nhwc_f16(const DinConvDesc* desc, const void* x, const vo
 
 /* OIHW fp32 [c_out, c_in, kh, kw] (optionally scaled per output channel by `scale`, for BN folding;
  * NULL = 1) -> fp16 [c_out][kh][kw][c_in_padded], zero-filled for c_in <= c < c_in_padded.
- * Device-to-device. */
+ * Rounding is error-feedback along each output row (every weight within 1 ulp(fp16) of its fp32 value, the
+ * row's summed rounding error ~1 ulp): weight rounding errors do not average out over pixels, see
+ * csrc/conv_tcgen05.cu.  split = 2 instead writes [c_out][2][kh][kw][c_in_padded]: hi = RN(w), lo = RN(w - hi)
+ * (for DinConvDesc.w_split = 2).  Device-to-device, one-time (not on the per-step path). */
 DIN_API int din_pack_conv_weight_f16(const float* w_oihw, const float* scale, void* w_packed, int c_out, int c_in,
-                             int c_in_padded, int kh, int kw, void* stream);
+                             int c_in_padded, int kh, int kw, int split, void* stream);
 
 /*
  * Max / average pooling, NHWC fp16, over channels [0, c) of buffers with x_c_stride / y_c_stride channels

@@ -46,7 +46,7 @@ def test_ctypes_table_matches_header():
         assert m, name
         args = [a for a in m.group(1).split(",") if a.strip() and a.strip() != "void"]
         assert len(args) == len(argtypes), (name, len(args), len(argtypes))
-    assert C.sizeof(lib.DinConvDesc) == 15 * 4
+    assert C.sizeof(lib.DinConvDesc) == 16 * 4
 
 
 def test_loads_and_validates_without_gpu():
@@ -55,7 +55,7 @@ def test_loads_and_validates_without_gpu():
     assert h.din_abi_version() == 1
     # invalid arguments are rejected before any CUDA call, with a message
     d = lib.DinConvDesc(n=1, h=8, w=8, c_in=44, x_c_stride=48, c_out=64, y_c_stride=64, kh=3, kw=3, stride=1,
-                        pad_h=1, pad_w=1, relu=1, out_f32=0, pool2=0)
+                        pad_h=1, pad_w=1, relu=1, out_f32=0, pool2=0, w_split=1)
     rc = h.din_conv2d_nhwc_f16(C.byref(d), C.c_void_p(16), C.c_void_p(16), None, None, C.c_void_p(16), None)
     assert rc == -1 and b"multiple of 8" in h.din_last_error_string()
     rc = h.din_dynamic_infer_f32(C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), 1, 10, 12, 128,

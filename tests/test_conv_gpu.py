@@ -10,6 +10,11 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
+def _unpack(wp, cin):
+    """packed fp16 [co][kh][kw][cin_p] -> OIHW fp32: the exact weights the kernel multiplies with."""
+    return wp[..., :cin].float().permute(0, 3, 1, 2).contiguous()
+
+
 def _ref_conv(x_nhwc_h, w_oihw_h, bias, stride, pad, relu, residual=None):
     x = x_nhwc_h.float().permute(0, 3, 1, 2)
     with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
@@ -57,12 +62,17 @@ def test_conv_matches_torch(cuda, case):
     bias = torch.randn(cout, generator=g).to(cuda)
     wp = ops.pack_conv_weight(wt)
     assert wp.shape == (cout, kh, kw, (cin + 63) // 64 * 64)
-    # the packed weight is exactly the fp16 rounding of the OIHW weight, tap-major, zero K padding
-    torch.testing.assert_close(wp[..., :cin].float(), wt.half().float().permute(0, 2, 3, 1), rtol=0, atol=0)
+    # packed weight: tap-major, zero K padding, error-feedback rounding: every element within one fp16 ulp
+    # of the row's largest weight (own rounding + the carried residual) and each output row's SUMMED rounding
+    # error ~1 ulp instead of ~sqrt(K) ulps
+    wu = _unpack(wp, cin)
+    row_ulp = wt.abs().amax(dim=(1, 2, 3), keepdim=True) * 2.0 ** -10
+    assert ((wu - wt).abs() <= row_ulp).all()
+    assert ((wu - wt).sum(dim=(1, 2, 3)).abs() <= 2 * row_ulp.flatten()).all()
     assert (wp[..., cin:] == 0).all()
     y = ops.conv2d_nhwc(x, wp, bias, stride=stride, pad=(ph, pw), relu=relu)
     torch.cuda.synchronize()
-    ref = _ref_conv(x, wt.half(), bias, stride, (ph, pw), relu)
+    ref = _ref_conv(x, wu, bias, stride, (ph, pw), relu)
     assert y.shape == ref.shape
     err = (y.float() - ref).abs().max().item()
     scale = ref.abs().max().item()
@@ -81,7 +91,7 @@ def test_conv_f32_out_residual_and_channel_slices(cuda):
     wp = ops.pack_conv_weight(wt)
     ops.conv2d_nhwc(xbuf, wp, bias, stride=1, pad=(1, 1), relu=True, residual=res, out=out,
                     c_in=128, x_c_offset=64, y_c_offset=64)
-    ref = _ref_conv(xbuf[..., 64:192].contiguous(), wt.half(), bias, 1, (1, 1), True,
+    ref = _ref_conv(xbuf[..., 64:192].contiguous(), _unpack(wp, 128), bias, 1, (1, 1), True,
                     residual=res[..., 64:136].contiguous())
     torch.cuda.synchronize()
     assert (out[..., :64] == 0).all() and (out[..., 136:] == 0).all()   # neighbours untouched
@@ -91,11 +101,35 @@ def test_conv_f32_out_residual_and_channel_slices(cuda):
     a = torch.randn(1, 1, 360, 1280, generator=g).to(cuda).half()
     wl = (torch.randn(1024, 1280, 1, 1, generator=g) * 0.03).to(cuda)
     bl = torch.randn(1024, generator=g).to(cuda)
-    y = ops.conv2d_nhwc(a, ops.pack_conv_weight(wl), bl, out_f32=True)
-    ref = a.float().reshape(360, 1280) @ wl.half().float().reshape(1024, 1280).t() + bl
+    wlp = ops.pack_conv_weight(wl)
+    y = ops.conv2d_nhwc(a, wlp, bl, out_f32=True)
+    ref = a.float().reshape(360, 1280) @ _unpack(wlp, 1280).reshape(1024, 1280).t() + bl
     torch.cuda.synchronize()
     err = (y.reshape(360, 1024) - ref).abs().max().item()
     assert err <= 2e-5 * max(1.0, ref.abs().max().item()) * 10, err
+
+
+@pytest.mark.parametrize("case", [(2, 45, 80, 128, 128, 3, 1, (1, 1)), (1, 23, 40, 192, 320, 1, 1, (0, 0)),
+                                  (1, 35, 35, 288, 384, 3, 2, (0, 0)), (1, 17, 29, 160, 192, (1, 7), 1, (0, 3))],
+                         ids=str)
+def test_conv_split_weights(cuda, case):
+    """w_split = 2: hi + lo fp16 weight parts accumulated in one TMEM tile == convolution with the (nearly)
+    exact fp32 weights; tolerance 5e-4 (the fp16 rounding of the output)."""
+    from din_b200 import ops
+    n, h, w, cin, cout, k, stride, pad = case
+    kh, kw = (k, k) if isinstance(k, int) else k
+    g = torch.Generator(device="cpu").manual_seed(99)
+    x = torch.randn(n, h, w, cin, generator=g).to(cuda).half()
+    wt = (torch.randn(cout, cin, kh, kw, generator=g) * (2.0 / (cin * kh * kw)) ** 0.5).to(cuda)
+    bias = torch.randn(cout, generator=g).to(cuda)
+    wp = ops.pack_conv_weight(wt, split=2)
+    assert wp.shape == (cout, 2, kh, kw, (cin + 63) // 64 * 64)
+    rec = (wp[:, 0, ..., :cin].float() + wp[:, 1, ..., :cin].float()).permute(0, 3, 1, 2)
+    assert (rec - wt).abs().max().item() <= 2.0 ** -20 * wt.abs().max().item()
+    y = ops.conv2d_nhwc(x, wp, bias, stride=stride, pad=pad, relu=True, out_f32=True)
+    ref = _ref_conv(x, wt, bias, stride, pad, True)
+    torch.cuda.synchronize()
+    assert (y - ref).abs().max().item() <= 2e-5 * ref.abs().max().item() * 4
 
 
 def test_stem_and_pool(cuda):

@@ -37,7 +37,7 @@ for (n, h, w, ci, co, k, pad, pool) in CASES:
     except Exception as e:  # noqa: BLE001
         print("case", (n, h, w, ci, co, k), "EXC", str(e)[:200])
         break
-    ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), wt.half().float(), b, padding=pad))
+    ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), wp[..., :ci].float().permute(0, 3, 1, 2).contiguous(), b, padding=pad))
     if pool:
         ref = F.max_pool2d(ref, 2, 2)
     ref = ref.permute(0, 2, 3, 1)
