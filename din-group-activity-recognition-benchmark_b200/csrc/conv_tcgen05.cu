@@ -111,7 +111,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   constexpr int kBBytes = BN * kBK * 2;
   constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem(smem_raw, 1024);
   uint8_t* smem_a = smem;
   const int b_stage_bytes = p.tb * kBBytes;
   uint8_t* smem_b = smem + p.n_a_stages * p.a_stage_bytes;
@@ -374,11 +374,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             }
           }
         }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-        }
         if (p.out_f32) {
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+          }
           if (valid_own) {
             float* yp = reinterpret_cast<float*>(p.y) + pix_own * p.y_c_stride + col0;
 #pragma unroll
@@ -391,7 +391,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
         __half2 h[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) h[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+        for (int e = 0; e < 16; ++e) {   // ReLU fused into the conversion (cvt.rn.relu.f16x2.f32)
+          const uint32_t u = pack_half2(f[2 * e], f[2 * e + 1], p.relu != 0);
+          h[e] = *reinterpret_cast<const __half2*>(&u);
+        }
         if (p.pool2) {
           // 2x2 window = lanes {m, m^1, m^tw, m^tw^1}: all inside this warp because tw <= 16.
           // max commutes with the (monotonic) fp16 rounding, so pooling the rounded values is exact.

@@ -64,6 +64,22 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// fp32 pair -> packed fp16x2 with round-to-nearest, optionally fused ReLU (cvt.rn.relu.f16x2.f32):
+// the low half holds `lo`.  ReLU commutes with the (monotonic) rounding, so this equals relu-then-round.
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi, bool relu) {
+  uint32_t r;
+  if (relu) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// Dynamic shared memory aligned up WITHOUT leaving the shared address space: offsetting the extern array by
+// an integer keeps LDS/STS code generation (a uintptr_t round-trip degrades every access to generic LD/ST).
+__device__ __forceinline__ uint8_t* align_smem(uint8_t* base, uint32_t alignment) {
+  const uint32_t a = smem_u32(base);
+  return base + (((a + alignment - 1) & ~(alignment - 1)) - a);
+}
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

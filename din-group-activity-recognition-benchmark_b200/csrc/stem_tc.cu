@@ -39,7 +39,8 @@ struct StemParams {
 template <int COUT, int KH, int KW, int STRIDE>
 struct StemCfg {
   static constexpr int kReal = 3 * KH * KW;
-  static constexpr int kPad = (kReal + 15) / 16 * 16;
+  static constexpr int kBiasK = kReal;                       // K columns kReal, kReal+1: A = 1, B = bias hi / lo
+  static constexpr int kPad = (kReal + 2 + 15) / 16 * 16;
   static constexpr int kSbo = kPad * 16;                      // bytes between 8-row groups
   static constexpr int kPatchW = 127 * STRIDE + KW;
   static constexpr int kPitch = kPatchW | 1;                  // odd pitch: bank spread for strided reads
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(kStemThreads)
 stem_tc_kernel(const StemParams p) {
   using Cfg = StemCfg<COUT, KH, KW, STRIDE>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* smem = align_smem(smem_raw, 128);
   uint8_t* a_s = smem;                                      // 16 row groups
   uint8_t* b_s = a_s + 16 * Cfg::kSbo;                      // COUT/8 row groups
   uint8_t* scratch = b_s + (COUT / 8) * Cfg::kSbo;          // 4 warps x 32 x 80 B
@@ -87,12 +88,20 @@ stem_tc_kernel(const StemParams p) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int k = kc * 8 + e;
-      // OIHW [c_out][3][kh][kw] flattened == [c_out][k] with k = (c*kh + ky)*kw + kx
-      hv[e] = __float2half_rn(k < Cfg::kReal ? __ldg(p.w + static_cast<size_t>(o) * Cfg::kReal + k) : 0.0f);
+      // OIHW [c_out][3][kh][kw] flattened == [c_out][k] with k = (c*kh + ky)*kw + kx.  The bias rides in two
+      // extra K columns (hi + lo fp16 parts, multiplied by A = 1): added exactly, in the fp32 accumulator.
+      float wv = 0.0f;
+      if (k < Cfg::kReal) {
+        wv = __ldg(p.w + static_cast<size_t>(o) * Cfg::kReal + k);
+      } else if (p.bias != nullptr && k <= Cfg::kBiasK + 1) {
+        const float bv = __ldg(p.bias + o);
+        const float bh = __half2float(__float2half_rn(bv));
+        wv = (k == Cfg::kBiasK) ? bh : bv - bh;
+      }
+      hv[e] = __float2half_rn(wv);
     }
     *reinterpret_cast<uint4*>(b_s + canon_off(o, kc, Cfg::kSbo)) = *reinterpret_cast<const uint4*>(hv);
   }
-  if (tid < COUT) bias_s[tid] = p.bias ? __ldg(p.bias + tid) : 0.0f;
   if (tid == 0) {
     mbar_init(mma_bar, 1);
     fence_mbar_init();
@@ -164,7 +173,7 @@ stem_tc_kernel(const StemParams p) {
               const int c = k / (KH * KW), r = k % (KH * KW);
               f[z] = prow[(c * KH + r / KW) * Cfg::kPitch + r % KW];
             } else {
-              f[z] = 0.0f;
+              f[z] = (k <= Cfg::kBiasK + 1) ? 1.0f : 0.0f;       // the two bias columns
             }
           }
           hv[e] = __floats2half2_rn(f[0], f[1]);
@@ -205,17 +214,13 @@ stem_tc_kernel(const StemParams p) {
       uint32_t v[32];
       tmem_ld_32x32b_x32(taddr + c0, v);
       tmem_ld_wait();
-      __half2 hh[16];
+      uint32_t hh[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float f0 = __uint_as_float(v[2 * j]) + bias_s[c0 + 2 * j];
-        float f1 = __uint_as_float(v[2 * j + 1]) + bias_s[c0 + 2 * j + 1];
-        if (p.relu) { f0 = fmaxf(f0, 0.0f); f1 = fmaxf(f1, 0.0f); }
-        hh[j] = __floats2half2_rn(f0, f1);
-      }
+      for (int j = 0; j < 16; ++j)
+        hh[j] = pack_half2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]), p.relu != 0);
       uint4* wr = reinterpret_cast<uint4*>(sc + lane * kEpiPitch);
 #pragma unroll
-      for (int u4 = 0; u4 < 4; ++u4) wr[u4] = *reinterpret_cast<uint4*>(&hh[4 * u4]);
+      for (int u4 = 0; u4 < 4; ++u4) wr[u4] = make_uint4(hh[4 * u4], hh[4 * u4 + 1], hh[4 * u4 + 2], hh[4 * u4 + 3]);
       __syncwarp();
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
