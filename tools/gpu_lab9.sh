@@ -1,0 +1,6 @@
+#!/bin/bash
+# full ncu capture of every conv launch of ONE step (2 clips = 20 frames: chunks of 16 + 4) for the roofline `traffic`
+mkdir -p gpurun_out
+timeout 1200 ncu --set full --clock-control none -k regex:"conv_igemm|stem_tc" -s 78 -c 28 -f -o gpurun_out/prof_step_v7 \
+   python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --clips-per-gpu 2 > gpurun_out/ncu_step.log 2>&1
+echo "ncu rc=$?"; tail -2 gpurun_out/ncu_step.log
