@@ -360,6 +360,7 @@ def main():
         "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, all launches of a step)",
                      "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["tflops_sustained"], "traffic": traffic,
+                     "traffic_unit": "DRAM bytes (read+write) per step in this kernel, ncu --set full (profiles/)",
                      "peak_source": peaks["source"] + ", sustained bf16 (= fp16 rate)",
                      "flops_per_step": conv_flops, "kernel_ms_per_step": conv_ms,
                      "kernel_share_of_step": conv_ms / all_ms,
