@@ -254,6 +254,9 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = ops.LAUNCHES
+    # per-launch CUDA events are recorded INSIDE the timed region (on the launching stream, no syncs), so the
+    # roofline numbers see the same sustained clocks as `value`
+    ops.RECORDER = []
     with ClockSampler(local_rank) as clocks:
         barrier()
         e0.record()
@@ -261,6 +264,7 @@ def main():
             out = step()
         e1.record()
         barrier()
+    rec, ops.RECORDER = ops.RECORDER, None
     launches = ops.LAUNCHES - launches0
     ms = e0.elapsed_time(e1)
     assert torch.isfinite(out).all()
@@ -311,15 +315,11 @@ def main():
         wall_e2e = (time.perf_counter() - t0) * 1e3
         e2e = {"ms": ms_e2e, "wall_ms": wall_e2e, "h2d": img_host.numel() * 4 + box_host.numel() * 4, "d2h": out_host.numel() * 4}
 
-    # ---- roofline of the dominant kernel: one extra (untimed) step with per-launch CUDA events
-    ops.RECORDER = []
-    step()
-    torch.cuda.synchronize()
-    rec, ops.RECORDER = ops.RECORDER, None
+    # ---- roofline of the dominant kernel from the events recorded in the timed region (per step averages)
     conv = [(n, f, b, a.elapsed_time(z)) for (n, f, b, a, z) in rec if n.startswith("conv")]
-    all_ms = sum(a.elapsed_time(z) for (_, _, _, a, z) in rec)
-    conv_ms = sum(t for *_, t in conv)
-    conv_flops = sum(f for _, f, _, _ in conv)
+    all_ms = sum(a.elapsed_time(z) for (_, _, _, a, z) in rec) / args.steps
+    conv_ms = sum(t for *_, t in conv) / args.steps
+    conv_flops = sum(f for _, f, _, _ in conv) / args.steps
     per_layer = {}
     for n, f, b, t in conv:
         e = per_layer.setdefault(n, [0, 0.0, 0])
@@ -328,7 +328,7 @@ def main():
     for (n, f, b, a, z) in rec:
         if not n.startswith("conv"):
             k = n.split("_")[0].split("@")[0]
-            other[k] = other.get(k, 0.0) + a.elapsed_time(z)
+            other[k] = other.get(k, 0.0) + a.elapsed_time(z) / args.steps
 
     if dist is not None:
         t = torch.tensor([ms, e2e["ms"] if e2e else 0.0], device=dev, dtype=torch.float64)
@@ -363,7 +363,8 @@ def main():
                      "traffic_unit": "DRAM bytes (read+write) per step in this kernel, ncu --set full (profiles/)",
                      "peak_source": peaks["source"] + ", sustained bf16 (= fp16 rate)",
                      "flops_per_step": conv_flops, "kernel_ms_per_step": conv_ms,
-                     "kernel_share_of_step": conv_ms / all_ms,
+                     "kernel_share_of_step": conv_ms / (ms / args.steps),
+                     "all_kernels_ms_per_step": all_ms,
                      "whole_path_tflops": value * gflop_per_clip / 1e3,
                      "whole_path_frac": value * gflop_per_clip / 1e3 / world / peaks["tflops_sustained"],
                      "other_kernels_ms": {k: round(v, 3) for k, v in sorted(other.items())},

@@ -104,7 +104,9 @@ __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
   return static_cast<uint64_t>(lo) | (static_cast<uint64_t>(hi) << 32);
 }
 
-template <int BN>
+// TB3 > 0 selects the statically unrolled issue path for 3x3 HALO convolutions (pitch 10, TB3 taps per weight
+// stage, no weight split): every descriptor offset is an immediate.
+template <int BN, int TB3>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const ConvKParams p) {
@@ -249,28 +251,54 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         for (int g = 0; g < a_groups; ++g) {
           mbar_wait(&a_full[sa], pa);
           const uint32_t a_lo = a_lo0 + sa * a_step;
-          int t = 0, kx = 0;
-          uint32_t row_off = 0, tap_off = 0;     // uniform: (ky*pitch + kx) * 8
-          for (int bg = 0; bg < b_groups; ++bg) {
-            const int nt = min(p.tb, taps_per_a - t);
-            mbar_wait(&b_full[sb], pb);
-            tc_fence_after_sync();
-            uint32_t b_lo = b_lo0 + sb * b_step;
-            for (int tt = 0; tt < nt; ++tt, ++t, b_lo += (kBBytes >> 4)) {
-              const uint32_t al = a_lo + tap_off;
+          if constexpr (TB3 > 0) {
+            // static 3x3: 9 taps, halo pitch 10 rows -> tap (ky,kx) starts (ky*10 + kx) * 8 sixteen-byte units in
+#pragma unroll
+            for (int bg = 0; bg < 9 / TB3; ++bg) {
+              mbar_wait(&b_full[sb], pb);
+              tc_fence_after_sync();
+              const uint32_t b_lo = b_lo0 + sb * b_step;
               if (leader) {
 #pragma unroll
-                for (int k = 0; k < kBK / 16; ++k)   // +32 bytes (2 x 16-byte units) per K=16 slice
-                  umma_f16_ss(d_tmem, desc64(al + 2u * k, a_hi), desc64(b_lo + 2u * k, b_hi), idesc,
-                              (k == 0) ? accum : 1u);
+                for (int tt = 0; tt < TB3; ++tt) {
+                  const int t = bg * TB3 + tt;
+                  const uint32_t al = a_lo + static_cast<uint32_t>(((t / 3) * 10 + (t % 3)) * 8);
+                  const uint32_t bl = b_lo + static_cast<uint32_t>(tt * (kBBytes >> 4));
+#pragma unroll
+                  for (int k = 0; k < kBK / 16; ++k)
+                    umma_f16_ss(d_tmem, desc64(al + 2u * k, a_hi), desc64(bl + 2u * k, b_hi), idesc,
+                                (bg == 0 && tt == 0 && k == 0) ? accum : 1u);
+                }
+                umma_commit(&b_empty[sb]);
               }
               accum = 1;
-              if (p.split == 1 || (t & 1)) {   // the lo part re-uses the A window of its hi part
-                if (++kx == p.kw) { kx = 0; row_off += pitch8; tap_off = row_off; } else { tap_off += kx8; }
-              }
+              if (++sb == p.n_b_stages) { sb = 0; pb ^= 1u; }
             }
-            if (leader) umma_commit(&b_empty[sb]);  // frees the weight slot when these MMAs retire
-            if (++sb == p.n_b_stages) { sb = 0; pb ^= 1u; }
+          } else {
+            // generic path: tap offsets from warp-uniform counters (never loaded from memory)
+            int t = 0, kx = 0;
+            uint32_t row_off = 0, tap_off = 0;     // uniform: (ky*pitch + kx) * 8
+            for (int bg = 0; bg < b_groups; ++bg) {
+              const int nt = min(p.tb, taps_per_a - t);
+              mbar_wait(&b_full[sb], pb);
+              tc_fence_after_sync();
+              uint32_t b_lo = b_lo0 + sb * b_step;
+              for (int tt = 0; tt < nt; ++tt, ++t, b_lo += (kBBytes >> 4)) {
+                const uint32_t al = a_lo + tap_off;
+                if (leader) {
+#pragma unroll
+                  for (int k = 0; k < kBK / 16; ++k)   // +32 bytes (2 x 16-byte units) per K=16 slice
+                    umma_f16_ss(d_tmem, desc64(al + 2u * k, a_hi), desc64(b_lo + 2u * k, b_hi), idesc,
+                                (k == 0) ? accum : 1u);
+                }
+                accum = 1;
+                if (p.split == 1 || (t & 1)) {   // the lo part re-uses the A window of its hi part
+                  if (++kx == p.kw) { kx = 0; row_off += pitch8; tap_off = row_off; } else { tap_off += kx8; }
+                }
+              }
+              if (leader) umma_commit(&b_empty[sb]);  // frees the weight slot when these MMAs retire
+              if (++sb == p.n_b_stages) { sb = 0; pb ^= 1u; }
+            }
           }
           if (leader) {
             umma_commit(&a_empty[sa]);                             // halo / tap tile fully consumed
@@ -440,18 +468,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
 }
 
-template <int BN>
+template <int BN, int TB3>
 int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvKParams& p, int grid, size_t smem,
                 cudaStream_t st) {
   static thread_local int attr_dev = -1;
   int dev = 0;
   DIN_CHECK_CUDA(cudaGetDevice(&dev));
   if (attr_dev != dev) {
-    DIN_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DIN_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, TB3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kSmemBudget + kNumEpiWarps * kEpiScratch + 4096 + 8192));
     attr_dev = dev;
   }
-  conv_igemm_kernel<BN><<<grid, kNumThreads, smem, st>>>(ta, tb, p);
+  conv_igemm_kernel<BN, TB3><<<grid, kNumThreads, smem, st>>>(ta, tb, p);
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;
 }
@@ -492,7 +520,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, const float* __r
     for (int t = 0; t < split * taps; ++t) orow[static_cast<size_t>(t) * c_in_p + c] = __float2half_rn(0.0f);
 }
 
-// Debug switch for GPU A/B runs: DIN_CONV_VARIANT bit2 (=4) forces TAP mode for every filter.
+// Debug switch for GPU A/B runs: DIN_CONV_VARIANT bit2 (=4) forces TAP mode for every filter, bit3 (=8)
+// disables the statically unrolled 3x3 issue path.
 // Unset = production default (HALO mode for stride-1 filters larger than 1x1).
 int conv_variant() {
   const char* e = std::getenv("DIN_CONV_VARIANT");
@@ -617,11 +646,13 @@ extern "C" int din_conv2d_nhwc_f16(const DinConvDesc* d, const void* x, const vo
   }
   DIN_CHECK_ARG(box_w <= 256 && box_h <= 256, "din_conv2d_nhwc_f16: TMA box too large");
   const int b_bytes = bn * kBK * 2;
+  const bool static3 = halo && d->kh == 3 && d->kw == 3 && p.split == 1 && !(variant >= 0 && (variant & 8));
   if (halo) {
     // several taps per weight stage: fewer barrier round-trips per MMA for the narrow-N layers
     p.tb = 40960 / b_bytes;
     if (p.tb < 1) p.tb = 1;
     if (p.tb > d->kh * d->kw * p.split) p.tb = d->kh * d->kw * p.split;
+    if (static3) p.tb = bn <= 64 ? 9 : (bn <= 128 ? 3 : 1);   // must match the TB3 template arguments below
     p.n_a_stages = 2;
     p.n_b_stages = (kSmemBudget - p.n_a_stages * p.a_stage_bytes) / (p.tb * b_bytes);
   } else {
@@ -665,11 +696,20 @@ extern "C" int din_conv2d_nhwc_f16(const DinConvDesc* d, const void* x, const vo
   DIN_CHECK_ARG(sms > 0, "din_conv2d_nhwc_f16: no CUDA device");
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (static3) {
+    switch (bn) {
+      case 256: return launch_conv<256, 1>(ta, tb, p, grid, smem, st);
+      case 192: return launch_conv<192, 1>(ta, tb, p, grid, smem, st);
+      case 128: return launch_conv<128, 3>(ta, tb, p, grid, smem, st);
+      case 96: return launch_conv<96, 3>(ta, tb, p, grid, smem, st);
+      default: return launch_conv<64, 9>(ta, tb, p, grid, smem, st);
+    }
+  }
   switch (bn) {
-    case 256: return launch_conv<256>(ta, tb, p, grid, smem, st);
-    case 192: return launch_conv<192>(ta, tb, p, grid, smem, st);
-    case 128: return launch_conv<128>(ta, tb, p, grid, smem, st);
-    case 96: return launch_conv<96>(ta, tb, p, grid, smem, st);
-    default: return launch_conv<64>(ta, tb, p, grid, smem, st);
+    case 256: return launch_conv<256, 0>(ta, tb, p, grid, smem, st);
+    case 192: return launch_conv<192, 0>(ta, tb, p, grid, smem, st);
+    case 128: return launch_conv<128, 0>(ta, tb, p, grid, smem, st);
+    case 96: return launch_conv<96, 0>(ta, tb, p, grid, smem, st);
+    default: return launch_conv<64, 0>(ta, tb, p, grid, smem, st);
   }
 }

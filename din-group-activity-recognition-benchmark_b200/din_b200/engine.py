@@ -17,6 +17,8 @@ nl_emb_1 -> ReLU -> (point_conv -> point_ln -> ReLU) -> DPI -> fuse + dpi_nl -> 
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -184,9 +186,11 @@ class DPIWeights:
 class DinEngine:
     """Forward plan for Dynamic_volleyball / Dynamic_collective built from a reference-named state_dict."""
 
-    def __init__(self, cfg, state_dict, device, dataset="volleyball", frames_per_chunk=16):
+    def __init__(self, cfg, state_dict, device, dataset="volleyball", frames_per_chunk=None):
         self.cfg, self.dataset, self.device = cfg, dataset, torch.device(device)
-        self.frames_per_chunk = frames_per_chunk
+        # frames per backbone launch: bounds the activation workspace (VGG-16 at 720p: 0.27 GB per frame
+        # live at once) while keeping every launch many waves long
+        self.frames_per_chunk = frames_per_chunk or int(os.environ.get("DIN_FRAMES_PER_CHUNK", "16"))
         sd = {k: v.detach().to(self.device, torch.float32) if v.is_floating_point() else v.detach().to(self.device)
               for k, v in state_dict.items()}
         self.T, self.N = cfg.num_frames, cfg.num_boxes
