@@ -45,6 +45,10 @@ WORKLOADS = {
     "volleyball_res18_lite128_T10_N12_720p": (
         dict(backbone="res18", image_size=(720, 1280), out_size=(23, 40), emb_features=512, num_frames=10,
              num_boxes=12, lite_dim=128, ST_kernel_size=[(3, 3)], sampling_ratio=(1,)), 32, 672.8),
+    # BASELINE.json configs[1]: Inception-v3, C = 1024 (no lite branch), B = 8 (patched oracle, SURVEY.md §8c bug I)
+    "volleyball_inv3_full_T10_N12_720p": (
+        dict(backbone="inv3", image_size=(720, 1280), out_size=(87, 157), emb_features=1056, num_frames=10,
+             num_boxes=12, lite_dim=None, ST_kernel_size=[(3, 3)], sampling_ratio=(1,)), 8, 1068.0),
 }
 DEFAULT_WORKLOAD = "volleyball_vgg16_lite128_T10_N12_720p"
 
