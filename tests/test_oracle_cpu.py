@@ -122,3 +122,17 @@ def test_oracle_vs_live_reference():
     ref = R.ref_forward(pc, sd, *batch)
     out = O.volleyball_forward(bb, sd, pc, *batch)
     assert (out - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+
+
+def test_config_defaults_match_reference():
+    """The drop-in Config exposes exactly the reference Config's attribute names and default values."""
+    import ref_harness as R
+    if not R.available():
+        pytest.skip("/root/reference not present on this machine")
+    ref_cfg = R.ref_module("config").Config
+    from config import Config
+    for ds in ("volleyball", "collective"):
+        a, b = vars(ref_cfg(ds)), vars(Config(ds))
+        assert set(a) == set(b), set(a) ^ set(b)
+        for k in a:
+            assert a[k] == b[k], (ds, k, a[k], b[k])
