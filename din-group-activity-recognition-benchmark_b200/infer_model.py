@@ -100,7 +100,9 @@ class _DinModel(nn.Module):
             self._engine_key = key
         return self._engine
 
-    def _check_mode(self):
+    def _check_mode(self, images):
+        if not images.is_cuda:
+            raise RuntimeError("the DIN hot path runs on sm_100a only: pass CUDA tensors (there is no CPU fallback)")
         if self.training and torch.is_grad_enabled():
             raise NotImplementedError(
                 "the sm_100a DIN path is forward-only in this release: use model.eval() and/or "
@@ -117,7 +119,7 @@ class Dynamic_volleyball(_DinModel):
 
     def forward(self, batch_data):
         images_in, boxes_in = batch_data
-        self._check_mode()
+        self._check_mode(images_in)
         with torch.cuda.device(images_in.device):
             scores = self.engine().forward_volleyball(images_in.float(), boxes_in.float())
         return {"activities": scores}
@@ -133,7 +135,7 @@ class Dynamic_collective(_DinModel):
 
     def forward(self, batch_data):
         images_in, boxes_in, bboxes_num_in = batch_data
-        self._check_mode()
+        self._check_mode(images_in)
         with torch.cuda.device(images_in.device):
             scores = self.engine().forward_collective(images_in.float(), boxes_in.float(), bboxes_num_in)
         return {"activities": scores}
