@@ -1,0 +1,130 @@
+"""Drop-in for the stage-1 base models of `base_model` (reference base_model.py:6-284).
+
+`Basenet_volleyball(cfg)` / `Basenet_collective(cfg)` keep the reference's constructor contract, module
+tree, state_dict key names, `savemodel` / `loadmodel` checkpoint format (the file `Dynamic_*.loadmodel`
+reads in stage 2: keys `backbone_state_dict`, `fc_emb_state_dict`, base_model.py:46-55,181-190) and
+`forward(batch) -> (actions_scores, activities_scores)`.  forward() runs the same sm_100a kernels as the
+stage-2 path (backbone plan, RoIAlign, tcgen05 embedding GEMM with the ReLU fused) plus the two small heads;
+torch modules below are parameter containers and are never called.
+
+Scope: evaluation / inference forward.
+"""
+import torch
+import torch.nn as nn
+
+from backbone.backbone import MyInception_v3, MyRes18, MyVGG16
+from din_b200.engine import BasenetEngine
+from roi_align.roi_align import RoIAlign
+
+
+class _Basenet(nn.Module):
+    _dataset = None
+    _emb_name = None
+
+    def _heads(self, cfg):
+        D, K, NFB = cfg.emb_features, cfg.crop_size[0], cfg.num_features_boxes
+        self.roi_align = RoIAlign(*cfg.crop_size)
+        setattr(self, self._emb_name, nn.Linear(K * K * D, NFB))
+        self.fc_actions = nn.Linear(NFB, cfg.num_actions)
+        self.fc_activities = nn.Linear(NFB, cfg.num_activities)
+        self._engine, self._engine_key = None, None
+
+    def savemodel(self, filepath):
+        state = {
+            "backbone_state_dict": self.backbone.state_dict(),
+            "fc_emb_state_dict": getattr(self, self._emb_name).state_dict(),
+            "fc_actions_state_dict": self.fc_actions.state_dict(),
+            "fc_activities_state_dict": self.fc_activities.state_dict(),
+        }
+        torch.save(state, filepath)
+        print("model saved to:", filepath)
+
+    def engine(self):
+        tensors = list(self.state_dict().values())
+        key = (str(tensors[0].device),) + tuple((t.data_ptr(), t._version) for t in tensors)
+        if self._engine_key != key:
+            dev = tensors[0].device
+            if dev.type != "cuda":
+                raise RuntimeError("the DIN hot path runs on sm_100a only: move the model to a CUDA device "
+                                   "(there is no CPU fallback)")
+            with torch.cuda.device(dev):
+                self._engine = BasenetEngine(self.cfg, self.state_dict(), dev, dataset=self._dataset,
+                                             emb_name=self._emb_name)
+            self._engine_key = key
+        return self._engine
+
+    def _check_mode(self, images):
+        if not images.is_cuda:
+            raise RuntimeError("the DIN hot path runs on sm_100a only: pass CUDA tensors (there is no CPU fallback)")
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError("the sm_100a stage-1 path is forward-only: use model.eval() and/or "
+                                      "torch.no_grad() (backward kernels: SURVEY.md §8f rank 1)")
+
+
+class Basenet_volleyball(_Basenet):
+    """reference base_model.py:6-142."""
+    _dataset, _emb_name = "volleyball", "fc_emb"
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        if cfg.backbone == "inv3":
+            self.backbone = MyInception_v3(transform_input=False, pretrained=True)
+        elif cfg.backbone == "vgg16":
+            self.backbone = MyVGG16(pretrained=True)
+        elif cfg.backbone == "res18":
+            self.backbone = MyRes18(pretrained=True)
+        else:
+            raise NotImplementedError(f"backbone {cfg.backbone!r} is outside the DIN hot-path scope")
+        self._heads(cfg)
+        self.dropout_emb = nn.Dropout(p=cfg.train_dropout_prob)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.kaiming_normal_(m.weight)
+                nn.init.zeros_(m.bias)
+
+    def loadmodel(self, filepath):
+        state = torch.load(filepath)
+        self.backbone.load_state_dict(state["backbone_state_dict"])
+        self.fc_emb.load_state_dict(state["fc_emb_state_dict"])
+        self.fc_actions.load_state_dict(state["fc_actions_state_dict"])
+        self.fc_activities.load_state_dict(state["fc_activities_state_dict"])
+        print("Load model states from: ", filepath)
+
+    def forward(self, batch_data):
+        images_in, boxes_in = batch_data
+        self._check_mode(images_in)
+        frames = images_in if images_in.dtype == torch.uint8 else images_in.float()
+        with torch.cuda.device(images_in.device):
+            return self.engine().forward_volleyball(frames, boxes_in.float())
+
+
+class Basenet_collective(_Basenet):
+    """reference base_model.py:145-284 (Inception-v3 hard-coded :159; actor count varies per frame)."""
+    _dataset, _emb_name = "collective", "fc_emb_1"
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        self.backbone = MyInception_v3(transform_input=False, pretrained=True)
+        if not cfg.train_backbone:
+            for p in self.backbone.parameters():
+                p.requires_grad = False
+        self._heads(cfg)
+        self.dropout_emb_1 = nn.Dropout(p=cfg.train_dropout_prob)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.kaiming_normal_(m.weight)
+
+    def loadmodel(self, filepath):
+        state = torch.load(filepath)
+        self.backbone.load_state_dict(state["backbone_state_dict"])
+        self.fc_emb_1.load_state_dict(state["fc_emb_state_dict"])
+        print("Load model states from: ", filepath)
+
+    def forward(self, batch_data):
+        images_in, boxes_in, bboxes_num_in = batch_data
+        self._check_mode(images_in)
+        frames = images_in if images_in.dtype == torch.uint8 else images_in.float()
+        with torch.cuda.device(images_in.device):
+            return self.engine().forward_collective(frames, boxes_in.float(), bboxes_num_in)

@@ -39,8 +39,9 @@ int din_encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int rank, void*
 int din_num_sms();
 
 // tensor-core stem convolution (stem_tc.cu); arguments already validated by din_stem_conv_nchw_f32
-int din_stem_tc_launch(const float* x, const float* w, const float* bias, void* y, int n, int h, int w_in,
-                       int c_out, int kh, int kw, int stride, int pad, int relu, int prep, cudaStream_t st);
+int din_stem_tc_launch(const void* x, int x_is_u8, const float* w, const float* bias, void* y, int n, int h,
+                       int w_in, int c_out, int kh, int kw, int stride, int pad, int relu, int prep,
+                       cudaStream_t st);
 
 #ifdef __CUDACC__
 namespace din {

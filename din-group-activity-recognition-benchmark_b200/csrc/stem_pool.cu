@@ -225,7 +225,7 @@ extern "C" int din_stem_conv_nchw_f32(const float* x, const float* w, const floa
     // convolution below — still a CUDA kernel of this library, not a fallback to another backend.
     const char* e = std::getenv("DIN_STEM_SIMT");
     if (!(e && e[0] == '1')) {
-      const int rc = din_stem_tc_launch(x, w, bias, y, n, h, w_in, c_out, kh, kw, stride, pad, relu, prep, st);
+      const int rc = din_stem_tc_launch(x, 0, w, bias, y, n, h, w_in, c_out, kh, kw, stride, pad, relu, prep, st);
       if (rc != DIN_ERR_UNSUPPORTED) return rc;
     }
   }
@@ -274,6 +274,24 @@ static int pool_common(const char* who, int avg, const void* x, void* y, int n, 
                                               x_c_stride / 8, y_c_stride / 8, oh, ow, k, stride, pad);
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;
+}
+
+extern "C" int din_stem_conv_nhwc_u8(const uint8_t* x, const float* w, const float* bias, void* y, int n, int h,
+                                     int w_in, int c_out, int kh, int kw, int stride, int pad, int relu, int prep,
+                                     void* stream) {
+  DIN_CHECK_ARG(x && w && y, "din_stem_conv_nhwc_u8: null pointer");
+  DIN_CHECK_ARG(n > 0 && h > 0 && w_in > 0, "din_stem_conv_nhwc_u8: bad extent n=%d h=%d w=%d", n, h, w_in);
+  DIN_CHECK_ARG(stride >= 1 && stride <= 2 && pad >= 0, "din_stem_conv_nhwc_u8: bad stride/pad");
+  DIN_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 15) == 0, "din_stem_conv_nhwc_u8: y must be 16-byte aligned");
+  DIN_CHECK_ARG((h + 2 * pad - kh) / stride + 1 > 0 && (w_in + 2 * pad - kw) / stride + 1 > 0,
+                "din_stem_conv_nhwc_u8: empty output");
+  const int rc = din_stem_tc_launch(x, 1, w, bias, y, n, h, w_in, c_out, kh, kw, stride, pad, relu, prep,
+                                    static_cast<cudaStream_t>(stream));
+  if (rc == DIN_ERR_UNSUPPORTED)
+    return din_set_error(DIN_ERR_UNSUPPORTED,
+                         "din_stem_conv_nhwc_u8: only the three backbone stems are instantiated (64x3x3 s1, 64x7x7 s2, "
+                         "32x3x3 s2), got c_out=%d %dx%d s%d", c_out, kh, kw, stride);
+  return rc;
 }
 
 extern "C" int din_maxpool2d_nhwc_f16(const void* x, void* y, int n, int h, int w, int c, int x_c_stride,

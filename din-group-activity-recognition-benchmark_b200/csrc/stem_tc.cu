@@ -28,7 +28,8 @@ constexpr int kStemThreads = 128;
 constexpr int kEpiPitch = 80;            // bytes per pixel row in the store-transpose scratch
 
 struct StemParams {
-  const float* x; const float* w; const float* bias; __half* y;
+  const void* x;          // fp32 NCHW [n,3,h,w]  or (U8) uint8 NHWC [n,h,w,3]
+  const float* w; const float* bias; __half* y;
   int n, h, w_in, oh, ow, pad, relu, prep;
   int strips_per_row;     // ceil(ow / 128)
   int num_tiles;          // n * oh * strips_per_row
@@ -65,7 +66,118 @@ __device__ __forceinline__ uint64_t desc_noswz(uint32_t addr, uint32_t lbo_bytes
   return d;
 }
 
-template <int COUT, int KH, int KW, int STRIDE>
+// Input patch of one tile held in registers between the global loads and the shared-memory staging, so that
+// the loads of tile i+1 are in flight while tile i is built, multiplied and stored (the kernel is a latency
+// chain per tile otherwise: global load -> smem -> im2col -> MMA -> TMEM -> store).
+//   fp32 NCHW: one float per (channel, filter row, column slot);  uint8 NHWC: the pixel's 3 bytes packed in
+//   one word per (filter row, column slot), bit 24 set = padding.
+template <int COUT, int KH, int KW, int STRIDE, bool U8>
+struct PatchRegs {
+  using Cfg = StemCfg<COUT, KH, KW, STRIDE>;
+  static constexpr int kN = U8 ? KH * Cfg::kLoadsPerRow : Cfg::kRows * Cfg::kLoadsPerRow;
+  uint32_t v[kN];
+};
+
+struct TileCoord { int img, oy, strip; };
+
+__device__ __forceinline__ TileCoord decode_tile(const StemParams& p, int tile) {
+  const int row = (__umulhi(tile, p.fd_mul) + tile) >> p.fd_shr;            // tile / strips_per_row
+  TileCoord t;
+  t.strip = tile - row * p.strips_per_row;
+  t.img = (__umulhi(row, p.fo_mul) + row) >> p.fo_shr;                      // row / oh
+  t.oy = row - t.img * p.oh;
+  return t;
+}
+
+template <int COUT, int KH, int KW, int STRIDE, bool U8>
+__device__ __forceinline__ void load_patch(const StemParams& p, const TileCoord& t, int tid,
+                                           PatchRegs<COUT, KH, KW, STRIDE, U8>& r) {
+  using Cfg = StemCfg<COUT, KH, KW, STRIDE>;
+  const int iy0 = t.oy * STRIDE - p.pad;
+  const int gx0 = t.strip * 128 * STRIDE - p.pad;
+  const size_t plane = static_cast<size_t>(p.h) * p.w_in;
+  if constexpr (U8) {
+    const uint8_t* xi = static_cast<const uint8_t*>(p.x) + static_cast<size_t>(t.img) * 3 * plane;
+#pragma unroll
+    for (int ky = 0; ky < KH; ++ky) {
+      const int gy = iy0 + ky;
+      const bool row_ok = gy >= 0 && gy < p.h;
+      const uint8_t* src = xi + static_cast<size_t>(row_ok ? gy : 0) * p.w_in * 3;
+#pragma unroll
+      for (int u = 0; u < Cfg::kLoadsPerRow; ++u) {
+        const int px = tid + u * kStemThreads;
+        const int gx = gx0 + px;
+        uint32_t w = 0x01000000u;
+        if (row_ok && px < Cfg::kPatchW && gx >= 0 && gx < p.w_in) {
+          const uint8_t* q = src + static_cast<size_t>(gx) * 3;
+          w = static_cast<uint32_t>(__ldg(q)) | (static_cast<uint32_t>(__ldg(q + 1)) << 8) |
+              (static_cast<uint32_t>(__ldg(q + 2)) << 16);
+        }
+        r.v[ky * Cfg::kLoadsPerRow + u] = w;
+      }
+    }
+  } else {
+    const float* xi = static_cast<const float*>(p.x) + static_cast<size_t>(t.img) * 3 * plane;
+    const float pad_val = p.prep ? 127.5f : 0.0f;                           // preps to exactly 0
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int ky = 0; ky < KH; ++ky) {
+        const int gy = iy0 + ky;
+        const bool row_ok = gy >= 0 && gy < p.h;
+        const float* src = xi + c * plane + static_cast<size_t>(row_ok ? gy : 0) * p.w_in;
+#pragma unroll
+        for (int u = 0; u < Cfg::kLoadsPerRow; ++u) {
+          const int px = tid + u * kStemThreads;
+          const int gx = gx0 + px;
+          const float f = (row_ok && px < Cfg::kPatchW && gx >= 0 && gx < p.w_in) ? __ldg(src + gx) : pad_val;
+          r.v[(c * KH + ky) * Cfg::kLoadsPerRow + u] = __float_as_uint(f);
+        }
+      }
+    }
+  }
+}
+
+// registers -> shared-memory patch [3*KH][kPitch] fp32, prep_images applied once per input element
+// (utils.py:14-17: (x/255 - 0.5)*2; the product by 1/255 differs from the division by at most 1 ulp(fp32),
+// far below the fp16 rounding applied next).  uint8 pixels convert exactly, so both ingest paths agree bit
+// for bit on equal pixel values.
+template <int COUT, int KH, int KW, int STRIDE, bool U8>
+__device__ __forceinline__ void stage_patch(const StemParams& p, int tid, float* patch,
+                                            const PatchRegs<COUT, KH, KW, STRIDE, U8>& r) {
+  using Cfg = StemCfg<COUT, KH, KW, STRIDE>;
+  if constexpr (U8) {
+#pragma unroll
+    for (int ky = 0; ky < KH; ++ky) {
+#pragma unroll
+      for (int u = 0; u < Cfg::kLoadsPerRow; ++u) {
+        const int px = tid + u * kStemThreads;
+        if (px < Cfg::kPatchW) {
+          const uint32_t w = r.v[ky * Cfg::kLoadsPerRow + u];
+          const bool is_pad = (w >> 24) != 0;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float f = static_cast<float>((w >> (8 * c)) & 0xFFu);
+            const float g = p.prep ? (f * (1.0f / 255.0f) - 0.5f) * 2.0f : f;
+            patch[(c * KH + ky) * Cfg::kPitch + px] = is_pad ? 0.0f : g;
+          }
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int rr = 0; rr < Cfg::kRows; ++rr) {
+#pragma unroll
+      for (int u = 0; u < Cfg::kLoadsPerRow; ++u) {
+        const int px = tid + u * kStemThreads;
+        const float f = __uint_as_float(r.v[rr * Cfg::kLoadsPerRow + u]);
+        if (px < Cfg::kPatchW) patch[rr * Cfg::kPitch + px] = p.prep ? (f * (1.0f / 255.0f) - 0.5f) * 2.0f : f;
+      }
+    }
+  }
+}
+
+template <int COUT, int KH, int KW, int STRIDE, bool U8>
 __global__ void __launch_bounds__(kStemThreads)
 stem_tc_kernel(const StemParams p) {
   using Cfg = StemCfg<COUT, KH, KW, STRIDE>;
@@ -80,6 +192,11 @@ stem_tc_kernel(const StemParams p) {
   float* patch = reinterpret_cast<float*>(tmem_ptr_smem + 4);               // [3*KH][kPitch] prep'd input rows
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // first tile's input loads go out before the one-time setup
+  PatchRegs<COUT, KH, KW, STRIDE, U8> regs;
+  TileCoord cur = decode_tile(p, blockIdx.x);
+  load_patch<COUT, KH, KW, STRIDE, U8>(p, cur, tid, regs);
 
   // ---- one-time setup: weights in UMMA layout, bias, barrier, TMEM
   for (int i = tid; i < COUT * (Cfg::kPad / 8); i += kStemThreads) {
@@ -113,50 +230,16 @@ stem_tc_kernel(const StemParams p) {
   tc_fence_after_sync();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);   // warp-uniform for UTCHMMA / LDTM
   constexpr uint32_t idesc = umma_idesc_f16_f32(128, COUT);
-  const size_t plane = static_cast<size_t>(p.h) * p.w_in;
-  const float pad_val = p.prep ? 127.5f : 0.0f;                               // preps to exactly 0
 
   uint32_t phase = 0;
   for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-    const int row = (__umulhi(tile, p.fd_mul) + tile) >> p.fd_shr;            // tile / strips_per_row
-    const int strip = tile - row * p.strips_per_row;
-    const int img = (__umulhi(row, p.fo_mul) + row) >> p.fo_shr;              // row / oh
-    const int oy = row - img * p.oh;
-    const float* xi = p.x + static_cast<size_t>(img) * 3 * plane;
-    const int iy0 = oy * STRIDE - p.pad;
-    const int gx0 = strip * 128 * STRIDE - p.pad;
-
-    // ---- stage the strip's input patch (all loads issued before the first use)
-    {
-      float v[Cfg::kRows][Cfg::kLoadsPerRow];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-#pragma unroll
-        for (int ky = 0; ky < KH; ++ky) {
-          const int gy = iy0 + ky;
-          const bool row_ok = gy >= 0 && gy < p.h;
-          const float* src = xi + c * plane + static_cast<size_t>(row_ok ? gy : 0) * p.w_in;
-#pragma unroll
-          for (int u = 0; u < Cfg::kLoadsPerRow; ++u) {
-            const int px = tid + u * kStemThreads;
-            const int gx = gx0 + px;
-            v[c * KH + ky][u] = (row_ok && px < Cfg::kPatchW && gx >= 0 && gx < p.w_in) ? __ldg(src + gx) : pad_val;
-          }
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < Cfg::kRows; ++r) {
-#pragma unroll
-        for (int u = 0; u < Cfg::kLoadsPerRow; ++u) {
-          const int px = tid + u * kStemThreads;
-          // prep_images (utils.py:14-17): (x/255 - 0.5)*2; the product by 1/255 differs from the division
-          // by at most 1 ulp(fp32), far below the fp16 rounding applied next
-          if (px < Cfg::kPatchW)
-            patch[r * Cfg::kPitch + px] = p.prep ? (v[r][u] * (1.0f / 255.0f) - 0.5f) * 2.0f : v[r][u];
-        }
-      }
-    }
+    const int img = cur.img, oy = cur.oy, strip = cur.strip;
+    stage_patch<COUT, KH, KW, STRIDE, U8>(p, tid, patch, regs);
     __syncthreads();
+    if (tile + static_cast<int>(gridDim.x) < p.num_tiles) {     // next tile's loads fly during this tile's work
+      cur = decode_tile(p, tile + gridDim.x);
+      load_patch<COUT, KH, KW, STRIDE, U8>(p, cur, tid, regs);
+    }
     // ---- im2col row of this thread's pixel -> A tile (canonical UMMA layout); all offsets are immediates
     {
       const float* prow = patch + tid * STRIDE;
@@ -252,7 +335,7 @@ void fastdiv(uint32_t d, uint32_t* mul, uint32_t* shr) {
   *mul = static_cast<uint32_t>(((static_cast<uint64_t>(1) << 32) * ((static_cast<uint64_t>(1) << l) - d)) / d + 1);
 }
 
-template <int COUT, int KH, int KW, int STRIDE>
+template <int COUT, int KH, int KW, int STRIDE, bool U8>
 int launch(StemParams& p, cudaStream_t st) {
   using Cfg = StemCfg<COUT, KH, KW, STRIDE>;
   const int sms = din_num_sms();
@@ -263,19 +346,30 @@ int launch(StemParams& p, cudaStream_t st) {
   if (per_sm < 1) per_sm = 1;
   long long grid = static_cast<long long>(sms > 0 ? sms : 148) * per_sm;
   if (grid > p.num_tiles) grid = p.num_tiles;
-  DIN_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel<COUT, KH, KW, STRIDE>,
+  DIN_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel<COUT, KH, KW, STRIDE, U8>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Cfg::kSmem)));
-  stem_tc_kernel<COUT, KH, KW, STRIDE><<<static_cast<int>(grid), kStemThreads, Cfg::kSmem, st>>>(p);
+  stem_tc_kernel<COUT, KH, KW, STRIDE, U8><<<static_cast<int>(grid), kStemThreads, Cfg::kSmem, st>>>(p);
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;
 }
 
+template <bool U8>
+int dispatch(StemParams& p, int c_out, int kh, int kw, int stride, cudaStream_t st) {
+  if (c_out == 64 && kh == 3 && kw == 3 && stride == 1) return launch<64, 3, 3, 1, U8>(p, st);   // VGG-16
+  if (c_out == 64 && kh == 7 && kw == 7 && stride == 2) return launch<64, 7, 7, 2, U8>(p, st);   // ResNet-18
+  if (c_out == 32 && kh == 3 && kw == 3 && stride == 2) return launch<32, 3, 3, 2, U8>(p, st);   // Inception-v3
+  return DIN_ERR_UNSUPPORTED;
+}
+
 }  // namespace
 
-// Returns DIN_ERR_UNSUPPORTED for filter geometries without a tensor-core instantiation (the caller then
+// x_is_u8 == 0: x is fp32 NCHW [n,3,h,w];  != 0: x is uint8 NHWC [n,h,w,3] (the decoded frame as the loader
+// holds it before `img.transpose(2,0,1)` / `.float()`, volleyball.py:239-243,270).
+// Returns DIN_ERR_UNSUPPORTED for filter geometries without a tensor-core instantiation (the fp32 caller then
 // uses the generic CUDA-core kernel in stem_pool.cu).
-int din_stem_tc_launch(const float* x, const float* w, const float* bias, void* y, int n, int h, int w_in,
-                       int c_out, int kh, int kw, int stride, int pad, int relu, int prep, cudaStream_t st) {
+int din_stem_tc_launch(const void* x, int x_is_u8, const float* w, const float* bias, void* y, int n, int h,
+                       int w_in, int c_out, int kh, int kw, int stride, int pad, int relu, int prep,
+                       cudaStream_t st) {
   StemParams p{};
   p.x = x; p.w = w; p.bias = bias; p.y = static_cast<__half*>(y);
   p.n = n; p.h = h; p.w_in = w_in;
@@ -284,12 +378,9 @@ int din_stem_tc_launch(const float* x, const float* w, const float* bias, void* 
   p.pad = pad; p.relu = relu; p.prep = prep;
   p.strips_per_row = (p.ow + 127) / 128;
   const long long tiles = static_cast<long long>(n) * p.oh * p.strips_per_row;
-  if (tiles >= INT32_MAX) return din_set_error(DIN_ERR_INVALID_ARG, "din_stem_conv_nchw_f32: too many tiles");
+  if (tiles >= INT32_MAX) return din_set_error(DIN_ERR_INVALID_ARG, "din_stem_conv: too many tiles");
   p.num_tiles = static_cast<int>(tiles);
   fastdiv(static_cast<uint32_t>(p.strips_per_row), &p.fd_mul, &p.fd_shr);
   fastdiv(static_cast<uint32_t>(p.oh), &p.fo_mul, &p.fo_shr);
-  if (c_out == 64 && kh == 3 && kw == 3 && stride == 1) return launch<64, 3, 3, 1>(p, st);   // VGG-16
-  if (c_out == 64 && kh == 7 && kw == 7 && stride == 2) return launch<64, 7, 7, 2>(p, st);   // ResNet-18
-  if (c_out == 32 && kh == 3 && kw == 3 && stride == 2) return launch<32, 3, 3, 2>(p, st);   // Inception-v3
-  return DIN_ERR_UNSUPPORTED;
+  return x_is_u8 ? dispatch<true>(p, c_out, kh, kw, stride, st) : dispatch<false>(p, c_out, kh, kw, stride, st);
 }

@@ -27,6 +27,7 @@ PROTOTYPES = {
     "din_last_error_string": (C.c_char_p, []),
     "din_device_sm_count": (C.c_int, []),
     "din_stem_conv_nchw_f32": (C.c_int, [_fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "din_stem_conv_nhwc_u8": (C.c_int, [_vp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_conv2d_nhwc_f16": (C.c_int, [C.POINTER(DinConvDesc), _vp, _vp, _fp, _vp, _vp, _vp]),
     "din_pack_conv_weight_f16": (C.c_int, [_fp, _fp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "din_maxpool2d_nhwc_f16": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
@@ -39,6 +40,8 @@ PROTOTYPES = {
     "din_dynamic_infer_f32": (C.c_int, [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _fp, C.c_float,
                                         _i, _vp, _vp]),
     "din_readout_f32": (C.c_int, [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "din_ce_metrics_f32": (C.c_int, [_fp, _vp, _fp, C.c_float, _fp, _vp, _vp, _vp, _fp, _i, _i, _vp]),
+    "din_mean_axis_f32": (C.c_int, [_fp, _fp, _i, _i, _i, _vp]),
 }
 
 _lock = threading.Lock()

@@ -5,7 +5,8 @@ weight version), owns the activation workspaces, and issues the kernel sequence 
 (`ops.py`).  No arithmetic happens in Python/torch here.
 
 Data layout in HBM
-  images        fp32 NCHW [B*T, 3, H, W]        raw 0..255, as the reference's loader produces them
+  images        fp32 NCHW [B*T, 3, H, W]        raw 0..255, as the reference's loader produces them, or
+                uint8 NHWC [B*T, H, W, 3]       the decoded frame before the loader's transpose + float()
   activations   fp16 NHWC, two ping-pong slabs sized for the largest layer of one frame chunk
   feature map   fp16 NHWC [B*T, OH, OW, D]      all frames (0.9 MB / frame for VGG-16)
   crops         fp16 [B*T*N, 25, D]             RoIAlign output == A operand of the embedding GEMM
@@ -241,9 +242,23 @@ class DinEngine:
                 .repeat_interleave(n_boxes).contiguous()
         return self._idx_cache[key]
 
+    @staticmethod
+    def _flat_frames(images):
+        """[B,T,3,H,W] fp32 (volleyball.py:243,270) or [B,T,H,W,3] uint8 (the frame before the loader's
+        transpose / float conversion) -> the same with B and T merged."""
+        if images.dtype == torch.uint8:
+            if images.dim() != 5 or images.shape[-1] != 3:
+                raise ValueError(f"uint8 images must be [B,T,H,W,3], got {tuple(images.shape)}")
+        elif images.dtype != torch.float32 or images.dim() != 5 or images.shape[2] != 3:
+            raise ValueError(f"images must be fp32 [B,T,3,H,W] or uint8 [B,T,H,W,3], got {images.dtype} "
+                             f"{tuple(images.shape)}")
+        return images.reshape((-1,) + tuple(images.shape[2:])).contiguous()
+
     def features(self, images_flat):
-        """[F,3,H,W] fp32 raw -> NHWC fp16 [F,OH,OW,D] (prep_images + backbone), chunked over frames."""
-        F_, _, H, W = images_flat.shape
+        """[F,3,H,W] fp32 raw (or [F,H,W,3] uint8) -> NHWC fp16 [F,OH,OW,D] (prep_images + backbone), chunked
+        over frames."""
+        F_ = images_flat.shape[0]
+        H, W = images_flat.shape[1:3] if images_flat.dtype == torch.uint8 else images_flat.shape[2:4]
         oh, ow, d = self.backbone.out_shape(H, W)
         assert d == self.D_stride, (d, self.D_stride)
         key = (F_, oh, ow, d)
@@ -273,8 +288,7 @@ class DinEngine:
     def forward_volleyball(self, images, boxes):
         B, T = images.shape[:2]
         N = self.N
-        H, W = images.shape[-2:]
-        fm = self.features(images.reshape(B * T, 3, H, W))
+        fm = self.features(self._flat_frames(images))
         OH, OW = self.cfg.out_size
         assert fm.shape[1:3] == (OH, OW), (tuple(fm.shape), self.cfg.out_size)          # infer_model.py:165
         x = self.embed(fm, boxes.reshape(B * T * N, 4).contiguous().float(), B, T, N)
@@ -297,8 +311,7 @@ class DinEngine:
     def forward_collective(self, images, boxes, bboxes_num):
         B, T = images.shape[:2]
         N = self.N                                                                      # MAX_N
-        H, W = images.shape[-2:]
-        fm = self.features(images.reshape(B * T, 3, H, W))
+        fm = self.features(self._flat_frames(images))
         x = self.embed(fm, boxes.reshape(B * T * N, 4).contiguous().float(), B, T, N)
         n_valid = bboxes_num.reshape(B, T)[:, 0].to(torch.int32).contiguous()           # :1289
         g = self.dpis[0](x, n_valid=n_valid)
@@ -308,3 +321,65 @@ class DinEngine:
                             inner_stride=self.C, rows=T, row_stride=N * self.C, cols=self.C, relu=True, pre=x,
                             n_valid=n_valid, out=s)
         return ops.readout(s, *self.fc_act, n_valid=n_valid)
+
+
+class BasenetEngine:
+    """Forward plan of the stage-1 base models (reference base_model.py:64-142, 200-284): the stage-2 path's
+    backbone + RoIAlign + embedding GEMM (ReLU fused in its epilogue), then fc_actions per actor and
+    max-over-actors -> fc_activities."""
+
+    def __init__(self, cfg, state_dict, device, dataset="volleyball", emb_name="fc_emb"):
+        self.cfg, self.dataset, self.device = cfg, dataset, torch.device(device)
+        self.frames_per_chunk = int(os.environ.get("DIN_FRAMES_PER_CHUNK", "16"))
+        sd = {k: v.detach().to(self.device, torch.float32) if v.is_floating_point() else v.detach().to(self.device)
+              for k, v in state_dict.items()}
+        self.N, self.D, self.K, self.NFB = cfg.num_boxes, cfg.emb_features, cfg.crop_size[0], cfg.num_features_boxes
+        self.backbone_name = "inv3" if dataset == "collective" else cfg.backbone       # base_model.py:159
+        self.backbone = build_backbone_plan(self.backbone_name, sd)
+        self.D_stride = (self.D + 63) // 64 * 64
+        w = sd[emb_name + ".weight"].view(self.NFB, self.D, self.K * self.K).permute(0, 2, 1)
+        wp = torch.zeros((self.NFB, self.K * self.K, self.D_stride), dtype=torch.float32, device=self.device)
+        wp[:, :, :self.D] = w
+        self.fc_emb = _Conv(wp.view(self.NFB, self.K * self.K * self.D_stride, 1, 1), sd[emb_name + ".bias"],
+                            relu=True, split=2 if self.backbone_name == "inv3" else 1)
+        self.fc_actions = (sd["fc_actions.weight"].contiguous(), sd["fc_actions.bias"].contiguous())
+        self.fc_act = (sd["fc_activities.weight"].contiguous(), sd["fc_activities.bias"].contiguous())
+        self._idx_cache, self._fm_cache = {}, None
+
+    _box_idx = DinEngine._box_idx
+    _flat_frames = staticmethod(DinEngine._flat_frames)
+    features = DinEngine.features
+
+    def _states(self, images, boxes, B, T, N):
+        fm = self.features(self._flat_frames(images))
+        OH, OW = self.cfg.out_size
+        assert fm.shape[1:3] == (OH, OW), (tuple(fm.shape), self.cfg.out_size)
+        M = B * T * N
+        crops = ops.roi_align_nhwc(fm, boxes.reshape(M, 4).contiguous().float(), self._box_idx(B * T, N), self.K,
+                                   self.K, d=self.D_stride)
+        # fc_emb + ReLU (base_model.py:119-120): ReLU fused in the GEMM epilogue, fp32 out
+        return self.fc_emb(crops.view(1, 1, M, self.K * self.K * self.D_stride), out_f32=True).view(M, self.NFB)
+
+    @torch.no_grad()
+    def forward_volleyball(self, images, boxes):
+        B, T = images.shape[:2]
+        N = self.N
+        x = self._states(images, boxes, B, T, N)                                        # [B*T*N, NFB]
+        actions = ops.linear_f32(x, *self.fc_actions)                                   # :129
+        activities = ops.readout(x.view(B, T, N, self.NFB), *self.fc_act)               # :133-136,140 (mean over T)
+        if T != 1:                                                                      # :138-139
+            actions = ops.mean_axis(actions.view(B, T, N * actions.shape[-1]), 1)
+        return actions.view(B * N, -1), activities
+
+    @torch.no_grad()
+    def forward_collective(self, images, boxes, bboxes_num):
+        B, T = images.shape[:2]
+        N = self.N                                                                      # MAX_N
+        x = self._states(images, boxes, B, T, N)
+        n_valid = bboxes_num.reshape(B * T).to(torch.int32).contiguous()                # per FRAME (:252)
+        actions_all = ops.linear_f32(x, *self.fc_actions)                               # [B*T*MAX_N, A]
+        activities = ops.readout(x.view(B * T, 1, N, self.NFB), *self.fc_act, n_valid=n_valid)   # [B*T, A]
+        # the reference concatenates the first N_bt rows of every frame (:256-279): a ragged gather whose
+        # size the host must know, exactly as the reference's Python loop does (one sync on bboxes_num)
+        keep = (torch.arange(N, device=self.device).view(1, N) < n_valid.view(B * T, 1)).reshape(-1)
+        return actions_all[keep.nonzero(as_tuple=True)[0]], activities

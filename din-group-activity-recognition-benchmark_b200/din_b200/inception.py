@@ -120,8 +120,10 @@ class Inv3Plan:
         return h, w, D_STRIDE
 
     def __call__(self, images, out=None):
-        """raw fp32 NCHW frames -> multiscale map [F, OH, OW, 1088] (channels [0,1056) valid, rest untouched)."""
-        F_, _, H, W = images.shape
+        """raw frames (fp32 NCHW or uint8 NHWC) -> multiscale map [F, OH, OW, 1088] (channels [0,1056) valid,
+        rest untouched)."""
+        F_ = images.shape[0]
+        H, W = images.shape[1:3] if images.dtype == torch.uint8 else images.shape[2:4]
         oh, ow, _ = self.out_shape(H, W)
         dev = images.device
         if out is None:

@@ -111,24 +111,29 @@ def conv2d_nhwc(x, w_packed, bias=None, *, stride=1, pad=(0, 0), relu=False, res
     return out
 
 
-def stem_conv(x_nchw, w_oihw, bias, *, stride=1, pad=0, relu=True, prep=True):
-    """Raw fp32 NCHW images (0..255) -> prep_images -> conv(+bias,+ReLU) -> NHWC fp16."""
-    _need(x_nchw, torch.float32, "x_nchw")
+def stem_conv(x, w_oihw, bias, *, stride=1, pad=0, relu=True, prep=True):
+    """Raw images (0..255) -> prep_images -> conv(+bias,+ReLU) -> NHWC fp16.
+    x: fp32 NCHW [n,3,h,w] (the reference loader's tensor) or uint8 NHWC [n,h,w,3] (the decoded frame)."""
     _need(w_oihw, torch.float32, "w_oihw")
-    n, c, h, w = x_nchw.shape
+    u8 = isinstance(x, torch.Tensor) and x.dtype == torch.uint8
+    _need(x, torch.uint8 if u8 else torch.float32, "x")
+    if u8:
+        n, h, w, c = x.shape
+    else:
+        n, c, h, w = x.shape
     assert c == 3
     co, ci, kh, kw = w_oihw.shape
     assert ci == 3
     oh = (h + 2 * pad - kh) // stride + 1
     ow = (w + 2 * pad - kw) // stride + 1
-    y = torch.empty((n, oh, ow, co), dtype=torch.float16, device=x_nchw.device)
+    y = torch.empty((n, oh, ow, co), dtype=torch.float16, device=x.device)
     if bias is not None:
         _need(bias, torch.float32, "bias")
-    with _launch(f"stem{kh}x{kw}s{stride}_3->{co}@{oh}x{ow}", 2 * n * oh * ow * co * kh * kw * 3,
-                 4 * n * 3 * h * w + 2 * n * oh * ow * co):
-        check(_lib.load().din_stem_conv_nchw_f32(_p(x_nchw), _p(w_oihw), _p(bias), _p(y), n, h, w, co, kh, kw,
-                                                 stride, pad, int(relu), int(prep), _stream()),
-              "din_stem_conv_nchw_f32")
+    fn = "din_stem_conv_nhwc_u8" if u8 else "din_stem_conv_nchw_f32"
+    with _launch(f"stem{kh}x{kw}s{stride}_3->{co}@{oh}x{ow}" + ("_u8" if u8 else ""),
+                 2 * n * oh * ow * co * kh * kw * 3, (1 if u8 else 4) * n * 3 * h * w + 2 * n * oh * ow * co):
+        check(getattr(_lib.load(), fn)(_p(x), _p(w_oihw), _p(bias), _p(y), n, h, w, co, kh, kw, stride, pad,
+                                       int(relu), int(prep), _stream()), fn)
     return y
 
 
@@ -266,3 +271,47 @@ def readout(s, w, bias, n_valid=None):
         check(_lib.load().din_readout_f32(_p(s), _p(w), _p(bias), _p(out), b, t, n, c, a, _p(n_valid), _stream()),
               "din_readout_f32")
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# after the path: loss / metrics on the device, stage-1 helper
+# ---------------------------------------------------------------------------------------------
+def ce_metrics(logits, labels, *, class_weight=None, loss_scale=1.0, conf=None, meters=None, want_grad=False):
+    """One launch: (loss [1], correct [1] int32, dlogits or None).  conf [a,a] int32 and meters [4] fp64 accumulate."""
+    _need(logits, torch.float32, "logits")
+    _need(labels, torch.int64, "labels")
+    b, a = logits.shape
+    assert labels.shape == (b,), (labels.shape, b)
+    if class_weight is not None:
+        _need(class_weight, torch.float32, "class_weight")
+        assert class_weight.shape == (a,)
+    if conf is not None:
+        _need(conf, torch.int32, "conf")
+        assert conf.shape == (a, a)
+    if meters is not None:
+        _need(meters, torch.float64, "meters")
+        assert meters.shape == (4,)
+    loss = torch.empty((1,), dtype=torch.float32, device=logits.device)
+    correct = torch.empty((1,), dtype=torch.int32, device=logits.device)
+    dlogits = torch.empty_like(logits) if want_grad else None
+    with _launch("ce_metrics", 0, 4 * b * a * (2 if want_grad else 1)):
+        check(_lib.load().din_ce_metrics_f32(_p(logits), _p(labels), _p(class_weight), float(loss_scale), _p(loss),
+                                             _p(correct), _p(conf), _p(meters), _p(dlogits), b, a, _stream()),
+              "din_ce_metrics_f32")
+    return loss, correct, dlogits
+
+
+def mean_axis(x, dim):
+    """fp32 mean over one axis (kept dims removed)."""
+    _need(x, torch.float32, "x")
+    shape = list(x.shape)
+    outer = 1
+    for s in shape[:dim]:
+        outer *= s
+    inner = 1
+    for s in shape[dim + 1:]:
+        inner *= s
+    y = torch.empty(shape[:dim] + shape[dim + 1:], dtype=torch.float32, device=x.device)
+    with _launch("mean_axis", 0, 4 * (x.numel() + y.numel())):
+        check(_lib.load().din_mean_axis_f32(_p(x), _p(y), outer, shape[dim], inner, _stream()), "din_mean_axis_f32")
+    return y

@@ -21,6 +21,12 @@ from roi_align.roi_align import RoIAlign
 from utils import print_log
 
 
+def _as_frames(images):
+    """fp32 [B,T,3,H,W] as the reference loader yields it (other float dtypes are converted); uint8
+    [B,T,H,W,3] (decoded frames, no transpose / float conversion) goes to the uint8-ingest stem as is."""
+    return images if images.dtype == torch.uint8 else images.float()
+
+
 def _make_backbone(cfg):
     if cfg.backbone == "inv3":
         return MyInception_v3(transform_input=False, pretrained=True)
@@ -121,7 +127,7 @@ class Dynamic_volleyball(_DinModel):
         images_in, boxes_in = batch_data
         self._check_mode(images_in)
         with torch.cuda.device(images_in.device):
-            scores = self.engine().forward_volleyball(images_in.float(), boxes_in.float())
+            scores = self.engine().forward_volleyball(_as_frames(images_in), boxes_in.float())
         return {"activities": scores}
 
 
@@ -137,7 +143,7 @@ class Dynamic_collective(_DinModel):
         images_in, boxes_in, bboxes_num_in = batch_data
         self._check_mode(images_in)
         with torch.cuda.device(images_in.device):
-            scores = self.engine().forward_collective(images_in.float(), boxes_in.float(), bboxes_num_in)
+            scores = self.engine().forward_collective(_as_frames(images_in), boxes_in.float(), bboxes_num_in)
         return {"activities": scores}
 
 

@@ -66,6 +66,19 @@ DIN_API int din_stem_conv_nchw_f32(const float* x, const float* w, const float* 
                            void* stream);
 
 /*
+ * The same stem with uint8 NHWC ingest: the decoded frame exactly as the reference's loader holds it before
+ * `img.transpose(2,0,1)` and `.float()` (volleyball.py:239-243,270; collective.py:189-193) -- 4x fewer bytes
+ * over PCIe and HBM than the fp32 CHW tensor; uint8 -> fp32 is exact, so the result is bit-identical to
+ * din_stem_conv_nchw_f32 on the same pixel values.  Replaces the loader's transpose + float conversion in
+ * addition to what din_stem_conv_nchw_f32 replaces.
+ * x : [n, h, w, 3] uint8.  Only the three backbone stems are instantiated (c_out/kh/kw/stride = 64/3/3/1,
+ * 64/7/7/2, 32/3/3/2); anything else returns DIN_ERR_UNSUPPORTED.
+ */
+DIN_API int din_stem_conv_nhwc_u8(const uint8_t* x, const float* w, const float* bias, void* y, int n, int h,
+                          int w_in, int c_out, int kh, int kw, int stride, int pad, int relu, int prep,
+                          void* stream);
+
+/*
  * Implicit-GEMM convolution on the tcgen05 tensor cores (TMA-staged fp16 operands, fp32 TMEM
  * accumulators), fused bias (+ residual) (+ ReLU) epilogue.  Also serves as the dense GEMM of the
  * path (kh = kw = 1, n = h = 1, w = rows).
@@ -201,6 +214,32 @@ DIN_API int din_dynamic_infer_f32(const float* x, const float* w_tap, const floa
  */
 DIN_API int din_readout_f32(const float* s, const float* w, const float* bias, float* logits, int b, int t,
                             int n, int c, int a, const int32_t* n_valid, void* stream);
+
+/* ---- after the path: loss / metrics on the device, stage-1 helper ------- */
+
+/*
+ * Cross-entropy (mean reduction, optional class weights), argmax, correct count, confusion matrix and
+ * epoch meters in ONE launch, with d(loss)/d(logits) for the backward pass; nothing is copied to the host.
+ * Replaces: F.cross_entropy / torch.argmax / torch.eq().sum() / .item() / ConfusionMeter.add /
+ *   AverageMeter.update per step (train_net_dynamic.py:191-199, 201-210, 217, 258-292; utils.py:193-264).
+ * logits       : fp32 [b, a];  labels: int64 [b] (labels outside [0, a) are ignored, like ignore_index)
+ * class_weight : fp32 [a] or NULL (cfg.actions_weights, train_net_dynamic.py:203-204)
+ * loss         : fp32 [1] = loss_scale * sum_i w[y_i] nll_i / sum_i w[y_i]             (or NULL)
+ * correct      : int32 [1] number of rows whose first arg-max equals the label (overwritten; or NULL)
+ * conf         : int32 [a, a], conf[target][predicted] += 1 (ACCUMULATES across calls; or NULL)
+ * meters       : fp64 [4] ACCUMULATING: sum(loss * b), sum(b), sum(correct), steps        (or NULL)
+ * dlogits      : fp32 [b, a] = loss_scale * w[y_i] / sum w * (softmax(logits_i) - onehot(y_i))   (or NULL)
+ * a <= 64.
+ */
+DIN_API int din_ce_metrics_f32(const float* logits, const int64_t* labels, const float* class_weight,
+                               float loss_scale, float* loss, int32_t* correct, int32_t* conf, double* meters,
+                               float* dlogits, int b, int a, void* stream);
+
+/*
+ * y[o, i] = mean over a of x[o, a, i]   (fp32; x is [outer, len, inner]).
+ * Replaces: actions_scores.reshape(B,T,N,-1).mean(dim=1) of the stage-1 base model (base_model.py:138-139).
+ */
+DIN_API int din_mean_axis_f32(const float* x, float* y, int outer, int len, int inner, void* stream);
 
 #ifdef __cplusplus
 } /* extern "C" */

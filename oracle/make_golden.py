@@ -42,8 +42,35 @@ def model_cases():
     }
 
 
+def basenet_cases():
+    def pc(backbone, hw, **kw):
+        return O.PathConfig(backbone=backbone, image_size=hw, out_size=O.backbone_out_size(backbone, *hw), **kw)
+    return {
+        "volleyball_vgg16": (pc("vgg16", (96, 160), num_frames=3, num_boxes=4), 2),
+        "volleyball_res18_T1": (pc("res18", (96, 160), num_frames=1, num_boxes=4), 2),
+        "collective_inv3": (pc("inv3", (139, 203), dataset="collective", emb_features=1056, num_frames=2,
+                               num_boxes=13, num_activities=5, num_actions=6), 2),
+    }
+
+
+def main_basenet():
+    """Stage-1 fixtures from the reference's base_model.Basenet_* (SURVEY.md §8f rank 3)."""
+    for name, (pc, B) in basenet_cases().items():
+        bb = O.build_backbone(pc.backbone)
+        sd = O.make_basenet_state_dict(pc, seed=0, backbone=bb)
+        batch = O.make_basenet_inputs(pc, B, seed=0)
+        actions, activities = R.ref_basenet_forward(pc, sd, *batch)
+        torch.save({"config": dataclasses.asdict(pc), "B": B, "seed": 0, "actions_ref": actions,
+                    "activities_ref": activities, "weights_checksum": checksum(sd.values()),
+                    "inputs_checksum": checksum(batch)}, os.path.join(OUT, f"basenet_{name}.pt"))
+        print("basenet", name, tuple(actions.shape), tuple(activities.shape))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--basenet-only" in sys.argv:
+        return main_basenet()
+    main_basenet()
     for name, (pc, B) in model_cases().items():
         bb = O.build_backbone(pc.backbone)
         sd = O.make_state_dict(pc, seed=0, backbone=bb)

@@ -174,6 +174,24 @@ def ref_forward(pc, sd, *batch):
         return model(tuple(batch))["activities"]
 
 
+def ref_basenet_forward(pc, sd, *batch):
+    """The reference's stage-1 Basenet_volleyball / Basenet_collective (base_model.py) in eval mode.
+    Basenet_collective hard-codes MyInception_v3 (base_model.py:159); no patches are needed."""
+    bm = ref_module("base_model")
+    cfg = make_ref_cfg(pc)
+    cfg.num_actions = pc.num_actions
+    import io
+    import warnings
+    with contextlib.redirect_stdout(io.StringIO()):
+        with _isolated_import():
+            model = (bm.Basenet_collective if pc.dataset == "collective" else bm.Basenet_volleyball)(cfg)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    with torch.no_grad(), warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        return model(tuple(batch))
+
+
 def ref_dpi_module(in_dim, kernel, ratios, scale_factor=True, beta_factor=False):
     """A bare reference Dynamic_Person_Inference (dynamic_infer_module.py:14-404)."""
     dm = ref_module("infer_module.dynamic_infer_module")

@@ -25,10 +25,30 @@ def _pc_from(d):
 
 MODEL_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "model_*.pt")))
 MODULE_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "module_*.pt")))
+BASENET_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "basenet_*.pt")))
 
 
 def test_fixtures_present():
-    assert len(MODEL_FIXTURES) == 7 and len(MODULE_FIXTURES) == 4
+    assert len(MODEL_FIXTURES) == 7 and len(MODULE_FIXTURES) == 4 and len(BASENET_FIXTURES) == 3
+
+
+@pytest.mark.parametrize("path", BASENET_FIXTURES, ids=[os.path.basename(p) for p in BASENET_FIXTURES])
+def test_oracle_reproduces_reference_basenet(path):
+    """Stage-1 restatement == what base_model.Basenet_* produced (fixtures from oracle/make_golden.py)."""
+    import din_oracle as O
+    fx = torch.load(path)
+    pc = _pc_from(fx["config"])
+    bb = O.build_backbone(pc.backbone)
+    sd = O.make_basenet_state_dict(pc, seed=fx["seed"], backbone=bb)
+    batch = O.make_basenet_inputs(pc, fx["B"], seed=fx["seed"])
+    assert abs(_checksum(sd.values()) - fx["weights_checksum"]) <= 1e-9 * fx["weights_checksum"]
+    assert abs(_checksum(batch) - fx["inputs_checksum"]) <= 1e-9 * fx["inputs_checksum"]
+    O.load_backbone(bb, sd)
+    fwd = O.basenet_collective_forward if pc.dataset == "collective" else O.basenet_volleyball_forward
+    actions, activities = fwd(bb, sd, pc, *batch)
+    for out, ref in ((actions, fx["actions_ref"]), (activities, fx["activities_ref"])):
+        assert out.shape == ref.shape
+        assert (out - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
 
 
 @pytest.mark.parametrize("path", MODEL_FIXTURES, ids=[os.path.basename(p) for p in MODEL_FIXTURES])

@@ -1,0 +1,127 @@
+"""Stage-1 base models and the on-device loss / metrics (rank 4) on the GPU:
+  * Basenet_volleyball / Basenet_collective (drop-in, CUDA path) vs the CPU oracle restatement of
+    base_model.py on the same seeded weights and inputs (1e-3 * max|ref|, as the stage-2 logits);
+  * the stage-1 checkpoint written by Basenet.savemodel loads into Dynamic_volleyball.loadmodel;
+  * din_ce_metrics_f32 vs torch (F.cross_entropy value + autograd gradient, argmax, confusion counts)."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(pc):
+    from config import Config
+    cfg = Config(pc.dataset)
+    cfg.log_path = None
+    for k in ("backbone", "image_size", "out_size", "emb_features", "num_frames", "num_boxes", "crop_size",
+              "num_features_boxes", "num_activities", "num_actions", "lite_dim"):
+        setattr(cfg, k, getattr(pc, k))
+    return cfg
+
+
+def _pc(backbone, hw, **kw):
+    import din_oracle as O
+    return O.PathConfig(backbone=backbone, image_size=hw, out_size=O.backbone_out_size(backbone, *hw), **kw)
+
+
+CASES = {
+    "volleyball_vgg16": (dict(backbone="vgg16", hw=(96, 160), num_frames=3, num_boxes=4), 2),
+    "volleyball_res18_T1": (dict(backbone="res18", hw=(96, 160), num_frames=1, num_boxes=4), 2),
+    "volleyball_inv3": (dict(backbone="inv3", hw=(139, 203), emb_features=1056, num_frames=2, num_boxes=5), 2),
+    "collective_inv3": (dict(backbone="inv3", hw=(139, 203), dataset="collective", emb_features=1056, num_frames=2,
+                             num_boxes=13, num_activities=5, num_actions=6), 2),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_basenet_matches_oracle(cuda, name):
+    import base_model as BM
+    import din_oracle as O
+    kw, B = CASES[name]
+    kw = dict(kw)
+    pc = _pc(kw.pop("backbone"), kw.pop("hw"), **kw)
+    bb = O.build_backbone(pc.backbone)
+    sd = O.make_basenet_state_dict(pc, seed=0, backbone=bb)
+    O.load_backbone(bb, sd)
+    batch = O.make_basenet_inputs(pc, B, seed=0)
+    fwd = O.basenet_collective_forward if pc.dataset == "collective" else O.basenet_volleyball_forward
+    ref_actions, ref_activities = fwd(bb, sd, pc, *batch)
+    model = (BM.Basenet_collective if pc.dataset == "collective" else BM.Basenet_volleyball)(_cfg(pc))
+    model.load_state_dict(sd, strict=True)
+    model = model.to(cuda).eval()
+    with torch.no_grad():
+        actions, activities = model(tuple(t.to(cuda) for t in batch))
+    torch.cuda.synchronize()
+    for out, ref, what in ((actions, ref_actions, "actions"), (activities, ref_activities, "activities")):
+        assert out.shape == ref.shape, (what, out.shape, ref.shape)
+        err = (out.cpu() - ref).abs().max().item()
+        scale = ref.abs().max().item()
+        print(f"\n[basenet] {name} {what}: max|Δ|={err:.3e} max|ref|={scale:.3f} rel={err / scale:.2e}")
+        assert err <= 1e-3 * scale, (what, err, scale)
+
+
+def test_stage1_checkpoint_feeds_stage2(cuda, tmp_path):
+    """savemodel (base_model.py:46-55) -> Dynamic_volleyball.loadmodel (infer_model.py:120-125)."""
+    import base_model as BM
+    import din_oracle as O
+    import infer_model as IM
+    pc = _pc("vgg16", (96, 160), num_frames=3, num_boxes=4)
+    sd1 = O.make_basenet_state_dict(pc, seed=1)
+    m1 = BM.Basenet_volleyball(_cfg(pc))
+    m1.load_state_dict(sd1, strict=True)
+    path = os.path.join(tmp_path, "stage1.pth")
+    m1.savemodel(path)
+    cfg = _cfg(pc)
+    m2 = IM.Dynamic_volleyball(cfg)
+    m2.loadmodel(path)
+    for k, v in m1.backbone.state_dict().items():
+        assert torch.equal(m2.backbone.state_dict()[k], v), k
+    assert torch.equal(m2.fc_emb_1.weight, m1.fc_emb.weight) and torch.equal(m2.fc_emb_1.bias, m1.fc_emb.bias)
+    # and the loaded stage-2 model runs
+    images, boxes = O.make_inputs(pc, 1, seed=1)
+    with torch.no_grad():
+        out = m2.to(cuda).eval()((images.to(cuda), boxes.to(cuda)))["activities"]
+    assert out.shape == (1, pc.num_activities) and torch.isfinite(out).all()
+
+
+@pytest.mark.parametrize("b,a,weighted", [(2, 8, False), (24, 9, True), (1, 4, False), (700, 8, True)])
+def test_ce_metrics_matches_torch(cuda, b, a, weighted):
+    from din_b200 import metrics
+    g = torch.Generator().manual_seed(b * 31 + a)
+    logits = (torch.randn(b, a, generator=g) * 3).to(cuda).requires_grad_(True)
+    labels = torch.randint(0, a, (b,), generator=g).to(cuda)
+    w = (torch.rand(a, generator=g) + 0.5).to(cuda) if weighted else None
+    meters = metrics.DeviceMeters(a, cuda)
+    loss = metrics.cross_entropy(logits, labels, weight=w, loss_scale=0.7, meters=meters)
+    loss.backward()
+    ref_logits = logits.detach().clone().requires_grad_(True)
+    ref = F.cross_entropy(ref_logits, labels, weight=w) * 0.7
+    ref.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - ref.item()) <= 2e-6 * max(1.0, abs(ref.item()))
+    assert (logits.grad - ref_logits.grad).abs().max().item() <= 2e-6
+    # second step, metrics only: the meters accumulate
+    logits2 = (torch.randn(b, a, generator=g) * 3).to(cuda)
+    labels2 = torch.randint(0, a, (b,), generator=g).to(cuda)
+    loss2 = meters.update(logits2, labels2, weight=w, loss_scale=0.7)
+    v = meters.value()
+    pred = torch.cat([logits.detach().argmax(1), logits2.argmax(1)]).cpu()
+    tgt = torch.cat([labels, labels2]).cpu()
+    conf = torch.zeros(a, a, dtype=torch.int64)
+    for p, t in zip(pred.tolist(), tgt.tolist()):
+        conf[t, p] += 1                                               # ConfusionMeter: rows = target
+    assert (torch.from_numpy(v["activities_conf"]).long() == conf).all()
+    assert v["samples"] == 2 * b and v["steps"] == 2
+    acc = (pred == tgt).float().mean().item() * 100
+    assert abs(v["activities_acc"] - acc) < 1e-4
+    want = (loss.item() * b + loss2.item() * b) / (2 * b)
+    assert abs(v["loss"] - want) <= 1e-6 * max(1.0, abs(want))
+
+
+def test_mean_axis(cuda):
+    from din_b200 import ops
+    x = torch.randn(3, 7, 45, device=cuda)
+    assert (ops.mean_axis(x, 1) - x.mean(1)).abs().max().item() <= 1e-6
