@@ -12,6 +12,7 @@
 #include <cfloat>
 
 #include "din_common.cuh"
+#include "din_head.cuh"
 
 namespace {
 
@@ -93,25 +94,6 @@ roi_align_kernel(const __half* __restrict__ fm, const float* __restrict__ boxes,
     }
     *reinterpret_cast<uint4*>(op + c) = o;
   }
-}
-
-// ================================================================================================
-// block-wide sum helper
-// ================================================================================================
-template <int kThreads>
-__device__ __forceinline__ float block_sum(float v, float* red /* >= 33 floats */) {
-  v = warp_sum(v);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __syncthreads();  // protect `red` from the previous use
-  if (lane == 0) red[warp] = v;
-  __syncthreads();
-  if (warp == 0) {
-    float t = lane < (kThreads / 32) ? red[lane] : 0.0f;
-    t = warp_sum(t);
-    if (lane == 0) red[32] = t;
-  }
-  __syncthreads();
-  return red[32];
 }
 
 // ================================================================================================
@@ -254,12 +236,6 @@ linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
 // Nothing but x is read from HBM and nothing but y is written: the 4 x [B,T,N,k²,C] gathers and the
 // ~40 elementwise temporaries of the reference never exist.
 // ================================================================================================
-constexpr int kDinThreads = 256;
-constexpr int kDinWarps = kDinThreads / 32;
-constexpr int kDinMaxN = 16;     // actors per frame (12 Volleyball, 13 Collective)
-constexpr int kDinMaxK2 = 9;     // taps
-constexpr int kDinMaxOutPerWarp = 4;  // ceil(27 / 8)
-
 __global__ void __launch_bounds__(kDinThreads)
 dynamic_infer_kernel(const float* __restrict__ x, const float* __restrict__ w_tap, const float* __restrict__ b_cat,
                      float* __restrict__ y, int T, int N, int C, int kt, int kn, int ratio, int scale_factor,
@@ -280,68 +256,7 @@ dynamic_infer_kernel(const float* __restrict__ x, const float* __restrict__ w_ta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C4 = C >> 2;
 
-  // ---- stage the kt rows
-  for (int i = threadIdx.x; i < kt * N * C4; i += kDinThreads) {
-    const int c4 = i % C4;
-    const int rn = i / C4;
-    const int n = rn % N;
-    const int ky = rn / N;
-    const int tt = t + dy0 + ky * ratio;
-    float4 v = make_float4(0, 0, 0, 0);
-    if (tt >= 0 && tt < T && n < Nb) v = __ldg(reinterpret_cast<const float4*>(xb + (static_cast<size_t>(tt) * N + n) * C) + c4);
-    reinterpret_cast<float4*>(xs)[i] = v;
-  }
-  __syncthreads();
-
-  // ---- phase 1: conv outputs.  warp w owns outputs o = w, w+8, ...; lanes sweep channels.
-  {
-    float acc[kDinMaxOutPerWarp][kDinMaxN];
-#pragma unroll
-    for (int a = 0; a < kDinMaxOutPerWarp; ++a)
-#pragma unroll
-      for (int n = 0; n < kDinMaxN; ++n) acc[a][n] = 0.0f;
-    for (int ky = 0; ky < kt; ++ky) {
-      for (int kx = 0; kx < kn; ++kx) {
-        const int tap = ky * kn + kx;
-        const int dx = dx0 + kx * ratio;
-        const float* wt = w_tap + static_cast<size_t>(tap) * n_out * C;
-        const float* xrow = xs + static_cast<size_t>(ky) * N * C;
-        for (int c4 = lane; c4 < C4; c4 += 32) {
-          float4 wv[kDinMaxOutPerWarp];
-#pragma unroll
-          for (int a = 0; a < kDinMaxOutPerWarp; ++a) {
-            const int o = warp + a * kDinWarps;
-            wv[a] = (o < n_out) ? __ldg(reinterpret_cast<const float4*>(wt + static_cast<size_t>(o) * C) + c4)
-                                : make_float4(0, 0, 0, 0);
-          }
-#pragma unroll
-          for (int n = 0; n < kDinMaxN; ++n) {
-            const int nn = n + dx;
-            if (n < Nb && nn >= 0 && nn < Nb) {
-              const float4 xv = reinterpret_cast<const float4*>(xrow + static_cast<size_t>(nn) * C)[c4];
-#pragma unroll
-              for (int a = 0; a < kDinMaxOutPerWarp; ++a) {
-                acc[a][n] = fmaf(wv[a].x, xv.x, acc[a][n]);
-                acc[a][n] = fmaf(wv[a].y, xv.y, acc[a][n]);
-                acc[a][n] = fmaf(wv[a].z, xv.z, acc[a][n]);
-                acc[a][n] = fmaf(wv[a].w, xv.w, acc[a][n]);
-              }
-            }
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int a = 0; a < kDinMaxOutPerWarp; ++a) {
-      const int o = warp + a * kDinWarps;
-#pragma unroll
-      for (int n = 0; n < kDinMaxN; ++n) {
-        const float v = warp_sum(acc[a][n]);
-        if (lane == 0 && o < n_out && n < Nb) conv_s[n * n_out + o] = v + __ldg(b_cat + o);
-      }
-    }
-  }
-  __syncthreads();
+  din_stage_rows_and_conv(xb, w_tap, b_cat, xs, conv_s, t, T, N, Nb, C, kt, kn, ratio, n_out, dy0, dx0);
 
   // ---- phase 2: one warp per actor
   const float coef = coef_ptr ? __ldg(coef_ptr) : coef_scalar;

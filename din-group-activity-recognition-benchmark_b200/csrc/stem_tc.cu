@@ -66,9 +66,8 @@ __device__ __forceinline__ uint64_t desc_noswz(uint32_t addr, uint32_t lbo_bytes
   return d;
 }
 
-// Input patch of one tile held in registers between the global loads and the shared-memory staging, so that
-// the loads of tile i+1 are in flight while tile i is built, multiplied and stored (the kernel is a latency
-// chain per tile otherwise: global load -> smem -> im2col -> MMA -> TMEM -> store).
+// Input patch of one tile held in registers between the global loads and the shared-memory staging (all loads
+// in flight at once).
 //   fp32 NCHW: one float per (channel, filter row, column slot);  uint8 NHWC: the pixel's 3 bytes packed in
 //   one word per (filter row, column slot), bit 24 set = padding.
 template <int COUT, int KH, int KW, int STRIDE, bool U8>
@@ -77,6 +76,13 @@ struct PatchRegs {
   static constexpr int kN = U8 ? KH * Cfg::kLoadsPerRow : Cfg::kRows * Cfg::kLoadsPerRow;
   uint32_t v[kN];
 };
+
+// prep_images with the contraction spelled out (one FMA, one exact doubling), so that every instantiation
+// rounds identically: (x/255 - 0.5)*2 (utils.py:14-17); the product by 1/255 differs from the division by at
+// most 1 ulp(fp32), far below the fp16 rounding applied next.
+__device__ __forceinline__ float prep_value(float f, bool prep) {
+  return prep ? __fmul_rn(__fmaf_rn(f, 1.0f / 255.0f, -0.5f), 2.0f) : f;
+}
 
 struct TileCoord { int img, oy, strip; };
 
@@ -118,7 +124,6 @@ __device__ __forceinline__ void load_patch(const StemParams& p, const TileCoord&
     }
   } else {
     const float* xi = static_cast<const float*>(p.x) + static_cast<size_t>(t.img) * 3 * plane;
-    const float pad_val = p.prep ? 127.5f : 0.0f;                           // preps to exactly 0
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
 #pragma unroll
@@ -130,7 +135,9 @@ __device__ __forceinline__ void load_patch(const StemParams& p, const TileCoord&
         for (int u = 0; u < Cfg::kLoadsPerRow; ++u) {
           const int px = tid + u * kStemThreads;
           const int gx = gx0 + px;
-          const float f = (row_ok && px < Cfg::kPatchW && gx >= 0 && gx < p.w_in) ? __ldg(src + gx) : pad_val;
+          // prep_images is applied to real pixels only: the convolution pads the PREPPED image with zeros
+          const float f = (row_ok && px < Cfg::kPatchW && gx >= 0 && gx < p.w_in)
+                              ? prep_value(__ldg(src + gx), p.prep != 0) : 0.0f;
           r.v[(c * KH + ky) * Cfg::kLoadsPerRow + u] = __float_as_uint(f);
         }
       }
@@ -139,9 +146,7 @@ __device__ __forceinline__ void load_patch(const StemParams& p, const TileCoord&
 }
 
 // registers -> shared-memory patch [3*KH][kPitch] fp32, prep_images applied once per input element
-// (utils.py:14-17: (x/255 - 0.5)*2; the product by 1/255 differs from the division by at most 1 ulp(fp32),
-// far below the fp16 rounding applied next).  uint8 pixels convert exactly, so both ingest paths agree bit
-// for bit on equal pixel values.
+// (prep_value).  uint8 pixels convert exactly, so both ingest paths agree bit for bit on equal pixel values.
 template <int COUT, int KH, int KW, int STRIDE, bool U8>
 __device__ __forceinline__ void stage_patch(const StemParams& p, int tid, float* patch,
                                             const PatchRegs<COUT, KH, KW, STRIDE, U8>& r) {
@@ -158,8 +163,7 @@ __device__ __forceinline__ void stage_patch(const StemParams& p, int tid, float*
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             const float f = static_cast<float>((w >> (8 * c)) & 0xFFu);
-            const float g = p.prep ? (f * (1.0f / 255.0f) - 0.5f) * 2.0f : f;
-            patch[(c * KH + ky) * Cfg::kPitch + px] = is_pad ? 0.0f : g;
+            patch[(c * KH + ky) * Cfg::kPitch + px] = is_pad ? 0.0f : prep_value(f, p.prep != 0);
           }
         }
       }
@@ -171,7 +175,7 @@ __device__ __forceinline__ void stage_patch(const StemParams& p, int tid, float*
       for (int u = 0; u < Cfg::kLoadsPerRow; ++u) {
         const int px = tid + u * kStemThreads;
         const float f = __uint_as_float(r.v[rr * Cfg::kLoadsPerRow + u]);
-        if (px < Cfg::kPatchW) patch[rr * Cfg::kPitch + px] = p.prep ? (f * (1.0f / 255.0f) - 0.5f) * 2.0f : f;
+        if (px < Cfg::kPatchW) patch[rr * Cfg::kPitch + px] = f;
       }
     }
   }
@@ -192,11 +196,6 @@ stem_tc_kernel(const StemParams p) {
   float* patch = reinterpret_cast<float*>(tmem_ptr_smem + 4);               // [3*KH][kPitch] prep'd input rows
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  // first tile's input loads go out before the one-time setup
-  PatchRegs<COUT, KH, KW, STRIDE, U8> regs;
-  TileCoord cur = decode_tile(p, blockIdx.x);
-  load_patch<COUT, KH, KW, STRIDE, U8>(p, cur, tid, regs);
 
   // ---- one-time setup: weights in UMMA layout, bias, barrier, TMEM
   for (int i = tid; i < COUT * (Cfg::kPad / 8); i += kStemThreads) {
@@ -233,13 +232,16 @@ stem_tc_kernel(const StemParams p) {
 
   uint32_t phase = 0;
   for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const TileCoord cur = decode_tile(p, tile);
     const int img = cur.img, oy = cur.oy, strip = cur.strip;
-    stage_patch<COUT, KH, KW, STRIDE, U8>(p, tid, patch, regs);
-    __syncthreads();
-    if (tile + static_cast<int>(gridDim.x) < p.num_tiles) {     // next tile's loads fly during this tile's work
-      cur = decode_tile(p, tile + gridDim.x);
+    {
+      // all loads of the patch are issued before the first use.  (Prefetching the NEXT tile's patch into
+      // registers was measured: +8 registers cost a resident CTA per SM and the kernel ran 7 % slower.)
+      PatchRegs<COUT, KH, KW, STRIDE, U8> regs;
       load_patch<COUT, KH, KW, STRIDE, U8>(p, cur, tid, regs);
+      stage_patch<COUT, KH, KW, STRIDE, U8>(p, tid, patch, regs);
     }
+    __syncthreads();
     // ---- im2col row of this thread's pixel -> A tile (canonical UMMA layout); all offsets are immediates
     {
       const float* prow = patch + tid * STRIDE;

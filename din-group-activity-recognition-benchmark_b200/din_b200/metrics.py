@@ -16,7 +16,7 @@ from . import ops
 class _CrossEntropyFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, labels, class_weight, loss_scale, conf, meters):
-        need = logits.requires_grad
+        need = ctx.needs_input_grad[0]
         loss, correct, dlogits = ops.ce_metrics(logits.detach().contiguous(), labels, class_weight=class_weight,
                                                 loss_scale=loss_scale, conf=conf, meters=meters, want_grad=need)
         ctx.save_for_backward(dlogits)

@@ -315,3 +315,122 @@ def mean_axis(x, dim):
     with _launch("mean_axis", 0, 4 * (x.numel() + y.numel())):
         check(_lib.load().din_mean_axis_f32(_p(x), _p(y), outer, shape[dim], inner, _stream()), "din_mean_axis_f32")
     return y
+
+
+# ---------------------------------------------------------------------------------------------
+# backward of the person-level head (first slice)
+# ---------------------------------------------------------------------------------------------
+def gemm_f32(a, b, *, m, n, k, a_strides, b_strides, out=None, alpha=1.0, accumulate=False):
+    """out[m,n] (+)= alpha * sum_k A(m,k) B(k,n) with explicit element strides (a fp32; b fp32 or fp16)."""
+    _need(a, torch.float32, "a")
+    if b.dtype not in (torch.float32, torch.float16) or not b.is_cuda or not b.is_contiguous():
+        raise _lib.DinError("gemm_f32: b must be a contiguous CUDA fp32/fp16 tensor")
+    if out is None:
+        assert not accumulate
+        out = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    _need(out, torch.float32, "out")
+    with _launch(f"gemm_f32_{m}x{n}x{k}", 2 * m * n * k, 4 * (m * k + m * n) + b.element_size() * n * k):
+        check(_lib.load().din_gemm_f32(_p(a), a_strides[0], a_strides[1], _p(b), int(b.dtype == torch.float16),
+                                       b_strides[0], b_strides[1], _p(out), out.stride(0) if out.dim() == 2 else n,
+                                       m, n, k, float(alpha), int(accumulate), _stream()), "din_gemm_f32")
+    return out
+
+
+def linear_bwd(x, w, dy, *, need_dx=True, dx_out=None, dx_accumulate=False, has_bias=True):
+    """y = x.w^T (+ bias), x [m,k] (fp32, or fp16 crops), w [n,k] (None when need_dx is False), dy [m,n]
+    -> (dx [m,k] | None, dw [n,k], db [n] | None)."""
+    n = dy.shape[-1]
+    m = dy.numel() // n
+    k = x.numel() // m
+    assert w is None or tuple(w.shape) == (n, k), (None if w is None else tuple(w.shape), n, k)
+    dx = None
+    if need_dx:
+        # dx[m,k] = sum_n dy[m,n] w[n,k]
+        dx = gemm_f32(dy, w, m=m, n=k, k=n, a_strides=(n, 1), b_strides=(k, 1), out=dx_out, accumulate=dx_accumulate)
+    # dw[n,k] = sum_m dy[m,n] x[m,k]
+    dw = gemm_f32(dy, x, m=n, n=k, k=m, a_strides=(1, n), b_strides=(k, 1))
+    db = None
+    if has_bias:
+        db = torch.empty((n,), dtype=torch.float32, device=dy.device)
+        with _launch("colsum", 0, 4 * m * n):
+            check(_lib.load().din_colsum_f32(_p(dy), _p(db), m, n, n, _stream()), "din_colsum_f32")
+    return dx, dw, db
+
+
+def scale_mask(x, mask, scale, out=None):
+    """x * mask * scale (dropout forward / backward); mask uint8 0/1 or None."""
+    _need(x, torch.float32, "x")
+    if mask is not None:
+        _need(mask, torch.uint8, "mask")
+        assert mask.numel() == x.numel()
+    if out is None:
+        out = torch.empty_like(x)
+    with _launch("scale_mask", 0, 9 * x.numel()):
+        check(_lib.load().din_scale_mask_f32(_p(x), _p(mask), float(scale), _p(out), x.numel(), _stream()),
+              "din_scale_mask_f32")
+    return out
+
+
+def readout_bwd(s, w, dlogits, n_valid=None):
+    """-> (ds [b,t,n,c], dw [a,c], dbias [a])."""
+    _need(s, torch.float32, "s")
+    _need(w, torch.float32, "w")
+    _need(dlogits, torch.float32, "dlogits")
+    b, t, n, c = s.shape
+    a = w.shape[0]
+    ds = torch.empty_like(s)
+    ws = torch.empty((b, t, c), dtype=torch.float32, device=s.device)
+    dw = torch.empty_like(w)
+    db = torch.empty((a,), dtype=torch.float32, device=s.device)
+    global LAUNCHES
+    LAUNCHES += 1                                   # two kernels
+    with _launch("readout_bwd", 0, 8 * s.numel()):
+        check(_lib.load().din_readout_bwd_f32(_p(s), _p(w), _p(dlogits), _p(ds), _p(ws), _p(dw), _p(db), b, t, n, c, a,
+                                              _p(n_valid), _stream()), "din_readout_bwd_f32")
+    return ds, dw, db
+
+
+def group_layernorm_bwd(x, gamma, beta, dy, *, n_outer, n_inner=1, outer_stride, inner_stride=0, rows=1,
+                        row_stride=0, cols, pre=None, relu=False, eps=1e-5, n_valid=None, dx_out=None,
+                        accumulate=False, param_grads=True):
+    """-> (dx, dgamma, dbeta); dx is also the gradient of `pre`; the gradient of `post` is dy itself."""
+    _need(x, torch.float32, "x")
+    _need(dy, torch.float32, "dy")
+    if dx_out is None:
+        assert not accumulate
+        # groups skipped through n_valid are never written: start from zeros so they are well defined
+        dx_out = torch.zeros_like(x) if n_valid is not None else torch.empty_like(x)
+    stats = torch.empty((n_outer * n_inner, 2), dtype=torch.float32, device=x.device)
+    dg = torch.empty_like(gamma) if param_grads else None
+    db = torch.empty_like(beta) if param_grads else None
+    global LAUNCHES
+    LAUNCHES += 1 if param_grads else 0             # second kernel: parameter gradients
+    with _launch("group_layernorm_bwd", 0, 16 * n_outer * n_inner * rows * cols):
+        check(_lib.load().din_group_layernorm_bwd_f32(_p(x), _p(pre), _p(gamma), _p(beta), _p(dy), _p(dx_out), _p(dg),
+                                                      _p(db), _p(stats), n_outer, n_inner, outer_stride, inner_stride,
+                                                      rows, row_stride, cols, float(eps), int(relu), int(accumulate),
+                                                      _p(n_valid), _stream()), "din_group_layernorm_bwd_f32")
+    return dx_out, dg, db
+
+
+def dynamic_infer_bwd(x, w_tap, b_cat, dy, dx, kernel, ratio, *, scale_factor=True, coef=1.0, coef_ptr=None,
+                      want_dcoef=False, n_valid=None):
+    """dx += ...; returns (dw_tap, db_cat, dcoef | None).  Launches three kernels."""
+    _need(x, torch.float32, "x")
+    _need(dy, torch.float32, "dy")
+    _need(dx, torch.float32, "dx")
+    b, t, n, c = x.shape
+    kt, kn = kernel
+    n_out = w_tap.shape[1]
+    dw = torch.empty_like(w_tap)
+    db = torch.empty_like(b_cat)
+    dcoef = torch.empty((1,), dtype=torch.float32, device=x.device) if want_dcoef else None
+    ws = torch.empty((b * t * n * (n_out + 1),), dtype=torch.float32, device=x.device)
+    global LAUNCHES
+    LAUNCHES += 2                                   # this entry point launches three kernels
+    with _launch(f"dynamic_infer_bwd_k{kt}x{kn}_r{ratio}_c{c}", 6 * b * t * n * n_out * kt * kn * c, 16 * x.numel()):
+        check(_lib.load().din_dynamic_infer_bwd_f32(_p(x), _p(w_tap), _p(b_cat), _p(dy), _p(dx), _p(dw), _p(db),
+                                                    _p(dcoef), _p(ws), b, t, n, c, kt, kn, ratio, int(scale_factor),
+                                                    C.c_void_p(coef_ptr or 0), float(coef), _p(n_valid), _stream()),
+              "din_dynamic_infer_bwd_f32")
+    return dw, db, dcoef

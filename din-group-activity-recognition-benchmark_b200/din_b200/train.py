@@ -1,0 +1,206 @@
+"""train.py — the stage-2 training step of the person-level head on one B200 (first slice).
+
+`forward_train` is DinEngine's forward with dropout applied and the intermediates the backward needs kept on a
+tape; `backward_head` turns d(loss)/d(logits) into gradients for every parameter after the backbone, under the
+reference's parameter names and layouts (so `optimizer.step()` in train_net_dynamic.py:220-224 works on the
+drop-in model unchanged).  Scope of this slice: the backbone is frozen (config.py:39 `train_backbone = False`);
+gradients stop at the feature map.  Host-side orchestration only: every number is produced by a kernel of
+libdin_sm100.so (ops.py); torch is used for buffers, views and layout permutes.
+
+Reference graph (infer_model.py:141-234 / 1226-1319, infer_module/dynamic_infer_module.py:121-151, 407-498):
+  crops -> fc_emb_1 -> nl_emb_1 -> ReLU -> [point_conv -> point_ln -> ReLU] = x
+  g = sum_i hidden_i( mean_r | sum_r beta_r  DIN_{i,r}(x) )          (Multi)   or   DPI_2(drop(relu(LN(DPI_1(x)))))
+  s = relu(dpi_nl(g + x)) (vgg16/inv3)  |  relu(dpi_nl(g)) + x (res18)  |  Collective: LN([T,C]) per actor of g + x
+  logits = mean_t fc_activities(max_n dropout(s))
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+def _dropout_mask(shape, p, device, training):
+    """0/1 byte mask from torch's CUDA generator (reproducible with torch.manual_seed), or None when inactive."""
+    if not training or p <= 0.0:
+        return None
+    return (torch.rand(shape, device=device) >= p).to(torch.uint8)
+
+
+def _dpi_forward(dpi, x, n_valid, tape):
+    """DPIWeights.__call__ keeping `tmp` (the mixed ratio outputs, input of hidden_weight)."""
+    tmp = torch.zeros_like(x) if n_valid is not None else torch.empty_like(x)
+    for i, r in enumerate(dpi.ratios):
+        w_tap, b_cat = dpi.taps[r]
+        if dpi.beta_factor:
+            ops.dynamic_infer(x, w_tap, b_cat, dpi.kernel, r, scale_factor=dpi.scale_factor, out=tmp,
+                              coef_ptr=dpi.beta.data_ptr() + 4 * i, accumulate=i > 0, n_valid=n_valid)
+        else:
+            ops.dynamic_infer(x, w_tap, b_cat, dpi.kernel, r, scale_factor=dpi.scale_factor, out=tmp,
+                              coef=1.0 / len(dpi.ratios), accumulate=i > 0, n_valid=n_valid)
+    tape.append(("dpi", dpi, x, tmp))
+    return tmp
+
+
+def _dpi_backward(dpi, prefix, x, tmp, dg, dx, n_valid, grads):
+    """g = tmp . hidden^T ; tmp = sum_r coef_r DIN_r(x).  dx += d/dx; parameter gradients -> grads[prefix + ...]."""
+    C = x.shape[-1]
+    M = x.numel() // C
+    dtmp, dwh, _ = ops.linear_bwd(tmp.view(M, C), dpi.hidden, dg.view(M, C), has_bias=False)
+    grads[prefix + "hidden_weight.weight"] = dwh
+    kt, kn = dpi.kernel
+    k2 = kt * kn
+    dbeta = []
+    for i, r in enumerate(dpi.ratios):
+        w_tap, b_cat = dpi.taps[r]
+        kw = dict(coef_ptr=dpi.beta.data_ptr() + 4 * i, want_dcoef=True) if dpi.beta_factor else \
+            dict(coef=1.0 / len(dpi.ratios))
+        dw, db, dcoef = ops.dynamic_infer_bwd(x, w_tap, b_cat, dtmp.view_as(x), dx, dpi.kernel, r,
+                                              scale_factor=dpi.scale_factor, n_valid=n_valid, **kw)
+        # packed [tap][o][c] -> OIHW [o, c, kt, kn] (layout only)
+        w_oihw = dw.permute(1, 2, 0).reshape(dw.shape[1], C, kt, kn)
+        grads[f"{prefix}p_conv.{r}.weight"] = w_oihw[:2 * k2].contiguous()
+        grads[f"{prefix}p_conv.{r}.bias"] = db[:2 * k2].contiguous()
+        if dpi.scale_factor:
+            grads[f"{prefix}scale_conv.{r}.weight"] = w_oihw[2 * k2:].contiguous()
+            grads[f"{prefix}scale_conv.{r}.bias"] = db[2 * k2:].contiguous()
+        if dpi.beta_factor:
+            dbeta.append(dcoef)
+    if dpi.beta_factor:
+        grads[prefix + "beta"] = torch.cat(dbeta)
+
+
+def forward_train(eng, images, boxes, bboxes_num=None, training=True):
+    """-> (logits [B, A], tape).  Same kernels as DinEngine.forward_*, plus dropout and saved intermediates."""
+    cfg = eng.cfg
+    B, T = images.shape[:2]
+    N, C = eng.N, eng.C
+    M = B * T * N
+    dev = eng.device
+    tape = {"B": B, "T": T, "dpi": []}
+    with torch.no_grad():
+        fm = eng.features(eng._flat_frames(images))
+        if eng.dataset == "volleyball":
+            OH, OW = cfg.out_size
+            assert fm.shape[1:3] == (OH, OW), (tuple(fm.shape), cfg.out_size)
+        # ---- embed (DinEngine.embed with the intermediates kept)
+        crops = ops.roi_align_nhwc(fm, boxes.reshape(M, 4).contiguous().float(), eng._box_idx(B * T, N), eng.K, eng.K,
+                                   d=eng.D_stride)
+        emb = eng.fc_emb(crops.view(1, 1, M, eng.K * eng.K * eng.D_stride), out_f32=True).view(M, eng.NFB)
+        x0 = ops.group_layernorm(emb, *eng.nl_emb, n_outer=M, outer_stride=eng.NFB, cols=eng.NFB, relu=True)
+        tape.update(crops=crops.view(M, -1), emb=emb, x0=x0)
+        g_sz = T * N * C
+        if cfg.lite_dim:
+            ylite = ops.linear_f32(x0, eng.point_w, eng.point_b)
+            x = ops.group_layernorm(ylite, *eng.point_ln, n_outer=B, outer_stride=g_sz, cols=g_sz, relu=True)
+            tape["ylite"] = ylite
+        else:
+            x = x0
+        x = x.view(B, T, N, C)
+        tape["x"] = x
+        n_valid = None
+        if eng.dataset == "collective":
+            n_valid = bboxes_num.reshape(B, T)[:, 0].to(torch.int32).contiguous()
+        tape["n_valid"] = n_valid
+        # ---- dynamic inference
+        if eng.hier:
+            tmp1 = _dpi_forward(eng.dpis[0], x, None, tape["dpi"])
+            y1 = ops.linear_f32(tmp1, eng.dpis[0].hidden, None)
+            y1n = ops.group_layernorm(y1, *eng.hier_ln, n_outer=B, outer_stride=g_sz, cols=g_sz, relu=True)
+            # F.dropout(p=0.5) (dynamic_infer_module.py:495; honours train/eval under oracle patch H)
+            hmask = _dropout_mask(y1n.shape, 0.5, dev, training)
+            y1d = ops.scale_mask(y1n, hmask, 2.0) if hmask is not None else y1n
+            tape.update(y1=y1, hmask=hmask, y1d=y1d)
+            tmp2 = _dpi_forward(eng.dpis[1], y1d, None, tape["dpi"])
+            g = ops.linear_f32(tmp2, eng.dpis[1].hidden, None)
+        else:
+            g = None
+            for i, dpi in enumerate(eng.dpis):
+                tmp = _dpi_forward(dpi, x, n_valid, tape["dpi"])
+                g = ops.linear_f32(tmp, dpi.hidden, None, out=g, accumulate=i > 0)
+        tape["g"] = g
+        # ---- fusion + LayerNorm + ReLU
+        if eng.dataset == "collective":
+            s = torch.zeros_like(g)
+            ops.group_layernorm(g, *eng.dpi_nl, n_outer=B, n_inner=N, outer_stride=g_sz, inner_stride=C, rows=T,
+                                row_stride=N * C, cols=C, relu=True, pre=x, n_valid=n_valid, out=s)
+        elif eng.backbone_name == "res18":
+            s = ops.group_layernorm(g, *eng.dpi_nl, n_outer=B, outer_stride=g_sz, cols=g_sz, relu=True, post=x)
+        else:
+            s = ops.group_layernorm(g, *eng.dpi_nl, n_outer=B, outer_stride=g_sz, cols=g_sz, relu=True, pre=x)
+        # ---- dropout_global (infer_model.py:209,216 / :1303) and read-out
+        p = float(cfg.train_dropout_prob)
+        mask = _dropout_mask(s.shape, p, dev, training)
+        s_d = ops.scale_mask(s, mask, 1.0 / (1.0 - p)) if mask is not None else s
+        tape.update(mask=mask, s_d=s_d, p=p)
+        logits = ops.readout(s_d, *eng.fc_act, n_valid=n_valid)
+    return logits, tape
+
+
+def backward_head(eng, tape, dlogits):
+    """d(loss)/d(logits) [B, A] -> {reference parameter name: gradient} for every parameter after the backbone."""
+    cfg = eng.cfg
+    B, T = tape["B"], tape["T"]
+    N, C, NFB = eng.N, eng.C, eng.NFB
+    M = B * T * N
+    g_sz = T * N * C
+    n_valid = tape["n_valid"]
+    x, g = tape["x"], tape["g"]
+    grads = {}
+    with torch.no_grad():
+        # ---- read-out and dropout
+        ds_d, dwa, dba = ops.readout_bwd(tape["s_d"], eng.fc_act[0], dlogits.contiguous().float(), n_valid=n_valid)
+        grads["fc_activities.weight"], grads["fc_activities.bias"] = dwa, dba
+        ds = ops.scale_mask(ds_d, tape["mask"], 1.0 / (1.0 - tape["p"])) if tape["mask"] is not None else ds_d
+        # ---- fusion LayerNorm: dg, and the gradient x receives directly (dx)
+        if eng.dataset == "collective":
+            dg, dgam, dbet = ops.group_layernorm_bwd(g, *eng.dpi_nl, ds, n_outer=B, n_inner=N, outer_stride=g_sz,
+                                                     inner_stride=C, rows=T, row_stride=N * C, cols=C, relu=True,
+                                                     pre=x, n_valid=n_valid)
+            dx = dg.clone()
+        elif eng.backbone_name == "res18":
+            dg, dgam, dbet = ops.group_layernorm_bwd(g, *eng.dpi_nl, ds, n_outer=B, outer_stride=g_sz, cols=g_sz,
+                                                     relu=True)
+            dx = ds.clone()                                    # `+ x` after the ReLU (infer_model.py:207)
+        else:
+            dg, dgam, dbet = ops.group_layernorm_bwd(g, *eng.dpi_nl, ds, n_outer=B, outer_stride=g_sz, cols=g_sz,
+                                                     relu=True, pre=x)
+            dx = dg.clone()                                    # LN(g + x): x gets the same gradient as g
+        grads["dpi_nl.weight"], grads["dpi_nl.bias"] = dgam.view_as(eng.dpi_nl[0]), dbet.view_as(eng.dpi_nl[1])
+        # ---- dynamic inference
+        if eng.hier:
+            (_, dpi1, x1, tmp1), (_, dpi2, x2, tmp2) = tape["dpi"]
+            dy1d = torch.zeros_like(x2)
+            _dpi_backward(dpi2, "DPI.DPI_2.", x2, tmp2, dg, dy1d, None, grads)
+            dy1n = ops.scale_mask(dy1d, tape["hmask"], 2.0) if tape["hmask"] is not None else dy1d
+            dy1, dgam, dbet = ops.group_layernorm_bwd(tape["y1"], *eng.hier_ln, dy1n, n_outer=B, outer_stride=g_sz,
+                                                      cols=g_sz, relu=True)
+            grads["DPI.hier_LN.weight"] = dgam.view_as(eng.hier_ln[0])
+            grads["DPI.hier_LN.bias"] = dbet.view_as(eng.hier_ln[1])
+            _dpi_backward(dpi1, "DPI.DPI_1.", x1, tmp1, dy1, dx, None, grads)
+        else:
+            for i, (_, dpi, xi, tmp) in enumerate(tape["dpi"]):
+                prefix = "DPI." if eng.dataset == "collective" else f"DPI.DIMlist.{i}."
+                _dpi_backward(dpi, prefix, xi, tmp, dg, dx, n_valid, grads)
+        # ---- lite branch
+        dx = dx.view(M, C)
+        if cfg.lite_dim:
+            dyl, dgam, dbet = ops.group_layernorm_bwd(tape["ylite"], *eng.point_ln, dx, n_outer=B, outer_stride=g_sz,
+                                                      cols=g_sz, relu=True)
+            grads["point_ln.weight"] = dgam.view_as(eng.point_ln[0])
+            grads["point_ln.bias"] = dbet.view_as(eng.point_ln[1])
+            dx0, dwp, dbp = ops.linear_bwd(tape["x0"], eng.point_w, dyl)
+            grads["point_conv.weight"], grads["point_conv.bias"] = dwp.view(C, NFB, 1, 1), dbp
+        else:
+            dx0 = dx
+        # ---- nl_emb_1 + fc_emb_1
+        demb, dgam, dbet = ops.group_layernorm_bwd(tape["emb"], *eng.nl_emb, dx0, n_outer=M, outer_stride=NFB,
+                                                   cols=NFB, relu=True)
+        grads["nl_emb_1.weight"], grads["nl_emb_1.bias"] = dgam, dbet
+        # dW in the kernel's K order (ky, kx, d_padded) -> the reference's (d, ky, kx) flatten (layout only)
+        _, dwk, dbe = ops.linear_bwd(tape["crops"], None, demb, need_dx=False)
+        KK = eng.K * eng.K
+        grads["fc_emb_1.weight"] = dwk.view(NFB, KK, eng.D_stride)[:, :, :eng.D].permute(0, 2, 1).reshape(NFB, -1) \
+            .contiguous()
+        grads["fc_emb_1.bias"] = dbe
+    return grads

@@ -6,7 +6,10 @@ so `scripts/train_volleyball_stage2_dynamic.py`'s model registry resolves and st
 checkpoints load unchanged.  forward() runs the sm_100a plan (din_b200/engine.py); torch modules below
 are parameter containers and are never called.
 
-Scope: evaluation / inference forward (no autograd through the CUDA path yet).
+Scope: evaluation / inference forward, and the training step with the backbone frozen (config.py:39
+`train_backbone = False`): `model.train()` + `loss.backward()` produce gradients for every parameter after the
+backbone through the backward kernels in csrc/head_bwd.cu (first slice).  Training the
+backbone itself (conv dgrad / wgrad) is not implemented and raises.
 """
 import collections
 
@@ -14,6 +17,7 @@ import torch
 import torch.nn as nn
 
 from backbone.backbone import MyInception_v3, MyRes18, MyVGG16
+from din_b200 import train as _train
 from din_b200.engine import DinEngine
 from infer_module.dynamic_infer_module import (Dynamic_Person_Inference, Hierarchical_Dynamic_Inference,
                                                Multi_Dynamic_Inference)
@@ -35,6 +39,26 @@ def _make_backbone(cfg):
     if cfg.backbone == "res18":
         return MyRes18(pretrained=True)
     raise NotImplementedError(f"backbone {cfg.backbone!r} is outside the DIN hot-path scope")
+
+
+class _DinTrainFn(torch.autograd.Function):
+    """The whole CUDA path as ONE autograd node: forward = din_b200.train.forward_train, backward =
+    din_b200.train.backward_head (gradients under the reference's parameter names)."""
+
+    @staticmethod
+    def forward(ctx, model, images, boxes, bboxes_num, names, *params):
+        logits, tape = _train.forward_train(model.engine(), images, boxes, bboxes_num, training=model.training)
+        ctx.eng, ctx.tape, ctx.names = model.engine(), tape, names
+        ctx.shapes = [tuple(p.shape) for p in params]
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        grads = _train.backward_head(ctx.eng, ctx.tape, dlogits)
+        ctx.tape = None
+        out = [grads[n].reshape(shp) if (need and n in grads) else None
+               for n, shp, need in zip(ctx.names, ctx.shapes, ctx.needs_input_grad[5:])]
+        return (None, None, None, None, None) + tuple(out)
 
 
 class _DinModel(nn.Module):
@@ -109,10 +133,28 @@ class _DinModel(nn.Module):
     def _check_mode(self, images):
         if not images.is_cuda:
             raise RuntimeError("the DIN hot path runs on sm_100a only: pass CUDA tensors (there is no CPU fallback)")
-        if self.training and torch.is_grad_enabled():
+
+    def _run(self, images, boxes, bboxes_num=None):
+        """eval: the forward plan.  train: forward with dropout; with grad enabled additionally one autograd
+        node whose backward is the CUDA head backward."""
+        eng = self.engine()
+        if not self.training:
+            if self._dataset == "collective":
+                return eng.forward_collective(images, boxes, bboxes_num)
+            return eng.forward_volleyball(images, boxes)
+        if any(isinstance(m, nn.modules.batchnorm._BatchNorm) and m.training for m in self.backbone.modules()):
             raise NotImplementedError(
-                "the sm_100a DIN path is forward-only in this release: use model.eval() and/or "
-                "torch.no_grad() (backward kernels: SURVEY.md §8f)")
+                "train mode with BatchNorm batch statistics is not implemented on the sm_100a path: freeze BN as "
+                "the reference does with cfg.set_bn_eval (train_net_dynamic.py:101-102, model.apply(set_bn_eval))")
+        if not torch.is_grad_enabled():
+            return _train.forward_train(eng, images, boxes, bboxes_num, training=True)[0]
+        if any(p.requires_grad for p in self.backbone.parameters()):
+            raise NotImplementedError(
+                "training the backbone (conv dgrad / wgrad kernels) is not implemented on the sm_100a path yet: "
+                "set cfg.train_backbone = False (config.py:39, the stage-2 default) -- SURVEY.md §8f rank 1")
+        named = [(n, p) for n, p in self.named_parameters() if not n.startswith("backbone.") and p.requires_grad]
+        names = tuple(n for n, _ in named)
+        return _DinTrainFn.apply(self, images, boxes, bboxes_num, names, *[p for _, p in named])
 
 
 class Dynamic_volleyball(_DinModel):
@@ -127,7 +169,7 @@ class Dynamic_volleyball(_DinModel):
         images_in, boxes_in = batch_data
         self._check_mode(images_in)
         with torch.cuda.device(images_in.device):
-            scores = self.engine().forward_volleyball(_as_frames(images_in), boxes_in.float())
+            scores = self._run(_as_frames(images_in), boxes_in.float())
         return {"activities": scores}
 
 
@@ -143,7 +185,7 @@ class Dynamic_collective(_DinModel):
         images_in, boxes_in, bboxes_num_in = batch_data
         self._check_mode(images_in)
         with torch.cuda.device(images_in.device):
-            scores = self.engine().forward_collective(_as_frames(images_in), boxes_in.float(), bboxes_num_in)
+            scores = self._run(_as_frames(images_in), boxes_in.float(), bboxes_num_in)
         return {"activities": scores}
 
 

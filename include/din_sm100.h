@@ -241,6 +241,69 @@ DIN_API int din_ce_metrics_f32(const float* logits, const int64_t* labels, const
  */
 DIN_API int din_mean_axis_f32(const float* x, float* y, int outer, int len, int inner, void* stream);
 
+/* ---- backward of the person-level head (first slice) ------------------------ *
+ * What `total_loss.backward()` (train_net_dynamic.py:220-224) computes for everything after the feature map,
+ * i.e. the stage-2 training step with the backbone frozen (config.py:39 train_backbone = False).  All fp32.
+ * Parameter gradients are OVERWRITTEN (fixed summation order, deterministic); activation gradients follow the
+ * per-call `accumulate` / "+=" rules stated below.                                                            */
+
+/*
+ * General strided GEMM: c[m, n] (+)= alpha * sum_k A(m, k) * B(k, n),  A(m,k) = a[m*a_stride_m + k*a_stride_k]
+ * (fp32), B(k,n) = b[k*b_stride_k + n*b_stride_n] (fp32, or fp16 when b_is_f16 -- the RoIAlign crops).
+ * Replaces autograd's mm / addmm backward of nn.Linear / 1x1 conv: dX = dY.W, dW = dY^T.X
+ *   (fc_emb_1 infer_model.py:184, point_conv :189-190, hidden_weight dynamic_infer_module.py:149).
+ */
+DIN_API int din_gemm_f32(const float* a, long long a_stride_m, long long a_stride_k, const void* b, int b_is_f16,
+                         long long b_stride_k, long long b_stride_n, float* c, long long ldc, int m, int n, int k,
+                         float alpha, int accumulate, void* stream);
+
+/* y[n] = sum_m x[m*ld + n]  (bias gradients of the linears above). */
+DIN_API int din_colsum_f32(const float* x, float* y, int m, int n, long long ld, void* stream);
+
+/* y = x * mask * scale, mask = 0/1 bytes (NULL = ones).  Dropout forward and backward with a caller-supplied
+ * mask (nn.Dropout / F.dropout: infer_model.py:209,216; dynamic_infer_module.py:495). */
+DIN_API int din_scale_mask_f32(const float* x, const uint8_t* mask, float scale, float* y, long long count,
+                               void* stream);
+
+/*
+ * Backward of din_readout_f32 (max over actors -> fc_activities -> mean over frames; infer_model.py:224-232).
+ * s [b,t,n,c], w [a,c], dlogits [b,a]  ->  ds [b,t,n,c] (gradient at each channel's FIRST arg-max actor, zero
+ * elsewhere), dw [a,c], dbias [a].  pooled_ws: workspace [b,t,c].
+ */
+DIN_API int din_readout_bwd_f32(const float* s, const float* w, const float* dlogits, float* ds, float* pooled_ws,
+                                float* dw, float* dbias, int b, int t, int n, int c, int a, const int32_t* n_valid,
+                                void* stream);
+
+/*
+ * Backward of din_group_layernorm_f32 (same group geometry; `post` needs no kernel: its gradient is dy).
+ * dx (+)= d(loss)/d(x) (which is also the gradient of `pre`); dgamma / dbeta [rows*cols] overwritten, or both
+ * NULL.  stats_ws: workspace [2 * n_outer * n_inner].
+ * Replaces autograd through nn.LayerNorm + F.relu (+ residual adds): infer_model.py:185-186, 191-192, 203-216,
+ *   1298-1301; dynamic_infer_module.py:493-494.
+ */
+DIN_API int din_group_layernorm_bwd_f32(const float* x, const float* pre, const float* gamma, const float* beta,
+                                        const float* dy, float* dx, float* dgamma, float* dbeta, float* stats_ws,
+                                        int n_outer, int n_inner, long long outer_stride, long long inner_stride,
+                                        int rows, long long row_stride, int cols, float eps, int relu,
+                                        int accumulate_dx, const int32_t* n_valid, void* stream);
+
+/*
+ * Backward of din_dynamic_infer_f32 for one sampling ratio (dynamic_infer_module.py:184-282 under autograd):
+ * given dy = d(loss)/d(y) where y = coef * DIN_ratio(x),
+ *   dx     += gradient through the four corner gathers (fp32 atomics) and through p_conv / scale_conv
+ *             (the caller zero-fills dx or passes the gradient x already received from other consumers);
+ *   dw_tap  = [kt*kn][n_out][c], db_cat = [n_out]: gradients in the packed layout of the forward;
+ *   dcoef   = [1] d(loss)/d(coef) (the gradient of beta[r] when beta_factor), or NULL.
+ * The offsets receive gradient only through the bilinear weights (floor is detached, :208); clamped positions
+ * pass gradient where 0 <= p <= max (torch.clamp); |.|' = sign with sign(0) = 0.
+ * ws: workspace [b*t*n*(n_out + 1)] floats.  Same shape limits as the forward.
+ */
+DIN_API int din_dynamic_infer_bwd_f32(const float* x, const float* w_tap, const float* b_cat, const float* dy,
+                                      float* dx, float* dw_tap, float* db_cat, float* dcoef, float* ws, int b, int t,
+                                      int n, int c, int kt, int kn, int ratio, int scale_factor,
+                                      const float* coef_ptr, float coef_scalar, const int32_t* n_valid,
+                                      void* stream);
+
 #ifdef __cplusplus
 } /* extern "C" */
 #endif

@@ -66,11 +66,34 @@ def main_basenet():
         print("basenet", name, tuple(actions.shape), tuple(activities.shape))
 
 
+def grad_cases():
+    c = model_cases()
+    return {k: c[k] for k in ("vgg16_lite", "vgg16_full_r13_beta", "vgg16_parallel_fields", "collective_res18")}
+
+
+def main_grads():
+    """Training-step fixtures: the REFERENCE model's own autograd gradients (ref_harness.ref_head_grads)."""
+    for name, (pc, B) in grad_cases().items():
+        bb = O.build_backbone(pc.backbone)
+        sd = O.make_state_dict(pc, seed=0, backbone=bb)
+        batch = O.make_inputs(pc, B, seed=0)
+        labels = torch.arange(B) % pc.num_activities
+        logits, loss, grads = R.ref_head_grads(pc, sd, labels, *batch)
+        torch.save({"config": dataclasses.asdict(pc), "B": B, "seed": 0, "labels": labels, "logits_ref": logits,
+                    "loss_ref": loss, "grads_ref": {k: O.grad_digest(v) for k, v in grads.items()},
+                    "weights_checksum": checksum(sd.values()), "inputs_checksum": checksum(batch)},
+                   os.path.join(OUT, f"grads_{name}.pt"))
+        print("grads", name, float(loss), len(grads))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--grads-only" in sys.argv:
+        return main_grads()
     if "--basenet-only" in sys.argv:
         return main_basenet()
     main_basenet()
+    main_grads()
     for name, (pc, B) in model_cases().items():
         bb = O.build_backbone(pc.backbone)
         sd = O.make_state_dict(pc, seed=0, backbone=bb)

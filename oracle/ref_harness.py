@@ -174,6 +174,29 @@ def ref_forward(pc, sd, *batch):
         return model(tuple(batch))["activities"]
 
 
+def ref_head_grads(pc, sd, labels, *batch):
+    """Train-mode forward + F.cross_entropy + backward of the REFERENCE model (train_net_dynamic.py:170-224)
+    with the backbone frozen (config.py:39), BatchNorm layers in eval mode (train_net_dynamic.py:101-102
+    `set_bn_eval`) and train_dropout_prob = 0 (deterministic).  -> (logits, loss, {param name: grad})."""
+    model = build_ref_model(pc, sd)
+    model.cfg.train_dropout_prob = 0.0
+    model.train()
+    model.dropout_global.p = 0.0
+    for m in model.modules():
+        if isinstance(m, (nn.BatchNorm2d, nn.Dropout)):
+            m.eval()
+    import io
+    import warnings
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        logits = model(tuple(batch))["activities"]
+        loss = F.cross_entropy(logits, labels)
+        loss.backward()
+    grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+    grads = {(n.replace("DPI.inner.", "DPI.") if pc.dataset == "collective" else n): g for n, g in grads.items()}
+    return logits.detach(), loss.detach(), grads
+
+
 def ref_basenet_forward(pc, sd, *batch):
     """The reference's stage-1 Basenet_volleyball / Basenet_collective (base_model.py) in eval mode.
     Basenet_collective hard-codes MyInception_v3 (base_model.py:159); no patches are needed."""

@@ -1,0 +1,393 @@
+"""Backward of the person-level head (first slice) on the GPU, through the C ABI.
+
+Kernel level (same fp32 inputs on both sides => tight tolerances, 1e-4 * max|ref| unless stated):
+  din_gemm_f32, din_group_layernorm_bwd_f32, din_readout_bwd_f32 vs torch autograd (fp32, GPU);
+  din_dynamic_infer_bwd_f32 vs torch autograd over the oracle's restatement of dynamic_infer_ratio (CPU).
+Model level: `model.train()` + cross-entropy + `backward()` on the drop-in models vs autograd over the oracle
+(which tests/test_oracle_cpu.py pins against the REFERENCE model's own gradients), with identical dropout masks;
+and against the committed reference-gradient fixtures directly.  The forward runs fp16 tensor-core operands
+(logits within 1e-3, north_star), so model-level gradients are compared by relative L2 error per tensor:
+||Δ||₂ <= 2e-2 ||ref||₂ (measured values are printed)."""
+import glob
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _close(a, b, tol=1e-4, what=""):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    err = (a - b).abs().max().item()
+    scale = max(b.abs().max().item(), 1e-12)
+    assert err <= tol * scale, f"{what}: max|Δ| {err:.3e} > {tol} * max|ref| {scale:.3e}"
+
+
+# ------------------------------------------------------------------------------------------------
+# kernels
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,n,k", [(70, 33, 50), (128, 64, 16), (1, 27, 960), (200, 129, 7)])
+def test_gemm_strided(cuda, m, n, k):
+    from din_b200 import ops
+    g = torch.Generator().manual_seed(m + n + k)
+    a = torch.randn(m, k, generator=g).to(cuda)
+    b = torch.randn(k, n, generator=g).to(cuda)
+    ref = a @ b
+    _close(ops.gemm_f32(a, b, m=m, n=n, k=k, a_strides=(k, 1), b_strides=(n, 1)), ref, what="NN")
+    at, bt = a.t().contiguous(), b.t().contiguous()
+    _close(ops.gemm_f32(at, bt, m=m, n=n, k=k, a_strides=(1, m), b_strides=(1, k)), ref, what="TT")
+    bh = b.half()
+    _close(ops.gemm_f32(a, bh, m=m, n=n, k=k, a_strides=(k, 1), b_strides=(n, 1)), a @ bh.float(), what="f16 B")
+    out = torch.ones(m, n, device=cuda)
+    ops.gemm_f32(a, b, m=m, n=n, k=k, a_strides=(k, 1), b_strides=(n, 1), out=out, alpha=0.5, accumulate=True)
+    _close(out, 1 + 0.5 * ref, what="alpha/accumulate")
+
+
+def test_linear_bwd(cuda):
+    from din_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(96, 48, generator=g).to(cuda).requires_grad_(True)
+    w = torch.randn(20, 48, generator=g).to(cuda).requires_grad_(True)
+    bias = torch.randn(20, generator=g).to(cuda).requires_grad_(True)
+    dy = torch.randn(96, 20, generator=g).to(cuda)
+    F.linear(x, w, bias).backward(dy)
+    dx, dw, db = ops.linear_bwd(x.detach(), w.detach(), dy)
+    _close(dx, x.grad, what="dx"); _close(dw, w.grad, what="dw"); _close(db, bias.grad, what="db")
+
+
+LN_CASES = {
+    # name: (x shape, normalized dims, pre, post, geometry kwargs builder)
+    "per_person": dict(shape=(37, 64), norm=(64,), pre=False, post=False),
+    "clip_wide_pre": dict(shape=(3, 4, 5, 32), norm=(4, 5, 32), pre=True, post=False),
+    "clip_wide_post": dict(shape=(3, 4, 5, 32), norm=(4, 5, 32), pre=False, post=True),
+}
+
+
+@pytest.mark.parametrize("name", sorted(LN_CASES))
+def test_group_layernorm_bwd(cuda, name):
+    from din_b200 import ops
+    c = LN_CASES[name]
+    g = torch.Generator().manual_seed(7)
+    shp, norm = c["shape"], c["norm"]
+    x = torch.randn(shp, generator=g).to(cuda).requires_grad_(True)
+    pre = torch.randn(shp, generator=g).to(cuda).requires_grad_(True) if c["pre"] else None
+    post = torch.randn(shp, generator=g).to(cuda).requires_grad_(True) if c["post"] else None
+    gamma = (torch.rand(norm, generator=g) + 0.5).to(cuda).requires_grad_(True)
+    beta = (torch.randn(norm, generator=g) * 0.3).to(cuda).requires_grad_(True)
+    dy = torch.randn(shp, generator=g).to(cuda)
+    u = x + pre if pre is not None else x
+    y = F.relu(F.layer_norm(u, norm, gamma, beta, 1e-5))
+    if post is not None:
+        y = y + post
+    y.backward(dy)
+    cols = 1
+    for d in norm:
+        cols *= d
+    n_outer = x.numel() // cols
+    dx, dg, db = ops.group_layernorm_bwd(x.detach(), gamma.detach(), beta.detach(), dy, n_outer=n_outer,
+                                         outer_stride=cols, cols=cols, relu=True,
+                                         pre=None if pre is None else pre.detach())
+    _close(dx, x.grad, what="dx"); _close(dg, gamma.grad, what="dgamma"); _close(db, beta.grad, what="dbeta")
+    if pre is not None:
+        _close(dx, pre.grad, what="dpre")
+    # accumulate into an existing gradient
+    acc = torch.full_like(dx, 2.0)
+    ops.group_layernorm_bwd(x.detach(), gamma.detach(), beta.detach(), dy, n_outer=n_outer, outer_stride=cols,
+                            cols=cols, relu=True, pre=None if pre is None else pre.detach(), dx_out=acc,
+                            accumulate=True, param_grads=False)
+    _close(acc, x.grad + 2.0, what="dx accumulate")
+
+
+def test_group_layernorm_bwd_collective_geometry(cuda):
+    """LayerNorm([T, C]) per (clip, actor) over the [N, T, C] permutation of [T, N, C] with per-clip actor counts."""
+    from din_b200 import ops
+    B, T, N, C = 3, 4, 6, 32
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(B, T, N, C, generator=g).to(cuda)
+    pre = torch.randn(B, T, N, C, generator=g).to(cuda)
+    gamma = (torch.rand(T, C, generator=g) + 0.5).to(cuda).requires_grad_(True)
+    beta = (torch.randn(T, C, generator=g) * 0.3).to(cuda).requires_grad_(True)
+    dy = torch.randn(B, T, N, C, generator=g).to(cuda)
+    nv = torch.tensor([6, 1, 4], dtype=torch.int32, device=cuda)
+    xs = x.clone().requires_grad_(True)
+    total = 0
+    for b in range(B):
+        n = int(nv[b])
+        u = (xs[b, :, :n] + pre[b, :, :n]).permute(1, 0, 2)                         # [n, T, C]
+        y = F.relu(F.layer_norm(u, (T, C), gamma, beta, 1e-5))
+        total = total + (y * dy[b, :, :n].permute(1, 0, 2)).sum()
+    total.backward()
+    dx, dg, db = ops.group_layernorm_bwd(x, gamma.detach(), beta.detach(), dy, n_outer=B, n_inner=N,
+                                         outer_stride=T * N * C, inner_stride=C, rows=T, row_stride=N * C, cols=C,
+                                         relu=True, pre=pre, n_valid=nv)
+    _close(dx, xs.grad, what="dx"); _close(dg, gamma.grad, what="dgamma"); _close(db, beta.grad, what="dbeta")
+
+
+@pytest.mark.parametrize("with_valid", [False, True])
+def test_readout_bwd(cuda, with_valid):
+    from din_b200 import ops
+    B, T, N, C, A = 3, 4, 5, 64, 8
+    g = torch.Generator().manual_seed(3)
+    s = F.relu(torch.randn(B, T, N, C, generator=g)).to(cuda).requires_grad_(True)   # zeros => arg-max ties
+    w = torch.randn(A, C, generator=g).to(cuda).requires_grad_(True)
+    bias = torch.randn(A, generator=g).to(cuda).requires_grad_(True)
+    dl = torch.randn(B, A, generator=g).to(cuda)
+    nv = torch.tensor([5, 2, 1], dtype=torch.int32, device=cuda) if with_valid else None
+    rows = []
+    for b in range(B):
+        n = int(nv[b]) if with_valid else N
+        pooled = s[b, :, :n].max(dim=1)[0]
+        rows.append(F.linear(pooled, w, bias).mean(dim=0, keepdim=True))
+    torch.cat(rows).backward(dl)
+    ds, dw, db = ops.readout_bwd(s.detach(), w.detach(), dl, n_valid=nv)
+    _close(dw, w.grad, what="dw"); _close(db, bias.grad, what="dbias")
+    # ties (several actors at the pooled value, here zeros): any sub-gradient is valid; compare where unique
+    sd = s.detach()
+    n_lim = (nv if with_valid else torch.full((B,), N, device=cuda, dtype=torch.int32)).view(B, 1, 1, 1)
+    valid = torch.arange(N, device=cuda).view(1, 1, N, 1) < n_lim
+    mx = torch.where(valid, sd, torch.full_like(sd, -1e30)).max(dim=2, keepdim=True)[0]
+    unique = ((sd == mx) & valid).sum(dim=2, keepdim=True) == 1
+    assert unique.float().mean().item() > 0.5
+    _close(torch.where(unique, ds, torch.zeros_like(ds)), torch.where(unique, s.grad, torch.zeros_like(ds)), what="ds")
+    # the total gradient mass per (b,t,c) is the same with or without ties
+    _close(ds.sum(dim=2), s.grad.sum(dim=2), what="ds mass")
+
+
+def test_scale_mask(cuda):
+    from din_b200 import ops
+    x = torch.randn(1000, device=cuda)
+    m = (torch.rand(1000, device=cuda) > 0.3).to(torch.uint8)
+    assert torch.equal(ops.scale_mask(x, m, 1.25), x * m.float() * 1.25)
+    assert torch.equal(ops.scale_mask(x, None, 2.0), x * 2.0)
+
+
+DIN_CASES = [
+    # kernel, ratio, scale_factor, beta(coef ptr), T, N, C, n_valid
+    ((3, 3), 1, True, False, 4, 5, 32, None),
+    ((3, 3), 3, True, True, 10, 12, 64, None),
+    ((1, 3), 1, True, False, 4, 5, 32, None),
+    ((3, 1), 2, True, False, 6, 5, 32, None),
+    ((3, 3), 1, False, False, 4, 5, 32, None),
+    ((3, 3), 2, True, True, 5, 13, 32, [13, 1, 4]),
+]
+
+
+@pytest.mark.parametrize("case", DIN_CASES, ids=[str(c[:4]) + ("_valid" if c[7] else "") for c in DIN_CASES])
+def test_dynamic_infer_bwd_matches_oracle_autograd(cuda, case):
+    import din_oracle as O
+    from din_b200 import ops
+    kernel, ratio, scale_factor, beta, T, N, C, valid = case
+    kt, kn = kernel
+    k2 = kt * kn
+    B = 3 if valid else 2
+    g = torch.Generator().manual_seed(100 + ratio + k2)
+    x = torch.randn(B, T, N, C, generator=g)
+    p_w = (torch.randn(2 * k2, C, kt, kn, generator=g) * 0.05).requires_grad_(True)
+    p_b = (torch.randn(2 * k2, generator=g) * 1.2).requires_grad_(True)
+    s_w = (torch.randn(k2, C, kt, kn, generator=g) * 0.05).requires_grad_(True) if scale_factor else None
+    s_b = (torch.randn(k2, generator=g) * 0.5).requires_grad_(True) if scale_factor else None
+    coef = torch.tensor([0.7]).requires_grad_(True)
+    dy = torch.randn(B, T, N, C, generator=g)
+    # ---- oracle: autograd over the restatement (per clip when actor counts vary, as the reference does)
+    xr = x.clone().requires_grad_(True)
+    total = 0
+    for b in range(B):
+        n = valid[b] if valid else N
+        out, _ = O.din_ratio(xr[b:b + 1, :, :n], p_w, p_b, s_w, s_b, kernel, ratio)
+        total = total + ((coef if beta else 0.5) * out * dy[b:b + 1, :, :n]).sum()
+    total.backward()
+    # ---- CUDA
+    w_tap, b_cat = ops.pack_din_weights(p_w.detach().to(cuda), p_b.detach().to(cuda),
+                                        None if s_w is None else s_w.detach().to(cuda),
+                                        None if s_b is None else s_b.detach().to(cuda))
+    nv = torch.tensor(valid, dtype=torch.int32, device=cuda) if valid else None
+    xc, dyc = x.to(cuda), dy.to(cuda)
+    if valid:                                     # gradient of padded actors is not defined by the reference
+        for b in range(B):
+            dyc[b, :, valid[b]:] = 0
+    coef_d = coef.detach().to(cuda)
+    dx = torch.zeros_like(xc)
+    dw, db, dcoef = ops.dynamic_infer_bwd(xc, w_tap, b_cat, dyc, dx, kernel, ratio, scale_factor=scale_factor,
+                                          coef=0.5, coef_ptr=coef_d.data_ptr() if beta else None, want_dcoef=beta,
+                                          n_valid=nv)
+    torch.cuda.synchronize()
+    _close(dx, xr.grad, 2e-4, "dx")
+    w_oihw = dw.permute(1, 2, 0).reshape(dw.shape[1], C, kt, kn)
+    _close(w_oihw[:2 * k2], p_w.grad, 2e-4, "d p_conv.weight")
+    _close(db[:2 * k2], p_b.grad, 2e-4, "d p_conv.bias")
+    if scale_factor:
+        _close(w_oihw[2 * k2:], s_w.grad, 2e-4, "d scale_conv.weight")
+        _close(db[2 * k2:], s_b.grad, 2e-4, "d scale_conv.bias")
+    if beta:
+        _close(dcoef, coef.grad, 2e-4, "d beta")
+
+
+# ------------------------------------------------------------------------------------------------
+# whole training step
+# ------------------------------------------------------------------------------------------------
+def _model_and_cfg(cuda, pc, sd, dropout):
+    import infer_model as IM
+    from config import Config
+    cfg = Config(pc.dataset)
+    cfg.log_path = None
+    for k in ("backbone", "image_size", "out_size", "emb_features", "num_frames", "num_boxes", "crop_size",
+              "num_features_boxes", "num_activities", "lite_dim", "ST_kernel_size", "scale_factor", "beta_factor",
+              "hierarchical_inference", "num_DIM"):
+        setattr(cfg, k, getattr(pc, k))
+    cfg.sampling_ratio = list(pc.sampling_ratio)
+    cfg.num_features_gcn = pc.num_features_boxes
+    cfg.train_backbone = False
+    cfg.train_dropout_prob = dropout
+    model = (IM.Dynamic_collective if pc.dataset == "collective" else IM.Dynamic_volleyball)(cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(cuda).train()
+    for m in model.modules():                       # the reference's set_bn_eval (train_net_dynamic.py:101-102)
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            m.eval()
+    return model, cfg
+
+
+def _rel_l2(a, b):
+    a, b = a.detach().double().cpu().flatten(), b.detach().double().cpu().flatten()
+    return float((a - b).norm() / max(float(b.norm()), 1e-30))
+
+
+def _pc(backbone, hw, **kw):
+    import din_oracle as O
+    return O.PathConfig(backbone=backbone, image_size=hw, out_size=O.backbone_out_size(backbone, *hw), **kw)
+
+
+STEP_CASES = {
+    "vgg16_lite": (dict(backbone="vgg16", hw=(96, 160), num_frames=3, num_boxes=4), 2, 0.3),
+    "vgg16_lite_nodrop": (dict(backbone="vgg16", hw=(96, 160), num_frames=3, num_boxes=4), 2, 0.0),
+    "res18_lite": (dict(backbone="res18", hw=(96, 160), num_frames=3, num_boxes=4), 2, 0.3),
+    "vgg16_full_r13_beta": (dict(backbone="vgg16", hw=(96, 160), num_frames=4, num_boxes=5, lite_dim=None,
+                                 sampling_ratio=(1, 3), beta_factor=True), 2, 0.3),
+    "vgg16_parallel_fields": (dict(backbone="vgg16", hw=(96, 160), num_frames=4, num_boxes=5,
+                                   ST_kernel_size=[(1, 3), (3, 1)], num_DIM=2), 2, 0.3),
+    "vgg16_hierarchical": (dict(backbone="vgg16", hw=(64, 96), num_frames=10, num_boxes=12, lite_dim=None,
+                                ST_kernel_size=[(1, 3), (3, 1)], hierarchical_inference=True), 1, 0.3),
+    "collective_res18": (dict(backbone="res18", hw=(96, 144), dataset="collective", num_frames=3, num_boxes=13,
+                              lite_dim=None, ST_kernel_size=(3, 3), num_activities=4), 3, 0.5),
+}
+
+
+@pytest.mark.parametrize("name", sorted(STEP_CASES))
+def test_training_step_matches_oracle(cuda, name):
+    """model.train(); loss = cross_entropy(model(batch)); loss.backward()  vs autograd over the oracle, with the
+    same dropout masks (drawn from torch's CUDA generator in the order the path draws them)."""
+    import din_oracle as O
+    from din_b200 import metrics
+    kw, B, p = STEP_CASES[name]
+    kw = dict(kw)
+    pc = _pc(kw.pop("backbone"), kw.pop("hw"), **kw)
+    bb = O.build_backbone(pc.backbone)
+    sd = O.make_state_dict(pc, seed=0, backbone=bb)
+    O.load_backbone(bb, sd)
+    bb.eval()
+    batch = O.make_inputs(pc, B, seed=0)
+    labels = torch.arange(B) % pc.num_activities
+    model, cfg = _model_and_cfg(cuda, pc, sd, p)
+    T, N, C = pc.num_frames, pc.num_boxes, pc.in_dim
+    # ---- CUDA step
+    torch.manual_seed(1234)
+    out = model(tuple(t.to(cuda) for t in batch))["activities"]
+    loss = metrics.cross_entropy(out, labels.to(cuda))
+    loss.backward()
+    torch.cuda.synchronize()
+    # ---- the same masks for the oracle
+    torch.manual_seed(1234)
+    hmask = None
+    if pc.hierarchical_inference:
+        hmask = (torch.rand((B, T, N, C), device=cuda) >= 0.5).cpu()
+    mask = (torch.rand((B, T, N, C), device=cuda) >= p).cpu() if p > 0 else None
+    ref_logits, ref_loss, ref_grads = O.head_grads(bb, sd, pc, labels, *batch,
+                                                   train={"p": p, "mask": mask, "hmask": hmask})
+    err = (out.detach().cpu() - ref_logits).abs().max().item()
+    assert err <= 1e-3 * ref_logits.abs().max().item(), ("logits", err)
+    assert abs(loss.item() - ref_loss.item()) <= 2e-3 * max(1.0, abs(ref_loss.item()))
+    got = {n: q.grad for n, q in model.named_parameters() if q.grad is not None}
+    assert set(got) == set(ref_grads), set(got) ^ set(ref_grads)
+    worst = 0.0
+    for k in sorted(ref_grads):
+        r = _rel_l2(got[k], ref_grads[k])
+        worst = max(worst, r)
+        print(f"[step {name}] {k:45s} rel-L2 {r:.2e}  |ref| {float(ref_grads[k].norm()):.3e}")
+        assert r <= 2e-2, (k, r)
+    print(f"[step {name}] logits max|Δ| {err:.2e}, loss {loss.item():.6f} vs {ref_loss.item():.6f}, worst rel-L2 {worst:.2e}")
+    assert all(q.grad is None for n, q in model.named_parameters() if n.startswith("backbone."))
+
+
+GRAD_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "grads_*.pt")))
+
+
+@pytest.mark.parametrize("path", GRAD_FIXTURES, ids=[os.path.basename(p) for p in GRAD_FIXTURES])
+def test_training_step_matches_reference_fixture(cuda, path):
+    """CUDA gradients vs the gradients the REFERENCE model produced (tests/golden/grads_*.pt; dropout 0)."""
+    import din_oracle as O
+    from din_b200 import metrics
+    from test_oracle_cpu import _pc_from
+    fx = torch.load(path)
+    pc = _pc_from(fx["config"])
+    sd = O.make_state_dict(pc, seed=fx["seed"])
+    batch = O.make_inputs(pc, fx["B"], seed=fx["seed"])
+    model, _ = _model_and_cfg(cuda, pc, sd, 0.0)
+    out = model(tuple(t.to(cuda) for t in batch))["activities"]
+    loss = metrics.cross_entropy(out, fx["labels"].to(cuda))
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - float(fx["loss_ref"])) <= 2e-3 * max(1.0, abs(float(fx["loss_ref"])))
+    got = {n: q.grad for n, q in model.named_parameters() if q.grad is not None}
+    assert set(got) == set(fx["grads_ref"])
+    for k, d in fx["grads_ref"].items():
+        flat = got[k].detach().double().cpu().flatten()
+        assert tuple(got[k].shape) == tuple(d["shape"])
+        l2 = float(flat.norm())
+        assert abs(l2 - d["l2"]) <= 2e-2 * max(d["l2"], 1e-30), (k, l2, d["l2"])
+        smp = (flat[d["idx"]].float() - d["samples"]).abs().max().item()
+        assert smp <= 2e-2 * max(d["max_abs"], 1e-30), (k, smp, d["max_abs"])
+
+
+def test_optimizer_loop_and_modes(cuda):
+    """Two Adam steps as train_net_dynamic.py:170-224 runs them (weights change => the plan is rebuilt), then
+    eval; training the backbone or batch-stat BatchNorm raise instead of silently doing something else."""
+    import din_oracle as O
+    from din_b200 import metrics
+    pc = _pc("vgg16", (96, 160), num_frames=3, num_boxes=4)
+    sd = O.make_state_dict(pc, seed=0)
+    batch = tuple(t.to(cuda) for t in O.make_inputs(pc, 2, seed=0))
+    labels = torch.tensor([1, 5], device=cuda)
+    model, cfg = _model_and_cfg(cuda, pc, sd, 0.3)
+    params = [q for q in model.parameters() if q.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-3)
+    meters = metrics.DeviceMeters(pc.num_activities, cuda)
+    losses = []
+    before = model.fc_activities.weight.detach().clone()
+    for _ in range(3):
+        out = model(batch)["activities"]
+        loss = metrics.cross_entropy(out, labels, meters=meters)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(torch.isfinite(torch.tensor(losses))) and not torch.equal(before, model.fc_activities.weight)
+    assert meters.value()["steps"] == 3
+    model.eval()
+    with torch.no_grad():
+        assert torch.isfinite(model(batch)["activities"]).all()
+    # backbone training is not implemented: loud error, no silent fallback
+    model.train()
+    for q in model.backbone.parameters():
+        q.requires_grad = True
+    with pytest.raises(NotImplementedError, match="training the backbone"):
+        model(batch)
+    pc2 = _pc("res18", (96, 160), num_frames=3, num_boxes=4)
+    m2, _ = _model_and_cfg(cuda, pc2, O.make_state_dict(pc2, seed=0), 0.3)
+    m2.train()                                        # BatchNorm back to batch statistics
+    with pytest.raises(NotImplementedError, match="BatchNorm"):
+        m2(batch)

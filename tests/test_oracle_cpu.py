@@ -30,6 +30,7 @@ BASENET_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "basenet_*.pt")))
 
 def test_fixtures_present():
     assert len(MODEL_FIXTURES) == 7 and len(MODULE_FIXTURES) == 4 and len(BASENET_FIXTURES) == 3
+    assert len(glob.glob(os.path.join(GOLDEN, "grads_*.pt"))) == 4
 
 
 @pytest.mark.parametrize("path", BASENET_FIXTURES, ids=[os.path.basename(p) for p in BASENET_FIXTURES])
@@ -156,3 +157,37 @@ def test_config_defaults_match_reference():
         assert set(a) == set(b), set(a) ^ set(b)
         for k in a:
             assert a[k] == b[k], (ds, k, a[k], b[k])
+
+
+GRAD_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "grads_*.pt")))
+
+
+def _digest_close(g, d, rtol=2e-4):
+    """gradient tensor vs a grad_digest fixture: sampled values and norms, relative to max|grad|."""
+    assert tuple(g.shape) == tuple(d["shape"]), (tuple(g.shape), d["shape"])
+    flat = g.detach().double().flatten()
+    scale = max(d["max_abs"], 1e-30)
+    assert (flat[d["idx"]].float() - d["samples"]).abs().max().item() <= rtol * scale
+    assert abs(float(flat.pow(2).sum().sqrt()) - d["l2"]) <= rtol * max(d["l2"], 1e-30)
+    assert abs(float(flat.sum()) - d["sum"]) <= rtol * max(d["abs_sum"], 1e-30)
+
+
+@pytest.mark.parametrize("path", GRAD_FIXTURES, ids=[os.path.basename(p) for p in GRAD_FIXTURES])
+def test_oracle_autograd_reproduces_reference_gradients(path):
+    """Training step: autograd over the restatement == the reference model's own
+    gradients (frozen backbone, BN eval, dropout 0) for every parameter after the backbone."""
+    import din_oracle as O
+    fx = torch.load(path)
+    pc = _pc_from(fx["config"])
+    bb = O.build_backbone(pc.backbone)
+    sd = O.make_state_dict(pc, seed=fx["seed"], backbone=bb)
+    batch = O.make_inputs(pc, fx["B"], seed=fx["seed"])
+    assert abs(_checksum(sd.values()) - fx["weights_checksum"]) <= 1e-9 * fx["weights_checksum"]
+    O.load_backbone(bb, sd)
+    bb.eval()
+    logits, loss, grads = O.head_grads(bb, sd, pc, fx["labels"], *batch)
+    assert (logits - fx["logits_ref"]).abs().max().item() <= 1e-5 * fx["logits_ref"].abs().max().item()
+    assert abs(float(loss) - float(fx["loss_ref"])) <= 1e-5
+    assert set(grads) == set(fx["grads_ref"]), set(grads) ^ set(fx["grads_ref"])
+    for k, d in fx["grads_ref"].items():
+        _digest_close(grads[k], d)
