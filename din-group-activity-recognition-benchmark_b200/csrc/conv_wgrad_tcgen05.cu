@@ -1,0 +1,312 @@
+// conv_wgrad_tcgen05.cu — weight gradient of the backbone's 3x3 stride-1 convolutions on the tcgen05 tensor cores.
+//
+// What autograd computes for nn.Conv2d.weight in `total_loss.backward()` (train_net_dynamic.py:220-224) when the
+// backbone is trained (scripts/train_volleyball_stage2_dynamic.py:12 `cfg.train_backbone = True`; VGG-16
+// features.*, backbone.py:88-99):
+//     dW[co][ky][kx][ci] = sum over (img, y, x) of  dZ[img, y, x, co] * X[img, y + ky - pad, x + kx - pad, ci]
+// i.e. a GEMM whose K dimension is the PIXEL index: D[co, (kx, ci)] += dZ^T[co, pixel] * X_shifted[pixel, ci].
+//
+// Both operands are NHWC fp16 activations, so the pixel index is the slow dimension of both tiles: they are
+// *MN-major* UMMA operands (instruction-descriptor bits 15/16), and the very same TMA boxes the forward kernel
+// loads (64 channels = one 128-byte swizzle row per pixel) are consumed without any transpose:
+//   * A = dZ tile: 16 x 8 output pixels x 128 output channels = two boxes {64 c, 8 w, 16 h}: K = 128 pixel rows,
+//     8-row groups 1024 B apart (SBO), the two 64-channel halves 16 KB apart (LBO);
+//   * B = the input halo rows of ONE filter row ky: {64 c, 10 w, 16 h} per 64 input channels; tap kx is the same
+//     shared memory seen through a descriptor shifted by kx rows, with SBO = the halo pitch (10 rows): the
+//     hardware applies the 128B swizzle on absolute address bits (probed for the forward kernel);
+//   * accumulators: three taps x NCI input channels = 384 (192) fp32 TMEM columns, accumulated over ALL pixel
+//     tiles the CTA owns (no per-tile epilogue); TMA zero-fill is the padding and also nulls ragged tiles.
+// Work unit = (128 output channels, NCI input channels, filter row ky); the pixel tiles of a unit are split over
+// several CTAs so that the grid fills the 148 SMs about twice; each CTA finishes with fp32 vector atomics into dW
+// (scaled by 1/loss-scale).  One producer warp, one MMA warp (a single elected lane issues), four epilogue warps.
+#include "din_common.cuh"
+
+namespace {
+
+using namespace din;
+
+struct WgradParams {
+  int c_in, c_out, kh, kw;
+  int pad_h, pad_w;
+  int tiles_x, tiles_per_img, num_tiles;   // 16 x 8 tiles of the dZ grid, all images
+  int n_ci_blk;                            // c_in / NCI
+  int tiles_per_split, splits;
+  float* dw;                               // [c_out][kh][kw][c_in] fp32
+  const float* inv_scale;                  // device scalar (1 / loss scale) or nullptr
+};
+
+constexpr int kWgThreads = 192;
+constexpr int kWgABytes = 128 * 128;       // one 64-channel half of the dZ tile: 128 pixel rows x 128 B
+constexpr int kWgBBytes = 160 * 128;       // one 64-channel block of the halo rows: 16 x 10 pixel rows x 128 B
+constexpr int kWgMaxStages = 6;
+
+// shared-memory descriptor for an MN-major SWIZZLE_128B operand (canonical layout ((8,8,m),(8,k)) in 16-byte
+// units: 64 contiguous MN elements per 128-byte row, 8 K rows per group): LBO = bytes between 64-element MN
+// chunks, SBO = bytes between 8-row K groups.
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr >> 4) & 0x3FFFu);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1u) << 46;
+  d |= static_cast<uint64_t>(2u) << 61;
+  return d;
+}
+
+// kind::f16 instruction descriptor: fp16 A/B, fp32 D, BOTH operands MN-major (bits 15, 16)
+__host__ __device__ constexpr uint32_t idesc_f16_f32_mn(int m, int n) {
+  return (1u << 4) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+template <int NCI>
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_constant__ CUtensorMap tmap_x,
+                  const WgradParams p, const int n_stages) {
+  constexpr int kStageBytes = 2 * kWgABytes + (NCI / 64) * kWgBBytes;
+  constexpr int kTmemCols = (3 * NCI <= 256) ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem(smem_raw, 1024);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + n_stages * kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = full + kWgMaxStages;
+  uint64_t* acc_full = empty + kWgMaxStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // ---- which unit / which slice of the pixel tiles
+  const int unit = blockIdx.x / p.splits;
+  const int split = blockIdx.x - unit * p.splits;
+  const int ky = unit % p.kh;
+  const int blk = unit / p.kh;
+  const int ci0 = (blk % p.n_ci_blk) * NCI;
+  const int co0 = (blk / p.n_ci_blk) * 128;
+  const int t_begin = split * p.tiles_per_split;
+  const int t_end = min(p.num_tiles, t_begin + p.tiles_per_split);
+  if (t_begin >= t_end) return;                       // uniform over the CTA
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_dz);
+    tma_prefetch_desc(&tmap_x);
+    for (int s = 0; s < n_stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr_smem);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer (one lane)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        const int img = tile / p.tiles_per_img;
+        const int r = tile - img * p.tiles_per_img;
+        const int tyi = r / p.tiles_x, txi = r - tyi * p.tiles_x;
+        const int x0 = txi * 8, y0 = tyi * 16;
+        mbar_wait(&empty[stage], phase ^ 1u);
+        uint8_t* sa = smem + stage * kStageBytes;
+        uint8_t* sb = sa + 2 * kWgABytes;
+        mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(kStageBytes));
+        tma_load_4d(sa, &tmap_dz, &full[stage], co0, x0, y0, img);
+        tma_load_4d(sa + kWgABytes, &tmap_dz, &full[stage], co0 + 64, x0, y0, img);   // beyond c_out: zero fill
+#pragma unroll
+        for (int c = 0; c < NCI / 64; ++c)
+          tma_load_4d(sb + c * kWgBBytes, &tmap_x, &full[stage], ci0 + c * 64, x0 - p.pad_w, y0 + ky - p.pad_h, img);
+        if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, one lane issues)
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = idesc_f16_f32_mn(128, NCI);
+    const uint32_t smem0 = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t accum = 0;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after_sync();
+      const uint32_t sa = smem0 + stage * kStageBytes;
+      const uint32_t sb = sa + 2 * kWgABytes;
+      if (leader) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {            // 16 pixels (two 8-pixel tile rows) per MMA
+            const uint64_t ad = desc_mn_sw128(sa + ks * 2048, kWgABytes, 1024);
+            const uint64_t bd = desc_mn_sw128(sb + kx * 128 + ks * 2560, kWgBBytes, 1280);
+            umma_f16_ss(tmem_base + kx * NCI, ad, bd, idesc, ks == 0 ? accum : 1u);
+          }
+        }
+        umma_commit(&empty[stage]);
+      }
+      accum = 1;
+      if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+    }
+    if (leader) umma_commit(acc_full);
+  } else {
+    // ------------------------------------------------------------------ epilogue: TMEM -> fp32 atomics into dW
+    const int q = warp & 3;                            // TMEM lane quadrant this warp may read
+    mbar_wait(acc_full, 0);
+    tc_fence_after_sync();
+    const float scl = p.inv_scale ? __ldg(p.inv_scale) : 1.0f;
+    const int co = co0 + q * 32 + lane;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+    for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < NCI; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + kx * NCI + c0, v);
+        tmem_ld_wait();
+        if (co < p.c_out) {
+          float* dst = p.dw + ((static_cast<size_t>(co) * p.kh + ky) * p.kw + kx) * p.c_in + ci0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            atomicAdd(reinterpret_cast<float4*>(dst + j),
+                      make_float4(__uint_as_float(v[j]) * scl, __uint_as_float(v[j + 1]) * scl,
+                                  __uint_as_float(v[j + 2]) * scl, __uint_as_float(v[j + 3]) * scl));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// db[c] += inv_scale * sum over pixels of dz[p][c]     (bias gradient; fp16 in, fp32 atomics out)
+__global__ void __launch_bounds__(256)
+colsum_f16_kernel(const __half* __restrict__ dz, float* __restrict__ db, long long rows, int c, int c_stride,
+                  const float* __restrict__ inv_scale) {
+  __shared__ float red[256][8 + 1];
+  const int octs = c >> 3;                              // channel octets
+  const int lanes_r = 256 / octs;                       // row lanes per CTA (octs <= 256)
+  const int oct = threadIdx.x % octs, rl = threadIdx.x / octs;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (rl < lanes_r) {
+    for (long long r = static_cast<long long>(blockIdx.x) * lanes_r + rl; r < rows;
+         r += static_cast<long long>(gridDim.x) * lanes_r) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(dz + r * c_stride) + oct);
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h[e]);
+        acc[2 * e] += f.x;
+        acc[2 * e + 1] += f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[threadIdx.x][e] = acc[e];
+  __syncthreads();
+  if (threadIdx.x < octs) {
+    const float scl = inv_scale ? __ldg(inv_scale) : 1.0f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float s = 0.0f;
+      for (int l = 0; l < lanes_r; ++l) s += red[l * octs + threadIdx.x][e];
+      atomicAdd(db + threadIdx.x * 8 + e, s * scl);
+    }
+  }
+}
+
+template <int NCI>
+int launch_wgrad(const CUtensorMap& tdz, const CUtensorMap& tx, const WgradParams& p, int grid, cudaStream_t st) {
+  constexpr int kStageBytes = 2 * kWgABytes + (NCI / 64) * kWgBBytes;
+  int n_stages = (220 * 1024) / kStageBytes;
+  if (n_stages > 4) n_stages = 4;
+  const size_t smem = static_cast<size_t>(n_stages) * kStageBytes + 1024 + (2 * kWgMaxStages + 1) * 8 + 16;
+  DIN_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<NCI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+  conv_wgrad_kernel<NCI><<<grid, kWgThreads, smem, st>>>(tdz, tx, p, n_stages);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
+}  // namespace
+
+extern "C" int din_conv2d_wgrad_nhwc_f16(const void* x, const void* dz, float* dw, float* dbias,
+                                         const float* inv_scale, int n, int h, int w, int c_in, int x_c_stride,
+                                         int c_out, int dz_c_stride, int kh, int kw, int pad_h, int pad_w,
+                                         void* stream) {
+  DIN_CHECK_ARG(x && dz && dw, "din_conv2d_wgrad_nhwc_f16: null pointer");
+  DIN_CHECK_ARG(n > 0 && h > 0 && w > 0, "din_conv2d_wgrad_nhwc_f16: bad extent n=%d h=%d w=%d", n, h, w);
+  DIN_CHECK_ARG(kh == 3 && kw == 3, "din_conv2d_wgrad_nhwc_f16: only 3x3 stride-1 filters (got %dx%d)", kh, kw);
+  DIN_CHECK_ARG(pad_h >= 0 && pad_h <= 2 && pad_w >= 0 && pad_w <= 2, "din_conv2d_wgrad_nhwc_f16: bad padding");
+  DIN_CHECK_ARG(c_in > 0 && c_in % 64 == 0 && x_c_stride >= c_in && x_c_stride % 8 == 0,
+                "din_conv2d_wgrad_nhwc_f16: c_in=%d must be a multiple of 64 (x_c_stride=%d)", c_in, x_c_stride);
+  DIN_CHECK_ARG(c_out > 0 && c_out % 8 == 0 && dz_c_stride >= c_out && dz_c_stride % 8 == 0,
+                "din_conv2d_wgrad_nhwc_f16: c_out=%d must be a multiple of 8 (dz_c_stride=%d)", c_out, dz_c_stride);
+  DIN_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(dw)) & 15) == 0,
+                "din_conv2d_wgrad_nhwc_f16: pointers must be 16-byte aligned");
+  const int oh = h + 2 * pad_h - kh + 1, ow = w + 2 * pad_w - kw + 1;
+  DIN_CHECK_ARG(oh > 0 && ow > 0, "din_conv2d_wgrad_nhwc_f16: empty output");
+  const int sms = din_num_sms();
+  DIN_CHECK_ARG(sms > 0, "din_conv2d_wgrad_nhwc_f16: no CUDA device");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  const int nci = (c_in % 128 == 0) ? 128 : 64;
+  WgradParams p{};
+  p.c_in = c_in; p.c_out = c_out; p.kh = kh; p.kw = kw; p.pad_h = pad_h; p.pad_w = pad_w;
+  p.tiles_x = (ow + 7) / 8;
+  p.tiles_per_img = p.tiles_x * ((oh + 15) / 16);
+  const long long tiles = static_cast<long long>(n) * p.tiles_per_img;
+  DIN_CHECK_ARG(tiles < INT32_MAX, "din_conv2d_wgrad_nhwc_f16: too many tiles");
+  p.num_tiles = static_cast<int>(tiles);
+  p.n_ci_blk = c_in / nci;
+  const int units = ((c_out + 127) / 128) * p.n_ci_blk * kh;
+  int splits = (2 * sms + units - 1) / units;
+  if (splits > p.num_tiles) splits = p.num_tiles;
+  if (splits < 1) splits = 1;
+  p.tiles_per_split = (p.num_tiles + splits - 1) / splits;
+  p.splits = (p.num_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.dw = dw; p.inv_scale = inv_scale;
+
+  CUtensorMap tdz, tx;
+  {
+    const uint64_t dims[4] = {static_cast<uint64_t>(c_out), static_cast<uint64_t>(ow), static_cast<uint64_t>(oh),
+                              static_cast<uint64_t>(n)};
+    const uint64_t cs = static_cast<uint64_t>(dz_c_stride) * 2;
+    const uint64_t strides[4] = {2, cs, cs * ow, cs * ow * oh};
+    const uint32_t box[4] = {64, 8, 16, 1};
+    const uint32_t es[4] = {1, 1, 1, 1};
+    int rc = din_encode_tmap(&tdz, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(dz), dims, strides, box, es,
+                             CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != DIN_OK) return rc;
+  }
+  {
+    const uint64_t dims[4] = {static_cast<uint64_t>(c_in), static_cast<uint64_t>(w), static_cast<uint64_t>(h),
+                              static_cast<uint64_t>(n)};
+    const uint64_t cs = static_cast<uint64_t>(x_c_stride) * 2;
+    const uint64_t strides[4] = {2, cs, cs * w, cs * w * h};
+    const uint32_t box[4] = {64, 10, 16, 1};
+    const uint32_t es[4] = {1, 1, 1, 1};
+    int rc = din_encode_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
+                             CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != DIN_OK) return rc;
+  }
+  const int grid = units * p.splits;
+  int rc = (nci == 128) ? launch_wgrad<128>(tdz, tx, p, grid, st) : launch_wgrad<64>(tdz, tx, p, grid, st);
+  if (rc != DIN_OK) return rc;
+  if (dbias != nullptr) {
+    DIN_CHECK_ARG(c_out <= 2048, "din_conv2d_wgrad_nhwc_f16: c_out=%d too large for the bias reduction", c_out);
+    const long long rows = static_cast<long long>(n) * oh * ow;
+    int g = 2 * sms;
+    const long long per = 256 / (c_out / 8);
+    if (static_cast<long long>(g) * per > rows) g = static_cast<int>((rows + per - 1) / per);
+    colsum_f16_kernel<<<g, 256, 0, st>>>(static_cast<const __half*>(dz), dbias, rows, c_out, dz_c_stride, inv_scale);
+    DIN_CHECK_CUDA(cudaGetLastError());
+  }
+  return DIN_OK;
+}

@@ -49,6 +49,7 @@ class _DinTrainFn(torch.autograd.Function):
     def forward(ctx, model, images, boxes, bboxes_num, names, *params):
         logits, tape = _train.forward_train(model.engine(), images, boxes, bboxes_num, training=model.training)
         ctx.eng, ctx.tape, ctx.names = model.engine(), tape, names
+        model._last_tape = tape if getattr(model, "keep_tape", False) else None     # test / debugging hook
         ctx.shapes = [tuple(p.shape) for p in params]
         return logits
 

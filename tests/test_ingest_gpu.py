@@ -48,8 +48,10 @@ def test_model_u8_frames_equal_f32_frames(cuda, backbone, hw):
     images, boxes = O.make_inputs(pc, 2, seed=2)                       # fp32 [B,T,3,H,W], integer-valued
     cfg = Config("volleyball")
     cfg.log_path = None
-    for k in ("backbone", "image_size", "out_size", "emb_features", "num_frames", "num_boxes", "lite_dim"):
+    for k in ("backbone", "image_size", "out_size", "emb_features", "num_frames", "num_boxes", "lite_dim",
+              "ST_kernel_size", "scale_factor", "beta_factor", "hierarchical_inference", "num_DIM"):
         setattr(cfg, k, getattr(pc, k))
+    cfg.sampling_ratio = list(pc.sampling_ratio)
     model = IM.Dynamic_volleyball(cfg)
     model.load_state_dict(sd, strict=True)
     model = model.to(cuda).eval()
