@@ -42,6 +42,7 @@ PROTOTYPES = {
     "din_readout_f32": (C.c_int, [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _vp, _vp]),
     "din_ce_metrics_f32": (C.c_int, [_fp, _vp, _fp, C.c_float, _fp, _vp, _vp, _vp, _fp, _i, _i, _vp]),
     "din_mean_axis_f32": (C.c_int, [_fp, _fp, _i, _i, _i, _vp]),
+    "din_conv2d_wgrad_nhwc_f16": (C.c_int, [_vp, _vp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_gemm_f32": (C.c_int, [_fp, _ll, _ll, _vp, _i, _ll, _ll, _fp, _ll, _i, _i, _i, C.c_float, _i, _vp]),
     "din_colsum_f32": (C.c_int, [_fp, _fp, _i, _i, _ll, _vp]),
     "din_scale_mask_f32": (C.c_int, [_fp, _vp, C.c_float, _fp, _ll, _vp]),

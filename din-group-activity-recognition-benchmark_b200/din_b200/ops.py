@@ -434,3 +434,28 @@ def dynamic_infer_bwd(x, w_tap, b_cat, dy, dx, kernel, ratio, *, scale_factor=Tr
                                                     C.c_void_p(coef_ptr or 0), float(coef), _p(n_valid), _stream()),
               "din_dynamic_infer_bwd_f32")
     return dw, db, dcoef
+
+
+# ---------------------------------------------------------------------------------------------
+# backward of the backbone (VGG-16: 3x3 stride-1 convolutions)
+# ---------------------------------------------------------------------------------------------
+def conv2d_wgrad_nhwc(x, dz, dw, dbias=None, *, pad=(1, 1), inv_scale=None, c_in=None, c_out=None):
+    """dw [c_out,3,3,c_in] fp32 (+)= sum_pixels dz (x) x_shifted;  dbias [c_out] (+)= sum_pixels dz.  Accumulates."""
+    _need(x, torch.float16, "x")
+    _need(dz, torch.float16, "dz")
+    _need(dw, torch.float32, "dw")
+    n, h, w, cx = x.shape
+    co, kh, kw, ci = dw.shape
+    assert dz.shape[0] == n and dz.shape[1] == h + 2 * pad[0] - kh + 1 and dz.shape[2] == w + 2 * pad[1] - kw + 1, \
+        (tuple(x.shape), tuple(dz.shape))
+    assert ci <= cx and co <= dz.shape[3]
+    if dbias is not None:
+        _need(dbias, torch.float32, "dbias")
+    if inv_scale is not None:
+        _need(inv_scale, torch.float32, "inv_scale")
+    flops = 2 * n * dz.shape[1] * dz.shape[2] * co * kh * kw * ci
+    with _launch(f"wgrad{kh}x{kw}_{ci}->{co}@{dz.shape[1]}x{dz.shape[2]}", flops, 2 * (x.numel() + dz.numel())):
+        check(_lib.load().din_conv2d_wgrad_nhwc_f16(_p(x), _p(dz), _p(dw), _p(dbias), _p(inv_scale), n, h, w, ci, cx, co,
+                                                    dz.shape[3], kh, kw, pad[0], pad[1], _stream()),
+              "din_conv2d_wgrad_nhwc_f16")
+    return dw

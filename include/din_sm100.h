@@ -304,6 +304,25 @@ DIN_API int din_dynamic_infer_bwd_f32(const float* x, const float* w_tap, const 
                                       const float* coef_ptr, float coef_scalar, const int32_t* n_valid,
                                       void* stream);
 
+/* ---- backward of the backbone (second slice: VGG-16) ------------------------- */
+
+/*
+ * Weight (and bias) gradient of a 3x3 stride-1 convolution on the tcgen05 tensor cores:
+ *     dw[co][ky][kx][ci] += inv_scale * sum_{img,y,x} dz[img,y,x,co] * x[img, y+ky-pad_h, x+kx-pad_w, ci]
+ *     dbias[co]          += inv_scale * sum_{img,y,x} dz[img,y,x,co]                      (dbias may be NULL)
+ * Replaces autograd's conv2d weight/bias backward for vgg16.features.* (backbone.py:88-99) when the backbone is
+ * trained (scripts/train_volleyball_stage2_dynamic.py:12).  The K dimension of this GEMM is the pixel index, so
+ * both NHWC fp16 operands are consumed as MN-major UMMA tiles straight from the forward kernel's TMA boxes.
+ * x  : fp16 NHWC [n, h, w, x_c_stride], channels [0, c_in) used (the conv's saved input), c_in % 64 == 0
+ * dz : fp16 NHWC [n, oh, ow, dz_c_stride], oh = h + 2*pad_h - 2 (gradient w.r.t. the conv output BEFORE ReLU,
+ *      possibly multiplied by a loss scale S; then *inv_scale = 1/S, a device scalar; NULL = 1)
+ * dw : fp32 [c_out][3][3][c_in] -- ACCUMULATED with atomics: zero-fill before the first call of a step (the
+ *      frames of a step may arrive in several calls); dbias likewise.
+ */
+DIN_API int din_conv2d_wgrad_nhwc_f16(const void* x, const void* dz, float* dw, float* dbias, const float* inv_scale,
+                                      int n, int h, int w, int c_in, int x_c_stride, int c_out, int dz_c_stride,
+                                      int kh, int kw, int pad_h, int pad_w, void* stream);
+
 #ifdef __cplusplus
 } /* extern "C" */
 #endif
