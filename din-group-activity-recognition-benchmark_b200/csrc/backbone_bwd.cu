@@ -1,0 +1,291 @@
+// backbone_bwd.cu — the HBM-bound pieces of the backbone's backward pass (SURVEY.md §8f rank 1, VGG-16 slice):
+//   * RoIAlign backward (bilinear scatter of the crop gradients into the feature-map gradient);
+//   * fp32 -> scaled fp16 conversion of the feature-map gradient (dynamic power-of-two loss scale);
+//   * ReLU (+ MaxPool2d(2,2)) backward between two convolutions;
+//   * weight / bias gradient of the 3-channel stem convolution (fused with prep_images on its input side).
+// The tensor-core pieces are conv_wgrad_tcgen05.cu (dW) and conv_tcgen05.cu itself (dX = the forward kernel run
+// on the 180-degree-rotated, transposed filter).
+//
+// Reference: autograd through roi_align (external crop_and_resize backward; infer_model.py:178-181),
+// vgg16.features (nn.ReLU(inplace), nn.MaxPool2d(2,2), nn.Conv2d; backbone.py:88-99) and prep_images
+// (utils.py:8-19) in `total_loss.backward()` (train_net_dynamic.py:220-224, cfg.train_backbone = True).
+#include <cfloat>
+
+#include "din_common.cuh"
+#include "din_head.cuh"
+
+namespace {
+
+using namespace din;
+
+// ================================================================================================
+// RoIAlign backward: dfm[img, corner, :] += w_corner * dcrop[m, bin, :]   (fp32 atomics; dfm zero-filled by caller)
+// One warp per (box, bin), lanes sweep channels -- the forward's mapping.
+// ================================================================================================
+__global__ void __launch_bounds__(256)
+roi_align_bwd_kernel(const float* __restrict__ dcrops, const float* __restrict__ boxes,
+                     const int* __restrict__ box_ind, float* __restrict__ dfm, int n_img, int H, int W, int D,
+                     int fm_c_stride, int M, int crop_h, int crop_w) {
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int bins = crop_h * crop_w;
+  if (warp_global >= M * bins) return;
+  const int m = warp_global / bins;
+  const int bin = warp_global - m * bins;
+  const int iy = bin / crop_w, ix = bin - iy * crop_w;
+  const RoiSample sp = roi_sample_point(boxes, box_ind, m, iy, ix, n_img, H, W, crop_h, crop_w);
+  if (!sp.ok) return;                                   // extrapolated sample: constant 0, no gradient
+  // forward: top = TL + (TR - TL) xl; bot = BL + (BR - BL) xl; out = top + (bot - top) yl
+  const float wtl = (1.0f - sp.xl) * (1.0f - sp.yl), wtr = sp.xl * (1.0f - sp.yl);
+  const float wbl = (1.0f - sp.xl) * sp.yl, wbr = sp.xl * sp.yl;
+  float* base = dfm + static_cast<size_t>(sp.img) * H * W * fm_c_stride;
+  float* ptl = base + (static_cast<size_t>(sp.top) * W + sp.left) * fm_c_stride;
+  float* ptr = base + (static_cast<size_t>(sp.top) * W + sp.right) * fm_c_stride;
+  float* pbl = base + (static_cast<size_t>(sp.bot) * W + sp.left) * fm_c_stride;
+  float* pbr = base + (static_cast<size_t>(sp.bot) * W + sp.right) * fm_c_stride;
+  const float* g = dcrops + (static_cast<size_t>(m) * bins + bin) * D;
+  for (int c = lane * 4; c < D; c += 128) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g + c));
+    auto add = [&](float* p, float wgt) {
+      if (wgt != 0.0f) atomicAdd(reinterpret_cast<float4*>(p + c), make_float4(v.x * wgt, v.y * wgt, v.z * wgt, v.w * wgt));
+    };
+    add(ptl, wtl); add(ptr, wtr); add(pbl, wbl); add(pbr, wbr);
+  }
+}
+
+// ================================================================================================
+// fp32 gradient -> fp16 with a dynamic power-of-two scale S = 2^floor(log2(target / max|x|)):
+//   scale_ws[0] = max|x| (bit pattern, reduced with atomicMax), [1] = S, [2] = 1/S.
+// The backbone's backward runs on fp16 tensor-core operands; S keeps the gradient inside fp16's normal range
+// and is undone exactly (power of two) in the weight-gradient epilogues.
+// ================================================================================================
+__global__ void __launch_bounds__(256)
+amax_kernel(const float* __restrict__ x, long long count, unsigned int* __restrict__ amax_bits) {
+  float m = 0.0f;
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < count;
+       i += static_cast<long long>(gridDim.x) * 256)
+    m = fmaxf(m, fabsf(__ldg(x + i)));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(amax_bits, __float_as_uint(m));   // non-negative floats order as uints
+}
+
+__global__ void __launch_bounds__(256)
+scale_to_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, long long count, float* __restrict__ scale_ws,
+                    float target) {
+  const float amax = __uint_as_float(*reinterpret_cast<const unsigned int*>(scale_ws));
+  float s = 1.0f;
+  if (amax > 0.0f && isfinite(amax)) {
+    int e;
+    frexpf(target / amax, &e);                            // target/amax = f * 2^e, f in [0.5, 1)
+    e = max(-24, min(24, e - 1));
+    s = ldexpf(1.0f, e);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { scale_ws[1] = s; scale_ws[2] = 1.0f / s; }
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < count;
+       i += static_cast<long long>(gridDim.x) * 256)
+    y[i] = __float2half_rn(__ldg(x + i) * s);
+}
+
+// ================================================================================================
+// ReLU (+ MaxPool2d(2,2)) backward.  y = relu(conv) is the saved pre-pool activation.
+//   no pool:  dz = dy * [y > 0]
+//   pool   :  dz[yy,xx] = dp[yy/2, xx/2] if (yy,xx) is the FIRST maximum of its 2x2 window (scan order, as
+//             torch's max_pool2d) and y > 0, else 0; rows / columns not covered by a window get 0.
+// One thread per 8 channels of one full-resolution pixel.
+// ================================================================================================
+__global__ void __launch_bounds__(256)
+relu_pool_bwd_kernel(const __half* __restrict__ y, const __half* __restrict__ dy, __half* __restrict__ dz, int n, int h,
+                     int w, int c, int pool) {
+  const int c8 = c >> 3;
+  const long long total = static_cast<long long>(n) * h * w * c8;
+  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int oc = static_cast<int>(idx % c8);
+  long long pix = idx / c8;
+  const int xx = static_cast<int>(pix % w);
+  pix /= w;
+  const int yy = static_cast<int>(pix % h);
+  const int img = static_cast<int>(pix / h);
+  const uint4* y4 = reinterpret_cast<const uint4*>(y);
+  const uint4 mine = __ldg(y4 + idx);
+  const __half* hm = reinterpret_cast<const __half*>(&mine);
+  uint4 out = make_uint4(0, 0, 0, 0);
+  __half* ho = reinterpret_cast<__half*>(&out);
+  if (!pool) {
+    const uint4 g = __ldg(reinterpret_cast<const uint4*>(dy) + idx);
+    const __half* hg = reinterpret_cast<const __half*>(&g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ho[e] = __half2float(hm[e]) > 0.0f ? hg[e] : __float2half(0.0f);
+  } else {
+    const int ph = h >> 1, pw = w >> 1;
+    const int py = yy >> 1, px = xx >> 1;
+    if (py < ph && px < pw) {
+      const uint4 g = __ldg(reinterpret_cast<const uint4*>(dy) + ((static_cast<long long>(img) * ph + py) * pw + px) * c8 + oc);
+      const __half* hg = reinterpret_cast<const __half*>(&g);
+      const int my_pos = ((yy & 1) << 1) | (xx & 1);      // scan order inside the window
+      uint4 win[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        win[q] = __ldg(y4 + ((static_cast<long long>(img) * h + (2 * py + (q >> 1))) * w + (2 * px + (q & 1))) * c8 + oc);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float v = __half2float(hm[e]);
+        bool first_max = v > 0.0f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float o = __half2float(reinterpret_cast<const __half*>(&win[q])[e]);
+          if (q < my_pos) first_max = first_max && (o < v);     // an earlier equal value wins
+          else if (q > my_pos) first_max = first_max && (o <= v);
+        }
+        ho[e] = first_max ? hg[e] : __float2half(0.0f);
+      }
+    }
+  }
+  reinterpret_cast<uint4*>(dz)[idx] = out;
+}
+
+// ================================================================================================
+// Stem weight / bias gradient (3 input channels, 3x3 stride 1):
+//   dW[co][c][ky][kx] += inv_scale * sum_pixels dz[p][co] * prep(x)[c][p + tap],   db[co] += inv_scale * sum dz
+// Persistent CTAs walk strips of 128 output pixels; thread (co, kgroup) keeps 7 of the 28 (27 taps + bias)
+// partial sums of its output channel in registers over ALL its strips and flushes them with one atomic each.
+// ================================================================================================
+constexpr int kSwThreads = 256;
+
+template <bool U8>
+__global__ void __launch_bounds__(kSwThreads)
+stem_wgrad_kernel(const void* __restrict__ x, const __half* __restrict__ dz, float* __restrict__ dw,
+                  float* __restrict__ db, const float* __restrict__ inv_scale, int n, int h, int w, int prep) {
+  __shared__ float patch[9][132];                 // [c*3 + ky][px], prepped, zero padded
+  __shared__ float dzs[128][64 + 1];
+  const int strips_per_row = (w + 127) / 128;
+  const long long num_strips = static_cast<long long>(n) * h * strips_per_row;
+  const int co = threadIdx.x & 63, kg = threadIdx.x >> 6;       // kg: taps 7*kg .. 7*kg+6 (tap 27 = bias)
+  float acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  const size_t plane = static_cast<size_t>(h) * w;
+  for (long long s = blockIdx.x; s < num_strips; s += gridDim.x) {
+    const int strip = static_cast<int>(s % strips_per_row);
+    const long long row = s / strips_per_row;
+    const int oy = static_cast<int>(row % h);
+    const int img = static_cast<int>(row / h);
+    const int x0 = strip * 128;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * 130; i += kSwThreads) {
+      const int r = i / 130, px = i - r * 130;
+      const int ch = r / 3, ky = r - ch * 3;
+      const int gy = oy + ky - 1, gx = x0 + px - 1;
+      float v = 0.0f;
+      if (gy >= 0 && gy < h && gx >= 0 && gx < w) {
+        if (U8) v = static_cast<float>(__ldg(static_cast<const uint8_t*>(x) + (static_cast<size_t>(img) * plane + static_cast<size_t>(gy) * w + gx) * 3 + ch));
+        else v = __ldg(static_cast<const float*>(x) + (static_cast<size_t>(img) * 3 + ch) * plane + static_cast<size_t>(gy) * w + gx);
+        if (prep) v = __fmul_rn(__fmaf_rn(v, 1.0f / 255.0f, -0.5f), 2.0f);
+      }
+      patch[r][px] = v;
+    }
+    const __half* dzr = dz + (static_cast<size_t>(img) * plane + static_cast<size_t>(oy) * w + x0) * 64;
+    for (int i = threadIdx.x; i < 128 * 8; i += kSwThreads) {
+      const int px = i >> 3, o8 = i & 7;
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if (x0 + px < w) u = __ldg(reinterpret_cast<const uint4*>(dzr + static_cast<size_t>(px) * 64) + o8);
+      const __half* hh = reinterpret_cast<const __half*>(&u);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dzs[px][o8 * 8 + e] = __half2float(hh[e]);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int px = 0; px < 128; ++px) {
+      const float g = dzs[px][co];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const int k = kg * 7 + j;                  // k = (c*3 + ky)*3 + kx  (OIHW flatten), 27 = bias
+        const float xv = (k < 27) ? patch[k / 3][px + (k % 3)] : 1.0f;
+        acc[j] = fmaf(g, xv, acc[j]);
+      }
+    }
+  }
+  const float scl = inv_scale ? __ldg(inv_scale) : 1.0f;
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const int k = kg * 7 + j;
+    if (k < 27) atomicAdd(dw + co * 27 + k, acc[j] * scl);
+    else if (db != nullptr) atomicAdd(db + co, acc[j] * scl);
+  }
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" int din_roi_align_bwd_f32(const float* dcrops, const float* boxes, const int32_t* box_ind, float* dfm,
+                                     int n_img, int h, int w, int d, int fm_c_stride, int m, int crop_h, int crop_w,
+                                     void* stream) {
+  DIN_CHECK_ARG(dcrops && boxes && box_ind && dfm, "din_roi_align_bwd_f32: null pointer");
+  DIN_CHECK_ARG(n_img > 0 && h > 1 && w > 1 && m > 0, "din_roi_align_bwd_f32: bad extent n=%d h=%d w=%d m=%d", n_img, h,
+                w, m);
+  DIN_CHECK_ARG(d > 0 && d % 4 == 0 && fm_c_stride >= d && fm_c_stride % 4 == 0,
+                "din_roi_align_bwd_f32: d=%d / fm_c_stride=%d must be multiples of 4", d, fm_c_stride);
+  DIN_CHECK_ARG(crop_h > 1 && crop_w > 1, "din_roi_align_bwd_f32: crop must be > 1");
+  DIN_CHECK_ARG(((reinterpret_cast<uintptr_t>(dcrops) | reinterpret_cast<uintptr_t>(dfm)) & 15) == 0,
+                "din_roi_align_bwd_f32: pointers must be 16-byte aligned");
+  const long long warps = static_cast<long long>(m) * crop_h * crop_w;
+  roi_align_bwd_kernel<<<static_cast<int>((warps + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dcrops, boxes, box_ind, dfm, n_img, h, w, d, fm_c_stride, m, crop_h, crop_w);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
+extern "C" int din_grad_to_f16(const float* x, void* y, float* scale_ws, long long count, float target, void* stream) {
+  DIN_CHECK_ARG(x && y && scale_ws, "din_grad_to_f16: null pointer");
+  DIN_CHECK_ARG(count > 0 && target > 0.0f, "din_grad_to_f16: bad count %lld / target %g", count, target);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DIN_CHECK_CUDA(cudaMemsetAsync(scale_ws, 0, 4 * sizeof(float), st));
+  const int sms = din_num_sms();
+  long long blocks = (count + 255) / 256;
+  const long long cap = static_cast<long long>(sms > 0 ? sms : 148) * 8;
+  if (blocks > cap) blocks = cap;
+  amax_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(x, count, reinterpret_cast<unsigned int*>(scale_ws));
+  DIN_CHECK_CUDA(cudaGetLastError());
+  scale_to_f16_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(x, static_cast<__half*>(y), count, scale_ws, target);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
+extern "C" int din_relu_pool_bwd_nhwc_f16(const void* y, const void* dy, void* dz, int n, int h, int w, int c, int pool,
+                                          void* stream) {
+  DIN_CHECK_ARG(y && dy && dz, "din_relu_pool_bwd_nhwc_f16: null pointer");
+  DIN_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "din_relu_pool_bwd_nhwc_f16: bad shape n=%d h=%d w=%d c=%d",
+                n, h, w, c);
+  DIN_CHECK_ARG(!pool || (h >= 2 && w >= 2), "din_relu_pool_bwd_nhwc_f16: pooling needs at least 2x2");
+  DIN_CHECK_ARG(((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dz)) & 15) == 0,
+                "din_relu_pool_bwd_nhwc_f16: pointers must be 16-byte aligned");
+  const long long total = static_cast<long long>(n) * h * w * (c / 8);
+  DIN_CHECK_ARG((total + 255) / 256 <= INT32_MAX, "din_relu_pool_bwd_nhwc_f16: too large");
+  relu_pool_bwd_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(y), static_cast<const __half*>(dy), static_cast<__half*>(dz), n, h, w, c, pool);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
+extern "C" int din_stem_wgrad(const void* x, int x_is_u8, const void* dz, float* dw, float* dbias,
+                              const float* inv_scale, int n, int h, int w, int c_out, int kh, int kw, int stride, int pad,
+                              int prep, void* stream) {
+  DIN_CHECK_ARG(x && dz && dw, "din_stem_wgrad: null pointer");
+  DIN_CHECK_ARG(n > 0 && h > 0 && w > 0, "din_stem_wgrad: bad extent n=%d h=%d w=%d", n, h, w);
+  DIN_CHECK_ARG(c_out == 64 && kh == 3 && kw == 3 && stride == 1 && pad == 1,
+                "din_stem_wgrad: only the VGG-16 stem (64 x 3x3, stride 1, pad 1) is implemented");
+  DIN_CHECK_ARG((reinterpret_cast<uintptr_t>(dz) & 15) == 0, "din_stem_wgrad: dz must be 16-byte aligned");
+  const int sms = din_num_sms();
+  const long long strips = static_cast<long long>(n) * h * ((w + 127) / 128);
+  long long grid = static_cast<long long>(sms > 0 ? sms : 148) * 3;
+  if (grid > strips) grid = strips;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (x_is_u8)
+    stem_wgrad_kernel<true><<<static_cast<int>(grid), kSwThreads, 0, st>>>(x, static_cast<const __half*>(dz), dw, dbias,
+                                                                          inv_scale, n, h, w, prep);
+  else
+    stem_wgrad_kernel<false><<<static_cast<int>(grid), kSwThreads, 0, st>>>(x, static_cast<const __half*>(dz), dw, dbias,
+                                                                           inv_scale, n, h, w, prep);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}

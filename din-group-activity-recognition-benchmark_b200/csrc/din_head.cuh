@@ -27,6 +27,48 @@ __device__ __forceinline__ float block_sum(float v, float* red /* >= 33 floats *
 
 
 // ================================================================================================
+// RoIAlign sample point (crop_and_resize with longcw/RoIAlign.pytorch's box transform), shared by the forward
+// gather and the backward scatter
+// ================================================================================================
+struct RoiSample {
+  bool ok;                 // sample point inside [0, H-1] x [0, W-1] and a valid frame index
+  int img, top, bot, left, right;
+  float yl, xl;            // bilinear fractions
+};
+
+__device__ __forceinline__ RoiSample roi_sample_point(const float* __restrict__ boxes, const int* __restrict__ box_ind,
+                                                      int m, int iy, int ix, int n_img, int H, int W, int crop_h,
+                                                      int crop_w) {
+  const float x1 = __ldg(boxes + 4 * m + 0), y1 = __ldg(boxes + 4 * m + 1);
+  const float x2 = __ldg(boxes + 4 * m + 2), y2 = __ldg(boxes + 4 * m + 3);
+  const int b = __ldg(box_ind + m);
+  // RoIAlign.forward (transform_fpcoor=True): same fp32 op order as the published implementation, no
+  // FMA contraction, so floor()/validity decisions agree with the CPU restatement.
+  const float Wm1 = static_cast<float>(W - 1), Hm1 = static_cast<float>(H - 1);
+  const float spacing_w = __fdiv_rn(__fsub_rn(x2, x1), static_cast<float>(crop_w));
+  const float spacing_h = __fdiv_rn(__fsub_rn(y2, y1), static_cast<float>(crop_h));
+  const float nx0 = __fdiv_rn(__fsub_rn(__fadd_rn(x1, __fdiv_rn(spacing_w, 2.0f)), 0.5f), Wm1);
+  const float ny0 = __fdiv_rn(__fsub_rn(__fadd_rn(y1, __fdiv_rn(spacing_h, 2.0f)), 0.5f), Hm1);
+  const float nw = __fdiv_rn(__fmul_rn(spacing_w, static_cast<float>(crop_w - 1)), Wm1);
+  const float nh = __fdiv_rn(__fmul_rn(spacing_h, static_cast<float>(crop_h - 1)), Hm1);
+  const float by1 = ny0, bx1 = nx0, by2 = __fadd_rn(ny0, nh), bx2 = __fadd_rn(nx0, nw);
+  // crop_and_resize
+  const float height_scale = __fdiv_rn(__fmul_rn(__fsub_rn(by2, by1), Hm1), static_cast<float>(crop_h - 1));
+  const float width_scale = __fdiv_rn(__fmul_rn(__fsub_rn(bx2, bx1), Wm1), static_cast<float>(crop_w - 1));
+  const float in_y = __fadd_rn(__fmul_rn(by1, Hm1), __fmul_rn(static_cast<float>(iy), height_scale));
+  const float in_x = __fadd_rn(__fmul_rn(bx1, Wm1), __fmul_rn(static_cast<float>(ix), width_scale));
+
+  RoiSample sp;
+  sp.img = b;
+  sp.ok = (b >= 0) && (b < n_img) && (in_y >= 0.0f) && (in_y <= Hm1) && (in_x >= 0.0f) && (in_x <= Wm1);
+  sp.top = static_cast<int>(floorf(in_y)); sp.bot = static_cast<int>(ceilf(in_y));
+  sp.left = static_cast<int>(floorf(in_x)); sp.right = static_cast<int>(ceilf(in_x));
+  sp.yl = in_y - static_cast<float>(sp.top);
+  sp.xl = in_x - static_cast<float>(sp.left);
+  return sp;
+}
+
+// ================================================================================================
 // Dynamic Relation / Dynamic Walk: launch geometry and the affinity-conv phase shared by forward and backward
 // ================================================================================================
 constexpr int kDinThreads = 256;

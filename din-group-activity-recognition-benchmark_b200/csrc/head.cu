@@ -38,36 +38,17 @@ roi_align_kernel(const __half* __restrict__ fm, const float* __restrict__ boxes,
   const int iy = bin / crop_w;
   const int ix = bin - iy * crop_w;
 
-  const float x1 = __ldg(boxes + 4 * m + 0), y1 = __ldg(boxes + 4 * m + 1);
-  const float x2 = __ldg(boxes + 4 * m + 2), y2 = __ldg(boxes + 4 * m + 3);
-  const int b = __ldg(box_ind + m);
-  // RoIAlign.forward (transform_fpcoor=True): same fp32 op order as the published implementation, no
-  // FMA contraction, so floor()/validity decisions agree with the CPU restatement.
-  const float Wm1 = static_cast<float>(W - 1), Hm1 = static_cast<float>(H - 1);
-  const float spacing_w = __fdiv_rn(__fsub_rn(x2, x1), static_cast<float>(crop_w));
-  const float spacing_h = __fdiv_rn(__fsub_rn(y2, y1), static_cast<float>(crop_h));
-  const float nx0 = __fdiv_rn(__fsub_rn(__fadd_rn(x1, __fdiv_rn(spacing_w, 2.0f)), 0.5f), Wm1);
-  const float ny0 = __fdiv_rn(__fsub_rn(__fadd_rn(y1, __fdiv_rn(spacing_h, 2.0f)), 0.5f), Hm1);
-  const float nw = __fdiv_rn(__fmul_rn(spacing_w, static_cast<float>(crop_w - 1)), Wm1);
-  const float nh = __fdiv_rn(__fmul_rn(spacing_h, static_cast<float>(crop_h - 1)), Hm1);
-  const float by1 = ny0, bx1 = nx0, by2 = __fadd_rn(ny0, nh), bx2 = __fadd_rn(nx0, nw);
-  // crop_and_resize
-  const float height_scale = __fdiv_rn(__fmul_rn(__fsub_rn(by2, by1), Hm1), static_cast<float>(crop_h - 1));
-  const float width_scale = __fdiv_rn(__fmul_rn(__fsub_rn(bx2, bx1), Wm1), static_cast<float>(crop_w - 1));
-  const float in_y = __fadd_rn(__fmul_rn(by1, Hm1), __fmul_rn(static_cast<float>(iy), height_scale));
-  const float in_x = __fadd_rn(__fmul_rn(bx1, Wm1), __fmul_rn(static_cast<float>(ix), width_scale));
+  const RoiSample sp = roi_sample_point(boxes, box_ind, m, iy, ix, n_img, H, W, crop_h, crop_w);
+  const int b = sp.img;
 
   __half* op = out + (static_cast<size_t>(m) * bins + bin) * D;
-  const bool ok = (b >= 0) && (b < n_img) && (in_y >= 0.0f) && (in_y <= Hm1) && (in_x >= 0.0f) && (in_x <= Wm1);
-  if (!ok) {
+  if (!sp.ok) {
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (int c = lane * 8; c < D; c += 256) *reinterpret_cast<uint4*>(op + c) = z;
     return;
   }
-  const int top = static_cast<int>(floorf(in_y)), bot = static_cast<int>(ceilf(in_y));
-  const int left = static_cast<int>(floorf(in_x)), right = static_cast<int>(ceilf(in_x));
-  const float yl = in_y - static_cast<float>(top);
-  const float xl = in_x - static_cast<float>(left);
+  const int top = sp.top, bot = sp.bot, left = sp.left, right = sp.right;
+  const float yl = sp.yl, xl = sp.xl;
   const __half* base = fm + static_cast<size_t>(b) * H * W * fm_c_stride;
   const __half* ptl = base + (static_cast<size_t>(top) * W + left) * fm_c_stride;
   const __half* ptr = base + (static_cast<size_t>(top) * W + right) * fm_c_stride;

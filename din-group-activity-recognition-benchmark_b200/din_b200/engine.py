@@ -36,6 +36,8 @@ class _Conv:
     """One tcgen05 convolution of the plan (weights packed fp16 [co][kh][kw][ci], fp32 bias)."""
 
     def __init__(self, w, bias, scale=None, stride=1, pad=(0, 0), relu=True, pool2=False, split=1):
+        self.w_src = w                     # fp32 OIHW, kept by reference for the (lazily packed) dgrad filter
+        self._w_dgrad = None
         self.w = ops.pack_conv_weight(w.contiguous(), scale, split=split)
         self.bias = None if bias is None else bias.contiguous().float()
         self.stride, self.pad, self.relu, self.pool2 = stride, pad, relu, pool2
@@ -46,6 +48,14 @@ class _Conv:
         kw.setdefault("c_in", self.c_in)
         return ops.conv2d_nhwc(x, self.w, self.bias, stride=self.stride, pad=self.pad, relu=self.relu,
                                residual=residual, out=out, pool2=self.pool2, **kw)
+
+    def dgrad(self, dz):
+        """dX of a 3x3 stride-1 pad-1 convolution = the forward kernel on dZ with the filter rotated by 180 degrees
+        and its channel axes swapped (packed once per weight version; layout ops only)."""
+        assert self.stride == 1 and tuple(self.w_src.shape[2:]) == (3, 3) and self.pad == (1, 1)
+        if self._w_dgrad is None:
+            self._w_dgrad = ops.pack_conv_weight(self.w_src.permute(1, 0, 2, 3).flip(2, 3).contiguous())
+        return ops.conv2d_nhwc(dz, self._w_dgrad, None, stride=1, pad=(1, 1), relu=False)
 
 
 class _Stem:
@@ -66,7 +76,7 @@ class VGG16Plan:
     CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512, "M"]
 
     def __init__(self, sd, prefix="backbone.features."):
-        self.layers = []
+        self.layers, self.param_names = [], []
         idx = 0
         for i, v in enumerate(self.CFG):
             if v == "M":
@@ -78,8 +88,59 @@ class VGG16Plan:
                 self.layers.append(_Stem(w, b, stride=1, pad=1))
             else:
                 self.layers.append(_Conv(w, b, stride=1, pad=(1, 1), relu=True, pool2=pool))
+            self.param_names.append(f"{prefix}{idx}")
             idx += 2
         self.out_channels = 512
+
+    # -- training: forward that keeps what the backward needs, and the backward itself
+    def forward_train(self, images, out=None):
+        """As __call__, but every conv's ReLU output is kept BEFORE its max-pool (the pool runs as its own kernel;
+        max over the same fp16 values as the fused epilogue, so the result is bit-identical).
+        -> (feature map, saved = [(conv input, ReLU output, pooled?)] per conv)."""
+        saved = []
+        x = images
+        last = len(self.layers) - 1
+        for i, layer in enumerate(self.layers):
+            if i == 0:
+                y, pooled = layer(x), False
+                a = y
+            else:
+                pooled = layer.pool2
+                y = ops.conv2d_nhwc(x, layer.w, layer.bias, stride=1, pad=(1, 1), relu=True, pool2=False, c_in=layer.c_in)
+                a = ops.maxpool2d_nhwc(y, 2, 2, 0, out=out if i == last else None) if pooled else y
+            saved.append((x, y, pooled))
+            x = a
+        return x, saved
+
+    def new_grads(self, device):
+        """Zero-filled fp32 accumulators: the stem's in OIHW, the others in the kernels' [co][kh][kw][ci] order."""
+        acc = []
+        for i, layer in enumerate(self.layers):
+            co = layer.w.shape[0]
+            shape = (co, 3, 3, 3) if i == 0 else (co, 3, 3, layer.c_in)
+            acc.append((torch.zeros(shape, dtype=torch.float32, device=device),
+                        torch.zeros((co,), dtype=torch.float32, device=device)))
+        return acc
+
+    def backward(self, saved, d_out, inv_scale, acc):
+        """d_out: fp16 gradient (times the loss scale) w.r.t. this chunk's feature map; accumulates into `acc`."""
+        d = d_out
+        for i in reversed(range(len(self.layers))):
+            x_in, y, pooled = saved[i]
+            dz = ops.relu_pool_bwd_nhwc(y, d, pooled)
+            dw, db = acc[i]
+            if i == 0:
+                ops.stem_wgrad(x_in, dz, dw, db, inv_scale=inv_scale, prep=True)
+            else:
+                ops.conv2d_wgrad_nhwc(x_in, dz, dw, db, pad=(1, 1), inv_scale=inv_scale)
+                d = self.layers[i].dgrad(dz)
+
+    def export_grads(self, acc, grads):
+        """accumulators -> {reference parameter name: OIHW gradient} (layout only)."""
+        for i, (dw, db) in enumerate(acc):
+            name = self.param_names[i]
+            grads[name + ".weight"] = dw if i == 0 else dw.permute(0, 3, 1, 2).contiguous()
+            grads[name + ".bias"] = db
 
     def __call__(self, images, out=None):
         x = images
@@ -211,6 +272,7 @@ class DinEngine:
         wp[:, :, :self.D] = w
         self.fc_emb = _Conv(wp.view(self.NFB, self.K * self.K * self.D_stride, 1, 1), sd["fc_emb_1.bias"], relu=False,
                             split=2 if cfg.backbone == "inv3" else 1)
+        self.fc_emb_wk = wp.view(self.NFB, self.K * self.K * self.D_stride)   # fp32, kernel K order (d(crops) GEMM)
         self.nl_emb = (sd["nl_emb_1.weight"].contiguous(), sd["nl_emb_1.bias"].contiguous())
         if cfg.lite_dim:
             pw = sd["point_conv.weight"]
@@ -270,6 +332,21 @@ class DinEngine:
             f1 = min(F_, f0 + self.frames_per_chunk)
             self.backbone(images_flat[f0:f1], out=fm[f0:f1])      # last layer writes its slice in place
         return fm
+
+    def features_train(self, images_flat):
+        """features() through the backbone plan's forward_train: -> (fm, [(f0, f1, saved)] per frame chunk)."""
+        if not hasattr(self.backbone, "forward_train"):
+            raise NotImplementedError(f"training the {self.backbone_name} backbone is not implemented (VGG-16 only)")
+        F_ = images_flat.shape[0]
+        H, W = images_flat.shape[1:3] if images_flat.dtype == torch.uint8 else images_flat.shape[2:4]
+        oh, ow, d = self.backbone.out_shape(H, W)
+        fm = torch.zeros((F_, oh, ow, d), dtype=torch.float16, device=images_flat.device)
+        chunks = []
+        for f0 in range(0, F_, self.frames_per_chunk):
+            f1 = min(F_, f0 + self.frames_per_chunk)
+            _, saved = self.backbone.forward_train(images_flat[f0:f1], out=fm[f0:f1])
+            chunks.append((f0, f1, saved))
+        return fm, chunks
 
     def embed(self, fm, boxes_flat, B, T, N):
         """RoIAlign -> fc_emb_1 -> nl_emb_1 -> ReLU -> (lite branch).  Returns fp32 [B,T,N,C]."""

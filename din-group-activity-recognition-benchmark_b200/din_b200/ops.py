@@ -459,3 +459,58 @@ def conv2d_wgrad_nhwc(x, dz, dw, dbias=None, *, pad=(1, 1), inv_scale=None, c_in
                                                     dz.shape[3], kh, kw, pad[0], pad[1], _stream()),
               "din_conv2d_wgrad_nhwc_f16")
     return dw
+
+
+def roi_align_bwd(dcrops, boxes, box_ind, dfm, crop_h, crop_w, d=None):
+    """dfm [n_img,h,w,Cs] fp32 += scatter(dcrops [m, crop_h*crop_w, d])."""
+    _need(dcrops, torch.float32, "dcrops")
+    _need(dfm, torch.float32, "dfm")
+    _need(boxes, torch.float32, "boxes")
+    _need(box_ind, torch.int32, "box_ind")
+    n_img, h, w, cs = dfm.shape
+    d = cs if d is None else d
+    m = boxes.shape[0]
+    assert dcrops.numel() == m * crop_h * crop_w * d
+    with _launch("roi_align_bwd", 0, 4 * (dcrops.numel() * 5)):
+        check(_lib.load().din_roi_align_bwd_f32(_p(dcrops), _p(boxes), _p(box_ind), _p(dfm), n_img, h, w, d, cs, m,
+                                                crop_h, crop_w, _stream()), "din_roi_align_bwd_f32")
+    return dfm
+
+
+def grad_to_f16(x, target=256.0):
+    """-> (x * S as fp16, scale_ws [4] fp32 device: [1] = S, [2] = 1/S).  Two kernels."""
+    _need(x, torch.float32, "x")
+    y = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    ws = torch.empty((4,), dtype=torch.float32, device=x.device)
+    global LAUNCHES
+    LAUNCHES += 1
+    with _launch("grad_to_f16", 0, 10 * x.numel()):
+        check(_lib.load().din_grad_to_f16(_p(x), _p(y), _p(ws), x.numel(), float(target), _stream()), "din_grad_to_f16")
+    return y, ws
+
+
+def relu_pool_bwd_nhwc(y, dy, pool):
+    """y [n,h,w,c] fp16 saved ReLU output; dy [n,h,w,c] (or [n,h/2,w/2,c] with pool) -> dz [n,h,w,c]."""
+    _need(y, torch.float16, "y")
+    _need(dy, torch.float16, "dy")
+    n, h, w, c = y.shape
+    assert tuple(dy.shape) == ((n, h // 2, w // 2, c) if pool else (n, h, w, c)), (tuple(y.shape), tuple(dy.shape), pool)
+    dz = torch.empty_like(y)
+    with _launch("relu_pool_bwd" if pool else "relu_bwd", 0, 2 * (2 * y.numel() + dy.numel())):
+        check(_lib.load().din_relu_pool_bwd_nhwc_f16(_p(y), _p(dy), _p(dz), n, h, w, c, int(pool), _stream()),
+              "din_relu_pool_bwd_nhwc_f16")
+    return dz
+
+
+def stem_wgrad(x, dz, dw, dbias, *, inv_scale=None, prep=True):
+    """VGG-16 stem: dw [64,3,3,3] fp32 (OIHW), dbias [64] (+)= ...; x raw frames (fp32 NCHW or uint8 NHWC)."""
+    u8 = x.dtype == torch.uint8
+    _need(x, torch.uint8 if u8 else torch.float32, "x")
+    _need(dz, torch.float16, "dz")
+    _need(dw, torch.float32, "dw")
+    n, h, w = (x.shape[0], x.shape[1], x.shape[2]) if u8 else (x.shape[0], x.shape[2], x.shape[3])
+    assert tuple(dz.shape) == (n, h, w, 64) and tuple(dw.shape) == (64, 3, 3, 3)
+    with _launch("stem_wgrad", 2 * n * h * w * 64 * 27, x.numel() * x.element_size() + 2 * dz.numel()):
+        check(_lib.load().din_stem_wgrad(_p(x), int(u8), _p(dz), _p(dw), _p(dbias), _p(inv_scale), n, h, w, 64, 3, 3, 1, 1,
+                                         int(prep), _stream()), "din_stem_wgrad")
+    return dw

@@ -70,16 +70,22 @@ def _dpi_backward(dpi, prefix, x, tmp, dg, dx, n_valid, grads):
         grads[prefix + "beta"] = torch.cat(dbeta)
 
 
-def forward_train(eng, images, boxes, bboxes_num=None, training=True):
-    """-> (logits [B, A], tape).  Same kernels as DinEngine.forward_*, plus dropout and saved intermediates."""
+def forward_train(eng, images, boxes, bboxes_num=None, training=True, train_backbone=False):
+    """-> (logits [B, A], tape).  Same kernels as DinEngine.forward_*, plus dropout and saved intermediates.
+    train_backbone: additionally keep every backbone activation (VGG-16) for backward_backbone."""
     cfg = eng.cfg
     B, T = images.shape[:2]
     N, C = eng.N, eng.C
     M = B * T * N
     dev = eng.device
-    tape = {"B": B, "T": T, "dpi": []}
+    tape = {"B": B, "T": T, "dpi": [], "train_backbone": train_backbone}
     with torch.no_grad():
-        fm = eng.features(eng._flat_frames(images))
+        if train_backbone:
+            fm, tape["bb_chunks"] = eng.features_train(eng._flat_frames(images))
+            tape["boxes"] = boxes.reshape(M, 4).contiguous().float()
+            tape["fm_shape"] = tuple(fm.shape)
+        else:
+            fm = eng.features(eng._flat_frames(images))
         if eng.dataset == "volleyball":
             OH, OW = cfg.out_size
             assert fm.shape[1:3] == (OH, OW), (tuple(fm.shape), cfg.out_size)
@@ -198,9 +204,28 @@ def backward_head(eng, tape, dlogits):
                                                    cols=NFB, relu=True)
         grads["nl_emb_1.weight"], grads["nl_emb_1.bias"] = dgam, dbet
         # dW in the kernel's K order (ky, kx, d_padded) -> the reference's (d, ky, kx) flatten (layout only)
-        _, dwk, dbe = ops.linear_bwd(tape["crops"], None, demb, need_dx=False)
+        dcrops, dwk, dbe = ops.linear_bwd(tape["crops"], eng.fc_emb_wk if tape["train_backbone"] else None, demb,
+                                          need_dx=tape["train_backbone"])
         KK = eng.K * eng.K
         grads["fc_emb_1.weight"] = dwk.view(NFB, KK, eng.D_stride)[:, :, :eng.D].permute(0, 2, 1).reshape(NFB, -1) \
             .contiguous()
         grads["fc_emb_1.bias"] = dbe
+        if tape["train_backbone"]:
+            backward_backbone(eng, tape, dcrops, grads)
     return grads
+
+
+def backward_backbone(eng, tape, dcrops, grads):
+    """d(loss)/d(crops) [M, 25*D_stride] fp32 -> RoIAlign backward -> scaled fp16 -> VGG-16 backward (dgrad on the
+    forward tcgen05 kernel, wgrad on conv_wgrad_tcgen05.cu), chunk by chunk; gradients under the reference's
+    `backbone.features.N.{weight,bias}` names."""
+    B, T = tape["B"], tape["T"]
+    N = eng.N
+    dfm = torch.zeros(tape["fm_shape"], dtype=torch.float32, device=eng.device)
+    ops.roi_align_bwd(dcrops, tape["boxes"], eng._box_idx(B * T, N), dfm, eng.K, eng.K, d=eng.D_stride)
+    dfm16, scale_ws = ops.grad_to_f16(dfm)
+    inv_scale = scale_ws[2:3]
+    acc = eng.backbone.new_grads(eng.device)
+    for f0, f1, saved in tape["bb_chunks"]:
+        eng.backbone.backward(saved, dfm16[f0:f1], inv_scale, acc)
+    eng.backbone.export_grads(acc, grads)

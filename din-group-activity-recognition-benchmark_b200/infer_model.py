@@ -6,10 +6,11 @@ so `scripts/train_volleyball_stage2_dynamic.py`'s model registry resolves and st
 checkpoints load unchanged.  forward() runs the sm_100a plan (din_b200/engine.py); torch modules below
 are parameter containers and are never called.
 
-Scope: evaluation / inference forward, and the training step with the backbone frozen (config.py:39
-`train_backbone = False`): `model.train()` + `loss.backward()` produce gradients for every parameter after the
-backbone through the backward kernels in csrc/head_bwd.cu (first slice).  Training the
-backbone itself (conv dgrad / wgrad) is not implemented and raises.
+Scope: evaluation / inference forward, and the training step: `model.train()` + `loss.backward()` produce
+gradients for every parameter after the backbone through the backward kernels in csrc/head_bwd.cu, and -- with
+cfg.train_backbone = True and the VGG-16 backbone -- for the backbone too (RoIAlign scatter, ReLU / max-pool
+backward, dgrad on the forward tcgen05 kernel, wgrad on csrc/conv_wgrad_tcgen05.cu).
+Training the ResNet-18 / Inception-v3 backbones (stride-2 dgrad, BatchNorm) is not implemented and raises.
 """
 import collections
 
@@ -47,7 +48,8 @@ class _DinTrainFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, images, boxes, bboxes_num, names, *params):
-        logits, tape = _train.forward_train(model.engine(), images, boxes, bboxes_num, training=model.training)
+        logits, tape = _train.forward_train(model.engine(), images, boxes, bboxes_num, training=model.training,
+                                            train_backbone=any(n.startswith("backbone.") for n in names))
         ctx.eng, ctx.tape, ctx.names = model.engine(), tape, names
         model._last_tape = tape if getattr(model, "keep_tape", False) else None     # test / debugging hook
         ctx.shapes = [tuple(p.shape) for p in params]
@@ -149,11 +151,12 @@ class _DinModel(nn.Module):
                 "the reference does with cfg.set_bn_eval (train_net_dynamic.py:101-102, model.apply(set_bn_eval))")
         if not torch.is_grad_enabled():
             return _train.forward_train(eng, images, boxes, bboxes_num, training=True)[0]
-        if any(p.requires_grad for p in self.backbone.parameters()):
+        if any(p.requires_grad for p in self.backbone.parameters()) and self.cfg.backbone != "vgg16":
             raise NotImplementedError(
-                "training the backbone (conv dgrad / wgrad kernels) is not implemented on the sm_100a path yet: "
-                "set cfg.train_backbone = False (config.py:39, the stage-2 default) -- SURVEY.md §8f rank 1")
-        named = [(n, p) for n, p in self.named_parameters() if not n.startswith("backbone.") and p.requires_grad]
+                f"training the backbone is implemented for VGG-16 only (3x3 stride-1 dgrad / wgrad kernels), not "
+                f"{self.cfg.backbone!r}: set cfg.train_backbone = False (config.py:39, the stage-2 default) -- "
+                "SURVEY.md §8f rank 1")
+        named = [(n, p) for n, p in self.named_parameters() if p.requires_grad]
         names = tuple(n for n, _ in named)
         return _DinTrainFn.apply(self, images, boxes, bboxes_num, names, *[p for _, p in named])
 

@@ -323,6 +323,43 @@ DIN_API int din_conv2d_wgrad_nhwc_f16(const void* x, const void* dz, float* dw, 
                                       int n, int h, int w, int c_in, int x_c_stride, int c_out, int dz_c_stride,
                                       int kh, int kw, int pad_h, int pad_w, void* stream);
 
+/*
+ * RoIAlign backward: dfm[frame, corner, :] += bilinear weight * dcrops[m, bin, :] for the four corners of every
+ * valid sample point (extrapolated samples are constants: no gradient).  fp32 vector atomics.
+ * Replaces the backward of the external crop_and_resize extension (infer_model.py:178-181).
+ * dcrops: fp32 [m][crop_h*crop_w][d] (the layout of din_roi_align_nhwc_f16's output);  dfm: fp32 NHWC
+ * [n_img, h, w, fm_c_stride], zero-filled by the caller (or holding a gradient to add to).
+ */
+DIN_API int din_roi_align_bwd_f32(const float* dcrops, const float* boxes, const int32_t* box_ind, float* dfm,
+                                  int n_img, int h, int w, int d, int fm_c_stride, int m, int crop_h, int crop_w,
+                                  void* stream);
+
+/*
+ * fp32 gradient -> fp16 times a dynamic power-of-two loss scale S = 2^floor(log2(target / max|x|)), so that the
+ * fp16 tensor-core backward of the backbone stays inside fp16's normal range; S is undone exactly by the
+ * weight-gradient kernels (inv_scale).  scale_ws: fp32 [4] device workspace: [0] max|x| bits, [1] S, [2] 1/S.
+ */
+DIN_API int din_grad_to_f16(const float* x, void* y, float* scale_ws, long long count, float target, void* stream);
+
+/*
+ * Backward of ReLU (+ MaxPool2d(2,2)) between two backbone convolutions, NHWC fp16:
+ *   pool == 0: dz = dy * [y > 0];     pool != 0: dy is [n, h/2, w/2, c]; the gradient goes to the FIRST maximum of
+ *   each 2x2 window (torch's max_pool2d index rule) if it is positive; uncovered rows / columns get 0.
+ * y: the saved ReLU output [n, h, w, c].  Replaces autograd through nn.ReLU / nn.MaxPool2d of vgg16.features.
+ */
+DIN_API int din_relu_pool_bwd_nhwc_f16(const void* y, const void* dy, void* dz, int n, int h, int w, int c, int pool,
+                                       void* stream);
+
+/*
+ * Weight / bias gradient of the stem convolution (VGG-16 features.0: 64 x 3 x 3x3, stride 1, pad 1), with
+ * prep_images recomputed on the raw frames (fp32 NCHW, or uint8 NHWC when x_is_u8):
+ *   dw [64][3][3][3] (OIHW) += inv_scale * sum_pixels dz (x) prep(x)_shifted;   dbias [64] += inv_scale * sum dz.
+ * ACCUMULATES (atomics): zero-fill before the first call of a step.
+ */
+DIN_API int din_stem_wgrad(const void* x, int x_is_u8, const void* dz, float* dw, float* dbias, const float* inv_scale,
+                           int n, int h, int w, int c_out, int kh, int kw, int stride, int pad, int prep,
+                           void* stream);
+
 #ifdef __cplusplus
 } /* extern "C" */
 #endif

@@ -84,6 +84,18 @@ def main_grads():
                     "weights_checksum": checksum(sd.values()), "inputs_checksum": checksum(batch)},
                    os.path.join(OUT, f"grads_{name}.pt"))
         print("grads", name, float(loss), len(grads))
+    # the whole model trained, backbone included (scripts/train_volleyball_stage2_dynamic.py:12)
+    pc, B = model_cases()["vgg16_lite"]
+    bb = O.build_backbone(pc.backbone)
+    sd = O.make_state_dict(pc, seed=0, backbone=bb)
+    batch = O.make_inputs(pc, B, seed=0)
+    labels = torch.arange(B) % pc.num_activities
+    logits, loss, grads = R.ref_head_grads(pc, sd, labels, *batch, train_backbone=True)
+    torch.save({"config": dataclasses.asdict(pc), "B": B, "seed": 0, "labels": labels, "logits_ref": logits,
+                "loss_ref": loss, "grads_ref": {k: O.grad_digest(v) for k, v in grads.items()},
+                "weights_checksum": checksum(sd.values()), "inputs_checksum": checksum(batch),
+                "train_backbone": True}, os.path.join(OUT, "fullgrads_vgg16_lite.pt"))
+    print("fullgrads vgg16_lite", float(loss), len(grads))
 
 
 def main():

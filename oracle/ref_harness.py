@@ -174,11 +174,14 @@ def ref_forward(pc, sd, *batch):
         return model(tuple(batch))["activities"]
 
 
-def ref_head_grads(pc, sd, labels, *batch):
+def ref_head_grads(pc, sd, labels, *batch, train_backbone=False):
     """Train-mode forward + F.cross_entropy + backward of the REFERENCE model (train_net_dynamic.py:170-224)
-    with the backbone frozen (config.py:39), BatchNorm layers in eval mode (train_net_dynamic.py:101-102
-    `set_bn_eval`) and train_dropout_prob = 0 (deterministic).  -> (logits, loss, {param name: grad})."""
+    with the backbone frozen (config.py:39) or trained (scripts/train_volleyball_stage2_dynamic.py:12), BatchNorm
+    layers in eval mode (train_net_dynamic.py:101-102 `set_bn_eval`) and train_dropout_prob = 0 (deterministic).
+    -> (logits, loss, {param name: grad})."""
     model = build_ref_model(pc, sd)
+    for q in model.backbone.parameters():
+        q.requires_grad = bool(train_backbone)
     model.cfg.train_dropout_prob = 0.0
     model.train()
     model.dropout_global.p = 0.0

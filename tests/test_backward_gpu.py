@@ -376,10 +376,10 @@ def test_training_step_matches_reference_fixture(cuda, path):
         smp = (flat[d["idx"]].float() - d["samples"]).abs().max().item()
         print(f"[fixture] {k:45s} l2 {l2:.4e} vs {d['l2']:.4e}   samples max|Δ| {smp:.2e} (max|ref| {d['max_abs']:.2e})")
         assert abs(l2 - d["l2"]) <= FULL_TOL * max(d["l2"], 1e-30), (k, l2, d["l2"])
-        # a flipped ReLU decision moves a single element by its full value: require 90 % of the sampled elements
-        # within 2e-2 * max|ref| rather than all of them
+        # a flipped ReLU decision moves a single element by its full value: require 85 % of the sampled elements
+        # within 2e-2 * max|ref| rather than all of them (the smallest tensors have 9 elements)
         near = ((flat[d["idx"]].float() - d["samples"]).abs() <= 2e-2 * max(d["max_abs"], 1e-30)).float().mean().item()
-        assert near >= 0.9, (k, near, smp, d["max_abs"])
+        assert near >= 0.85, (k, near, smp, d["max_abs"])
 
 
 def test_optimizer_loop_and_modes(cuda):
@@ -409,14 +409,63 @@ def test_optimizer_loop_and_modes(cuda):
     model.eval()
     with torch.no_grad():
         assert torch.isfinite(model(batch)["activities"]).all()
-    # backbone training is not implemented: loud error, no silent fallback
-    model.train()
-    for q in model.backbone.parameters():
-        q.requires_grad = True
-    with pytest.raises(NotImplementedError, match="training the backbone"):
-        model(batch)
+    # ResNet-18: training the backbone / batch-statistics BatchNorm are not implemented: loud errors
     pc2 = _pc("res18", (96, 160), num_frames=3, num_boxes=4)
     m2, _ = _model_and_cfg(cuda, pc2, O.make_state_dict(pc2, seed=0), 0.3)
+    for q in m2.backbone.parameters():
+        q.requires_grad = True
+    with pytest.raises(NotImplementedError, match="training the backbone"):
+        m2(batch)
     m2.train()                                        # BatchNorm back to batch statistics
     with pytest.raises(NotImplementedError, match="BatchNorm"):
         m2(batch)
+
+
+def test_full_training_step_with_backbone(cuda):
+    """cfg.train_backbone = True on VGG-16 (scripts/train_volleyball_stage2_dynamic.py:12): gradients of all 43
+    parameter tensors vs autograd over the oracle, and vs the REFERENCE model's gradients (fixture).
+    The backbone's backward runs on fp16 tensor-core operands (dynamic loss scale): relative L2 per tensor."""
+    import din_oracle as O
+    from din_b200 import metrics
+    from test_oracle_cpu import _pc_from
+    fx = torch.load(os.path.join(GOLDEN, "fullgrads_vgg16_lite.pt"))
+    pc = _pc_from(fx["config"])
+    bb = O.build_backbone(pc.backbone)
+    sd = O.make_state_dict(pc, seed=fx["seed"], backbone=bb)
+    O.load_backbone(bb, sd)
+    bb.eval()
+    batch = O.make_inputs(pc, fx["B"], seed=fx["seed"])
+    labels = fx["labels"]
+    model, cfg = _model_and_cfg(cuda, pc, sd, 0.0)
+    for q in model.backbone.parameters():
+        q.requires_grad = True
+    out = model(tuple(t.to(cuda) for t in batch))["activities"]
+    loss = metrics.cross_entropy(out, labels.to(cuda))
+    loss.backward()
+    torch.cuda.synchronize()
+    got = {n: q.grad for n, q in model.named_parameters() if q.grad is not None}
+    ref_logits, ref_loss, ref_grads = O.head_grads(bb, sd, pc, labels, *batch, train_backbone=True)
+    assert set(got) == set(ref_grads) == set(fx["grads_ref"]), set(got) ^ set(ref_grads)
+    worst = 0.0
+    for k in sorted(ref_grads):
+        r = _rel_l2(got[k], ref_grads[k])
+        l2 = float(got[k].double().norm())
+        worst = max(worst, r)
+        print(f"[full step] {k:45s} rel-L2 {r:.2e}  |ref| {float(ref_grads[k].norm()):.3e}  fixture l2 {fx['grads_ref'][k]['l2']:.3e}")
+        assert abs(l2 - fx["grads_ref"][k]["l2"]) <= 1e-2 * fx["grads_ref"][k]["l2"], (k, l2)   # norms: 1 %
+    print(f"[full step] loss {loss.item():.6f} vs {ref_loss.item():.6f}, worst rel-L2 {worst:.2e}")
+    assert abs(loss.item() - ref_loss.item()) <= 2e-3 * max(1.0, abs(ref_loss.item()))
+    assert worst <= BB_TOL, worst
+    # one optimizer step over everything, then a second forward (weights repacked)
+    opt = torch.optim.Adam([q for q in model.parameters() if q.requires_grad], lr=1e-4)
+    opt.step()
+    out2 = model(tuple(t.to(cuda) for t in batch))["activities"]
+    assert torch.isfinite(out2).all() and not torch.equal(out2, out)
+
+
+# Relative L2 per gradient tensor with the backbone trained.  Every layer's fp16 forward flips the ReLU / max-pool
+# decision of the ~0.1 % of units nearest a tie, and a flipped unit reroutes its whole gradient, so the error grows
+# like sqrt(#layers passed): measured 2.6e-2 at features.28 (last conv), 3.7e-2 at features.19, 7e-2 at
+# features.7, 1.3e-1 at features.0 -- while every tensor's NORM agrees with the reference's to 3-4 digits and each
+# kernel on the way is exact or 1e-4-tight in isolation (tests/test_conv_bwd_gpu.py).
+BB_TOL = 2e-1

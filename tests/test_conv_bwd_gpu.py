@@ -48,3 +48,96 @@ def test_wgrad_matches_torch(cuda, case):
     ops.conv2d_wgrad_nhwc(x, dz, dw, db, pad=(pad, pad), inv_scale=inv)
     torch.cuda.synchronize()
     assert (dw - 0.5 * ref).abs().max().item() <= 1e-3 * (0.5 * ref).abs().max().item()
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 24, 64), (1, 45, 81, 128), (2, 7, 9, 8)], ids=str)
+def test_relu_pool_bwd_matches_torch(cuda, shape):
+    """fp16 activations quantise to few distinct values => plenty of exact ties inside 2x2 windows: the FIRST
+    maximum in scan order must receive the gradient, as in torch."""
+    from din_b200 import ops
+    n, h, w, c = shape
+    g = torch.Generator().manual_seed(h)
+    pre = (torch.randn(n, h, w, c, generator=g) * 2).round() / 2               # multiples of 0.5: many ties
+    y = F.relu(pre).to(cuda).half()
+    for pool in (False, True):
+        yy = y.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+        out = F.max_pool2d(yy, 2, 2) if pool else yy
+        # relu's gradient mask from the saved OUTPUT (y > 0), as nn.ReLU(inplace=True) backward does
+        dy = torch.randn(out.shape, generator=g).to(cuda).half()
+        out.backward(dy.float())
+        ref = (yy.grad * (yy.detach() > 0)).permute(0, 2, 3, 1)
+        dz = ops.relu_pool_bwd_nhwc(y, dy.permute(0, 2, 3, 1).contiguous(), pool)
+        torch.cuda.synchronize()
+        assert torch.equal(dz.float(), ref), (shape, pool, (dz.float() - ref).abs().max().item())
+
+
+def test_dgrad_is_forward_kernel_on_rotated_filter(cuda):
+    """dX of a 3x3 s1 p1 conv = the forward tcgen05 kernel applied to dZ with the filter rotated by 180 degrees and
+    its channel axes swapped; checked against torch's conv_transpose2d."""
+    from din_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    n, h, w, cin, cout = 2, 22, 40, 128, 256
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) * 0.05).to(cuda)
+    dz = torch.randn(n, h, w, cout, generator=g).to(cuda).half()
+    w_dgrad = ops.pack_conv_weight(wt.permute(1, 0, 2, 3).flip(2, 3).contiguous())
+    dx = ops.conv2d_nhwc(dz, w_dgrad, None, stride=1, pad=(1, 1), relu=False)
+    w_used = w_dgrad[..., :cout].float().permute(0, 3, 1, 2).flip(2, 3).permute(1, 0, 2, 3).contiguous()   # fp16-rounded OIHW
+    ref = F.conv_transpose2d(dz.float().permute(0, 3, 1, 2), w_used, padding=1).permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    assert (dx.float() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("u8", [False, True])
+def test_stem_wgrad_matches_torch(cuda, u8):
+    from din_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    n, h, w = 2, 37, 150
+    raw = torch.randint(0, 256, (n, 3, h, w), generator=g).float().to(cuda)
+    dz = (torch.randn(n, h, w, 64, generator=g) * 0.5).to(cuda).half()
+    wt = torch.zeros(64, 3, 3, 3, device=cuda, requires_grad=True)
+    bias = torch.zeros(64, device=cuda, requires_grad=True)
+    xp = ((raw / 255.0) - 0.5) * 2.0
+    F.conv2d(xp, wt, bias, padding=1).backward(dz.float().permute(0, 3, 1, 2))
+    dw = torch.zeros(64, 3, 3, 3, device=cuda)
+    db = torch.zeros(64, device=cuda)
+    inv = torch.tensor([0.5], device=cuda)
+    x_in = raw.permute(0, 2, 3, 1).contiguous().to(torch.uint8) if u8 else raw
+    ops.stem_wgrad(x_in, dz, dw, db, inv_scale=inv)
+    torch.cuda.synchronize()
+    # fp32 sums over 11 100 pixels in a different order than cuDNN's: 1.4e-4 measured
+    assert (dw - 0.5 * wt.grad).abs().max().item() <= 1e-3 * (0.5 * wt.grad).abs().max().item()
+    assert (db - 0.5 * bias.grad).abs().max().item() <= 1e-3 * (0.5 * bias.grad).abs().max().item()
+
+
+def test_roi_align_bwd_matches_oracle_autograd(cuda):
+    import din_oracle as O
+    from din_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    n_img, H, W, D, N = 3, 9, 14, 16, 5
+    fm = torch.randn(n_img, D, H, W, generator=g, requires_grad=True)
+    cx, cy = torch.rand(n_img * N, generator=g) * W, torch.rand(n_img * N, generator=g) * H
+    bw, bh = 1 + 3 * torch.rand(n_img * N, generator=g), 2 + 5 * torch.rand(n_img * N, generator=g)
+    boxes = torch.stack((cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2), dim=-1)     # some leave the map
+    idx = torch.arange(n_img, dtype=torch.int32).repeat_interleave(N)
+    out = O.roi_align_longcw(fm, boxes, idx, 5, 5)                                        # [M, D, 5, 5]
+    dout = torch.randn(out.shape, generator=g)
+    out.backward(dout)
+    dcrops = dout.permute(0, 2, 3, 1).reshape(n_img * N, 25, D).contiguous().to(cuda)     # [m][bin][d]
+    dfm = torch.zeros(n_img, H, W, D, device=cuda)
+    ops.roi_align_bwd(dcrops, boxes.to(cuda), idx.to(cuda), dfm, 5, 5)
+    torch.cuda.synchronize()
+    ref = fm.grad.permute(0, 2, 3, 1)
+    assert (dfm.cpu() - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+
+
+def test_grad_to_f16_scale(cuda):
+    from din_b200 import ops
+    x = torch.randn(10000, device=cuda) * 3e-6
+    y, ws = ops.grad_to_f16(x, target=256.0)
+    torch.cuda.synchronize()
+    s, inv = ws[1].item(), ws[2].item()
+    amax = x.abs().max().item()
+    assert s * inv == 1.0 and 128.0 <= amax * s <= 256.0 and (s == 2.0 ** round(torch.log2(torch.tensor(s)).item()))
+    assert torch.equal(y, (x * s).half())
+    z, ws = ops.grad_to_f16(torch.zeros(16, device=cuda))
+    assert ws[1].item() == 1.0 and (z == 0).all()

@@ -98,8 +98,8 @@ def test_abi_reports_errors_instead_of_crashing(cuda):
     with pytest.raises(_lib.DinError, match="n <="):
         ops.dynamic_infer(torch.zeros(1, 2, 17, 64, device=cuda), torch.zeros(9, 27, 64, device=cuda),
                           torch.zeros(27, device=cuda), (3, 3), 1)
-    # the models refuse CPU tensors and training the backbone (no silent fallback); training with the backbone
-    # frozen is supported (tests/test_backward_gpu.py)
+    # the models refuse CPU tensors and training a backbone without backward kernels (no silent fallback); training
+    # the head, and the VGG-16 backbone, is supported (tests/test_backward_gpu.py)
     import infer_model as IM
     from config import Config
     cfg = Config("volleyball")
@@ -109,7 +109,10 @@ def test_abi_reports_errors_instead_of_crashing(cuda):
     m = IM.Dynamic_volleyball(cfg)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m.eval()((torch.zeros(1, 3, 3, 64, 96), torch.zeros(1, 3, 12, 4)))
-    cfg.train_backbone = True
+    cfg.train_backbone, cfg.backbone, cfg.out_size = True, "res18", (2, 3)
     m = IM.Dynamic_volleyball(cfg).to(cuda).train()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
+            mod.eval()
     with pytest.raises(NotImplementedError, match="training the backbone"):
         m((torch.zeros(1, 3, 3, 64, 96, device=cuda), torch.zeros(1, 3, 12, 4, device=cuda)))

@@ -191,3 +191,22 @@ def test_oracle_autograd_reproduces_reference_gradients(path):
     assert set(grads) == set(fx["grads_ref"]), set(grads) ^ set(fx["grads_ref"])
     for k, d in fx["grads_ref"].items():
         _digest_close(grads[k], d)
+
+
+def test_oracle_autograd_reproduces_reference_backbone_gradients():
+    """cfg.train_backbone = True (scripts/train_volleyball_stage2_dynamic.py:12): autograd over the restatement,
+    backbone included, == the reference model's own gradients for all 43 parameter tensors."""
+    import din_oracle as O
+    fx = torch.load(os.path.join(GOLDEN, "fullgrads_vgg16_lite.pt"))
+    pc = _pc_from(fx["config"])
+    bb = O.build_backbone(pc.backbone)
+    sd = O.make_state_dict(pc, seed=fx["seed"], backbone=bb)
+    batch = O.make_inputs(pc, fx["B"], seed=fx["seed"])
+    O.load_backbone(bb, sd)
+    bb.eval()
+    logits, loss, grads = O.head_grads(bb, sd, pc, fx["labels"], *batch, train_backbone=True)
+    assert abs(float(loss) - float(fx["loss_ref"])) <= 1e-5
+    assert set(grads) == set(fx["grads_ref"]), set(grads) ^ set(fx["grads_ref"])
+    assert sum(k.startswith("backbone.") for k in grads) == 26
+    for k, d in fx["grads_ref"].items():
+        _digest_close(grads[k], d)
