@@ -134,6 +134,63 @@ def build_model(pc, device):
     return model.to(device).eval(), sd, bb
 
 
+def train_step_info(model, pc, dev, images_d, boxes_d, clips, steps=5, warmup=2):
+    """Supplementary (NOT the headline metric): one stage-2 TRAINING step -- train-mode forward, on-device
+    cross-entropy, backward through the head and the VGG-16 backbone -- on `clips` clips
+    (scripts/train_volleyball_stage2_dynamic.py:42 batch_size = 2).  The optimizer is torch's and is not timed."""
+    import torch
+    from din_b200 import metrics, ops
+    try:
+        model.train()
+        for q in model.parameters():
+            q.requires_grad = True
+        im, bx = images_d[:clips].contiguous(), boxes_d[:clips].contiguous()
+        labels = (torch.arange(clips, device=dev) % pc.num_activities)
+
+        def step():
+            for q in model.parameters():
+                q.grad = None
+            loss = metrics.cross_entropy(model((im, bx))["activities"], labels)
+            loss.backward()
+            return loss
+
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        ops.RECORDER = []
+        launches0 = ops.LAUNCHES
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize()
+        rec, ops.RECORDER = ops.RECORDER, None
+        ms = e0.elapsed_time(e1) / steps
+        by = {}
+        flops = 0.0
+        for (n, f, b, a, z) in rec:
+            k = n.split("_")[0].split("@")[0]
+            k = "conv_fwd/dgrad" if k.startswith("conv") else ("wgrad" if k.startswith("wgrad") else k)
+            by[k] = by.get(k, 0.0) + a.elapsed_time(z) / steps
+            flops += f / steps
+        info = {"clips": clips, "ms_per_step": ms, "clips_per_s": clips / (ms / 1e3), "loss": float(loss.detach()),
+                "backbone_trained": True, "gpu_launches_per_step": (ops.LAUNCHES - launches0) // steps,
+                "algorithmic_tflops": flops / (ms / 1e3) / 1e12,
+                "kernels_ms": {k: round(v, 3) for k, v in sorted(by.items(), key=lambda kv: -kv[1])[:10]},
+                "note": "forward(train) + cross-entropy + backward, optimizer not timed"}
+    except Exception as e:                                   # never lose the headline line to the supplementary one
+        info = {"error": f"{type(e).__name__}: {e}"[:300]}
+    finally:
+        ops.RECORDER = None
+        model.eval()
+        for q in model.parameters():
+            q.requires_grad = False
+            q.grad = None
+        torch.cuda.empty_cache()
+    return info
+
+
 def cpu_reference_clips_per_s(pc, sd, bb, budget_s, steps=1, warmup=0):
     """Times the CPU port of the reference path (oracle/din_oracle.py) with all host threads.
     A step is one clip (B=1); if (steps+warmup) clips would exceed `budget_s`, the clip is cut to the first
@@ -188,6 +245,8 @@ def main():
     ap.add_argument("--clips-per-gpu", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true")
+    ap.add_argument("--train-clips", type=int, default=2, help="clips per training step (reference batch_size = 2)")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -379,6 +438,8 @@ def main():
     if e2e:
         line["e2e"] = {"value": total_clips / (e2e["ms"] / 1e3), "unit": UNIT,
                        "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"]}
+    if world == 1 and not args.no_train_step and pc.backbone == "vgg16" and pc.dataset == "volleyball":
+        line["train_step"] = train_step_info(model, pc, dev, images_d, boxes_d, args.train_clips)
     if world == 1 and not args.no_cpu_baseline:
         v, cores, sample, _ = cpu_reference_clips_per_s(pc, sd, bb, budget_s=args.cpu_budget_s)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}

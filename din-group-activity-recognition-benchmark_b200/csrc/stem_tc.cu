@@ -75,13 +75,16 @@ struct PatchRegs {
   using Cfg = StemCfg<COUT, KH, KW, STRIDE>;
   static constexpr int kN = U8 ? KH * Cfg::kLoadsPerRow : Cfg::kRows * Cfg::kLoadsPerRow;
   uint32_t v[kN];
+  uint32_t valid;     // fp32 path: bit (ky * kLoadsPerRow + u) = that (row, column slot) is inside the image
 };
 
 // prep_images with the contraction spelled out (one FMA, one exact doubling), so that every instantiation
 // rounds identically: (x/255 - 0.5)*2 (utils.py:14-17); the product by 1/255 differs from the division by at
 // most 1 ulp(fp32), far below the fp16 rounding applied next.
+// Branch-free: without prep the constants are (1, 0, 1), which reproduce f exactly.
 __device__ __forceinline__ float prep_value(float f, bool prep) {
-  return prep ? __fmul_rn(__fmaf_rn(f, 1.0f / 255.0f, -0.5f), 2.0f) : f;
+  const float a = prep ? 1.0f / 255.0f : 1.0f, b = prep ? -0.5f : 0.0f, c = prep ? 2.0f : 1.0f;
+  return __fmul_rn(__fmaf_rn(f, a, b), c);
 }
 
 struct TileCoord { int img, oy, strip; };
@@ -98,10 +101,14 @@ __device__ __forceinline__ TileCoord decode_tile(const StemParams& p, int tile) 
 template <int COUT, int KH, int KW, int STRIDE, bool U8>
 __device__ __forceinline__ void load_patch(const StemParams& p, const TileCoord& t, int tid,
                                            PatchRegs<COUT, KH, KW, STRIDE, U8>& r) {
+  // Every load is a PREDICATED load with no arithmetic on its result in this function: the compiler then issues
+  // all of them back to back (one exposed memory latency per tile).  Doing prep_images right at the load put
+  // each LDG in its own branch and serialised 18 latencies: the kernel ran 60 % slower (measured).
   using Cfg = StemCfg<COUT, KH, KW, STRIDE>;
   const int iy0 = t.oy * STRIDE - p.pad;
   const int gx0 = t.strip * 128 * STRIDE - p.pad;
   const size_t plane = static_cast<size_t>(p.h) * p.w_in;
+  r.valid = 0u;
   if constexpr (U8) {
     const uint8_t* xi = static_cast<const uint8_t*>(p.x) + static_cast<size_t>(t.img) * 3 * plane;
 #pragma unroll
@@ -113,13 +120,10 @@ __device__ __forceinline__ void load_patch(const StemParams& p, const TileCoord&
       for (int u = 0; u < Cfg::kLoadsPerRow; ++u) {
         const int px = tid + u * kStemThreads;
         const int gx = gx0 + px;
-        uint32_t w = 0x01000000u;
-        if (row_ok && px < Cfg::kPatchW && gx >= 0 && gx < p.w_in) {
-          const uint8_t* q = src + static_cast<size_t>(gx) * 3;
-          w = static_cast<uint32_t>(__ldg(q)) | (static_cast<uint32_t>(__ldg(q + 1)) << 8) |
-              (static_cast<uint32_t>(__ldg(q + 2)) << 16);
-        }
-        r.v[ky * Cfg::kLoadsPerRow + u] = w;
+        const bool ok = row_ok && px < Cfg::kPatchW && gx >= 0 && gx < p.w_in;
+        const uint8_t* q = src + static_cast<size_t>(ok ? gx : 0) * 3;
+        const uint32_t b0 = ok ? __ldg(q) : 0u, b1 = ok ? __ldg(q + 1) : 0u, b2 = ok ? __ldg(q + 2) : 0u;
+        r.v[ky * Cfg::kLoadsPerRow + u] = b0 | (b1 << 8) | (b2 << 16) | (ok ? 0u : 0x01000000u);
       }
     }
   } else {
@@ -135,10 +139,11 @@ __device__ __forceinline__ void load_patch(const StemParams& p, const TileCoord&
         for (int u = 0; u < Cfg::kLoadsPerRow; ++u) {
           const int px = tid + u * kStemThreads;
           const int gx = gx0 + px;
-          // prep_images is applied to real pixels only: the convolution pads the PREPPED image with zeros
-          const float f = (row_ok && px < Cfg::kPatchW && gx >= 0 && gx < p.w_in)
-                              ? prep_value(__ldg(src + gx), p.prep != 0) : 0.0f;
-          r.v[(c * KH + ky) * Cfg::kLoadsPerRow + u] = __float_as_uint(f);
+          const bool ok = row_ok && px < Cfg::kPatchW && gx >= 0 && gx < p.w_in;
+          // padding: the raw value that preps to EXACTLY 0 under prep_value's FMA is not representable, so the
+          // pad is a plain 0 here and stage_patch skips prep for it (prep == 0: a 0 is a 0 anyway)
+          r.v[(c * KH + ky) * Cfg::kLoadsPerRow + u] = __float_as_uint(ok ? __ldg(src + gx) : 0.0f);
+          if (c == 0) r.valid |= (ok ? 1u : 0u) << (ky * Cfg::kLoadsPerRow + u);
         }
       }
     }
@@ -175,7 +180,8 @@ __device__ __forceinline__ void stage_patch(const StemParams& p, int tid, float*
       for (int u = 0; u < Cfg::kLoadsPerRow; ++u) {
         const int px = tid + u * kStemThreads;
         const float f = __uint_as_float(r.v[rr * Cfg::kLoadsPerRow + u]);
-        if (px < Cfg::kPatchW) patch[rr * Cfg::kPitch + px] = f;
+        const bool ok = (r.valid >> ((rr % KH) * Cfg::kLoadsPerRow + u)) & 1u;      // same for the 3 channels
+        if (px < Cfg::kPatchW) patch[rr * Cfg::kPitch + px] = ok ? prep_value(f, p.prep != 0) : 0.0f;
       }
     }
   }

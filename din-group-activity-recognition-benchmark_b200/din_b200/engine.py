@@ -248,7 +248,9 @@ class DPIWeights:
 class DinEngine:
     """Forward plan for Dynamic_volleyball / Dynamic_collective built from a reference-named state_dict."""
 
-    def __init__(self, cfg, state_dict, device, dataset="volleyball", frames_per_chunk=None):
+    def __init__(self, cfg, state_dict, device, dataset="volleyball", frames_per_chunk=None, backbone_plan=None):
+        """backbone_plan: a plan built earlier from the same backbone weights (a training loop with the backbone
+        frozen changes only the head's weights between steps: the 14.7 M backbone weights are not re-packed)."""
         self.cfg, self.dataset, self.device = cfg, dataset, torch.device(device)
         # frames per backbone launch: bounds the activation workspace (VGG-16 at 720p: 0.27 GB per frame
         # live at once) while keeping every launch many waves long
@@ -260,7 +262,7 @@ class DinEngine:
         self.NFB = cfg.num_features_boxes
         self.C = cfg.lite_dim if cfg.lite_dim else self.NFB
         self.backbone_name = cfg.backbone
-        self.backbone = build_backbone_plan(cfg.backbone, sd)
+        self.backbone = backbone_plan if backbone_plan is not None else build_backbone_plan(cfg.backbone, sd)
 
         # fc_emb_1: the reference flattens crops as (d, ky, kx) (infer_model.py:181); RoIAlign here emits
         # (ky, kx, d), so permute the weight's columns once.  Public parameter stays [NFB, K*K*D].

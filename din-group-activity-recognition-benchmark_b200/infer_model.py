@@ -103,6 +103,7 @@ class _DinModel(nn.Module):
                 if m.bias is not None:
                     nn.init.zeros_(m.bias)
         self._engine, self._engine_key = None, None
+        self._bb_plan_key = None
 
     # -- reference API ---------------------------------------------------------------------------
     def loadmodel(self, filepath):
@@ -128,9 +129,12 @@ class _DinModel(nn.Module):
             if dev.type != "cuda":
                 raise RuntimeError("the DIN hot path runs on sm_100a only: move the model to a CUDA device "
                                    "(there is no CPU fallback)")
+            # the backbone plan survives head-only weight updates (frozen-backbone training)
+            bb_key = (str(dev),) + tuple((t.data_ptr(), t._version) for t in self.backbone.state_dict().values())
+            plan = self._engine.backbone if (self._engine is not None and self._bb_plan_key == bb_key) else None
             with torch.cuda.device(dev):
-                self._engine = DinEngine(self.cfg, self.state_dict(), dev, dataset=self._dataset)
-            self._engine_key = key
+                self._engine = DinEngine(self.cfg, self.state_dict(), dev, dataset=self._dataset, backbone_plan=plan)
+            self._engine_key, self._bb_plan_key = key, bb_key
         return self._engine
 
     def _check_mode(self, images):
