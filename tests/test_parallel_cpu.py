@@ -68,3 +68,45 @@ def test_sharded_forward_world2_gloo(n_clips):
         assert p.exitcode == 0
     assert [r[1] for r in res] == [True, True]      # identical, correctly ordered logits on both ranks
     assert [r[2] for r in res] == [11.0, 11.0]      # max over ranks
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from din_b200.parallel import GradientAllReducer
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(5, 3)
+    extra = torch.nn.Parameter(torch.zeros(4))            # never used: no gradient on any rank
+    frozen = torch.nn.Parameter(torch.zeros(2), requires_grad=False)
+    x = torch.full((2, 5), float(rank + 1))
+    lin(x).sum().backward()
+    local = [p.grad.clone() for p in lin.parameters()]
+    reducer = GradientAllReducer(list(lin.parameters()) + [extra, frozen])
+    n = reducer()
+    # the mean over ranks of grads computed with x = 1 and x = 2: weight grad rows = 2 * mean(1, 2) = 3, bias = 2
+    ok = (n == 15 + 3 + 4 and torch.allclose(lin.weight.grad, torch.full((3, 5), 3.0))
+          and torch.allclose(lin.bias.grad, torch.full((3,), 2.0)) and torch.equal(extra.grad, torch.zeros(4))
+          and frozen.grad is None and not torch.equal(local[0], lin.weight.grad))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world2_gloo():
+    """One flat all-reduce per step averages every parameter gradient over the ranks."""
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                       "din-group-activity-recognition-benchmark_b200")
+    os.environ["PYTHONPATH"] = pkg + os.pathsep + os.environ.get("PYTHONPATH", "")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[1] for r in res] == [True, True]
