@@ -405,11 +405,15 @@ din_conv_bwd_dx_kernel(const float* __restrict__ dconv, const float* __restrict_
     dcs[i] = v;
   }
   __syncthreads();
+  // thread = (actor slice, channel quad): with C = 128 only 32 quads exist, so the 256 threads also split the
+  // actors (slice s owns actors s, s + n_slices, ...); with C = 1024 there is one slice and 16 accumulators
   const int C4 = C >> 2;
-  for (int c4 = threadIdx.x; c4 < C4; c4 += 256) {
+  const int n_slices = (C4 >= 256) ? 1 : (256 / C4 < kDinMaxN ? 256 / C4 : kDinMaxN);
+  for (int item = threadIdx.x; item < C4 * n_slices; item += 256) {
+    const int c4 = item % C4, slice = item / C4;
     float4 acc[kDinMaxN];
 #pragma unroll
-    for (int n = 0; n < kDinMaxN; ++n) acc[n] = make_float4(0, 0, 0, 0);
+    for (int j = 0; j < kDinMaxN; ++j) acc[j] = make_float4(0, 0, 0, 0);
     for (int ky = 0; ky < kt; ++ky) {
       for (int kx = 0; kx < kn; ++kx) {
         const int tap = ky * kn + kx;
@@ -417,59 +421,64 @@ din_conv_bwd_dx_kernel(const float* __restrict__ dconv, const float* __restrict_
         for (int o = 0; o < n_out; ++o) {
           const float4 wv = __ldg(reinterpret_cast<const float4*>(w_tap + (static_cast<size_t>(tap) * n_out + o) * C) + c4);
 #pragma unroll
-          for (int n = 0; n < kDinMaxN; ++n) {
+          for (int j = 0; j < kDinMaxN; ++j) {
+            const int n = slice + j * n_slices;
             const int ns = n - dxk;                  // source actor
             if (n < Nb && ns >= 0 && ns < Nb) {
               const float d = dcs[(ky * N + ns) * n_out + o];
-              acc[n].x = fmaf(d, wv.x, acc[n].x); acc[n].y = fmaf(d, wv.y, acc[n].y);
-              acc[n].z = fmaf(d, wv.z, acc[n].z); acc[n].w = fmaf(d, wv.w, acc[n].w);
+              acc[j].x = fmaf(d, wv.x, acc[j].x); acc[j].y = fmaf(d, wv.y, acc[j].y);
+              acc[j].z = fmaf(d, wv.z, acc[j].z); acc[j].w = fmaf(d, wv.w, acc[j].w);
             }
           }
         }
       }
     }
 #pragma unroll
-    for (int n = 0; n < kDinMaxN; ++n) {
+    for (int j = 0; j < kDinMaxN; ++j) {
+      const int n = slice + j * n_slices;
       if (n < Nb) {
         float4* dst = reinterpret_cast<float4*>(dx + ((static_cast<size_t>(b) * T + t) * N + n) * C) + c4;
         float4 v = *dst;
-        v.x += acc[n].x; v.y += acc[n].y; v.z += acc[n].z; v.w += acc[n].w;
+        v.x += acc[j].x; v.y += acc[j].y; v.z += acc[j].z; v.w += acc[j].w;
         *dst = v;
       }
     }
   }
 }
 
-// dW[tap][o][c] = sum_{b,t,n} dconv[b,t,n,o] * x~[b, t+dy_tap, n+dx_tap, c];  block (0,0) also reduces db and d(coef)
+// dW[tap][o][c] = sum_{b,t,n} dconv[b,t,n,o] * x~[b, t+dy_tap, n+dx_tap, c], in two deterministic stages:
+//   stage 1  grid (tap, 128-channel chunk, node split): partial sums over a contiguous range of nodes -> part[s]
+//   stage 2  dW = sum_s part[s] (fixed order); one extra block reduces db and d(coef)
+// (a single pass over all 960 nodes per block was a 0.6 ms latency chain at grid 9-72, ncu r1_v9)
 constexpr int kDwThreads = 128;
 constexpr int kDwNodes = 32;
 constexpr int kDwMaxOut = 27;
 
 __global__ void __launch_bounds__(kDwThreads)
-din_conv_bwd_dw_kernel(const float* __restrict__ x, const float* __restrict__ dconv,
-                       const float* __restrict__ dcoef_part, float* __restrict__ dw_tap, float* __restrict__ db_cat,
-                       float* __restrict__ dcoef, int B, int T, int N, int C, int kt, int kn, int ratio, int n_out,
-                       const int* __restrict__ n_valid) {
+din_conv_bwd_dw_partial_kernel(const float* __restrict__ x, const float* __restrict__ dconv, float* __restrict__ part,
+                               int B, int T, int N, int C, int kt, int kn, int ratio, int n_out, int nodes_per_split,
+                               const int* __restrict__ n_valid) {
   __shared__ float dcs[kDwNodes][kDwMaxOut + 1];
-  __shared__ float red[33];
   const int tap = blockIdx.x;
   const int ky = tap / kn, kx = tap - ky * kn;
   const int dyk = -(((kt - 1) * ratio + 1) / 2) + ky * ratio;
   const int dxk = -(((kn - 1) * ratio + 1) / 2) + kx * ratio;
   const int c = blockIdx.y * kDwThreads + threadIdx.x;
   const int nodes = B * T * N;
+  const int node_begin = blockIdx.z * nodes_per_split;
+  const int node_end = min(nodes, node_begin + nodes_per_split);
   float acc[kDwMaxOut];
 #pragma unroll
   for (int o = 0; o < kDwMaxOut; ++o) acc[o] = 0.0f;
-  for (int n0 = 0; n0 < nodes; n0 += kDwNodes) {
+  for (int n0 = node_begin; n0 < node_end; n0 += kDwNodes) {
     __syncthreads();
     for (int i = threadIdx.x; i < kDwNodes * n_out; i += kDwThreads) {
       const int j = i / n_out, o = i - j * n_out;
-      dcs[j][o] = (n0 + j < nodes) ? __ldg(dconv + static_cast<size_t>(n0 + j) * n_out + o) : 0.0f;
+      dcs[j][o] = (n0 + j < node_end) ? __ldg(dconv + static_cast<size_t>(n0 + j) * n_out + o) : 0.0f;
     }
     __syncthreads();
     if (c < C) {
-      for (int j = 0; j < kDwNodes && n0 + j < nodes; ++j) {
+      for (int j = 0; j < kDwNodes && n0 + j < node_end; ++j) {
         const int node = n0 + j;
         const int n = node % N;
         const int bt = node / N;
@@ -485,24 +494,49 @@ din_conv_bwd_dw_kernel(const float* __restrict__ x, const float* __restrict__ dc
     }
   }
   if (c < C) {
+    float* dst = part + (static_cast<size_t>(blockIdx.z) * gridDim.x + tap) * n_out * C;
 #pragma unroll
     for (int o = 0; o < kDwMaxOut; ++o)
-      if (o < n_out) dw_tap[(static_cast<size_t>(tap) * n_out + o) * C + c] = acc[o];
+      if (o < n_out) dst[static_cast<size_t>(o) * C + c] = acc[o];
   }
-  if (blockIdx.x == 0 && blockIdx.y == 0) {
-    // bias gradient: padded actors hold zeros in dconv (din_bwd_kernel writes them)
-    if (threadIdx.x < n_out) {
+}
+
+__global__ void __launch_bounds__(256)
+din_conv_bwd_dw_reduce_kernel(const float* __restrict__ part, const float* __restrict__ dconv,
+                              const float* __restrict__ dcoef_part, float* __restrict__ dw_tap,
+                              float* __restrict__ db_cat, float* __restrict__ dcoef, int total /* k2*n_out*C */,
+                              int splits, int nodes, int n_out) {
+  __shared__ float red[33];
+  if (blockIdx.x < gridDim.x - 1) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < total) {
       float s = 0.0f;
-      for (int node = 0; node < nodes; ++node) s += __ldg(dconv + static_cast<size_t>(node) * n_out + threadIdx.x);
-      db_cat[threadIdx.x] = s;
+      for (int sp = 0; sp < splits; ++sp) s += __ldg(part + static_cast<size_t>(sp) * total + i);
+      dw_tap[i] = s;
     }
-    if (dcoef != nullptr && dcoef_part != nullptr) {
-      float s = 0.0f;
-      for (int node = threadIdx.x; node < nodes; node += kDwThreads) s += __ldg(dcoef_part + node);
-      s = block_sum<kDwThreads>(s, red);
-      if (threadIdx.x == 0) dcoef[0] = s;
-    }
+    return;
   }
+  // last block: bias gradient (padded actors hold zeros in dconv) and d(coef)
+  if (threadIdx.x < n_out) {
+    float s = 0.0f;
+    for (int node = 0; node < nodes; ++node) s += __ldg(dconv + static_cast<size_t>(node) * n_out + threadIdx.x);
+    db_cat[threadIdx.x] = s;
+  }
+  if (dcoef != nullptr) {
+    float s = 0.0f;
+    for (int node = threadIdx.x; node < nodes; node += 256) s += __ldg(dcoef_part + node);
+    s = block_sum<256>(s, red);
+    if (threadIdx.x == 0) dcoef[0] = s;
+  }
+}
+
+// node splits of stage 1 and the workspace that follows from them
+__host__ inline int din_bwd_splits(int nodes, int k2, int c) {
+  const int blocks = k2 * ((c + kDwThreads - 1) / kDwThreads);
+  int splits = (2 * 148 + blocks - 1) / blocks;
+  const int max_splits = (nodes + kDwNodes - 1) / kDwNodes;
+  if (splits > max_splits) splits = max_splits;
+  return splits < 1 ? 1 : splits;
 }
 
 }  // namespace
@@ -615,9 +649,24 @@ extern "C" int din_dynamic_infer_bwd_f32(const float* x, const float* w_tap, con
   const size_t smem2 = static_cast<size_t>(kt) * n * n_out * sizeof(float);
   din_conv_bwd_dx_kernel<<<b * t, 256, smem2, st>>>(dconv, w_tap, dx, t, n, c, kt, kn, ratio, n_out, n_valid);
   DIN_CHECK_CUDA(cudaGetLastError());
-  dim3 grid(kt * kn, (c + kDwThreads - 1) / kDwThreads);
-  din_conv_bwd_dw_kernel<<<grid, kDwThreads, 0, st>>>(x, dconv, dcoef_part, dw_tap, db_cat, dcoef, b, t, n, c, kt, kn,
-                                                      ratio, n_out, n_valid);
+  const int k2 = kt * kn;
+  const int splits = din_bwd_splits(static_cast<int>(nodes), k2, c);
+  const int nodes_per_split = (static_cast<int>(nodes) + splits - 1) / splits;
+  float* part = dcoef_part + nodes;           // [splits][k2][n_out][c]
+  dim3 grid(k2, (c + kDwThreads - 1) / kDwThreads, splits);
+  din_conv_bwd_dw_partial_kernel<<<grid, kDwThreads, 0, st>>>(x, dconv, part, b, t, n, c, kt, kn, ratio, n_out,
+                                                              nodes_per_split, n_valid);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  const int total = k2 * n_out * c;
+  din_conv_bwd_dw_reduce_kernel<<<(total + 255) / 256 + 1, 256, 0, st>>>(part, dconv, dcoef_part, dw_tap, db_cat, dcoef,
+                                                                        total, splits, static_cast<int>(nodes), n_out);
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;
+}
+
+extern "C" long long din_dynamic_infer_bwd_ws_floats(int b, int t, int n, int c, int kt, int kn, int scale_factor) {
+  if (b <= 0 || t <= 0 || n <= 0 || c <= 0 || kt <= 0 || kn <= 0) return -1;
+  const long long nodes = static_cast<long long>(b) * t * n;
+  const int k2 = kt * kn, n_out = (scale_factor ? 3 : 2) * k2;
+  return nodes * (n_out + 1) + static_cast<long long>(din_bwd_splits(static_cast<int>(nodes), k2, c)) * k2 * n_out * c;
 }

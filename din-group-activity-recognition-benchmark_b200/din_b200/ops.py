@@ -415,7 +415,7 @@ def group_layernorm_bwd(x, gamma, beta, dy, *, n_outer, n_inner=1, outer_stride,
 
 def dynamic_infer_bwd(x, w_tap, b_cat, dy, dx, kernel, ratio, *, scale_factor=True, coef=1.0, coef_ptr=None,
                       want_dcoef=False, n_valid=None):
-    """dx += ...; returns (dw_tap, db_cat, dcoef | None).  Launches three kernels."""
+    """dx += ...; returns (dw_tap, db_cat, dcoef | None).  Launches four kernels."""
     _need(x, torch.float32, "x")
     _need(dy, torch.float32, "dy")
     _need(dx, torch.float32, "dx")
@@ -425,9 +425,10 @@ def dynamic_infer_bwd(x, w_tap, b_cat, dy, dx, kernel, ratio, *, scale_factor=Tr
     dw = torch.empty_like(w_tap)
     db = torch.empty_like(b_cat)
     dcoef = torch.empty((1,), dtype=torch.float32, device=x.device) if want_dcoef else None
-    ws = torch.empty((b * t * n * (n_out + 1),), dtype=torch.float32, device=x.device)
+    ws_floats = _lib.load().din_dynamic_infer_bwd_ws_floats(b, t, n, c, kt, kn, int(scale_factor))
+    ws = torch.empty((ws_floats,), dtype=torch.float32, device=x.device)
     global LAUNCHES
-    LAUNCHES += 2                                   # this entry point launches three kernels
+    LAUNCHES += 3                                   # this entry point launches four kernels
     with _launch(f"dynamic_infer_bwd_k{kt}x{kn}_r{ratio}_c{c}", 6 * b * t * n * n_out * kt * kn * c, 16 * x.numel()):
         check(_lib.load().din_dynamic_infer_bwd_f32(_p(x), _p(w_tap), _p(b_cat), _p(dy), _p(dx), _p(dw), _p(db),
                                                     _p(dcoef), _p(ws), b, t, n, c, kt, kn, ratio, int(scale_factor),

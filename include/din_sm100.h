@@ -296,8 +296,9 @@ DIN_API int din_group_layernorm_bwd_f32(const float* x, const float* pre, const 
  *   dcoef   = [1] d(loss)/d(coef) (the gradient of beta[r] when beta_factor), or NULL.
  * The offsets receive gradient only through the bilinear weights (floor is detached, :208); clamped positions
  * pass gradient where 0 <= p <= max (torch.clamp); |.|' = sign with sign(0) = 0.
- * ws: workspace [b*t*n*(n_out + 1)] floats.  Same shape limits as the forward.
+ * ws: workspace of din_dynamic_infer_bwd_ws_floats(...) floats.  Same shape limits as the forward.  Four launches.
  */
+DIN_API long long din_dynamic_infer_bwd_ws_floats(int b, int t, int n, int c, int kt, int kn, int scale_factor);
 DIN_API int din_dynamic_infer_bwd_f32(const float* x, const float* w_tap, const float* b_cat, const float* dy,
                                       float* dx, float* dw_tap, float* db_cat, float* dcoef, float* ws, int b, int t,
                                       int n, int c, int kt, int kn, int ratio, int scale_factor,
