@@ -235,7 +235,22 @@ def cpu_reference_clips_per_s(pc, sd, bb, budget_s, steps=1, warmup=0):
     return clips_per_s, torch.get_num_threads(), sample, dt
 
 
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line, but libraries write to file descriptor 1 behind Python's back (NCCL
+    prints its version banner there at communicator creation): point fd 1 at stderr for the whole run and keep a
+    private duplicate of the real stdout for the final line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+def _emit(real_stdout, obj):
+    os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
+
 def main():
+    real_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -275,14 +290,14 @@ def main():
         sd = O.make_state_dict(pc, seed=0, backbone=bb)
         v, cores, sample, dt = cpu_reference_clips_per_s(pc, sd, bb, budget_s=200.0, steps=max(1, args.steps),
                                                          warmup=args.warmup)
-        print(json.dumps({
+        _emit(real_stdout, {
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(config, clips_per_gpu=1, global_clips_per_step=1, parallelism="cpu"),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}))
+            "gpu_launches": 0})
         return
 
     # ------------------------------------------------------------------ our arm (B200)
@@ -443,7 +458,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         v, cores, sample, _ = cpu_reference_clips_per_s(pc, sd, bb, budget_s=args.cpu_budget_s)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-    print(json.dumps(line))
+    _emit(real_stdout, line)
     if dist is not None:
         dist.destroy_process_group()
 

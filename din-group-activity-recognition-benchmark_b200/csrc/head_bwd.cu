@@ -110,6 +110,14 @@ scale_mask_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask,
   y[i] = x[i] * m;
 }
 
+// dz = dy * [y > 0]  (fp32 ReLU backward from the saved OUTPUT, as F.relu's autograd; base_model.py:120)
+__global__ void __launch_bounds__(256)
+relu_bwd_f32_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dz, long long count) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= count) return;
+  dz[i] = y[i] > 0.0f ? dy[i] : 0.0f;
+}
+
 // ================================================================================================
 // read-out backward.  Forward: pooled = max_n s; scores = pooled.W^T + bias; logits = mean_t scores.
 //   kernel 1 (CTA per (clip, frame)): pooled + first arg-max (torch.max's index), dpooled = (dlogits/T).W,
@@ -576,6 +584,15 @@ extern "C" int din_scale_mask_f32(const float* x, const uint8_t* mask, float sca
   DIN_CHECK_ARG(count > 0 && (count + 255) / 256 <= INT32_MAX, "din_scale_mask_f32: bad count %lld", count);
   scale_mask_kernel<<<static_cast<int>((count + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, mask, scale, y, count);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
+extern "C" int din_relu_bwd_f32(const float* y, const float* dy, float* dz, long long count, void* stream) {
+  DIN_CHECK_ARG(y && dy && dz, "din_relu_bwd_f32: null pointer");
+  DIN_CHECK_ARG(count > 0 && (count + 255) / 256 <= INT32_MAX, "din_relu_bwd_f32: bad count %lld", count);
+  relu_bwd_f32_kernel<<<static_cast<int>((count + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, dy, dz,
+                                                                                                            count);
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;
 }

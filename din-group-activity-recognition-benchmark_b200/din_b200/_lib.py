@@ -50,6 +50,7 @@ PROTOTYPES = {
     "din_gemm_f32": (C.c_int, [_fp, _ll, _ll, _vp, _i, _ll, _ll, _fp, _ll, _i, _i, _i, C.c_float, _i, _vp]),
     "din_colsum_f32": (C.c_int, [_fp, _fp, _i, _i, _ll, _vp]),
     "din_scale_mask_f32": (C.c_int, [_fp, _vp, C.c_float, _fp, _ll, _vp]),
+    "din_relu_bwd_f32": (C.c_int, [_fp, _fp, _fp, _ll, _vp]),
     "din_readout_bwd_f32": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _vp, _vp]),
     "din_group_layernorm_bwd_f32": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _ll, _ll, _i,
                                               _ll, _i, C.c_float, _i, _i, _vp, _vp]),

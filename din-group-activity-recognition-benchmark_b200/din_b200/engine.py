@@ -421,6 +421,8 @@ class BasenetEngine:
         wp[:, :, :self.D] = w
         self.fc_emb = _Conv(wp.view(self.NFB, self.K * self.K * self.D_stride, 1, 1), sd[emb_name + ".bias"],
                             relu=True, split=2 if self.backbone_name == "inv3" else 1)
+        self.fc_emb_wk = wp.view(self.NFB, self.K * self.K * self.D_stride)   # fp32, kernel K order (d(crops) GEMM)
+        self.emb_name = emb_name
         self.fc_actions = (sd["fc_actions.weight"].contiguous(), sd["fc_actions.bias"].contiguous())
         self.fc_act = (sd["fc_activities.weight"].contiguous(), sd["fc_activities.bias"].contiguous())
         self._idx_cache, self._fm_cache = {}, None
@@ -428,6 +430,7 @@ class BasenetEngine:
     _box_idx = DinEngine._box_idx
     _flat_frames = staticmethod(DinEngine._flat_frames)
     features = DinEngine.features
+    features_train = DinEngine.features_train
 
     def _states(self, images, boxes, B, T, N):
         fm = self.features(self._flat_frames(images))

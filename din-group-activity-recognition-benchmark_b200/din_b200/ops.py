@@ -371,6 +371,17 @@ def scale_mask(x, mask, scale, out=None):
     return out
 
 
+def relu_bwd_f32(y, dy):
+    """dy * [y > 0] (fp32)."""
+    _need(y, torch.float32, "y")
+    _need(dy, torch.float32, "dy")
+    assert y.numel() == dy.numel()
+    dz = torch.empty_like(dy)
+    with _launch("relu_bwd_f32", 0, 12 * y.numel()):
+        check(_lib.load().din_relu_bwd_f32(_p(y), _p(dy), _p(dz), y.numel(), _stream()), "din_relu_bwd_f32")
+    return dz
+
+
 def readout_bwd(s, w, dlogits, n_valid=None):
     """-> (ds [b,t,n,c], dw [a,c], dbias [a])."""
     _need(s, torch.float32, "s")

@@ -229,3 +229,67 @@ def backward_backbone(eng, tape, dcrops, grads):
     for f0, f1, saved in tape["bb_chunks"]:
         eng.backbone.backward(saved, dfm16[f0:f1], inv_scale, acc)
     eng.backbone.export_grads(acc, grads)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# stage 1: Basenet_volleyball (base_model.py:64-142) -- scripts/train_volleyball_stage1.py trains it with the VGG-16
+# backbone, T = 1, cross-entropy on the activities plus weighted cross-entropy on the per-actor actions
+# ------------------------------------------------------------------------------------------------------------------
+def basenet_forward_train(eng, images, boxes, training=True, train_backbone=True):
+    """-> ((actions [B*N, A], activities [B, A2]), tape)."""
+    cfg = eng.cfg
+    B, T = images.shape[:2]
+    N, NFB = eng.N, eng.NFB
+    M = B * T * N
+    tape = {"B": B, "T": T, "train_backbone": train_backbone}
+    with torch.no_grad():
+        if train_backbone:
+            fm, tape["bb_chunks"] = eng.features_train(eng._flat_frames(images))
+            tape["boxes"] = boxes.reshape(M, 4).contiguous().float()
+            tape["fm_shape"] = tuple(fm.shape)
+        else:
+            fm = eng.features(eng._flat_frames(images))
+        crops = ops.roi_align_nhwc(fm, boxes.reshape(M, 4).contiguous().float(), eng._box_idx(B * T, N), eng.K, eng.K,
+                                   d=eng.D_stride)
+        x = eng.fc_emb(crops.view(1, 1, M, eng.K * eng.K * eng.D_stride), out_f32=True).view(M, NFB)   # ReLU fused
+        p = float(cfg.train_dropout_prob)
+        mask = _dropout_mask(x.shape, p, eng.device, training)                                         # dropout_emb :121
+        x_d = ops.scale_mask(x, mask, 1.0 / (1.0 - p)) if mask is not None else x
+        tape.update(crops=crops.view(M, -1), x=x, x_d=x_d, mask=mask, p=p)
+        actions = ops.linear_f32(x_d, *eng.fc_actions)
+        activities = ops.readout(x_d.view(B, T, N, NFB), *eng.fc_act)
+        if T != 1:
+            actions = ops.mean_axis(actions.view(B, T, N * actions.shape[-1]), 1)
+    return (actions.view(B * N, -1), activities), tape
+
+
+def basenet_backward(eng, tape, dactions, dactivities):
+    """(d/d actions [B*N, A], d/d activities [B, A2]) -> {reference parameter name: gradient}."""
+    B, T = tape["B"], tape["T"]
+    N, NFB = eng.N, eng.NFB
+    M = B * T * N
+    grads = {}
+    with torch.no_grad():
+        x_d = tape["x_d"]
+        dx, dwa, dba = ops.readout_bwd(x_d.view(B, T, N, NFB), eng.fc_act[0], dactivities.contiguous().float())
+        grads["fc_activities.weight"], grads["fc_activities.bias"] = dwa, dba
+        A = eng.fc_actions[0].shape[0]
+        dact = dactions.contiguous().float().view(B, 1, N, A)
+        if T != 1:                                             # mean over frames (:138-139): broadcast / T
+            dact = ops.scale_mask(dact.expand(B, T, N, A).contiguous(), None, 1.0 / T)
+        _, dw, db = ops.linear_bwd(x_d, eng.fc_actions[0], dact.reshape(M, A), dx_out=dx.view(M, NFB), dx_accumulate=True)
+        grads["fc_actions.weight"], grads["fc_actions.bias"] = dw, db
+        dx = dx.view(M, NFB)
+        if tape["mask"] is not None:
+            dx = ops.scale_mask(dx, tape["mask"], 1.0 / (1.0 - tape["p"]))
+        demb = ops.relu_bwd_f32(tape["x"], dx)                 # F.relu (:120)
+        dcrops, dwk, dbe = ops.linear_bwd(tape["crops"], eng.fc_emb_wk if tape["train_backbone"] else None, demb,
+                                          need_dx=tape["train_backbone"])
+        KK = eng.K * eng.K
+        name = eng.emb_name
+        grads[name + ".weight"] = dwk.view(NFB, KK, eng.D_stride)[:, :, :eng.D].permute(0, 2, 1).reshape(NFB, -1) \
+            .contiguous()
+        grads[name + ".bias"] = dbe
+        if tape["train_backbone"]:
+            backward_backbone(eng, tape, dcrops, grads)
+    return grads

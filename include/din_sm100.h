@@ -265,6 +265,9 @@ DIN_API int din_colsum_f32(const float* x, float* y, int m, int n, long long ld,
 DIN_API int din_scale_mask_f32(const float* x, const uint8_t* mask, float scale, float* y, long long count,
                                void* stream);
 
+/* dz = dy * [y > 0] (fp32): backward of F.relu from its saved output (base_model.py:120, the stage-1 embedding). */
+DIN_API int din_relu_bwd_f32(const float* y, const float* dy, float* dz, long long count, void* stream);
+
 /*
  * Backward of din_readout_f32 (max over actors -> fc_activities -> mean over frames; infer_model.py:224-232).
  * s [b,t,n,c], w [a,c], dlogits [b,a]  ->  ds [b,t,n,c] (gradient at each channel's FIRST arg-max actor, zero

@@ -472,3 +472,33 @@ def test_full_training_step_with_backbone(cuda):
 # features.7, 1.3e-1 at features.0 -- while every tensor's NORM agrees with the reference's to 3-4 digits and each
 # kernel on the way is exact or 1e-4-tight in isolation (tests/test_conv_bwd_gpu.py).
 BB_TOL = 2e-1
+
+
+def test_gradient_of_batch_is_mean_of_per_clip_gradients(cuda):
+    """Size-independent property behind the data-parallel step: with dropout off, the gradient of
+    the batch-mean loss equals the mean of the per-clip gradients (what the single flat all-reduce averages),
+    backbone included; and two identical steps agree to atomics noise."""
+    import din_oracle as O
+    from din_b200 import metrics
+    pc = _pc("vgg16", (96, 160), num_frames=3, num_boxes=4)
+    sd = O.make_state_dict(pc, seed=4)
+    batch = tuple(t.to(cuda) for t in O.make_inputs(pc, 2, seed=4))
+    labels = torch.tensor([3, 6], device=cuda)
+    model, _ = _model_and_cfg(cuda, pc, sd, 0.0)
+    for q in model.backbone.parameters():
+        q.requires_grad = True
+
+    def grads(clips, lab):
+        for q in model.parameters():
+            q.grad = None
+        metrics.cross_entropy(model(clips)["activities"], lab).backward()
+        return {n: q.grad.clone() for n, q in model.named_parameters()}
+
+    full = grads(batch, labels)
+    again = grads(batch, labels)
+    g0 = grads(tuple(t[:1] for t in batch), labels[:1])
+    g1 = grads(tuple(t[1:] for t in batch), labels[1:])
+    for k in full:
+        assert _rel_l2(again[k], full[k]) <= 1e-5, ("determinism", k)
+        # the dynamic loss scale differs between the runs (per-step max|dfm|), hence fp16 rounding differs: 2e-3
+        assert _rel_l2(0.5 * (g0[k] + g1[k]), full[k]) <= 2e-3, (k, _rel_l2(0.5 * (g0[k] + g1[k]), full[k]))
