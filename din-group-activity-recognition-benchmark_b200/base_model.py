@@ -7,14 +7,39 @@ reads in stage 2: keys `backbone_state_dict`, `fc_emb_state_dict`, base_model.py
 stage-2 path (backbone plan, RoIAlign, tcgen05 embedding GEMM with the ReLU fused) plus the two small heads;
 torch modules below are parameter containers and are never called.
 
-Scope: evaluation / inference forward.
+Scope: evaluation / inference forward; `Basenet_volleyball` with the VGG-16 backbone -- the
+model scripts/train_volleyball_stage1.py trains -- also runs its training step on the CUDA path (one autograd node:
+both heads, dropout, the embedding and the whole backbone).  Other stage-1 training
+configurations raise.
 """
 import torch
 import torch.nn as nn
 
 from backbone.backbone import MyInception_v3, MyRes18, MyVGG16
+from din_b200 import train as _train
 from din_b200.engine import BasenetEngine
 from roi_align.roi_align import RoIAlign
+
+
+class _BasenetTrainFn(torch.autograd.Function):
+    """Stage-1 forward + backward as one autograd node (din_b200.train.basenet_forward_train / basenet_backward)."""
+
+    @staticmethod
+    def forward(ctx, model, images, boxes, names, *params):
+        train_bb = any(n.startswith("backbone.") for n in names)
+        (actions, activities), tape = _train.basenet_forward_train(model.engine(), images, boxes,
+                                                                    training=model.training, train_backbone=train_bb)
+        ctx.eng, ctx.tape, ctx.names = model.engine(), tape, names
+        ctx.shapes = [tuple(p.shape) for p in params]
+        return actions, activities
+
+    @staticmethod
+    def backward(ctx, dactions, dactivities):
+        grads = _train.basenet_backward(ctx.eng, ctx.tape, dactions, dactivities)
+        ctx.tape = None
+        out = [grads[n].reshape(shp) if (need and n in grads) else None
+               for n, shp, need in zip(ctx.names, ctx.shapes, ctx.needs_input_grad[4:])]
+        return (None, None, None, None) + tuple(out)
 
 
 class _Basenet(nn.Module):
@@ -56,9 +81,11 @@ class _Basenet(nn.Module):
     def _check_mode(self, images):
         if not images.is_cuda:
             raise RuntimeError("the DIN hot path runs on sm_100a only: pass CUDA tensors (there is no CPU fallback)")
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("the sm_100a stage-1 path is forward-only: use model.eval() and/or "
-                                      "torch.no_grad() (backward kernels: SURVEY.md §8f rank 1)")
+        if self.training and (self._dataset != "volleyball" or self.cfg.backbone != "vgg16"):
+            raise NotImplementedError(
+                "stage-1 training on the sm_100a path is implemented for Basenet_volleyball with the VGG-16 backbone "
+                "(scripts/train_volleyball_stage1.py); use model.eval() for the other configurations "
+                "(SURVEY.md §8f rank 1)")
 
 
 class Basenet_volleyball(_Basenet):
@@ -96,7 +123,14 @@ class Basenet_volleyball(_Basenet):
         self._check_mode(images_in)
         frames = images_in if images_in.dtype == torch.uint8 else images_in.float()
         with torch.cuda.device(images_in.device):
-            return self.engine().forward_volleyball(frames, boxes_in.float())
+            if not self.training:
+                return self.engine().forward_volleyball(frames, boxes_in.float())
+            if not torch.is_grad_enabled():
+                return _train.basenet_forward_train(self.engine(), frames, boxes_in.float(), training=True,
+                                                    train_backbone=False)[0]
+            named = [(n, p) for n, p in self.named_parameters() if p.requires_grad]
+            return _BasenetTrainFn.apply(self, frames, boxes_in.float(), tuple(n for n, _ in named),
+                                         *[p for _, p in named])
 
 
 class Basenet_collective(_Basenet):

@@ -98,14 +98,38 @@ def main_grads():
     print("fullgrads vgg16_lite", float(loss), len(grads))
 
 
+def main_basenet_grads():
+    """Stage-1 training-step fixture from the reference's own Basenet_volleyball (VGG-16, T = 1 as
+    scripts/train_volleyball_stage1.py, class-weighted action loss)."""
+    pc = O.PathConfig(backbone="vgg16", image_size=(96, 160), out_size=O.backbone_out_size("vgg16", 96, 160),
+                      num_frames=1, num_boxes=4)
+    B = 3
+    bb = O.build_backbone(pc.backbone)
+    sd = O.make_basenet_state_dict(pc, seed=0, backbone=bb)
+    batch = O.make_basenet_inputs(pc, B, seed=0)
+    g = torch.Generator().manual_seed(9)
+    actions_labels = torch.randint(0, pc.num_actions, (B * pc.num_boxes,), generator=g)
+    activities_labels = torch.randint(0, pc.num_activities, (B,), generator=g)
+    weights = torch.tensor([1., 1., 2., 3., 1., 2., 2., 0.2, 1.])       # scripts/train_volleyball_stage1.py:33
+    loss, grads = R.ref_basenet_grads(pc, sd, actions_labels, activities_labels, weights, *batch)
+    torch.save({"config": dataclasses.asdict(pc), "B": B, "seed": 0, "actions_labels": actions_labels,
+                "activities_labels": activities_labels, "actions_weights": weights, "loss_ref": loss,
+                "grads_ref": {k: O.grad_digest(v) for k, v in grads.items()},
+                "weights_checksum": checksum(sd.values())}, os.path.join(OUT, "stage1grads_vgg16_T1.pt"))
+    print("basenet grads", float(loss), len(grads))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--basenet-grads-only" in sys.argv:
+        return main_basenet_grads()
     if "--grads-only" in sys.argv:
         return main_grads()
     if "--basenet-only" in sys.argv:
         return main_basenet()
     main_basenet()
     main_grads()
+    main_basenet_grads()
     for name, (pc, B) in model_cases().items():
         bb = O.build_backbone(pc.backbone)
         sd = O.make_state_dict(pc, seed=0, backbone=bb)

@@ -218,6 +218,30 @@ def ref_basenet_forward(pc, sd, *batch):
         return model(tuple(batch))
 
 
+def ref_basenet_grads(pc, sd, actions_labels, activities_labels, actions_weights, *batch):
+    """The reference's stage-1 training step (train_net.py:163-189) on base_model.Basenet_volleyball: train mode,
+    dropout 0, everything trainable.  -> (loss, {param name: grad})."""
+    bm = ref_module("base_model")
+    cfg = make_ref_cfg(pc)
+    cfg.num_actions = pc.num_actions
+    cfg.train_dropout_prob = 0.0
+    cfg.train_backbone = True
+    import io
+    import warnings
+    with contextlib.redirect_stdout(io.StringIO()):
+        with _isolated_import():
+            model = bm.Basenet_volleyball(cfg)
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        actions, activities = model(tuple(batch))
+        loss = F.cross_entropy(activities, activities_labels) + \
+            cfg.actions_loss_weight * F.cross_entropy(actions, actions_labels, weight=actions_weights)
+        loss.backward()
+    return loss.detach(), {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+
 def ref_dpi_module(in_dim, kernel, ratios, scale_factor=True, beta_factor=False):
     """A bare reference Dynamic_Person_Inference (dynamic_infer_module.py:14-404)."""
     dm = ref_module("infer_module.dynamic_infer_module")

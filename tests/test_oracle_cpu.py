@@ -210,3 +210,23 @@ def test_oracle_autograd_reproduces_reference_backbone_gradients():
     assert sum(k.startswith("backbone.") for k in grads) == 26
     for k, d in fx["grads_ref"].items():
         _digest_close(grads[k], d)
+
+
+def test_oracle_autograd_reproduces_reference_stage1_gradients():
+    """Stage-1 training step (train_net.py:163-189) on Basenet_volleyball / VGG-16: autograd over the restatement ==
+    the reference model's own gradients (32 tensors: backbone, fc_emb, fc_actions, fc_activities)."""
+    import din_oracle as O
+    fx = torch.load(os.path.join(GOLDEN, "stage1grads_vgg16_T1.pt"))
+    pc = _pc_from(fx["config"])
+    bb = O.build_backbone(pc.backbone)
+    sd = O.make_basenet_state_dict(pc, seed=fx["seed"], backbone=bb)
+    assert abs(_checksum(sd.values()) - fx["weights_checksum"]) <= 1e-9 * fx["weights_checksum"]
+    O.load_backbone(bb, sd)
+    bb.eval()
+    batch = O.make_basenet_inputs(pc, fx["B"], seed=fx["seed"])
+    loss, grads = O.basenet_grads(bb, sd, pc, fx["actions_labels"], fx["activities_labels"], *batch,
+                                  actions_weights=fx["actions_weights"])
+    assert abs(float(loss) - float(fx["loss_ref"])) <= 1e-5
+    assert set(grads) == set(fx["grads_ref"]), set(grads) ^ set(fx["grads_ref"])
+    for k, d in fx["grads_ref"].items():
+        _digest_close(grads[k], d)

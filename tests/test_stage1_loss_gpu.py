@@ -130,3 +130,79 @@ def test_mean_axis(cuda):
     from din_b200 import ops
     x = torch.randn(3, 7, 45, device=cuda)
     assert (ops.mean_axis(x, 1) - x.mean(1)).abs().max().item() <= 1e-6
+
+
+def test_stage1_training_step(cuda):
+    """scripts/train_volleyball_stage1.py's step on the CUDA path: Basenet_volleyball (VGG-16, T = 1), activities CE +
+    class-weighted actions CE (train_net.py:163-189), everything trained.  vs autograd over the oracle with the same
+    dropout mask, and vs the REFERENCE model's gradient norms (fixture, dropout 0)."""
+    import base_model as BM
+    import din_oracle as O
+    from din_b200 import metrics
+    from test_oracle_cpu import _pc_from
+    fx = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stage1grads_vgg16_T1.pt"))
+    pc = _pc_from(fx["config"])
+    bb = O.build_backbone(pc.backbone)
+    sd = O.make_basenet_state_dict(pc, seed=fx["seed"], backbone=bb)
+    O.load_backbone(bb, sd)
+    bb.eval()
+    batch = O.make_basenet_inputs(pc, fx["B"], seed=fx["seed"])
+    w = fx["actions_weights"]
+
+    def rel_l2(a, b):
+        a, b = a.detach().double().cpu().flatten(), b.detach().double().cpu().flatten()
+        return float((a - b).norm() / max(float(b.norm()), 1e-30))
+
+    for p_drop in (0.0, 0.3):
+        cfg = _cfg(pc)
+        cfg.train_backbone, cfg.train_dropout_prob = True, p_drop
+        model = BM.Basenet_volleyball(cfg)
+        model.load_state_dict(sd, strict=True)
+        model = model.to(cuda).train()
+        torch.manual_seed(77)
+        actions, activities = model(tuple(t.to(cuda) for t in batch))
+        loss = metrics.cross_entropy(activities, fx["activities_labels"].to(cuda)) + \
+            cfg.actions_loss_weight * metrics.cross_entropy(actions, fx["actions_labels"].to(cuda), weight=w.to(cuda))
+        loss.backward()
+        torch.cuda.synchronize()
+        torch.manual_seed(77)
+        M = fx["B"] * pc.num_frames * pc.num_boxes
+        mask = (torch.rand((M, pc.num_features_boxes), device=cuda) >= p_drop).cpu() if p_drop > 0 else None
+        ref_loss, ref_grads = O.basenet_grads(bb, sd, pc, fx["actions_labels"], fx["activities_labels"], *batch,
+                                              train={"p": p_drop, "mask": mask}, actions_weights=w)
+        got = {n: q.grad for n, q in model.named_parameters() if q.grad is not None}
+        assert set(got) == set(ref_grads), set(got) ^ set(ref_grads)
+        worst = max(rel_l2(got[k], ref_grads[k]) for k in ref_grads)
+        print(f"\n[stage1 step p={p_drop}] loss {loss.item():.5f} vs {ref_loss.item():.5f}; worst rel-L2 {worst:.2e}; "
+              f"heads: {rel_l2(got['fc_actions.weight'], ref_grads['fc_actions.weight']):.2e} / "
+              f"{rel_l2(got['fc_activities.weight'], ref_grads['fc_activities.weight']):.2e}")
+        assert abs(loss.item() - ref_loss.item()) <= 2e-3 * max(1.0, abs(ref_loss.item()))
+        assert worst <= 2e-1, worst                       # fp16 backbone: see tests/test_backward_gpu.py (BB_TOL)
+        assert rel_l2(got["fc_actions.weight"], ref_grads["fc_actions.weight"]) <= 5e-3
+        if p_drop == 0.0:
+            for k, d in fx["grads_ref"].items():
+                l2 = float(got[k].double().norm())
+                assert abs(l2 - d["l2"]) <= 3e-2 * d["l2"], (k, l2, d["l2"])
+    # the frame mean over T (base_model.py:138-140) has its own backward path: T = 3, frozen backbone
+    pc3 = _pc("vgg16", (96, 160), num_frames=3, num_boxes=4)
+    sd3 = O.make_basenet_state_dict(pc3, seed=1)
+    cfg = _cfg(pc3)
+    cfg.train_backbone, cfg.train_dropout_prob = False, 0.0
+    model = BM.Basenet_volleyball(cfg)
+    model.load_state_dict(sd3, strict=True)
+    model = model.to(cuda).train()
+    for q in model.backbone.parameters():         # Basenet_volleyball itself never freezes (base_model.py:10-41)
+        q.requires_grad = False
+    batch3 = O.make_basenet_inputs(pc3, 2, seed=1)
+    a_lab = torch.arange(8) % pc3.num_actions
+    g_lab = torch.tensor([1, 2])
+    actions, activities = model(tuple(t.to(cuda) for t in batch3))
+    (metrics.cross_entropy(activities, g_lab.to(cuda)) + metrics.cross_entropy(actions, a_lab.to(cuda))).backward()
+    bb3 = O.build_backbone("vgg16")
+    O.load_backbone(bb3, sd3)
+    bb3.eval()
+    _, ref3 = O.basenet_grads(bb3, sd3, pc3, a_lab, g_lab, *batch3)
+    for k in ("fc_emb.weight", "fc_emb.bias", "fc_actions.weight", "fc_actions.bias", "fc_activities.weight"):
+        got = dict(model.named_parameters())[k].grad
+        assert rel_l2(got, ref3[k]) <= 3e-2, (k, rel_l2(got, ref3[k]))
+    assert all(q.grad is None for n, q in model.named_parameters() if n.startswith("backbone."))
