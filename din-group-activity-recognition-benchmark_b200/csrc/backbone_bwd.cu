@@ -10,6 +10,7 @@
 // vgg16.features (nn.ReLU(inplace), nn.MaxPool2d(2,2), nn.Conv2d; backbone.py:88-99) and prep_images
 // (utils.py:8-19) in `total_loss.backward()` (train_net_dynamic.py:220-224, cfg.train_backbone = True).
 #include <cfloat>
+#include <cstdlib>
 
 #include "din_common.cuh"
 #include "din_head.cuh"
@@ -94,6 +95,9 @@ scale_to_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, long lo
 // One thread per 8 channels of one full-resolution pixel.
 // ================================================================================================
 // All arithmetic on packed half2 (ncu on the first version: SM 86 % busy converting to fp32, DRAM 33 %).
+// One thread per element and a huge grid: two persistent grid-stride variants that also accumulated the bias
+// gradient on the way (1 and 4 elements per iteration) were measured 1.8x and 2x SLOWER than this kernel plus the
+// separate column-sum pass (their loads end up in per-element branches and serialise); dropped.
 __device__ __forceinline__ __half2 h2_gt(__half2 a, __half2 b) { return __hgt2(a, b); }   // 1.0 / 0.0 per lane
 
 __global__ void __launch_bounds__(256)
@@ -279,6 +283,13 @@ extern "C" int din_stem_wgrad(const void* x, int x_is_u8, const void* dz, float*
   DIN_CHECK_ARG(c_out == 64 && kh == 3 && kw == 3 && stride == 1 && pad == 1,
                 "din_stem_wgrad: only the VGG-16 stem (64 x 3x3, stride 1, pad 1) is implemented");
   DIN_CHECK_ARG((reinterpret_cast<uintptr_t>(dz) & 15) == 0, "din_stem_wgrad: dz must be 16-byte aligned");
+  {
+    // production path: tensor cores (stem_tc.cu).  DIN_STEM_WGRAD_SIMT=1 keeps the CUDA-core kernel below for A/B
+    // measurements -- still a kernel of this library.
+    const char* e = std::getenv("DIN_STEM_WGRAD_SIMT");
+    if (!(e && e[0] == '1'))
+      return din_stem_wgrad_tc_launch(x, x_is_u8, dz, dw, dbias, inv_scale, n, h, w, prep, static_cast<cudaStream_t>(stream));
+  }
   const int sms = din_num_sms();
   const long long strips = static_cast<long long>(n) * h * ((w + 127) / 128);
   long long grid = static_cast<long long>(sms > 0 ? sms : 148) * 3;

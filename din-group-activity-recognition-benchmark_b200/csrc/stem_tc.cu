@@ -377,6 +377,142 @@ int dispatch(StemParams& p, int c_out, int kh, int kw, int stride, cudaStream_t 
   return DIN_ERR_UNSUPPORTED;
 }
 
+// ================================================================================================
+// Stem weight / bias gradient on the tensor cores (VGG-16 features.0: 64 x 3 x 3x3, stride 1, pad 1):
+//     dW[co][k] += inv_scale * sum_pixels dZ[p][co] * im2col(prep(x))[p][k],  k = (c*3 + ky)*3 + kx;   db = column k = 27
+// The same GEMM shape as conv_wgrad_tcgen05.cu (K = the pixel index, both operands MN-major), per 128-pixel strip:
+//   A = dZ strip [128 pixels][64 channels] fp16, one TMA box in the 128B-swizzled layout; the upper half of M = 128
+//       reads a zero-filled region (LBO points at it), so no M = 64 data path is needed;
+//   B = the im2col rows of the strip [128 pixels][32] fp16 (27 taps, a ones column for the bias, 4 zero columns),
+//       written by the 128 threads in the canonical no-swizzle MN-major layout from the staged input patch --
+//       the forward stem's load_patch / stage_patch;
+//   D = [128 x 32] fp32 in TMEM, accumulated over ALL strips of a persistent CTA, flushed once with atomics.
+// Replaces the CUDA-core stem_wgrad_kernel (12 % of a training step in the first launch list).
+// ================================================================================================
+constexpr int kSwgABytes = 128 * 128;            // dZ strip tile
+constexpr int kSwgBBytes = 128 * 64;             // im2col tile
+constexpr size_t kSwgSmem = 1024 + 2 * kSwgABytes + kSwgBBytes + 64 + static_cast<size_t>(9) * 131 * 4;
+
+__device__ __forceinline__ uint64_t desc_mn_sw128_stem(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr >> 4) & 0x3FFFu);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1u) << 46;
+  d |= static_cast<uint64_t>(2u) << 61;          // SWIZZLE_128B
+  return d;
+}
+
+template <bool U8>
+__global__ void __launch_bounds__(kStemThreads)
+stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dz, const StemParams p, float* __restrict__ dw,
+                     float* __restrict__ db, const float* __restrict__ inv_scale) {
+  using Cfg = StemCfg<64, 3, 3, 1>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem(smem_raw, 1024);
+  uint8_t* a_s = smem;                                      // [128 pixel rows][128 B], TMA, SWIZZLE_128B
+  uint8_t* z_s = a_s + kSwgABytes;                          // zeros: the upper 64 rows of M
+  uint8_t* b_s = z_s + kSwgABytes;                          // im2col, no-swizzle MN-major
+  uint64_t* tma_bar = reinterpret_cast<uint64_t*>(b_s + kSwgBBytes);
+  uint64_t* mma_bar = tma_bar + 1;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  float* patch = reinterpret_cast<float*>(tmem_ptr_smem + 4);               // [9][kPitch]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < kSwgABytes / 16; i += kStemThreads) reinterpret_cast<uint4*>(z_s)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    tma_prefetch_desc(&tmap_dz);
+    mbar_init(tma_bar, 1);
+    mbar_init(mma_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<32>(tmem_ptr_smem);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+  // kind::f16, fp32 accumulate, A and B MN-major (bits 15, 16), M = 128, N = 32
+  constexpr uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>(32 >> 3) << 17) |
+                             (static_cast<uint32_t>(128 >> 4) << 24);
+
+  uint32_t phase = 0;
+  bool any = false;
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const TileCoord cur = decode_tile(p, tile);
+    if (tid == 0) {                                          // the previous strip's MMAs have retired (mma_bar wait)
+      mbar_arrive_expect_tx(tma_bar, kSwgABytes);
+      tma_load_4d(a_s, &tmap_dz, tma_bar, 0, cur.strip * 128, cur.oy, cur.img);
+    }
+    {
+      PatchRegs<64, 3, 3, 1, U8> regs;
+      load_patch<64, 3, 3, 1, U8>(p, cur, tid, regs);
+      stage_patch<64, 3, 3, 1, U8>(p, tid, patch, regs);
+    }
+    __syncthreads();
+    {
+      // im2col row of pixel `tid`: 32 fp16 = four 16-byte chunks; chunk j of pixel p lives at
+      // (p / 8) * 512 + j * 128 + (p % 8) * 16   (8-pixel groups 512 B apart = LBO, 8-column chunks 128 B apart = SBO)
+      const float* prow = patch + tid;
+      uint8_t* dst = b_s + (tid >> 3) * 512 + (tid & 7) * 16;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __align__(16) __half2 hv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float f[2];
+#pragma unroll
+          for (int z = 0; z < 2; ++z) {
+            const int k = j * 8 + 2 * e + z;
+            f[z] = (k < 27) ? prow[(k / 3) * Cfg::kPitch + (k % 3)] : (k == 27 ? 1.0f : 0.0f);
+          }
+          hv[e] = __floats2half2_rn(f[0], f[1]);
+        }
+        *reinterpret_cast<uint4*>(dst + j * 128) = *reinterpret_cast<const uint4*>(hv);
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (warp == 0) {
+      mbar_wait(tma_bar, phase);
+      tc_fence_after_sync();
+      const uint32_t a_addr = smem_u32(a_s), b_addr = smem_u32(b_s);
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {                    // 16 pixels per MMA
+          const uint64_t ad = desc_mn_sw128_stem(a_addr + ks * 2048, kSwgABytes, 1024);
+          const uint64_t bd = desc_noswz(b_addr + ks * 1024, 512, 128);
+          umma_f16_ss(tmem_base, ad, bd, idesc, (any || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(mma_bar);
+      }
+      __syncwarp();
+    }
+    any = true;
+    mbar_wait(mma_bar, phase);                               // a_s, b_s and the patch may be rebuilt
+    phase ^= 1u;
+    tc_fence_after_sync();
+  }
+
+  // ---- flush: TMEM lanes 0..63 = output channels, columns = taps (27 = bias)
+  if (any && warp < 2) {
+    const float scl = inv_scale ? __ldg(inv_scale) : 1.0f;
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16), v);
+    tmem_ld_wait();
+    const int co = warp * 32 + lane;
+#pragma unroll
+    for (int k = 0; k < 27; ++k) atomicAdd(dw + co * 27 + k, __uint_as_float(v[k]) * scl);
+    if (db != nullptr) atomicAdd(db + co, __uint_as_float(v[27]) * scl);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc<32>(tmem_base);
+  }
+}
+
 }  // namespace
 
 // x_is_u8 == 0: x is fp32 NCHW [n,3,h,w];  != 0: x is uint8 NHWC [n,h,w,3] (the decoded frame as the loader
@@ -399,4 +535,41 @@ int din_stem_tc_launch(const void* x, int x_is_u8, const float* w, const float* 
   fastdiv(static_cast<uint32_t>(p.strips_per_row), &p.fd_mul, &p.fd_shr);
   fastdiv(static_cast<uint32_t>(p.oh), &p.fo_mul, &p.fo_shr);
   return x_is_u8 ? dispatch<true>(p, c_out, kh, kw, stride, st) : dispatch<false>(p, c_out, kh, kw, stride, st);
+}
+
+// Tensor-core stem weight gradient (see stem_wgrad_tc_kernel); arguments validated by din_stem_wgrad.
+int din_stem_wgrad_tc_launch(const void* x, int x_is_u8, const void* dz, float* dw, float* dbias, const float* inv_scale,
+                             int n, int h, int w_in, int prep, cudaStream_t st) {
+  StemParams p{};
+  p.x = x; p.n = n; p.h = h; p.w_in = w_in; p.oh = h; p.ow = w_in; p.pad = 1; p.prep = prep;
+  p.strips_per_row = (p.ow + 127) / 128;
+  const long long tiles = static_cast<long long>(n) * p.oh * p.strips_per_row;
+  if (tiles >= INT32_MAX) return din_set_error(DIN_ERR_INVALID_ARG, "din_stem_wgrad: too many tiles");
+  p.num_tiles = static_cast<int>(tiles);
+  fastdiv(static_cast<uint32_t>(p.strips_per_row), &p.fd_mul, &p.fd_shr);
+  fastdiv(static_cast<uint32_t>(p.oh), &p.fo_mul, &p.fo_shr);
+  CUtensorMap tdz;
+  {
+    const uint64_t dims[4] = {64, static_cast<uint64_t>(w_in), static_cast<uint64_t>(h), static_cast<uint64_t>(n)};
+    const uint64_t strides[4] = {2, 128, 128ull * w_in, 128ull * w_in * h};
+    const uint32_t box[4] = {64, 128, 1, 1};
+    const uint32_t es[4] = {1, 1, 1, 1};
+    int rc = din_encode_tmap(&tdz, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(dz), dims, strides, box, es,
+                             CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != DIN_OK) return rc;
+  }
+  const int sms = din_num_sms();
+  long long grid = static_cast<long long>(sms > 0 ? sms : 148) * 4;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  if (x_is_u8) {
+    DIN_CHECK_CUDA(cudaFuncSetAttribute(stem_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(kSwgSmem)));
+    stem_wgrad_tc_kernel<true><<<static_cast<int>(grid), kStemThreads, kSwgSmem, st>>>(tdz, p, dw, dbias, inv_scale);
+  } else {
+    DIN_CHECK_CUDA(cudaFuncSetAttribute(stem_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(kSwgSmem)));
+    stem_wgrad_tc_kernel<false><<<static_cast<int>(grid), kStemThreads, kSwgSmem, st>>>(tdz, p, dw, dbias, inv_scale);
+  }
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
 }

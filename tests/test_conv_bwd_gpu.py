@@ -87,9 +87,13 @@ def test_dgrad_is_forward_kernel_on_rotated_filter(cuda):
     assert (dx.float() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("simt", [False, True], ids=["tensor", "simt"])
 @pytest.mark.parametrize("u8", [False, True])
-def test_stem_wgrad_matches_torch(cuda, u8):
+def test_stem_wgrad_matches_torch(cuda, u8, simt, monkeypatch):
+    """Default = the tcgen05 kernel (fp16 im2col operands: 1e-3); DIN_STEM_WGRAD_SIMT=1 = the CUDA-core kernel kept
+    for A/B measurements (fp32 patches)."""
     from din_b200 import ops
+    monkeypatch.setenv("DIN_STEM_WGRAD_SIMT", "1" if simt else "0")
     g = torch.Generator().manual_seed(5)
     n, h, w = 2, 37, 150
     raw = torch.randint(0, 256, (n, 3, h, w), generator=g).float().to(cuda)
