@@ -73,7 +73,7 @@ int din_num_sms() {
 
 extern "C" {
 
-int din_abi_version(void) { return 1; }
+int din_abi_version(void) { return 2; }   // 2: + uint8 ingest, loss / metrics, backward entry points
 
 const char* din_last_error_string(void) { return g_err; }
 

@@ -28,6 +28,7 @@ def _lib():
 def test_header_declares_something():
     names = _declared()
     assert "din_conv2d_nhwc_f16" in names and "din_dynamic_infer_f32" in names and len(names) >= 12
+    assert {"din_conv2d_wgrad_nhwc_f16", "din_dynamic_infer_bwd_f32", "din_stem_conv_nhwc_u8", "din_ce_metrics_f32"} <= set(names)
 
 
 def test_library_exports_every_declared_symbol():
@@ -52,7 +53,7 @@ def test_ctypes_table_matches_header():
 def test_loads_and_validates_without_gpu():
     lib = _lib()
     h = lib.load()
-    assert h.din_abi_version() == 1
+    assert h.din_abi_version() == 2
     # invalid arguments are rejected before any CUDA call, with a message
     d = lib.DinConvDesc(n=1, h=8, w=8, c_in=44, x_c_stride=48, c_out=64, y_c_stride=64, kh=3, kw=3, stride=1,
                         pad_h=1, pad_w=1, relu=1, out_f32=0, pool2=0, w_split=1)

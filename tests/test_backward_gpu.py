@@ -504,3 +504,29 @@ def test_gradient_of_batch_is_mean_of_per_clip_gradients(cuda):
         assert _rel_l2(again[k], full[k]) <= 5e-3, ("run-to-run", k, _rel_l2(again[k], full[k]))
         # the dynamic loss scale differs between the runs (per-step max|dfm|), hence fp16 rounding differs: 2e-3
         assert _rel_l2(0.5 * (g0[k] + g1[k]), full[k]) <= 1e-2, (k, _rel_l2(0.5 * (g0[k] + g1[k]), full[k]))
+
+
+def test_training_reduces_loss_on_a_fixed_batch(cuda):
+    """End-to-end sanity of the gradients' SIGN and scale: 12 Adam steps on one fixed batch (everything trained, dropout
+    on, as train_net_dynamic.py:170-224 runs them) must overfit it."""
+    import din_oracle as O
+    from din_b200 import metrics
+    pc = _pc("vgg16", (96, 160), num_frames=3, num_boxes=4)
+    sd = O.make_state_dict(pc, seed=5)
+    batch = tuple(t.to(cuda) for t in O.make_inputs(pc, 4, seed=5))
+    labels = torch.tensor([0, 3, 5, 7], device=cuda)
+    model, _ = _model_and_cfg(cuda, pc, sd, 0.3)
+    for q in model.backbone.parameters():
+        q.requires_grad = True
+    opt = torch.optim.Adam([q for q in model.parameters() if q.requires_grad], lr=2e-4)
+    torch.manual_seed(0)
+    losses = []
+    for _ in range(12):
+        loss = metrics.cross_entropy(model(batch)["activities"], labels)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    print(f"\n[overfit] loss {losses[0]:.3f} -> {losses[-1]:.3f}  ({[round(v, 2) for v in losses]})")
+    assert all(torch.isfinite(torch.tensor(losses)))
+    assert min(losses[-3:]) < 0.5 * losses[0], losses
