@@ -104,6 +104,173 @@ __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
   return static_cast<uint64_t>(lo) | (static_cast<uint64_t>(hi) << 32);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Epilogue warps (shared by the one-CTA and the CTA-pair kernels): TMEM -> registers -> bias / residual / ReLU /
+// 2x2 max-pool -> global.
+// ------------------------------------------------------------------------------------------------
+template <int BN, bool TWO_CTA>
+__device__ __forceinline__ void conv_epilogue_warps(const ConvKParams& p, uint32_t tmem_base, uint8_t* epi_scratch,
+                                                    const float* bias_s, uint64_t* tmem_full, uint64_t* tmem_empty,
+                                                    int warp, int lane, int tile_first, int tile_limit,
+                                                    int tile_step, int cta_rank) {
+  {
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    // warp e = warp - 4: TMEM lane quadrant q = e & 3 (a warp may only touch lanes 32*(warp%4)..+31), and
+    // the two warps of a quadrant split the tile's 32-column chunks (even / odd) between them.
+    const int q = warp & 3;
+    const int chunk_sel = (warp - 4) >> 2;
+    uint8_t* scratch = epi_scratch + (warp - 4) * kEpiScratch;
+    // Store side of the transpose: after the scratch round-trip, lane l writes 16-byte unit (l & 3) of
+    // pixel slot (l >> 2) + 8*k (k = 0..3) — i.e. four lanes write one pixel's 64 contiguous bytes, so
+    // every global store instruction covers full 32-byte sectors (no partial-sector read-modify-write).
+    // With the fused pool only 8 lanes of the warp hold a pooled pixel: one store instruction.
+    const int unit = lane & 3;
+    int src_lane[4];   // which lane's (= which tile pixel's) row this lane stores in round k
+    int n_rounds;
+    if (p.pool2) {
+      const int i = lane >> 2, half_tw = p.tw >> 1;
+      src_lane[0] = (i / half_tw) * 2 * p.tw + (i % half_tw) * 2;
+      src_lane[1] = src_lane[2] = src_lane[3] = 0;
+      n_rounds = 1;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) src_lane[k] = (lane >> 2) + 8 * k;
+      n_rounds = 4;
+    }
+    int it = 0;
+    for (int ti = tile_first; ti < tile_limit; ti += tile_step, ++it) {
+      // one CTA per tile: ti is the tile.  CTA pair: ti is the pair index, this CTA's tile is 2*ti + rank and may
+      // lie beyond the last tile (odd count): its operands were zero-filled by the TMA unit, nothing is stored.
+      const int tile = TWO_CTA ? 2 * ti + cta_rank : ti;
+      const bool tile_ok = tile < p.num_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      const int mt = fdiv(tile, p.fd_ntn);
+      const int nt = tile - mt * p.n_tiles_n;
+      const int img = fdiv(mt, p.fd_tpi);
+      const int r = mt - img * p.tiles_per_img;
+      const int tyi = fdiv(r, p.fd_tx);
+      const int txi = r - tyi * p.tiles_x;
+      const int n0 = nt * BN;
+      // own pixel (residual / fp32 path) and the pixels this lane stores after the transpose
+      const int m_own = q * 32 + lane;
+      const int oy_own = tyi * p.th + (m_own >> p.tw_log2), ox_own = txi * p.tw + (m_own & (p.tw - 1));
+      const bool valid_own = tile_ok && (oy_own < p.oh) && (ox_own < p.ow);
+      const size_t pix_own = (static_cast<size_t>(img) * p.oh + oy_own) * p.ow + ox_own;
+      size_t st_pix[4];
+      bool st_valid[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int m = q * 32 + src_lane[k];
+        const int oy = tyi * p.th + (m >> p.tw_log2), ox = txi * p.tw + (m & (p.tw - 1));
+        if (p.pool2) {
+          const int poh = p.oh >> 1, pow_ = p.ow >> 1;
+          st_valid[k] = tile_ok && (k == 0) && ((oy >> 1) < poh) && ((ox >> 1) < pow_);
+          st_pix[k] = (static_cast<size_t>(img) * poh + (oy >> 1)) * pow_ + (ox >> 1);
+        } else {
+          st_valid[k] = tile_ok && (oy < p.oh) && (ox < p.ow);
+          st_pix[k] = (static_cast<size_t>(img) * p.oh + oy) * p.ow + ox;
+        }
+      }
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(taddr + 32 * chunk_sel, v);
+#pragma unroll 1
+      for (int c0 = 32 * chunk_sel; c0 < BN; c0 += 64) {
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (c0 + 64 < BN) tmem_ld_32x32b_x32(taddr + c0 + 64, v);   // prefetch this warp's next chunk
+        const int col0 = n0 + c0;
+        if (col0 >= p.c_out) continue;   // warp-uniform
+        {
+          const float4* bs = reinterpret_cast<const float4*>(bias_s + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = bs[j];
+            f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+          }
+        }
+        if (p.residual != nullptr && valid_own) {
+          const __half* rp = p.residual + pix_own * p.y_c_stride + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (col0 + j < p.c_out) {
+              const uint4 rr = __ldg(reinterpret_cast<const uint4*>(rp + j));
+              const __half2* h2 = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 t2 = __half22float2(h2[e]);
+                f[j + 2 * e] += t2.x;
+                f[j + 2 * e + 1] += t2.y;
+              }
+            }
+          }
+        }
+        if (p.out_f32) {
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+          }
+          if (valid_own) {
+            float* yp = reinterpret_cast<float*>(p.y) + pix_own * p.y_c_stride + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (col0 + j < p.c_out)
+                *reinterpret_cast<float4*>(yp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            }
+          }
+          continue;
+        }
+        __half2 h[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {   // ReLU fused into the conversion (cvt.rn.relu.f16x2.f32)
+          const uint32_t u = pack_half2(f[2 * e], f[2 * e + 1], p.relu != 0);
+          h[e] = *reinterpret_cast<const __half2*>(&u);
+        }
+        if (p.pool2) {
+          // 2x2 window = lanes {m, m^1, m^tw, m^tw^1}: all inside this warp because tw <= 16.
+          // max commutes with the (monotonic) fp16 rounding, so pooling the rounded values is exact.
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            uint32_t u = *reinterpret_cast<uint32_t*>(&h[e]);
+            uint32_t o1 = __shfl_xor_sync(0xffffffffu, u, 1);
+            h[e] = __hmax2(h[e], *reinterpret_cast<__half2*>(&o1));
+            u = *reinterpret_cast<uint32_t*>(&h[e]);
+            uint32_t o2 = __shfl_xor_sync(0xffffffffu, u, p.tw);
+            h[e] = __hmax2(h[e], *reinterpret_cast<__half2*>(&o2));
+          }
+        }
+        // transpose through the warp's scratch: 80-byte row pitch makes both sides bank-conflict free
+        {
+          uint4* wr = reinterpret_cast<uint4*>(scratch + lane * kEpiPitch);
+#pragma unroll
+          for (int u4 = 0; u4 < 4; ++u4) wr[u4] = *reinterpret_cast<uint4*>(&h[4 * u4]);
+        }
+        __syncwarp();
+        if (col0 + unit * 8 < p.c_out) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (k < n_rounds && st_valid[k]) {
+              const uint4 o = *reinterpret_cast<const uint4*>(scratch + src_lane[k] * kEpiPitch + unit * 16);
+              __half* yp = reinterpret_cast<__half*>(p.y) + st_pix[k] * p.y_c_stride + col0 + unit * 8;
+              *reinterpret_cast<uint4*>(yp) = o;
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before_sync();
+      if constexpr (TWO_CTA) mbar_arrive_cluster(&tmem_empty[acc], 0);   // the leader CTA's barrier (it issues the MMAs)
+      else mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+}
+
 // TB3 > 0 selects the statically unrolled issue path for 3x3 HALO convolutions (pitch 10, TB3 taps per weight
 // stage, no weight split): every descriptor offset is an immediate.
 template <int BN, int TB3>
@@ -309,155 +476,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue (8 warps)
-    // warp e = warp - 4: TMEM lane quadrant q = e & 3 (a warp may only touch lanes 32*(warp%4)..+31), and
-    // the two warps of a quadrant split the tile's 32-column chunks (even / odd) between them.
-    const int q = warp & 3;
-    const int chunk_sel = (warp - 4) >> 2;
-    uint8_t* scratch = epi_scratch + (warp - 4) * kEpiScratch;
-    // Store side of the transpose: after the scratch round-trip, lane l writes 16-byte unit (l & 3) of
-    // pixel slot (l >> 2) + 8*k (k = 0..3) — i.e. four lanes write one pixel's 64 contiguous bytes, so
-    // every global store instruction covers full 32-byte sectors (no partial-sector read-modify-write).
-    // With the fused pool only 8 lanes of the warp hold a pooled pixel: one store instruction.
-    const int unit = lane & 3;
-    int src_lane[4];   // which lane's (= which tile pixel's) row this lane stores in round k
-    int n_rounds;
-    if (p.pool2) {
-      const int i = lane >> 2, half_tw = p.tw >> 1;
-      src_lane[0] = (i / half_tw) * 2 * p.tw + (i % half_tw) * 2;
-      src_lane[1] = src_lane[2] = src_lane[3] = 0;
-      n_rounds = 1;
-    } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) src_lane[k] = (lane >> 2) + 8 * k;
-      n_rounds = 4;
-    }
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1u;
-      const int mt = fdiv(tile, p.fd_ntn);
-      const int nt = tile - mt * p.n_tiles_n;
-      const int img = fdiv(mt, p.fd_tpi);
-      const int r = mt - img * p.tiles_per_img;
-      const int tyi = fdiv(r, p.fd_tx);
-      const int txi = r - tyi * p.tiles_x;
-      const int n0 = nt * BN;
-      // own pixel (residual / fp32 path) and the pixels this lane stores after the transpose
-      const int m_own = q * 32 + lane;
-      const int oy_own = tyi * p.th + (m_own >> p.tw_log2), ox_own = txi * p.tw + (m_own & (p.tw - 1));
-      const bool valid_own = (oy_own < p.oh) && (ox_own < p.ow);
-      const size_t pix_own = (static_cast<size_t>(img) * p.oh + oy_own) * p.ow + ox_own;
-      size_t st_pix[4];
-      bool st_valid[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int m = q * 32 + src_lane[k];
-        const int oy = tyi * p.th + (m >> p.tw_log2), ox = txi * p.tw + (m & (p.tw - 1));
-        if (p.pool2) {
-          const int poh = p.oh >> 1, pow_ = p.ow >> 1;
-          st_valid[k] = (k == 0) && ((oy >> 1) < poh) && ((ox >> 1) < pow_);
-          st_pix[k] = (static_cast<size_t>(img) * poh + (oy >> 1)) * pow_ + (ox >> 1);
-        } else {
-          st_valid[k] = (oy < p.oh) && (ox < p.ow);
-          st_pix[k] = (static_cast<size_t>(img) * p.oh + oy) * p.ow + ox;
-        }
-      }
-
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after_sync();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(taddr + 32 * chunk_sel, v);
-#pragma unroll 1
-      for (int c0 = 32 * chunk_sel; c0 < BN; c0 += 64) {
-        tmem_ld_wait();
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (c0 + 64 < BN) tmem_ld_32x32b_x32(taddr + c0 + 64, v);   // prefetch this warp's next chunk
-        const int col0 = n0 + c0;
-        if (col0 >= p.c_out) continue;   // warp-uniform
-        {
-          const float4* bs = reinterpret_cast<const float4*>(bias_s + col0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = bs[j];
-            f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
-          }
-        }
-        if (p.residual != nullptr && valid_own) {
-          const __half* rp = p.residual + pix_own * p.y_c_stride + col0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (col0 + j < p.c_out) {
-              const uint4 rr = __ldg(reinterpret_cast<const uint4*>(rp + j));
-              const __half2* h2 = reinterpret_cast<const __half2*>(&rr);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 t2 = __half22float2(h2[e]);
-                f[j + 2 * e] += t2.x;
-                f[j + 2 * e + 1] += t2.y;
-              }
-            }
-          }
-        }
-        if (p.out_f32) {
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-          }
-          if (valid_own) {
-            float* yp = reinterpret_cast<float*>(p.y) + pix_own * p.y_c_stride + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (col0 + j < p.c_out)
-                *reinterpret_cast<float4*>(yp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            }
-          }
-          continue;
-        }
-        __half2 h[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {   // ReLU fused into the conversion (cvt.rn.relu.f16x2.f32)
-          const uint32_t u = pack_half2(f[2 * e], f[2 * e + 1], p.relu != 0);
-          h[e] = *reinterpret_cast<const __half2*>(&u);
-        }
-        if (p.pool2) {
-          // 2x2 window = lanes {m, m^1, m^tw, m^tw^1}: all inside this warp because tw <= 16.
-          // max commutes with the (monotonic) fp16 rounding, so pooling the rounded values is exact.
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            uint32_t u = *reinterpret_cast<uint32_t*>(&h[e]);
-            uint32_t o1 = __shfl_xor_sync(0xffffffffu, u, 1);
-            h[e] = __hmax2(h[e], *reinterpret_cast<__half2*>(&o1));
-            u = *reinterpret_cast<uint32_t*>(&h[e]);
-            uint32_t o2 = __shfl_xor_sync(0xffffffffu, u, p.tw);
-            h[e] = __hmax2(h[e], *reinterpret_cast<__half2*>(&o2));
-          }
-        }
-        // transpose through the warp's scratch: 80-byte row pitch makes both sides bank-conflict free
-        {
-          uint4* wr = reinterpret_cast<uint4*>(scratch + lane * kEpiPitch);
-#pragma unroll
-          for (int u4 = 0; u4 < 4; ++u4) wr[u4] = *reinterpret_cast<uint4*>(&h[4 * u4]);
-        }
-        __syncwarp();
-        if (col0 + unit * 8 < p.c_out) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (k < n_rounds && st_valid[k]) {
-              const uint4 o = *reinterpret_cast<const uint4*>(scratch + src_lane[k] * kEpiPitch + unit * 16);
-              __half* yp = reinterpret_cast<__half*>(p.y) + st_pix[k] * p.y_c_stride + col0 + unit * 8;
-              *reinterpret_cast<uint4*>(yp) = o;
-            }
-          }
-        }
-        __syncwarp();
-      }
-      tc_fence_before_sync();
-      mbar_arrive(&tmem_empty[acc]);
-    }
+    conv_epilogue_warps<BN, false>(p, tmem_base, epi_scratch, bias_s, tmem_full, tmem_empty, warp, lane, blockIdx.x,
+                                   p.num_tiles, gridDim.x, 0);
   }
 
   tc_fence_before_sync();
@@ -466,6 +486,190 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     tc_fence_after_sync();
     tmem_dealloc<kTmemCols>(tmem_base);
   }
+}
+
+// ================================================================================================
+// CTA-pair variant for the narrow-N 3x3 layers (c_out = 64 / 128: VGG conv1_2, conv2_x, ResNet layer1/2).
+// With BN = 64 a single-CTA MMA (128 x 64 x 16) keeps the tensor pipe busy for 32 cycles but reads 6 KB of
+// operands from shared memory (48 cycles at 128 B/clk) and costs one issue slot: ncu showed 41 % (BN = 64) and
+// 60-66 % (BN = 128) tensor-pipe activity with the issuing thread as the limit.  Here two CTAs of a cluster (one
+// TPC) work on two adjacent pixel tiles against the SAME weights with ONE tcgen05.mma.cta_group::2 (M = 256) per
+// step: half the MMA instructions per SM, and each CTA stages only half of every weight tile.
+// Differences from conv_igemm_kernel (static 3x3 HALO path only, one N tile):
+//   * both CTAs run the same producers on their own tile / their half of the weight rows; every TMA completes on
+//     the LEADER's full barrier (it expects the bytes of both CTAs);
+//   * only the leader's MMA warp issues; tcgen05.commit multicasts to the empty / tmem_full barriers of both CTAs;
+//   * each CTA's epilogue drains its own TMEM half and arrives on the leader's tmem_empty barrier.
+// ================================================================================================
+template <int BN, int TB3>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                       const ConvKParams p) {
+  constexpr int kBHalfBytes = (BN / 2) * kBK * 2;            // this CTA's half of one tap's weight tile
+  constexpr int kTmemCols = (2 * BN <= 128) ? 128 : 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem(smem_raw, 1024);
+  uint8_t* smem_a = smem;
+  constexpr int b_stage_bytes = TB3 * kBHalfBytes;
+  uint8_t* smem_b = smem + p.n_a_stages * p.a_stage_bytes;
+  uint8_t* epi_scratch = smem_b + p.n_b_stages * b_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_scratch + kNumEpiWarps * kEpiScratch);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + kMaxStages;
+  uint64_t* b_full = a_empty + kMaxStages;
+  uint64_t* b_empty = b_full + kMaxStages;
+  uint64_t* tmem_full = b_empty + kMaxStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(tmem_ptr_smem + 4 + 64);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int pair_first = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
+  const int n_pairs = (p.num_tiles + 1) >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < p.n_a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < p.n_b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 2 * 32 * kNumEpiWarps); }
+    fence_mbar_init();
+  }
+  if (warp >= 4) {
+    for (int c = threadIdx.x - 128; c < BN; c += 32 * kNumEpiWarps)
+      bias_s[c] = (p.bias != nullptr && c < p.c_out) ? __ldg(p.bias + c) : 0.0f;
+  }
+  if (warp == 1) tmem_alloc_2cta<kTmemCols>(tmem_ptr_smem);
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();                                        // the peer's barriers exist before anything signals them
+  tc_fence_after_sync();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ A producer: this CTA's tile of the pair
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pi = pair_first; pi < n_pairs; pi += pair_step) {
+        const int mt = 2 * pi + rank;                        // beyond the last tile: img >= n, zero-filled
+        const int img = fdiv(mt, p.fd_tpi);
+        const int r = mt - img * p.tiles_per_img;
+        const int tyi = fdiv(r, p.fd_tx);
+        const int txi = r - tyi * p.tiles_x;
+        const int ix0 = txi * p.tw - p.pad_w;
+        const int iy0 = tyi * p.th - p.pad_h;
+        for (int g = 0; g < p.n_cblk; ++g) {
+          mbar_wait(&a_empty[stage], phase ^ 1u);
+          if (rank == 0) mbar_arrive_expect_tx(&a_full[stage], 2u * p.a_tx_bytes);
+          tma_load_4d_2cta(smem_a + stage * p.a_stage_bytes, &tmap_a, &a_full[stage], g * kBK, ix0, iy0, img);
+          if (++stage == p.n_a_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ B producer: this CTA's half of the weight rows
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int n0 = rank * (BN / 2);
+      for (int pi = pair_first; pi < n_pairs; pi += pair_step) {
+        for (int g = 0; g < p.n_cblk; ++g) {
+#pragma unroll 1
+          for (int bg = 0; bg < 9 / TB3; ++bg) {
+            mbar_wait(&b_empty[stage], phase ^ 1u);
+            if (rank == 0) mbar_arrive_expect_tx(&b_full[stage], 2u * TB3 * kBHalfBytes);
+            uint8_t* sb = smem_b + stage * b_stage_bytes;
+#pragma unroll
+            for (int tt = 0; tt < TB3; ++tt)
+              tma_load_2d_2cta(sb + tt * kBHalfBytes, &tmap_b, &b_full[stage], g * kBK + (bg * TB3 + tt) * p.c_in, n0);
+            if (++stage == p.n_b_stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer: the leader CTA only
+    if (rank == 0) {
+      const bool leader = elect_one();
+      constexpr uint32_t idesc = umma_idesc_f16_f32(256, BN);
+      const uint32_t a_hi = desc_hi(static_cast<uint32_t>(p.pitch_rows) * 128u);
+      const uint32_t b_hi = desc_hi(1024u);
+      const uint32_t a_lo0 = desc_lo(smem_u32(smem_a));
+      const uint32_t b_lo0 = desc_lo(smem_u32(smem_b));
+      const uint32_t a_step = static_cast<uint32_t>(p.a_stage_bytes) >> 4;
+      constexpr uint32_t b_step = static_cast<uint32_t>(b_stage_bytes) >> 4;
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int it = 0;
+      for (int pi = pair_first; pi < n_pairs; pi += pair_step, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1u) ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        uint32_t accum = 0;
+        for (int g = 0; g < p.n_cblk; ++g) {
+          mbar_wait(&a_full[sa], pa);
+          const uint32_t a_lo = a_lo0 + sa * a_step;
+#pragma unroll
+          for (int bg = 0; bg < 9 / TB3; ++bg) {
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after_sync();
+            const uint32_t b_lo = b_lo0 + sb * b_step;
+            if (leader) {
+#pragma unroll
+              for (int tt = 0; tt < TB3; ++tt) {
+                const int t = bg * TB3 + tt;
+                const uint32_t al = a_lo + static_cast<uint32_t>(((t / 3) * 10 + (t % 3)) * 8);
+                const uint32_t bl = b_lo + static_cast<uint32_t>(tt * (kBHalfBytes >> 4));
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k)
+                  umma_f16_ss_2cta(d_tmem, desc64(al + 2u * k, a_hi), desc64(bl + 2u * k, b_hi), idesc,
+                                   (bg == 0 && tt == 0 && k == 0) ? accum : 1u);
+              }
+              umma_commit_2cta(&b_empty[sb]);
+            }
+            accum = 1;
+            if (++sb == p.n_b_stages) { sb = 0; pb ^= 1u; }
+          }
+          if (leader) {
+            umma_commit_2cta(&a_empty[sa]);
+            if (g == p.n_cblk - 1) umma_commit_2cta(&tmem_full[acc]);
+          }
+          if (++sa == p.n_a_stages) { sa = 0; pa ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    conv_epilogue_warps<BN, true>(p, tmem_base, epi_scratch, bias_s, tmem_full, tmem_empty, warp, lane, pair_first,
+                                  n_pairs, pair_step, rank);
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();                                        // nobody leaves while the peer may still signal it
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc_2cta<kTmemCols>(tmem_base);
+  }
+}
+
+template <int BN, int TB3>
+int launch_conv_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const ConvKParams& p, int grid, size_t smem,
+                     cudaStream_t st) {
+  static thread_local int attr_dev = -1;
+  int dev = 0;
+  DIN_CHECK_CUDA(cudaGetDevice(&dev));
+  if (attr_dev != dev) {
+    DIN_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_2cta_kernel<BN, TB3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kSmemBudget + kNumEpiWarps * kEpiScratch + 4096 + 8192));
+    attr_dev = dev;
+  }
+  conv_igemm_2cta_kernel<BN, TB3><<<grid, kNumThreads, smem, st>>>(ta, tb, p);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
 }
 
 template <int BN, int TB3>
@@ -645,11 +849,18 @@ extern "C" int din_conv2d_nhwc_f16(const DinConvDesc* d, const void* x, const vo
     box_h = static_cast<uint32_t>((p.th - 1) * d->stride + 1);
   }
   DIN_CHECK_ARG(box_w <= 256 && box_h <= 256, "din_conv2d_nhwc_f16: TMA box too large");
-  const int b_bytes = bn * kBK * 2;
   const bool static3 = halo && d->kh == 3 && d->kw == 3 && p.split == 1 && !(variant >= 0 && (variant & 8));
+  // CTA pair (cta_group::2, M = 256) for the narrow-N 3x3 layers: see conv_igemm_2cta_kernel.  DIN_CONV_2CTA=0
+  // keeps them on the one-CTA kernel (A/B measurements).
+  bool two_cta = static3 && (bn == 64 || bn == 128) && p.n_tiles_n == 1 && p.num_tiles >= 2;
+  {
+    const char* e = std::getenv("DIN_CONV_2CTA");
+    if (e && e[0] == '0') two_cta = false;
+  }
+  const int b_bytes = (two_cta ? bn / 2 : bn) * kBK * 2;     // bytes of one tap's weight tile staged by ONE CTA
   if (halo) {
     // several taps per weight stage: fewer barrier round-trips per MMA for the narrow-N layers
-    p.tb = 40960 / b_bytes;
+    p.tb = 40960 / (bn * kBK * 2);
     if (p.tb < 1) p.tb = 1;
     if (p.tb > d->kh * d->kw * p.split) p.tb = d->kh * d->kw * p.split;
     if (static3) p.tb = bn <= 64 ? 9 : (bn <= 128 ? 3 : 1);   // must match the TB3 template arguments below
@@ -686,7 +897,7 @@ extern "C" int din_conv2d_nhwc_f16(const DinConvDesc* d, const void* x, const vo
     const uint64_t ktot = static_cast<uint64_t>(d->kh) * d->kw * p.c_in;   // packed with the padded c_in
     const uint64_t dims[2] = {ktot * p.split, static_cast<uint64_t>(d->c_out)};
     const uint64_t strides[2] = {2, ktot * p.split * 2};
-    const uint32_t box[2] = {static_cast<uint32_t>(kBK), static_cast<uint32_t>(bn)};
+    const uint32_t box[2] = {static_cast<uint32_t>(kBK), static_cast<uint32_t>(two_cta ? bn / 2 : bn)};
     const uint32_t es[2] = {1, 1};
     int rc = din_encode_tmap(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w_packed), dims, strides,
                              box, es, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -696,6 +907,12 @@ extern "C" int din_conv2d_nhwc_f16(const DinConvDesc* d, const void* x, const vo
   DIN_CHECK_ARG(sms > 0, "din_conv2d_nhwc_f16: no CUDA device");
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (two_cta) {
+    const int pairs = (p.num_tiles + 1) / 2;
+    int grid2 = 2 * (pairs < sms / 2 ? pairs : sms / 2);     // whole clusters of 2
+    return bn == 64 ? launch_conv_2cta<64, 9>(ta, tb, p, grid2, smem, st)
+                    : launch_conv_2cta<128, 3>(ta, tb, p, grid2, smem, st);
+  }
   if (static3) {
     switch (bn) {
       case 256: return launch_conv<256, 1>(ta, tb, p, grid, smem, st);
