@@ -71,6 +71,7 @@ struct ConvKParams {
   int per_row_loads;          // 1: one TMA box per halo row (padded pitch); 0: one box per halo
   int use_base_offset;        // descriptor base_offset = (start >> 7) & 7
   int a_stage_bytes, n_a_stages, n_b_stages;
+  int b_resident;             // CTA-pair kernel: the whole packed weight stays in shared memory (loaded once per CTA)
   int tb;                     // weight tiles per B stage
   int split;                  // 1, or 2: weights stored as hi + lo fp16 parts, both multiplied with the same A tile
   int k_part;                 // K extent of one weight part = taps * c_in (padded)
@@ -575,6 +576,23 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       int stage = 0;
       uint32_t phase = 0;
       const int n0 = rank * (BN / 2);
+      if (p.b_resident) {
+        // the layer's whole weight fits next to the halo ring: every (block, tap group) gets its own stage, loaded
+        // ONCE and reused by all tiles of this CTA.  (Streaming it per tile made conv1_2 L2-bandwidth bound: 37 KB of
+        // weights + 23 KB of halo per CTA for 1152 tensor cycles = 12 TB/s over the chip.)
+        for (int g = 0; g < p.n_cblk; ++g) {
+#pragma unroll 1
+          for (int bg = 0; bg < 9 / TB3; ++bg) {
+            if (pair_first >= n_pairs) break;
+            if (rank == 0) mbar_arrive_expect_tx(&b_full[stage], 2u * TB3 * kBHalfBytes);
+            uint8_t* sb = smem_b + stage * b_stage_bytes;
+#pragma unroll
+            for (int tt = 0; tt < TB3; ++tt)
+              tma_load_2d_2cta(sb + tt * kBHalfBytes, &tmap_b, &b_full[stage], g * kBK + (bg * TB3 + tt) * p.c_in, n0);
+            ++stage;
+          }
+        }
+      } else
       for (int pi = pair_first; pi < n_pairs; pi += pair_step) {
         for (int g = 0; g < p.n_cblk; ++g) {
 #pragma unroll 1
@@ -615,7 +633,7 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
           const uint32_t a_lo = a_lo0 + sa * a_step;
 #pragma unroll
           for (int bg = 0; bg < 9 / TB3; ++bg) {
-            mbar_wait(&b_full[sb], pb);
+            if (!p.b_resident || it == 0) mbar_wait(&b_full[sb], pb);   // resident weights arrive once
             tc_fence_after_sync();
             const uint32_t b_lo = b_lo0 + sb * b_step;
             if (leader) {
@@ -629,10 +647,10 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                   umma_f16_ss_2cta(d_tmem, desc64(al + 2u * k, a_hi), desc64(bl + 2u * k, b_hi), idesc,
                                    (bg == 0 && tt == 0 && k == 0) ? accum : 1u);
               }
-              umma_commit_2cta(&b_empty[sb]);
+              if (!p.b_resident) umma_commit_2cta(&b_empty[sb]);
             }
             accum = 1;
-            if (++sb == p.n_b_stages) { sb = 0; pb ^= 1u; }
+            if (++sb == p.n_b_stages) { sb = 0; pb ^= 1u; }   // resident: n_b_stages = stages per tile, wraps per tile
           }
           if (leader) {
             umma_commit_2cta(&a_empty[sa]);
@@ -874,8 +892,21 @@ extern "C" int din_conv2d_nhwc_f16(const DinConvDesc* d, const void* x, const vo
   }
   if (p.n_a_stages > kMaxStages) p.n_a_stages = kMaxStages;
   if (p.n_b_stages > kMaxStages) p.n_b_stages = kMaxStages;
-  DIN_CHECK_ARG(p.n_a_stages >= 2 && p.n_b_stages >= 2, "din_conv2d_nhwc_f16: filter %dx%d does not fit shared memory",
-                d->kh, d->kw);
+  if (two_cta) {
+    // resident weights: one stage per (channel block, tap group), if they fit beside a 2-deep halo ring
+    const int stages = p.n_cblk * (9 / p.tb);
+    const size_t need = static_cast<size_t>(stages) * p.tb * b_bytes + 2u * p.a_stage_bytes;
+    const char* e = std::getenv("DIN_CONV_RESIDENT");
+    if (stages <= kMaxStages && need <= kSmemBudget + 4096 && !(e && e[0] == '0')) {
+      p.b_resident = 1;
+      p.n_b_stages = stages;
+      // what the weights leave free goes to a deeper halo ring (the producer runs further ahead of the MMAs)
+      int a_stages = static_cast<int>((kSmemBudget + 4096 - static_cast<size_t>(stages) * p.tb * b_bytes) / p.a_stage_bytes);
+      p.n_a_stages = a_stages > 4 ? 4 : (a_stages < 2 ? 2 : a_stages);
+    }
+  }
+  DIN_CHECK_ARG(p.n_a_stages >= 2 && (p.n_b_stages >= 2 || p.b_resident),
+                "din_conv2d_nhwc_f16: filter %dx%d does not fit shared memory", d->kh, d->kw);
   const size_t smem = static_cast<size_t>(p.n_a_stages) * p.a_stage_bytes +
                       static_cast<size_t>(p.n_b_stages) * p.tb * b_bytes + kNumEpiWarps * kEpiScratch + 1024 /*align*/ +
                       (4 * kMaxStages + 4) * 8 + 16 + 64 * 4 /*tap offsets*/ +
