@@ -165,3 +165,22 @@ def test_stem_and_pool(cuda):
     ref = F.interpolate(t.float().permute(0, 3, 1, 2), size=(91, 163), mode="bilinear", align_corners=True)
     assert (up[..., 16:].float() - ref.permute(0, 2, 3, 1)).abs().max().item() <= 4e-3
     assert (up[..., :16] == 0).all()
+
+
+@pytest.mark.parametrize("shape", [(64, 3, 3, 3), (128, 64, 3, 3), (512, 512, 3, 3), (1024, 12800, 1, 1), (40, 72, 1, 7),
+                                   (64, 3, 7, 7)], ids=str)
+def test_weight_packing_fast_kernel_is_bit_identical_to_the_serial_one(cuda, shape, monkeypatch):
+    """The shared-memory-staged packing kernel (re-run on every training step) must reproduce the element-by-element
+    error-feedback kernel bit for bit, with and without a BN scale, for both weight formats."""
+    from din_b200 import ops
+    g = torch.Generator().manual_seed(sum(shape))
+    w = (torch.randn(*shape, generator=g) * 0.05).to(cuda)
+    sc = (torch.rand(shape[0], generator=g) + 0.5).to(cuda)
+    for scale in (None, sc):
+        for split in (1, 2):
+            monkeypatch.setenv("DIN_PACK_SERIAL", "1")
+            ref = ops.pack_conv_weight(w, scale, split=split)
+            monkeypatch.setenv("DIN_PACK_SERIAL", "0")
+            out = ops.pack_conv_weight(w, scale, split=split)
+            torch.cuda.synchronize()
+            assert out.shape == ref.shape and torch.equal(out, ref), (shape, scale is not None, split)
