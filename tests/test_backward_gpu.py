@@ -530,3 +530,35 @@ def test_training_reduces_loss_on_a_fixed_batch(cuda):
     print(f"\n[overfit] loss {losses[0]:.3f} -> {losses[-1]:.3f}  ({[round(v, 2) for v in losses]})")
     assert all(torch.isfinite(torch.tensor(losses)))
     assert min(losses[-3:]) < 0.5 * losses[0], losses
+
+
+def test_collective_training_step_with_vgg16_backbone(cuda):
+    """Dynamic_collective (variable actor counts, LayerNorm([T, C]) per actor) with cfg.train_backbone = True on the
+    VGG-16 backbone: every gradient vs autograd over the oracle (fp16 backbone tolerance, see BB_TOL)."""
+    import din_oracle as O
+    from din_b200 import metrics
+    pc = _pc("vgg16", (96, 144), dataset="collective", num_frames=3, num_boxes=13, lite_dim=None, ST_kernel_size=(3, 3),
+             num_activities=4)
+    bb = O.build_backbone(pc.backbone)
+    sd = O.make_state_dict(pc, seed=6, backbone=bb)
+    O.load_backbone(bb, sd)
+    bb.eval()
+    batch = O.make_inputs(pc, 3, seed=6)
+    labels = torch.tensor([0, 3, 1])
+    model, _ = _model_and_cfg(cuda, pc, sd, 0.0)
+    for q in model.backbone.parameters():
+        q.requires_grad = True
+    out = model(tuple(t.to(cuda) for t in batch))["activities"]
+    loss = metrics.cross_entropy(out, labels.to(cuda))
+    loss.backward()
+    torch.cuda.synchronize()
+    ref_logits, ref_loss, ref_grads = O.head_grads(bb, sd, pc, labels, *batch, train_backbone=True)
+    got = {n: q.grad for n, q in model.named_parameters() if q.grad is not None}
+    assert set(got) == set(ref_grads), set(got) ^ set(ref_grads)
+    worst = max(_rel_l2(got[k], ref_grads[k]) for k in ref_grads)
+    worst_norm = max(abs(float(got[k].double().norm()) - float(ref_grads[k].double().norm())) /
+                     max(float(ref_grads[k].double().norm()), 1e-30) for k in ref_grads)
+    print(f"\n[collective full step] loss {loss.item():.5f} vs {ref_loss.item():.5f}; worst rel-L2 {worst:.2e}; worst "
+          f"norm error {worst_norm:.2e}")
+    assert abs(loss.item() - ref_loss.item()) <= 2e-3 * max(1.0, abs(ref_loss.item()))
+    assert worst <= BB_TOL and worst_norm <= 5e-2, (worst, worst_norm)
