@@ -11,6 +11,8 @@ TMA tensor map is given the real channel extent and zero-fills the rest of the l
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -24,14 +26,28 @@ def _c(v, k, s, p=0):
     return (v + 2 * p - k) // s + 1
 
 
+def _split_for(name):
+    """2 = hi + lo fp16 weight parts (exact weights, 2x tensor work), 1 = one fp16 part (error-feedback rounding).
+    DIN_INV3_SPLIT (measurement knob): 'none' (default), 'all', or a comma list of substrings of the layer names that
+    keep the split.  tools/inv3_split_study.py (profiles/inv3_split_study_r1.log): with error-feedback weight rounding
+    in place the logits error is set by the fp16 ACTIVATION rounding of the 37-conv chain -- 5.1e-4 .. 8.8e-4 of
+    max|logit| without any split vs 5.9e-4 .. 7.6e-4 with all layers split (4 cases, tolerance 1e-3) -- while the
+    split costs 2x tensor work: 7.70 -> 5.48 ms per 16 frames at 720p."""
+    sel = os.environ.get("DIN_INV3_SPLIT", "none")
+    if sel == "all":
+        return 2
+    if sel == "none":
+        return 1
+    return 2 if any(tok and tok in name for tok in sel.split(",")) else 1
+
+
 class _BasicConv:
     def __init__(self, sd, name, stride=1, pad=(0, 0)):
         bn = {k: sd[f"{name}.bn.{k}"] for k in ("weight", "bias", "running_mean", "running_var")}
         bn["eps"] = 1e-3
         w, s, b = _fold_bn(sd[f"{name}.conv.weight"], bn)
-        # split-weight mode: Inception is ~37 convolutions deep and single-fp16 weights leave its logits at
-        # 1.1-1.2e-3 of max|logit| on small inputs (tools/e2e_errors.py); hi+lo weights bring it to ~5e-4
-        self.conv = _Conv(w, b, s, stride=stride, pad=pad, relu=True, split=2)
+        # split-weight mode is available (w_split = 2) but off by default: see _split_for
+        self.conv = _Conv(w, b, s, stride=stride, pad=pad, relu=True, split=_split_for(name))
         self.c_in, self.c_out = w.shape[1], w.shape[0]
 
     def __call__(self, x, out=None, x_c_offset=0, y_c_offset=0):
