@@ -26,6 +26,8 @@
 // version (producer / epilogue warps, double-buffered A tile and accumulator, 256-bit per-lane stores instead of
 // the shared-memory transpose): -9 % -- per-lane 32-byte stores to 32 different lines are slower than the
 // transposed 64-byte-contiguous ones.
+#include <cstdlib>
+
 #include "din_common.cuh"
 
 namespace {
@@ -344,6 +346,201 @@ stem_tc_kernel(const StemParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Wide variant for the large-K stems (ResNet-18 7x7 s2: K = 147 -> 160): 256 threads per CTA.  The 128-thread kernel
+// spends its time in the im2col build (147 shared loads + 74 conversions + 20 stores per thread, 2 CTAs = 8 warps per
+// SM: latency-bound, 0.8 TB/s of output).  Here two threads share a pixel (each builds half of the K chunks), the
+// patch staging is spread over 256 threads, and the eight warps split the epilogue by (TMEM lane quadrant, 32-column
+// chunk) -- twice the warps per SM for the same shared memory.
+// ------------------------------------------------------------------------------------------------
+// chunks [KC0, KC1) of pixel `pix`'s im2col row -> A tile (canonical no-swizzle layout); all offsets immediates
+template <int COUT, int KH, int KW, int STRIDE, int KC0, int KC1>
+__device__ __forceinline__ void build_im2col_chunks(const float* prow, uint8_t* a_s, int pix) {
+  using Cfg = StemCfg<COUT, KH, KW, STRIDE>;
+#pragma unroll
+  for (int kc = KC0; kc < KC1; ++kc) {
+    __align__(16) __half2 hv[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float f[2];
+#pragma unroll
+      for (int z = 0; z < 2; ++z) {
+        const int k = kc * 8 + 2 * e + z;
+        if (k < Cfg::kReal) {
+          const int c = k / (KH * KW), r = k % (KH * KW);
+          f[z] = prow[(c * KH + r / KW) * Cfg::kPitch + r % KW];
+        } else {
+          f[z] = (k <= Cfg::kBiasK + 1) ? 1.0f : 0.0f;
+        }
+      }
+      hv[e] = __floats2half2_rn(f[0], f[1]);
+    }
+    *reinterpret_cast<uint4*>(a_s + canon_off(pix, kc, Cfg::kSbo)) = *reinterpret_cast<const uint4*>(hv);
+  }
+}
+
+constexpr int kWideThreads = 256;
+
+template <int COUT, int KH, int KW, int STRIDE, bool U8>
+__global__ void __launch_bounds__(kWideThreads)
+stem_tc_wide_kernel(const StemParams p) {
+  using Cfg = StemCfg<COUT, KH, KW, STRIDE>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem(smem_raw, 128);
+  uint8_t* a_s = smem;
+  uint8_t* b_s = a_s + 16 * Cfg::kSbo;
+  uint8_t* scratch = b_s + (COUT / 8) * Cfg::kSbo;          // 8 warps x 32 x 80 B
+  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(scratch + 8 * 32 * kEpiPitch);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  float* patch = reinterpret_cast<float*>(tmem_ptr_smem + 4);               // [3*KH][kPitch]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < COUT * (Cfg::kPad / 8); i += kWideThreads) {
+    const int o = i / (Cfg::kPad / 8), kc = i % (Cfg::kPad / 8);
+    __align__(16) __half hv[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = kc * 8 + e;
+      float wv = 0.0f;
+      if (k < Cfg::kReal) {
+        wv = __ldg(p.w + static_cast<size_t>(o) * Cfg::kReal + k);
+      } else if (p.bias != nullptr && k <= Cfg::kBiasK + 1) {
+        const float bv = __ldg(p.bias + o);
+        const float bh = __half2float(__float2half_rn(bv));
+        wv = (k == Cfg::kBiasK) ? bh : bv - bh;
+      }
+      hv[e] = __float2half_rn(wv);
+    }
+    *reinterpret_cast<uint4*>(b_s + canon_off(o, kc, Cfg::kSbo)) = *reinterpret_cast<const uint4*>(hv);
+  }
+  if (tid == 0) {
+    mbar_init(mma_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+  constexpr uint32_t idesc = umma_idesc_f16_f32(128, COUT);
+  const size_t plane = static_cast<size_t>(p.h) * p.w_in;
+  constexpr int kElems = (U8 ? KH : Cfg::kRows) * Cfg::kPatchW;             // loads per tile (a uint8 load = 3 channels)
+  constexpr int kIter = (kElems + kWideThreads - 1) / kWideThreads;
+
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const TileCoord cur = decode_tile(p, tile);
+    const int iy0 = cur.oy * STRIDE - p.pad;
+    const int gx0 = cur.strip * 128 * STRIDE - p.pad;
+    // ---- stage the patch: predicated loads first (all in flight), prep + store afterwards
+    {
+      uint32_t v[kIter];
+      bool ok[kIter];
+#pragma unroll
+      for (int u = 0; u < kIter; ++u) {
+        const int i = tid + u * kWideThreads;
+        const int r = i / Cfg::kPatchW, px = i - r * Cfg::kPatchW;          // r: (c, ky) row, or ky for uint8
+        const int ky = U8 ? r : r % KH;
+        const int gy = iy0 + ky, gx = gx0 + px;
+        ok[u] = i < kElems && gy >= 0 && gy < p.h && gx >= 0 && gx < p.w_in;
+        const int cy = min(max(gy, 0), p.h - 1), cx = min(max(gx, 0), p.w_in - 1);
+        if constexpr (U8) {
+          const uint8_t* q = static_cast<const uint8_t*>(p.x) + (static_cast<size_t>(cur.img) * plane + static_cast<size_t>(cy) * p.w_in + cx) * 3;
+          v[u] = static_cast<uint32_t>(__ldg(q)) | (static_cast<uint32_t>(__ldg(q + 1)) << 8) | (static_cast<uint32_t>(__ldg(q + 2)) << 16);
+        } else {
+          const int c = r / KH;
+          v[u] = __float_as_uint(__ldg(static_cast<const float*>(p.x) + (static_cast<size_t>(cur.img) * 3 + min(c, 2)) * plane +
+                                       static_cast<size_t>(cy) * p.w_in + cx));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kIter; ++u) {
+        const int i = tid + u * kWideThreads;
+        if (i < kElems) {
+          const int r = i / Cfg::kPatchW, px = i - r * Cfg::kPatchW;
+          if constexpr (U8) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+              patch[(c * KH + r) * Cfg::kPitch + px] =
+                  ok[u] ? prep_value(static_cast<float>((v[u] >> (8 * c)) & 0xFFu), p.prep != 0) : 0.0f;
+          } else {
+            patch[r * Cfg::kPitch + px] = ok[u] ? prep_value(__uint_as_float(v[u]), p.prep != 0) : 0.0f;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- im2col: threads t and t + 128 share pixel t & 127 and build half of its K chunks each (two statically
+    //      unrolled instantiations, so every patch offset stays an immediate)
+    {
+      const int pix = tid & 127;
+      constexpr int kChunks = Cfg::kPad / 8, kHalfChunks = (kChunks + 1) / 2;
+      if (tid < 128) build_im2col_chunks<COUT, KH, KW, STRIDE, 0, kHalfChunks>(patch + pix * STRIDE, a_s, pix);
+      else build_im2col_chunks<COUT, KH, KW, STRIDE, kHalfChunks, kChunks>(patch + pix * STRIDE, a_s, pix);
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after_sync();
+      const uint32_t a_addr = smem_u32(a_s), b_addr = smem_u32(b_s);
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < Cfg::kPad / 16; ++ks) {
+          const uint64_t ad = desc_noswz(a_addr + ks * 256, 128, Cfg::kSbo);
+          const uint64_t bd = desc_noswz(b_addr + ks * 256, 128, Cfg::kSbo);
+          umma_f16_ss(tmem_base, ad, bd, idesc, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(mma_bar);
+      }
+      __syncwarp();
+    }
+    mbar_wait(mma_bar, phase);
+    phase ^= 1u;
+    tc_fence_after_sync();
+    // ---- epilogue: warp = (lane quadrant q, 32-column chunk)
+    {
+      const int q = warp & 3, chunk = warp >> 2;
+      const int c0 = chunk * 32;
+      if (c0 < COUT) {
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        uint8_t* sc = scratch + warp * 32 * kEpiPitch;
+        const int unit = lane & 3;
+        __half* yrow = p.y + ((static_cast<size_t>(cur.img) * p.oh + cur.oy) * p.ow) * COUT;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + c0, v);
+        tmem_ld_wait();
+        uint32_t hh[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          hh[j] = pack_half2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]), p.relu != 0);
+        uint4* wr = reinterpret_cast<uint4*>(sc + lane * kEpiPitch);
+#pragma unroll
+        for (int u4 = 0; u4 < 4; ++u4) wr[u4] = make_uint4(hh[4 * u4], hh[4 * u4 + 1], hh[4 * u4 + 2], hh[4 * u4 + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int src = (lane >> 2) + 8 * k;
+          const int sx = cur.strip * 128 + q * 32 + src;
+          if (sx < p.ow) {
+            const uint4 o = *reinterpret_cast<const uint4*>(sc + src * kEpiPitch + unit * 16);
+            *reinterpret_cast<uint4*>(yrow + static_cast<size_t>(sx) * COUT + c0 + unit * 8) = o;
+          }
+        }
+      }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
 void fastdiv(uint32_t d, uint32_t* mul, uint32_t* shr) {
   uint32_t l = 0;
   while ((1u << l) < d) ++l;
@@ -352,7 +549,30 @@ void fastdiv(uint32_t d, uint32_t* mul, uint32_t* shr) {
 }
 
 template <int COUT, int KH, int KW, int STRIDE, bool U8>
+int launch_wide(StemParams& p, cudaStream_t st) {
+  using Cfg = StemCfg<COUT, KH, KW, STRIDE>;
+  constexpr size_t kSmemWide = Cfg::kSmem + 4 * 32 * kEpiPitch;      // eight epilogue scratch areas instead of four
+  const int sms = din_num_sms();
+  int per_sm = static_cast<int>((224 * 1024) / (kSmemWide + 1024));   // 227 KB per SM, 1 KB reserved per CTA
+  const int tmem_limit = 512 / Cfg::kTmemCols;
+  if (per_sm > tmem_limit) per_sm = tmem_limit;
+  if (per_sm > 4) per_sm = 4;
+  if (per_sm < 1) per_sm = 1;
+  long long grid = static_cast<long long>(sms > 0 ? sms : 148) * per_sm;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  DIN_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_wide_kernel<COUT, KH, KW, STRIDE, U8>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemWide)));
+  stem_tc_wide_kernel<COUT, KH, KW, STRIDE, U8><<<static_cast<int>(grid), kWideThreads, kSmemWide, st>>>(p);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
+template <int COUT, int KH, int KW, int STRIDE, bool U8>
 int launch(StemParams& p, cudaStream_t st) {
+  if constexpr (KH * KW >= 25) {                       // large-K stems: the 256-thread kernel (DIN_STEM_WIDE=0: A/B)
+    const char* e = std::getenv("DIN_STEM_WIDE");
+    if (!(e && e[0] == '0')) return launch_wide<COUT, KH, KW, STRIDE, U8>(p, st);
+  }
   using Cfg = StemCfg<COUT, KH, KW, STRIDE>;
   const int sms = din_num_sms();
   int per_sm = static_cast<int>((200 * 1024) / Cfg::kSmem);
