@@ -474,13 +474,15 @@ def test_full_training_step_with_backbone(cuda):
 BB_TOL = 2e-1
 
 
-def test_gradient_of_batch_is_mean_of_per_clip_gradients(cuda):
-    """Size-independent property behind the data-parallel step: with dropout off, the gradient of
-    the batch-mean loss equals the mean of the per-clip gradients (what the single flat all-reduce averages),
-    backbone included; and two identical steps agree to atomics noise."""
+@pytest.mark.parametrize("hw,T,N", [((96, 160), 3, 4), ((720, 1280), 2, 12)], ids=["small", "720p"])
+def test_gradient_of_batch_is_mean_of_per_clip_gradients(cuda, hw, T, N):
+    """Size-independent property behind the data-parallel step, also at BASELINE's frame size (where
+    the CPU oracle would take minutes): with dropout off, the gradient of the batch-mean loss equals the mean of the
+    per-clip gradients (what the single flat all-reduce averages), backbone included; and two identical steps agree
+    to atomics noise."""
     import din_oracle as O
     from din_b200 import metrics
-    pc = _pc("vgg16", (96, 160), num_frames=3, num_boxes=4)
+    pc = _pc("vgg16", hw, num_frames=T, num_boxes=N)
     sd = O.make_state_dict(pc, seed=4)
     batch = tuple(t.to(cuda) for t in O.make_inputs(pc, 2, seed=4))
     labels = torch.tensor([3, 6], device=cuda)
