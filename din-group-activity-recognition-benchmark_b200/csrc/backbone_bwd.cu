@@ -220,6 +220,167 @@ stem_wgrad_kernel(const void* __restrict__ x, const __half* __restrict__ dz, flo
   }
 }
 
+// ================================================================================================
+// ResNet-18 pieces (stride-2 convolutions, 3x3 stride-2 max-pool, eval-mode BatchNorm folded into the convolutions)
+// ================================================================================================
+// dst[n, 2*oy, 2*ox, :] (+)= src[n, oy, ox, :]; with accumulate == 0 every other dst pixel is zero-filled.
+//   accumulate == 0: "zero insertion": dZ of a stride-2 convolution laid out on the input grid, so that BOTH its data
+//                    gradient and its weight gradient are the stride-1 kernels' (dX = conv(dZ_up, rot W), dW = wgrad(X,
+//                    dZ_up)): 4x the useful work on the three stride-2 3x3 layers, no new tensor-core code;
+//   accumulate == 1: the 1x1 stride-2 shortcut's data gradient added at the even positions.
+__global__ void __launch_bounds__(256)
+scatter2_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int n, int h, int w, int c8, int oh, int ow,
+                int accumulate) {
+  const long long total = static_cast<long long>(n) * h * w * c8;
+  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int oc = static_cast<int>(idx % c8);
+  long long pix = idx / c8;
+  const int ix = static_cast<int>(pix % w);
+  pix /= w;
+  const int iy = static_cast<int>(pix % h);
+  const int img = static_cast<int>(pix / h);
+  const bool hit = !(iy & 1) && !(ix & 1) && (iy >> 1) < oh && (ix >> 1) < ow;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (hit) v = __ldg(reinterpret_cast<const uint4*>(src) + ((static_cast<long long>(img) * oh + (iy >> 1)) * ow + (ix >> 1)) * c8 + oc);
+  uint4* d = reinterpret_cast<uint4*>(dst) + idx;
+  if (accumulate) {
+    if (!hit) return;
+    uint4 cur = *d;
+    __half2* a = reinterpret_cast<__half2*>(&cur);
+    const __half2* b = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) a[e] = __hadd2(a[e], b[e]);
+    *d = cur;
+  } else {
+    *d = v;
+  }
+}
+
+// y = a + b (fp16, the residual branch merging two gradients)
+__global__ void __launch_bounds__(256)
+add_f16_kernel(const __half* __restrict__ a, const __half* __restrict__ b, __half* __restrict__ y, long long count8) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= count8) return;
+  const uint4 va = __ldg(reinterpret_cast<const uint4*>(a) + i), vb = __ldg(reinterpret_cast<const uint4*>(b) + i);
+  uint4 o;
+  const __half2* ha = reinterpret_cast<const __half2*>(&va);
+  const __half2* hb = reinterpret_cast<const __half2*>(&vb);
+  __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) ho[e] = __hadd2(ha[e], hb[e]);
+  reinterpret_cast<uint4*>(y)[i] = o;
+}
+
+// Backward of MaxPool2d(3, 2, 1) fused with the ReLU before it (resnet18.relu / .maxpool):
+//   dz[iy,ix] = [x > 0] * sum over the (1, 2 or 4) windows containing (iy,ix) of  dy[window] * [(iy,ix) is the window's
+//   FIRST maximum in scan order]   (padding is -inf and never wins, as torch).
+__global__ void __launch_bounds__(256)
+maxpool3s2_relu_bwd_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, __half* __restrict__ dz, int n,
+                           int h, int w, int c8, int oh, int ow) {
+  const long long total = static_cast<long long>(n) * h * w * c8;
+  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int oc = static_cast<int>(idx % c8);
+  long long pix = idx / c8;
+  const int ix = static_cast<int>(pix % w);
+  pix /= w;
+  const int iy = static_cast<int>(pix % h);
+  const int img = static_cast<int>(pix / h);
+  const uint4* x4 = reinterpret_cast<const uint4*>(x) + static_cast<long long>(img) * h * w * c8 + oc;
+  const uint4* dy4 = reinterpret_cast<const uint4*>(dy) + static_cast<long long>(img) * oh * ow * c8 + oc;
+  const uint4 mine = __ldg(x4 + (static_cast<long long>(iy) * w + ix) * c8);
+  const __half2* hm = reinterpret_cast<const __half2*>(&mine);
+  const __half2 zero = __float2half2_rn(0.0f), one = __float2half2_rn(1.0f);
+  const __half2 ninf = __half2half2(__ushort_as_half(static_cast<unsigned short>(0xFC00)));
+  __half2 acc[4] = {zero, zero, zero, zero};
+  // windows oy with 2*oy - 1 <= iy <= 2*oy + 1
+  const int oy_lo = iy >> 1, oy_hi = (iy + 1) >> 1;
+  const int ox_lo = ix >> 1, ox_hi = (ix + 1) >> 1;
+  for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+    if (oy >= oh) continue;
+    for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+      if (ox >= ow) continue;
+      const int my_pos = (iy - (2 * oy - 1)) * 3 + (ix - (2 * ox - 1));     // scan position of (iy,ix) in this window
+      __half2 sel[4] = {one, one, one, one};
+#pragma unroll
+      for (int q = 0; q < 9; ++q) {
+        const int yy = 2 * oy - 1 + q / 3, xx = 2 * ox - 1 + q % 3;
+        const bool ok = yy >= 0 && yy < h && xx >= 0 && xx < w;
+        const uint4 v = __ldg(x4 + (static_cast<long long>(min(max(yy, 0), h - 1)) * w + min(max(xx, 0), w - 1)) * c8);
+        const __half2* hv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __half2 o = ok ? hv[e] : ninf;
+          const __half2 f = q < my_pos ? __hgt2(hm[e], o) : (q > my_pos ? __hge2(hm[e], o) : one);
+          sel[e] = __hmul2(sel[e], f);
+        }
+      }
+      const uint4 g = __ldg(dy4 + (static_cast<long long>(oy) * ow + ox) * c8);
+      const __half2* hg = reinterpret_cast<const __half2*>(&g);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[e] = __hfma2(hg[e], sel[e], acc[e]);
+    }
+  }
+  uint4 out;
+  __half2* ho = reinterpret_cast<__half2*>(&out);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) ho[e] = __hmul2(acc[e], __hgt2(hm[e], zero));
+  reinterpret_cast<uint4*>(dz)[idx] = out;
+}
+
+// Eval-mode BatchNorm folded into a convolution: z = gamma * xhat + beta.  d(gamma)[c] += inv_scale * sum_p dz * xhat with
+// xhat = (z - beta) / gamma recovered from the saved activation (z = zsrc - sub; wherever the ReLU zeroed z, dz is zero
+// too, so the post-ReLU tensor serves).  d(beta) is the convolution's bias gradient (conv_wgrad's dbias).
+__global__ void __launch_bounds__(256)
+bn_gamma_grad_kernel(const __half* __restrict__ dz, const __half* __restrict__ zsrc, const __half* __restrict__ sub,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ dgamma,
+                     long long rows, int c, const float* __restrict__ inv_scale) {
+  __shared__ float red[256][8 + 1];
+  const int octs = c >> 3;
+  const int lanes_r = 256 / octs;
+  const int oct = threadIdx.x % octs, rl = threadIdx.x / octs;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (rl < lanes_r) {
+    float be[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) be[e] = __ldg(beta + oct * 8 + e);
+    for (long long r = static_cast<long long>(blockIdx.x) * lanes_r + rl; r < rows;
+         r += static_cast<long long>(gridDim.x) * lanes_r) {
+      const uint4 g = __ldg(reinterpret_cast<const uint4*>(dz + r * c) + oct);
+      const uint4 z = __ldg(reinterpret_cast<const uint4*>(zsrc + r * c) + oct);
+      uint4 sb = make_uint4(0, 0, 0, 0);
+      if (sub != nullptr) sb = __ldg(reinterpret_cast<const uint4*>(sub + r * c) + oct);
+      const __half* hg = reinterpret_cast<const __half*>(&g);
+      const __half* hz = reinterpret_cast<const __half*>(&z);
+      const __half* hs = reinterpret_cast<const __half*>(&sb);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        acc[e] = fmaf(__half2float(hg[e]), (__half2float(hz[e]) - __half2float(hs[e])) - be[e], acc[e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[threadIdx.x][e] = acc[e];
+  __syncthreads();
+  if (threadIdx.x < octs) {
+    const float scl = inv_scale ? __ldg(inv_scale) : 1.0f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float s = 0.0f;
+      for (int l = 0; l < lanes_r; ++l) s += red[l * octs + threadIdx.x][e];
+      atomicAdd(dgamma + threadIdx.x * 8 + e, s * scl / __ldg(gamma + threadIdx.x * 8 + e));
+    }
+  }
+}
+
+// w[r][:] *= scale[r]   (gradient of the un-folded convolution weight: dW = dW_folded * gamma / sqrt(var + eps))
+__global__ void __launch_bounds__(256)
+scale_rows_kernel(float* __restrict__ w, const float* __restrict__ scale, long long rows, long long cols) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= rows * cols) return;
+  w[i] *= __ldg(scale + i / cols);
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -280,15 +441,16 @@ extern "C" int din_stem_wgrad(const void* x, int x_is_u8, const void* dz, float*
                               int prep, void* stream) {
   DIN_CHECK_ARG(x && dz && dw, "din_stem_wgrad: null pointer");
   DIN_CHECK_ARG(n > 0 && h > 0 && w > 0, "din_stem_wgrad: bad extent n=%d h=%d w=%d", n, h, w);
-  DIN_CHECK_ARG(c_out == 64 && kh == 3 && kw == 3 && stride == 1 && pad == 1,
-                "din_stem_wgrad: only the VGG-16 stem (64 x 3x3, stride 1, pad 1) is implemented");
+  DIN_CHECK_ARG(c_out == 64 && kh == kw && ((kh == 3 && stride == 1 && pad == 1) || (kh == 7 && stride == 2 && pad == 3)),
+                "din_stem_wgrad: only the VGG-16 (64 x 3x3 s1 p1) and ResNet-18 (64 x 7x7 s2 p3) stems are implemented");
   DIN_CHECK_ARG((reinterpret_cast<uintptr_t>(dz) & 15) == 0, "din_stem_wgrad: dz must be 16-byte aligned");
   {
     // production path: tensor cores (stem_tc.cu).  DIN_STEM_WGRAD_SIMT=1 keeps the CUDA-core kernel below for A/B
     // measurements -- still a kernel of this library.
     const char* e = std::getenv("DIN_STEM_WGRAD_SIMT");
-    if (!(e && e[0] == '1'))
-      return din_stem_wgrad_tc_launch(x, x_is_u8, dz, dw, dbias, inv_scale, n, h, w, prep, static_cast<cudaStream_t>(stream));
+    if (!(e && e[0] == '1') || kh != 3)
+      return din_stem_wgrad_tc_launch(x, x_is_u8, dz, dw, dbias, inv_scale, n, h, w, kh, stride, pad, prep,
+                                      static_cast<cudaStream_t>(stream));
   }
   const int sms = din_num_sms();
   const long long strips = static_cast<long long>(n) * h * ((w + 127) / 128);
@@ -301,6 +463,73 @@ extern "C" int din_stem_wgrad(const void* x, int x_is_u8, const void* dz, float*
   else
     stem_wgrad_kernel<false><<<static_cast<int>(grid), kSwThreads, 0, st>>>(x, static_cast<const __half*>(dz), dw, dbias,
                                                                            inv_scale, n, h, w, prep);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
+extern "C" int din_scatter2_nhwc_f16(const void* src, void* dst, int n, int h, int w, int c, int oh, int ow, int accumulate,
+                                     void* stream) {
+  DIN_CHECK_ARG(src && dst, "din_scatter2_nhwc_f16: null pointer");
+  DIN_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && oh > 0 && ow > 0 && 2 * (oh - 1) < h && 2 * (ow - 1) < w,
+                "din_scatter2_nhwc_f16: bad shape n=%d h=%d w=%d c=%d oh=%d ow=%d", n, h, w, c, oh, ow);
+  DIN_CHECK_ARG(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0,
+                "din_scatter2_nhwc_f16: pointers must be 16-byte aligned");
+  const long long total = static_cast<long long>(n) * h * w * (c / 8);
+  DIN_CHECK_ARG((total + 255) / 256 <= INT32_MAX, "din_scatter2_nhwc_f16: too large");
+  scatter2_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(src), static_cast<__half*>(dst), n, h, w, c / 8, oh, ow, accumulate);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
+extern "C" int din_add_f16(const void* a, const void* b, void* y, long long count, void* stream) {
+  DIN_CHECK_ARG(a && b && y, "din_add_f16: null pointer");
+  DIN_CHECK_ARG(count > 0 && count % 8 == 0, "din_add_f16: count=%lld must be a positive multiple of 8", count);
+  DIN_CHECK_ARG(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(y)) & 15) == 0,
+                "din_add_f16: pointers must be 16-byte aligned");
+  const long long n8 = count / 8;
+  DIN_CHECK_ARG((n8 + 255) / 256 <= INT32_MAX, "din_add_f16: too large");
+  add_f16_kernel<<<static_cast<int>((n8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(a), static_cast<const __half*>(b), static_cast<__half*>(y), n8);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
+extern "C" int din_maxpool3s2_relu_bwd_nhwc_f16(const void* x, const void* dy, void* dz, int n, int h, int w, int c,
+                                                void* stream) {
+  DIN_CHECK_ARG(x && dy && dz, "din_maxpool3s2_relu_bwd_nhwc_f16: null pointer");
+  DIN_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "din_maxpool3s2_relu_bwd_nhwc_f16: bad shape");
+  const int oh = (h + 2 - 3) / 2 + 1, ow = (w + 2 - 3) / 2 + 1;
+  const long long total = static_cast<long long>(n) * h * w * (c / 8);
+  DIN_CHECK_ARG((total + 255) / 256 <= INT32_MAX, "din_maxpool3s2_relu_bwd_nhwc_f16: too large");
+  maxpool3s2_relu_bwd_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), static_cast<const __half*>(dy), static_cast<__half*>(dz), n, h, w, c / 8, oh, ow);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
+extern "C" int din_bn_gamma_grad_f16(const void* dz, const void* zsrc, const void* sub, const float* gamma,
+                                     const float* beta, float* dgamma, const float* inv_scale, long long rows, int c,
+                                     void* stream) {
+  DIN_CHECK_ARG(dz && zsrc && gamma && beta && dgamma, "din_bn_gamma_grad_f16: null pointer");
+  DIN_CHECK_ARG(rows > 0 && c > 0 && c % 8 == 0 && c <= 2048, "din_bn_gamma_grad_f16: bad shape rows=%lld c=%d", rows, c);
+  const int sms = din_num_sms();
+  int g = 2 * (sms > 0 ? sms : 148);
+  const long long per = 256 / (c / 8);
+  if (static_cast<long long>(g) * per > rows) g = static_cast<int>((rows + per - 1) / per);
+  bn_gamma_grad_kernel<<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(dz), static_cast<const __half*>(zsrc), static_cast<const __half*>(sub), gamma, beta,
+      dgamma, rows, c, inv_scale);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
+extern "C" int din_scale_rows_f32(float* w, const float* scale, long long rows, long long cols, void* stream) {
+  DIN_CHECK_ARG(w && scale && rows > 0 && cols > 0, "din_scale_rows_f32: bad arguments");
+  const long long total = rows * cols;
+  DIN_CHECK_ARG((total + 255) / 256 <= INT32_MAX, "din_scale_rows_f32: too large");
+  scale_rows_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(w, scale, rows,
+                                                                                                         cols);
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;
 }

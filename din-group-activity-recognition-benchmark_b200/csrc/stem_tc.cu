@@ -610,8 +610,18 @@ int dispatch(StemParams& p, int c_out, int kh, int kw, int stride, cudaStream_t 
 // Replaces the CUDA-core stem_wgrad_kernel (12 % of a training step in the first launch list).
 // ================================================================================================
 constexpr int kSwgABytes = 128 * 128;            // dZ strip tile
-constexpr int kSwgBBytes = 128 * 64;             // im2col tile
-constexpr size_t kSwgSmem = 1024 + 2 * kSwgABytes + kSwgBBytes + 64 + static_cast<size_t>(9) * 131 * 4;
+
+template <int KH, int KW, int STRIDE>
+struct SwgCfg {
+  using Cfg = StemCfg<64, KH, KW, STRIDE>;
+  static constexpr int kTaps = 3 * KH * KW;                          // + 1 ones column = bias gradient
+  static constexpr int kN = (kTaps + 1 + 15) / 16 * 16;              // MMA N (multiple of 16): 32 / 160
+  static constexpr int kChunks = kN / 8;                             // 16-byte chunks per im2col row
+  static constexpr int kLbo = kChunks * 128;                         // bytes between 8-pixel groups
+  static constexpr int kBBytes = 128 * kN * 2;
+  static constexpr int kTmemCols = kN <= 32 ? 32 : (kN <= 64 ? 64 : (kN <= 128 ? 128 : 256));
+  static constexpr size_t kSmem = 1024 + 2 * kSwgABytes + kBBytes + 64 + static_cast<size_t>(Cfg::kRows) * Cfg::kPitch * 4;
+};
 
 __device__ __forceinline__ uint64_t desc_mn_sw128_stem(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -623,20 +633,21 @@ __device__ __forceinline__ uint64_t desc_mn_sw128_stem(uint32_t addr, uint32_t l
   return d;
 }
 
-template <bool U8>
+template <int KH, int KW, int STRIDE, bool U8>
 __global__ void __launch_bounds__(kStemThreads)
 stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dz, const StemParams p, float* __restrict__ dw,
                      float* __restrict__ db, const float* __restrict__ inv_scale) {
-  using Cfg = StemCfg<64, 3, 3, 1>;
+  using Cfg = StemCfg<64, KH, KW, STRIDE>;
+  using SC = SwgCfg<KH, KW, STRIDE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem(smem_raw, 1024);
   uint8_t* a_s = smem;                                      // [128 pixel rows][128 B], TMA, SWIZZLE_128B
   uint8_t* z_s = a_s + kSwgABytes;                          // zeros: the upper 64 rows of M
   uint8_t* b_s = z_s + kSwgABytes;                          // im2col, no-swizzle MN-major
-  uint64_t* tma_bar = reinterpret_cast<uint64_t*>(b_s + kSwgBBytes);
+  uint64_t* tma_bar = reinterpret_cast<uint64_t*>(b_s + SC::kBBytes);
   uint64_t* mma_bar = tma_bar + 1;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(mma_bar + 1);
-  float* patch = reinterpret_cast<float*>(tmem_ptr_smem + 4);               // [9][kPitch]
+  float* patch = reinterpret_cast<float*>(tmem_ptr_smem + 4);               // [3*KH][kPitch]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   for (int i = tid; i < kSwgABytes / 16; i += kStemThreads) reinterpret_cast<uint4*>(z_s)[i] = make_uint4(0, 0, 0, 0);
@@ -646,14 +657,14 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dz, const StemPara
     mbar_init(mma_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc<32>(tmem_ptr_smem);
+  if (warp == 0) tmem_alloc<SC::kTmemCols>(tmem_ptr_smem);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
-  // kind::f16, fp32 accumulate, A and B MN-major (bits 15, 16), M = 128, N = 32
-  constexpr uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>(32 >> 3) << 17) |
+  // kind::f16, fp32 accumulate, A and B MN-major (bits 15, 16), M = 128, N = kN
+  constexpr uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>(SC::kN >> 3) << 17) |
                              (static_cast<uint32_t>(128 >> 4) << 24);
 
   uint32_t phase = 0;
@@ -665,26 +676,26 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dz, const StemPara
       tma_load_4d(a_s, &tmap_dz, tma_bar, 0, cur.strip * 128, cur.oy, cur.img);
     }
     {
-      PatchRegs<64, 3, 3, 1, U8> regs;
-      load_patch<64, 3, 3, 1, U8>(p, cur, tid, regs);
-      stage_patch<64, 3, 3, 1, U8>(p, tid, patch, regs);
+      PatchRegs<64, KH, KW, STRIDE, U8> regs;
+      load_patch<64, KH, KW, STRIDE, U8>(p, cur, tid, regs);
+      stage_patch<64, KH, KW, STRIDE, U8>(p, tid, patch, regs);
     }
     __syncthreads();
     {
-      // im2col row of pixel `tid`: 32 fp16 = four 16-byte chunks; chunk j of pixel p lives at
-      // (p / 8) * 512 + j * 128 + (p % 8) * 16   (8-pixel groups 512 B apart = LBO, 8-column chunks 128 B apart = SBO)
-      const float* prow = patch + tid;
-      uint8_t* dst = b_s + (tid >> 3) * 512 + (tid & 7) * 16;
+      // im2col row of pixel `tid`: kN fp16 = kChunks 16-byte chunks; chunk j of pixel p lives at
+      // (p / 8) * kLbo + j * 128 + (p % 8) * 16   (8-pixel groups kLbo apart = LBO, 8-column chunks 128 B apart = SBO)
+      const float* prow = patch + tid * STRIDE;
+      uint8_t* dst = b_s + (tid >> 3) * SC::kLbo + (tid & 7) * 16;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < SC::kChunks; ++j) {
         __align__(16) __half2 hv[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           float f[2];
 #pragma unroll
           for (int z = 0; z < 2; ++z) {
-            const int k = j * 8 + 2 * e + z;
-            f[z] = (k < 27) ? prow[(k / 3) * Cfg::kPitch + (k % 3)] : (k == 27 ? 1.0f : 0.0f);
+            const int k = j * 8 + 2 * e + z;                 // k = (c*KH + ky)*KW + kx (OIHW flatten); kTaps = bias
+            f[z] = (k < SC::kTaps) ? prow[(k / KW) * Cfg::kPitch + (k % KW)] : (k == SC::kTaps ? 1.0f : 0.0f);
           }
           hv[e] = __floats2half2_rn(f[0], f[1]);
         }
@@ -701,7 +712,7 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dz, const StemPara
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {                    // 16 pixels per MMA
           const uint64_t ad = desc_mn_sw128_stem(a_addr + ks * 2048, kSwgABytes, 1024);
-          const uint64_t bd = desc_noswz(b_addr + ks * 1024, 512, 128);
+          const uint64_t bd = desc_noswz(b_addr + ks * 2 * SC::kLbo, SC::kLbo, 128);
           umma_f16_ss(tmem_base, ad, bd, idesc, (any || ks > 0) ? 1u : 0u);
         }
         umma_commit(mma_bar);
@@ -714,23 +725,48 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dz, const StemPara
     tc_fence_after_sync();
   }
 
-  // ---- flush: TMEM lanes 0..63 = output channels, columns = taps (27 = bias)
+  // ---- flush: TMEM lanes 0..63 = output channels, columns = taps (kTaps = bias)
   if (any && warp < 2) {
     const float scl = inv_scale ? __ldg(inv_scale) : 1.0f;
-    uint32_t v[32];
-    tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16), v);
-    tmem_ld_wait();
     const int co = warp * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < SC::kN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+      tmem_ld_wait();
 #pragma unroll
-    for (int k = 0; k < 27; ++k) atomicAdd(dw + co * 27 + k, __uint_as_float(v[k]) * scl);
-    if (db != nullptr) atomicAdd(db + co, __uint_as_float(v[27]) * scl);
+      for (int j = 0; j < 32; ++j) {
+        const int k = c0 + j;
+        if (k < SC::kTaps) atomicAdd(dw + co * SC::kTaps + k, __uint_as_float(v[j]) * scl);
+        else if (k == SC::kTaps && db != nullptr) atomicAdd(db + co, __uint_as_float(v[j]) * scl);
+      }
+    }
   }
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) {
     tc_fence_after_sync();
-    tmem_dealloc<32>(tmem_base);
+    tmem_dealloc<SC::kTmemCols>(tmem_base);
   }
+}
+
+template <int KH, int KW, int STRIDE, bool U8>
+int launch_stem_wgrad(const CUtensorMap& tdz, StemParams& p, float* dw, float* dbias, const float* inv_scale,
+                      cudaStream_t st) {
+  using SC = SwgCfg<KH, KW, STRIDE>;
+  const int sms = din_num_sms();
+  int per_sm = static_cast<int>((224 * 1024) / (SC::kSmem + 1024));
+  if (per_sm > 512 / SC::kTmemCols) per_sm = 512 / SC::kTmemCols;
+  if (per_sm > 4) per_sm = 4;
+  if (per_sm < 1) per_sm = 1;
+  long long grid = static_cast<long long>(sms > 0 ? sms : 148) * per_sm;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  DIN_CHECK_CUDA(cudaFuncSetAttribute(stem_wgrad_tc_kernel<KH, KW, STRIDE, U8>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SC::kSmem)));
+  stem_wgrad_tc_kernel<KH, KW, STRIDE, U8><<<static_cast<int>(grid), kStemThreads, SC::kSmem, st>>>(tdz, p, dw, dbias,
+                                                                                                  inv_scale);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
 }
 
 }  // namespace
@@ -758,10 +794,13 @@ int din_stem_tc_launch(const void* x, int x_is_u8, const float* w, const float* 
 }
 
 // Tensor-core stem weight gradient (see stem_wgrad_tc_kernel); arguments validated by din_stem_wgrad.
+// Geometries: VGG-16 (3x3, stride 1, pad 1) and ResNet-18 (7x7, stride 2, pad 3), 64 output channels.
 int din_stem_wgrad_tc_launch(const void* x, int x_is_u8, const void* dz, float* dw, float* dbias, const float* inv_scale,
-                             int n, int h, int w_in, int prep, cudaStream_t st) {
+                             int n, int h, int w_in, int kh, int stride, int pad, int prep, cudaStream_t st) {
   StemParams p{};
-  p.x = x; p.n = n; p.h = h; p.w_in = w_in; p.oh = h; p.ow = w_in; p.pad = 1; p.prep = prep;
+  p.x = x; p.n = n; p.h = h; p.w_in = w_in; p.pad = pad; p.prep = prep;
+  p.oh = (h + 2 * pad - kh) / stride + 1;
+  p.ow = (w_in + 2 * pad - kh) / stride + 1;
   p.strips_per_row = (p.ow + 127) / 128;
   const long long tiles = static_cast<long long>(n) * p.oh * p.strips_per_row;
   if (tiles >= INT32_MAX) return din_set_error(DIN_ERR_INVALID_ARG, "din_stem_wgrad: too many tiles");
@@ -770,26 +809,19 @@ int din_stem_wgrad_tc_launch(const void* x, int x_is_u8, const void* dz, float* 
   fastdiv(static_cast<uint32_t>(p.oh), &p.fo_mul, &p.fo_shr);
   CUtensorMap tdz;
   {
-    const uint64_t dims[4] = {64, static_cast<uint64_t>(w_in), static_cast<uint64_t>(h), static_cast<uint64_t>(n)};
-    const uint64_t strides[4] = {2, 128, 128ull * w_in, 128ull * w_in * h};
+    const uint64_t dims[4] = {64, static_cast<uint64_t>(p.ow), static_cast<uint64_t>(p.oh), static_cast<uint64_t>(n)};
+    const uint64_t strides[4] = {2, 128, 128ull * p.ow, 128ull * p.ow * p.oh};
     const uint32_t box[4] = {64, 128, 1, 1};
     const uint32_t es[4] = {1, 1, 1, 1};
     int rc = din_encode_tmap(&tdz, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(dz), dims, strides, box, es,
                              CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != DIN_OK) return rc;
   }
-  const int sms = din_num_sms();
-  long long grid = static_cast<long long>(sms > 0 ? sms : 148) * 4;
-  if (grid > p.num_tiles) grid = p.num_tiles;
-  if (x_is_u8) {
-    DIN_CHECK_CUDA(cudaFuncSetAttribute(stem_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(kSwgSmem)));
-    stem_wgrad_tc_kernel<true><<<static_cast<int>(grid), kStemThreads, kSwgSmem, st>>>(tdz, p, dw, dbias, inv_scale);
-  } else {
-    DIN_CHECK_CUDA(cudaFuncSetAttribute(stem_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(kSwgSmem)));
-    stem_wgrad_tc_kernel<false><<<static_cast<int>(grid), kStemThreads, kSwgSmem, st>>>(tdz, p, dw, dbias, inv_scale);
-  }
-  DIN_CHECK_CUDA(cudaGetLastError());
-  return DIN_OK;
+  if (kh == 3 && stride == 1)
+    return x_is_u8 ? launch_stem_wgrad<3, 3, 1, true>(tdz, p, dw, dbias, inv_scale, st)
+                   : launch_stem_wgrad<3, 3, 1, false>(tdz, p, dw, dbias, inv_scale, st);
+  if (kh == 7 && stride == 2)
+    return x_is_u8 ? launch_stem_wgrad<7, 7, 2, true>(tdz, p, dw, dbias, inv_scale, st)
+                   : launch_stem_wgrad<7, 7, 2, false>(tdz, p, dw, dbias, inv_scale, st);
+  return din_set_error(DIN_ERR_UNSUPPORTED, "din_stem_wgrad: unsupported stem geometry %dx%d stride %d", kh, kh, stride);
 }

@@ -47,6 +47,11 @@ PROTOTYPES = {
     "din_grad_to_f16": (C.c_int, [_fp, _vp, _fp, _ll, C.c_float, _vp]),
     "din_relu_pool_bwd_nhwc_f16": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "din_stem_wgrad": (C.c_int, [_vp, _i, _vp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "din_scatter2_nhwc_f16": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "din_add_f16": (C.c_int, [_vp, _vp, _vp, _ll, _vp]),
+    "din_maxpool3s2_relu_bwd_nhwc_f16": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "din_bn_gamma_grad_f16": (C.c_int, [_vp, _vp, _vp, _fp, _fp, _fp, _fp, _ll, _i, _vp]),
+    "din_scale_rows_f32": (C.c_int, [_fp, _fp, _ll, _ll, _vp]),
     "din_gemm_f32": (C.c_int, [_fp, _ll, _ll, _vp, _i, _ll, _ll, _fp, _ll, _i, _i, _i, C.c_float, _i, _vp]),
     "din_colsum_f32": (C.c_int, [_fp, _fp, _i, _i, _ll, _vp]),
     "din_scale_mask_f32": (C.c_int, [_fp, _vp, C.c_float, _fp, _ll, _vp]),

@@ -514,15 +514,80 @@ def relu_pool_bwd_nhwc(y, dy, pool):
     return dz
 
 
-def stem_wgrad(x, dz, dw, dbias, *, inv_scale=None, prep=True):
-    """VGG-16 stem: dw [64,3,3,3] fp32 (OIHW), dbias [64] (+)= ...; x raw frames (fp32 NCHW or uint8 NHWC)."""
+def stem_wgrad(x, dz, dw, dbias, *, stride=1, pad=1, inv_scale=None, prep=True):
+    """Stem weight gradient: dw [64,3,k,k] fp32 (OIHW), dbias [64] (+)= ...; x raw frames (fp32 NCHW or uint8 NHWC).
+    VGG-16: k = 3, stride 1, pad 1;  ResNet-18: k = 7, stride 2, pad 3."""
     u8 = x.dtype == torch.uint8
     _need(x, torch.uint8 if u8 else torch.float32, "x")
     _need(dz, torch.float16, "dz")
     _need(dw, torch.float32, "dw")
     n, h, w = (x.shape[0], x.shape[1], x.shape[2]) if u8 else (x.shape[0], x.shape[2], x.shape[3])
-    assert tuple(dz.shape) == (n, h, w, 64) and tuple(dw.shape) == (64, 3, 3, 3)
-    with _launch("stem_wgrad", 2 * n * h * w * 64 * 27, x.numel() * x.element_size() + 2 * dz.numel()):
-        check(_lib.load().din_stem_wgrad(_p(x), int(u8), _p(dz), _p(dw), _p(dbias), _p(inv_scale), n, h, w, 64, 3, 3, 1, 1,
-                                         int(prep), _stream()), "din_stem_wgrad")
+    k = dw.shape[2]
+    oh, ow = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    assert tuple(dz.shape) == (n, oh, ow, 64) and tuple(dw.shape) == (64, 3, k, k), (tuple(dz.shape), tuple(dw.shape))
+    with _launch(f"stem_wgrad{k}x{k}", 2 * n * oh * ow * 64 * 3 * k * k, x.numel() * x.element_size() + 2 * dz.numel()):
+        check(_lib.load().din_stem_wgrad(_p(x), int(u8), _p(dz), _p(dw), _p(dbias), _p(inv_scale), n, h, w, 64, k, k,
+                                         stride, pad, int(prep), _stream()), "din_stem_wgrad")
     return dw
+
+
+def scatter2_nhwc(src, h, w, dst=None):
+    """dst[n, 2oy, 2ox] (+)= src[n, oy, ox]: dst None -> zero insertion into a new [n,h,w,c]; else accumulate."""
+    _need(src, torch.float16, "src")
+    n, oh, ow, c = src.shape
+    acc = dst is not None
+    if dst is None:
+        dst = torch.empty((n, h, w, c), dtype=torch.float16, device=src.device)
+    _need(dst, torch.float16, "dst")
+    assert tuple(dst.shape) == (n, h, w, c)
+    with _launch("scatter2", 0, 2 * (src.numel() + dst.numel())):
+        check(_lib.load().din_scatter2_nhwc_f16(_p(src), _p(dst), n, h, w, c, oh, ow, int(acc), _stream()),
+              "din_scatter2_nhwc_f16")
+    return dst
+
+
+def add_f16(a, b):
+    _need(a, torch.float16, "a")
+    _need(b, torch.float16, "b")
+    assert a.shape == b.shape
+    y = torch.empty_like(a)
+    with _launch("add_f16", 0, 6 * a.numel()):
+        check(_lib.load().din_add_f16(_p(a), _p(b), _p(y), a.numel(), _stream()), "din_add_f16")
+    return y
+
+
+def maxpool3s2_relu_bwd_nhwc(x, dy):
+    """x [n,h,w,c] saved ReLU output, dy [n,oh,ow,c] -> dz [n,h,w,c] (MaxPool2d(3,2,1) + ReLU backward)."""
+    _need(x, torch.float16, "x")
+    _need(dy, torch.float16, "dy")
+    n, h, w, c = x.shape
+    assert tuple(dy.shape) == (n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c), (tuple(x.shape), tuple(dy.shape))
+    dz = torch.empty_like(x)
+    with _launch("maxpool3s2_bwd", 0, 2 * (2 * x.numel() + dy.numel())):
+        check(_lib.load().din_maxpool3s2_relu_bwd_nhwc_f16(_p(x), _p(dy), _p(dz), n, h, w, c, _stream()),
+              "din_maxpool3s2_relu_bwd_nhwc_f16")
+    return dz
+
+
+def bn_gamma_grad(dz, zsrc, gamma, beta, dgamma, *, sub=None, inv_scale=None):
+    """dgamma [c] fp32 += inv_scale * sum dz * ((zsrc - sub) - beta) / gamma   (eval-mode BN folded into its conv)."""
+    _need(dz, torch.float16, "dz")
+    _need(zsrc, torch.float16, "zsrc")
+    _need(dgamma, torch.float32, "dgamma")
+    c = dz.shape[-1]
+    rows = dz.numel() // c
+    assert zsrc.shape == dz.shape and (sub is None or sub.shape == dz.shape)
+    with _launch("bn_gamma_grad", 0, 2 * dz.numel() * (3 if sub is not None else 2)):
+        check(_lib.load().din_bn_gamma_grad_f16(_p(dz), _p(zsrc), _p(sub), _p(gamma), _p(beta), _p(dgamma), _p(inv_scale),
+                                                rows, c, _stream()), "din_bn_gamma_grad_f16")
+    return dgamma
+
+
+def scale_rows(w, scale):
+    """w[r] *= scale[r] in place (w fp32 [rows, ...])."""
+    _need(w, torch.float32, "w")
+    _need(scale, torch.float32, "scale")
+    rows = w.shape[0]
+    with _launch("scale_rows", 0, 8 * w.numel()):
+        check(_lib.load().din_scale_rows_f32(_p(w), _p(scale), rows, w.numel() // rows, _stream()), "din_scale_rows_f32")
+    return w

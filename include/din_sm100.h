@@ -355,14 +355,51 @@ DIN_API int din_relu_pool_bwd_nhwc_f16(const void* y, const void* dy, void* dz, 
                                        void* stream);
 
 /*
- * Weight / bias gradient of the stem convolution (VGG-16 features.0: 64 x 3 x 3x3, stride 1, pad 1), with
- * prep_images recomputed on the raw frames (fp32 NCHW, or uint8 NHWC when x_is_u8):
- *   dw [64][3][3][3] (OIHW) += inv_scale * sum_pixels dz (x) prep(x)_shifted;   dbias [64] += inv_scale * sum dz.
- * ACCUMULATES (atomics): zero-fill before the first call of a step.
+ * Weight / bias gradient of the stem convolution -- VGG-16 features.0 (64 x 3 x 3x3, stride 1, pad 1) or ResNet-18
+ * conv1 (64 x 3 x 7x7, stride 2, pad 3; BN folded: the caller un-folds) -- with prep_images recomputed on the raw
+ * frames (fp32 NCHW, or uint8 NHWC when x_is_u8), on the tensor cores:
+ *   dw [64][3][kh][kw] (OIHW) += inv_scale * sum_pixels dz (x) prep(x)_shifted;   dbias [64] += inv_scale * sum dz.
+ * dz: fp16 NHWC [n, oh, ow, 64].  ACCUMULATES (atomics): zero-fill before the first call of a step.
  */
 DIN_API int din_stem_wgrad(const void* x, int x_is_u8, const void* dz, float* dw, float* dbias, const float* inv_scale,
                            int n, int h, int w, int c_out, int kh, int kw, int stride, int pad, int prep,
                            void* stream);
+
+/* ---- ResNet-18 backward helpers (stride-2 convolutions, 3x3/2 max-pool, eval-mode BatchNorm folded into the convs) -- */
+
+/*
+ * dst[n, 2*oy, 2*ox, :] (+)= src[n, oy, ox, :]  (NHWC fp16; dst is [n,h,w,c], src [n,oh,ow,c]).
+ * accumulate == 0: zero insertion -- the gradient of a stride-2 convolution's output laid out on its input grid, so
+ *   that dX = din_conv2d_nhwc_f16(dZ_up, rot180(W)^T) and dW = din_conv2d_wgrad_nhwc_f16(X, dZ_up) are the stride-1
+ *   kernels (resnet18 layer{2,3,4}.0.conv1, backbone.py:115-132);  accumulate != 0: adds src at the even positions
+ *   (data gradient of the 1x1 stride-2 shortcut, layer{2,3,4}.0.downsample.0).
+ */
+DIN_API int din_scatter2_nhwc_f16(const void* src, void* dst, int n, int h, int w, int c, int oh, int ow, int accumulate,
+                                  void* stream);
+
+/* y = a + b, fp16, count elements (multiple of 8): merging the two gradient branches of a residual block. */
+DIN_API int din_add_f16(const void* a, const void* b, void* y, long long count, void* stream);
+
+/*
+ * Backward of resnet18.relu + resnet18.maxpool (MaxPool2d(3, 2, 1)): x = the saved ReLU output [n,h,w,c], dy the
+ * gradient of the pooled map [n,oh,ow,c] -> dz [n,h,w,c]: every window sends its gradient to its FIRST maximum (scan
+ * order, padding never wins, as torch), masked by x > 0.
+ */
+DIN_API int din_maxpool3s2_relu_bwd_nhwc_f16(const void* x, const void* dy, void* dz, int n, int h, int w, int c,
+                                             void* stream);
+
+/*
+ * Gradient of an eval-mode BatchNorm's weight when the BN is folded into its convolution (z = gamma*xhat + beta):
+ *   dgamma[c] += inv_scale * sum_p dz[p,c] * ((zsrc[p,c] - sub[p,c]) - beta[c]) / gamma[c]      (sub may be NULL)
+ * zsrc: the saved activation (post-ReLU serves: dz is zero wherever the ReLU clipped); sub: the residual that was
+ * added before the ReLU (BasicBlock.bn2).  d(beta) is the convolution's bias gradient.  Rows of c fp16 values.
+ */
+DIN_API int din_bn_gamma_grad_f16(const void* dz, const void* zsrc, const void* sub, const float* gamma,
+                                  const float* beta, float* dgamma, const float* inv_scale, long long rows, int c,
+                                  void* stream);
+
+/* w[r][:] *= scale[r]: un-folds the BN scale from a folded convolution's weight gradient. */
+DIN_API int din_scale_rows_f32(float* w, const float* scale, long long rows, long long cols, void* stream);
 
 #ifdef __cplusplus
 } /* extern "C" */

@@ -145,3 +145,108 @@ def test_grad_to_f16_scale(cuda):
     assert torch.equal(y, (x * s).half())
     z, ws = ops.grad_to_f16(torch.zeros(16, device=cuda))
     assert ws[1].item() == 1.0 and (z == 0).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# ResNet-18 backward helpers
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(2, 12, 16, 64), (1, 45, 81, 64), (2, 9, 7, 8)], ids=str)
+def test_maxpool3s2_relu_bwd_matches_torch(cuda, shape):
+    from din_b200 import ops
+    n, h, w, c = shape
+    g = torch.Generator().manual_seed(w)
+    x = F.relu((torch.randn(n, h, w, c, generator=g) * 2).round() / 2).to(cuda).half()        # ties + zeros
+    xx = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    out = F.max_pool2d(xx, 3, 2, 1)
+    dy = torch.randn(out.shape, generator=g).to(cuda).half()
+    out.backward(dy.float())
+    ref = (xx.grad * (xx.detach() > 0)).permute(0, 2, 3, 1)
+    dz = ops.maxpool3s2_relu_bwd_nhwc(x, dy.permute(0, 2, 3, 1).contiguous())
+    torch.cuda.synchronize()
+    # a pixel can collect up to four windows' gradients: sums of fp16 values, rounded once more to fp16
+    assert (dz.float() - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
+    assert ((dz.float() != 0) == (ref != 0)).float().mean().item() > 0.999
+
+
+def test_scatter2_add_and_scale_rows(cuda):
+    from din_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    src = torch.randn(2, 5, 7, 16, generator=g).to(cuda).half()
+    up = ops.scatter2_nhwc(src, 9, 13)
+    ref = torch.zeros(2, 9, 13, 16, device=cuda, dtype=torch.float16)
+    ref[:, ::2, ::2] = src
+    assert torch.equal(up, ref)
+    base = torch.randn(2, 10, 14, 16, generator=g).to(cuda).half()
+    want = base.clone()
+    want[:, :10:2, :14:2] += src
+    ops.scatter2_nhwc(src, 10, 14, dst=base)
+    assert torch.equal(base, want)
+    a, b = torch.randn(3, 40, generator=g).to(cuda).half(), torch.randn(3, 40, generator=g).to(cuda).half()
+    assert torch.equal(ops.add_f16(a, b), a + b)
+    wgt = torch.randn(6, 3, 3, 8, generator=g).to(cuda)
+    sc = torch.rand(6, generator=g).to(cuda) + 0.5
+    want = wgt * sc.view(-1, 1, 1, 1)
+    assert torch.allclose(ops.scale_rows(wgt.clone(), sc), want, rtol=1e-6, atol=0)
+
+
+def test_stride2_conv_backward_by_zero_insertion(cuda):
+    """dX and dW of a 3x3 stride-2 pad-1 convolution through the STRIDE-1 kernels on the zero-inserted dZ."""
+    from din_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    n, h, w, cin, cout = 2, 23, 40, 64, 128
+    x = torch.randn(n, h, w, cin, generator=g).to(cuda).half()
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) * 0.05).to(cuda)
+    oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    dz = torch.randn(n, oh, ow, cout, generator=g).to(cuda).half()
+    xr = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    w_dgrad = ops.pack_conv_weight(wt.permute(1, 0, 2, 3).flip(2, 3).contiguous())
+    w_used = w_dgrad[..., :cout].float().permute(0, 3, 1, 2).flip(2, 3).permute(1, 0, 2, 3).contiguous().requires_grad_(True)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    F.conv2d(xr, w_used, None, stride=2, padding=1).backward(dz.float().permute(0, 3, 1, 2))
+    torch.backends.cudnn.allow_tf32 = old
+    dz_up = ops.scatter2_nhwc(dz, h, w)
+    dx = ops.conv2d_nhwc(dz_up, w_dgrad, None, stride=1, pad=(1, 1), relu=False)
+    dw = torch.zeros(cout, 3, 3, cin, device=cuda)
+    ops.conv2d_wgrad_nhwc(x, dz_up, dw, None, pad=(1, 1))
+    torch.cuda.synchronize()
+    ref_dx = xr.grad.permute(0, 2, 3, 1)
+    assert (dx.float() - ref_dx).abs().max().item() <= 2e-3 * ref_dx.abs().max().item()
+    ref_dw = w_used.grad.permute(0, 2, 3, 1)
+    assert (dw - ref_dw).abs().max().item() <= 1e-3 * ref_dw.abs().max().item()
+
+
+def test_bn_gamma_grad_and_stem7_wgrad(cuda):
+    from din_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    # folded eval-mode BN + residual + ReLU: dgamma from the saved post-ReLU activation
+    n, h, w, c = 2, 9, 11, 64
+    conv = torch.randn(n, c, h, w, generator=g).to(cuda)
+    idn = torch.randn(n, c, h, w, generator=g).to(cuda).half().float()
+    gamma = (torch.rand(c, generator=g) + 0.5).to(cuda).requires_grad_(True)
+    beta = (torch.randn(c, generator=g) * 0.2).to(cuda)
+    mean, var = torch.randn(c, generator=g).to(cuda) * 0.1, torch.rand(c, generator=g).to(cuda) + 0.5
+    z = F.batch_norm(conv, mean, var, gamma, beta, training=False, eps=1e-5)
+    y = F.relu(z + idn)
+    dy = torch.randn(y.shape, generator=g).to(cuda)
+    y.backward(dy)
+    yh = y.detach().permute(0, 2, 3, 1).contiguous().half()
+    dzh = (dy * (y.detach() > 0)).permute(0, 2, 3, 1).contiguous().half()
+    dgam = torch.zeros(c, device=cuda)
+    ops.bn_gamma_grad(dzh, yh, gamma.detach(), beta, dgam, sub=idn.permute(0, 2, 3, 1).contiguous().half())
+    torch.cuda.synchronize()
+    assert (dgam - gamma.grad).abs().max().item() <= 5e-3 * gamma.grad.abs().max().item()
+    # ResNet stem: 7x7 stride 2 pad 3 on prep(raw)
+    raw = torch.randint(0, 256, (2, 3, 45, 150), generator=g).float().to(cuda)
+    wt = torch.zeros(64, 3, 7, 7, device=cuda, requires_grad=True)
+    bias = torch.zeros(64, device=cuda, requires_grad=True)
+    out = F.conv2d(((raw / 255.0) - 0.5) * 2.0, wt, bias, stride=2, padding=3)
+    dz = (torch.randn(out.shape, generator=g) * 0.5).to(cuda).half()
+    out.backward(dz.float())
+    for u8 in (False, True):
+        dw, db = torch.zeros(64, 3, 7, 7, device=cuda), torch.zeros(64, device=cuda)
+        xin = raw.permute(0, 2, 3, 1).contiguous().to(torch.uint8) if u8 else raw
+        ops.stem_wgrad(xin, dz.permute(0, 2, 3, 1).contiguous(), dw, db, stride=2, pad=3)
+        torch.cuda.synchronize()
+        assert (dw - wt.grad).abs().max().item() <= 2e-3 * wt.grad.abs().max().item(), u8
+        assert (db - bias.grad).abs().max().item() <= 2e-3 * bias.grad.abs().max().item(), u8
