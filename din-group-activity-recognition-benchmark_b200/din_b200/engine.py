@@ -35,8 +35,10 @@ def _fold_bn(conv_w, bn):
 class _Conv:
     """One tcgen05 convolution of the plan (weights packed fp16 [co][kh][kw][ci], fp32 bias)."""
 
-    def __init__(self, w, bias, scale=None, stride=1, pad=(0, 0), relu=True, pool2=False, split=1):
+    def __init__(self, w, bias, scale=None, stride=1, pad=(0, 0), relu=True, pool2=False, split=1, bn=None):
         self.w_src = w                     # fp32 OIHW, kept by reference for the (lazily packed) dgrad filter
+        self.bn_scale = scale              # folded eval-mode BatchNorm: gamma / sqrt(var + eps) (None: no BN)
+        self.bn = bn                       # its {'weight', 'bias', ...} (training: d(gamma) needs gamma and beta)
         self._w_dgrad = None
         self.w = ops.pack_conv_weight(w.contiguous(), scale, split=split)
         self.bias = None if bias is None else bias.contiguous().float()
@@ -50,16 +52,20 @@ class _Conv:
                                residual=residual, out=out, pool2=self.pool2, **kw)
 
     def dgrad(self, dz):
-        """dX of a 3x3 stride-1 pad-1 convolution = the forward kernel on dZ with the filter rotated by 180 degrees
-        and its channel axes swapped (packed once per weight version; layout ops only)."""
-        assert self.stride == 1 and tuple(self.w_src.shape[2:]) == (3, 3) and self.pad == (1, 1)
+        """dX of a stride-1 convolution (3x3 pad 1, or 1x1) = the forward kernel on dZ with the filter rotated by 180
+        degrees and its channel axes swapped (packed once per weight version; a folded BN scale is multiplied in: one-time
+        weight prep).  Stride-2 layers pass the zero-inserted dZ (ops.scatter2_nhwc)."""
+        k = self.w_src.shape[2]
+        assert k == self.w_src.shape[3] and k in (1, 3)
         if self._w_dgrad is None:
-            self._w_dgrad = ops.pack_conv_weight(self.w_src.permute(1, 0, 2, 3).flip(2, 3).contiguous())
-        return ops.conv2d_nhwc(dz, self._w_dgrad, None, stride=1, pad=(1, 1), relu=False)
+            w = self.w_src if self.bn_scale is None else self.w_src * self.bn_scale.view(-1, 1, 1, 1)
+            self._w_dgrad = ops.pack_conv_weight(w.permute(1, 0, 2, 3).flip(2, 3).contiguous())
+        return ops.conv2d_nhwc(dz, self._w_dgrad, None, stride=1, pad=(k // 2, k // 2), relu=False)
 
 
 class _Stem:
-    def __init__(self, w, bias, scale=None, stride=1, pad=0):
+    def __init__(self, w, bias, scale=None, stride=1, pad=0, bn=None):
+        self.bn_scale, self.bn = scale, bn
         if scale is not None:
             w = w * scale.view(-1, 1, 1, 1)       # one-time weight prep (BN folding), not on the hot path
         self.w, self.bias, self.stride, self.pad = w.contiguous().float(), bias.contiguous().float(), stride, pad
@@ -161,7 +167,9 @@ class Res18Plan:
             return {k: sd[f"{p}.{k}"] for k in ("weight", "bias", "running_mean", "running_var")} | {"eps": 1e-5}
 
         w, s, b = _fold_bn(sd[prefix + "0.weight"], bn(prefix + "1"))
-        self.stem = _Stem(w, b, scale=s, stride=2, pad=3)
+        self.stem = _Stem(w, b, scale=s, stride=2, pad=3, bn=bn(prefix + "1"))
+        self.prefix = prefix
+        self.block_names = []
         self.blocks = []
         chans = [64, 128, 256, 512]
         for li, c in enumerate(chans):
@@ -170,13 +178,14 @@ class Res18Plan:
                 stride = 2 if (li > 0 and bi == 0) else 1
                 w1, s1, b1 = _fold_bn(sd[p + "conv1.weight"], bn(p + "bn1"))
                 w2, s2, b2 = _fold_bn(sd[p + "conv2.weight"], bn(p + "bn2"))
-                conv1 = _Conv(w1, b1, s1, stride=stride, pad=(1, 1), relu=True)
-                conv2 = _Conv(w2, b2, s2, stride=1, pad=(1, 1), relu=True)   # ReLU after the residual add
+                conv1 = _Conv(w1, b1, s1, stride=stride, pad=(1, 1), relu=True, bn=bn(p + "bn1"))
+                conv2 = _Conv(w2, b2, s2, stride=1, pad=(1, 1), relu=True, bn=bn(p + "bn2"))   # ReLU after the residual add
                 down = None
                 if (p + "downsample.0.weight") in sd:
                     wd, sdn, bd = _fold_bn(sd[p + "downsample.0.weight"], bn(p + "downsample.1"))
-                    down = _Conv(wd, bd, sdn, stride=stride, pad=(0, 0), relu=False)
+                    down = _Conv(wd, bd, sdn, stride=stride, pad=(0, 0), relu=False, bn=bn(p + "downsample.1"))
                 self.blocks.append((conv1, conv2, down))
+                self.block_names.append(p)
         self.out_channels = 512
 
     def __call__(self, images, out=None):
@@ -196,6 +205,85 @@ class Res18Plan:
         for _ in range(4):
             h, w = c(h, 3, 2, 1), c(w, 3, 2, 1)
         return h, w, 512
+
+    # -- training (BatchNorm in eval mode, i.e. folded, as cfg.set_bn_eval leaves it) -----------
+    def forward_train(self, images, out=None):
+        """As __call__, keeping the stem output and every block's (input, conv1 output, identity, output)."""
+        x0 = self.stem(images)
+        x = ops.maxpool2d_nhwc(x0, 3, 2, 1)
+        saved = {"images": images, "x0": x0, "blocks": []}
+        last = len(self.blocks) - 1
+        for i, (conv1, conv2, down) in enumerate(self.blocks):
+            identity = x if down is None else down(x)
+            a1 = conv1(x)
+            y = conv2(a1, residual=identity, out=out if i == last else None)
+            saved["blocks"].append((x, a1, identity, y))
+            x = y
+        return x, saved
+
+    @staticmethod
+    def _acc(co, ci, device, taps=3):
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=device)  # noqa: E731
+        return {"dw": z(co, taps, taps, ci), "dbeta": z(co), "dgamma": z(co)}
+
+    def new_grads(self, device):
+        """Zero-filled fp32 accumulators of the FOLDED convolutions ([co][3][3][ci]; the stem's in OIHW; the 1x1
+        shortcut's as the centre tap of a 3x3) plus d(beta) / d(gamma) of every BatchNorm."""
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=device)  # noqa: E731
+        acc = {"stem": {"dw": z(64, 3, 7, 7), "dbeta": z(64), "dgamma": z(64)}, "blocks": []}
+        for conv1, conv2, down in self.blocks:
+            acc["blocks"].append((self._acc(conv1.c_out, conv1.c_in, device), self._acc(conv2.c_out, conv2.c_in, device),
+                                  None if down is None else self._acc(down.c_out, down.c_in, device)))
+        return acc
+
+    def backward(self, saved, d_out, inv_scale, acc):
+        """d_out: fp16 gradient (times the loss scale) w.r.t. this chunk's feature map; accumulates into `acc`.
+        Stride-2 layers go through zero insertion (ops.scatter2_nhwc), so dgrad / wgrad stay the stride-1 kernels."""
+        def gamma_grad(conv, a, dz, z, sub=None):
+            ops.bn_gamma_grad(dz, z, conv.bn["weight"], conv.bn["bias"], a["dgamma"], sub=sub, inv_scale=inv_scale)
+
+        d = d_out
+        for bi in reversed(range(len(self.blocks))):
+            x_in, a1, identity, y = saved["blocks"][bi]
+            conv1, conv2, down = self.blocks[bi]
+            a_c1, a_c2, a_dn = acc["blocks"][bi]
+            h_in, w_in = x_in.shape[1:3]
+            dz2 = ops.relu_pool_bwd_nhwc(y, d, False)                         # ReLU after the residual add
+            ops.conv2d_wgrad_nhwc(a1, dz2, a_c2["dw"], a_c2["dbeta"], pad=(1, 1), inv_scale=inv_scale)
+            gamma_grad(conv2, a_c2, dz2, y, sub=identity)
+            dz1 = ops.relu_pool_bwd_nhwc(a1, conv2.dgrad(dz2), False)
+            gamma_grad(conv1, a_c1, dz1, a1)
+            dz1u = ops.scatter2_nhwc(dz1, h_in, w_in) if conv1.stride == 2 else dz1
+            ops.conv2d_wgrad_nhwc(x_in, dz1u, a_c1["dw"], a_c1["dbeta"], pad=(1, 1), inv_scale=inv_scale)
+            dx = conv1.dgrad(dz1u)
+            if down is None:
+                dx = ops.add_f16(dx, dz2)                                     # the identity shortcut
+            else:
+                # 1x1 stride-2 shortcut: its weight gradient is the centre tap of a 3x3 pad-1 wgrad on the zero-inserted
+                # dZ (9x the useful work on three small layers, no extra tensor-core kernel)
+                dz2u = ops.scatter2_nhwc(dz2, h_in, w_in)
+                ops.conv2d_wgrad_nhwc(x_in, dz2u, a_dn["dw"], a_dn["dbeta"], pad=(1, 1), inv_scale=inv_scale)
+                gamma_grad(down, a_dn, dz2, identity)
+                ops.scatter2_nhwc(down.dgrad(dz2), h_in, w_in, dst=dx)
+            d = dx
+        dz0 = ops.maxpool3s2_relu_bwd_nhwc(saved["x0"], d)
+        a0 = acc["stem"]
+        ops.stem_wgrad(saved["images"], dz0, a0["dw"], a0["dbeta"], stride=2, pad=3, inv_scale=inv_scale, prep=True)
+        ops.bn_gamma_grad(dz0, saved["x0"], self.stem.bn["weight"], self.stem.bn["bias"], a0["dgamma"], inv_scale=inv_scale)
+
+    def export_grads(self, acc, grads):
+        """accumulators -> {reference parameter name: gradient}: un-fold the BN scale from the conv weight gradients
+        (din_scale_rows_f32), OIHW layout (permutes only)."""
+        def put(conv_name, bn_name, conv, a, w_oihw):
+            grads[conv_name + ".weight"] = ops.scale_rows(w_oihw.contiguous(), conv.bn_scale)
+            grads[bn_name + ".weight"], grads[bn_name + ".bias"] = a["dgamma"], a["dbeta"]
+
+        put(self.prefix + "0", self.prefix + "1", self.stem, acc["stem"], acc["stem"]["dw"])
+        for p, (conv1, conv2, down), (a1, a2, ad) in zip(self.block_names, self.blocks, acc["blocks"]):
+            put(p + "conv1", p + "bn1", conv1, a1, a1["dw"].permute(0, 3, 1, 2))
+            put(p + "conv2", p + "bn2", conv2, a2, a2["dw"].permute(0, 3, 1, 2))
+            if down is not None:
+                put(p + "downsample.0", p + "downsample.1", down, ad, ad["dw"][:, 1:2, 1:2, :].permute(0, 3, 1, 2))
 
 
 def build_backbone_plan(name, sd):

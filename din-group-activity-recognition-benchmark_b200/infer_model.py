@@ -8,9 +8,10 @@ are parameter containers and are never called.
 
 Scope: evaluation / inference forward, and the training step: `model.train()` + `loss.backward()` produce
 gradients for every parameter after the backbone through the backward kernels in csrc/head_bwd.cu, and -- with
-cfg.train_backbone = True and the VGG-16 backbone -- for the backbone too (RoIAlign scatter, ReLU / max-pool
-backward, dgrad on the forward tcgen05 kernel, wgrad on csrc/conv_wgrad_tcgen05.cu).
-Training the ResNet-18 / Inception-v3 backbones (stride-2 dgrad, BatchNorm) is not implemented and raises.
+cfg.train_backbone = True and the VGG-16 or ResNet-18 backbone (BatchNorm in eval mode) -- for the backbone too
+(RoIAlign scatter, ReLU / max-pool backward, dgrad on the forward tcgen05 kernel, wgrad on
+csrc/conv_wgrad_tcgen05.cu, zero insertion for the stride-2 layers).
+Training the Inception-v3 backbone, or BatchNorm with batch statistics, is not implemented and raises.
 """
 import collections
 
@@ -155,9 +156,9 @@ class _DinModel(nn.Module):
                 "the reference does with cfg.set_bn_eval (train_net_dynamic.py:101-102, model.apply(set_bn_eval))")
         if not torch.is_grad_enabled():
             return _train.forward_train(eng, images, boxes, bboxes_num, training=True)[0]
-        if any(p.requires_grad for p in self.backbone.parameters()) and self.cfg.backbone != "vgg16":
+        if any(p.requires_grad for p in self.backbone.parameters()) and self.cfg.backbone not in ("vgg16", "res18"):
             raise NotImplementedError(
-                f"training the backbone is implemented for VGG-16 only (3x3 stride-1 dgrad / wgrad kernels), not "
+                f"training the backbone is implemented for VGG-16 and ResNet-18 (BatchNorm in eval mode), not "
                 f"{self.cfg.backbone!r}: set cfg.train_backbone = False (config.py:39, the stage-2 default) -- "
                 "SURVEY.md §8f rank 1")
         named = [(n, p) for n, p in self.named_parameters() if p.requires_grad]

@@ -84,18 +84,24 @@ def main_grads():
                     "weights_checksum": checksum(sd.values()), "inputs_checksum": checksum(batch)},
                    os.path.join(OUT, f"grads_{name}.pt"))
         print("grads", name, float(loss), len(grads))
-    # the whole model trained, backbone included (scripts/train_volleyball_stage2_dynamic.py:12)
-    pc, B = model_cases()["vgg16_lite"]
-    bb = O.build_backbone(pc.backbone)
-    sd = O.make_state_dict(pc, seed=0, backbone=bb)
-    batch = O.make_inputs(pc, B, seed=0)
-    labels = torch.arange(B) % pc.num_activities
-    logits, loss, grads = R.ref_head_grads(pc, sd, labels, *batch, train_backbone=True)
-    torch.save({"config": dataclasses.asdict(pc), "B": B, "seed": 0, "labels": labels, "logits_ref": logits,
-                "loss_ref": loss, "grads_ref": {k: O.grad_digest(v) for k, v in grads.items()},
-                "weights_checksum": checksum(sd.values()), "inputs_checksum": checksum(batch),
-                "train_backbone": True}, os.path.join(OUT, "fullgrads_vgg16_lite.pt"))
-    print("fullgrads vgg16_lite", float(loss), len(grads))
+    main_fullgrads()
+
+
+def main_fullgrads():
+    """The whole model trained, backbone included (scripts/train_volleyball_stage2_dynamic.py:12); ResNet-18 with its
+    BatchNorm layers in eval mode (config.py set_bn_eval / train_net.py:25-28)."""
+    for name in ("vgg16_lite", "res18_lite"):
+        pc, B = model_cases()[name]
+        bb = O.build_backbone(pc.backbone)
+        sd = O.make_state_dict(pc, seed=0, backbone=bb)
+        batch = O.make_inputs(pc, B, seed=0)
+        labels = torch.arange(B) % pc.num_activities
+        logits, loss, grads = R.ref_head_grads(pc, sd, labels, *batch, train_backbone=True)
+        torch.save({"config": dataclasses.asdict(pc), "B": B, "seed": 0, "labels": labels, "logits_ref": logits,
+                    "loss_ref": loss, "grads_ref": {k: O.grad_digest(v) for k, v in grads.items()},
+                    "weights_checksum": checksum(sd.values()), "inputs_checksum": checksum(batch),
+                    "train_backbone": True}, os.path.join(OUT, f"fullgrads_{name}.pt"))
+        print("fullgrads", name, float(loss), len(grads))
 
 
 def main_basenet_grads():
@@ -121,6 +127,9 @@ def main_basenet_grads():
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--fullgrads-only" in sys.argv:
+        main_fullgrads()
+        sys.exit(0)
     if "--basenet-grads-only" in sys.argv:
         return main_basenet_grads()
     if "--grads-only" in sys.argv:

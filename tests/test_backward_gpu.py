@@ -409,26 +409,30 @@ def test_optimizer_loop_and_modes(cuda):
     model.eval()
     with torch.no_grad():
         assert torch.isfinite(model(batch)["activities"]).all()
-    # ResNet-18: training the backbone / batch-statistics BatchNorm are not implemented: loud errors
-    pc2 = _pc("res18", (96, 160), num_frames=3, num_boxes=4)
-    m2, _ = _model_and_cfg(cuda, pc2, O.make_state_dict(pc2, seed=0), 0.3)
-    for q in m2.backbone.parameters():
+    # training the Inception-v3 backbone / batch-statistics BatchNorm are not implemented: loud errors
+    pc3 = _pc("inv3", (139, 203), emb_features=1056, num_frames=2, num_boxes=4, lite_dim=None)
+    m3, _ = _model_and_cfg(cuda, pc3, O.make_state_dict(pc3, seed=0), 0.3)
+    for q in m3.backbone.parameters():
         q.requires_grad = True
     with pytest.raises(NotImplementedError, match="training the backbone"):
-        m2(batch)
+        m3(tuple(t.to(cuda) for t in O.make_inputs(pc3, 2, seed=0)))
+    pc2 = _pc("res18", (96, 160), num_frames=3, num_boxes=4)
+    m2, _ = _model_and_cfg(cuda, pc2, O.make_state_dict(pc2, seed=0), 0.3)
     m2.train()                                        # BatchNorm back to batch statistics
     with pytest.raises(NotImplementedError, match="BatchNorm"):
         m2(batch)
 
 
-def test_full_training_step_with_backbone(cuda):
-    """cfg.train_backbone = True on VGG-16 (scripts/train_volleyball_stage2_dynamic.py:12): gradients of all 43
-    parameter tensors vs autograd over the oracle, and vs the REFERENCE model's gradients (fixture).
+@pytest.mark.parametrize("case", ["vgg16_lite", "res18_lite"])
+def test_full_training_step_with_backbone(cuda, case):
+    """cfg.train_backbone = True (scripts/train_volleyball_stage2_dynamic.py:12) on VGG-16 (43 parameter tensors) and
+    ResNet-18 (77, BatchNorm in eval mode: gamma / beta still train): every gradient vs autograd over the oracle, and
+    vs the REFERENCE model's gradients (fixture).
     The backbone's backward runs on fp16 tensor-core operands (dynamic loss scale): relative L2 per tensor."""
     import din_oracle as O
     from din_b200 import metrics
     from test_oracle_cpu import _pc_from
-    fx = torch.load(os.path.join(GOLDEN, "fullgrads_vgg16_lite.pt"))
+    fx = torch.load(os.path.join(GOLDEN, f"fullgrads_{case}.pt"))
     pc = _pc_from(fx["config"])
     bb = O.build_backbone(pc.backbone)
     sd = O.make_state_dict(pc, seed=fx["seed"], backbone=bb)
