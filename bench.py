@@ -136,7 +136,7 @@ def build_model(pc, device):
 
 def train_step_info(model, pc, dev, images_d, boxes_d, clips, steps=5, warmup=2):
     """Supplementary (NOT the headline metric): one stage-2 TRAINING step -- train-mode forward, on-device
-    cross-entropy, backward through the head and the VGG-16 backbone -- on `clips` clips
+    cross-entropy, backward through the head and the VGG-16 / ResNet-18 backbone -- on `clips` clips
     (scripts/train_volleyball_stage2_dynamic.py:42 batch_size = 2), followed by torch's SGD step with lr = 0: the update
     itself is torch's, but it bumps the weights' versions, so the timed step includes re-packing every weight into the
     kernels' fp16 layouts, as a real training loop pays it."""
@@ -144,6 +144,9 @@ def train_step_info(model, pc, dev, images_d, boxes_d, clips, steps=5, warmup=2)
     from din_b200 import metrics, ops
     try:
         model.train()
+        for m in model.modules():                           # the reference's set_bn_eval (train_net_dynamic.py:101-102)
+            if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+                m.eval()
         for q in model.parameters():
             q.requires_grad = True
         im, bx = images_d[:clips].contiguous(), boxes_d[:clips].contiguous()
@@ -471,7 +474,7 @@ def main():
                           "h2d_bytes_per_step": e2e_u8["h2d"], "d2h_bytes_per_step": e2e_u8["d2h"],
                           "input": "uint8 [B,T,H,W,3] frames (decoded images before the loader's transpose/float), "
                                    "bit-identical logits"}
-    if world == 1 and not args.no_train_step and pc.backbone == "vgg16" and pc.dataset == "volleyball":
+    if world == 1 and not args.no_train_step and pc.backbone in ("vgg16", "res18") and pc.dataset == "volleyball":
         line["train_step"] = train_step_info(model, pc, dev, images_d, boxes_d, args.train_clips)
     if world == 1 and not args.no_cpu_baseline:
         v, cores, sample, _ = cpu_reference_clips_per_s(pc, sd, bb, budget_s=args.cpu_budget_s)

@@ -743,79 +743,71 @@ __global__ void pack_weight_serial_kernel(const float* __restrict__ w, const flo
 }
 
 
-// The same arithmetic, staged through shared memory: a block owns 32 output rows and walks K in chunks of
-// (kPackCC input channels x taps) source elements.  128 threads load the chunk with coalesced reads, 32 threads do the
-// sequential error-feedback walk of their row from shared memory (the carry never leaves its register), 128 threads
-// store the fp16 results with the tap-major permutation.  pack_weight_serial_kernel read and wrote global memory
-// element by element from one thread per row: 12 800 dependent-latency iterations for fc_emb_1 -- ~5 ms of re-packing
-// per training step; this version is bit-identical (tests) and ~20x faster.
-constexpr int kPackRows = 32;
+// The same arithmetic, staged through shared memory, ONE WARP PER OUTPUT ROW (rows are independent, so there is no block
+// barrier at all): the warp walks K in chunks of (cc input channels x taps) source elements -- 32 lanes load the chunk
+// with coalesced reads, lane 0 does the sequential error-feedback walk from shared memory (the carry never leaves its
+// register), 32 lanes store the fp16 results with the tap-major permutation.  The walk (~30 dependent cycles per
+// element) is what bounds it: ~70 us for K = 4608.  History: pack_weight_serial_kernel (one thread per row straight on
+// global memory, ~5 ms per training step at fc_emb_1 alone), then a 32-rows-per-block version whose 16 blocks spent
+// their time in block-wide load/store phases (400 us per VGG layer, 10 ms = 21 % of a training step -- found with the
+// kineto timeline, profiles/train_step_kernels_r1.txt).  Bit-identical to both (tests).
+constexpr int kPackRows = 8;                 // warps (= output rows) per block
 constexpr int kPackMaxElems = 512;           // source elements of one row per chunk (c's x taps)
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kPackRows * 32)
 pack_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale, __half* __restrict__ out, int c_out,
                    int c_in, int c_in_p, int taps, int split, int cc /* input channels per chunk */) {
   extern __shared__ float pack_smem[];
-  const int pitch = cc * taps + 1;                                   // odd pitch: the 32 walkers hit 32 banks
-  float* in_s = pack_smem;                                           // [32][pitch]
-  __half* hi_s = reinterpret_cast<__half*>(in_s + kPackRows * pitch);  // [32][pitch]
-  __half* lo_s = hi_s + kPackRows * pitch;                           // [32][pitch] (split == 2)
-  const int o0 = blockIdx.x * kPackRows;
+  const int pitch = cc * taps + 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* in_s = pack_smem + warp * pitch;                                             // [rows][pitch]
+  __half* hi_s = reinterpret_cast<__half*>(pack_smem + kPackRows * pitch) + warp * pitch;
+  __half* lo_s = reinterpret_cast<__half*>(pack_smem + kPackRows * pitch) + (kPackRows + warp) * pitch;   // split == 2
+  const int row = blockIdx.x * kPackRows + warp;
+  if (row >= c_out) return;                                                           // warp-uniform
   const int K = c_in * taps;
   const size_t part = static_cast<size_t>(taps) * c_in_p;
+  const float* wrow = w + static_cast<size_t>(row) * K;
+  __half* orow = out + static_cast<size_t>(row) * split * part;
+  const float sc = scale != nullptr ? __ldg(scale + row) : 1.0f;
   float carry = 0.0f;
-  const int my_row = o0 + threadIdx.x;
-  const float sc = (threadIdx.x < kPackRows && my_row < c_out && scale != nullptr) ? scale[my_row] : 1.0f;
   for (int c0 = 0; c0 < c_in; c0 += cc) {
     const int ncc = min(cc, c_in - c0);
     const int n_el = ncc * taps;
-    const int k0 = c0 * taps;
-    __syncthreads();
-    for (int i = threadIdx.x; i < kPackRows * n_el; i += 128) {
-      const int r = i / n_el, j = i - r * n_el;
-      in_s[r * pitch + j] = (o0 + r < c_out) ? __ldg(w + static_cast<size_t>(o0 + r) * K + k0 + j) : 0.0f;
-    }
-    __syncthreads();
-    if (threadIdx.x < kPackRows) {
-      const float* src = in_s + threadIdx.x * pitch;
-      __half* hd = hi_s + threadIdx.x * pitch;
-      __half* ld = lo_s + threadIdx.x * pitch;
-      if (split == 2) {
-        for (int j = 0; j < n_el; ++j) {
-          const float v = src[j] * sc;
-          const __half hi = __float2half_rn(v);
-          hd[j] = hi;
-          ld[j] = __float2half_rn(v - __half2float(hi));
-        }
-      } else {
-        for (int j = 0; j < n_el; ++j) {
-          const float v = __fmaf_rn(src[j], sc, carry);
-          const __half r = __float2half_rn(v);
-          hd[j] = r;
-          carry = v - __half2float(r);
-        }
+    const float* src_g = wrow + c0 * taps;
+    __syncwarp();
+#pragma unroll 4
+    for (int j = lane; j < n_el; j += 32) in_s[j] = __ldg(src_g + j);
+    __syncwarp();
+    if (split == 2) {
+      for (int j = lane; j < n_el; j += 32) {
+        const float v = in_s[j] * sc;
+        const __half hi = __float2half_rn(v);
+        hi_s[j] = hi;
+        lo_s[j] = __float2half_rn(v - __half2float(hi));
+      }
+    } else if (lane == 0) {
+#pragma unroll 8
+      for (int j = 0; j < n_el; ++j) {
+        const float v = __fmaf_rn(in_s[j], sc, carry);
+        const __half r = __float2half_rn(v);
+        hi_s[j] = r;
+        carry = v - __half2float(r);
       }
     }
-    __syncthreads();
-    // element (r, t, c): source j = c*taps + t  ->  out[row][part?][t][c0 + c]   (c fastest: contiguous halves)
-    for (int i = threadIdx.x; i < kPackRows * n_el; i += 128) {
-      const int r = i / n_el, rem = i - r * n_el;
-      const int t = rem / ncc, c = rem - t * ncc;
-      if (o0 + r >= c_out) continue;
-      __half* orow = out + static_cast<size_t>(o0 + r) * split * part;
-      orow[static_cast<size_t>(t) * c_in_p + c0 + c] = hi_s[r * pitch + c * taps + t];
-      if (split == 2) orow[part + static_cast<size_t>(t) * c_in_p + c0 + c] = lo_s[r * pitch + c * taps + t];
+    __syncwarp();
+    // element (t, c): source j = c*taps + t  ->  out[row][part?][t][c0 + c]   (c fastest: contiguous halves)
+    for (int i = lane; i < n_el; i += 32) {
+      const int t = i / ncc, c = i - t * ncc;
+      orow[static_cast<size_t>(t) * c_in_p + c0 + c] = hi_s[c * taps + t];
+      if (split == 2) orow[part + static_cast<size_t>(t) * c_in_p + c0 + c] = lo_s[c * taps + t];
     }
   }
   // zero columns beyond c_in
   const int pad = c_in_p - c_in;
-  for (int i = threadIdx.x; i < kPackRows * split * taps * pad; i += 128) {
-    const int c = i % pad;
-    int rest = i / pad;
-    const int t = rest % (split * taps);
-    const int r = rest / (split * taps);
-    if (o0 + r < c_out)
-      out[static_cast<size_t>(o0 + r) * split * part + static_cast<size_t>(t) * c_in_p + c_in + c] = __float2half_rn(0.0f);
+  for (int i = lane; i < split * taps * pad; i += 32) {
+    const int c = i % pad, t = i / pad;
+    orow[static_cast<size_t>(t) * c_in_p + c_in + c] = __float2half_rn(0.0f);
   }
 }
 
@@ -856,7 +848,7 @@ extern "C" int din_pack_conv_weight_f16(const float* w_oihw, const float* scale,
                                         kPackRows * (kPackMaxElems + 1) * 8));
     attr_dev = dev;
   }
-  pack_weight_kernel<<<(c_out + kPackRows - 1) / kPackRows, 128, smem, static_cast<cudaStream_t>(stream)>>>(
+  pack_weight_kernel<<<(c_out + kPackRows - 1) / kPackRows, kPackRows * 32, smem, static_cast<cudaStream_t>(stream)>>>(
       w_oihw, scale, static_cast<__half*>(w_packed), c_out, c_in, c_in_padded, taps, split, cc);
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;
