@@ -753,35 +753,62 @@ __global__ void pack_weight_serial_kernel(const float* __restrict__ w, const flo
 // kineto timeline, profiles/train_step_kernels_r1.txt).  Bit-identical to both (tests).
 constexpr int kPackRows = 8;                 // warps (= output rows) per block
 constexpr int kPackMaxElems = 512;           // source elements of one row per chunk (c's x taps)
+constexpr int kPackMaxJobs = 64;             // weights per launch (the table travels as a kernel parameter)
+
+// Several weights in ONE launch (din_pack_conv_weights_f16): the walk is latency-bound on a handful of CTAs, so the ~25
+// weights of a backbone are packed side by side (~0.1-0.2 ms) instead of back to back (2.8 ms per VGG-16 training step).
+// transposed != 0 packs the DATA-GRADIENT filter straight from the forward weight: packed row = input channel, column =
+// output channel, taps rotated by 180 degrees (no permute / flip / contiguous copies), scale indexed by the column.
+struct PackJobs {
+  DinPackJob job[kPackMaxJobs];
+  int first_block[kPackMaxJobs + 1];         // prefix sum of ceil(rows / kPackRows)
+  int n;
+};
 
 __global__ void __launch_bounds__(kPackRows * 32)
-pack_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale, __half* __restrict__ out, int c_out,
-                   int c_in, int c_in_p, int taps, int split, int cc /* input channels per chunk */) {
+pack_weight_kernel(const __grid_constant__ PackJobs jobs) {
   extern __shared__ float pack_smem[];
-  const int pitch = cc * taps + 1;
+  int ji = 0;
+  while (ji + 1 < jobs.n && static_cast<int>(blockIdx.x) >= jobs.first_block[ji + 1]) ++ji;
+  const DinPackJob& jb = jobs.job[ji];
+  const int rows = jb.rows, cols = jb.cols, c_in_p = jb.cols_padded, taps = jb.kh * jb.kw, split = jb.split;
+  const bool tr = jb.transposed != 0;
+  int cc = kPackMaxElems / taps;
+  if (cc > cols) cc = cols;
+  const int pitch = kPackMaxElems + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* in_s = pack_smem + warp * pitch;                                             // [rows][pitch]
   __half* hi_s = reinterpret_cast<__half*>(pack_smem + kPackRows * pitch) + warp * pitch;
   __half* lo_s = reinterpret_cast<__half*>(pack_smem + kPackRows * pitch) + (kPackRows + warp) * pitch;   // split == 2
-  const int row = blockIdx.x * kPackRows + warp;
-  if (row >= c_out) return;                                                           // warp-uniform
-  const int K = c_in * taps;
+  const int row = (static_cast<int>(blockIdx.x) - jobs.first_block[ji]) * kPackRows + warp;
+  if (row >= rows) return;                                                            // warp-uniform
   const size_t part = static_cast<size_t>(taps) * c_in_p;
-  const float* wrow = w + static_cast<size_t>(row) * K;
-  __half* orow = out + static_cast<size_t>(row) * split * part;
-  const float sc = scale != nullptr ? __ldg(scale + row) : 1.0f;
+  const float* w = jb.w;
+  const float* scale = jb.scale;
+  __half* orow = static_cast<__half*>(jb.out) + static_cast<size_t>(row) * split * part;
+  const float sc_row = (!tr && scale != nullptr) ? __ldg(scale + row) : 1.0f;
   float carry = 0.0f;
-  for (int c0 = 0; c0 < c_in; c0 += cc) {
-    const int ncc = min(cc, c_in - c0);
+  for (int c0 = 0; c0 < cols; c0 += cc) {
+    const int ncc = min(cc, cols - c0);
     const int n_el = ncc * taps;
-    const float* src_g = wrow + c0 * taps;
     __syncwarp();
+    if (!tr) {
+      const float* src_g = w + (static_cast<size_t>(row) * cols + c0) * taps;
 #pragma unroll 4
-    for (int j = lane; j < n_el; j += 32) in_s[j] = __ldg(src_g + j);
+      for (int j = lane; j < n_el; j += 32) in_s[j] = __ldg(src_g + j);
+    } else {
+      // source element of packed (row = ci, column c = co, tap t): w[co][ci][taps - 1 - t]  (x scale[co], exactly as the
+      // forward pack's fma does it below -- here the product is formed first, once, in fp32)
+      for (int j = lane; j < n_el; j += 32) {
+        const int c = j / taps, t = j - c * taps;
+        const float v = __ldg(w + (static_cast<size_t>(c0 + c) * rows + row) * taps + (taps - 1 - t));
+        in_s[j] = scale != nullptr ? __fmul_rn(v, __ldg(scale + c0 + c)) : v;
+      }
+    }
     __syncwarp();
     if (split == 2) {
       for (int j = lane; j < n_el; j += 32) {
-        const float v = in_s[j] * sc;
+        const float v = in_s[j] * sc_row;
         const __half hi = __float2half_rn(v);
         hi_s[j] = hi;
         lo_s[j] = __float2half_rn(v - __half2float(hi));
@@ -789,7 +816,7 @@ pack_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale,
     } else if (lane == 0) {
 #pragma unroll 8
       for (int j = 0; j < n_el; ++j) {
-        const float v = __fmaf_rn(in_s[j], sc, carry);
+        const float v = __fmaf_rn(in_s[j], sc_row, carry);
         const __half r = __float2half_rn(v);
         hi_s[j] = r;
         carry = v - __half2float(r);
@@ -803,11 +830,11 @@ pack_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale,
       if (split == 2) orow[part + static_cast<size_t>(t) * c_in_p + c0 + c] = lo_s[c * taps + t];
     }
   }
-  // zero columns beyond c_in
-  const int pad = c_in_p - c_in;
+  // zero columns beyond the last channel
+  const int pad = c_in_p - cols;
   for (int i = lane; i < split * taps * pad; i += 32) {
     const int c = i % pad, t = i / pad;
-    orow[static_cast<size_t>(t) * c_in_p + c_in + c] = __float2half_rn(0.0f);
+    orow[static_cast<size_t>(t) * c_in_p + cols + c] = __float2half_rn(0.0f);
   }
 }
 
@@ -821,37 +848,61 @@ int conv_variant() {
 
 }  // namespace
 
-extern "C" int din_pack_conv_weight_f16(const float* w_oihw, const float* scale, void* w_packed, int c_out,
-                                        int c_in, int c_in_padded, int kh, int kw, int split, void* stream) {
-  DIN_CHECK_ARG(w_oihw && w_packed, "din_pack_conv_weight_f16: null pointer");
-  DIN_CHECK_ARG(split == 1 || split == 2, "din_pack_conv_weight_f16: split=%d (1 or 2)", split);
-  DIN_CHECK_ARG(c_out > 0 && c_in > 0 && c_in_padded >= c_in && kh > 0 && kw > 0,
-                "din_pack_conv_weight_f16: bad shape c_out=%d c_in=%d c_in_padded=%d k=%dx%d", c_out, c_in,
-                c_in_padded, kh, kw);
-  const int taps = kh * kw;
-  const char* e = std::getenv("DIN_PACK_SERIAL");
-  if ((e && e[0] == '1') || taps > kPackMaxElems) {            // the element-by-element kernel, kept for the A/B test
-    const int block = 32;
-    pack_weight_serial_kernel<<<(c_out + block - 1) / block, block, 0, static_cast<cudaStream_t>(stream)>>>(
-        w_oihw, scale, static_cast<__half*>(w_packed), c_out, c_in, c_in_padded, taps, split);
-    DIN_CHECK_CUDA(cudaGetLastError());
-    return DIN_OK;
-  }
-  int cc = kPackMaxElems / taps;
-  if (cc > c_in) cc = c_in;
-  const size_t smem = static_cast<size_t>(kPackRows) * (cc * taps + 1) * (sizeof(float) + 2 * sizeof(__half));
+extern "C" int din_pack_conv_weights_f16(const DinPackJob* jobs, int n_jobs, void* stream) {
+  DIN_CHECK_ARG(jobs && n_jobs > 0, "din_pack_conv_weights_f16: no jobs");
   static thread_local int attr_dev = -1;
+  const size_t smem = static_cast<size_t>(kPackRows) * (kPackMaxElems + 1) * (sizeof(float) + 2 * sizeof(__half));
   int dev = 0;
   DIN_CHECK_CUDA(cudaGetDevice(&dev));
   if (attr_dev != dev) {
     DIN_CHECK_CUDA(cudaFuncSetAttribute(pack_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kPackRows * (kPackMaxElems + 1) * 8));
+                                        static_cast<int>(smem)));
     attr_dev = dev;
   }
-  pack_weight_kernel<<<(c_out + kPackRows - 1) / kPackRows, kPackRows * 32, smem, static_cast<cudaStream_t>(stream)>>>(
-      w_oihw, scale, static_cast<__half*>(w_packed), c_out, c_in, c_in_padded, taps, split, cc);
-  DIN_CHECK_CUDA(cudaGetLastError());
+  const char* e = std::getenv("DIN_PACK_SERIAL");
+  const bool serial = e && e[0] == '1';
+  for (int j0 = 0; j0 < n_jobs; j0 += kPackMaxJobs) {
+    PackJobs t{};
+    t.n = std::min(kPackMaxJobs, n_jobs - j0);
+    int blocks = 0;
+    for (int i = 0; i < t.n; ++i) {
+      const DinPackJob& jb = jobs[j0 + i];
+      DIN_CHECK_ARG(jb.w && jb.out, "din_pack_conv_weights_f16: job %d: null pointer", j0 + i);
+      DIN_CHECK_ARG(jb.split == 1 || jb.split == 2, "din_pack_conv_weights_f16: job %d: split=%d (1 or 2)", j0 + i,
+                    jb.split);
+      DIN_CHECK_ARG(jb.rows > 0 && jb.cols > 0 && jb.cols_padded >= jb.cols && jb.kh > 0 && jb.kw > 0,
+                    "din_pack_conv_weights_f16: job %d: bad shape rows=%d cols=%d cols_padded=%d k=%dx%d", j0 + i, jb.rows,
+                    jb.cols, jb.cols_padded, jb.kh, jb.kw);
+      if (serial || jb.kh * jb.kw > kPackMaxElems) {      // the element-by-element kernel, kept for the A/B test
+        DIN_CHECK_ARG(!jb.transposed, "din_pack_conv_weights_f16: job %d: the serial kernel packs forward filters only",
+                      j0 + i);
+        pack_weight_serial_kernel<<<(jb.rows + 31) / 32, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+            jb.w, jb.scale, static_cast<__half*>(jb.out), jb.rows, jb.cols, jb.cols_padded, jb.kh * jb.kw, jb.split);
+        DIN_CHECK_CUDA(cudaGetLastError());
+        t.job[i] = jb;
+        t.job[i].rows = 0;                                // nothing left for the batched launch
+      } else {
+        t.job[i] = jb;
+      }
+      t.first_block[i] = blocks;
+      blocks += (t.job[i].rows + kPackRows - 1) / kPackRows;
+    }
+    t.first_block[t.n] = blocks;
+    if (blocks == 0) continue;
+    pack_weight_kernel<<<blocks, kPackRows * 32, smem, static_cast<cudaStream_t>(stream)>>>(t);
+    DIN_CHECK_CUDA(cudaGetLastError());
+  }
   return DIN_OK;
+}
+
+extern "C" int din_pack_conv_weight_f16(const float* w_oihw, const float* scale, void* w_packed, int c_out,
+                                        int c_in, int c_in_padded, int kh, int kw, int split, void* stream) {
+  DIN_CHECK_ARG(w_oihw && w_packed, "din_pack_conv_weight_f16: null pointer");
+  DinPackJob jb{};
+  jb.w = w_oihw; jb.scale = scale; jb.out = w_packed;
+  jb.rows = c_out; jb.cols = c_in; jb.cols_padded = c_in_padded; jb.kh = kh; jb.kw = kw; jb.split = split;
+  jb.transposed = 0;
+  return din_pack_conv_weights_f16(&jb, 1, stream);
 }
 
 extern "C" int din_conv2d_nhwc_f16(const DinConvDesc* d, const void* x, const void* w_packed, const float* bias,

@@ -19,6 +19,11 @@ class DinConvDesc(C.Structure):
         "pad_h", "pad_w", "relu", "out_f32", "pool2", "w_split")]
 
 
+class DinPackJob(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("scale", C.c_void_p), ("out", C.c_void_p)] + [(name, C.c_int32) for name in (
+        "rows", "cols", "cols_padded", "kh", "kw", "split", "transposed", "reserved")]
+
+
 _vp, _i, _fp, _ll = C.c_void_p, C.c_int, C.c_void_p, C.c_longlong  # float* is passed as a raw address
 
 # name -> (restype, argtypes).  tests/test_abi.py checks this table against include/din_sm100.h.
@@ -30,6 +35,7 @@ PROTOTYPES = {
     "din_stem_conv_nhwc_u8": (C.c_int, [_vp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_conv2d_nhwc_f16": (C.c_int, [C.POINTER(DinConvDesc), _vp, _vp, _fp, _vp, _vp, _vp]),
     "din_pack_conv_weight_f16": (C.c_int, [_fp, _fp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "din_pack_conv_weights_f16": (C.c_int, [C.POINTER(DinPackJob), _i, _vp]),
     "din_maxpool2d_nhwc_f16": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_avgpool2d_nhwc_f16": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_upsample_bilinear_nhwc_f16": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -32,6 +32,37 @@ def _fold_bn(conv_w, bn):
     return conv_w, scale.contiguous(), bias.contiguous()
 
 
+class _PackBatch:
+    """`with _PackBatch():` -- every _Conv built inside registers its weight instead of packing it, and ONE
+    din_pack_conv_weights_f16 launch packs them all on exit (a training step rebuilds the plan after every optimizer
+    step: ~25 latency-bound packs back to back were 2.8 ms of a 43 ms VGG-16 step)."""
+    active = None
+
+    def __enter__(self):
+        self.outer, self.convs = _PackBatch.active, []
+        _PackBatch.active = self
+        return self
+
+    def __exit__(self, *exc):
+        _PackBatch.active = self.outer
+        if exc[0] is None:
+            _pack_convs(self.convs)
+        return False
+
+
+def _pack_convs(convs):
+    todo = [c for c in convs if c._w is None]
+    for c, t in zip(todo, ops.pack_conv_weights([(c.w_src, c.bn_scale, c.split, False) for c in todo])):
+        c._w = t
+
+
+def _pack_dgrad_filters(convs):
+    """The data-gradient filters of `convs` (packed straight from the forward weights, one launch)."""
+    todo = [c for c in convs if c._w_dgrad is None]
+    for c, t in zip(todo, ops.pack_conv_weights([(c.w_src, c.bn_scale, 1, True) for c in todo])):
+        c._w_dgrad = t
+
+
 class _Conv:
     """One tcgen05 convolution of the plan (weights packed fp16 [co][kh][kw][ci], fp32 bias)."""
 
@@ -39,12 +70,22 @@ class _Conv:
         self.w_src = w                     # fp32 OIHW, kept by reference for the (lazily packed) dgrad filter
         self.bn_scale = scale              # folded eval-mode BatchNorm: gamma / sqrt(var + eps) (None: no BN)
         self.bn = bn                       # its {'weight', 'bias', ...} (training: d(gamma) needs gamma and beta)
+        self.w_src = w = w.contiguous()
         self._w_dgrad = None
-        self.w = ops.pack_conv_weight(w.contiguous(), scale, split=split)
+        self._w, self.split = None, split
+        if _PackBatch.active is not None:
+            _PackBatch.active.convs.append(self)
+        else:
+            _pack_convs([self])
         self.bias = None if bias is None else bias.contiguous().float()
         self.stride, self.pad, self.relu, self.pool2 = stride, pad, relu, pool2
-        self.c_out, self.c_in_padded = self.w.shape[0], self.w.shape[-1]
-        self.c_in = w.shape[1]
+        self.c_out, self.c_in = w.shape[0], w.shape[1]
+        self.c_in_padded = (self.c_in + 63) // 64 * 64
+
+    @property
+    def w(self):
+        assert self._w is not None, "weight used inside the _PackBatch block that defers its packing"
+        return self._w
 
     def __call__(self, x, out=None, residual=None, **kw):
         kw.setdefault("c_in", self.c_in)
@@ -57,9 +98,7 @@ class _Conv:
         weight prep).  Stride-2 layers pass the zero-inserted dZ (ops.scatter2_nhwc)."""
         k = self.w_src.shape[2]
         assert k == self.w_src.shape[3] and k in (1, 3)
-        if self._w_dgrad is None:
-            w = self.w_src if self.bn_scale is None else self.w_src * self.bn_scale.view(-1, 1, 1, 1)
-            self._w_dgrad = ops.pack_conv_weight(w.permute(1, 0, 2, 3).flip(2, 3).contiguous())
+        _pack_dgrad_filters([self])                  # normally done for the whole plan by forward_train
         return ops.conv2d_nhwc(dz, self._w_dgrad, None, stride=1, pad=(k // 2, k // 2), relu=False)
 
 
@@ -106,6 +145,7 @@ class VGG16Plan:
         saved = []
         x = images
         last = len(self.layers) - 1
+        _pack_dgrad_filters(self.layers[1:])
         for i, layer in enumerate(self.layers):
             if i == 0:
                 y, pooled = layer(x), False
@@ -209,6 +249,7 @@ class Res18Plan:
     # -- training (BatchNorm in eval mode, i.e. folded, as cfg.set_bn_eval leaves it) -----------
     def forward_train(self, images, out=None):
         """As __call__, keeping the stem output and every block's (input, conv1 output, identity, output)."""
+        _pack_dgrad_filters([c for convs in self.blocks for c in convs if c is not None])
         x0 = self.stem(images)
         x = ops.maxpool2d_nhwc(x0, 3, 2, 1)
         saved = {"images": images, "x0": x0, "blocks": []}
@@ -287,13 +328,14 @@ class Res18Plan:
 
 
 def build_backbone_plan(name, sd):
-    if name == "vgg16":
-        return VGG16Plan(sd)
-    if name == "res18":
-        return Res18Plan(sd)
-    if name == "inv3":
-        from .inception import Inv3Plan
-        return Inv3Plan(sd)
+    with _PackBatch():                     # all of the backbone's filters packed by one launch
+        if name == "vgg16":
+            return VGG16Plan(sd)
+        if name == "res18":
+            return Res18Plan(sd)
+        if name == "inv3":
+            from .inception import Inv3Plan
+            return Inv3Plan(sd)
     raise ValueError(f"backbone {name!r} is outside the hot-path scope (vgg16 / res18 / inv3)")
 
 

@@ -67,6 +67,30 @@ def pack_conv_weight(w_oihw, scale=None, c_in_padded=None, split=1):
     return out
 
 
+def pack_conv_weights(jobs):
+    """Several weights packed by one launch.  jobs: [(w_oihw fp32, scale | None, split, transposed)].
+    transposed: the data-gradient filter of the convolution with forward weight w (rot180, channel axes swapped,
+    scale per forward output channel) -- no permute / flip copies.  -> [packed fp16 tensors]."""
+    if not jobs:
+        return []
+    arr = (_lib.DinPackJob * len(jobs))()
+    outs = []
+    for j, (w, scale, split, transposed) in zip(arr, jobs):
+        _need(w, torch.float32, "w_oihw")
+        a, b, kh, kw = w.shape
+        rows, cols = (b, a) if transposed else (a, b)
+        cp = (cols + 63) // 64 * 64
+        if scale is not None:
+            _need(scale, torch.float32, "scale")
+            assert scale.numel() == a
+        out = torch.empty((rows, kh, kw, cp) if split == 1 else (rows, 2, kh, kw, cp), dtype=torch.float16, device=w.device)
+        outs.append(out)
+        j.w, j.scale, j.out = w.data_ptr(), (0 if scale is None else scale.data_ptr()) or None, out.data_ptr()
+        j.rows, j.cols, j.cols_padded, j.kh, j.kw, j.split, j.transposed = rows, cols, cp, kh, kw, split, int(transposed)
+    check(_lib.load().din_pack_conv_weights_f16(arr, len(jobs), _stream()), "din_pack_conv_weights_f16")
+    return outs
+
+
 def conv2d_nhwc(x, w_packed, bias=None, *, stride=1, pad=(0, 0), relu=False, residual=None, out=None,
                 out_f32=False, c_in=None, x_c_offset=0, y_c_offset=0, c_out=None, pool2=False):
     """x: [n,h,w,Cx] fp16 NHWC (the conv reads channels [x_c_offset, x_c_offset+c_in)).

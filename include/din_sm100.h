@@ -123,6 +123,27 @@ DIN_API int din_conv2d_nhwc_f16(const DinConvDesc* desc, const void* x, const vo
 DIN_API int din_pack_conv_weight_f16(const float* w_oihw, const float* scale, void* w_packed, int c_out, int c_in,
                              int c_in_padded, int kh, int kw, int split, void* stream);
 
+/* Several weights packed by ONE launch (the packing walk is latency-bound on a few CTAs, so a backbone's ~25 filters are
+ * packed side by side: a training step re-packs every weight after the optimizer step).
+ * transposed = 0: as din_pack_conv_weight_f16 (w is [rows][cols][kh][kw], scale indexes rows).
+ * transposed = 1: the DATA-GRADIENT filter of the convolution whose forward weight w is [cols][rows][kh][kw]
+ *                 (torch: w.permute(1,0,2,3).flip(2,3), times scale[col]): packed row = input channel, column = output
+ *                 channel, taps rotated by 180 degrees -- what din_conv2d_nhwc_f16 needs to compute dX = conv(dZ, .).
+ * Replaces: the per-layer weight preparation that torch.nn.Conv2d's cuDNN backward does internally
+ * (backbone/backbone.py:88-132 layers under train_net_dynamic.py:186 loss.backward()). */
+typedef struct DinPackJob {
+  const float* w;           /* fp32 source weight (device) */
+  const float* scale;       /* fp32 per-output-channel scale (BatchNorm folding) or NULL */
+  void* out;                /* fp16 [rows][split][kh][kw][cols_padded] (device, 16-byte aligned) */
+  int32_t rows, cols;       /* packed rows (GEMM M) and columns per tap */
+  int32_t cols_padded;      /* cols rounded up to a multiple of 64, zero-filled */
+  int32_t kh, kw;
+  int32_t split;            /* 1, or 2 (hi / lo parts) */
+  int32_t transposed;       /* see above */
+  int32_t reserved;
+} DinPackJob;
+DIN_API int din_pack_conv_weights_f16(const DinPackJob* jobs, int n_jobs, void* stream);
+
 /*
  * Max / average pooling, NHWC fp16, over channels [0, c) of buffers with x_c_stride / y_c_stride channels
  * (so a pool can read a channel slice and write straight into a concat buffer).

@@ -184,3 +184,23 @@ def test_weight_packing_fast_kernel_is_bit_identical_to_the_serial_one(cuda, sha
             out = ops.pack_conv_weight(w, scale, split=split)
             torch.cuda.synchronize()
             assert out.shape == ref.shape and torch.equal(out, ref), (shape, scale is not None, split)
+
+
+def test_batched_packing_matches_single_packs_and_dgrad_filters(cuda):
+    """din_pack_conv_weights_f16: one launch for many weights == one din_pack_conv_weight_f16 each (bit for bit), and its
+    transposed mode == packing w.permute(1,0,2,3).flip(2,3) (x the BN scale), the data-gradient filter."""
+    from din_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    shapes = [(64, 64, 3, 3), (128, 64, 3, 3), (256, 128, 3, 3), (128, 64, 1, 1), (512, 512, 3, 3), (24, 40, 1, 7),
+              (1024, 3200, 1, 1)] + [(64, 64, 3, 3)] * 70              # > 64 jobs: more than one launch
+    ws = [(torch.randn(*s, generator=g) * 0.05).to(cuda) for s in shapes]
+    scs = [(torch.rand(s[0], generator=g) + 0.5).to(cuda) if i % 2 else None for i, s in enumerate(shapes)]
+    splits = [2 if i == 3 else 1 for i in range(len(shapes))]
+    outs = ops.pack_conv_weights([(w, sc, sp, False) for w, sc, sp in zip(ws, scs, splits)])
+    for w, sc, sp, out in zip(ws, scs, splits, outs):
+        assert torch.equal(out, ops.pack_conv_weight(w, sc, split=sp)), tuple(w.shape)
+    outs = ops.pack_conv_weights([(w, sc, 1, True) for w, sc in zip(ws[:7], scs[:7])])
+    for w, sc, out in zip(ws[:7], scs[:7], outs):
+        wf = w if sc is None else w * sc.view(-1, 1, 1, 1)
+        ref = ops.pack_conv_weight(wf.permute(1, 0, 2, 3).flip(2, 3).contiguous())
+        assert out.shape == ref.shape and torch.equal(out, ref), tuple(w.shape)
