@@ -78,6 +78,7 @@ struct ConvKParams {
   uint32_t a_tx_bytes;
   const float* bias;
   const __half* residual;
+  int res_mask;               // 0: y += residual;  1: y *= [residual > 0]  (ReLU backward fused into a dgrad convolution)
   void* y;
 };
 
@@ -206,8 +207,13 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvKParams& p, uint32
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float2 t2 = __half22float2(h2[e]);
-                f[j + 2 * e] += t2.x;
-                f[j + 2 * e + 1] += t2.y;
+                if (p.res_mask) {
+                  f[j + 2 * e] = t2.x > 0.0f ? f[j + 2 * e] : 0.0f;
+                  f[j + 2 * e + 1] = t2.y > 0.0f ? f[j + 2 * e + 1] : 0.0f;
+                } else {
+                  f[j + 2 * e] += t2.x;
+                  f[j + 2 * e + 1] += t2.y;
+                }
               }
             }
           }
@@ -905,8 +911,27 @@ extern "C" int din_pack_conv_weight_f16(const float* w_oihw, const float* scale,
   return din_pack_conv_weights_f16(&jb, 1, stream);
 }
 
+namespace {
+int conv2d_launch(const DinConvDesc* d, const void* x, const void* w_packed, const float* bias, const void* residual,
+                  int res_mask, void* y, void* stream);
+}  // namespace
+
 extern "C" int din_conv2d_nhwc_f16(const DinConvDesc* d, const void* x, const void* w_packed, const float* bias,
                                    const void* residual, void* y, void* stream) {
+  return conv2d_launch(d, x, w_packed, bias, residual, 0, y, stream);
+}
+
+extern "C" int din_conv2d_relu_bwd_nhwc_f16(const DinConvDesc* d, const void* dz, const void* w_packed,
+                                            const void* y_saved, void* dx, void* stream) {
+  DIN_CHECK_ARG(y_saved != nullptr, "din_conv2d_relu_bwd_nhwc_f16: y_saved is NULL");
+  DIN_CHECK_ARG(d && !d->relu && !d->pool2 && !d->out_f32,
+                "din_conv2d_relu_bwd_nhwc_f16: relu / pool2 / out_f32 must be 0 in the descriptor");
+  return conv2d_launch(d, dz, w_packed, nullptr, y_saved, 1, dx, stream);
+}
+
+namespace {
+int conv2d_launch(const DinConvDesc* d, const void* x, const void* w_packed, const float* bias, const void* residual,
+                  int res_mask, void* y, void* stream) {
   DIN_CHECK_ARG(d && x && w_packed && y, "din_conv2d_nhwc_f16: null pointer");
   DIN_CHECK_ARG(d->n > 0 && d->h > 0 && d->w > 0, "din_conv2d_nhwc_f16: bad extent n=%d h=%d w=%d", d->n, d->h,
                 d->w);
@@ -982,7 +1007,7 @@ extern "C" int din_conv2d_nhwc_f16(const DinConvDesc* d, const void* x, const vo
   p.split = d->w_split == 2 ? 2 : 1;
   p.k_part = d->kh * d->kw * p.c_in;
   p.fd_ntn = make_fastdiv(p.n_tiles_n); p.fd_tpi = make_fastdiv(p.tiles_per_img); p.fd_tx = make_fastdiv(p.tiles_x);
-  p.bias = bias; p.residual = static_cast<const __half*>(residual); p.y = y;
+  p.bias = bias; p.residual = static_cast<const __half*>(residual); p.res_mask = res_mask; p.y = y;
 
   // A staging geometry
   uint32_t box_w, box_h;
@@ -1099,3 +1124,4 @@ extern "C" int din_conv2d_nhwc_f16(const DinConvDesc* d, const void* x, const vo
     default: return launch_conv<64, 0>(ta, tb, p, grid, smem, st);
   }
 }
+}  // namespace

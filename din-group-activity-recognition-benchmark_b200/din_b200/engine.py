@@ -92,14 +92,14 @@ class _Conv:
         return ops.conv2d_nhwc(x, self.w, self.bias, stride=self.stride, pad=self.pad, relu=self.relu,
                                residual=residual, out=out, pool2=self.pool2, **kw)
 
-    def dgrad(self, dz):
+    def dgrad(self, dz, relu_mask=None):
         """dX of a stride-1 convolution (3x3 pad 1, or 1x1) = the forward kernel on dZ with the filter rotated by 180
         degrees and its channel axes swapped (packed once per weight version; a folded BN scale is multiplied in: one-time
         weight prep).  Stride-2 layers pass the zero-inserted dZ (ops.scatter2_nhwc)."""
         k = self.w_src.shape[2]
         assert k == self.w_src.shape[3] and k in (1, 3)
         _pack_dgrad_filters([self])                  # normally done for the whole plan by forward_train
-        return ops.conv2d_nhwc(dz, self._w_dgrad, None, stride=1, pad=(k // 2, k // 2), relu=False)
+        return ops.conv2d_nhwc(dz, self._w_dgrad, None, stride=1, pad=(k // 2, k // 2), relu=False, relu_mask=relu_mask)
 
 
 class _Stem:
@@ -170,16 +170,18 @@ class VGG16Plan:
 
     def backward(self, saved, d_out, inv_scale, acc):
         """d_out: fp16 gradient (times the loss scale) w.r.t. this chunk's feature map; accumulates into `acc`."""
-        d = d_out
+        d, masked = d_out, False
         for i in reversed(range(len(self.layers))):
             x_in, y, pooled = saved[i]
-            dz = ops.relu_pool_bwd_nhwc(y, d, pooled)
+            dz = d if masked else ops.relu_pool_bwd_nhwc(y, d, pooled)
             dw, db = acc[i]
             if i == 0:
                 ops.stem_wgrad(x_in, dz, dw, db, inv_scale=inv_scale, prep=True)
             else:
                 ops.conv2d_wgrad_nhwc(x_in, dz, dw, db, pad=(1, 1), inv_scale=inv_scale)
-                d = self.layers[i].dgrad(dz)
+                # the layer below feeds this one without a pool: its ReLU backward rides in this dgrad's epilogue
+                masked = not saved[i - 1][2]
+                d = self.layers[i].dgrad(dz, relu_mask=saved[i - 1][1] if masked else None)
 
     def export_grads(self, acc, grads):
         """accumulators -> {reference parameter name: OIHW gradient} (layout only)."""
@@ -292,7 +294,7 @@ class Res18Plan:
             dz2 = ops.relu_pool_bwd_nhwc(y, d, False)                         # ReLU after the residual add
             ops.conv2d_wgrad_nhwc(a1, dz2, a_c2["dw"], a_c2["dbeta"], pad=(1, 1), inv_scale=inv_scale)
             gamma_grad(conv2, a_c2, dz2, y, sub=identity)
-            dz1 = ops.relu_pool_bwd_nhwc(a1, conv2.dgrad(dz2), False)
+            dz1 = conv2.dgrad(dz2, relu_mask=a1)                              # conv1's ReLU backward in the epilogue
             gamma_grad(conv1, a_c1, dz1, a1)
             dz1u = ops.scatter2_nhwc(dz1, h_in, w_in) if conv1.stride == 2 else dz1
             ops.conv2d_wgrad_nhwc(x_in, dz1u, a_c1["dw"], a_c1["dbeta"], pad=(1, 1), inv_scale=inv_scale)

@@ -92,9 +92,11 @@ def pack_conv_weights(jobs):
 
 
 def conv2d_nhwc(x, w_packed, bias=None, *, stride=1, pad=(0, 0), relu=False, residual=None, out=None,
-                out_f32=False, c_in=None, x_c_offset=0, y_c_offset=0, c_out=None, pool2=False):
+                out_f32=False, c_in=None, x_c_offset=0, y_c_offset=0, c_out=None, pool2=False, relu_mask=None):
     """x: [n,h,w,Cx] fp16 NHWC (the conv reads channels [x_c_offset, x_c_offset+c_in)).
-    w_packed: [c_out, kh, kw, c_in] fp16.  Returns / fills `out` [n,oh,ow,Cy] at channel offset y_c_offset."""
+    w_packed: [c_out, kh, kw, c_in] fp16.  Returns / fills `out` [n,oh,ow,Cy] at channel offset y_c_offset.
+    relu_mask: saved ReLU output shaped like the result -> result * [relu_mask > 0] (din_conv2d_relu_bwd_nhwc_f16: a
+    data-gradient convolution fused with the ReLU backward of the layer below)."""
     _need(x, torch.float16, "x")
     _need(w_packed, torch.float16, "w_packed")
     n, h, w, cx = x.shape
@@ -129,6 +131,14 @@ def conv2d_nhwc(x, w_packed, bias=None, *, stride=1, pad=(0, 0), relu=False, res
         _need(bias, torch.float32, "bias")
     flops = 2 * n * oh * ow * co * kh * kw * c_in       # algorithmic: the real c_in, not the K padding
     nbytes = 2 * n * h * w * c_in + 2 * co * kh * kw * ci + esz_y * n * yh * yw * co
+    if relu_mask is not None:
+        _need(relu_mask, torch.float16, "relu_mask")
+        assert relu_mask.shape == out.shape and residual is None and bias is None and not (relu or pool2 or out_f32)
+        with _launch(f"conv{kh}x{kw}s{stride}_{c_in}->{co}@{oh}x{ow}+relubwd", flops, nbytes + 2 * out.numel()):
+            check(_lib.load().din_conv2d_relu_bwd_nhwc_f16(C.byref(d), xp, _p(w_packed),
+                                                           C.c_void_p(relu_mask.data_ptr() + 2 * y_c_offset), yp,
+                                                           _stream()), "din_conv2d_relu_bwd_nhwc_f16")
+        return out
     with _launch(f"conv{kh}x{kw}s{stride}_{c_in}->{co}@{oh}x{ow}" + ("+pool" if pool2 else ""), flops, nbytes):
         check(_lib.load().din_conv2d_nhwc_f16(C.byref(d), xp, _p(w_packed), _p(bias), rp, yp, _stream()),
               "din_conv2d_nhwc_f16")

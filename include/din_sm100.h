@@ -114,6 +114,15 @@ typedef struct DinConvDesc {
 DIN_API int din_conv2d_nhwc_f16(const DinConvDesc* desc, const void* x, const void* w_packed, const float* bias,
                         const void* residual, void* y, void* stream);
 
+/* Data gradient of a convolution fused with the backward of the ReLU that FOLLOWS the layer below:
+ *   dx = conv(dz, w_packed) * [y_saved > 0]
+ * (w_packed = the data-gradient filter, DinPackJob.transposed = 1; y_saved = that layer's saved ReLU output, fp16, indexed
+ * as dx with y_c_stride).  Same kernels as din_conv2d_nhwc_f16 -- the mask replaces the residual add in the epilogue -- so
+ * the gradient is written once instead of written, re-read, masked and written again.  desc.relu / pool2 / out_f32 = 0.
+ * Replaces: cudnn_convolution_backward_input + threshold_backward under train_net_dynamic.py:186 loss.backward(). */
+DIN_API int din_conv2d_relu_bwd_nhwc_f16(const DinConvDesc* desc, const void* dz, const void* w_packed,
+                                 const void* y_saved, void* dx, void* stream);
+
 /* OIHW fp32 [c_out, c_in, kh, kw] (optionally scaled per output channel by `scale`, for BN folding;
  * NULL = 1) -> fp16 [c_out][kh][kw][c_in_padded], zero-filled for c_in <= c < c_in_padded.
  * Rounding is error-feedback along each output row (every weight within 1 ulp(fp16) of its fp32 value, the

@@ -250,3 +250,22 @@ def test_bn_gamma_grad_and_stem7_wgrad(cuda):
         torch.cuda.synchronize()
         assert (dw - wt.grad).abs().max().item() <= 2e-3 * wt.grad.abs().max().item(), u8
         assert (db - bias.grad).abs().max().item() <= 2e-3 * bias.grad.abs().max().item(), u8
+
+
+@pytest.mark.parametrize("ci,co,hw", [(64, 64, (40, 72)), (128, 128, (24, 40)), (512, 256, (12, 20)), (128, 64, (17, 23))],
+                         ids=str)
+def test_dgrad_with_fused_relu_backward_equals_conv_then_mask(cuda, ci, co, hw):
+    """din_conv2d_relu_bwd_nhwc_f16 == din_conv2d_nhwc_f16 followed by the ReLU mask, bit for bit (every kernel variant:
+    CTA pair BN = 64 / 128, one-CTA BN = 256)."""
+    from din_b200 import ops
+    g = torch.Generator().manual_seed(ci + co)
+    h, w = hw
+    dz = torch.randn(2, h, w, ci, generator=g).to(cuda).half()
+    wp = ops.pack_conv_weight((torch.randn(co, ci, 3, 3, generator=g) * 0.05).to(cuda))
+    y = torch.relu(torch.randn(2, h, w, co, generator=g)).to(cuda).half()
+    plain = ops.conv2d_nhwc(dz, wp, None, stride=1, pad=(1, 1))
+    fused = ops.conv2d_nhwc(dz, wp, None, stride=1, pad=(1, 1), relu_mask=y)
+    torch.cuda.synchronize()
+    want = torch.where(y > 0, plain, torch.zeros_like(plain))
+    assert torch.equal(fused, want)
+    assert (fused != 0).any() and (y == 0).any()
