@@ -90,7 +90,7 @@ def main_grads():
 def main_fullgrads():
     """The whole model trained, backbone included (scripts/train_volleyball_stage2_dynamic.py:12); ResNet-18 with its
     BatchNorm layers in eval mode (config.py set_bn_eval / train_net.py:25-28)."""
-    for name in ("vgg16_lite", "res18_lite"):
+    for name in ("vgg16_lite", "res18_lite", "collective_res18"):   # the last: scripts/train_collective_stage2_dynamic.py
         pc, B = model_cases()[name]
         bb = O.build_backbone(pc.backbone)
         sd = O.make_state_dict(pc, seed=0, backbone=bb)

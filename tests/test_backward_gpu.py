@@ -423,7 +423,7 @@ def test_optimizer_loop_and_modes(cuda):
         m2(batch)
 
 
-@pytest.mark.parametrize("case", ["vgg16_lite", "res18_lite"])
+@pytest.mark.parametrize("case", ["vgg16_lite", "res18_lite", "collective_res18"])
 def test_full_training_step_with_backbone(cuda, case):
     """cfg.train_backbone = True (scripts/train_volleyball_stage2_dynamic.py:12) on VGG-16 (43 parameter tensors) and
     ResNet-18 (77, BatchNorm in eval mode: gamma / beta still train): every gradient vs autograd over the oracle, and
