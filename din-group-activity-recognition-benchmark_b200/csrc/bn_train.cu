@@ -22,6 +22,18 @@ namespace {
 
 using namespace din;
 
+// eight consecutive channels of z (fp16 or fp32) as floats
+__device__ __forceinline__ void load8(const __half* p, float (&f)[8]) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  const __half* h = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) f[e] = __half2float(h[e]);
+}
+__device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
 struct RowMap {
   int octs, lanes_r, oct, rl;
 };
@@ -60,20 +72,20 @@ __device__ __forceinline__ void block_reduce_pairs(const float (&a)[8], const fl
   }
 }
 
+template <typename ZT>
 __global__ void __launch_bounds__(256)
-bn_stats_kernel(const __half* __restrict__ z, long long rows, int c, double* __restrict__ sum, double* __restrict__ sumsq) {
+bn_stats_kernel(const ZT* __restrict__ z, long long rows, int c, double* __restrict__ sum, double* __restrict__ sumsq) {
   const RowMap m = row_map(c);
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (m.rl < m.lanes_r) {
     for (long long r = static_cast<long long>(blockIdx.x) * m.lanes_r + m.rl; r < rows;
          r += static_cast<long long>(gridDim.x) * m.lanes_r) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(z + r * c) + m.oct);
-      const __half* h = reinterpret_cast<const __half*>(&v);
+      float f[8];
+      load8(z + r * c + m.oct * 8, f);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const float f = __half2float(h[e]);
-        s[e] += f;
-        q[e] = fmaf(f, f, q[e]);
+        s[e] += f[e];
+        q[e] = fmaf(f[e], f[e], q[e]);
       }
     }
   }
@@ -105,34 +117,36 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
   }
 }
 
+template <typename ZT>
 __global__ void __launch_bounds__(256)
-bn_apply_kernel(const __half* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
+bn_apply_kernel(const ZT* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
                 const __half* __restrict__ residual, __half* __restrict__ y, long long count8, int c8, int relu) {
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= count8) return;
   const int oc = static_cast<int>(i % c8);
-  const uint4 v = __ldg(reinterpret_cast<const uint4*>(z) + i);
+  float zf[8];
+  load8(z + i * 8, zf);
   uint4 rv = make_uint4(0, 0, 0, 0);
   if (residual != nullptr) rv = __ldg(reinterpret_cast<const uint4*>(residual) + i);
   const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale) + 2 * oc), s1 = __ldg(reinterpret_cast<const float4*>(scale) + 2 * oc + 1);
   const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift) + 2 * oc), h1 = __ldg(reinterpret_cast<const float4*>(shift) + 2 * oc + 1);
   const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
   const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-  const __half* hz = reinterpret_cast<const __half*>(&v);
   const __half* hr = reinterpret_cast<const __half*>(&rv);
   uint4 o;
   __half* ho = reinterpret_cast<__half*>(&o);
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    float f = fmaf(__half2float(hz[e]), sc[e], sh[e]) + __half2float(hr[e]);
+    float f = fmaf(zf[e], sc[e], sh[e]) + __half2float(hr[e]);
     if (relu) f = fmaxf(f, 0.0f);
     ho[e] = __float2half_rn(f);
   }
   reinterpret_cast<uint4*>(y)[i] = o;
 }
 
+template <typename ZT>
 __global__ void __launch_bounds__(256)
-bn_bwd_reduce_kernel(const __half* __restrict__ g, const __half* __restrict__ z, const float* __restrict__ mean,
+bn_bwd_reduce_kernel(const __half* __restrict__ g, const ZT* __restrict__ z, const float* __restrict__ mean,
                      const float* __restrict__ invstd, long long rows, int c, float* __restrict__ sg,
                      float* __restrict__ sgx) {
   const RowMap m = row_map(c);
@@ -147,22 +161,23 @@ bn_bwd_reduce_kernel(const __half* __restrict__ g, const __half* __restrict__ z,
     for (long long r = static_cast<long long>(blockIdx.x) * m.lanes_r + m.rl; r < rows;
          r += static_cast<long long>(gridDim.x) * m.lanes_r) {
       const uint4 gv = __ldg(reinterpret_cast<const uint4*>(g + r * c) + m.oct);
-      const uint4 zv = __ldg(reinterpret_cast<const uint4*>(z + r * c) + m.oct);
+      float zf[8];
+      load8(z + r * c + m.oct * 8, zf);
       const __half* hg = reinterpret_cast<const __half*>(&gv);
-      const __half* hz = reinterpret_cast<const __half*>(&zv);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float gf = __half2float(hg[e]);
         a[e] += gf;
-        b[e] = fmaf(gf, (__half2float(hz[e]) - mu[e]) * is[e], b[e]);
+        b[e] = fmaf(gf, (zf[e] - mu[e]) * is[e], b[e]);
       }
     }
   }
   block_reduce_pairs<float>(a, b, m, sg, sgx);
 }
 
+template <typename ZT>
 __global__ void __launch_bounds__(256)
-bn_bwd_apply_kernel(const __half* __restrict__ g, const __half* __restrict__ z, const float* __restrict__ mean,
+bn_bwd_apply_kernel(const __half* __restrict__ g, const ZT* __restrict__ z, const float* __restrict__ mean,
                     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ sg,
                     const float* __restrict__ sgx, float inv_count, __half* __restrict__ dz, long long count8, int c8,
                     float* __restrict__ dbeta, float* __restrict__ dgamma, const float* __restrict__ inv_scale) {
@@ -177,16 +192,16 @@ bn_bwd_apply_kernel(const __half* __restrict__ g, const __half* __restrict__ z, 
   if (i >= count8) return;
   const int oc = static_cast<int>(i % c8);
   const uint4 gv = __ldg(reinterpret_cast<const uint4*>(g) + i);
-  const uint4 zv = __ldg(reinterpret_cast<const uint4*>(z) + i);
+  float zf[8];
+  load8(z + i * 8, zf);
   const __half* hg = reinterpret_cast<const __half*>(&gv);
-  const __half* hz = reinterpret_cast<const __half*>(&zv);
   uint4 o;
   __half* ho = reinterpret_cast<__half*>(&o);
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int ch = oc * 8 + e;
     const float is = __ldg(invstd + ch);
-    const float xh = (__half2float(hz[e]) - __ldg(mean + ch)) * is;
+    const float xh = (zf[e] - __ldg(mean + ch)) * is;
     const float v = __ldg(gamma + ch) * is * (__half2float(hg[e]) - __ldg(sg + ch) * inv_count - xh * __ldg(sgx + ch) * inv_count);
     ho[e] = __float2half_rn(v);
   }
@@ -203,13 +218,15 @@ int reduce_grid(long long rows, int c) {
 
 }  // namespace
 
-extern "C" int din_bn_stats_f16(const void* z, long long rows, int c, double* sum, double* sumsq, void* stream) {
-  DIN_CHECK_ARG(z && sum && sumsq, "din_bn_stats_f16: null pointer");
-  DIN_CHECK_ARG(rows > 0 && c > 0 && c % 8 == 0 && c <= 2048, "din_bn_stats_f16: bad shape rows=%lld c=%d", rows, c);
+extern "C" int din_bn_stats(const void* z, int z_is_f32, long long rows, int c, double* sum, double* sumsq,
+                            void* stream) {
+  DIN_CHECK_ARG(z && sum && sumsq, "din_bn_stats: null pointer");
+  DIN_CHECK_ARG(rows > 0 && c > 0 && c % 8 == 0 && c <= 2048, "din_bn_stats: bad shape rows=%lld c=%d", rows, c);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DIN_CHECK_CUDA(cudaMemsetAsync(sum, 0, sizeof(double) * c, st));
   DIN_CHECK_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(double) * c, st));
-  bn_stats_kernel<<<reduce_grid(rows, c), 256, 0, st>>>(static_cast<const __half*>(z), rows, c, sum, sumsq);
+  if (z_is_f32) bn_stats_kernel<float><<<reduce_grid(rows, c), 256, 0, st>>>(static_cast<const float*>(z), rows, c, sum, sumsq);
+  else bn_stats_kernel<__half><<<reduce_grid(rows, c), 256, 0, st>>>(static_cast<const __half*>(z), rows, c, sum, sumsq);
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;
 }
@@ -227,35 +244,52 @@ extern "C" int din_bn_finalize_f32(const double* sum, const double* sumsq, long 
   return DIN_OK;
 }
 
-extern "C" int din_bn_apply_f16(const void* z, const float* scale, const float* shift, const void* residual, void* y,
-                                long long rows, int c, int relu, void* stream) {
-  DIN_CHECK_ARG(z && scale && shift && y, "din_bn_apply_f16: null pointer");
-  DIN_CHECK_ARG(rows > 0 && c > 0 && c % 8 == 0, "din_bn_apply_f16: bad shape rows=%lld c=%d", rows, c);
+extern "C" int din_bn_apply(const void* z, int z_is_f32, const float* scale, const float* shift, const void* residual,
+                            void* y, long long rows, int c, int relu, void* stream) {
+  DIN_CHECK_ARG(z && scale && shift && y, "din_bn_apply: null pointer");
+  DIN_CHECK_ARG(rows > 0 && c > 0 && c % 8 == 0, "din_bn_apply: bad shape rows=%lld c=%d", rows, c);
   const long long count8 = rows * (c / 8);
-  DIN_CHECK_ARG((count8 + 255) / 256 <= INT32_MAX, "din_bn_apply_f16: too large");
-  bn_apply_kernel<<<static_cast<int>((count8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(z), scale, shift, static_cast<const __half*>(residual), static_cast<__half*>(y), count8,
-      c / 8, relu);
+  DIN_CHECK_ARG((count8 + 255) / 256 <= INT32_MAX, "din_bn_apply: too large");
+  const int grid = static_cast<int>((count8 + 255) / 256);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (z_is_f32)
+    bn_apply_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(z), scale, shift,
+                                                 static_cast<const __half*>(residual), static_cast<__half*>(y), count8,
+                                                 c / 8, relu);
+  else
+    bn_apply_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(z), scale, shift,
+                                                  static_cast<const __half*>(residual), static_cast<__half*>(y), count8,
+                                                  c / 8, relu);
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;
 }
 
-extern "C" int din_bn_bwd_f16(const void* g, const void* z, const float* mean, const float* invstd, const float* gamma,
+extern "C" int din_bn_bwd(const void* g, const void* z, int z_is_f32, const float* mean, const float* invstd, const float* gamma,
                               float* sums, void* dz, float* dbeta, float* dgamma, const float* inv_scale, long long rows,
                               int c, void* stream) {
-  DIN_CHECK_ARG(g && z && mean && invstd && gamma && sums && dz, "din_bn_bwd_f16: null pointer");
-  DIN_CHECK_ARG((dbeta == nullptr) == (dgamma == nullptr), "din_bn_bwd_f16: dbeta / dgamma");
-  DIN_CHECK_ARG(rows > 0 && c > 0 && c % 8 == 0 && c <= 2048, "din_bn_bwd_f16: bad shape rows=%lld c=%d", rows, c);
+  DIN_CHECK_ARG(g && z && mean && invstd && gamma && sums && dz, "din_bn_bwd: null pointer");
+  DIN_CHECK_ARG((dbeta == nullptr) == (dgamma == nullptr), "din_bn_bwd: dbeta / dgamma");
+  DIN_CHECK_ARG(rows > 0 && c > 0 && c % 8 == 0 && c <= 2048, "din_bn_bwd: bad shape rows=%lld c=%d", rows, c);
   const long long count8 = rows * (c / 8);
-  DIN_CHECK_ARG((count8 + 255) / 256 <= INT32_MAX, "din_bn_bwd_f16: too large");
+  DIN_CHECK_ARG((count8 + 255) / 256 <= INT32_MAX, "din_bn_bwd: too large");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DIN_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c, st));
-  bn_bwd_reduce_kernel<<<reduce_grid(rows, c), 256, 0, st>>>(static_cast<const __half*>(g), static_cast<const __half*>(z),
-                                                             mean, invstd, rows, c, sums, sums + c);
-  DIN_CHECK_CUDA(cudaGetLastError());
-  bn_bwd_apply_kernel<<<static_cast<int>((count8 + 255) / 256), 256, 0, st>>>(
-      static_cast<const __half*>(g), static_cast<const __half*>(z), mean, invstd, gamma, sums, sums + c,
-      1.0f / static_cast<float>(rows), static_cast<__half*>(dz), count8, c / 8, dbeta, dgamma, inv_scale);
+  const __half* gh = static_cast<const __half*>(g);
+  const int grid = static_cast<int>((count8 + 255) / 256);
+  const float inv_count = 1.0f / static_cast<float>(rows);
+  if (z_is_f32) {
+    const float* zf = static_cast<const float*>(z);
+    bn_bwd_reduce_kernel<float><<<reduce_grid(rows, c), 256, 0, st>>>(gh, zf, mean, invstd, rows, c, sums, sums + c);
+    DIN_CHECK_CUDA(cudaGetLastError());
+    bn_bwd_apply_kernel<float><<<grid, 256, 0, st>>>(gh, zf, mean, invstd, gamma, sums, sums + c, inv_count,
+                                                     static_cast<__half*>(dz), count8, c / 8, dbeta, dgamma, inv_scale);
+  } else {
+    const __half* zh = static_cast<const __half*>(z);
+    bn_bwd_reduce_kernel<__half><<<reduce_grid(rows, c), 256, 0, st>>>(gh, zh, mean, invstd, rows, c, sums, sums + c);
+    DIN_CHECK_CUDA(cudaGetLastError());
+    bn_bwd_apply_kernel<__half><<<grid, 256, 0, st>>>(gh, zh, mean, invstd, gamma, sums, sums + c, inv_count,
+                                                      static_cast<__half*>(dz), count8, c / 8, dbeta, dgamma, inv_scale);
+  }
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;
 }

@@ -103,14 +103,14 @@ class _Conv:
 
 
 class _Stem:
-    def __init__(self, w, bias, scale=None, stride=1, pad=0, bn=None):
-        self.bn_scale, self.bn = scale, bn
+    def __init__(self, w, bias, scale=None, stride=1, pad=0, bn=None, relu=True):
+        self.bn_scale, self.bn, self.relu = scale, bn, relu
         if scale is not None:
             w = w * scale.view(-1, 1, 1, 1)       # one-time weight prep (BN folding), not on the hot path
         self.w, self.bias, self.stride, self.pad = w.contiguous().float(), bias.contiguous().float(), stride, pad
 
     def __call__(self, images):
-        return ops.stem_conv(images, self.w, self.bias, stride=self.stride, pad=self.pad, relu=True, prep=True)
+        return ops.stem_conv(images, self.w, self.bias, stride=self.stride, pad=self.pad, relu=self.relu, prep=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -204,12 +204,26 @@ class VGG16Plan:
 class Res18Plan:
     """torchvision resnet18 up to layer4 (backbone.py:115-132), eval-mode BN folded into the convs."""
 
-    def __init__(self, sd, prefix="backbone.features."):
+    def __init__(self, sd, prefix="backbone.features.", bn_train=False):
+        """bn_train: BatchNorm on batch statistics (module.train() without cfg.set_bn_eval): the convolutions stay
+        un-folded and every BatchNorm runs as its own kernels (csrc/bn_train.cu); forward_train / backward only."""
+        self.bn_train = bn_train
+        self._nbt = []
+
         def bn(p):
+            if f"{p}.num_batches_tracked" in sd:
+                self._nbt.append(sd[f"{p}.num_batches_tracked"])
             return {k: sd[f"{p}.{k}"] for k in ("weight", "bias", "running_mean", "running_var")} | {"eps": 1e-5}
 
-        w, s, b = _fold_bn(sd[prefix + "0.weight"], bn(prefix + "1"))
-        self.stem = _Stem(w, b, scale=s, stride=2, pad=3, bn=bn(prefix + "1"))
+        def _fold(w, b):
+            if bn_train:
+                return w, None, None
+            return _fold_bn(w, b)
+
+        w, s, b = _fold(sd[prefix + "0.weight"], bn(prefix + "1"))
+        if bn_train:
+            b = torch.zeros(w.shape[0], dtype=torch.float32, device=w.device)
+        self.stem = _Stem(w, b, scale=s, stride=2, pad=3, bn=bn(prefix + "1"), relu=not bn_train)
         self.prefix = prefix
         self.block_names = []
         self.blocks = []
@@ -218,19 +232,20 @@ class Res18Plan:
             for bi in range(2):
                 p = f"{prefix}{4 + li}.{bi}."
                 stride = 2 if (li > 0 and bi == 0) else 1
-                w1, s1, b1 = _fold_bn(sd[p + "conv1.weight"], bn(p + "bn1"))
-                w2, s2, b2 = _fold_bn(sd[p + "conv2.weight"], bn(p + "bn2"))
-                conv1 = _Conv(w1, b1, s1, stride=stride, pad=(1, 1), relu=True, bn=bn(p + "bn1"))
-                conv2 = _Conv(w2, b2, s2, stride=1, pad=(1, 1), relu=True, bn=bn(p + "bn2"))   # ReLU after the residual add
+                w1, s1, b1 = _fold(sd[p + "conv1.weight"], bn(p + "bn1"))
+                w2, s2, b2 = _fold(sd[p + "conv2.weight"], bn(p + "bn2"))
+                conv1 = _Conv(w1, b1, s1, stride=stride, pad=(1, 1), relu=not bn_train, bn=bn(p + "bn1"))
+                conv2 = _Conv(w2, b2, s2, stride=1, pad=(1, 1), relu=not bn_train, bn=bn(p + "bn2"))   # ReLU after the residual add
                 down = None
                 if (p + "downsample.0.weight") in sd:
-                    wd, sdn, bd = _fold_bn(sd[p + "downsample.0.weight"], bn(p + "downsample.1"))
+                    wd, sdn, bd = _fold(sd[p + "downsample.0.weight"], bn(p + "downsample.1"))
                     down = _Conv(wd, bd, sdn, stride=stride, pad=(0, 0), relu=False, bn=bn(p + "downsample.1"))
                 self.blocks.append((conv1, conv2, down))
                 self.block_names.append(p)
         self.out_channels = 512
 
     def __call__(self, images, out=None):
+        assert not self.bn_train, "a batch-statistics plan only runs forward_train (DinEngine.features does that)"
         x = self.stem(images)
         x = ops.maxpool2d_nhwc(x, 3, 2, 1)
         last = len(self.blocks) - 1
@@ -251,6 +266,8 @@ class Res18Plan:
     # -- training (BatchNorm in eval mode, i.e. folded, as cfg.set_bn_eval leaves it) -----------
     def forward_train(self, images, out=None):
         """As __call__, keeping the stem output and every block's (input, conv1 output, identity, output)."""
+        if self.bn_train:
+            return self._forward_train_bn(images, out)
         _pack_dgrad_filters([c for convs in self.blocks for c in convs if c is not None])
         x0 = self.stem(images)
         x = ops.maxpool2d_nhwc(x0, 3, 2, 1)
@@ -282,6 +299,9 @@ class Res18Plan:
     def backward(self, saved, d_out, inv_scale, acc):
         """d_out: fp16 gradient (times the loss scale) w.r.t. this chunk's feature map; accumulates into `acc`.
         Stride-2 layers go through zero insertion (ops.scatter2_nhwc), so dgrad / wgrad stay the stride-1 kernels."""
+        if self.bn_train:
+            return self._backward_bn(saved, d_out, inv_scale, acc)
+
         def gamma_grad(conv, a, dz, z, sub=None):
             ops.bn_gamma_grad(dz, z, conv.bn["weight"], conv.bn["bias"], a["dgamma"], sub=sub, inv_scale=inv_scale)
 
@@ -314,11 +334,80 @@ class Res18Plan:
         ops.stem_wgrad(saved["images"], dz0, a0["dw"], a0["dbeta"], stride=2, pad=3, inv_scale=inv_scale, prep=True)
         ops.bn_gamma_grad(dz0, saved["x0"], self.stem.bn["weight"], self.stem.bn["bias"], a0["dgamma"], inv_scale=inv_scale)
 
+    # -- BatchNorm on batch statistics (scripts/train_collective_stage2_dynamic.py: ResNet-18 trained with
+    #    cfg.set_bn_eval = False): conv -> raw z -> stats -> normalise (+ residual) -> ReLU, all frames of the step at once
+    def _bn(self, layer, z, residual=None, relu=True, out=None):
+        b = layer.bn
+        y, stats = ops.bn_train_forward(z, b["weight"], b["bias"], b["running_mean"], b["running_var"], eps=b["eps"],
+                                        residual=residual, relu=relu, out=out)
+        return y, stats
+
+    def _forward_train_bn(self, images, out=None):
+        convs = [c for cs in self.blocks for c in cs if c is not None]
+        _pack_dgrad_filters(convs)
+        z0 = self.stem(images)
+        x0, st0 = self._bn(self.stem, z0)
+        x = ops.maxpool2d_nhwc(x0, 3, 2, 1)
+        saved = {"images": images, "z0": z0, "x0": x0, "st0": st0, "blocks": []}
+        last = len(self.blocks) - 1
+        for i, (conv1, conv2, down) in enumerate(self.blocks):
+            zd = std = None
+            identity = x
+            # raw convolution outputs in fp32: the normalised activation is then rounded to fp16 once, as the folded
+            # eval-mode epilogue does (fp16 z: twice the ReLU decision flips, gradients 15-20 % off instead of 2-7 %)
+            if down is not None:
+                zd = down(x, out_f32=True)
+                identity, std = self._bn(down, zd, relu=False)
+            z1 = conv1(x, out_f32=True)
+            a1, st1 = self._bn(conv1, z1)
+            z2 = conv2(a1, out_f32=True)
+            y, st2 = self._bn(conv2, z2, residual=identity, out=out if i == last else None)
+            saved["blocks"].append((x, z1, a1, st1, z2, y, st2, zd, std))
+            x = y
+        if self._nbt:
+            torch._foreach_add_(self._nbt, 1)                # num_batches_tracked
+        for c in [self.stem] + convs:                        # the kernels wrote the running statistics through raw
+            for k in ("running_mean", "running_var"):        # pointers: tell torch (plan caches key on ._version)
+                torch.autograd.graph.increment_version(c.bn[k])
+        return x, saved
+
+    def _backward_bn(self, saved, d_out, inv_scale, acc):
+        def bn_bwd(layer, a, g, z, stats):
+            return ops.bn_train_backward(g, z, stats[0], stats[1], layer.bn["weight"], a["dbeta"], a["dgamma"],
+                                         inv_scale=inv_scale)
+
+        d = d_out
+        for bi in reversed(range(len(self.blocks))):
+            x_in, z1, a1, st1, z2, y, st2, zd, std = saved["blocks"][bi]
+            conv1, conv2, down = self.blocks[bi]
+            a_c1, a_c2, a_dn = acc["blocks"][bi]
+            h_in, w_in = x_in.shape[1:3]
+            g2 = ops.relu_pool_bwd_nhwc(y, d, False)                          # also the shortcut branch's gradient
+            dz2 = bn_bwd(conv2, a_c2, g2, z2, st2)
+            ops.conv2d_wgrad_nhwc(a1, dz2, a_c2["dw"], None, pad=(1, 1), inv_scale=inv_scale)
+            dz1 = bn_bwd(conv1, a_c1, conv2.dgrad(dz2, relu_mask=a1), z1, st1)
+            dz1u = ops.scatter2_nhwc(dz1, h_in, w_in) if conv1.stride == 2 else dz1
+            ops.conv2d_wgrad_nhwc(x_in, dz1u, a_c1["dw"], None, pad=(1, 1), inv_scale=inv_scale)
+            dx = conv1.dgrad(dz1u)
+            if down is None:
+                dx = ops.add_f16(dx, g2)
+            else:
+                dzd = bn_bwd(down, a_dn, g2, zd, std)
+                ops.conv2d_wgrad_nhwc(x_in, ops.scatter2_nhwc(dzd, h_in, w_in), a_dn["dw"], None, pad=(1, 1),
+                                      inv_scale=inv_scale)
+                ops.scatter2_nhwc(down.dgrad(dzd), h_in, w_in, dst=dx)
+            d = dx
+        a0 = acc["stem"]
+        dz0 = bn_bwd(self.stem, a0, ops.maxpool3s2_relu_bwd_nhwc(saved["x0"], d), saved["z0"], saved["st0"])
+        ops.stem_wgrad(saved["images"], dz0, a0["dw"], torch.zeros_like(a0["dbeta"]), stride=2, pad=3,
+                       inv_scale=inv_scale, prep=True)
+
     def export_grads(self, acc, grads):
         """accumulators -> {reference parameter name: gradient}: un-fold the BN scale from the conv weight gradients
         (din_scale_rows_f32), OIHW layout (permutes only)."""
         def put(conv_name, bn_name, conv, a, w_oihw):
-            grads[conv_name + ".weight"] = ops.scale_rows(w_oihw.contiguous(), conv.bn_scale)
+            w_oihw = w_oihw.contiguous()
+            grads[conv_name + ".weight"] = w_oihw if self.bn_train else ops.scale_rows(w_oihw, conv.bn_scale)
             grads[bn_name + ".weight"], grads[bn_name + ".bias"] = a["dgamma"], a["dbeta"]
 
         put(self.prefix + "0", self.prefix + "1", self.stem, acc["stem"], acc["stem"]["dw"])
@@ -329,12 +418,14 @@ class Res18Plan:
                 put(p + "downsample.0", p + "downsample.1", down, ad, ad["dw"][:, 1:2, 1:2, :].permute(0, 3, 1, 2))
 
 
-def build_backbone_plan(name, sd):
+def build_backbone_plan(name, sd, bn_train=False):
+    if bn_train and name != "res18":
+        raise NotImplementedError(f"BatchNorm on batch statistics is implemented for ResNet-18 only, not {name!r}")
     with _PackBatch():                     # all of the backbone's filters packed by one launch
         if name == "vgg16":
             return VGG16Plan(sd)
         if name == "res18":
-            return Res18Plan(sd)
+            return Res18Plan(sd, bn_train=bn_train)
         if name == "inv3":
             from .inception import Inv3Plan
             return Inv3Plan(sd)
@@ -380,7 +471,8 @@ class DPIWeights:
 class DinEngine:
     """Forward plan for Dynamic_volleyball / Dynamic_collective built from a reference-named state_dict."""
 
-    def __init__(self, cfg, state_dict, device, dataset="volleyball", frames_per_chunk=None, backbone_plan=None):
+    def __init__(self, cfg, state_dict, device, dataset="volleyball", frames_per_chunk=None, backbone_plan=None,
+                 bn_train=False):
         """backbone_plan: a plan built earlier from the same backbone weights (a training loop with the backbone
         frozen changes only the head's weights between steps: the 14.7 M backbone weights are not re-packed)."""
         self.cfg, self.dataset, self.device = cfg, dataset, torch.device(device)
@@ -394,7 +486,8 @@ class DinEngine:
         self.NFB = cfg.num_features_boxes
         self.C = cfg.lite_dim if cfg.lite_dim else self.NFB
         self.backbone_name = cfg.backbone
-        self.backbone = backbone_plan if backbone_plan is not None else build_backbone_plan(cfg.backbone, sd)
+        self.backbone = (backbone_plan if backbone_plan is not None
+                         else build_backbone_plan(cfg.backbone, sd, bn_train=bn_train))
 
         # fc_emb_1: the reference flattens crops as (d, ky, kx) (infer_model.py:181); RoIAlign here emits
         # (ky, kx, d), so permute the weight's columns once.  Public parameter stays [NFB, K*K*D].
@@ -453,6 +546,8 @@ class DinEngine:
     def features(self, images_flat):
         """[F,3,H,W] fp32 raw (or [F,H,W,3] uint8) -> NHWC fp16 [F,OH,OW,D] (prep_images + backbone), chunked
         over frames."""
+        if getattr(self.backbone, "bn_train", False):        # BatchNorm on batch statistics: the training-mode forward
+            return self.features_train(images_flat)[0]
         F_ = images_flat.shape[0]
         H, W = images_flat.shape[1:3] if images_flat.dtype == torch.uint8 else images_flat.shape[2:4]
         oh, ow, d = self.backbone.out_shape(H, W)
@@ -476,8 +571,10 @@ class DinEngine:
         oh, ow, d = self.backbone.out_shape(H, W)
         fm = torch.zeros((F_, oh, ow, d), dtype=torch.float16, device=images_flat.device)
         chunks = []
-        for f0 in range(0, F_, self.frames_per_chunk):
-            f1 = min(F_, f0 + self.frames_per_chunk)
+        # batch statistics couple all frames of the step: one chunk
+        per_chunk = F_ if getattr(self.backbone, "bn_train", False) else self.frames_per_chunk
+        for f0 in range(0, F_, per_chunk):
+            f1 = min(F_, f0 + per_chunk)
             _, saved = self.backbone.forward_train(images_flat[f0:f1], out=fm[f0:f1])
             chunks.append((f0, f1, saved))
         return fm, chunks

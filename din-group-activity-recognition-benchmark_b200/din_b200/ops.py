@@ -625,3 +625,51 @@ def scale_rows(w, scale):
     with _launch("scale_rows", 0, 8 * w.numel()):
         check(_lib.load().din_scale_rows_f32(_p(w), _p(scale), rows, w.numel() // rows, _stream()), "din_scale_rows_f32")
     return w
+
+
+# ---- BatchNorm2d on batch statistics (csrc/bn_train.cu) ----------------------------------------------------------------
+def bn_train_forward(z, gamma, beta, running_mean=None, running_var=None, *, eps=1e-5, momentum=0.1, residual=None,
+                     relu=True, out=None):
+    """z: raw convolution output fp16 or fp32 [..., c].  -> (y = [relu](BN_batch(z) [+ residual]) fp16, (mean, invstd)
+    fp32 [c]).  running_mean / running_var are updated in place as nn.BatchNorm2d.train() does."""
+    f32 = z.dtype == torch.float32
+    _need(z, torch.float32 if f32 else torch.float16, "z")
+    c = z.shape[-1]
+    rows = z.numel() // c
+    for name, t in (("gamma", gamma), ("beta", beta), ("running_mean", running_mean), ("running_var", running_var)):
+        if t is not None:
+            _need(t, torch.float32, name)
+    sums = torch.empty((2, c), dtype=torch.float64, device=z.device)
+    par = torch.empty((4, c), dtype=torch.float32, device=z.device)          # scale, shift, mean, invstd
+    y = torch.empty(z.shape, dtype=torch.float16, device=z.device) if out is None else out
+    _need(y, torch.float16, "out")
+    assert y.shape == z.shape
+    if residual is not None:
+        _need(residual, torch.float16, "residual")
+        assert residual.shape == z.shape
+    lib = _lib.load()
+    with _launch("bn_stats", 0, z.element_size() * z.numel()):
+        check(lib.din_bn_stats(_p(z), int(f32), rows, c, _p(sums[0]), _p(sums[1]), _stream()), "din_bn_stats")
+    check(lib.din_bn_finalize_f32(_p(sums[0]), _p(sums[1]), rows, _p(gamma), _p(beta), float(eps), float(momentum),
+                                  _p(running_mean), _p(running_var), _p(par[0]), _p(par[1]), _p(par[2]), _p(par[3]), c,
+                                  _stream()), "din_bn_finalize_f32")
+    with _launch("bn_apply", 0, z.numel() * (z.element_size() + (4 if residual is not None else 2))):
+        check(lib.din_bn_apply(_p(z), int(f32), _p(par[0]), _p(par[1]), _p(residual), _p(y), rows, c, int(relu),
+                               _stream()), "din_bn_apply")
+    return y, (par[2], par[3])
+
+
+def bn_train_backward(g, z, mean, invstd, gamma, dbeta=None, dgamma=None, *, inv_scale=None):
+    """g: dY fp16 (masked by the ReLU, times the loss scale) -> dz fp16; dbeta / dgamma [c] fp32 += (unscaled) sums."""
+    f32 = z.dtype == torch.float32
+    _need(g, torch.float16, "g")
+    _need(z, torch.float32 if f32 else torch.float16, "z")
+    assert g.shape == z.shape
+    c = z.shape[-1]
+    rows = z.numel() // c
+    sums = torch.empty(2 * c, dtype=torch.float32, device=z.device)
+    dz = torch.empty_like(g)
+    with _launch("bn_bwd", 0, z.numel() * (2 * z.element_size() + 6)):
+        check(_lib.load().din_bn_bwd(_p(g), _p(z), int(f32), _p(mean), _p(invstd), _p(gamma), _p(sums), _p(dz), _p(dbeta),
+                                     _p(dgamma), _p(inv_scale), rows, c, _stream()), "din_bn_bwd")
+    return dz

@@ -122,19 +122,26 @@ class _DinModel(nn.Module):
         print(str(len(picked)) + " parameters loaded for " + prefix)
 
     # -- plan management -------------------------------------------------------------------------
+    def _bn_batch_stats(self):
+        """True when the backbone's BatchNorm layers run on batch statistics (train() without cfg.set_bn_eval)."""
+        return self.training and any(isinstance(m, nn.modules.batchnorm._BatchNorm) and m.training
+                                     for m in self.backbone.modules())
+
     def engine(self):
         tensors = list(self.state_dict().values())
-        key = (str(tensors[0].device),) + tuple((t.data_ptr(), t._version) for t in tensors)
+        bn_train = self._bn_batch_stats()
+        key = (str(tensors[0].device), bn_train) + tuple((t.data_ptr(), t._version) for t in tensors)
         if self._engine_key != key:
             dev = tensors[0].device
             if dev.type != "cuda":
                 raise RuntimeError("the DIN hot path runs on sm_100a only: move the model to a CUDA device "
                                    "(there is no CPU fallback)")
             # the backbone plan survives head-only weight updates (frozen-backbone training)
-            bb_key = (str(dev),) + tuple((t.data_ptr(), t._version) for t in self.backbone.state_dict().values())
+            bb_key = (str(dev), bn_train) + tuple((t.data_ptr(), t._version) for t in self.backbone.state_dict().values())
             plan = self._engine.backbone if (self._engine is not None and self._bb_plan_key == bb_key) else None
             with torch.cuda.device(dev):
-                self._engine = DinEngine(self.cfg, self.state_dict(), dev, dataset=self._dataset, backbone_plan=plan)
+                self._engine = DinEngine(self.cfg, self.state_dict(), dev, dataset=self._dataset, backbone_plan=plan,
+                                         bn_train=bn_train)
             self._engine_key, self._bb_plan_key = key, bb_key
         return self._engine
 
@@ -145,15 +152,19 @@ class _DinModel(nn.Module):
     def _run(self, images, boxes, bboxes_num=None):
         """eval: the forward plan.  train: forward with dropout; with grad enabled additionally one autograd
         node whose backward is the CUDA head backward."""
+        if self._bn_batch_stats():
+            bns = [m for m in self.backbone.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm)]
+            if self.cfg.backbone != "res18" or not all(m.training and m.momentum == 0.1 and m.track_running_stats
+                                                       for m in bns):
+                raise NotImplementedError(
+                    "train mode with BatchNorm batch statistics is implemented for the ResNet-18 backbone (all of its "
+                    "BatchNorm layers in train mode): freeze BN as the reference does with cfg.set_bn_eval "
+                    "(train_net_dynamic.py:101-102, model.apply(set_bn_eval))")
         eng = self.engine()
         if not self.training:
             if self._dataset == "collective":
                 return eng.forward_collective(images, boxes, bboxes_num)
             return eng.forward_volleyball(images, boxes)
-        if any(isinstance(m, nn.modules.batchnorm._BatchNorm) and m.training for m in self.backbone.modules()):
-            raise NotImplementedError(
-                "train mode with BatchNorm batch statistics is not implemented on the sm_100a path: freeze BN as "
-                "the reference does with cfg.set_bn_eval (train_net_dynamic.py:101-102, model.apply(set_bn_eval))")
         if not torch.is_grad_enabled():
             return _train.forward_train(eng, images, boxes, bboxes_num, training=True)[0]
         if any(p.requires_grad for p in self.backbone.parameters()) and self.cfg.backbone not in ("vgg16", "res18"):

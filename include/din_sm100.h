@@ -432,25 +432,26 @@ DIN_API int din_bn_gamma_grad_f16(const void* dz, const void* zsrc, const void* 
 DIN_API int din_scale_rows_f32(float* w, const float* scale, long long rows, long long cols, void* stream);
 
 /* ---- BatchNorm2d on batch statistics (module.train() without cfg.set_bn_eval: config.py:80, train_net_dynamic.py:161;
- *      nn.BatchNorm2d layers of backbone/backbone.py:115-132).  z: raw convolution output, fp16 [rows][c] (NHWC),
- *      c % 8 == 0.  csrc/bn_train.cu. */
+ *      nn.BatchNorm2d layers of backbone/backbone.py:115-132).  z: raw convolution output [rows][c] (NHWC), fp16 or
+ *      (z_is_f32) fp32 -- fp32 keeps the pre-normalisation values exact, so that y is rounded once, like the folded
+ *      eval-mode epilogue; c % 8 == 0.  csrc/bn_train.cu. */
 /* sum[c], sumsq[c] (fp64, overwritten) = per-channel sum / sum of squares of z over all rows */
-DIN_API int din_bn_stats_f16(const void* z, long long rows, int c, double* sum, double* sumsq, void* stream);
+DIN_API int din_bn_stats(const void* z, int z_is_f32, long long rows, int c, double* sum, double* sumsq, void* stream);
 /* mean, biased var -> invstd = 1/sqrt(var + eps); scale = gamma * invstd; shift = beta - mean * scale;
  * running_mean / running_var (or both NULL) updated in place: (1 - momentum) * old + momentum * new (unbiased var). */
 DIN_API int din_bn_finalize_f32(const double* sum, const double* sumsq, long long count, const float* gamma,
                         const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                         float* scale, float* shift, float* mean, float* invstd, int c, void* stream);
 /* y = [relu]( z * scale[c] + shift[c] [+ residual] ), fp16 */
-DIN_API int din_bn_apply_f16(const void* z, const float* scale, const float* shift, const void* residual, void* y,
-                     long long rows, int c, int relu, void* stream);
+DIN_API int din_bn_apply(const void* z, int z_is_f32, const float* scale, const float* shift, const void* residual,
+                 void* y, long long rows, int c, int relu, void* stream);
 /* g = dY (already masked by the ReLU, fp16, times the loss scale S); xhat = (z - mean) * invstd:
  *   dz = gamma * invstd * (g - sum(g)/rows - xhat * sum(g*xhat)/rows)            (fp16)
  *   dbeta += sum(g) * inv_scale,  dgamma += sum(g*xhat) * inv_scale               (fp32 [c], or both NULL)
  * sums: fp32 [2*c] scratch (overwritten).  inv_scale: device scalar 1/S or NULL. */
-DIN_API int din_bn_bwd_f16(const void* g, const void* z, const float* mean, const float* invstd, const float* gamma,
-                   float* sums, void* dz, float* dbeta, float* dgamma, const float* inv_scale, long long rows, int c,
-                   void* stream);
+DIN_API int din_bn_bwd(const void* g, const void* z, int z_is_f32, const float* mean, const float* invstd,
+               const float* gamma, float* sums, void* dz, float* dbeta, float* dgamma, const float* inv_scale,
+               long long rows, int c, void* stream);
 
 #ifdef __cplusplus
 } /* extern "C" */

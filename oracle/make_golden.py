@@ -102,6 +102,21 @@ def main_fullgrads():
                     "weights_checksum": checksum(sd.values()), "inputs_checksum": checksum(batch),
                     "train_backbone": True}, os.path.join(OUT, f"fullgrads_{name}.pt"))
         print("fullgrads", name, float(loss), len(grads))
+    # BatchNorm on batch statistics (cfg.set_bn_eval = False, the default: scripts/train_collective_stage2_dynamic.py)
+    for name in ("res18_lite", "collective_res18"):
+        pc, B = model_cases()[name]
+        bb = O.build_backbone(pc.backbone)
+        sd = O.make_state_dict(pc, seed=0, backbone=bb)
+        batch = O.make_inputs(pc, B, seed=0)
+        labels = torch.arange(B) % pc.num_activities
+        logits, loss, grads, bufs = R.ref_head_grads(pc, sd, labels, *batch, train_backbone=True, bn_train=True,
+                                                     return_buffers=True)
+        torch.save({"config": dataclasses.asdict(pc), "B": B, "seed": 0, "labels": labels, "logits_ref": logits,
+                    "loss_ref": loss, "grads_ref": {k: O.grad_digest(v) for k, v in grads.items()},
+                    "buffers_ref": {k: O.grad_digest(v.float()) for k, v in bufs.items()},
+                    "weights_checksum": checksum(sd.values()), "inputs_checksum": checksum(batch),
+                    "train_backbone": True, "bn_train": True}, os.path.join(OUT, f"bntrain_{name}.pt"))
+        print("bntrain", name, float(loss), len(grads), len(bufs))
 
 
 def main_basenet_grads():

@@ -174,11 +174,12 @@ def ref_forward(pc, sd, *batch):
         return model(tuple(batch))["activities"]
 
 
-def ref_head_grads(pc, sd, labels, *batch, train_backbone=False):
+def ref_head_grads(pc, sd, labels, *batch, train_backbone=False, bn_train=False, return_buffers=False):
     """Train-mode forward + F.cross_entropy + backward of the REFERENCE model (train_net_dynamic.py:170-224)
     with the backbone frozen (config.py:39) or trained (scripts/train_volleyball_stage2_dynamic.py:12), BatchNorm
-    layers in eval mode (train_net_dynamic.py:101-102 `set_bn_eval`) and train_dropout_prob = 0 (deterministic).
-    -> (logits, loss, {param name: grad})."""
+    layers in eval mode (train_net_dynamic.py:101-102 `set_bn_eval`) -- or, with bn_train, on batch statistics
+    (cfg.set_bn_eval = False, the config.py:80 default) -- and train_dropout_prob = 0 (deterministic).
+    -> (logits, loss, {param name: grad}) [, {BatchNorm buffer name: value after the step}]."""
     model = build_ref_model(pc, sd)
     for q in model.backbone.parameters():
         q.requires_grad = bool(train_backbone)
@@ -186,7 +187,7 @@ def ref_head_grads(pc, sd, labels, *batch, train_backbone=False):
     model.train()
     model.dropout_global.p = 0.0
     for m in model.modules():
-        if isinstance(m, (nn.BatchNorm2d, nn.Dropout)):
+        if isinstance(m, nn.Dropout) or (isinstance(m, nn.BatchNorm2d) and not bn_train):
             m.eval()
     import io
     import warnings
@@ -197,6 +198,9 @@ def ref_head_grads(pc, sd, labels, *batch, train_backbone=False):
         loss.backward()
     grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
     grads = {(n.replace("DPI.inner.", "DPI.") if pc.dataset == "collective" else n): g for n, g in grads.items()}
+    if return_buffers:
+        bufs = {n: b.detach().clone() for n, b in model.named_buffers() if n.startswith("backbone.")}
+        return logits.detach(), loss.detach(), grads, bufs
     return logits.detach(), loss.detach(), grads
 
 

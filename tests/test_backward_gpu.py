@@ -416,11 +416,9 @@ def test_optimizer_loop_and_modes(cuda):
         q.requires_grad = True
     with pytest.raises(NotImplementedError, match="training the backbone"):
         m3(tuple(t.to(cuda) for t in O.make_inputs(pc3, 2, seed=0)))
-    pc2 = _pc("res18", (96, 160), num_frames=3, num_boxes=4)
-    m2, _ = _model_and_cfg(cuda, pc2, O.make_state_dict(pc2, seed=0), 0.3)
-    m2.train()                                        # BatchNorm back to batch statistics
+    m3.train()                                        # BatchNorm back to batch statistics: ResNet-18 only
     with pytest.raises(NotImplementedError, match="BatchNorm"):
-        m2(batch)
+        m3(tuple(t.to(cuda) for t in O.make_inputs(pc3, 2, seed=0)))
 
 
 @pytest.mark.parametrize("case", ["vgg16_lite", "res18_lite", "collective_res18"])
@@ -568,3 +566,76 @@ def test_collective_training_step_with_vgg16_backbone(cuda):
           f"norm error {worst_norm:.2e}")
     assert abs(loss.item() - ref_loss.item()) <= 2e-3 * max(1.0, abs(ref_loss.item()))
     assert worst <= BB_TOL and worst_norm <= 5e-2, (worst, worst_norm)
+
+
+@pytest.mark.parametrize("case", ["res18_lite", "collective_res18"])
+def test_training_step_with_batchnorm_on_batch_statistics(cuda, case):
+    """ResNet-18 trained WITHOUT cfg.set_bn_eval (config.py:80 default; scripts/train_collective_stage2_dynamic.py):
+    every BatchNorm normalises with the statistics of the step's B*T frames and updates its running statistics.
+    Gradients vs autograd over the oracle (bb.train()) and vs the reference model's own (fixture); running statistics vs
+    the oracle's; eval() afterwards folds the UPDATED statistics."""
+    import din_oracle as O
+    from din_b200 import metrics
+    from test_oracle_cpu import _pc_from
+    fx = torch.load(os.path.join(GOLDEN, f"bntrain_{case}.pt"))
+    pc = _pc_from(fx["config"])
+    bb = O.build_backbone(pc.backbone)
+    sd = O.make_state_dict(pc, seed=fx["seed"], backbone=bb)
+    O.load_backbone(bb, sd)
+    bb.train()
+    batch = O.make_inputs(pc, fx["B"], seed=fx["seed"])
+    labels = fx["labels"]
+    model, cfg = _model_and_cfg(cuda, pc, sd, 0.0)
+    model.train()                                                    # BatchNorm layers back on batch statistics
+    for q in model.backbone.parameters():
+        q.requires_grad = True
+    gpu_batch = tuple(t.to(cuda) for t in batch)
+    with torch.no_grad():
+        eval_before = model.eval()(gpu_batch)["activities"].clone()
+    model.train()
+    out = model(gpu_batch)["activities"]
+    loss = metrics.cross_entropy(out, labels.to(cuda))
+    loss.backward()
+    torch.cuda.synchronize()
+    got = {n: q.grad for n, q in model.named_parameters() if q.grad is not None}
+    ref_logits, ref_loss, ref_grads = O.head_grads(bb, sd, pc, labels, *batch, train_backbone=True)
+    assert set(got) == set(ref_grads) == set(fx["grads_ref"]), set(got) ^ set(ref_grads)
+    print(f"[bn-train {case}] logits max|d| {(out.detach().cpu() - ref_logits).abs().max().item():.2e}, "
+          f"loss {loss.item():.6f} vs {ref_loss.item():.6f} (reference fixture {float(fx['loss_ref']):.6f})")
+    assert abs(loss.item() - ref_loss.item()) <= 3e-3 * max(1.0, abs(ref_loss.item()))
+    worst = worst_norm = 0.0
+    for k in sorted(ref_grads):
+        r = _rel_l2(got[k], ref_grads[k])
+        l2 = float(got[k].double().norm())
+        norm_err = abs(l2 - fx["grads_ref"][k]["l2"]) / fx["grads_ref"][k]["l2"]
+        worst, worst_norm = max(worst, r), max(worst_norm, norm_err)
+        print(f"[bn-train {case}] {k:45s} rel-L2 {r:.2e}  norm vs reference {norm_err:.2e}")
+    print(f"[bn-train {case}] worst rel-L2 {worst:.2e}, worst norm error vs the reference fixture {worst_norm:.2e}")
+    # batch statistics make the network ~3x more sensitive to fp16-sized perturbations than eval-mode BatchNorm: the
+    # ORACLE's own gradients move by 1.9e-1 (worst tensor; eval mode 6.7e-2) when every conv weight is perturbed by
+    # 3e-4 relative (tools/bn_sensitivity.py); measured here 1.8e-1 .. 1.9e-1, norms within 5.6e-2 of the reference's
+    assert worst <= 3e-1, worst
+    assert worst_norm <= 8e-2, worst_norm
+    # running statistics: one momentum step from (0, 1) towards the batch statistics
+    bufs = dict(model.named_buffers())
+    n_bn = 0
+    for n, b in bb.named_buffers():
+        mine = bufs["backbone." + n].detach().cpu()
+        if n.endswith("num_batches_tracked"):
+            assert int(mine) == int(b) == 1, (n, int(mine), int(b))   # one train-mode forward each; eval does not count
+            continue
+        n_bn += 1
+        assert torch.allclose(mine, b, rtol=5e-3, atol=2e-4), (n, (mine - b).abs().max().item())
+    assert n_bn == 40
+    # eval() now folds the updated statistics: the logits move
+    with torch.no_grad():
+        eval_after = model.eval()(gpu_batch)["activities"]
+    assert torch.isfinite(eval_after).all() and not torch.allclose(eval_after, eval_before)
+    # frozen backbone, BatchNorm still on batch statistics (scripts/train_volleyball_stage2_arg.py: train_backbone False)
+    model.train()
+    for q in model.backbone.parameters():
+        q.requires_grad = False
+        q.grad = None
+    out2 = model(gpu_batch)["activities"]
+    out2.sum().backward()
+    assert torch.isfinite(out2).all() and all(q.grad is None for q in model.backbone.parameters())

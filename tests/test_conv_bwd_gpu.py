@@ -269,3 +269,39 @@ def test_dgrad_with_fused_relu_backward_equals_conv_then_mask(cuda, ci, co, hw):
     want = torch.where(y > 0, plain, torch.zeros_like(plain))
     assert torch.equal(fused, want)
     assert (fused != 0).any() and (y == 0).any()
+
+
+@pytest.mark.parametrize("shape", [(4, 45, 80, 64), (3, 12, 20, 512), (2, 7, 9, 24)], ids=str)
+def test_batch_stat_batchnorm_forward_backward_match_torch(cuda, shape):
+    """csrc/bn_train.cu vs F.batch_norm(training=True) + ReLU (+ residual) and its autograd, incl. running statistics."""
+    from din_b200 import ops
+    n, h, w, c = shape
+    g = torch.Generator().manual_seed(c)
+    z = (torch.randn(n, h, w, c, generator=g) * 1.5 + torch.randn(c, generator=g)).to(cuda).half()
+    res = torch.randn(n, h, w, c, generator=g).to(cuda).half()
+    gamma = (torch.rand(c, generator=g) + 0.5).to(cuda)
+    beta = (torch.randn(c, generator=g) * 0.3).to(cuda)
+    dy = torch.randn(n, h, w, c, generator=g).to(cuda).half()
+    for residual, zin in ((None, z), (res, z), (res, z.float())):          # z as fp16 or fp32
+        rm, rv = torch.zeros(c, device=cuda), torch.ones(c, device=cuda)
+        rm_ref, rv_ref = rm.clone(), rv.clone()
+        zz = z.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+        gg, bb = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+        pre = F.batch_norm(zz, rm_ref, rv_ref, gg, bb, training=True, momentum=0.1, eps=1e-5)
+        if residual is not None:
+            pre = pre + residual.float().permute(0, 3, 1, 2)
+        ref = F.relu(pre)
+        ref.backward(dy.float().permute(0, 3, 1, 2))
+        y, (mean, invstd) = ops.bn_train_forward(zin, gamma, beta, rm, rv, residual=residual, relu=True)
+        gmask = ops.relu_pool_bwd_nhwc(y, dy, False)
+        dbeta, dgamma = torch.zeros(c, device=cuda), torch.zeros(c, device=cuda)
+        dz = ops.bn_train_backward(gmask, zin, mean, invstd, gamma, dbeta, dgamma)
+        torch.cuda.synchronize()
+        assert (y.float() - ref.detach().permute(0, 2, 3, 1)).abs().max().item() <= 4e-3 * max(1.0, ref.abs().max().item())
+        assert torch.allclose(rm, rm_ref, rtol=1e-4, atol=1e-5) and torch.allclose(rv, rv_ref, rtol=1e-4, atol=1e-5)
+
+        def rel(a, b):
+            return float((a.double() - b.double()).norm() / b.double().norm())
+        # ReLU decisions of units within fp16 rounding of zero can differ from the fp32 reference
+        assert rel(dz.float(), zz.grad.permute(0, 2, 3, 1)) <= 2e-2
+        assert rel(dbeta, bb.grad) <= 1e-2 and rel(dgamma, gg.grad) <= 1e-2

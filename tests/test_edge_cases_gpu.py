@@ -109,7 +109,7 @@ def test_abi_reports_errors_instead_of_crashing(cuda):
     m = IM.Dynamic_volleyball(cfg)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m.eval()((torch.zeros(1, 3, 3, 64, 96), torch.zeros(1, 3, 12, 4)))
-    cfg.train_backbone, cfg.backbone, cfg.out_size = True, "res18", (2, 3)
-    m = IM.Dynamic_volleyball(cfg).to(cuda).train()          # BatchNorm left on batch statistics
+    cfg.train_backbone, cfg.backbone, cfg.out_size, cfg.emb_features = True, "inv3", (2, 3), 1056
+    m = IM.Dynamic_volleyball(cfg).to(cuda).train()          # BatchNorm left on batch statistics (ResNet-18 only)
     with pytest.raises(NotImplementedError, match="BatchNorm"):
         m((torch.zeros(1, 3, 3, 64, 96, device=cuda), torch.zeros(1, 3, 12, 4, device=cuda)))

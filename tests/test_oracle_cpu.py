@@ -230,3 +230,29 @@ def test_oracle_autograd_reproduces_reference_stage1_gradients():
     assert set(grads) == set(fx["grads_ref"]), set(grads) ^ set(fx["grads_ref"])
     for k, d in fx["grads_ref"].items():
         _digest_close(grads[k], d)
+
+
+@pytest.mark.parametrize("fixture,bn_train", [("fullgrads_res18_lite", False), ("fullgrads_collective_res18", False),
+                                              ("bntrain_res18_lite", True), ("bntrain_collective_res18", True)])
+def test_oracle_autograd_reproduces_reference_resnet_gradients(fixture, bn_train):
+    """ResNet-18 trained (scripts/train_collective_stage2_dynamic.py:12-16), BatchNorm in eval mode (cfg.set_bn_eval) or
+    on batch statistics (the config.py:80 default): autograd over the restatement == the reference model's own
+    gradients, and -- batch statistics -- the same running statistics after the step."""
+    import din_oracle as O
+    fx = torch.load(os.path.join(GOLDEN, fixture + ".pt"))
+    pc = _pc_from(fx["config"])
+    bb = O.build_backbone(pc.backbone)
+    sd = O.make_state_dict(pc, seed=fx["seed"], backbone=bb)
+    batch = O.make_inputs(pc, fx["B"], seed=fx["seed"])
+    O.load_backbone(bb, sd)
+    bb.train(bn_train)
+    logits, loss, grads = O.head_grads(bb, sd, pc, fx["labels"], *batch, train_backbone=True)
+    assert abs(float(loss) - float(fx["loss_ref"])) <= 1e-5
+    assert set(grads) == set(fx["grads_ref"]), set(grads) ^ set(fx["grads_ref"])
+    for k, d in fx["grads_ref"].items():
+        _digest_close(grads[k], d)
+    if bn_train:
+        bufs = {"backbone." + n: b for n, b in bb.named_buffers()}
+        assert set(bufs) == set(fx["buffers_ref"])
+        for k, d in fx["buffers_ref"].items():
+            _digest_close(bufs[k].float(), d)
