@@ -24,8 +24,9 @@ dev = torch.device("cuda:0")
 model, sd, bb = bench.build_model(pc, dev)
 images, boxes = (t.to(dev) for t in O.make_inputs(pc, 2, seed=0))
 model.train()
+BN_BATCH = len(sys.argv) > 2 and sys.argv[2] == "bn"      # BatchNorm on batch statistics (no cfg.set_bn_eval)
 for m in model.modules():
-    if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+    if isinstance(m, torch.nn.modules.batchnorm._BatchNorm) and not BN_BATCH:
         m.eval()
 for q in model.parameters():
     q.requires_grad = True
@@ -50,7 +51,7 @@ for _ in range(5):
 t_host = (time.perf_counter() - t0) / 5
 torch.cuda.synchronize()
 t_all = (time.perf_counter() - t0) / 5
-print(f"{bbname}: host issue time {t_host * 1e3:.1f} ms / step, with final sync {t_all * 1e3:.1f} ms / step")
+print(f"{bbname}{' (BatchNorm on batch statistics)' if BN_BATCH else ''}: host issue time {t_host * 1e3:.1f} ms / step, with final sync {t_all * 1e3:.1f} ms / step")
 if os.environ.get("DIN_KINETO", "1") == "1":
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
