@@ -377,18 +377,33 @@ bn_gamma_grad_kernel(const __half* __restrict__ dz, const __half* __restrict__ z
     float be[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) be[e] = __ldg(beta + oct * 8 + e);
-    for (long long r = static_cast<long long>(blockIdx.x) * lanes_r + rl; r < rows;
-         r += static_cast<long long>(gridDim.x) * lanes_r) {
+    // two rows in flight per thread (all loads issued before the arithmetic): the kernel is latency-bound otherwise
+    const long long step = static_cast<long long>(gridDim.x) * lanes_r;
+    for (long long r = static_cast<long long>(blockIdx.x) * lanes_r + rl; r < rows; r += 2 * step) {
+      const long long r2 = r + step;
+      const bool two = r2 < rows;
+      const long long rb = two ? r2 : r;
       const uint4 g = __ldg(reinterpret_cast<const uint4*>(dz + r * c) + oct);
       const uint4 z = __ldg(reinterpret_cast<const uint4*>(zsrc + r * c) + oct);
-      uint4 sb = make_uint4(0, 0, 0, 0);
-      if (sub != nullptr) sb = __ldg(reinterpret_cast<const uint4*>(sub + r * c) + oct);
+      const uint4 g2 = __ldg(reinterpret_cast<const uint4*>(dz + rb * c) + oct);
+      const uint4 z2 = __ldg(reinterpret_cast<const uint4*>(zsrc + rb * c) + oct);
+      uint4 sb = make_uint4(0, 0, 0, 0), sb2 = make_uint4(0, 0, 0, 0);
+      if (sub != nullptr) {
+        sb = __ldg(reinterpret_cast<const uint4*>(sub + r * c) + oct);
+        sb2 = __ldg(reinterpret_cast<const uint4*>(sub + rb * c) + oct);
+      }
       const __half* hg = reinterpret_cast<const __half*>(&g);
       const __half* hz = reinterpret_cast<const __half*>(&z);
       const __half* hs = reinterpret_cast<const __half*>(&sb);
+      const __half* hg2 = reinterpret_cast<const __half*>(&g2);
+      const __half* hz2 = reinterpret_cast<const __half*>(&z2);
+      const __half* hs2 = reinterpret_cast<const __half*>(&sb2);
+      const float w2 = two ? 1.0f : 0.0f;
 #pragma unroll
-      for (int e = 0; e < 8; ++e)
+      for (int e = 0; e < 8; ++e) {
         acc[e] = fmaf(__half2float(hg[e]), (__half2float(hz[e]) - __half2float(hs[e])) - be[e], acc[e]);
+        acc[e] = fmaf(w2 * __half2float(hg2[e]), (__half2float(hz2[e]) - __half2float(hs2[e])) - be[e], acc[e]);
+      }
     }
   }
 #pragma unroll
