@@ -206,3 +206,51 @@ def test_stage1_training_step(cuda):
         got = dict(model.named_parameters())[k].grad
         assert rel_l2(got, ref3[k]) <= 3e-2, (k, rel_l2(got, ref3[k]))
     assert all(q.grad is None for n, q in model.named_parameters() if n.startswith("backbone."))
+
+
+def test_stage1_training_step_resnet18(cuda):
+    """Basenet_volleyball with the ResNet-18 backbone (T = 1), BatchNorm in eval mode (cfg.set_bn_eval, train_net.py:83-84):
+    every gradient vs autograd over the oracle; BatchNorm on batch statistics is refused in stage 1."""
+    import base_model as BM
+    import din_oracle as O
+    from din_b200 import metrics
+    pc = _pc("res18", (96, 160), num_frames=1, num_boxes=4)
+    bb = O.build_backbone(pc.backbone)
+    sd = O.make_basenet_state_dict(pc, seed=3, backbone=bb)
+    # random-init ResNet-18 with identity BatchNorm statistics and no LayerNorm after it yields logits of +-250 (a
+    # saturated softmax: an ill-conditioned gradient test); scale the embedding down to logits of a few units
+    sd["fc_emb.weight"] = sd["fc_emb.weight"] * 0.02
+    O.load_backbone(bb, sd)
+    bb.eval()
+    B = 3
+    batch = O.make_basenet_inputs(pc, B, seed=3)
+    a_lab = torch.arange(B * pc.num_frames * pc.num_boxes) % pc.num_actions
+    g_lab = torch.arange(B) % pc.num_activities
+    cfg = _cfg(pc)
+    cfg.train_backbone, cfg.train_dropout_prob = True, 0.0
+    model = BM.Basenet_volleyball(cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(cuda).train()
+    with pytest.raises(NotImplementedError, match="BatchNorm"):
+        model(tuple(t.to(cuda) for t in batch))
+    for m in model.modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            m.eval()
+    actions, activities = model(tuple(t.to(cuda) for t in batch))
+    loss = metrics.cross_entropy(activities, g_lab.to(cuda)) + \
+        cfg.actions_loss_weight * metrics.cross_entropy(actions, a_lab.to(cuda))
+    loss.backward()
+    torch.cuda.synchronize()
+    ref_loss, ref_grads = O.basenet_grads(bb, sd, pc, a_lab, g_lab, *batch, train={"p": 0.0, "mask": None},
+                                          actions_loss_weight=cfg.actions_loss_weight)
+    got = {n: q.grad for n, q in model.named_parameters() if q.grad is not None}
+    assert set(got) == set(ref_grads), set(got) ^ set(ref_grads)
+
+    def rel_l2(a, b):
+        a, b = a.detach().double().cpu().flatten(), b.detach().double().cpu().flatten()
+        return float((a - b).norm() / max(float(b.norm()), 1e-30))
+    worst = max(rel_l2(got[k], ref_grads[k]) for k in ref_grads)
+    print(f"\n[stage1 res18] loss {loss.item():.5f} vs {ref_loss.item():.5f}; worst rel-L2 {worst:.2e}")
+    assert abs(loss.item() - ref_loss.item()) <= 2e-3 * max(1.0, abs(ref_loss.item()))
+    assert worst <= 2e-1, worst
+    assert rel_l2(got["fc_actions.weight"], ref_grads["fc_actions.weight"]) <= 1e-2
