@@ -73,7 +73,9 @@ int din_num_sms() {
 
 extern "C" {
 
-int din_abi_version(void) { return 2; }   // 2: + uint8 ingest, loss / metrics, backward entry points
+// 2: + uint8 ingest, loss / metrics, backward entry points
+// 3: + batched weight packing, dgrad with fused ReLU backward, ResNet-18 backward helpers, batch-statistics BatchNorm
+int din_abi_version(void) { return 3; }
 
 const char* din_last_error_string(void) { return g_err; }
 

@@ -48,12 +48,23 @@ def test_ctypes_table_matches_header():
         args = [a for a in m.group(1).split(",") if a.strip() and a.strip() != "void"]
         assert len(args) == len(argtypes), (name, len(args), len(argtypes))
     assert C.sizeof(lib.DinConvDesc) == 16 * 4
+    # struct layouts: field names and order as in the header
+    for struct in (lib.DinConvDesc, lib.DinPackJob):
+        m = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct.__name__, struct.__name__), src, flags=re.S)
+        assert m, struct.__name__
+        fields = []
+        for decl in m.group(1).split(";"):
+            decl = decl.strip()
+            if decl:
+                fields += [n.strip().lstrip("*") for n in re.sub(r"^(const\s+)?\w+\s*\*?", "", decl, count=1).split(",")]
+        assert fields == [n for n, _ in struct._fields_], (struct.__name__, fields)
+    assert C.sizeof(lib.DinPackJob) == 3 * 8 + 8 * 4
 
 
 def test_loads_and_validates_without_gpu():
     lib = _lib()
     h = lib.load()
-    assert h.din_abi_version() == 2
+    assert h.din_abi_version() == 3
     # invalid arguments are rejected before any CUDA call, with a message
     d = lib.DinConvDesc(n=1, h=8, w=8, c_in=44, x_c_stride=48, c_out=64, y_c_stride=64, kh=3, kw=3, stride=1,
                         pad_h=1, pad_w=1, relu=1, out_f32=0, pool2=0, w_split=1)
