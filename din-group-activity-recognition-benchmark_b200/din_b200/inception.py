@@ -29,7 +29,7 @@ def _c(v, k, s, p=0):
 def _split_for(name):
     """2 = hi + lo fp16 weight parts (exact weights, 2x tensor work), 1 = one fp16 part (error-feedback rounding).
     DIN_INV3_SPLIT (measurement knob): 'none' (default), 'all', or a comma list of substrings of the layer names that
-    keep the split.  tools/inv3_split_study.py (profiles/inv3_split_study_r1.log): with error-feedback weight rounding
+    keep the split.  tests/tools/inv3_split_study.py (profiles/inv3_split_study_r1.log): with error-feedback weight rounding
     in place the logits error is set by the fp16 ACTIVATION rounding of the 37-conv chain -- 5.1e-4 .. 8.8e-4 of
     max|logit| without any split vs 5.9e-4 .. 7.6e-4 with all layers split (4 cases, tolerance 1e-3) -- while the
     split costs 2x tensor work: 7.70 -> 5.48 ms per 16 frames at 720p."""

@@ -615,7 +615,7 @@ def test_training_step_with_batchnorm_on_batch_statistics(cuda, case):
     print(f"[bn-train {case}] worst rel-L2 {worst:.2e}, worst norm error vs the reference fixture {worst_norm:.2e}")
     # batch statistics make the network ~3x more sensitive to fp16-sized perturbations than eval-mode BatchNorm: the
     # ORACLE's own gradients move by 1.9e-1 (worst tensor; eval mode 6.7e-2) when every conv weight is perturbed by
-    # 3e-4 relative (tools/bn_sensitivity.py); measured here 1.8e-1 .. 1.9e-1, norms within 5.6e-2 of the reference's
+    # 3e-4 relative (tests/tools/bn_sensitivity.py); measured here 1.8e-1 .. 1.9e-1, norms within 5.6e-2 of the reference's
     assert worst <= 3e-1, worst
     assert worst_norm <= 8e-2, worst_norm
     # running statistics: one momentum step from (0, 1) towards the batch statistics

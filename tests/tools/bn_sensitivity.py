@@ -5,7 +5,7 @@ CPU only.  Result (res18_lite, 2 clips x 3 frames at 96x160), committed in profi
 i.e. the batch-statistics network is ~3x more sensitive; the CUDA path's deviations from the oracle (6.8e-2 / 1.8e-1) are
 of exactly this size.  Sets the tolerances of tests/test_backward_gpu.py."""
 import sys, os, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, 'oracle')); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import din_oracle as O
 from test_oracle_cpu import _pc_from

@@ -2,7 +2,7 @@
 every rank runs forward + backward (VGG-16 backbone trained) on its shard of the clips, ONE flat all-reduce
 averages the gradients (din_b200.parallel.GradientAllReducer), and the result is compared with the gradient of the
 same global batch computed on a single GPU (rank 0).  Dropout is off so that the two are comparable.
-usage: python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/train_ddp_check.py"""
+usage: python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/tools/train_ddp_check.py"""
 import os
 import sys
 import time
@@ -10,7 +10,7 @@ import time
 import torch
 import torch.distributed as dist
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (os.path.join(ROOT, "din-group-activity-recognition-benchmark_b200"), os.path.join(ROOT, "oracle")):
     sys.path.insert(0, p)
 import din_oracle as O  # noqa: E402  (synthetic weights / inputs only)

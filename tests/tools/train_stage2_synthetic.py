@@ -3,8 +3,8 @@ reference's model class swapped for the drop-in, F.cross_entropy + the per-step 
 din_b200.metrics (one launch, meters stay on the device), and nn.DataParallel replaced by one process per GPU with a
 single flat gradient all-reduce per step.
 
-  python tools/train_stage2_synthetic.py --steps 20                      # one GPU
-  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/train_stage2_synthetic.py
+  python tests/tools/train_stage2_synthetic.py --steps 20                      # one GPU
+  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/tools/train_stage2_synthetic.py
 """
 import argparse
 import os
@@ -13,7 +13,7 @@ import time
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (os.path.join(ROOT, "din-group-activity-recognition-benchmark_b200"), os.path.join(ROOT, "oracle")):
     sys.path.insert(0, p)
 import din_oracle as O  # noqa: E402  (synthetic weights / inputs only: the oracle's generators)

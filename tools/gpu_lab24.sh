@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 nvidia-smi -L | head -3
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 tools/train_ddp_check.py > gpurun_out/train_ddp_n2.log 2>&1
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 tests/tools/train_ddp_check.py > gpurun_out/train_ddp_n2.log 2>&1
 echo "ddp rc=$?"; grep -v Warning gpurun_out/train_ddp_n2.log | tail -4
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_n2_24.json 2> gpurun_out/bench_n2_24.err
 echo "n2 rc=$?"; python - <<'PY'
