@@ -565,7 +565,7 @@ class DinEngine:
     def features_train(self, images_flat):
         """features() through the backbone plan's forward_train: -> (fm, [(f0, f1, saved)] per frame chunk)."""
         if not hasattr(self.backbone, "forward_train"):
-            raise NotImplementedError(f"training the {self.backbone_name} backbone is not implemented (VGG-16 only)")
+            raise NotImplementedError(f"training the {self.backbone_name} backbone is not implemented (VGG-16 / ResNet-18)")
         F_ = images_flat.shape[0]
         H, W = images_flat.shape[1:3] if images_flat.dtype == torch.uint8 else images_flat.shape[2:4]
         oh, ow, d = self.backbone.out_shape(H, W)

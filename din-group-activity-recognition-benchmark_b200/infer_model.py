@@ -11,7 +11,8 @@ gradients for every parameter after the backbone through the backward kernels in
 cfg.train_backbone = True and the VGG-16 or ResNet-18 backbone (BatchNorm in eval mode) -- for the backbone too
 (RoIAlign scatter, ReLU / max-pool backward, dgrad on the forward tcgen05 kernel, wgrad on
 csrc/conv_wgrad_tcgen05.cu, zero insertion for the stride-2 layers).
-Training the Inception-v3 backbone, or BatchNorm with batch statistics, is not implemented and raises.
+ResNet-18 also trains with BatchNorm on batch statistics (csrc/bn_train.cu: no cfg.set_bn_eval, the reference's default).
+Training the Inception-v3 backbone, or Inception-v3 with BatchNorm on batch statistics, is not implemented and raises.
 """
 import collections
 
