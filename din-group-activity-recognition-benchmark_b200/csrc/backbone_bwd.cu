@@ -421,6 +421,28 @@ bn_gamma_grad_kernel(const __half* __restrict__ dz, const __half* __restrict__ z
   }
 }
 
+// d(gamma) of an eval-mode BatchNorm folded into its convolution, WITHOUT touching the activations: with c = conv(x, W) the
+// un-normalised output, z = gamma * (c - mean) * invstd + beta, so
+//   d(gamma) = invstd * (sum_p dz * c - mean * sum_p dz) = invstd * (<W, dWf> - mean * d(beta))
+// because sum_p dz[p] * c[p] = sum_k W[k] * (sum_p dz[p] * x[p + k]) = <W, dWf>, dWf being the gradient w.r.t. the FOLDED
+// weight that the wgrad kernel already produced.  Exact in fp32, no division by gamma (bn_gamma_grad_kernel recovers
+// xhat as (z - beta) / gamma from fp16 activations: fine for random init, noise-amplifying for the near-zero gammas a
+// trained checkpoint holds), and no pass over HBM-sized tensors.  One block per output channel.
+__global__ void __launch_bounds__(128)
+bn_fold_grads_kernel(const float* __restrict__ w, const float* __restrict__ dwf, const float* __restrict__ dbeta,
+                     const float* __restrict__ running_mean, const float* __restrict__ running_var, float eps,
+                     float* __restrict__ dgamma, long long cols) {
+  __shared__ float red[33];
+  const long long row = blockIdx.x;
+  const float* wr = w + row * cols;
+  const float* dr = dwf + row * cols;
+  float acc = 0.0f;
+  for (long long i = threadIdx.x; i < cols; i += 128) acc = fmaf(__ldg(wr + i), __ldg(dr + i), acc);
+  const float dot = block_sum<128>(acc, red);
+  if (threadIdx.x == 0)
+    dgamma[row] = rsqrtf(__ldg(running_var + row) + eps) * (dot - __ldg(running_mean + row) * __ldg(dbeta + row));
+}
+
 // w[r][:] *= scale[r]   (gradient of the un-folded convolution weight: dW = dW_folded * gamma / sqrt(var + eps))
 __global__ void __launch_bounds__(256)
 scale_rows_kernel(float* __restrict__ w, const float* __restrict__ scale, long long rows, long long cols) {
@@ -572,6 +594,17 @@ extern "C" int din_bn_gamma_grad_f16(const void* dz, const void* zsrc, const voi
   bn_gamma_grad_kernel<<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(dz), static_cast<const __half*>(zsrc), static_cast<const __half*>(sub), gamma, beta,
       dgamma, rows, c, inv_scale);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
+extern "C" int din_bn_fold_grads_f32(const float* w, const float* dwf, const float* dbeta, const float* running_mean,
+                                     const float* running_var, float eps, float* dgamma, int rows, long long cols,
+                                     void* stream) {
+  DIN_CHECK_ARG(w && dwf && dbeta && running_mean && running_var && dgamma, "din_bn_fold_grads_f32: null pointer");
+  DIN_CHECK_ARG(rows > 0 && cols > 0, "din_bn_fold_grads_f32: bad shape rows=%d cols=%lld", rows, cols);
+  bn_fold_grads_kernel<<<rows, 128, 0, static_cast<cudaStream_t>(stream)>>>(w, dwf, dbeta, running_mean, running_var, eps,
+                                                                            dgamma, cols);
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;
 }

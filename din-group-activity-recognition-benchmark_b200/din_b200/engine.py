@@ -105,6 +105,7 @@ class _Conv:
 class _Stem:
     def __init__(self, w, bias, scale=None, stride=1, pad=0, bn=None, relu=True):
         self.bn_scale, self.bn, self.relu = scale, bn, relu
+        self.w_src = w.contiguous().float()       # un-folded (d(gamma) of a folded BatchNorm needs it)
         if scale is not None:
             w = w * scale.view(-1, 1, 1, 1)       # one-time weight prep (BN folding), not on the hot path
         self.w, self.bias, self.stride, self.pad = w.contiguous().float(), bias.contiguous().float(), stride, pad
@@ -301,10 +302,6 @@ class Res18Plan:
         Stride-2 layers go through zero insertion (ops.scatter2_nhwc), so dgrad / wgrad stay the stride-1 kernels."""
         if self.bn_train:
             return self._backward_bn(saved, d_out, inv_scale, acc)
-
-        def gamma_grad(conv, a, dz, z, sub=None):
-            ops.bn_gamma_grad(dz, z, conv.bn["weight"], conv.bn["bias"], a["dgamma"], sub=sub, inv_scale=inv_scale)
-
         d = d_out
         for bi in reversed(range(len(self.blocks))):
             x_in, a1, identity, y = saved["blocks"][bi]
@@ -313,9 +310,7 @@ class Res18Plan:
             h_in, w_in = x_in.shape[1:3]
             dz2 = ops.relu_pool_bwd_nhwc(y, d, False)                         # ReLU after the residual add
             ops.conv2d_wgrad_nhwc(a1, dz2, a_c2["dw"], a_c2["dbeta"], pad=(1, 1), inv_scale=inv_scale)
-            gamma_grad(conv2, a_c2, dz2, y, sub=identity)
             dz1 = conv2.dgrad(dz2, relu_mask=a1)                              # conv1's ReLU backward in the epilogue
-            gamma_grad(conv1, a_c1, dz1, a1)
             dz1u = ops.scatter2_nhwc(dz1, h_in, w_in) if conv1.stride == 2 else dz1
             ops.conv2d_wgrad_nhwc(x_in, dz1u, a_c1["dw"], a_c1["dbeta"], pad=(1, 1), inv_scale=inv_scale)
             dx = conv1.dgrad(dz1u)
@@ -326,13 +321,12 @@ class Res18Plan:
                 # dZ (9x the useful work on three small layers, no extra tensor-core kernel)
                 dz2u = ops.scatter2_nhwc(dz2, h_in, w_in)
                 ops.conv2d_wgrad_nhwc(x_in, dz2u, a_dn["dw"], a_dn["dbeta"], pad=(1, 1), inv_scale=inv_scale)
-                gamma_grad(down, a_dn, dz2, identity)
                 ops.scatter2_nhwc(down.dgrad(dz2), h_in, w_in, dst=dx)
             d = dx
         dz0 = ops.maxpool3s2_relu_bwd_nhwc(saved["x0"], d)
         a0 = acc["stem"]
         ops.stem_wgrad(saved["images"], dz0, a0["dw"], a0["dbeta"], stride=2, pad=3, inv_scale=inv_scale, prep=True)
-        ops.bn_gamma_grad(dz0, saved["x0"], self.stem.bn["weight"], self.stem.bn["bias"], a0["dgamma"], inv_scale=inv_scale)
+        # d(gamma) of every folded BatchNorm comes from dW and d(beta) at export time (din_bn_fold_grads_f32)
 
     # -- BatchNorm on batch statistics (scripts/train_collective_stage2_dynamic.py: ResNet-18 trained with
     #    cfg.set_bn_eval = False): conv -> raw z -> stats -> normalise (+ residual) -> ReLU, all frames of the step at once
@@ -407,7 +401,12 @@ class Res18Plan:
         (din_scale_rows_f32), OIHW layout (permutes only)."""
         def put(conv_name, bn_name, conv, a, w_oihw):
             w_oihw = w_oihw.contiguous()
-            grads[conv_name + ".weight"] = w_oihw if self.bn_train else ops.scale_rows(w_oihw, conv.bn_scale)
+            if not self.bn_train:
+                # folded eval-mode BatchNorm: d(gamma) = invstd * (<W, dW_folded> - mean * d(beta)), then dW = scale * dW_folded
+                ops.bn_fold_grads(conv.w_src, w_oihw, a["dbeta"], conv.bn["running_mean"], conv.bn["running_var"],
+                                  a["dgamma"], eps=conv.bn["eps"])
+                ops.scale_rows(w_oihw, conv.bn_scale)
+            grads[conv_name + ".weight"] = w_oihw
             grads[bn_name + ".weight"], grads[bn_name + ".bias"] = a["dgamma"], a["dbeta"]
 
         put(self.prefix + "0", self.prefix + "1", self.stem, acc["stem"], acc["stem"]["dw"])

@@ -617,6 +617,20 @@ def bn_gamma_grad(dz, zsrc, gamma, beta, dgamma, *, sub=None, inv_scale=None):
     return dgamma
 
 
+def bn_fold_grads(w, dwf, dbeta, running_mean, running_var, dgamma, eps=1e-5):
+    """dgamma[r] = rsqrt(var[r] + eps) * (<w[r], dwf[r]> - mean[r] * dbeta[r])   (eval-mode BN folded into its conv;
+    w the un-folded weight, dwf the gradient w.r.t. the folded one, same element order)."""
+    for name, t in (("w", w), ("dwf", dwf), ("dbeta", dbeta), ("running_mean", running_mean),
+                    ("running_var", running_var), ("dgamma", dgamma)):
+        _need(t, torch.float32, name)
+    rows = w.shape[0]
+    assert w.shape == dwf.shape and dbeta.numel() == rows == dgamma.numel() == running_mean.numel()
+    with _launch("bn_fold_grads", 2 * w.numel(), 8 * w.numel()):
+        check(_lib.load().din_bn_fold_grads_f32(_p(w), _p(dwf), _p(dbeta), _p(running_mean), _p(running_var), float(eps),
+                                                _p(dgamma), rows, w.numel() // rows, _stream()), "din_bn_fold_grads_f32")
+    return dgamma
+
+
 def scale_rows(w, scale):
     """w[r] *= scale[r] in place (w fp32 [rows, ...])."""
     _need(w, torch.float32, "w")

@@ -431,6 +431,14 @@ DIN_API int din_bn_gamma_grad_f16(const void* dz, const void* zsrc, const void* 
 /* w[r][:] *= scale[r]: un-folds the BN scale from a folded convolution's weight gradient. */
 DIN_API int din_scale_rows_f32(float* w, const float* scale, long long rows, long long cols, void* stream);
 
+/* d(gamma) of an eval-mode BatchNorm folded into its convolution, from quantities the backward already has:
+ *   dgamma[r] = rsqrt(running_var[r] + eps) * ( <w[r,:], dwf[r,:]> - running_mean[r] * dbeta[r] )
+ * w: the UN-folded fp32 weight [rows][cols] (OIHW rows); dwf: gradient w.r.t. the folded weight in the same order
+ * (before din_scale_rows_f32); dbeta: the folded convolution's bias gradient.  Overwrites dgamma [rows].
+ * Replaces autograd of nn.BatchNorm2d.weight in eval mode (backbone.py:115-132 under cfg.set_bn_eval). */
+DIN_API int din_bn_fold_grads_f32(const float* w, const float* dwf, const float* dbeta, const float* running_mean,
+                          const float* running_var, float eps, float* dgamma, int rows, long long cols, void* stream);
+
 /* ---- BatchNorm2d on batch statistics (module.train() without cfg.set_bn_eval: config.py:80, train_net_dynamic.py:161;
  *      nn.BatchNorm2d layers of backbone/backbone.py:115-132).  z: raw convolution output [rows][c] (NHWC), fp16 or
  *      (z_is_f32) fp32 -- fp32 keeps the pre-normalisation values exact, so that y is rounded once, like the folded
