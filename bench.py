@@ -26,6 +26,7 @@ import sys
 import threading
 import time
 
+os.environ.setdefault("DIN_OFFLINE", "1")     # synthetic weights: never try to download ImageNet checkpoints
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "din-group-activity-recognition-benchmark_b200")
 for p in (PKG, os.path.join(ROOT, "oracle")):

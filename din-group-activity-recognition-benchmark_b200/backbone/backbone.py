@@ -6,25 +6,30 @@ unchanged).  Their forward runs the sm_100a plan in din_b200/engine.py — tcgen
 convolutions on NHWC fp16 — never the torchvision modules.
 """
 import os
-import warnings
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F          # noqa: F401  (the reference's star-imports hand `F` to its trainers)
 import torchvision.models as models
 
 from din_b200 import engine as _engine
 
 
 def _build(fn, pretrained, **kw):
-    """torchvision constructor; ImageNet weights only if the checkpoint is already in the local hub cache
-    (the reference passes pretrained=True everywhere and then overwrites the weights via loadmodel())."""
-    if pretrained:
-        w = models.get_model_weights(fn).DEFAULT
+    """torchvision constructor.  `pretrained=True` means ImageNet weights exactly as in the reference
+    (`models.vgg16(pretrained=True)`, backbone.py:14,92,118): torchvision loads them from the hub cache or downloads
+    them, and a failed download RAISES -- stage-1 training silently starting from random weights would be far worse
+    than an error.  Machines without network access opt out explicitly with DIN_OFFLINE=1 (tests, the synthetic
+    benchmark, stage-2 runs that overwrite the backbone through loadmodel() anyway): then the cached checkpoint is
+    used when present and random initialisation otherwise."""
+    if not pretrained:
+        return fn(weights=None, **kw)
+    w = models.get_model_weights(fn).DEFAULT
+    if os.environ.get("DIN_OFFLINE", "0") not in ("", "0"):
         path = os.path.join(torch.hub.get_dir(), "checkpoints", os.path.basename(w.url))
-        if os.path.exists(path):
-            return fn(weights=w, **kw)
-        warnings.warn(f"{os.path.basename(w.url)} not in the local hub cache (offline): random init")
-    return fn(weights=None, **kw)
+        if not os.path.exists(path):
+            return fn(weights=None, **kw)
+    return fn(weights=w, **kw)
 
 
 class _PlanBackbone(nn.Module):

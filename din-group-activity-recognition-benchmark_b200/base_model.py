@@ -16,6 +16,7 @@ import torch
 import torch.nn as nn
 
 from backbone.backbone import MyInception_v3, MyRes18, MyVGG16
+from din_b200 import plan_cache as _pc
 from din_b200 import train as _train
 from din_b200.engine import BasenetEngine
 from roi_align.roi_align import RoIAlign
@@ -52,7 +53,8 @@ class _Basenet(nn.Module):
         setattr(self, self._emb_name, nn.Linear(K * K * D, NFB))
         self.fc_actions = nn.Linear(NFB, cfg.num_actions)
         self.fc_activities = nn.Linear(NFB, cfg.num_activities)
-        self._engine, self._engine_key = None, None
+        self._owner = [self]               # nn.DataParallel replicas find the original model here (din_b200/plan_cache.py)
+        self._plans = _pc.PlanTable()
 
     def savemodel(self, filepath):
         state = {
@@ -65,18 +67,15 @@ class _Basenet(nn.Module):
         print("model saved to:", filepath)
 
     def engine(self):
-        tensors = list(self.state_dict().values())
-        key = (str(tensors[0].device),) + tuple((t.data_ptr(), t._version) for t in tensors)
-        if self._engine_key != key:
-            dev = tensors[0].device
-            if dev.type != "cuda":
-                raise RuntimeError("the DIN hot path runs on sm_100a only: move the model to a CUDA device "
-                                   "(there is no CPU fallback)")
+        own, dev, key = _pc.owner_of(self), _pc.device_of(self), _pc.version_key(self)
+        slot = own._plans.get(dev)
+        if slot is None or slot["key"] != key:
+            _pc.require_cuda(dev)
             with torch.cuda.device(dev):
-                self._engine = BasenetEngine(self.cfg, self.state_dict(), dev, dataset=self._dataset,
-                                             emb_name=self._emb_name)
-            self._engine_key = key
-        return self._engine
+                eng = BasenetEngine(self.cfg, _pc.named_tensors(self), dev, dataset=self._dataset,
+                                    emb_name=self._emb_name)
+            slot = own._plans.put(dev, key=key, engine=eng)
+        return slot["engine"]
 
     def _check_mode(self, images):
         if not images.is_cuda:
@@ -133,7 +132,7 @@ class Basenet_volleyball(_Basenet):
             if not torch.is_grad_enabled():
                 return _train.basenet_forward_train(self.engine(), frames, boxes_in.float(), training=True,
                                                     train_backbone=False)[0]
-            named = [(n, p) for n, p in self.named_parameters() if p.requires_grad]
+            named = _pc.trainable(self)
             return _BasenetTrainFn.apply(self, frames, boxes_in.float(), tuple(n for n, _ in named),
                                          *[p for _, p in named])
 

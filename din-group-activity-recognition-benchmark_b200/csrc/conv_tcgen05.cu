@@ -683,14 +683,7 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 template <int BN, int TB3>
 int launch_conv_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const ConvKParams& p, int grid, size_t smem,
                      cudaStream_t st) {
-  static thread_local int attr_dev = -1;
-  int dev = 0;
-  DIN_CHECK_CUDA(cudaGetDevice(&dev));
-  if (attr_dev != dev) {
-    DIN_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_2cta_kernel<BN, TB3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kSmemBudget + kNumEpiWarps * kEpiScratch + 4096 + 8192));
-    attr_dev = dev;
-  }
+  DIN_OPT_IN_SMEM((conv_igemm_2cta_kernel<BN, TB3>), kSmemBudget + kNumEpiWarps * kEpiScratch + 4096 + 8192);
   conv_igemm_2cta_kernel<BN, TB3><<<grid, kNumThreads, smem, st>>>(ta, tb, p);
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;
@@ -699,14 +692,7 @@ int launch_conv_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const ConvKPa
 template <int BN, int TB3>
 int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvKParams& p, int grid, size_t smem,
                 cudaStream_t st) {
-  static thread_local int attr_dev = -1;
-  int dev = 0;
-  DIN_CHECK_CUDA(cudaGetDevice(&dev));
-  if (attr_dev != dev) {
-    DIN_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, TB3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kSmemBudget + kNumEpiWarps * kEpiScratch + 4096 + 8192));
-    attr_dev = dev;
-  }
+  DIN_OPT_IN_SMEM((conv_igemm_kernel<BN, TB3>), kSmemBudget + kNumEpiWarps * kEpiScratch + 4096 + 8192);
   conv_igemm_kernel<BN, TB3><<<grid, kNumThreads, smem, st>>>(ta, tb, p);
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;

@@ -227,8 +227,7 @@ int launch_wgrad(const CUtensorMap& tdz, const CUtensorMap& tx, const WgradParam
   int n_stages = (220 * 1024) / kStageBytes;
   if (n_stages > 4) n_stages = 4;
   const size_t smem = static_cast<size_t>(n_stages) * kStageBytes + 1024 + (2 * kWgMaxStages + 1) * 8 + 16;
-  DIN_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<NCI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(smem)));
+  DIN_OPT_IN_SMEM(conv_wgrad_kernel<NCI>, smem);
   conv_wgrad_kernel<NCI><<<grid, kWgThreads, smem, st>>>(tdz, tx, p, n_stages);
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;

@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/din_sm100.h"
 
 // ----------------------------------------------------------------------------------------------
@@ -28,6 +30,21 @@ int din_set_error(int code, const char* fmt, ...);
     if (_e != cudaSuccess)                                                               \
       return din_set_error(DIN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                 \
                            cudaGetErrorString(_e), __FILE__, __LINE__);                  \
+  } while (0)
+
+// Dynamic shared memory above 48 KB is an opt-in per (function, device).  The opt-in is made once -- and raised only
+// when a launch needs more than any earlier one -- instead of on every launch: in the 130-260-launch training steps
+// the per-launch cudaFuncSetAttribute calls were a visible share of the host issue time.
+#define DIN_OPT_IN_SMEM(kernel, bytes)                                                                   \
+  do {                                                                                                   \
+    static std::atomic<int> _opted[64];                                                                  \
+    int _dev = 0;                                                                                        \
+    DIN_CHECK_CUDA(cudaGetDevice(&_dev));                                                                \
+    const int _want = static_cast<int>(bytes);                                                           \
+    if (_opted[_dev & 63].load(std::memory_order_relaxed) < _want) {                                     \
+      DIN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, _want));  \
+      _opted[_dev & 63].store(_want, std::memory_order_relaxed);                                         \
+    }                                                                                                    \
   } while (0)
 
 // Encodes a tiled tensor map through the driver entry point (no -lcuda link dependency).

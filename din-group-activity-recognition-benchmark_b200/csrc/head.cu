@@ -25,10 +25,14 @@ using namespace din;
 // every global access is a fully coalesced 512-byte warp transaction on the NHWC map.  The output row
 // of box m is [bin][channel] — the K-order the packed fc_emb weight uses — so RoIAlign's result is
 // directly the A operand of the embedding GEMM.
+// OutT = __half: the operand of the tensor-core embedding GEMM.  OutT = float: the un-rounded crops for the fp32
+// embedding path taken when there are fewer actor rows than half an MMA tile (engine.py: embed).
+template <typename OutT>
 __global__ void __launch_bounds__(256)
 roi_align_kernel(const __half* __restrict__ fm, const float* __restrict__ boxes, const int* __restrict__ box_ind,
-                 __half* __restrict__ out, int n_img, int H, int W, int D, int fm_c_stride, int M, int crop_h,
+                 OutT* __restrict__ out, int n_img, int H, int W, int D, int fm_c_stride, int M, int crop_h,
                  int crop_w) {
+  constexpr bool kF32 = sizeof(OutT) == 4;
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int bins = crop_h * crop_w;
@@ -41,10 +45,13 @@ roi_align_kernel(const __half* __restrict__ fm, const float* __restrict__ boxes,
   const RoiSample sp = roi_sample_point(boxes, box_ind, m, iy, ix, n_img, H, W, crop_h, crop_w);
   const int b = sp.img;
 
-  __half* op = out + (static_cast<size_t>(m) * bins + bin) * D;
+  OutT* op = out + (static_cast<size_t>(m) * bins + bin) * D;
   if (!sp.ok) {
     const uint4 z = make_uint4(0, 0, 0, 0);
-    for (int c = lane * 8; c < D; c += 256) *reinterpret_cast<uint4*>(op + c) = z;
+    for (int c = lane * 8; c < D; c += 256) {
+      *reinterpret_cast<uint4*>(op + c) = z;
+      if (kF32) *reinterpret_cast<uint4*>(op + c + 4) = z;
+    }
     return;
   }
   const int top = sp.top, bot = sp.bot, left = sp.left, right = sp.right;
@@ -63,17 +70,26 @@ roi_align_kernel(const __half* __restrict__ fm, const float* __restrict__ boxes,
     const __half2* htr = reinterpret_cast<const __half2*>(&vtr);
     const __half2* hbl = reinterpret_cast<const __half2*>(&vbl);
     const __half2* hbr = reinterpret_cast<const __half2*>(&vbr);
-    uint4 o;
-    __half2* ho = reinterpret_cast<__half2*>(&o);
+    float r[8];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float2 tl = __half22float2(htl[e]), tr = __half22float2(htr[e]);
       const float2 bl = __half22float2(hbl[e]), br = __half22float2(hbr[e]);
       const float t0 = tl.x + (tr.x - tl.x) * xl, t1 = tl.y + (tr.y - tl.y) * xl;
       const float b0 = bl.x + (br.x - bl.x) * xl, b1 = bl.y + (br.y - bl.y) * xl;
-      ho[e] = __floats2half2_rn(t0 + (b0 - t0) * yl, t1 + (b1 - t1) * yl);
+      r[2 * e] = t0 + (b0 - t0) * yl;
+      r[2 * e + 1] = t1 + (b1 - t1) * yl;
     }
-    *reinterpret_cast<uint4*>(op + c) = o;
+    if constexpr (kF32) {
+      *reinterpret_cast<float4*>(op + c) = make_float4(r[0], r[1], r[2], r[3]);
+      *reinterpret_cast<float4*>(op + c + 4) = make_float4(r[4], r[5], r[6], r[7]);
+    } else {
+      uint4 o;
+      __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) ho[e] = __floats2half2_rn(r[2 * e], r[2 * e + 1]);
+      *reinterpret_cast<uint4*>(op + c) = o;
+    }
   }
 }
 
@@ -339,24 +355,42 @@ readout_kernel(const float* __restrict__ s, const float* __restrict__ w, const f
 // ================================================================================================
 // C ABI
 // ================================================================================================
+static int roi_align_launch(const char* who, const void* fm, const float* boxes, const int32_t* box_ind, void* out,
+                            bool out_f32, int n_img, int h, int w, int d, int fm_c_stride, int m, int crop_h,
+                            int crop_w, void* stream) {
+  DIN_CHECK_ARG(fm && boxes && box_ind && out, "%s: null pointer", who);
+  DIN_CHECK_ARG(n_img > 0 && h > 1 && w > 1 && m > 0, "%s: bad extent n=%d h=%d w=%d m=%d", who, n_img, h, w, m);
+  DIN_CHECK_ARG(d > 0 && d % 8 == 0 && fm_c_stride >= d && fm_c_stride % 8 == 0,
+                "%s: d=%d / fm_c_stride=%d must be multiples of 8", who, d, fm_c_stride);
+  DIN_CHECK_ARG(crop_h > 1 && crop_w > 1, "%s: crop must be > 1", who);
+  DIN_CHECK_ARG((reinterpret_cast<uintptr_t>(fm) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                "%s: pointers must be 16-byte aligned", who);
+  const long long warps = static_cast<long long>(m) * crop_h * crop_w;
+  const int grid = static_cast<int>((warps + 7) / 8);
+  if (out_f32)
+    roi_align_kernel<float><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(fm), boxes, box_ind, static_cast<float*>(out), n_img, h, w, d, fm_c_stride, m,
+        crop_h, crop_w);
+  else
+    roi_align_kernel<__half><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(fm), boxes, box_ind, static_cast<__half*>(out), n_img, h, w, d, fm_c_stride, m,
+        crop_h, crop_w);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
 extern "C" int din_roi_align_nhwc_f16(const void* fm, const float* boxes, const int32_t* box_ind, void* out,
                                       int n_img, int h, int w, int d, int fm_c_stride, int m, int crop_h,
                                       int crop_w, void* stream) {
-  DIN_CHECK_ARG(fm && boxes && box_ind && out, "din_roi_align_nhwc_f16: null pointer");
-  DIN_CHECK_ARG(n_img > 0 && h > 1 && w > 1 && m > 0, "din_roi_align_nhwc_f16: bad extent n=%d h=%d w=%d m=%d",
-                n_img, h, w, m);
-  DIN_CHECK_ARG(d > 0 && d % 8 == 0 && fm_c_stride >= d && fm_c_stride % 8 == 0,
-                "din_roi_align_nhwc_f16: d=%d / fm_c_stride=%d must be multiples of 8", d, fm_c_stride);
-  DIN_CHECK_ARG(crop_h > 1 && crop_w > 1, "din_roi_align_nhwc_f16: crop must be > 1");
-  DIN_CHECK_ARG((reinterpret_cast<uintptr_t>(fm) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
-                "din_roi_align_nhwc_f16: pointers must be 16-byte aligned");
-  const long long warps = static_cast<long long>(m) * crop_h * crop_w;
-  const int grid = static_cast<int>((warps + 7) / 8);
-  roi_align_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(fm), boxes, box_ind, static_cast<__half*>(out), n_img, h, w, d, fm_c_stride, m,
-      crop_h, crop_w);
-  DIN_CHECK_CUDA(cudaGetLastError());
-  return DIN_OK;
+  return roi_align_launch("din_roi_align_nhwc_f16", fm, boxes, box_ind, out, false, n_img, h, w, d, fm_c_stride, m,
+                          crop_h, crop_w, stream);
+}
+
+extern "C" int din_roi_align_nhwc_f16_f32out(const void* fm, const float* boxes, const int32_t* box_ind, float* out,
+                                             int n_img, int h, int w, int d, int fm_c_stride, int m, int crop_h,
+                                             int crop_w, void* stream) {
+  return roi_align_launch("din_roi_align_nhwc_f16_f32out", fm, boxes, box_ind, out, true, n_img, h, w, d, fm_c_stride,
+                          m, crop_h, crop_w, stream);
 }
 
 extern "C" int din_group_layernorm_f32(const float* x, const float* pre, const float* post, const float* gamma,
@@ -411,8 +445,7 @@ extern "C" int din_dynamic_infer_f32(const float* x, const float* w_tap, const f
                 "din_dynamic_infer_f32: pointers must be 16-byte aligned");
   const size_t smem = (static_cast<size_t>(kt) * n * c + static_cast<size_t>(n) * n_out) * sizeof(float);
   DIN_CHECK_ARG(smem <= 220 * 1024, "din_dynamic_infer_f32: kt*n*c too large for shared memory (%zu bytes)", smem);
-  DIN_CHECK_CUDA(cudaFuncSetAttribute(dynamic_infer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(smem)));
+  DIN_OPT_IN_SMEM(dynamic_infer_kernel, smem);
   dynamic_infer_kernel<<<b * t, kDinThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       x, w_tap, b_cat, y, t, n, c, kt, kn, ratio, scale_factor, coef_ptr, coef_scalar, accumulate, n_valid);
   DIN_CHECK_CUDA(cudaGetLastError());

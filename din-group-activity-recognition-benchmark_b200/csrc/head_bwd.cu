@@ -658,8 +658,7 @@ extern "C" int din_dynamic_infer_bwd_f32(const float* x, const float* w_tap, con
   float* dcoef_part = ws + nodes * n_out;     // [nodes]
   const size_t smem = (static_cast<size_t>(kt) * n * c + static_cast<size_t>(n) * n_out) * sizeof(float);
   DIN_CHECK_ARG(smem <= 220 * 1024, "din_dynamic_infer_bwd_f32: kt*n*c too large for shared memory (%zu bytes)", smem);
-  DIN_CHECK_CUDA(cudaFuncSetAttribute(din_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(smem)));
+  DIN_OPT_IN_SMEM(din_bwd_kernel, smem);
   din_bwd_kernel<<<b * t, kDinThreads, smem, st>>>(x, w_tap, b_cat, dy, dx, dconv, dcoef_part, t, n, c, kt, kn, ratio,
                                                    scale_factor, coef_ptr, coef_scalar, n_valid);
   DIN_CHECK_CUDA(cudaGetLastError());

@@ -363,13 +363,11 @@ extern "C" int din_stem_conv_nchw_f32(const float* x, const float* w, const floa
   const size_t smem = (static_cast<size_t>(K) * c_out + 3 * in_th * in_tw_p) * sizeof(float);
   dim3 grid((ow + kStemTileW - 1) / kStemTileW, (oh + kStemTileH - 1) / kStemTileH, n);
   if (c_out == 64) {
-    DIN_CHECK_CUDA(cudaFuncSetAttribute(stem_conv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(smem)));
+    DIN_OPT_IN_SMEM(stem_conv_kernel<32>, smem);
     stem_conv_kernel<32><<<grid, kStemThreads, smem, st>>>(x, w, bias, static_cast<__half*>(y), h, w_in, oh, ow,
                                                            kh, kw, stride, pad, relu, prep);
   } else {
-    DIN_CHECK_CUDA(cudaFuncSetAttribute(stem_conv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(smem)));
+    DIN_OPT_IN_SMEM(stem_conv_kernel<16>, smem);
     stem_conv_kernel<16><<<grid, kStemThreads, smem, st>>>(x, w, bias, static_cast<__half*>(y), h, w_in, oh, ow,
                                                            kh, kw, stride, pad, relu, prep);
   }

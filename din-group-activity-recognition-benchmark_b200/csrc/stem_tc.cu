@@ -560,8 +560,7 @@ int launch_wide(StemParams& p, cudaStream_t st) {
   if (per_sm < 1) per_sm = 1;
   long long grid = static_cast<long long>(sms > 0 ? sms : 148) * per_sm;
   if (grid > p.num_tiles) grid = p.num_tiles;
-  DIN_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_wide_kernel<COUT, KH, KW, STRIDE, U8>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemWide)));
+  DIN_OPT_IN_SMEM((stem_tc_wide_kernel<COUT, KH, KW, STRIDE, U8>), kSmemWide);
   stem_tc_wide_kernel<COUT, KH, KW, STRIDE, U8><<<static_cast<int>(grid), kWideThreads, kSmemWide, st>>>(p);
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;
@@ -582,8 +581,7 @@ int launch(StemParams& p, cudaStream_t st) {
   if (per_sm < 1) per_sm = 1;
   long long grid = static_cast<long long>(sms > 0 ? sms : 148) * per_sm;
   if (grid > p.num_tiles) grid = p.num_tiles;
-  DIN_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel<COUT, KH, KW, STRIDE, U8>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Cfg::kSmem)));
+  DIN_OPT_IN_SMEM((stem_tc_kernel<COUT, KH, KW, STRIDE, U8>), Cfg::kSmem);
   stem_tc_kernel<COUT, KH, KW, STRIDE, U8><<<static_cast<int>(grid), kStemThreads, Cfg::kSmem, st>>>(p);
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;
@@ -761,8 +759,7 @@ int launch_stem_wgrad(const CUtensorMap& tdz, StemParams& p, float* dw, float* d
   if (per_sm < 1) per_sm = 1;
   long long grid = static_cast<long long>(sms > 0 ? sms : 148) * per_sm;
   if (grid > p.num_tiles) grid = p.num_tiles;
-  DIN_CHECK_CUDA(cudaFuncSetAttribute(stem_wgrad_tc_kernel<KH, KW, STRIDE, U8>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SC::kSmem)));
+  DIN_OPT_IN_SMEM((stem_wgrad_tc_kernel<KH, KW, STRIDE, U8>), SC::kSmem);
   stem_wgrad_tc_kernel<KH, KW, STRIDE, U8><<<static_cast<int>(grid), kStemThreads, SC::kSmem, st>>>(tdz, p, dw, dbias,
                                                                                                   inv_scale);
   DIN_CHECK_CUDA(cudaGetLastError());

@@ -26,11 +26,12 @@ class DinPackJob(C.Structure):
 
 _vp, _i, _fp, _ll = C.c_void_p, C.c_int, C.c_void_p, C.c_longlong  # float* is passed as a raw address
 
-# name -> (restype, argtypes).  tests/test_abi.py checks this table against include/din_sm100.h.
+# name -> (restype, argtypes).  tests/test_abi_cpu.py checks this table against include/din_sm100.h.
 PROTOTYPES = {
     "din_abi_version": (C.c_int, []),
     "din_last_error_string": (C.c_char_p, []),
     "din_device_sm_count": (C.c_int, []),
+    "din_tmap_cache_stats": (C.c_int, [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "din_stem_conv_nchw_f32": (C.c_int, [_fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_stem_conv_nhwc_u8": (C.c_int, [_vp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_conv2d_nhwc_f16": (C.c_int, [C.POINTER(DinConvDesc), _vp, _vp, _fp, _vp, _vp, _vp]),
@@ -46,6 +47,7 @@ PROTOTYPES = {
     "din_avgpool2d_nhwc_f16": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_upsample_bilinear_nhwc_f16": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_roi_align_nhwc_f16": (C.c_int, [_vp, _fp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "din_roi_align_nhwc_f16_f32out": (C.c_int, [_vp, _fp, _vp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_group_layernorm_f32": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _ll, _ll, _i, _ll, _i,
                                           C.c_float, _i, _vp, _vp]),
     "din_linear_f32": (C.c_int, [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _vp]),

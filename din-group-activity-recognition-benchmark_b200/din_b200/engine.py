@@ -63,6 +63,16 @@ def _pack_dgrad_filters(convs):
         c._w_dgrad = t
 
 
+# A launch with fewer output pixels than one wave of 128-pixel tiles (148 SMs) is latency-bound: the tensor pipe idles
+# most of its ~10 us either way.  Such launches run with the weight split into hi + lo fp16 parts (w_split = 2: both
+# multiplied with the same A tile into the same accumulator, i.e. weights exact to ~22 bits) -- precision that costs
+# nothing exactly where the path needs it most: tiny inputs (one frame, one actor) have no averaging over pixels or
+# actors to hide operand rounding behind (tests/test_edge_cases_gpu.py holds T = N = 1 to the same 1e-3 as every
+# BASELINE shape).  Full-size launches are untouched.
+SMALL_LAUNCH_PIXELS = 148 * 128
+SMALL_EMBED_ROWS = 64       # fewer actor rows than half an MMA tile: fp32 crops + fp32 fc_emb_1 (din_linear_f32)
+
+
 class _Conv:
     """One tcgen05 convolution of the plan (weights packed fp16 [co][kh][kw][ci], fp32 bias)."""
 
@@ -72,6 +82,7 @@ class _Conv:
         self.bn = bn                       # its {'weight', 'bias', ...} (training: d(gamma) needs gamma and beta)
         self.w_src = w = w.contiguous()
         self._w_dgrad = None
+        self._w_exact = None               # hi + lo parts, packed on first use by a latency-bound launch
         self._w, self.split = None, split
         if _PackBatch.active is not None:
             _PackBatch.active.convs.append(self)
@@ -87,9 +98,16 @@ class _Conv:
         assert self._w is not None, "weight used inside the _PackBatch block that defers its packing"
         return self._w
 
+    def _weight_for(self, x):
+        if self.split == 2 or x.shape[0] * x.shape[1] * x.shape[2] > SMALL_LAUNCH_PIXELS * self.stride * self.stride:
+            return self.w
+        if self._w_exact is None:
+            self._w_exact = ops.pack_conv_weights([(self.w_src, self.bn_scale, 2, False)])[0]
+        return self._w_exact
+
     def __call__(self, x, out=None, residual=None, **kw):
         kw.setdefault("c_in", self.c_in)
-        return ops.conv2d_nhwc(x, self.w, self.bias, stride=self.stride, pad=self.pad, relu=self.relu,
+        return ops.conv2d_nhwc(x, self._weight_for(x), self.bias, stride=self.stride, pad=self.pad, relu=self.relu,
                                residual=residual, out=out, pool2=self.pool2, **kw)
 
     def dgrad(self, dz, relu_mask=None):
@@ -499,6 +517,7 @@ class DinEngine:
         self.fc_emb = _Conv(wp.view(self.NFB, self.K * self.K * self.D_stride, 1, 1), sd["fc_emb_1.bias"], relu=False,
                             split=2 if cfg.backbone == "inv3" else 1)
         self.fc_emb_wk = wp.view(self.NFB, self.K * self.K * self.D_stride)   # fp32, kernel K order (d(crops) GEMM)
+        self.fc_emb_bias = sd["fc_emb_1.bias"].contiguous().float()
         self.nl_emb = (sd["nl_emb_1.weight"].contiguous(), sd["nl_emb_1.bias"].contiguous())
         if cfg.lite_dim:
             pw = sd["point_conv.weight"]
@@ -581,8 +600,15 @@ class DinEngine:
     def embed(self, fm, boxes_flat, B, T, N):
         """RoIAlign -> fc_emb_1 -> nl_emb_1 -> ReLU -> (lite branch).  Returns fp32 [B,T,N,C]."""
         M = B * T * N
-        crops = ops.roi_align_nhwc(fm, boxes_flat, self._box_idx(B * T, N), self.K, self.K, d=self.D_stride)
-        emb = self.fc_emb(crops.view(1, 1, M, self.K * self.K * self.D_stride), out_f32=True).view(M, self.NFB)
+        if M < SMALL_EMBED_ROWS:
+            # a handful of actors: the GEMM is a latency-bound sliver of one MMA tile either way, so it runs in fp32
+            # on un-rounded crops and the fp32 weight (no fp16 rounding of either operand)
+            crops = ops.roi_align_nhwc(fm, boxes_flat, self._box_idx(B * T, N), self.K, self.K, d=self.D_stride,
+                                       out_f32=True)
+            emb = ops.linear_f32(crops.view(M, -1), self.fc_emb_wk, self.fc_emb_bias)
+        else:
+            crops = ops.roi_align_nhwc(fm, boxes_flat, self._box_idx(B * T, N), self.K, self.K, d=self.D_stride)
+            emb = self.fc_emb(crops.view(1, 1, M, self.K * self.K * self.D_stride), out_f32=True).view(M, self.NFB)
         x = ops.group_layernorm(emb, *self.nl_emb, n_outer=M, outer_stride=self.NFB, cols=self.NFB, relu=True)
         if self.cfg.lite_dim:
             y = ops.linear_f32(x, self.point_w, self.point_b)

@@ -215,20 +215,31 @@ def upsample_bilinear_nhwc(x, oh, ow, out=None, c=None, x_c_offset=0, y_c_offset
 # ---------------------------------------------------------------------------------------------
 # person-level head
 # ---------------------------------------------------------------------------------------------
-def roi_align_nhwc(fm, boxes, box_ind, crop_h, crop_w, d=None, out=None):
-    """fm [n_img,h,w,Cs] fp16 NHWC; boxes [m,4] fp32; box_ind [m] int32 -> [m, crop_h*crop_w, d] fp16."""
+def roi_align_nhwc(fm, boxes, box_ind, crop_h, crop_w, d=None, out=None, out_f32=False):
+    """fm [n_img,h,w,Cs] fp16 NHWC; boxes [m,4] fp32; box_ind [m] int32 -> [m, crop_h*crop_w, d] fp16
+    (out_f32: the un-rounded fp32 crops, for the fp32 embedding of very small batches)."""
     _need(fm, torch.float16, "fm")
     _need(boxes, torch.float32, "boxes")
     _need(box_ind, torch.int32, "box_ind")
     n_img, h, w, cs = fm.shape
     d = cs if d is None else d
     m = boxes.shape[0]
+    dt = torch.float32 if out_f32 else torch.float16
     if out is None:
-        out = torch.empty((m, crop_h * crop_w, d), dtype=torch.float16, device=fm.device)
-    with _launch("roi_align", 0, 2 * n_img * h * w * d + 2 * m * crop_h * crop_w * d):
-        check(_lib.load().din_roi_align_nhwc_f16(_p(fm), _p(boxes), _p(box_ind), _p(out), n_img, h, w, d, cs, m,
-                                                 crop_h, crop_w, _stream()), "din_roi_align_nhwc_f16")
+        out = torch.empty((m, crop_h * crop_w, d), dtype=dt, device=fm.device)
+    _need(out, dt, "out")
+    fn = "din_roi_align_nhwc_f16_f32out" if out_f32 else "din_roi_align_nhwc_f16"
+    with _launch("roi_align", 0, 2 * n_img * h * w * d + out.element_size() * m * crop_h * crop_w * d):
+        check(getattr(_lib.load(), fn)(_p(fm), _p(boxes), _p(box_ind), _p(out), n_img, h, w, d, cs, m,
+                                       crop_h, crop_w, _stream()), fn)
     return out
+
+
+def tmap_cache_stats():
+    """(cached maps, hits, misses) of the library's CUtensorMap cache."""
+    h, m = C.c_ulonglong(0), C.c_ulonglong(0)
+    n = _lib.load().din_tmap_cache_stats(C.byref(h), C.byref(m))
+    return n, h.value, m.value
 
 
 def group_layernorm(x, gamma, beta, *, n_outer, n_inner=1, outer_stride, inner_stride=0, rows=1, row_stride=0,

@@ -16,10 +16,16 @@ Training the Inception-v3 backbone, or Inception-v3 with BatchNorm on batch stat
 """
 import collections
 
+# The reference's trainers take `torch`, `nn`, `F`, `np`, `models`, the meters ... from the star-imports of this module
+# (train_net_dynamic.py:13 `from infer_model import *`, infer_model.py:1-2), so the same two star-imports stay here.
+from backbone.backbone import *          # noqa: F401,F403
+from utils import *                      # noqa: F401,F403
+
 import torch
 import torch.nn as nn
 
 from backbone.backbone import MyInception_v3, MyRes18, MyVGG16
+from din_b200 import plan_cache as _pc
 from din_b200 import train as _train
 from din_b200.engine import DinEngine
 from infer_module.dynamic_infer_module import (Dynamic_Person_Inference, Hierarchical_Dynamic_Inference,
@@ -104,8 +110,8 @@ class _DinModel(nn.Module):
                 nn.init.kaiming_normal_(m.weight)
                 if m.bias is not None:
                     nn.init.zeros_(m.bias)
-        self._engine, self._engine_key = None, None
-        self._bb_plan_key = None
+        self._owner = [self]               # nn.DataParallel replicas find the original model here (din_b200/plan_cache.py)
+        self._plans = _pc.PlanTable()
 
     # -- reference API ---------------------------------------------------------------------------
     def loadmodel(self, filepath):
@@ -129,22 +135,24 @@ class _DinModel(nn.Module):
                                      for m in self.backbone.modules())
 
     def engine(self):
-        tensors = list(self.state_dict().values())
+        """The forward plan for this model on its device: rebuilt only when a tensor of the (owner) model changed."""
+        own = _pc.owner_of(self)
+        dev = _pc.device_of(self)
         bn_train = self._bn_batch_stats()
-        key = (str(tensors[0].device), bn_train) + tuple((t.data_ptr(), t._version) for t in tensors)
-        if self._engine_key != key:
-            dev = tensors[0].device
-            if dev.type != "cuda":
-                raise RuntimeError("the DIN hot path runs on sm_100a only: move the model to a CUDA device "
-                                   "(there is no CPU fallback)")
-            # the backbone plan survives head-only weight updates (frozen-backbone training)
-            bb_key = (str(dev), bn_train) + tuple((t.data_ptr(), t._version) for t in self.backbone.state_dict().values())
-            plan = self._engine.backbone if (self._engine is not None and self._bb_plan_key == bb_key) else None
+        key = (bn_train,) + _pc.version_key(self)
+        slot = own._plans.get(dev)
+        if slot is None or slot["key"] != key:
+            _pc.require_cuda(dev)
+            # the backbone plan survives head-only weight updates (frozen-backbone training); on batch statistics the
+            # convolutions run un-folded and the kernels read the running statistics through live pointers, so the
+            # BatchNorm buffers (bumped every step) are not part of the backbone's key
+            bb_key = (bn_train,) + _pc.version_key(self, buffers=not bn_train, prefix="backbone")
+            plan = slot["engine"].backbone if (slot is not None and slot["bb_key"] == bb_key) else None
             with torch.cuda.device(dev):
-                self._engine = DinEngine(self.cfg, self.state_dict(), dev, dataset=self._dataset, backbone_plan=plan,
-                                         bn_train=bn_train)
-            self._engine_key, self._bb_plan_key = key, bb_key
-        return self._engine
+                eng = DinEngine(self.cfg, _pc.named_tensors(self), dev, dataset=self._dataset, backbone_plan=plan,
+                                bn_train=bn_train)
+            slot = own._plans.put(dev, key=key, bb_key=bb_key, engine=eng)
+        return slot["engine"]
 
     def _check_mode(self, images):
         if not images.is_cuda:
@@ -168,12 +176,12 @@ class _DinModel(nn.Module):
             return eng.forward_volleyball(images, boxes)
         if not torch.is_grad_enabled():
             return _train.forward_train(eng, images, boxes, bboxes_num, training=True)[0]
-        if any(p.requires_grad for p in self.backbone.parameters()) and self.cfg.backbone not in ("vgg16", "res18"):
+        named = _pc.trainable(self)
+        if any(n.startswith("backbone.") for n, _ in named) and self.cfg.backbone not in ("vgg16", "res18"):
             raise NotImplementedError(
                 f"training the backbone is implemented for VGG-16 and ResNet-18 (BatchNorm in eval mode), not "
                 f"{self.cfg.backbone!r}: set cfg.train_backbone = False (config.py:39, the stage-2 default) -- "
                 "SURVEY.md §8f rank 1")
-        named = [(n, p) for n, p in self.named_parameters() if p.requires_grad]
         names = tuple(n for n, _ in named)
         return _DinTrainFn.apply(self, images, boxes, bboxes_num, names, *[p for _, p in named])
 

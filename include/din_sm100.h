@@ -48,6 +48,9 @@ DIN_API int din_abi_version(void);
 DIN_API const char* din_last_error_string(void);
 /* Number of SMs of the current device (148 on B200), or a negative error. */
 DIN_API int din_device_sm_count(void);
+/* Encoded CUtensorMaps are cached per (base pointer, extents, strides, box, swizzle): SURVEY.md section 8b.  Returns the
+ * number of cached maps and, through the optional out-pointers, the hit / miss counts since load (diagnostics). */
+DIN_API int din_tmap_cache_stats(unsigned long long* hits, unsigned long long* misses);
 
 /* ---- backbone ------------------------------------------------------------------------------ */
 
@@ -193,6 +196,12 @@ DIN_API int din_upsample_bilinear_nhwc_f16(const void* x, void* y, int n, int h,
 DIN_API int din_roi_align_nhwc_f16(const void* fm, const float* boxes, const int32_t* box_ind, void* out,
                                    int n_img, int h, int w, int d, int fm_c_stride, int m, int crop_h,
                                    int crop_w, void* stream);
+/* Same sampling, un-rounded fp32 output [m][crop_h*crop_w][d]: the A operand of the fp32 embedding path
+ * (din_linear_f32) that the plan takes when there are fewer actor rows than half an MMA tile -- a launch that small is
+ * latency-bound, so skipping the fp16 rounding of crops and fc_emb_1 weights costs nothing there. */
+DIN_API int din_roi_align_nhwc_f16_f32out(const void* fm, const float* boxes, const int32_t* box_ind, float* out,
+                                          int n_img, int h, int w, int d, int fm_c_stride, int m, int crop_h,
+                                          int crop_w, void* stream);
 
 /*
  * LayerNorm over strided groups with optional pre-add, ReLU, post-add:

@@ -1,6 +1,7 @@
 """ref_harness.py — imports the REAL reference classes from /root/reference.  TEST INFRASTRUCTURE ONLY.
 
-Usable only where /root/reference exists (the authoring container); never on the GPU box.  It is how the
+Usable where /root/reference exists (the authoring container) or where oracle/make_ref.py staged a byte-for-byte
+copy under oracle/_ref/reference (git-ignored; it travels to the GPU box with the snapshot).  It is how the
 oracle restatement (din_oracle.py) is pinned and how the fixtures in tests/golden/ are generated.
 
 Recipe:
@@ -30,8 +31,9 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-REF_ROOT = "/root/reference"
 _HERE = os.path.dirname(os.path.abspath(__file__))
+REF_ROOT = next((p for p in ("/root/reference", os.path.join(_HERE, "_ref", "reference"))
+                 if os.path.exists(os.path.join(p, "infer_model.py"))), "/root/reference")
 _SHIMS = os.path.join(_HERE, "shims")
 
 _COLLIDING = ("config", "utils", "backbone", "infer_model", "infer_module", "gcn_model", "base_model",

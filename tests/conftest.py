@@ -3,6 +3,7 @@ import sys
 
 import pytest
 
+os.environ.setdefault("DIN_OFFLINE", "1")     # no network: pretrained=True falls back to random init (backbone.py:_build)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "din-group-activity-recognition-benchmark_b200")
 for p in (PKG, os.path.join(ROOT, "oracle"), ROOT):
