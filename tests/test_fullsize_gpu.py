@@ -1,0 +1,106 @@
+"""Logits parity at the BASELINE.json shapes themselves: every config (and the headline workload of bench.py) at its
+real frame size, T = 10 frames, real actor counts -- one clip per case (two to three for Collective, so that the actor
+count differs between clips), which the CPU oracle finishes in seconds.  Tolerance is north_star's:
+max|delta| <= 1e-3 * max|ref|.  Reference: infer_model.py:141-234 (Volleyball), :1226-1319 (Collective),
+infer_module/dynamic_infer_module.py:446-498 (hierarchical; oracle patch H), patch I for Inception-v3.
+
+Also here: the fp16 overflow audit SURVEY.md §7 (hard part 1) asks for -- the same path with the backbone's weights
+rescaled so that its activations reach the magnitudes of an ImageNet-pretrained network and far beyond."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(cuda, backbone, hw, B, **kw):
+    from test_e2e_gpu import _pc, _run_case
+    return _run_case(cuda, _pc(backbone, hw, **kw), B)
+
+
+def test_headline_vgg16_lite128_T10_N12_720p(cuda):
+    """bench.py's default workload = scripts/train_volleyball_stage2_dynamic.py (VGG-16, lite_dim 128, T=10, N=12)."""
+    _run(cuda, "vgg16", (720, 1280), 1, num_frames=10, num_boxes=12)
+
+
+def test_config2_inception_v3_T10_N12_720p(cuda):
+    """BASELINE configs[1]: Inception-v3 to Mixed_6e, multiscale 1056-channel map 87x157, C = 1024."""
+    _run(cuda, "inv3", (720, 1280), 1, emb_features=1056, num_frames=10, num_boxes=12, lite_dim=None)
+
+
+def test_config3_res18_lite128_T10_N12_720p(cuda):
+    """BASELINE configs[2]: lite-DIN (lite_dim 128) on ResNet-18."""
+    _run(cuda, "res18", (720, 1280), 1, num_frames=10, num_boxes=12)
+
+
+def test_config4_vgg16_hierarchical_st_factorized_T10_N12_720p(cuda):
+    """BASELINE configs[3]: ST-factorized DIN, ST_kernel_size [(1,3),(3,1)], hierarchical (hier_LN is hard-coded to
+    [10,12,1024], dynamic_infer_module.py:475, so lite_dim is None)."""
+    _run(cuda, "vgg16", (720, 1280), 1, num_frames=10, num_boxes=12, lite_dim=None,
+         ST_kernel_size=[(1, 3), (3, 1)], hierarchical_inference=True)
+
+
+def test_config5_collective_res18_480x720_T10_ragged_actors(cuda):
+    """BASELINE configs[4]: Collective, ResNet-18 at 480x720, up to 13 actors, a different actor count per clip."""
+    import din_oracle as O
+    from test_e2e_gpu import _pc
+    pc = _pc("res18", (480, 720), dataset="collective", num_frames=10, num_boxes=13, lite_dim=None,
+             ST_kernel_size=(3, 3), num_activities=4)
+    counts = O.make_inputs(pc, 3, seed=0)[2][:, 0].tolist()
+    assert len(set(counts)) > 1, counts                          # ragged
+    from test_e2e_gpu import _run_case
+    _run_case(cuda, pc, 3)
+
+
+def test_edge_T1_N1_over_seeds(cuda):
+    """The degenerate clip (one frame, one actor, 2x3 map) has nothing to average operand rounding over; it is held
+    to the same 1e-3 as the BASELINE shapes (latency-bound launches run with exact weights and an fp32 embedding,
+    din_b200/engine.py: SMALL_LAUNCH_PIXELS / SMALL_EMBED_ROWS).  Four seeds, all must pass."""
+    from test_e2e_gpu import _pc, _run_case
+    for seed in range(4):
+        _run_case(cuda, _pc("vgg16", (64, 96), num_frames=1, num_boxes=1), 1, seed=seed)
+
+
+@pytest.mark.parametrize("gain,expect_finite", [(1.45, True), (1.75, True)])
+def test_fp16_overflow_audit_pretrained_scale(cuda, gain, expect_finite):
+    """fp16 activations overflow at 65504.  Kaiming-random weights keep activations O(1), so parity tests alone say
+    nothing about range.  Here every VGG-16 conv weight is multiplied by `gain` (biases by the accumulated gain), which
+    scales layer l's activations by gain^l: gain 1.45 puts conv5_3 at 125x and the feature map's maximum at
+    ~1e3 (the top of what ImageNet-pretrained VGG-16 features reach), gain 1.75 at 1444x, maximum ~1.1e4: an order
+    beyond, still 6x under the fp16 limit.  The CUDA path must stay finite and still match the fp32 oracle to 1e-3 (nl_emb_1's LayerNorm
+    removes the scale after the embedding, so the logits stay O(1))."""
+    import din_oracle as O
+    import infer_model as IM
+    from config import Config
+    pc = O.PathConfig(backbone="vgg16", image_size=(192, 320), out_size=(6, 10), num_frames=3, num_boxes=6)
+    bb = O.build_backbone("vgg16")
+    sd = O.make_state_dict(pc, seed=0, backbone=bb)
+    acc, layer = 1.0, 0
+    for k in sorted((k for k in sd if k.startswith("backbone.features.") and k.endswith(".weight")),
+                    key=lambda s: int(s.split(".")[2])):
+        acc *= gain
+        layer += 1
+        sd[k] = sd[k] * gain
+        sd[k.replace(".weight", ".bias")] = sd[k.replace(".weight", ".bias")] * acc
+    O.load_backbone(bb, sd)
+    images, boxes = O.make_inputs(pc, 2, seed=0)
+    ref, inter = O.volleyball_forward(bb, sd, pc, images, boxes, return_intermediates=True)
+    fm_max = inter["features"].abs().max().item()
+    cfg = Config("volleyball")
+    cfg.log_path = None
+    for k in ("backbone", "image_size", "out_size", "emb_features", "num_frames", "num_boxes", "lite_dim",
+              "ST_kernel_size", "beta_factor"):
+        setattr(cfg, k, getattr(pc, k))
+    cfg.sampling_ratio = list(pc.sampling_ratio)
+    model = IM.Dynamic_volleyball(cfg)
+    model.load_state_dict(sd)
+    model = model.to(cuda).eval()
+    with torch.no_grad():
+        out = model((images.to(cuda), boxes.to(cuda)))["activities"].cpu()
+        fm = model.engine().features(images.reshape(-1, 3, 192, 320).to(cuda))
+    got_max = fm.float().abs().max().item()
+    err, scale = (out - ref).abs().max().item(), ref.abs().max().item()
+    print(f"\n[overflow audit] gain {gain}^13 = {acc:.0f}x: oracle feature-map max {fm_max:.1f}, CUDA {got_max:.1f} "
+          f"(fp16 max 65504); logits rel err {err / scale:.2e}")
+    assert torch.isfinite(fm).all() and torch.isfinite(out).all()
+    assert abs(got_max - fm_max) <= 2e-3 * fm_max
+    assert err <= 1e-3 * scale
