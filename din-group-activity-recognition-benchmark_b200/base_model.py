@@ -31,13 +31,18 @@ class _BasenetTrainFn(torch.autograd.Function):
         (actions, activities), tape = _train.basenet_forward_train(model.engine(), images, boxes,
                                                                     training=model.training, train_backbone=train_bb)
         ctx.eng, ctx.tape, ctx.names = model.engine(), tape, names
+        ctx.sink = getattr(_pc.owner_of(model), "grad_sink", None)
         ctx.shapes = [tuple(p.shape) for p in params]
         return actions, activities
 
     @staticmethod
     def backward(ctx, dactions, dactivities):
-        grads = _train.basenet_backward(ctx.eng, ctx.tape, dactions, dactivities)
+        sink = ctx.sink if (ctx.sink is not None and ctx.sink.active()) else None
+        grads = _train.basenet_backward(ctx.eng, ctx.tape, dactions, dactivities, sink=sink)
         ctx.tape = None
+        if sink is not None:
+            sink.finish()
+            return (None,) * (4 + len(ctx.names))
         out = [grads[n].reshape(shp) if (need and n in grads) else None
                for n, shp, need in zip(ctx.names, ctx.shapes, ctx.needs_input_grad[4:])]
         return (None, None, None, None) + tuple(out)

@@ -24,6 +24,10 @@ class DinPackJob(C.Structure):
         "rows", "cols", "cols_padded", "kh", "kw", "split", "transposed", "reserved")]
 
 
+class DinFlatJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst_offset", C.c_longlong), ("numel", C.c_longlong)]
+
+
 _vp, _i, _fp, _ll = C.c_void_p, C.c_int, C.c_void_p, C.c_longlong  # float* is passed as a raw address
 
 # name -> (restype, argtypes).  tests/test_abi_cpu.py checks this table against include/din_sm100.h.
@@ -73,6 +77,7 @@ PROTOTYPES = {
     "din_readout_bwd_f32": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _vp, _vp]),
     "din_group_layernorm_bwd_f32": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _ll, _ll, _i,
                                               _ll, _i, C.c_float, _i, _i, _vp, _vp]),
+    "din_pack_flat_f32": (C.c_int, [C.POINTER(DinFlatJob), _i, _fp, C.c_float, _vp]),
     "din_dynamic_infer_bwd_ws_floats": (C.c_longlong, [_i, _i, _i, _i, _i, _i, _i]),
     "din_dynamic_infer_bwd_f32": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i,
                                             _i, _i, _fp, C.c_float, _vp, _vp]),

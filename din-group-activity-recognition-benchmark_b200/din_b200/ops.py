@@ -698,3 +698,19 @@ def bn_train_backward(g, z, mean, invstd, gamma, dbeta=None, dgamma=None, *, inv
         check(_lib.load().din_bn_bwd(_p(g), _p(z), int(f32), _p(mean), _p(invstd), _p(gamma), _p(sums), _p(dz), _p(dbeta),
                                      _p(dgamma), _p(inv_scale), rows, c, _stream()), "din_bn_bwd")
     return dz
+
+
+def pack_flat(tensors, flat, offsets, scale=1.0):
+    """flat[offsets[i] : offsets[i] + tensors[i].numel()] = scale * tensors[i] for all i, in ONE launch (csrc/flat.cu)."""
+    _need(flat, torch.float32, "flat")
+    arr = (_lib.DinFlatJob * len(tensors))()
+    total = 0
+    for j, t, off in zip(arr, tensors, offsets):
+        _need(t, torch.float32, "gradient")
+        if off < 0 or off + t.numel() > flat.numel():
+            raise _lib.DinError("pack_flat: tensor does not fit the flat buffer")
+        j.src, j.dst_offset, j.numel = t.data_ptr(), off, t.numel()
+        total += t.numel()
+    with _launch(f"pack_flat_{len(tensors)}", 0, 8 * total):
+        check(_lib.load().din_pack_flat_f32(arr, len(tensors), _p(flat), float(scale), _stream()), "din_pack_flat_f32")
+    return flat

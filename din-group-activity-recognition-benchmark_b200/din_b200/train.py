@@ -143,8 +143,11 @@ def forward_train(eng, images, boxes, bboxes_num=None, training=True, train_back
     return logits, tape
 
 
-def backward_head(eng, tape, dlogits):
-    """d(loss)/d(logits) [B, A] -> {reference parameter name: gradient} for every parameter after the backbone."""
+def backward_head(eng, tape, dlogits, sink=None):
+    """d(loss)/d(logits) [B, A] -> {reference parameter name: gradient} for every parameter after the backbone (and,
+    with tape['train_backbone'], the backbone's).  sink(stage, grads) is called as soon as a group of gradients is
+    final -- "head" before the backbone's backward starts, "backbone" at the end -- so that a data-parallel run can
+    exchange the head's gradients while the backbone's backward still runs (parallel.BucketedGradientReducer)."""
     cfg = eng.cfg
     B, T = tape["B"], tape["T"]
     N, C, NFB = eng.N, eng.C, eng.NFB
@@ -210,8 +213,12 @@ def backward_head(eng, tape, dlogits):
         grads["fc_emb_1.weight"] = dwk.view(NFB, KK, eng.D_stride)[:, :, :eng.D].permute(0, 2, 1).reshape(NFB, -1) \
             .contiguous()
         grads["fc_emb_1.bias"] = dbe
+        if sink is not None:
+            sink("head", grads)
         if tape["train_backbone"]:
             backward_backbone(eng, tape, dcrops, grads)
+            if sink is not None:
+                sink("backbone", grads)
     return grads
 
 
@@ -263,8 +270,9 @@ def basenet_forward_train(eng, images, boxes, training=True, train_backbone=True
     return (actions.view(B * N, -1), activities), tape
 
 
-def basenet_backward(eng, tape, dactions, dactivities):
-    """(d/d actions [B*N, A], d/d activities [B, A2]) -> {reference parameter name: gradient}."""
+def basenet_backward(eng, tape, dactions, dactivities, sink=None):
+    """(d/d actions [B*N, A], d/d activities [B, A2]) -> {reference parameter name: gradient}; `sink` as in
+    backward_head."""
     B, T = tape["B"], tape["T"]
     N, NFB = eng.N, eng.NFB
     M = B * T * N
@@ -290,6 +298,10 @@ def basenet_backward(eng, tape, dactions, dactivities):
         grads[name + ".weight"] = dwk.view(NFB, KK, eng.D_stride)[:, :, :eng.D].permute(0, 2, 1).reshape(NFB, -1) \
             .contiguous()
         grads[name + ".bias"] = dbe
+        if sink is not None:
+            sink("head", grads)
         if tape["train_backbone"]:
             backward_backbone(eng, tape, dcrops, grads)
+            if sink is not None:
+                sink("backbone", grads)
     return grads

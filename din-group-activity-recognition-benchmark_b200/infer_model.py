@@ -59,14 +59,21 @@ class _DinTrainFn(torch.autograd.Function):
         logits, tape = _train.forward_train(model.engine(), images, boxes, bboxes_num, training=model.training,
                                             train_backbone=any(n.startswith("backbone.") for n in names))
         ctx.eng, ctx.tape, ctx.names = model.engine(), tape, names
+        ctx.sink = getattr(_pc.owner_of(model), "grad_sink", None)
         model._last_tape = tape if getattr(model, "keep_tape", False) else None     # test / debugging hook
         ctx.shapes = [tuple(p.shape) for p in params]
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
-        grads = _train.backward_head(ctx.eng, ctx.tape, dlogits)
+        sink = ctx.sink if (ctx.sink is not None and ctx.sink.active()) else None
+        grads = _train.backward_head(ctx.eng, ctx.tape, dlogits, sink=sink)
         ctx.tape = None
+        if sink is not None:
+            # data-parallel run (din_b200.parallel.BucketedGradientReducer): the gradients were packed into the flat
+            # buffer and all-reduced as the backward produced them; .grad becomes a view of that buffer (no copies)
+            sink.finish()
+            return (None,) * (5 + len(ctx.names))
         out = [grads[n].reshape(shp) if (need and n in grads) else None
                for n, shp, need in zip(ctx.names, ctx.shapes, ctx.needs_input_grad[5:])]
         return (None, None, None, None, None) + tuple(out)

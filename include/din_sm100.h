@@ -470,6 +470,18 @@ DIN_API int din_bn_bwd(const void* g, const void* z, int z_is_f32, const float* 
                const float* gamma, float* sums, void* dz, float* dbeta, float* dgamma, const float* inv_scale,
                long long rows, int c, void* stream);
 
+/* ---- data-parallel training: gradients -> one flat fp32 buffer (csrc/flat.cu) -----------------------------------
+ * flat[dst_offset + i] = scale * src[i] for every job, ALL jobs in one launch (<= 96 per launch, more are split).
+ * The flat buffer is what the step's all-reduce runs on (ncclAllReduce through torch.distributed); `scale` carries
+ * the rank's weight local_clips / global_clips so that the SUM over ranks is the global-batch mean gradient.
+ * Replaces: the reduce_add_coalesced on GPU 0 inside nn.DataParallel's backward (train_net_dynamic.py:96,220-224). */
+typedef struct DinFlatJob {
+  const void* src;          /* fp32 gradient tensor (device, contiguous) */
+  int64_t dst_offset;       /* element offset into `flat` */
+  int64_t numel;
+} DinFlatJob;
+DIN_API int din_pack_flat_f32(const DinFlatJob* jobs, int n_jobs, float* flat, float scale, void* stream);
+
 #ifdef __cplusplus
 } /* extern "C" */
 #endif

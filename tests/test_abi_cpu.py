@@ -49,7 +49,7 @@ def test_ctypes_table_matches_header():
         assert len(args) == len(argtypes), (name, len(args), len(argtypes))
     assert C.sizeof(lib.DinConvDesc) == 16 * 4
     # struct layouts: field names and order as in the header
-    for struct in (lib.DinConvDesc, lib.DinPackJob):
+    for struct in (lib.DinConvDesc, lib.DinPackJob, lib.DinFlatJob):
         m = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct.__name__, struct.__name__), src, flags=re.S)
         assert m, struct.__name__
         fields = []
@@ -59,6 +59,7 @@ def test_ctypes_table_matches_header():
                 fields += [n.strip().lstrip("*") for n in re.sub(r"^(const\s+)?\w+\s*\*?", "", decl, count=1).split(",")]
         assert fields == [n for n, _ in struct._fields_], (struct.__name__, fields)
     assert C.sizeof(lib.DinPackJob) == 3 * 8 + 8 * 4
+    assert C.sizeof(lib.DinFlatJob) == 3 * 8
 
 
 def test_loads_and_validates_without_gpu():

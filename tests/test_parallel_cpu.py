@@ -110,3 +110,77 @@ def test_gradient_allreduce_world2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert [r[1] for r in res] == [True, True]
+
+
+def _bucket_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from din_b200.parallel import BucketedGradientReducer
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.backbone = torch.nn.Linear(5, 3)
+            self.fc_emb_1 = torch.nn.Linear(3, 7)           # 21 + 7 elements: slots are padded to multiples of 4
+            self.unused = torch.nn.Parameter(torch.zeros(6))
+            self.frozen = torch.nn.Parameter(torch.zeros(2), requires_grad=False)
+
+    torch.manual_seed(0)
+    net = Net()
+    reducer = BucketedGradientReducer(net)
+    assert net.grad_sink is reducer and reducer.active()
+    ok = True
+    for step in range(2):                                   # the flat buffer is re-used across steps
+        # rank r holds r + 1 of the 3 clips of the global batch; its "mean over local clips" gradient is (r + 1 + step)
+        local, total = rank + 1, 3
+        val = float(rank + 1 + step)
+        grads = {n: torch.full_like(p, val) for n, p in net.named_parameters() if n not in ("unused", "frozen")}
+        for p in net.parameters():
+            p.grad = None
+        reducer.set_batch(local, total)
+        reducer("head", grads)                              # issued while the "backbone backward" would still run
+        reducer("backbone", grads)
+        reducer.finish()
+        want = (1 / 3) * (1 + step) + (2 / 3) * (2 + step)  # sum_r (n_r / n) g_r = the global-batch mean gradient
+        for n, p in net.named_parameters():
+            if n == "frozen":
+                ok &= p.grad is None
+            elif n == "unused":
+                ok &= bool(torch.equal(p.grad, torch.zeros(6)))
+            else:
+                ok &= bool(torch.allclose(p.grad, torch.full_like(p, want), atol=1e-6))
+                ok &= p.grad.data_ptr() % 16 == 0 and p.grad.is_contiguous()
+        # .grad tensors are views of ONE flat buffer
+        base = reducer._flat.data_ptr()
+        ok &= all(base <= p.grad.data_ptr() < base + 4 * reducer.numel for p in net.parameters() if p.grad is not None)
+    q.put((rank, bool(ok), reducer.stats["steps"]))
+    dist.destroy_process_group()
+
+
+def test_bucketed_gradient_reducer_world2_gloo():
+    """Two buckets (head first, backbone last), each all-reduced asynchronously as soon as it is final; unequal shards
+    are weighted by local_clips / global_clips so that the result is the global-batch mean gradient."""
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                       "din-group-activity-recognition-benchmark_b200")
+    os.environ["PYTHONPATH"] = pkg + os.pathsep + os.environ.get("PYTHONPATH", "")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[1:] for r in res] == [(True, 2), (True, 2)]
+
+
+def test_gradient_allreduce_weights_unequal_shards():
+    from din_b200.parallel import _rank_weight
+    assert _rank_weight(1, 4) == 0.25 and _rank_weight(0, 4) == 0.0
+    with pytest.raises(ValueError):
+        _rank_weight(5, 4)
