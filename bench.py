@@ -50,7 +50,23 @@ WORKLOADS = {
     "volleyball_inv3_full_T10_N12_720p": (
         dict(backbone="inv3", image_size=(720, 1280), out_size=(87, 157), emb_features=1056, num_frames=10,
              num_boxes=12, lite_dim=None, ST_kernel_size=[(3, 3)], sampling_ratio=(1,)), 8, 1068.0),
+    # BASELINE.json configs[3]: ST-factorized DIN, ST_kernel_size [(1,3),(3,1)], hierarchical (C = 1024: hier_LN is
+    # hard-coded to [10,12,1024], dynamic_infer_module.py:475); patched oracle, SURVEY.md §8c bug H
+    "volleyball_vgg16_hier_st_T10_N12_720p": (
+        dict(backbone="vgg16", image_size=(720, 1280), out_size=(22, 40), emb_features=512, num_frames=10,
+             num_boxes=12, lite_dim=None, ST_kernel_size=[(1, 3), (3, 1)], sampling_ratio=(1,),
+             hierarchical_inference=True), 8, 5641.2),
+    # BASELINE.json configs[4]: Collective stage-2 DIN (scripts/train_collective_stage2_dynamic.py): ResNet-18 at
+    # 480x720, up to 13 actors per clip (a different count per clip), 4 activities; B = 16 global on 4 GPUs = 4 clips
+    # per GPU there (use --global-clips 16 for that strong-scaling shape); patched oracle, bug C
+    "collective_res18_T10_N13_480p": (
+        dict(dataset="collective", backbone="res18", image_size=(480, 720), out_size=(15, 23), emb_features=512,
+             num_frames=10, num_boxes=13, lite_dim=None, ST_kernel_size=(3, 3), sampling_ratio=(1,),
+             num_activities=4), 16, 254.8),
 }
+# BASELINE.json configs[2] ("ResNet-18 lite, B=32, 8 x B200") is volleyball_res18_lite128_T10_N12_720p with
+# --global-clips 32: 32 clips per step in total, 4 per GPU at N = 8 (strong scaling); without the flag every GPU keeps
+# 32 clips (weak scaling).
 DEFAULT_WORKLOAD = "volleyball_vgg16_lite128_T10_N12_720p"
 
 
@@ -135,14 +151,19 @@ def build_model(pc, device):
     return model.to(device).eval(), sd, bb
 
 
-def train_step_info(model, pc, dev, images_d, boxes_d, clips, steps=5, warmup=2):
+def train_step_info(model, pc, dev, images_d, boxes_d, clips, steps=5, warmup=2, dist=None):
     """Supplementary (NOT the headline metric): one stage-2 TRAINING step -- train-mode forward, on-device
     cross-entropy, backward through the head and the VGG-16 / ResNet-18 backbone -- on `clips` clips
     (scripts/train_volleyball_stage2_dynamic.py:42 batch_size = 2), followed by torch's SGD step with lr = 0: the update
     itself is torch's, but it bumps the weights' versions, so the timed step includes re-packing every weight into the
-    kernels' fp16 layouts, as a real training loop pays it."""
+    kernels' fp16 layouts, as a real training loop pays it.
+    With several ranks (dist given) every rank trains on its own `clips` clips (weak scaling) and the gradient
+    all-reduce over NCCL is INSIDE the timed step: din_b200.parallel.BucketedGradientReducer packs the gradients into
+    one flat buffer (one launch per bucket) and exchanges the head's bucket while the backbone's backward still runs;
+    the time reported is the max over ranks."""
     import torch
     from din_b200 import metrics, ops
+    reducer = None
     try:
         model.train()
         for m in model.modules():                           # the reference's set_bn_eval (train_net_dynamic.py:101-102)
@@ -154,6 +175,9 @@ def train_step_info(model, pc, dev, images_d, boxes_d, clips, steps=5, warmup=2)
         labels = (torch.arange(clips, device=dev) % pc.num_activities)
 
         opt = torch.optim.SGD(list(model.parameters()), lr=0.0)
+        if dist is not None:
+            from din_b200.parallel import BucketedGradientReducer
+            reducer = BucketedGradientReducer(model)          # installs model.grad_sink: exchange happens in backward()
 
         def step():
             opt.zero_grad(set_to_none=True)
@@ -165,6 +189,9 @@ def train_step_info(model, pc, dev, images_d, boxes_d, clips, steps=5, warmup=2)
         for _ in range(warmup):
             step()
         torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
         ops.RECORDER = []
         launches0 = ops.LAUNCHES
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -175,6 +202,12 @@ def train_step_info(model, pc, dev, images_d, boxes_d, clips, steps=5, warmup=2)
         torch.cuda.synchronize()
         rec, ops.RECORDER = ops.RECORDER, None
         ms = e0.elapsed_time(e1) / steps
+        world = 1
+        if dist is not None:
+            world = dist.get_world_size()
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
         by = {}
         flops = 0.0
         for (n, f, b, a, z) in rec:
@@ -182,15 +215,21 @@ def train_step_info(model, pc, dev, images_d, boxes_d, clips, steps=5, warmup=2)
             k = "conv_fwd/dgrad" if k.startswith("conv") else ("wgrad" if k.startswith("wgrad") else k)
             by[k] = by.get(k, 0.0) + a.elapsed_time(z) / steps
             flops += f / steps
-        info = {"clips": clips, "ms_per_step": ms, "clips_per_s": clips / (ms / 1e3), "loss": float(loss.detach()),
+        info = {"clips_per_gpu": clips, "world": world, "ms_per_step": ms, "clips_per_s": clips * world / (ms / 1e3),
+                "loss": float(loss.detach()),
+                "allreduce": (None if reducer is None else
+                              {"elements": reducer.numel, "bytes_per_step": reducer.stats["bytes"] // max(1, reducer.stats["steps"]),
+                               "buckets": ["head (overlaps the backbone's backward)", "backbone"]}),
                 "backbone_trained": True, "gpu_launches_per_step": (ops.LAUNCHES - launches0) // steps,
-                "algorithmic_tflops": flops / (ms / 1e3) / 1e12,
+                "algorithmic_tflops_per_gpu": flops / (ms / 1e3) / 1e12,
                 "kernels_ms": {k: round(v, 3) for k, v in sorted(by.items(), key=lambda kv: -kv[1])[:10]},
                 "note": "forward(train) + cross-entropy + backward + SGD(lr=0) step (weights re-packed every step)"}
     except Exception as e:                                   # never lose the headline line to the supplementary one
         info = {"error": f"{type(e).__name__}: {e}"[:300]}
     finally:
         ops.RECORDER = None
+        if reducer is not None:
+            model.grad_sink = None
         model.eval()
         for q in model.parameters():
             q.requires_grad = False
@@ -199,48 +238,83 @@ def train_step_info(model, pc, dev, images_d, boxes_d, clips, steps=5, warmup=2)
     return info
 
 
+def _slice_frames(pc, sd, t_s):
+    """The same workload cut to its first t_s frames (LayerNorm parameters shaped [T, ...] are cut with it)."""
+    import dataclasses
+    pcs = dataclasses.replace(pc, num_frames=t_s)
+    if t_s == pc.num_frames:
+        return pcs, sd
+    sds = dict(sd)
+    for k in ("dpi_nl.weight", "dpi_nl.bias", "point_ln.weight", "point_ln.bias", "DPI.hier_LN.weight",
+              "DPI.hier_LN.bias"):
+        if k in sds and sds[k].shape[0] == pc.num_frames:
+            sds[k] = sds[k][:t_s].contiguous()
+    return pcs, sds
+
+
 def cpu_reference_clips_per_s(pc, sd, bb, budget_s, steps=1, warmup=0):
-    """Times the CPU port of the reference path (oracle/din_oracle.py) with all host threads.
-    A step is one clip (B=1); if (steps+warmup) clips would exceed `budget_s`, the clip is cut to the first
-    `t_s` frames and the result is scaled by t_s/T (the backbone is >= 97 % of the CPU time and linear in
-    frames).  Returns (clips/s, cores, sample description, seconds per step)."""
+    """Times the reference path on the host cores (all threads), one clip per step.
+
+    kind "reference": the reference's OWN classes (infer_model.Dynamic_volleyball / Dynamic_collective, imported
+    unmodified from /root/reference or from the copy oracle/make_ref.py staged under oracle/_ref/, with the documented
+    patches I / H / C applied in memory, oracle/ref_harness.py) whenever those sources are present;
+    kind "port": the oracle restatement (oracle/din_oracle.py) otherwise.  Where both exist the port is run once on the
+    same clip and the agreement of the two logits is reported.
+    If (steps + warmup) clips would exceed `budget_s`, the clip is cut to its first t_s frames and the result is scaled
+    by t_s / T (the backbone is >= 97 % of the CPU time and linear in frames; the hierarchical model's hard-coded
+    [10,12,1024] LayerNorm keeps T = 10).  -> (clips/s, threads, kind, sample description, seconds per step)."""
     import torch
     import din_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     O.load_backbone(bb, sd)
     T = pc.num_frames
-    images, boxes = O.make_inputs(pc, 1, seed=0)
-    # probe: one frame through the backbone
+    batch = O.make_inputs(pc, 1, seed=0)
+    images = batch[0]
     t0 = time.perf_counter()
     with torch.no_grad():
-        bb(O.prep_images(images[0, :1]))
+        bb(O.prep_images(images[0, :1]))                      # probe: one frame through the backbone
     t_frame = time.perf_counter() - t0
     t_s = T
-    if (steps + warmup) * T * t_frame > budget_s:
-        t_s = max(1, int(budget_s / ((steps + warmup) * t_frame)))
-        t_s = min(t_s, T)
-    import dataclasses
-    pcs = dataclasses.replace(pc, num_frames=t_s)
-    if t_s != T:
-        sds = dict(sd)
-        for k in ("dpi_nl.weight", "dpi_nl.bias", "point_ln.weight", "point_ln.bias"):
-            if k in sds:
-                sds[k] = sds[k][:t_s].contiguous()
-    else:
-        sds = sd
-    im, bx = images[:, :t_s].contiguous(), boxes[:, :t_s].contiguous()
+    if (steps + warmup) * T * t_frame > budget_s and not pc.hierarchical_inference:
+        t_s = min(T, max(1, int(budget_s / ((steps + warmup) * t_frame))))
+    pcs, sds = _slice_frames(pc, sd, t_s)
+    cut = tuple(t[:, :t_s].contiguous() for t in batch)
+
+    port = O.collective_forward if pc.dataset == "collective" else O.volleyball_forward
+    kind, agree = "port", None
+    run = lambda: port(bb, sds, pcs, *cut)                    # noqa: E731
+    try:
+        import ref_harness as R
+        if R.available():
+            import contextlib
+            import io
+            import warnings
+            model = R.build_ref_model(pcs, sds)
+
+            def run():
+                with torch.no_grad(), warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+                    warnings.simplefilter("ignore")
+                    return model(cut)["activities"]
+            kind = "reference"
+    except Exception as e:                                    # never lose the line to the optional arm
+        print(f"[bench] reference classes unavailable ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
     for _ in range(warmup):
-        O.volleyball_forward(bb, sds, pcs, im, bx)
+        run()
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.volleyball_forward(bb, sds, pcs, im, bx)
+        out = run()
     dt = (time.perf_counter() - t0) / steps
+    if kind == "reference":
+        agree = float((out - port(bb, sds, pcs, *cut)).abs().max())
     clips_per_s = (t_s / T) / dt
     sample = (f"{steps} step(s) x 1 clip x {t_s}/{T} frames at {pc.image_size[0]}x{pc.image_size[1]}, N={pc.num_boxes}; "
-              f"oracle port (torch-CPU fp32, oneDNN), {torch.get_num_threads()} threads"
-              + ("" if t_s == T else "; clips/s scaled by frames/T"))
-    return clips_per_s, torch.get_num_threads(), sample, dt
+              + ("the reference's own infer_model classes (patched in memory: SURVEY.md §8c), "
+                 if kind == "reference" else "oracle port, ")
+              + f"torch-CPU fp32 (oneDNN), {torch.get_num_threads()} threads"
+              + ("" if t_s == T else "; clips/s scaled by frames/T")
+              + ("" if agree is None else f"; max|reference - oracle port| on this clip = {agree:.2e}"))
+    return clips_per_s, torch.get_num_threads(), kind, sample, dt
 
 
 def _claim_stdout():
@@ -266,6 +340,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--clips-per-gpu", type=int, default=None)
+    ap.add_argument("--global-clips", type=int, default=None,
+                    help="fixed TOTAL clips per step, split over the GPUs (strong scaling), e.g. 32 for BASELINE configs[2]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-train-step", action="store_true")
@@ -278,10 +354,15 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    import dataclasses
     import torch
     import din_oracle as O
     kw, clips_per_gpu, gflop_per_clip = WORKLOADS[args.workload]
-    if args.clips_per_gpu:
+    scaling = "weak"
+    if args.global_clips:
+        assert args.global_clips % world == 0, "--global-clips must divide by the number of GPUs"
+        clips_per_gpu, scaling = args.global_clips // world, "strong"
+    elif args.clips_per_gpu:
         clips_per_gpu = args.clips_per_gpu
     pc = O.PathConfig(**kw)
     config = {"workload": args.workload, "backbone": pc.backbone, "clips_per_gpu": clips_per_gpu,
@@ -296,14 +377,14 @@ def main():
             return
         bb = O.build_backbone(pc.backbone)
         sd = O.make_state_dict(pc, seed=0, backbone=bb)
-        v, cores, sample, dt = cpu_reference_clips_per_s(pc, sd, bb, budget_s=200.0, steps=max(1, args.steps),
-                                                         warmup=args.warmup)
+        v, cores, kind, sample, dt = cpu_reference_clips_per_s(pc, sd, bb, budget_s=200.0, steps=max(1, args.steps),
+                                                               warmup=args.warmup)
         _emit(real_stdout, {
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(config, clips_per_gpu=1, global_clips_per_step=1, parallelism="cpu"),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0})
         return
@@ -321,10 +402,12 @@ def main():
     model, sd, bb = build_model(pc, dev)
     B, T, N = clips_per_gpu, pc.num_frames, pc.num_boxes
     H, W = pc.image_size
-    images_h, boxes_h = O.make_inputs(pc, 1, seed=rank)          # boxes pattern from the oracle generator
+    # boxes (and Collective's per-clip actor counts: a different count per clip) from the oracle's generator
+    host = O.make_inputs(dataclasses.replace(pc, image_size=(8, 8)), B, seed=rank)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     images_d = torch.randint(0, 256, (B, T, 3, H, W), generator=g, device=dev, dtype=torch.int32).float()
-    boxes_d = boxes_h.repeat(B, 1, 1, 1).to(dev)
+    boxes_d = host[1].to(dev)
+    extra_d = tuple(t.to(dev) for t in host[2:])                 # (bboxes_num [B,T] int32,) for Collective
 
     def barrier():
         if dist is not None:
@@ -333,7 +416,7 @@ def main():
 
     def step():
         with torch.no_grad():
-            return model((images_d, boxes_d))["activities"]
+            return model((images_d, boxes_d) + extra_d)["activities"]
 
     for _ in range(args.warmup):
         step()
@@ -366,7 +449,7 @@ def main():
         img_host = torch.empty(img_src.shape, dtype=img_src.dtype).pin_memory()
         img_host.copy_(img_src)
         box_host = boxes_d.cpu().pin_memory()
-        bufs = [(torch.empty_like(img_src), torch.empty_like(boxes_d)) for _ in range(2)]
+        bufs = [(torch.empty_like(img_src), torch.empty_like(boxes_d)) + extra_d for _ in range(2)]
         out_host = torch.empty((B, pc.num_activities), dtype=torch.float32).pin_memory()
         copy_stream = torch.cuda.Stream(device=dev)
         main_stream = torch.cuda.current_stream()
@@ -424,6 +507,11 @@ def main():
             k = n.split("_")[0].split("@")[0]
             other[k] = other.get(k, 0.0) + a.elapsed_time(z) / args.steps
 
+    # supplementary: the training step (all ranks take part: its gradient all-reduce is inside the timed step)
+    train_info = None
+    if not args.no_train_step and pc.backbone in ("vgg16", "res18") and pc.dataset == "volleyball":
+        train_info = train_step_info(model, pc, dev, images_d, boxes_d, min(args.train_clips, B), dist=dist)
+
     if dist is not None:
         t = torch.tensor([ms, e2e["ms"] if e2e else 0.0, e2e_u8["ms"] if e2e_u8 else 0.0], device=dev,
                          dtype=torch.float64)
@@ -449,7 +537,7 @@ def main():
         traffic = json.load(open(tpath)).get(args.workload)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (backbone), f32 (head)",
         "data": "synthetic", "config": config,
         "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, all launches of a step)",
@@ -475,11 +563,11 @@ def main():
                           "h2d_bytes_per_step": e2e_u8["h2d"], "d2h_bytes_per_step": e2e_u8["d2h"],
                           "input": "uint8 [B,T,H,W,3] frames (decoded images before the loader's transpose/float), "
                                    "bit-identical logits"}
-    if world == 1 and not args.no_train_step and pc.backbone in ("vgg16", "res18") and pc.dataset == "volleyball":
-        line["train_step"] = train_step_info(model, pc, dev, images_d, boxes_d, args.train_clips)
+    if train_info is not None:
+        line["train_step"] = train_info
     if world == 1 and not args.no_cpu_baseline:
-        v, cores, sample, _ = cpu_reference_clips_per_s(pc, sd, bb, budget_s=args.cpu_budget_s)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        v, cores, kind, sample, _ = cpu_reference_clips_per_s(pc, sd, bb, budget_s=args.cpu_budget_s)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
     _emit(real_stdout, line)
     if dist is not None:
         dist.destroy_process_group()
