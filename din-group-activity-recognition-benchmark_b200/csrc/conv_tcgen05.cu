@@ -680,6 +680,358 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   }
 }
 
+// ================================================================================================
+// conv1_1 + conv1_2 in ONE kernel (inference): VGG-16's first two layers, backbone.py:88-99 features.0-4.
+//
+// The stand-alone stem (stem_tc.cu) writes its 64-channel 720p output to HBM -- 118 MB per frame, 10.7x what it reads
+// -- and conv1_2 reads it straight back: 4.2 ms + the halo reads of a 38.7 ms step, for a layer of 0.6 % of the FLOPs.
+// Here the CTA-pair conv1_2 kernel (conv_igemm_2cta_kernel<64, 9>: resident weights, one cta_group::2 MMA of M = 256
+// per K step) produces its own A operand: instead of a TMA box of conv1_1's output, four extra warps per CTA compute
+// the tile's 18 x 10 halo of conv1_1 from the 3-channel image --
+//   patch   TMA box {12, 20, 3} of the raw fp32 NCHW image (or {48 B, 20} of the uint8 NHWC frame) -> shared memory,
+//           three tiles ahead;
+//   im2col  thread r builds halo pixel r's K = 27 (+ 2 bias columns, padded to 32) fp16 row in the canonical
+//           no-swizzle UMMA layout (prep_images fused, zero where conv1_1 pads): 180 rows, two per thread;
+//   MMA     the leader's MMA warp issues 2 row blocks x 2 K steps of tcgen05.mma.cta_group::2 (M = 256 = 128 halo
+//           rows of each CTA, N = 64, the stem weights split 32 + 32 rows over the pair) into a double-buffered stem
+//           accumulator in TMEM (columns 128..383), one tile ahead of the main loop;
+//   drain   the same four warps read the accumulator back (tcgen05.ld), ReLU, round to fp16 -- the exact values the
+//           stand-alone stem stores -- zero the halo pixels outside the image (conv1_2's padding) and write the
+//           128-byte-swizzled K-major A stage the main MMAs consume through their shifted-window descriptors.
+// The stem's output never exists in HBM; the image is read once (11 MB fp32 per frame).  Everything after the A
+// stage -- resident weights, 36 MMAs per tile pair, TMEM double buffering, epilogue with the fused 2x2 max-pool --
+// is conv_igemm_2cta_kernel's.  Training keeps the two-kernel path (the backward needs conv1_1's activations).
+// ================================================================================================
+constexpr int kFusedThreads = 512;          // 4 role warps + 8 epilogue warps + 4 stem warps
+constexpr int kFusedStemWarp0 = 12;
+constexpr int kHaloH = 18, kHaloW = 10, kHaloRows = kHaloH * kHaloW;      // conv1_2's 16 x 8 tile + 1 pixel border
+constexpr int kPatchH = 20, kPatchW = 12;                                 // conv1_1's input for that halo
+constexpr int kStemKPad = 32, kStemSbo = kStemKPad * 16;                  // K = 27 + 2 bias columns -> 32
+constexpr int kColBufBytes = 2 * 16 * kStemSbo;                           // two 128-row blocks per CTA
+constexpr int kPatchStageBytes = 3072;                                    // >= 3*20*12*4 (fp32) / 20*48 (uint8)
+constexpr int kPatchStages = 3;
+constexpr int kFusedAStages = 4;
+
+struct FusedStemParams {
+  const float* w1;       // [64][3][3][3] fp32 (OIHW)
+  const float* b1;       // [64]
+  int img_h, img_w, n_img;
+  int prep;              // apply prep_images to the raw pixel values
+};
+
+template <bool U8>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
+conv1_fused_2cta_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_constant__ CUtensorMap tmap_b,
+                        const ConvKParams p, const FusedStemParams sp) {
+  constexpr int BN = 64, TB3 = 9;
+  constexpr int kBHalfBytes = (BN / 2) * kBK * 2;
+  constexpr int kTmemCols = 512;                 // [0,128) conv1_2 accumulators, [128,384) stem accumulators
+  constexpr int b_stage_bytes = TB3 * kBHalfBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem(smem_raw, 1024);
+  uint8_t* smem_a = smem;                                                   // kFusedAStages x a_stage_bytes (SW128)
+  uint8_t* smem_b = smem_a + kFusedAStages * p.a_stage_bytes;               // resident conv1_2 weights (this CTA's half)
+  uint8_t* col_s = smem_b + b_stage_bytes;                                  // 2 x im2col buffers (canonical layout)
+  uint8_t* w1_s = col_s + 2 * kColBufBytes;                                 // stem weights, this CTA's 32 rows
+  uint8_t* patch_s = w1_s + 4 * kStemSbo;                                   // kPatchStages x raw input patches
+  uint8_t* epi_scratch = patch_s + kPatchStages * kPatchStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_scratch + kNumEpiWarps * kEpiScratch);
+  uint64_t* a_full = bars;                       // [4]  leader: 8 warp arrivals (4 stem warps x 2 CTAs)
+  uint64_t* a_empty = a_full + kFusedAStages;    // [4]  both: multicast commit
+  uint64_t* b_full = a_empty + kFusedAStages;    // [1]
+  uint64_t* tmem_full = b_full + 1;              // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint64_t* patch_full = tmem_empty + 2;         // [3]  local: TMA bytes
+  uint64_t* patch_empty = patch_full + kPatchStages;   // [3]  local: 4 stem warps
+  uint64_t* col_full = patch_empty + kPatchStages;     // [2]  leader: 8 warp arrivals
+  uint64_t* stem_done = col_full + 2;            // [2]  both: multicast commit of the stem MMAs
+  uint64_t* stem_free = stem_done + 2;           // [2]  leader: 8 warp arrivals (stem accumulator drained)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(stem_free + 2);
+  float* bias_s = reinterpret_cast<float*>(tmem_ptr_smem + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int pair_first = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
+  const int n_pairs = (p.num_tiles + 1) >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_img);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < kFusedAStages; ++s) { mbar_init(&a_full[s], 8); mbar_init(&a_empty[s], 1); }
+    mbar_init(&b_full[0], 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 2 * 32 * kNumEpiWarps);
+      mbar_init(&col_full[a], 8); mbar_init(&stem_done[a], 1); mbar_init(&stem_free[a], 8);
+    }
+    for (int s = 0; s < kPatchStages; ++s) { mbar_init(&patch_full[s], 1); mbar_init(&patch_empty[s], 4); }
+    fence_mbar_init();
+  }
+  if (warp >= 4 && warp < kFusedStemWarp0) {
+    for (int c = threadIdx.x - 128; c < BN; c += 32 * kNumEpiWarps)
+      bias_s[c] = (p.bias != nullptr && c < p.c_out) ? __ldg(p.bias + c) : 0.0f;
+  }
+  if (warp >= kFusedStemWarp0) {
+    const int st = threadIdx.x - 32 * kFusedStemWarp0;        // 0..127
+    // the im2col buffers start out zeroed: rows 180..255 of every buffer are never written and must stay finite
+    for (int i = st; i < 2 * kColBufBytes / 16; i += 128) reinterpret_cast<uint4*>(col_s)[i] = make_uint4(0, 0, 0, 0);
+    // stem weights, this CTA's 32 output channels x 4 K chunks = one 16-byte chunk per thread; bias in K columns 27
+    // (hi) and 28 (lo), multiplied by A = 1: added exactly, in the fp32 accumulator (as stem_tc.cu)
+    {
+      const int o_local = st >> 2, kc = st & 3, o = rank * (BN / 2) + o_local;
+      __align__(16) __half hv[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k = kc * 8 + e;
+        float wv = 0.0f;
+        if (k < 27) {
+          wv = __ldg(sp.w1 + o * 27 + k);
+        } else if (sp.b1 != nullptr && k <= 28) {
+          const float bv = __ldg(sp.b1 + o);
+          const float bh = __half2float(__float2half_rn(bv));
+          wv = (k == 27) ? bh : bv - bh;
+        }
+        hv[e] = __float2half_rn(wv);
+      }
+      *reinterpret_cast<uint4*>(w1_s + canon_off(o_local, kc, kStemSbo)) = *reinterpret_cast<const uint4*>(hv);
+    }
+    fence_proxy_async_smem();
+  }
+  if (warp == 1) tmem_alloc_2cta<kTmemCols>(tmem_ptr_smem);
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ patch producer: this CTA's tile of each pair
+    if (lane == 0) {
+      int j = 0;
+      for (int pi = pair_first; pi < n_pairs; pi += pair_step, ++j) {
+        const int mt = 2 * pi + rank;                        // beyond the last tile: img >= n_img, zero-filled
+        const int img = fdiv(mt, p.fd_tpi);
+        const int r = mt - img * p.tiles_per_img;
+        const int tyi = fdiv(r, p.fd_tx);
+        const int txi = r - tyi * p.tiles_x;
+        const int ps = j % kPatchStages;
+        mbar_wait(&patch_empty[ps], (((j / kPatchStages) & 1) ^ 1));
+        if constexpr (U8) {
+          mbar_arrive_expect_tx(&patch_full[ps], kPatchH * 48u);
+          tma_load_3d(patch_s + ps * kPatchStageBytes, &tmap_img, &patch_full[ps], (txi * p.tw - 2) * 3,
+                      tyi * p.th - 2, img);
+        } else {
+          mbar_arrive_expect_tx(&patch_full[ps], 3u * kPatchH * kPatchW * 4u);
+          tma_load_3d(patch_s + ps * kPatchStageBytes, &tmap_img, &patch_full[ps], txi * p.tw - 2, tyi * p.th - 2,
+                      img * 3);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ conv1_2 weights: resident, loaded once
+    if (lane == 0 && pair_first < n_pairs) {
+      if (rank == 0) mbar_arrive_expect_tx(&b_full[0], 2u * TB3 * kBHalfBytes);
+#pragma unroll
+      for (int tt = 0; tt < TB3; ++tt)
+        tma_load_2d_2cta(smem_b + tt * kBHalfBytes, &tmap_b, &b_full[0], tt * p.c_in, rank * (BN / 2));
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer: the leader CTA only
+    if (rank == 0) {
+      const bool leader = elect_one();
+      constexpr uint32_t idesc = umma_idesc_f16_f32(256, BN);
+      const uint32_t a_hi = desc_hi(static_cast<uint32_t>(p.pitch_rows) * 128u);
+      const uint32_t b_hi = desc_hi(1024u);
+      const uint32_t a_lo0 = desc_lo(smem_u32(smem_a));
+      const uint32_t b_lo = desc_lo(smem_u32(smem_b));
+      const uint32_t a_step = static_cast<uint32_t>(p.a_stage_bytes) >> 4;
+      const uint32_t col_addr = smem_u32(col_s), w1_addr = smem_u32(w1_s);
+      // stem MMAs of local iteration j: im2col buffer / stem accumulator j & 1
+      auto issue_stem = [&](int j) {
+        const int cb = j & 1;
+        const uint32_t use = static_cast<uint32_t>(j >> 1);           // k-th use of this buffer
+        mbar_wait(&col_full[cb], use & 1u);
+        if (use > 0) mbar_wait(&stem_free[cb], (use - 1u) & 1u);      // the previous result has been drained
+        tc_fence_after_sync();
+        if (leader) {
+#pragma unroll
+          for (int rb = 0; rb < 2; ++rb) {
+            const uint32_t d_stem = tmem_base + 128u + static_cast<uint32_t>(cb * 128 + rb * 64);
+#pragma unroll
+            for (int ks = 0; ks < kStemKPad / 16; ++ks) {
+              const uint64_t ad = desc_noswz(col_addr + cb * kColBufBytes + rb * (16 * kStemSbo) + ks * 256, 128, kStemSbo);
+              const uint64_t bd = desc_noswz(w1_addr + ks * 256, 128, kStemSbo);
+              umma_f16_ss_2cta(d_stem, ad, bd, idesc, ks > 0 ? 1u : 0u);
+            }
+          }
+          umma_commit_2cta(&stem_done[cb]);
+        }
+      };
+      int sa = 0;
+      uint32_t pa = 0;
+      int it = 0;
+      if (pair_first < n_pairs) issue_stem(0);
+      for (int pi = pair_first; pi < n_pairs; pi += pair_step, ++it) {
+        if (pi + pair_step < n_pairs) issue_stem(it + 1);             // one tile ahead: its drain overlaps these MMAs
+        const int acc = it & 1;
+        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1u) ^ 1u);
+        mbar_wait(&a_full[sa], pa);
+        if (it == 0) mbar_wait(&b_full[0], 0);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        const uint32_t a_lo = a_lo0 + sa * a_step;
+        if (leader) {
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const uint32_t al = a_lo + static_cast<uint32_t>(((t / 3) * 10 + (t % 3)) * 8);
+            const uint32_t bl = b_lo + static_cast<uint32_t>(t * (kBHalfBytes >> 4));
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_f16_ss_2cta(d_tmem, desc64(al + 2u * k, a_hi), desc64(bl + 2u * k, b_hi), idesc,
+                               (t == 0 && k == 0) ? 0u : 1u);
+          }
+          umma_commit_2cta(&a_empty[sa]);
+          umma_commit_2cta(&tmem_full[acc]);
+        }
+        if (++sa == kFusedAStages) { sa = 0; pa ^= 1u; }
+      }
+    }
+  } else if (warp >= kFusedStemWarp0) {
+    // ------------------------------------------------------------------ stem warps: im2col build + accumulator drain
+    const int st = threadIdx.x - 32 * kFusedStemWarp0;        // 0..127
+    const int q = warp & 3;                                   // TMEM lane quadrant of this warp
+
+    auto tile_of = [&](int pi, int& img, int& tyi, int& txi) {
+      const int mt = 2 * pi + rank;
+      img = fdiv(mt, p.fd_tpi);
+      const int r = mt - img * p.tiles_per_img;
+      tyi = fdiv(r, p.fd_tx);
+      txi = r - tyi * p.tiles_x;
+    };
+
+    // im2col rows of halo pixels st and st + 128 for local iteration j (tile pair pi)
+    auto build = [&](int j, int pi) {
+      int img, tyi, txi;
+      tile_of(pi, img, tyi, txi);
+      const int ps = j % kPatchStages, cb = j & 1;
+      const uint32_t use = static_cast<uint32_t>(j >> 1);
+      if (use > 0) mbar_wait(&stem_done[cb], (use - 1u) & 1u);       // the MMAs that read this buffer have retired
+      mbar_wait(&patch_full[ps], (j / kPatchStages) & 1);
+      const uint8_t* patch = patch_s + ps * kPatchStageBytes;
+      const int gy0 = tyi * p.th - 2, gx0 = txi * p.tw - 2;           // image coordinates of patch element (0, 0)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int r = st + half * 128;
+        if (r < kHaloRows) {
+          const int hy = r / kHaloW, hx = r - hy * kHaloW;
+          bool rok[3], cok[3];
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            rok[d] = (gy0 + hy + d >= 0) && (gy0 + hy + d < sp.img_h);
+            cok[d] = (gx0 + hx + d >= 0) && (gx0 + hx + d < sp.img_w);
+          }
+          float f[kStemKPad];
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+                float raw;
+                if constexpr (U8) raw = static_cast<float>(patch[(hy + dy) * 48 + (hx + dx) * 3 + c]);
+                else raw = reinterpret_cast<const float*>(patch)[(c * kPatchH + hy + dy) * kPatchW + hx + dx];
+                f[(c * 3 + dy) * 3 + dx] = (rok[dy] && cok[dx]) ? prep_value(raw, sp.prep != 0) : 0.0f;
+              }
+          f[27] = 1.0f; f[28] = 1.0f; f[29] = 0.0f; f[30] = 0.0f; f[31] = 0.0f;      // the two bias columns
+          uint8_t* dst = col_s + cb * kColBufBytes + half * (16 * kStemSbo);
+#pragma unroll
+          for (int kc = 0; kc < kStemKPad / 8; ++kc) {
+            uint4 o;
+            o.x = pack_half2(f[kc * 8 + 0], f[kc * 8 + 1], false);
+            o.y = pack_half2(f[kc * 8 + 2], f[kc * 8 + 3], false);
+            o.z = pack_half2(f[kc * 8 + 4], f[kc * 8 + 5], false);
+            o.w = pack_half2(f[kc * 8 + 6], f[kc * 8 + 7], false);
+            *reinterpret_cast<uint4*>(dst + canon_off(st, kc, kStemSbo)) = o;
+          }
+        }
+      }
+      fence_proxy_async_smem();                               // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&patch_empty[ps]);
+        mbar_arrive_cluster(&col_full[cb], 0);
+      }
+    };
+
+    // stem accumulator -> ReLU -> fp16 -> this tile's A stage (SW128 K-major rows = halo pixels)
+    auto drain = [&](int j, int pi) {
+      int img, tyi, txi;
+      tile_of(pi, img, tyi, txi);
+      const int cb = j & 1, as = j % kFusedAStages;
+      mbar_wait(&stem_done[cb], static_cast<uint32_t>(j >> 1) & 1u);
+      mbar_wait(&a_empty[as], ((j / kFusedAStages) & 1) ^ 1);
+      tc_fence_after_sync();
+      uint8_t* a_stage = smem_a + as * p.a_stage_bytes;
+      const int oy0 = tyi * p.th - 1, ox0 = txi * p.tw - 1;           // conv1_1 output coordinates of halo pixel (0, 0)
+#pragma unroll
+      for (int rb = 0; rb < 2; ++rb) {
+        if (rb == 1 && q >= 2) break;                                 // rows 192.. do not exist (warp-uniform)
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 128u +
+                               static_cast<uint32_t>(cb * 128 + rb * 64);
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32b_x32(taddr, v0);
+        tmem_ld_32x32b_x32(taddr + 32, v1);
+        tmem_ld_wait();
+        const int r = rb * 128 + q * 32 + lane;
+        if (r < kHaloRows) {
+          const int hy = r / kHaloW, hx = r - hy * kHaloW;
+          const int oy = oy0 + hy, ox = ox0 + hx;
+          const bool inside = (img < sp.n_img) && oy >= 0 && oy < sp.img_h && ox >= 0 && ox < sp.img_w;
+          uint8_t* row = a_stage + r * 128;
+          const int sw = r & 7;
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) {
+            const uint32_t* v = c8 < 4 ? v0 + c8 * 8 : v1 + (c8 - 4) * 8;
+            uint4 o = make_uint4(0, 0, 0, 0);
+            if (inside) {
+              o.x = pack_half2(__uint_as_float(v[0]), __uint_as_float(v[1]), true);
+              o.y = pack_half2(__uint_as_float(v[2]), __uint_as_float(v[3]), true);
+              o.z = pack_half2(__uint_as_float(v[4]), __uint_as_float(v[5]), true);
+              o.w = pack_half2(__uint_as_float(v[6]), __uint_as_float(v[7]), true);
+            }
+            *reinterpret_cast<uint4*>(row + ((c8 ^ sw) << 4)) = o;
+          }
+        }
+      }
+      tc_fence_before_sync();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_cluster(&a_full[as], 0);
+        mbar_arrive_cluster(&stem_free[cb], 0);
+      }
+    };
+
+    int j = 0;
+    if (pair_first < n_pairs) build(0, pair_first);
+    for (int pi = pair_first; pi < n_pairs; pi += pair_step, ++j) {
+      if (pi + pair_step < n_pairs) build(j + 1, pi + pair_step);
+      drain(j, pi);
+    }
+  } else if (warp >= 4) {
+    conv_epilogue_warps<BN, true>(p, tmem_base, epi_scratch, bias_s, tmem_full, tmem_empty, warp, lane, pair_first,
+                                  n_pairs, pair_step, rank);
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc_2cta<kTmemCols>(tmem_base);
+  }
+}
+
 template <int BN, int TB3>
 int launch_conv_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const ConvKParams& p, int grid, size_t smem,
                      cudaStream_t st) {
@@ -905,6 +1257,93 @@ int conv2d_launch(const DinConvDesc* d, const void* x, const void* w_packed, con
 extern "C" int din_conv2d_nhwc_f16(const DinConvDesc* d, const void* x, const void* w_packed, const float* bias,
                                    const void* residual, void* y, void* stream) {
   return conv2d_launch(d, x, w_packed, bias, residual, 0, y, stream);
+}
+
+// conv1_1 (3 -> 64, 3x3, pad 1, ReLU, prep_images fused) + conv1_2 (64 -> 64, 3x3, pad 1, bias, ReLU, optional 2x2
+// max-pool) in one launch: conv1_fused_2cta_kernel.
+extern "C" int din_conv3x3_stem_pair_nhwc_f16(const void* x, int x_is_u8, const float* w1, const float* b1,
+                                              const void* w2_packed, const float* b2, void* y, int n, int h, int w,
+                                              int y_c_stride, int relu2, int pool2, int prep, void* stream) {
+  const char* who = "din_conv3x3_stem_pair_nhwc_f16";
+  DIN_CHECK_ARG(x && w1 && w2_packed && y, "%s: null pointer", who);
+  DIN_CHECK_ARG(n > 0 && h >= 2 && w >= 2, "%s: bad extent n=%d h=%d w=%d", who, n, h, w);
+  DIN_CHECK_ARG(y_c_stride >= 64 && y_c_stride % 8 == 0, "%s: y_c_stride=%d", who, y_c_stride);
+  DIN_CHECK_ARG(x_is_u8 ? (w % 16 == 0) : (w % 4 == 0),
+                "%s: image rows must be 16-byte multiples for the TMA patch loads (w=%d, %s): use the two-kernel path", who, w,
+                x_is_u8 ? "uint8 NHWC needs w %% 16 == 0" : "fp32 NCHW needs w %% 4 == 0");
+  DIN_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w2_packed) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(b2) & 15) == 0,
+                "%s: pointers must be 16-byte aligned", who);
+  constexpr int BN = 64;
+  ConvKParams p{};
+  p.oh = h; p.ow = w;
+  p.c_out = 64; p.y_c_stride = y_c_stride;
+  p.tw = 8; p.th = 16; p.tw_log2 = 3;
+  p.tiles_x = (w + p.tw - 1) / p.tw;
+  p.tiles_per_img = p.tiles_x * ((h + p.th - 1) / p.th);
+  p.n_tiles_n = 1;
+  const long long total_tiles = static_cast<long long>(n) * p.tiles_per_img;
+  DIN_CHECK_ARG(total_tiles < INT32_MAX / 2, "%s: too many tiles", who);
+  p.num_tiles = static_cast<int>(total_tiles);
+  p.kh = 3; p.kw = 3; p.stride = 1; p.pad_h = 1; p.pad_w = 1;
+  p.n_cblk = 1; p.c_in = kBK;
+  p.relu = relu2; p.out_f32 = 0; p.pool2 = pool2;
+  p.split = 1; p.k_part = 9 * kBK;
+  p.fd_ntn = make_fastdiv(1); p.fd_tpi = make_fastdiv(p.tiles_per_img); p.fd_tx = make_fastdiv(p.tiles_x);
+  p.bias = b2; p.residual = nullptr; p.res_mask = 0; p.y = y;
+  p.halo = 1; p.halo_rows = kHaloH; p.pitch_rows = kHaloW; p.per_row_loads = 0; p.use_base_offset = 0;
+  p.a_stage_bytes = ((kHaloRows * 128) + 1023) & ~1023;
+  p.a_tx_bytes = 0;
+  p.tb = 9; p.n_a_stages = kFusedAStages; p.n_b_stages = 1; p.b_resident = 1;
+  DIN_CHECK_ARG(!pool2 || (h >= 2 && w >= 2), "%s: pool2 needs an output of at least 2x2", who);
+
+  CUtensorMap timg, tb;
+  if (x_is_u8) {
+    const uint64_t dims[3] = {static_cast<uint64_t>(w) * 3, static_cast<uint64_t>(h), static_cast<uint64_t>(n)};
+    const uint64_t strides[3] = {1, static_cast<uint64_t>(w) * 3, static_cast<uint64_t>(w) * 3 * h};
+    const uint32_t box[3] = {48, kPatchH, 1};
+    const uint32_t es[3] = {1, 1, 1};
+    int rc = din_encode_tmap(&timg, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(x), dims, strides, box, es,
+                             CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc != DIN_OK) return rc;
+  } else {
+    const uint64_t dims[3] = {static_cast<uint64_t>(w), static_cast<uint64_t>(h), static_cast<uint64_t>(n) * 3};
+    const uint64_t strides[3] = {4, static_cast<uint64_t>(w) * 4, static_cast<uint64_t>(w) * 4 * h};
+    const uint32_t box[3] = {kPatchW, kPatchH, 3};
+    const uint32_t es[3] = {1, 1, 1};
+    int rc = din_encode_tmap(&timg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(x), dims, strides, box, es,
+                             CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc != DIN_OK) return rc;
+  }
+  {
+    const uint64_t ktot = 9ull * kBK;
+    const uint64_t dims[2] = {ktot, 64};
+    const uint64_t strides[2] = {2, ktot * 2};
+    const uint32_t box[2] = {static_cast<uint32_t>(kBK), BN / 2};
+    const uint32_t es[2] = {1, 1};
+    int rc = din_encode_tmap(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w2_packed), dims, strides, box, es,
+                             CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != DIN_OK) return rc;
+  }
+  FusedStemParams sp{};
+  sp.w1 = w1; sp.b1 = b1; sp.img_h = h; sp.img_w = w; sp.n_img = n; sp.prep = prep;
+  const int sms = din_num_sms();
+  DIN_CHECK_ARG(sms > 0, "%s: no CUDA device", who);
+  const int pairs = (p.num_tiles + 1) / 2;
+  const int grid = 2 * (pairs < sms / 2 ? pairs : sms / 2);
+  const size_t smem = static_cast<size_t>(kFusedAStages) * p.a_stage_bytes + 9 * (BN / 2) * kBK * 2 + 2 * kColBufBytes +
+                      4 * kStemSbo + kPatchStages * kPatchStageBytes + kNumEpiWarps * kEpiScratch + 1024 /*align*/ +
+                      32 * 8 /*barriers*/ + 16 + BN * 4;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (x_is_u8) {
+    DIN_OPT_IN_SMEM(conv1_fused_2cta_kernel<true>, smem);
+    conv1_fused_2cta_kernel<true><<<grid, kFusedThreads, smem, st>>>(timg, tb, p, sp);
+  } else {
+    DIN_OPT_IN_SMEM(conv1_fused_2cta_kernel<false>, smem);
+    conv1_fused_2cta_kernel<false><<<grid, kFusedThreads, smem, st>>>(timg, tb, p, sp);
+  }
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
 }
 
 extern "C" int din_conv2d_relu_bwd_nhwc_f16(const DinConvDesc* d, const void* dz, const void* w_packed,

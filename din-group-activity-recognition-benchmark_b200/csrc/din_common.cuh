@@ -168,6 +168,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
                                             int c2, int c3) {
   asm volatile(
@@ -320,6 +326,32 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
 // N>>3 at bit 17, M>>4 at bit 24.
 __host__ __device__ constexpr uint32_t umma_idesc_f16_f32(int m, int n) {
   return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// ----------------------------------------------------------------------------------------------
+// 3-channel stem helpers shared by stem_tc.cu and the fused conv1_1 + conv1_2 kernel (conv_tcgen05.cu)
+// ----------------------------------------------------------------------------------------------
+// canonical no-swizzle K-major layout: 16-byte chunk kc of row r of an [rows x k_pad] operand
+__device__ __forceinline__ uint32_t canon_off(int r, int kc, int sbo_bytes) {
+  return static_cast<uint32_t>((r >> 3) * sbo_bytes + kc * 128 + (r & 7) * 16);
+}
+
+__device__ __forceinline__ uint64_t desc_noswz(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr >> 4) & 0x3FFFu);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1u) << 46;   // descriptor version (Blackwell); layout type 0 = no swizzle
+  return d;
+}
+
+// prep_images with the contraction spelled out (one FMA, one exact doubling), so that every instantiation
+// rounds identically: (x/255 - 0.5)*2 (utils.py:14-17); the product by 1/255 differs from the division by at
+// most 1 ulp(fp32), far below the fp16 rounding applied next.
+// Branch-free: without prep the constants are (1, 0, 1), which reproduce f exactly.
+__device__ __forceinline__ float prep_value(float f, bool prep) {
+  const float a = prep ? 1.0f / 255.0f : 1.0f, b = prep ? -0.5f : 0.0f, c = prep ? 2.0f : 1.0f;
+  return __fmul_rn(__fmaf_rn(f, a, b), c);
 }
 
 }  // namespace din

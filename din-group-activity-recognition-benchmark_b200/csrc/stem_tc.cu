@@ -62,20 +62,6 @@ struct StemCfg {
                                   static_cast<size_t>(kRows) * kPitch * 4;
 };
 
-// canonical no-swizzle K-major layout: 16-byte chunk kc of row r of an [rows x k_pad] operand
-__device__ __forceinline__ uint32_t canon_off(int r, int kc, int sbo_bytes) {
-  return static_cast<uint32_t>((r >> 3) * sbo_bytes + kc * 128 + (r & 7) * 16);
-}
-
-__device__ __forceinline__ uint64_t desc_noswz(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((addr >> 4) & 0x3FFFu);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= static_cast<uint64_t>(1u) << 46;   // descriptor version (Blackwell); layout type 0 = no swizzle
-  return d;
-}
-
 // Input patch of one tile held in registers between the global loads and the shared-memory staging (all loads
 // in flight at once).
 //   fp32 NCHW: one float per (channel, filter row, column slot);  uint8 NHWC: the pixel's 3 bytes packed in
@@ -87,15 +73,6 @@ struct PatchRegs {
   uint32_t v[kN];
   uint32_t valid;     // fp32 path: bit (ky * kLoadsPerRow + u) = that (row, column slot) is inside the image
 };
-
-// prep_images with the contraction spelled out (one FMA, one exact doubling), so that every instantiation
-// rounds identically: (x/255 - 0.5)*2 (utils.py:14-17); the product by 1/255 differs from the division by at
-// most 1 ulp(fp32), far below the fp16 rounding applied next.
-// Branch-free: without prep the constants are (1, 0, 1), which reproduce f exactly.
-__device__ __forceinline__ float prep_value(float f, bool prep) {
-  const float a = prep ? 1.0f / 255.0f : 1.0f, b = prep ? -0.5f : 0.0f, c = prep ? 2.0f : 1.0f;
-  return __fmul_rn(__fmaf_rn(f, a, b), c);
-}
 
 struct TileCoord { int img, oy, strip; };
 

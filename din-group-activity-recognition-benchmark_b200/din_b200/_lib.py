@@ -39,6 +39,7 @@ PROTOTYPES = {
     "din_stem_conv_nchw_f32": (C.c_int, [_fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_stem_conv_nhwc_u8": (C.c_int, [_vp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_conv2d_nhwc_f16": (C.c_int, [C.POINTER(DinConvDesc), _vp, _vp, _fp, _vp, _vp, _vp]),
+    "din_conv3x3_stem_pair_nhwc_f16": (C.c_int, [_vp, _i, _fp, _fp, _vp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_conv2d_relu_bwd_nhwc_f16": (C.c_int, [C.POINTER(DinConvDesc), _vp, _vp, _vp, _vp, _vp]),
     "din_pack_conv_weight_f16": (C.c_int, [_fp, _fp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "din_bn_fold_grads_f32": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_float, _fp, _i, _ll, _vp]),

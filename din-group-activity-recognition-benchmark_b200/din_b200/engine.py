@@ -69,8 +69,10 @@ def _pack_dgrad_filters(convs):
 # nothing exactly where the path needs it most: tiny inputs (one frame, one actor) have no averaging over pixels or
 # actors to hide operand rounding behind (tests/test_edge_cases_gpu.py holds T = N = 1 to the same 1e-3 as every
 # BASELINE shape).  Full-size launches are untouched.
-SMALL_LAUNCH_PIXELS = 148 * 128
-SMALL_EMBED_ROWS = 64       # fewer actor rows than half an MMA tile: fp32 crops + fp32 fc_emb_1 (din_linear_f32)
+FUSE_CONV1 = os.environ.get("DIN_FUSE_CONV1", "1") != "0"      # A/B knob: 0 = stand-alone stem + conv1_2
+SMALL_LAUNCH_PIXELS = 148 * 128 if os.environ.get("DIN_SMALL_EXACT", "1") != "0" else 0
+# fewer actor rows than half an MMA tile: fp32 crops + fp32 fc_emb_1 (din_linear_f32)
+SMALL_EMBED_ROWS = 64 if os.environ.get("DIN_SMALL_EMBED_F32", "1") != "0" else 0
 
 
 class _Conv:
@@ -212,7 +214,17 @@ class VGG16Plan:
     def __call__(self, images, out=None):
         x = images
         last = len(self.layers) - 1
-        for i, layer in enumerate(self.layers):
+        first = 0
+        stem, c12 = self.layers[0], self.layers[1]
+        n_px = images.shape[0] * (images.shape[1] * images.shape[2] if images.dtype == torch.uint8
+                                  else images.shape[2] * images.shape[3])
+        if FUSE_CONV1 and ops.stem_pair_supported(images) and n_px > SMALL_LAUNCH_PIXELS:
+            # conv1_1 + conv1_2 (+ pool) in one launch: conv1_1's output never reaches HBM (inference only; the
+            # training forward keeps every activation).  Tiny launches stay on the two-kernel path (exact weights).
+            x = ops.stem_conv_pair(images, stem.w, stem.bias, c12.w, c12.bias, relu=True, pool2=c12.pool2, prep=True)
+            first = 2
+        for i in range(first, len(self.layers)):
+            layer = self.layers[i]
             x = layer(x, out=out) if i == last else layer(x)
         return x
 

@@ -171,6 +171,41 @@ def stem_conv(x, w_oihw, bias, *, stride=1, pad=0, relu=True, prep=True):
     return y
 
 
+def stem_pair_supported(x):
+    """The fused conv1_1 + conv1_2 kernel loads image patches by TMA: rows must be 16-byte multiples."""
+    if x.dtype == torch.uint8:
+        return x.dim() == 4 and x.shape[-1] == 3 and x.shape[2] % 16 == 0
+    return x.dim() == 4 and x.shape[1] == 3 and x.shape[3] % 4 == 0
+
+
+def stem_conv_pair(x, w1_oihw, b1, w2_packed, b2, *, relu=True, pool2=False, prep=True, out=None):
+    """Raw images -> prep_images -> conv3x3(3->64)+bias+ReLU -> conv3x3(64->64)+bias(+ReLU)(+2x2 max-pool) -> NHWC fp16,
+    one launch; the 64-channel intermediate never leaves the SM (din_conv3x3_stem_pair_nhwc_f16)."""
+    is_u8 = x.dtype == torch.uint8
+    if not is_u8:
+        _need(x, torch.float32, "x")
+    elif not (x.is_cuda and x.is_contiguous()):
+        raise _lib.DinError("x must be a contiguous CUDA tensor")
+    _need(w1_oihw, torch.float32, "w1_oihw")
+    _need(w2_packed, torch.float16, "w2_packed")
+    if tuple(w1_oihw.shape) != (64, 3, 3, 3) or tuple(w2_packed.shape) != (64, 3, 3, 64):
+        raise _lib.DinError(f"stem_conv_pair: weights must be [64,3,3,3] and packed [64,3,3,64], got "
+                            f"{tuple(w1_oihw.shape)} / {tuple(w2_packed.shape)}")
+    n, h, w = (x.shape[0], x.shape[1], x.shape[2]) if is_u8 else (x.shape[0], x.shape[2], x.shape[3])
+    yh, yw = (h // 2, w // 2) if pool2 else (h, w)
+    if out is None:
+        out = torch.empty((n, yh, yw, 64), dtype=torch.float16, device=x.device)
+    _need(out, torch.float16, "out")
+    assert out.shape[:3] == (n, yh, yw) and out.shape[3] >= 64, (tuple(out.shape), (n, yh, yw))
+    flops = 2 * n * h * w * 64 * (27 + 9 * 64)
+    nbytes = x.numel() * x.element_size() + 2 * n * yh * yw * 64
+    with _launch(f"conv3x3s1_3->64->64@{h}x{w}+stem" + ("+pool" if pool2 else ""), flops, nbytes):
+        check(_lib.load().din_conv3x3_stem_pair_nhwc_f16(_p(x), int(is_u8), _p(w1_oihw), _p(b1), _p(w2_packed), _p(b2),
+                                                         _p(out), n, h, w, out.shape[3], int(relu), int(pool2),
+                                                         int(prep), _stream()), "din_conv3x3_stem_pair_nhwc_f16")
+    return out
+
+
 def _pool(fn_name, x, k, stride, pad, out, c, x_c_offset, y_c_offset):
     _need(x, torch.float16, "x")
     n, h, w, cx = x.shape

@@ -117,6 +117,20 @@ typedef struct DinConvDesc {
 DIN_API int din_conv2d_nhwc_f16(const DinConvDesc* desc, const void* x, const void* w_packed, const float* bias,
                         const void* residual, void* y, void* stream);
 
+/* VGG-16's first two layers in ONE launch (inference): conv1_1 = 3x3 pad 1 over the 3-channel image (prep_images fused,
+ * bias, ReLU) computed tile by tile INSIDE the CTA-pair kernel of conv1_2 = 3x3 pad 1, 64 -> 64 channels, bias, ReLU,
+ * optional fused 2x2 max-pool: conv1_1's 64-channel output (118 MB per 720p frame) never reaches HBM
+ * (csrc/conv_tcgen05.cu: conv1_fused_2cta_kernel).  Same values as din_stem_conv_* followed by din_conv2d_nhwc_f16.
+ * Replaces: prep_images (utils.py:8-19) + vgg16.features[0:4] (+ features[4] with pool2) of backbone.py:88-99.
+ * x        : fp32 NCHW [n,3,h,w] raw 0..255, w % 4 == 0   |   (x_is_u8) uint8 NHWC [n,h,w,3], w % 16 == 0
+ *            (TMA row pitch; other widths: use the two separate calls)
+ * w1, b1   : conv1_1 weight fp32 OIHW [64,3,3,3] and bias [64] (or NULL)
+ * w2_packed: conv1_2 weight packed by din_pack_conv_weight_f16 (fp16 [64][3][3][64]); b2: fp32 [64] or NULL
+ * y        : fp16 NHWC [n, h, w, y_c_stride] (pool2: [n, h/2, w/2, y_c_stride]), channels [0, 64) written */
+DIN_API int din_conv3x3_stem_pair_nhwc_f16(const void* x, int x_is_u8, const float* w1, const float* b1,
+                                           const void* w2_packed, const float* b2, void* y, int n, int h, int w,
+                                           int y_c_stride, int relu2, int pool2, int prep, void* stream);
+
 /* Data gradient of a convolution fused with the backward of the ReLU that FOLLOWS the layer below:
  *   dx = conv(dz, w_packed) * [y_saved > 0]
  * (w_packed = the data-gradient filter, DinPackJob.transposed = 1; y_saved = that layer's saved ReLU output, fp16, indexed

@@ -204,3 +204,50 @@ def test_batched_packing_matches_single_packs_and_dgrad_filters(cuda):
         wf = w if sc is None else w * sc.view(-1, 1, 1, 1)
         ref = ops.pack_conv_weight(wf.permute(1, 0, 2, 3).flip(2, 3).contiguous())
         assert out.shape == ref.shape and torch.equal(out, ref), tuple(w.shape)
+
+
+@pytest.mark.parametrize("n,h,w,pool,u8", [(2, 48, 64, True, False), (1, 50, 76, False, False), (3, 37, 100, True, False),
+                                            (2, 48, 64, True, True), (1, 66, 112, False, True),
+                                            (2, 720, 1280, True, False), (1, 720, 1280, True, True)],
+                         ids=lambda v: str(v))
+def test_stem_pair_fused_equals_the_two_kernel_path(cuda, n, h, w, pool, u8):
+    """conv1_1 + conv1_2 in one launch (conv1_fused_2cta_kernel: the stem computed inside conv1_2's A producer) must
+    reproduce the stand-alone stem followed by the CTA-pair convolution -- the same fp16 roundings in the same places,
+    so the comparison is on bits (one fp16 ulp is tolerated on at most 1e-5 of the elements, should a tensor-core
+    accumulation order differ between M = 128 and M = 256 instructions) -- and both match fp32 torch.  Shapes cover
+    ragged tiles (h % 16, w % 8 != 0), odd tile counts (an idle second CTA in the last pair), uint8 frames, 720p."""
+    from din_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(11)
+    img = torch.randint(0, 256, (n, 3, h, w), generator=g)
+    w1 = (torch.randn(64, 3, 3, 3, generator=g) * 0.3).to(cuda)
+    b1 = (torch.randn(64, generator=g) * 0.2).to(cuda)
+    w2 = (torch.randn(64, 64, 3, 3, generator=g) * (2.0 / 576) ** 0.5).to(cuda)
+    b2 = (torch.randn(64, generator=g) * 0.1).to(cuda)
+    w2p = ops.pack_conv_weight(w2)
+    x = img.permute(0, 2, 3, 1).contiguous().to(torch.uint8).to(cuda) if u8 else img.float().to(cuda)
+    assert ops.stem_pair_supported(x)
+    y1 = ops.stem_conv(x, w1, b1, stride=1, pad=1, relu=True, prep=True)
+    want = ops.conv2d_nhwc(y1, w2p, b2, stride=1, pad=(1, 1), relu=True, pool2=pool)
+    got = ops.stem_conv_pair(x, w1, b1, w2p, b2, relu=True, pool2=pool, prep=True)
+    torch.cuda.synchronize()
+    assert got.shape == want.shape
+    diff = (got.float() - want.float()).abs()
+    n_diff = int((diff > 0).sum())
+    print(f"\n[stem pair] {n}x{h}x{w} pool={pool} u8={u8}: {n_diff} of {diff.numel()} elements differ, max |diff| {diff.max().item():.3e}")
+    assert n_diff <= 1e-5 * diff.numel() and diff.max().item() <= 2e-3 * want.float().abs().max().item()
+    if h * w <= 128 * 128:
+        xp = ((img.float().to(cuda) / 255.0) - 0.5) * 2.0
+        ref = F.relu(F.conv2d(F.relu(F.conv2d(xp, w1, b1, padding=1)), w2, b2, padding=1))
+        if pool:
+            ref = F.max_pool2d(ref, 2, 2)
+        ref = ref.permute(0, 2, 3, 1)
+        assert (got.float() - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
+
+
+def test_stem_pair_rejects_unaligned_widths(cuda):
+    from din_b200 import _lib, ops
+    x = torch.zeros(1, 3, 32, 30, device=cuda)
+    assert not ops.stem_pair_supported(x)
+    w2p = ops.pack_conv_weight(torch.zeros(64, 64, 3, 3, device=cuda))
+    with pytest.raises(_lib.DinError):
+        ops.stem_conv_pair(x, torch.zeros(64, 3, 3, 3, device=cuda), None, w2p, None)

@@ -223,3 +223,64 @@ def test_readout(cuda):
     nv = torch.tensor([13, 3, 1], dtype=torch.int32)
     ref = torch.stack([F.linear(s[i, :, :int(nv[i])].max(dim=1)[0], w, b).mean(dim=0) for i in range(B)])
     _close(ops.readout(s.to(cuda), w.to(cuda), b.to(cuda), n_valid=nv.to(cuda)), ref, 2e-5, "readout n_valid")
+
+
+def test_dpi_modules_train_standalone(cuda):
+    """Autograd through the stand-alone infer_module.dynamic_infer_module classes (reference
+    dynamic_infer_module.py:121-151, 436-443, 491-498): gradient w.r.t. the input and every parameter against torch
+    autograd over the oracle, for a bare module (two ratios, beta), parallel fields and the hierarchical pair."""
+    import din_oracle as O
+    from infer_module.dynamic_infer_module import (Dynamic_Person_Inference, Hierarchical_Dynamic_Inference,
+                                                   Multi_Dynamic_Inference)
+    g = torch.Generator().manual_seed(21)
+
+    def randomise(mod):
+        for n, p in mod.named_parameters():
+            with torch.no_grad():
+                if "p_conv" in n or "scale_conv" in n:
+                    p.copy_(torch.randn(p.shape, generator=g) * (0.01 if n.endswith("weight") else 0.5))
+                elif n.endswith("beta"):
+                    p.copy_(torch.rand(p.shape, generator=g) + 0.5)
+                elif "LN" in n:
+                    p.copy_(torch.rand(p.shape, generator=g) + 0.5 if n.endswith("weight")
+                            else torch.randn(p.shape, generator=g) * 0.1)
+
+    def check(mod, x, ref_fn, prefix, what):
+        randomise(mod)
+        mod.eval()                                            # dropout off (hierarchical), gradients still flow
+        sd = {prefix + k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in mod.state_dict().items()}
+        xr = x.clone().requires_grad_(True)
+        w = torch.randn(x.shape, generator=g)
+        (ref_fn(xr, sd) * w).sum().backward()
+        mod = mod.to(cuda)
+        xc = x.to(cuda).requires_grad_(True)
+        y, mad = mod(xc)
+        assert y.requires_grad and mad.numel() == 0
+        (y * w.to(cuda)).sum().backward()
+        _close(xc.grad, xr.grad, 2e-4, what + " d/dx")
+        n_checked = 0
+        for n, p in mod.named_parameters():
+            assert p.grad is not None, n
+            _close(p.grad, sd[prefix + n].grad, 3e-4, f"{what} d/d{n}")
+            n_checked += 1
+        return n_checked
+
+    m = Dynamic_Person_Inference(128, (10, 12), kernel_size=(3, 3), dynamic_sampling=True, sampling_ratio=[1, 3],
+                                 scale_factor=True, beta_factor=True)
+    n = check(m, torch.randn(2, 6, 7, 128, generator=g),
+              lambda x, sd: O.dynamic_person_inference(x, sd, "", (3, 3), [1, 3], True, True), "", "DPI")
+    assert n == 10                                            # hidden, beta, 2 x (p_conv w/b, scale_conv w/b)
+    mm = Multi_Dynamic_Inference(64, (10, 12), kernel_size=[(1, 3), (3, 1)], dynamic_sampling=True,
+                                 sampling_ratio=[1], scale_factor=True, num_DIM=2)
+    pc = O.PathConfig(ST_kernel_size=[(1, 3), (3, 1)], num_DIM=2, sampling_ratio=(1,))
+    check(mm, torch.randn(2, 4, 5, 64, generator=g), lambda x, sd: O.dpi_forward(x, sd, pc), "DPI.", "Multi")
+    mh = Hierarchical_Dynamic_Inference(1024, (10, 12), kernel_size=[(1, 3), (3, 1)], dynamic_sampling=True,
+                                        sampling_ratio=[1], scale_factor=True)
+    pch = O.PathConfig(ST_kernel_size=[(1, 3), (3, 1)], hierarchical_inference=True, sampling_ratio=(1,), lite_dim=None)
+    check(mh, torch.randn(1, 10, 12, 1024, generator=g), lambda x, sd: O.dpi_forward(x, sd, pch), "DPI.", "Hierarchical")
+    # train() mode of the hierarchical module draws its dropout mask from torch's generator and still back-propagates
+    mh.train()
+    xt = torch.randn(1, 10, 12, 1024, generator=g).to(cuda).requires_grad_(True)
+    yt, _ = mh(xt)
+    yt.square().mean().backward()
+    assert torch.isfinite(xt.grad).all() and float(xt.grad.abs().max()) > 0

@@ -118,7 +118,7 @@ def main():
     cfg = seen["cfg"]
     log = open(cfg.log_path).read()
     losses = [float(x) for x in re.findall(r"Loss: ([-+0-9.eE]+|nan|inf)", log)]
-    ckpts = sorted(glob.glob(os.path.join(cfg.result_path, "stage2_epoch*.pth")))
+    ckpts = sorted(glob.glob(os.path.join(glob.escape(cfg.result_path), "stage2_epoch*.pth")))   # the name holds [ ]
     assert ckpts, "train_net wrote no checkpoint"
     state = torch.load(ckpts[-1], map_location="cpu")
     sd = {k[len("module."):] if k.startswith("module.") else k: v for k, v in state["state_dict"].items()}
