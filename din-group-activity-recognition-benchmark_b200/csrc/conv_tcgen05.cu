@@ -688,8 +688,11 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 // Here the CTA-pair conv1_2 kernel (conv_igemm_2cta_kernel<64, 9>: resident weights, one cta_group::2 MMA of M = 256
 // per K step) produces its own A operand: instead of a TMA box of conv1_1's output, four extra warps per CTA compute
 // the tile's 18 x 10 halo of conv1_1 from the 3-channel image --
-//   patch   TMA box {12, 20, 3} of the raw fp32 NCHW image (or {48 B, 20} of the uint8 NHWC frame) -> shared memory,
-//           three tiles ahead;
+//   patch   TMA box {16, 20, 3} of the raw fp32 NCHW image (or {96 B, 20} of the uint8 NHWC frame) -> shared memory,
+//           three tiles ahead.  The box is wider than the 12 pixels needed because a TMA box must START on a 16-byte
+//           boundary in its innermost dimension (an unaligned inner coordinate is an illegal-instruction fault, probed
+//           on the B200: tools/probes/tma_probe.cu): fp32 starts 4 pixels left of the tile, uint8 at the enclosing
+//           multiple of 16 pixels;
 //   im2col  thread r builds halo pixel r's K = 27 (+ 2 bias columns, padded to 32) fp16 row in the canonical
 //           no-swizzle UMMA layout (prep_images fused, zero where conv1_1 pads): 180 rows, two per thread;
 //   MMA     the leader's MMA warp issues 2 row blocks x 2 K steps of tcgen05.mma.cta_group::2 (M = 256 = 128 halo
@@ -705,18 +708,38 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 constexpr int kFusedThreads = 512;          // 4 role warps + 8 epilogue warps + 4 stem warps
 constexpr int kFusedStemWarp0 = 12;
 constexpr int kHaloH = 18, kHaloW = 10, kHaloRows = kHaloH * kHaloW;      // conv1_2's 16 x 8 tile + 1 pixel border
-constexpr int kPatchH = 20, kPatchW = 12;                                 // conv1_1's input for that halo
+constexpr int kPatchH = 20, kPatchW = 16;                                 // conv1_1's input for that halo: 12 columns
+                                                                          // needed, 16 loaded (16-byte aligned start)
+constexpr int kPatchXOff = 2;                                             // needed column 0 = loaded column 2 (fp32)
+constexpr int kPatchU8Bytes = 96;                                         // uint8: 32 pixels x 3 bytes per patch row
 constexpr int kStemKPad = 32, kStemSbo = kStemKPad * 16;                  // K = 27 + 2 bias columns -> 32
 constexpr int kColBufBytes = 2 * 16 * kStemSbo;                           // two 128-row blocks per CTA
-constexpr int kPatchStageBytes = 3072;                                    // >= 3*20*12*4 (fp32) / 20*48 (uint8)
+constexpr int kPatchStageBytes = 4096;                                    // >= 3*20*16*4 (fp32) / 20*96 (uint8)
 constexpr int kPatchStages = 3;
 constexpr int kFusedAStages = 4;
+
+// Bounded wait that records WHICH wait timed out (code, block, thread) in a host-mapped word before trapping: after a
+// trap the context is gone, but the pinned host word survives (DIN_FUSED_DEBUG=1, read back by din_debug_word()).
+__device__ __forceinline__ void mbar_wait_code(uint64_t* bar, uint32_t parity, unsigned int* dbg, unsigned int code) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (dbg ? (1u << 22) : (1u << 26))) {
+      if (dbg) {
+        atomicCAS_system(dbg, 0u, (code << 24) | ((blockIdx.x & 0xFFFu) << 12) | (threadIdx.x & 0xFFFu));
+        dbg[1 + (code & 31u)] = (static_cast<unsigned int>(parity) << 31) | (blockIdx.x << 12) | threadIdx.x;
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
 
 struct FusedStemParams {
   const float* w1;       // [64][3][3][3] fp32 (OIHW)
   const float* b1;       // [64]
   int img_h, img_w, n_img;
   int prep;              // apply prep_images to the raw pixel values
+  unsigned int* dbg;     // host-mapped debug words (DIN_FUSED_DEBUG=1) or NULL
 };
 
 template <bool U8>
@@ -746,8 +769,8 @@ conv1_fused_2cta_kernel(const __grid_constant__ CUtensorMap tmap_img, const __gr
   uint64_t* col_full = patch_empty + kPatchStages;     // [2]  leader: 8 warp arrivals
   uint64_t* stem_done = col_full + 2;            // [2]  both: multicast commit of the stem MMAs
   uint64_t* stem_free = stem_done + 2;           // [2]  leader: 8 warp arrivals (stem accumulator drained)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(stem_free + 2);
-  float* bias_s = reinterpret_cast<float*>(tmem_ptr_smem + 4);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 30);       // 25 barriers used; the block is 32 x 8 bytes
+  float* bias_s = reinterpret_cast<float*>(bars + 32);                    // 16-byte aligned (read as float4)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -815,15 +838,15 @@ conv1_fused_2cta_kernel(const __grid_constant__ CUtensorMap tmap_img, const __gr
         const int tyi = fdiv(r, p.fd_tx);
         const int txi = r - tyi * p.tiles_x;
         const int ps = j % kPatchStages;
-        mbar_wait(&patch_empty[ps], (((j / kPatchStages) & 1) ^ 1));
+        mbar_wait_code(&patch_empty[ps], (((j / kPatchStages) & 1) ^ 1), sp.dbg, 1u /*patch_empty*/);
         if constexpr (U8) {
-          mbar_arrive_expect_tx(&patch_full[ps], kPatchH * 48u);
-          tma_load_3d(patch_s + ps * kPatchStageBytes, &tmap_img, &patch_full[ps], (txi * p.tw - 2) * 3,
+          mbar_arrive_expect_tx(&patch_full[ps], static_cast<uint32_t>(kPatchH * kPatchU8Bytes));
+          tma_load_3d(patch_s + ps * kPatchStageBytes, &tmap_img, &patch_full[ps], ((txi * p.tw - 2) & ~15) * 3,
                       tyi * p.th - 2, img);
         } else {
           mbar_arrive_expect_tx(&patch_full[ps], 3u * kPatchH * kPatchW * 4u);
-          tma_load_3d(patch_s + ps * kPatchStageBytes, &tmap_img, &patch_full[ps], txi * p.tw - 2, tyi * p.th - 2,
-                      img * 3);
+          tma_load_3d(patch_s + ps * kPatchStageBytes, &tmap_img, &patch_full[ps], txi * p.tw - 2 - kPatchXOff,
+                      tyi * p.th - 2, img * 3);
         }
       }
     }
@@ -850,8 +873,8 @@ conv1_fused_2cta_kernel(const __grid_constant__ CUtensorMap tmap_img, const __gr
       auto issue_stem = [&](int j) {
         const int cb = j & 1;
         const uint32_t use = static_cast<uint32_t>(j >> 1);           // k-th use of this buffer
-        mbar_wait(&col_full[cb], use & 1u);
-        if (use > 0) mbar_wait(&stem_free[cb], (use - 1u) & 1u);      // the previous result has been drained
+        mbar_wait_code(&col_full[cb], use & 1u, sp.dbg, 2u /*col_full*/);
+        if (use > 0) mbar_wait_code(&stem_free[cb], (use - 1u) & 1u, sp.dbg, 3u /*stem_free*/);      // the previous result has been drained
         tc_fence_after_sync();
         if (leader) {
 #pragma unroll
@@ -874,9 +897,9 @@ conv1_fused_2cta_kernel(const __grid_constant__ CUtensorMap tmap_img, const __gr
       for (int pi = pair_first; pi < n_pairs; pi += pair_step, ++it) {
         if (pi + pair_step < n_pairs) issue_stem(it + 1);             // one tile ahead: its drain overlaps these MMAs
         const int acc = it & 1;
-        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1u) ^ 1u);
-        mbar_wait(&a_full[sa], pa);
-        if (it == 0) mbar_wait(&b_full[0], 0);
+        mbar_wait_code(&tmem_empty[acc], ((it >> 1) & 1u) ^ 1u, sp.dbg, 4u /*tmem_empty*/);
+        mbar_wait_code(&a_full[sa], pa, sp.dbg, 5u /*a_full*/);
+        if (it == 0) mbar_wait_code(&b_full[0], 0, sp.dbg, 6u /*b_full*/);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
         const uint32_t a_lo = a_lo0 + sa * a_step;
@@ -915,10 +938,11 @@ conv1_fused_2cta_kernel(const __grid_constant__ CUtensorMap tmap_img, const __gr
       tile_of(pi, img, tyi, txi);
       const int ps = j % kPatchStages, cb = j & 1;
       const uint32_t use = static_cast<uint32_t>(j >> 1);
-      if (use > 0) mbar_wait(&stem_done[cb], (use - 1u) & 1u);       // the MMAs that read this buffer have retired
-      mbar_wait(&patch_full[ps], (j / kPatchStages) & 1);
+      if (use > 0) mbar_wait_code(&stem_done[cb], (use - 1u) & 1u, sp.dbg, 7u /*stem_done*/);       // the MMAs that read this buffer have retired
+      mbar_wait_code(&patch_full[ps], (j / kPatchStages) & 1, sp.dbg, 8u /*patch_full*/);
       const uint8_t* patch = patch_s + ps * kPatchStageBytes;
-      const int gy0 = tyi * p.th - 2, gx0 = txi * p.tw - 2;           // image coordinates of patch element (0, 0)
+      const int gy0 = tyi * p.th - 2, gx0 = txi * p.tw - 2;           // image coordinates of the first NEEDED patch element
+      const int xoff = U8 ? (gx0 - (gx0 & ~15)) : kPatchXOff;         // its column in the (wider, aligned) loaded box
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int r = st + half * 128;
@@ -938,8 +962,8 @@ conv1_fused_2cta_kernel(const __grid_constant__ CUtensorMap tmap_img, const __gr
 #pragma unroll
               for (int dx = 0; dx < 3; ++dx) {
                 float raw;
-                if constexpr (U8) raw = static_cast<float>(patch[(hy + dy) * 48 + (hx + dx) * 3 + c]);
-                else raw = reinterpret_cast<const float*>(patch)[(c * kPatchH + hy + dy) * kPatchW + hx + dx];
+                if constexpr (U8) raw = static_cast<float>(patch[(hy + dy) * kPatchU8Bytes + (xoff + hx + dx) * 3 + c]);
+                else raw = reinterpret_cast<const float*>(patch)[(c * kPatchH + hy + dy) * kPatchW + xoff + hx + dx];
                 f[(c * 3 + dy) * 3 + dx] = (rok[dy] && cok[dx]) ? prep_value(raw, sp.prep != 0) : 0.0f;
               }
           f[27] = 1.0f; f[28] = 1.0f; f[29] = 0.0f; f[30] = 0.0f; f[31] = 0.0f;      // the two bias columns
@@ -968,8 +992,8 @@ conv1_fused_2cta_kernel(const __grid_constant__ CUtensorMap tmap_img, const __gr
       int img, tyi, txi;
       tile_of(pi, img, tyi, txi);
       const int cb = j & 1, as = j % kFusedAStages;
-      mbar_wait(&stem_done[cb], static_cast<uint32_t>(j >> 1) & 1u);
-      mbar_wait(&a_empty[as], ((j / kFusedAStages) & 1) ^ 1);
+      mbar_wait_code(&stem_done[cb], static_cast<uint32_t>(j >> 1) & 1u, sp.dbg, 9u /*stem_done*/);
+      mbar_wait_code(&a_empty[as], ((j / kFusedAStages) & 1) ^ 1, sp.dbg, 10u /*a_empty*/);
       tc_fence_after_sync();
       uint8_t* a_stage = smem_a + as * p.a_stage_bytes;
       const int oy0 = tyi * p.th - 1, ox0 = txi * p.tw - 1;           // conv1_1 output coordinates of halo pixel (0, 0)
@@ -1259,6 +1283,27 @@ extern "C" int din_conv2d_nhwc_f16(const DinConvDesc* d, const void* x, const vo
   return conv2d_launch(d, x, w_packed, bias, residual, 0, y, stream);
 }
 
+namespace {
+unsigned int* g_dbg_host = nullptr;
+unsigned int* fused_debug_words() {
+  static unsigned int* dev = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* e = std::getenv("DIN_FUSED_DEBUG");
+    if (e && e[0] == '1' && cudaHostAlloc(reinterpret_cast<void**>(&g_dbg_host), 64 * sizeof(unsigned int),
+                                          cudaHostAllocMapped) == cudaSuccess) {
+      for (int i = 0; i < 64; ++i) g_dbg_host[i] = 0u;
+      if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev), g_dbg_host, 0) != cudaSuccess) dev = nullptr;
+    }
+  }
+  return dev;
+}
+}  // namespace
+
+// diagnostics: word i of the fused kernel's wait-timeout record (0 when DIN_FUSED_DEBUG is not set / nothing timed out)
+extern "C" unsigned int din_debug_word(int i) { return (g_dbg_host && i >= 0 && i < 64) ? g_dbg_host[i] : 0u; }
+
 // conv1_1 (3 -> 64, 3x3, pad 1, ReLU, prep_images fused) + conv1_2 (64 -> 64, 3x3, pad 1, bias, ReLU, optional 2x2
 // max-pool) in one launch: conv1_fused_2cta_kernel.
 extern "C" int din_conv3x3_stem_pair_nhwc_f16(const void* x, int x_is_u8, const float* w1, const float* b1,
@@ -1301,7 +1346,7 @@ extern "C" int din_conv3x3_stem_pair_nhwc_f16(const void* x, int x_is_u8, const 
   if (x_is_u8) {
     const uint64_t dims[3] = {static_cast<uint64_t>(w) * 3, static_cast<uint64_t>(h), static_cast<uint64_t>(n)};
     const uint64_t strides[3] = {1, static_cast<uint64_t>(w) * 3, static_cast<uint64_t>(w) * 3 * h};
-    const uint32_t box[3] = {48, kPatchH, 1};
+    const uint32_t box[3] = {kPatchU8Bytes, kPatchH, 1};
     const uint32_t es[3] = {1, 1, 1};
     int rc = din_encode_tmap(&timg, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(x), dims, strides, box, es,
                              CU_TENSOR_MAP_SWIZZLE_NONE);
@@ -1327,6 +1372,7 @@ extern "C" int din_conv3x3_stem_pair_nhwc_f16(const void* x, int x_is_u8, const 
   }
   FusedStemParams sp{};
   sp.w1 = w1; sp.b1 = b1; sp.img_h = h; sp.img_w = w; sp.n_img = n; sp.prep = prep;
+  sp.dbg = fused_debug_words();
   const int sms = din_num_sms();
   DIN_CHECK_ARG(sms > 0, "%s: no CUDA device", who);
   const int pairs = (p.num_tiles + 1) / 2;

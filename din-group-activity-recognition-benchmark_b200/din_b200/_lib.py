@@ -35,6 +35,7 @@ PROTOTYPES = {
     "din_abi_version": (C.c_int, []),
     "din_last_error_string": (C.c_char_p, []),
     "din_device_sm_count": (C.c_int, []),
+    "din_debug_word": (C.c_uint, [_i]),
     "din_tmap_cache_stats": (C.c_int, [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "din_stem_conv_nchw_f32": (C.c_int, [_fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_stem_conv_nhwc_u8": (C.c_int, [_vp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -69,6 +69,25 @@ def _pack_dgrad_filters(convs):
 # nothing exactly where the path needs it most: tiny inputs (one frame, one actor) have no averaging over pixels or
 # actors to hide operand rounding behind (tests/test_edge_cases_gpu.py holds T = N = 1 to the same 1e-3 as every
 # BASELINE shape).  Full-size launches are untouched.
+# Frames per backbone launch.  A chunk bounds the activation workspace; beyond that, bigger is better (every launch is a
+# persistent kernel that pays its prologue, pipeline fill and last-wave tail once): the inference forward sizes chunks
+# so that the widest activation of a chunk stays under CHUNK_BYTES.  ResNet-18's late layers (23 x 40 maps) went from
+# 470 to > 700 TFLOP/s when their launches grew from 16 to 64+ frames.  DIN_FRAMES_PER_CHUNK pins a fixed count.
+CHUNK_BYTES = int(float(os.environ.get("DIN_CHUNK_GB", "4")) * (1 << 30))
+# widest fp16 NHWC activation per frame, in bytes per input pixel: VGG-16 conv1_x (64 ch at full size), ResNet-18 stem
+# (64 ch at 1/4 of the pixels), Inception-v3 Conv2d_2b (64 ch at ~1/4)
+_ACT_BYTES_PER_PIXEL = {"vgg16": 128.0, "res18": 32.0, "inv3": 32.0}
+
+
+def frames_per_chunk(backbone_name, n_frames, h, w, fixed=None):
+    if fixed:
+        return min(n_frames, fixed)
+    per_frame = _ACT_BYTES_PER_PIXEL.get(backbone_name, 128.0) * h * w
+    cap = max(1, int(CHUNK_BYTES // per_frame))
+    n_chunks = -(-n_frames // cap)
+    return -(-n_frames // n_chunks)                 # even split: 80 frames with cap 36 -> 27 + 27 + 26
+
+
 FUSE_CONV1 = os.environ.get("DIN_FUSE_CONV1", "1") != "0"      # A/B knob: 0 = stand-alone stem + conv1_2
 SMALL_LAUNCH_PIXELS = 148 * 128 if os.environ.get("DIN_SMALL_EXACT", "1") != "0" else 0
 # fewer actor rows than half an MMA tile: fp32 crops + fp32 fc_emb_1 (din_linear_f32)
@@ -507,7 +526,7 @@ class DinEngine:
         self.cfg, self.dataset, self.device = cfg, dataset, torch.device(device)
         # frames per backbone launch: bounds the activation workspace (VGG-16 at 720p: 0.27 GB per frame
         # live at once) while keeping every launch many waves long
-        self.frames_per_chunk = frames_per_chunk or int(os.environ.get("DIN_FRAMES_PER_CHUNK", "16"))
+        self.frames_per_chunk = frames_per_chunk or int(os.environ.get("DIN_FRAMES_PER_CHUNK", "0")) or None
         sd = {k: v.detach().to(self.device, torch.float32) if v.is_floating_point() else v.detach().to(self.device)
               for k, v in state_dict.items()}
         self.T, self.N = cfg.num_frames, cfg.num_boxes
@@ -587,8 +606,9 @@ class DinEngine:
             # zero-initialised once: pad channels beyond D are never written and must stay finite (zero)
             self._fm_cache = (key, torch.zeros(key, dtype=torch.float16, device=images_flat.device))
         fm = self._fm_cache[1]
-        for f0 in range(0, F_, self.frames_per_chunk):
-            f1 = min(F_, f0 + self.frames_per_chunk)
+        per_chunk = frames_per_chunk(self.backbone_name, F_, H, W, self.frames_per_chunk)
+        for f0 in range(0, F_, per_chunk):
+            f1 = min(F_, f0 + per_chunk)
             self.backbone(images_flat[f0:f1], out=fm[f0:f1])      # last layer writes its slice in place
         return fm
 
@@ -602,7 +622,8 @@ class DinEngine:
         fm = torch.zeros((F_, oh, ow, d), dtype=torch.float16, device=images_flat.device)
         chunks = []
         # batch statistics couple all frames of the step: one chunk
-        per_chunk = F_ if getattr(self.backbone, "bn_train", False) else self.frames_per_chunk
+        # training keeps every activation of a chunk for the backward: 16-frame chunks (VGG-16 at 720p: 0.56 GB / frame)
+        per_chunk = F_ if getattr(self.backbone, "bn_train", False) else (self.frames_per_chunk or 16)
         for f0 in range(0, F_, per_chunk):
             f1 = min(F_, f0 + per_chunk)
             _, saved = self.backbone.forward_train(images_flat[f0:f1], out=fm[f0:f1])
@@ -675,7 +696,7 @@ class BasenetEngine:
 
     def __init__(self, cfg, state_dict, device, dataset="volleyball", emb_name="fc_emb"):
         self.cfg, self.dataset, self.device = cfg, dataset, torch.device(device)
-        self.frames_per_chunk = int(os.environ.get("DIN_FRAMES_PER_CHUNK", "16"))
+        self.frames_per_chunk = int(os.environ.get("DIN_FRAMES_PER_CHUNK", "0")) or None
         sd = {k: v.detach().to(self.device, torch.float32) if v.is_floating_point() else v.detach().to(self.device)
               for k, v in state_dict.items()}
         self.N, self.D, self.K, self.NFB = cfg.num_boxes, cfg.emb_features, cfg.crop_size[0], cfg.num_features_boxes

@@ -51,6 +51,10 @@ DIN_API int din_device_sm_count(void);
 /* Encoded CUtensorMaps are cached per (base pointer, extents, strides, box, swizzle): SURVEY.md section 8b.  Returns the
  * number of cached maps and, through the optional out-pointers, the hit / miss counts since load (diagnostics). */
 DIN_API int din_tmap_cache_stats(unsigned long long* hits, unsigned long long* misses);
+/* Diagnostics of din_conv3x3_stem_pair_nhwc_f16 with DIN_FUSED_DEBUG=1 in the environment: every bounded mbarrier wait
+ * of that kernel records (wait id << 24 | block << 12 | thread) in a host-mapped word before it traps, so that a
+ * mis-programmed pipeline names the wait that starved even though the context is lost.  Word 0 = first timeout. */
+DIN_API unsigned int din_debug_word(int i);
 
 /* ---- backbone ------------------------------------------------------------------------------ */
 
