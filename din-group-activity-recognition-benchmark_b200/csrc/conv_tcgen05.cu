@@ -705,8 +705,8 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 // stage -- resident weights, 36 MMAs per tile pair, TMEM double buffering, epilogue with the fused 2x2 max-pool --
 // is conv_igemm_2cta_kernel's.  Training keeps the two-kernel path (the backward needs conv1_1's activations).
 // ================================================================================================
-constexpr int kFusedThreads = 512;          // 4 role warps + 8 epilogue warps + 4 stem warps
-constexpr int kFusedStemWarp0 = 12;
+constexpr int kFusedThreads = 640;          // 4 role warps + 8 epilogue warps + 4 im2col warps + 4 drain warps
+constexpr int kFusedStemWarp0 = 12;         // warps 12..15 build im2col rows, warps 16..19 drain the stem accumulator
 constexpr int kHaloH = 18, kHaloW = 10, kHaloRows = kHaloH * kHaloW;      // conv1_2's 16 x 8 tile + 1 pixel border
 constexpr int kPatchH = 20, kPatchW = 16;                                 // conv1_1's input for that halo: 12 columns
                                                                           // needed, 16 loaded (16-byte aligned start)
@@ -794,7 +794,7 @@ conv1_fused_2cta_kernel(const __grid_constant__ CUtensorMap tmap_img, const __gr
     for (int c = threadIdx.x - 128; c < BN; c += 32 * kNumEpiWarps)
       bias_s[c] = (p.bias != nullptr && c < p.c_out) ? __ldg(p.bias + c) : 0.0f;
   }
-  if (warp >= kFusedStemWarp0) {
+  if (warp >= kFusedStemWarp0 && warp < kFusedStemWarp0 + 4) {
     const int st = threadIdx.x - 32 * kFusedStemWarp0;        // 0..127
     // the im2col buffers start out zeroed: rows 180..255 of every buffer are never written and must stay finite
     for (int i = st; i < 2 * kColBufBytes / 16; i += 128) reinterpret_cast<uint4*>(col_s)[i] = make_uint4(0, 0, 0, 0);
@@ -921,7 +921,8 @@ conv1_fused_2cta_kernel(const __grid_constant__ CUtensorMap tmap_img, const __gr
     }
   } else if (warp >= kFusedStemWarp0) {
     // ------------------------------------------------------------------ stem warps: im2col build + accumulator drain
-    const int st = threadIdx.x - 32 * kFusedStemWarp0;        // 0..127
+    const bool builder = warp < kFusedStemWarp0 + 4;
+    const int st = (threadIdx.x - 32 * kFusedStemWarp0) & 127;    // 0..127 within the role
     const int q = warp & 3;                                   // TMEM lane quadrant of this warp
 
     auto tile_of = [&](int pi, int& img, int& tyi, int& txi) {
@@ -1002,28 +1003,29 @@ conv1_fused_2cta_kernel(const __grid_constant__ CUtensorMap tmap_img, const __gr
         if (rb == 1 && q >= 2) break;                                 // rows 192.. do not exist (warp-uniform)
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 128u +
                                static_cast<uint32_t>(cb * 128 + rb * 64);
-        uint32_t v0[32], v1[32];
-        tmem_ld_32x32b_x32(taddr, v0);
-        tmem_ld_32x32b_x32(taddr + 32, v1);
-        tmem_ld_wait();
         const int r = rb * 128 + q * 32 + lane;
-        if (r < kHaloRows) {
-          const int hy = r / kHaloW, hx = r - hy * kHaloW;
-          const int oy = oy0 + hy, ox = ox0 + hx;
-          const bool inside = (img < sp.n_img) && oy >= 0 && oy < sp.img_h && ox >= 0 && ox < sp.img_w;
-          uint8_t* row = a_stage + r * 128;
-          const int sw = r & 7;
+        const int hy = r / kHaloW, hx = r - hy * kHaloW;
+        const int oy = oy0 + hy, ox = ox0 + hx;
+        const bool inside = (r < kHaloRows) && (img < sp.n_img) && oy >= 0 && oy < sp.img_h && ox >= 0 && ox < sp.img_w;
+        uint8_t* row = a_stage + r * 128;
+        const int sw = r & 7;
 #pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8) {
-            const uint32_t* v = c8 < 4 ? v0 + c8 * 8 : v1 + (c8 - 4) * 8;
-            uint4 o = make_uint4(0, 0, 0, 0);
-            if (inside) {
-              o.x = pack_half2(__uint_as_float(v[0]), __uint_as_float(v[1]), true);
-              o.y = pack_half2(__uint_as_float(v[2]), __uint_as_float(v[3]), true);
-              o.z = pack_half2(__uint_as_float(v[4]), __uint_as_float(v[5]), true);
-              o.w = pack_half2(__uint_as_float(v[6]), __uint_as_float(v[7]), true);
+        for (int hv = 0; hv < 2; ++hv) {                              // 32 channels at a time (register pressure)
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + 32 * hv, v);
+          tmem_ld_wait();
+          if (r < kHaloRows) {
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              uint4 o = make_uint4(0, 0, 0, 0);
+              if (inside) {
+                o.x = pack_half2(__uint_as_float(v[c4 * 8 + 0]), __uint_as_float(v[c4 * 8 + 1]), true);
+                o.y = pack_half2(__uint_as_float(v[c4 * 8 + 2]), __uint_as_float(v[c4 * 8 + 3]), true);
+                o.z = pack_half2(__uint_as_float(v[c4 * 8 + 4]), __uint_as_float(v[c4 * 8 + 5]), true);
+                o.w = pack_half2(__uint_as_float(v[c4 * 8 + 6]), __uint_as_float(v[c4 * 8 + 7]), true);
+              }
+              *reinterpret_cast<uint4*>(row + (((hv * 4 + c4) ^ sw) << 4)) = o;
             }
-            *reinterpret_cast<uint4*>(row + ((c8 ^ sw) << 4)) = o;
           }
         }
       }
@@ -1036,11 +1038,13 @@ conv1_fused_2cta_kernel(const __grid_constant__ CUtensorMap tmap_img, const __gr
       }
     };
 
+    // one warp per scheduler and role: a single warp doing both (the first version) was latency-bound at ~3000
+    // cycles per tile -- im2col of tile j+1 and the drain of tile j now run on different warps, concurrently
     int j = 0;
-    if (pair_first < n_pairs) build(0, pair_first);
-    for (int pi = pair_first; pi < n_pairs; pi += pair_step, ++j) {
-      if (pi + pair_step < n_pairs) build(j + 1, pi + pair_step);
-      drain(j, pi);
+    if (builder) {
+      for (int pi = pair_first; pi < n_pairs; pi += pair_step, ++j) build(j, pi);
+    } else {
+      for (int pi = pair_first; pi < n_pairs; pi += pair_step, ++j) drain(j, pi);
     }
   } else if (warp >= 4) {
     conv_epilogue_warps<BN, true>(p, tmem_base, epi_scratch, bias_s, tmem_full, tmem_empty, warp, lane, pair_first,
