@@ -158,11 +158,16 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvKParams& p, uint32
       const int m_own = q * 32 + lane;
       const int oy_own = tyi * p.th + (m_own >> p.tw_log2), ox_own = txi * p.tw + (m_own & (p.tw - 1));
       const bool valid_own = tile_ok && (oy_own < p.oh) && (ox_own < p.ow);
-      const size_t pix_own = (static_cast<size_t>(img) * p.oh + oy_own) * p.ow + ox_own;
+      // (the un-pooled pixel index is only needed by the residual / fp32 paths: computed there, not once per tile)
+      auto pix_own_of = [&]() { return (static_cast<size_t>(img) * p.oh + oy_own) * p.ow + ox_own; };
+      const bool pool_ok = p.pool2 && tile_ok && ((lane & 1) == 0) && ((lane & p.tw) == 0) &&
+                           ((oy_own >> 1) < (p.oh >> 1)) && ((ox_own >> 1) < (p.ow >> 1));
+      const size_t pool_pix = (static_cast<size_t>(img) * (p.oh >> 1) + (oy_own >> 1)) * (p.ow >> 1) + (ox_own >> 1);
       size_t st_pix[4];
       bool st_valid[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
+        if (p.pool2) { st_pix[k] = 0; st_valid[k] = false; continue; }            // pooled tiles store directly
         const int m = q * 32 + src_lane[k];
         const int oy = tyi * p.th + (m >> p.tw_log2), ox = txi * p.tw + (m & (p.tw - 1));
         if (p.pool2) {
@@ -175,7 +180,7 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvKParams& p, uint32
         }
       }
 
-      mbar_wait(&tmem_full[acc], acc_phase);
+      mbar_wait_relaxed(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
       uint32_t v[32];
@@ -189,7 +194,7 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvKParams& p, uint32
         if (c0 + 64 < BN) tmem_ld_32x32b_x32(taddr + c0 + 64, v);   // prefetch this warp's next chunk
         const int col0 = n0 + c0;
         if (col0 >= p.c_out) continue;   // warp-uniform
-        {
+        if (p.bias != nullptr) {        // (the fused conv1 kernel adds its bias on the tensor core: p.bias == nullptr)
           const float4* bs = reinterpret_cast<const float4*>(bias_s + col0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -198,7 +203,7 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvKParams& p, uint32
           }
         }
         if (p.residual != nullptr && valid_own) {
-          const __half* rp = p.residual + pix_own * p.y_c_stride + col0;
+          const __half* rp = p.residual + pix_own_of() * p.y_c_stride + col0;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             if (col0 + j < p.c_out) {
@@ -224,7 +229,7 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvKParams& p, uint32
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
           }
           if (valid_own) {
-            float* yp = reinterpret_cast<float*>(p.y) + pix_own * p.y_c_stride + col0;
+            float* yp = reinterpret_cast<float*>(p.y) + pix_own_of() * p.y_c_stride + col0;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               if (col0 + j < p.c_out)
@@ -251,6 +256,16 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvKParams& p, uint32
             uint32_t o2 = __shfl_xor_sync(0xffffffffu, u, p.tw);
             h[e] = __hmax2(h[e], *reinterpret_cast<__half2*>(&o2));
           }
+          // the window's representative lane (even column, even row: 8 lanes of the warp) stores its pooled pixel's 32
+          // channels itself -- 64 contiguous bytes = two full sectors per lane, no shared-memory transpose (that
+          // round trip was 128 of the ~1250 LSU wavefronts per tile of a kernel bound by the shared-memory data pipe)
+          if (pool_ok) {
+            __half* yp = reinterpret_cast<__half*>(p.y) + pool_pix * p.y_c_stride + col0;
+#pragma unroll
+            for (int u4 = 0; u4 < 4; ++u4)
+              if (col0 + u4 * 8 < p.c_out) reinterpret_cast<uint4*>(yp)[u4] = *reinterpret_cast<uint4*>(&h[4 * u4]);
+          }
+          continue;
         }
         // transpose through the warp's scratch: 80-byte row pitch makes both sides bank-conflict free
         {
@@ -353,7 +368,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int ix0 = txi * p.tw * p.stride - p.pad_w;
         const int iy0 = tyi * p.th * p.stride - p.pad_h;
         for (int g = 0; g < a_groups; ++g) {
-          mbar_wait(&a_empty[stage], phase ^ 1u);
+          mbar_wait_relaxed(&a_empty[stage], phase ^ 1u);
           uint8_t* sa = smem_a + stage * p.a_stage_bytes;
           mbar_arrive_expect_tx(&a_full[stage], p.a_tx_bytes);
           if (p.halo) {
@@ -382,7 +397,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           for (int bg = 0; bg < b_groups; ++bg) {
             const int v0 = bg * p.tb;
             const int nt = min(p.tb, taps_per_a - v0);
-            mbar_wait(&b_empty[stage], phase ^ 1u);
+            mbar_wait_relaxed(&b_empty[stage], phase ^ 1u);
             mbar_arrive_expect_tx(&b_full[stage], static_cast<uint32_t>(nt) * kBBytes);
             uint8_t* sb = smem_b + stage * b_stage_bytes;
             for (int tt = 0; tt < nt; ++tt) {
@@ -569,7 +584,7 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         const int ix0 = txi * p.tw - p.pad_w;
         const int iy0 = tyi * p.th - p.pad_h;
         for (int g = 0; g < p.n_cblk; ++g) {
-          mbar_wait(&a_empty[stage], phase ^ 1u);
+          mbar_wait_relaxed(&a_empty[stage], phase ^ 1u);
           if (rank == 0) mbar_arrive_expect_tx(&a_full[stage], 2u * p.a_tx_bytes);
           tma_load_4d_2cta(smem_a + stage * p.a_stage_bytes, &tmap_a, &a_full[stage], g * kBK, ix0, iy0, img);
           if (++stage == p.n_a_stages) { stage = 0; phase ^= 1u; }
@@ -603,7 +618,7 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         for (int g = 0; g < p.n_cblk; ++g) {
 #pragma unroll 1
           for (int bg = 0; bg < 9 / TB3; ++bg) {
-            mbar_wait(&b_empty[stage], phase ^ 1u);
+            mbar_wait_relaxed(&b_empty[stage], phase ^ 1u);
             if (rank == 0) mbar_arrive_expect_tx(&b_full[stage], 2u * TB3 * kBHalfBytes);
             uint8_t* sb = smem_b + stage * b_stage_bytes;
 #pragma unroll
@@ -705,25 +720,40 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 // stage -- resident weights, 36 MMAs per tile pair, TMEM double buffering, epilogue with the fused 2x2 max-pool --
 // is conv_igemm_2cta_kernel's.  Training keeps the two-kernel path (the backward needs conv1_1's activations).
 // ================================================================================================
-constexpr int kFusedThreads = 640;          // 4 role warps + 8 epilogue warps + 4 im2col warps + 4 drain warps
-constexpr int kFusedStemWarp0 = 12;         // warps 12..15 build im2col rows, warps 16..19 drain the stem accumulator
+// Stem warps: 4 (each builds the im2col rows of tile j+1, then drains tile j) or 8 (4 builders + 4 drainers).  Measured
+// on the B200: 8 is SLOWER (628 vs 714 TFLOP/s for the layer pair) -- the kernel's limit is the shared-memory data
+// pipe, not those warps' instruction streams, and four more polling / storing warps only add to it.
+constexpr bool kFusedSplitStem = false;
+constexpr int kFusedThreads = kFusedSplitStem ? 640 : 512;   // 4 role warps + 8 epilogue warps + 4 (8) stem warps
+constexpr int kFusedStemWarp0 = 12;
 constexpr int kHaloH = 18, kHaloW = 10, kHaloRows = kHaloH * kHaloW;      // conv1_2's 16 x 8 tile + 1 pixel border
-constexpr int kPatchH = 20, kPatchW = 16;                                 // conv1_1's input for that halo: 12 columns
-                                                                          // needed, 16 loaded (16-byte aligned start)
+constexpr int kPatchH = 20, kPatchW = 24;                                 // conv1_1's input for that halo: 12 columns
+                                                                          // needed; the box starts 4 columns early
+                                                                          // (16-byte aligned) and is 24 wide so that
+                                                                          // the 4 patch rows a warp's 32 halo pixels
+                                                                          // touch fall into different banks (a
+                                                                          // 16-float pitch puts rows y, y+2 on top of
+                                                                          // each other: 2-way conflicts, measured)
 constexpr int kPatchXOff = 2;                                             // needed column 0 = loaded column 2 (fp32)
 constexpr int kPatchU8Bytes = 96;                                         // uint8: 32 pixels x 3 bytes per patch row
 constexpr int kStemKPad = 32, kStemSbo = kStemKPad * 16;                  // K = 27 + 2 bias columns -> 32
 constexpr int kColBufBytes = 2 * 16 * kStemSbo;                           // two 128-row blocks per CTA
-constexpr int kPatchStageBytes = 4096;                                    // >= 3*20*16*4 (fp32) / 20*96 (uint8)
+constexpr int kPatchStageBytes = 6144;                                    // >= 3*20*24*4 (fp32) / 20*96 (uint8)
 constexpr int kPatchStages = 3;
 constexpr int kFusedAStages = 4;
 
 // Bounded wait that records WHICH wait timed out (code, block, thread) in a host-mapped word before trapping: after a
 // trap the context is gone, but the pinned host word survives (DIN_FUSED_DEBUG=1, read back by din_debug_word()).
+template <bool kTight>
 __device__ __forceinline__ void mbar_wait_code(uint64_t* bar, uint32_t parity, unsigned int* dbg, unsigned int code) {
+  if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (dbg ? (1u << 22) : (1u << 26))) {
+    // even the MMA issuer backs off a little: in this kernel it waits most of the time (the shared-memory data pipe is
+    // the limit) and its polls are shared-memory traffic too
+    if (kTight) asm volatile("nanosleep.u32 32;" ::: "memory");
+    else asm volatile("nanosleep.u32 256;" ::: "memory");
+    if (++spins > (dbg ? (1u << 21) : (1u << 25))) {
       if (dbg) {
         atomicCAS_system(dbg, 0u, (code << 24) | ((blockIdx.x & 0xFFFu) << 12) | (threadIdx.x & 0xFFFu));
         dbg[1 + (code & 31u)] = (static_cast<unsigned int>(parity) << 31) | (blockIdx.x << 12) | threadIdx.x;
@@ -737,6 +767,7 @@ __device__ __forceinline__ void mbar_wait_code(uint64_t* bar, uint32_t parity, u
 struct FusedStemParams {
   const float* w1;       // [64][3][3][3] fp32 (OIHW)
   const float* b1;       // [64]
+  const float* b2;       // conv1_2 bias [64] or NULL: added by one extra K = 16 MMA (ones x [bias_hi, bias_lo])
   int img_h, img_w, n_img;
   int prep;              // apply prep_images to the raw pixel values
   unsigned int* dbg;     // host-mapped debug words (DIN_FUSED_DEBUG=1) or NULL
@@ -756,7 +787,9 @@ conv1_fused_2cta_kernel(const __grid_constant__ CUtensorMap tmap_img, const __gr
   uint8_t* smem_b = smem_a + kFusedAStages * p.a_stage_bytes;               // resident conv1_2 weights (this CTA's half)
   uint8_t* col_s = smem_b + b_stage_bytes;                                  // 2 x im2col buffers (canonical layout)
   uint8_t* w1_s = col_s + 2 * kColBufBytes;                                 // stem weights, this CTA's 32 rows
-  uint8_t* patch_s = w1_s + 4 * kStemSbo;                                   // kPatchStages x raw input patches
+  uint8_t* ones_s = w1_s + 4 * kStemSbo;                                    // A of the bias MMA: 128 rows x K = 16, columns 0, 1 = 1
+  uint8_t* b2_s = ones_s + 4096;                                            // B of the bias MMA: this CTA's 32 rows x [hi, lo, 0..]
+  uint8_t* patch_s = b2_s + 1024;                                           // kPatchStages x raw input patches
   uint8_t* epi_scratch = patch_s + kPatchStages * kPatchStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_scratch + kNumEpiWarps * kEpiScratch);
   uint64_t* a_full = bars;                       // [4]  leader: 8 warp arrivals (4 stem warps x 2 CTAs)
@@ -818,6 +851,26 @@ conv1_fused_2cta_kernel(const __grid_constant__ CUtensorMap tmap_img, const __gr
       }
       *reinterpret_cast<uint4*>(w1_s + canon_off(o_local, kc, kStemSbo)) = *reinterpret_cast<const uint4*>(hv);
     }
+    // conv1_2's bias rides on the tensor core too: D (+)= ones[128 x 16] x b2[64 x 16]^T with ones columns 0, 1 = 1 and
+    // b2 columns 0, 1 = the bias's hi / lo fp16 parts -- one K = 16 MMA per tile instead of 8 shared-memory loads and 32
+    // adds per epilogue thread.  Both tiles: no-swizzle K-major, K chunk planes 2048 B (A) / 512 B (B) apart, rows 16 B.
+    {
+      // columns (1, 2^-11) against (bias_hi, bias_lo * 2^11): the lo part of a bias of magnitude 0.1 is ~5e-5, an fp16
+      // subnormal; scaled by 2^11 both factors are normal numbers and the product is the same
+      const uint32_t one_eps = 0x10003C00u;                       // fp16 (1, 2^-11)
+      reinterpret_cast<uint4*>(ones_s)[st] = make_uint4(one_eps, 0u, 0u, 0u);          // chunk 0 of row st
+      reinterpret_cast<uint4*>(ones_s + 2048)[st] = make_uint4(0u, 0u, 0u, 0u);        // chunk 1
+      if (st < 64) {
+        const int o_local = st & 31, kc = st >> 5;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (kc == 0 && sp.b2 != nullptr) {
+          const float bv = __ldg(sp.b2 + rank * (BN / 2) + o_local);
+          const float bh = __half2float(__float2half_rn(bv));
+          v.x = pack_half2(bh, (bv - bh) * 2048.0f, false);
+        }
+        reinterpret_cast<uint4*>(b2_s + kc * 512)[o_local] = v;
+      }
+    }
     fence_proxy_async_smem();
   }
   if (warp == 1) tmem_alloc_2cta<kTmemCols>(tmem_ptr_smem);
@@ -838,7 +891,7 @@ conv1_fused_2cta_kernel(const __grid_constant__ CUtensorMap tmap_img, const __gr
         const int tyi = fdiv(r, p.fd_tx);
         const int txi = r - tyi * p.tiles_x;
         const int ps = j % kPatchStages;
-        mbar_wait_code(&patch_empty[ps], (((j / kPatchStages) & 1) ^ 1), sp.dbg, 1u /*patch_empty*/);
+        mbar_wait_code<false>(&patch_empty[ps], (((j / kPatchStages) & 1) ^ 1), sp.dbg, 1u /*patch_empty*/);
         if constexpr (U8) {
           mbar_arrive_expect_tx(&patch_full[ps], static_cast<uint32_t>(kPatchH * kPatchU8Bytes));
           tma_load_3d(patch_s + ps * kPatchStageBytes, &tmap_img, &patch_full[ps], ((txi * p.tw - 2) & ~15) * 3,
@@ -869,12 +922,13 @@ conv1_fused_2cta_kernel(const __grid_constant__ CUtensorMap tmap_img, const __gr
       const uint32_t b_lo = desc_lo(smem_u32(smem_b));
       const uint32_t a_step = static_cast<uint32_t>(p.a_stage_bytes) >> 4;
       const uint32_t col_addr = smem_u32(col_s), w1_addr = smem_u32(w1_s);
+      const uint32_t ones_addr = smem_u32(ones_s), b2_addr = smem_u32(b2_s);
       // stem MMAs of local iteration j: im2col buffer / stem accumulator j & 1
       auto issue_stem = [&](int j) {
         const int cb = j & 1;
         const uint32_t use = static_cast<uint32_t>(j >> 1);           // k-th use of this buffer
-        mbar_wait_code(&col_full[cb], use & 1u, sp.dbg, 2u /*col_full*/);
-        if (use > 0) mbar_wait_code(&stem_free[cb], (use - 1u) & 1u, sp.dbg, 3u /*stem_free*/);      // the previous result has been drained
+        mbar_wait_code<true>(&col_full[cb], use & 1u, sp.dbg, 2u /*col_full*/);
+        if (use > 0) mbar_wait_code<true>(&stem_free[cb], (use - 1u) & 1u, sp.dbg, 3u /*stem_free*/);      // the previous result has been drained
         tc_fence_after_sync();
         if (leader) {
 #pragma unroll
@@ -897,21 +951,21 @@ conv1_fused_2cta_kernel(const __grid_constant__ CUtensorMap tmap_img, const __gr
       for (int pi = pair_first; pi < n_pairs; pi += pair_step, ++it) {
         if (pi + pair_step < n_pairs) issue_stem(it + 1);             // one tile ahead: its drain overlaps these MMAs
         const int acc = it & 1;
-        mbar_wait_code(&tmem_empty[acc], ((it >> 1) & 1u) ^ 1u, sp.dbg, 4u /*tmem_empty*/);
-        mbar_wait_code(&a_full[sa], pa, sp.dbg, 5u /*a_full*/);
-        if (it == 0) mbar_wait_code(&b_full[0], 0, sp.dbg, 6u /*b_full*/);
+        mbar_wait_code<true>(&tmem_empty[acc], ((it >> 1) & 1u) ^ 1u, sp.dbg, 4u /*tmem_empty*/);
+        mbar_wait_code<true>(&a_full[sa], pa, sp.dbg, 5u /*a_full*/);
+        if (it == 0) mbar_wait_code<true>(&b_full[0], 0, sp.dbg, 6u /*b_full*/);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
         const uint32_t a_lo = a_lo0 + sa * a_step;
         if (leader) {
+          umma_f16_ss_2cta(d_tmem, desc_noswz(ones_addr, 2048, 128), desc_noswz(b2_addr, 512, 128), idesc, 0u);   // = bias
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
             const uint32_t al = a_lo + static_cast<uint32_t>(((t / 3) * 10 + (t % 3)) * 8);
             const uint32_t bl = b_lo + static_cast<uint32_t>(t * (kBHalfBytes >> 4));
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k)
-              umma_f16_ss_2cta(d_tmem, desc64(al + 2u * k, a_hi), desc64(bl + 2u * k, b_hi), idesc,
-                               (t == 0 && k == 0) ? 0u : 1u);
+              umma_f16_ss_2cta(d_tmem, desc64(al + 2u * k, a_hi), desc64(bl + 2u * k, b_hi), idesc, 1u);
           }
           umma_commit_2cta(&a_empty[sa]);
           umma_commit_2cta(&tmem_full[acc]);
@@ -921,7 +975,7 @@ conv1_fused_2cta_kernel(const __grid_constant__ CUtensorMap tmap_img, const __gr
     }
   } else if (warp >= kFusedStemWarp0) {
     // ------------------------------------------------------------------ stem warps: im2col build + accumulator drain
-    const bool builder = warp < kFusedStemWarp0 + 4;
+    const bool builder = warp < kFusedStemWarp0 + 4;          // split mode only
     const int st = (threadIdx.x - 32 * kFusedStemWarp0) & 127;    // 0..127 within the role
     const int q = warp & 3;                                   // TMEM lane quadrant of this warp
 
@@ -939,8 +993,8 @@ conv1_fused_2cta_kernel(const __grid_constant__ CUtensorMap tmap_img, const __gr
       tile_of(pi, img, tyi, txi);
       const int ps = j % kPatchStages, cb = j & 1;
       const uint32_t use = static_cast<uint32_t>(j >> 1);
-      if (use > 0) mbar_wait_code(&stem_done[cb], (use - 1u) & 1u, sp.dbg, 7u /*stem_done*/);       // the MMAs that read this buffer have retired
-      mbar_wait_code(&patch_full[ps], (j / kPatchStages) & 1, sp.dbg, 8u /*patch_full*/);
+      if (use > 0) mbar_wait_code<false>(&stem_done[cb], (use - 1u) & 1u, sp.dbg, 7u /*stem_done*/);       // the MMAs that read this buffer have retired
+      mbar_wait_code<false>(&patch_full[ps], (j / kPatchStages) & 1, sp.dbg, 8u /*patch_full*/);
       const uint8_t* patch = patch_s + ps * kPatchStageBytes;
       const int gy0 = tyi * p.th - 2, gx0 = txi * p.tw - 2;           // image coordinates of the first NEEDED patch element
       const int xoff = U8 ? (gx0 - (gx0 & ~15)) : kPatchXOff;         // its column in the (wider, aligned) loaded box
@@ -993,8 +1047,8 @@ conv1_fused_2cta_kernel(const __grid_constant__ CUtensorMap tmap_img, const __gr
       int img, tyi, txi;
       tile_of(pi, img, tyi, txi);
       const int cb = j & 1, as = j % kFusedAStages;
-      mbar_wait_code(&stem_done[cb], static_cast<uint32_t>(j >> 1) & 1u, sp.dbg, 9u /*stem_done*/);
-      mbar_wait_code(&a_empty[as], ((j / kFusedAStages) & 1) ^ 1, sp.dbg, 10u /*a_empty*/);
+      mbar_wait_code<false>(&stem_done[cb], static_cast<uint32_t>(j >> 1) & 1u, sp.dbg, 9u /*stem_done*/);
+      mbar_wait_code<false>(&a_empty[as], ((j / kFusedAStages) & 1) ^ 1, sp.dbg, 10u /*a_empty*/);
       tc_fence_after_sync();
       uint8_t* a_stage = smem_a + as * p.a_stage_bytes;
       const int oy0 = tyi * p.th - 1, ox0 = txi * p.tw - 1;           // conv1_1 output coordinates of halo pixel (0, 0)
@@ -1038,13 +1092,19 @@ conv1_fused_2cta_kernel(const __grid_constant__ CUtensorMap tmap_img, const __gr
       }
     };
 
-    // one warp per scheduler and role: a single warp doing both (the first version) was latency-bound at ~3000
-    // cycles per tile -- im2col of tile j+1 and the drain of tile j now run on different warps, concurrently
     int j = 0;
-    if (builder) {
-      for (int pi = pair_first; pi < n_pairs; pi += pair_step, ++j) build(j, pi);
+    if constexpr (kFusedSplitStem) {
+      if (builder) {
+        for (int pi = pair_first; pi < n_pairs; pi += pair_step, ++j) build(j, pi);
+      } else {
+        for (int pi = pair_first; pi < n_pairs; pi += pair_step, ++j) drain(j, pi);
+      }
     } else {
-      for (int pi = pair_first; pi < n_pairs; pi += pair_step, ++j) drain(j, pi);
+      if (pair_first < n_pairs) build(0, pair_first);
+      for (int pi = pair_first; pi < n_pairs; pi += pair_step, ++j) {
+        if (pi + pair_step < n_pairs) build(j + 1, pi + pair_step);
+        drain(j, pi);
+      }
     }
   } else if (warp >= 4) {
     conv_epilogue_warps<BN, true>(p, tmem_base, epi_scratch, bias_s, tmem_full, tmem_empty, warp, lane, pair_first,
@@ -1339,7 +1399,8 @@ extern "C" int din_conv3x3_stem_pair_nhwc_f16(const void* x, int x_is_u8, const 
   p.relu = relu2; p.out_f32 = 0; p.pool2 = pool2;
   p.split = 1; p.k_part = 9 * kBK;
   p.fd_ntn = make_fastdiv(1); p.fd_tpi = make_fastdiv(p.tiles_per_img); p.fd_tx = make_fastdiv(p.tiles_x);
-  p.bias = b2; p.residual = nullptr; p.res_mask = 0; p.y = y;
+  p.bias = nullptr;            // conv1_2's bias is added by the kernel's bias MMA (FusedStemParams.b2)
+  p.residual = nullptr; p.res_mask = 0; p.y = y;
   p.halo = 1; p.halo_rows = kHaloH; p.pitch_rows = kHaloW; p.per_row_loads = 0; p.use_base_offset = 0;
   p.a_stage_bytes = ((kHaloRows * 128) + 1023) & ~1023;
   p.a_tx_bytes = 0;
@@ -1375,14 +1436,15 @@ extern "C" int din_conv3x3_stem_pair_nhwc_f16(const void* x, int x_is_u8, const 
     if (rc != DIN_OK) return rc;
   }
   FusedStemParams sp{};
-  sp.w1 = w1; sp.b1 = b1; sp.img_h = h; sp.img_w = w; sp.n_img = n; sp.prep = prep;
+  sp.w1 = w1; sp.b1 = b1; sp.b2 = b2; sp.img_h = h; sp.img_w = w; sp.n_img = n; sp.prep = prep;
   sp.dbg = fused_debug_words();
   const int sms = din_num_sms();
   DIN_CHECK_ARG(sms > 0, "%s: no CUDA device", who);
   const int pairs = (p.num_tiles + 1) / 2;
   const int grid = 2 * (pairs < sms / 2 ? pairs : sms / 2);
   const size_t smem = static_cast<size_t>(kFusedAStages) * p.a_stage_bytes + 9 * (BN / 2) * kBK * 2 + 2 * kColBufBytes +
-                      4 * kStemSbo + kPatchStages * kPatchStageBytes + kNumEpiWarps * kEpiScratch + 1024 /*align*/ +
+                      4 * kStemSbo + 4096 + 1024 /*bias MMA tiles*/ + kPatchStages * kPatchStageBytes +
+                      kNumEpiWarps * kEpiScratch + 1024 /*align*/ +
                       32 * 8 /*barriers*/ + 16 + BN * 4;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (x_is_u8) {

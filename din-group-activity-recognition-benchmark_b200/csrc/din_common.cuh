@@ -147,12 +147,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a mis-programmed pipeline traps (launch fails with an error the host reports)
-// instead of hanging the device. try_wait sleeps in hardware, so the bound is generous.
+// Bounded waits: a mis-programmed pipeline traps (launch fails with an error the host reports) instead of hanging the
+// device.
+//   mbar_wait          tight poll: for the one warp whose wake-up latency is on the critical path (the MMA issuer).
+//   mbar_wait_relaxed  poll, then back off with nanosleep: for every other role.  An mbarrier poll is a shared-memory
+//                      operation plus ~4 instructions of loop; ncu on the fused conv1 kernel counted ~640 polls and
+//                      ~2800 poll-loop instructions per tile from its ~15 waiting warps -- a quarter of the LSU
+//                      wavefronts of a kernel whose limit IS the shared-memory data pipe (tensor-core operand reads +
+//                      LSU traffic = 1 wavefront per cycle), and half of all instructions issued.  (try_wait's
+//                      suspend-time hint was tried first: on this part it does not lengthen the hardware wait.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    asm volatile("nanosleep.u32 256;" ::: "memory");
+    if (++spins > (1u << 24)) __trap();
   }
 }
 

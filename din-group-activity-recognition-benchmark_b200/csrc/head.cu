@@ -10,6 +10,9 @@
 //   fusion + dpi_nl           infer_model.py:203-216 (volleyball), :1298-1301 (collective)
 //   read-out                  infer_model.py:224-232 (volleyball), :1311-1313 (collective)
 #include <cfloat>
+#include <cstdlib>
+
+#include <cooperative_groups.h>
 
 #include "din_common.cuh"
 #include "din_head.cuh"
@@ -317,6 +320,193 @@ dynamic_infer_kernel(const float* __restrict__ x, const float* __restrict__ w_ta
 }
 
 // ================================================================================================
+// The same step, parallel over channels: a thread-block CLUSTER per (clip, frame group).
+//
+// dynamic_infer_kernel above runs one CTA per (clip, frame): 80 CTAs for the bench's 8 clips, each streaming the whole
+// tap-major weight (1 MB at C = 1024) from L2 through dependent loads -- ncu: 161 us at C = 1024 and 28 us at C = 128
+// with 12 % of the warp slots active, for 0.5 GFLOP and 9 MB of compulsory traffic.  Here the channel dimension is
+// split over the CTAs of a cluster (C/8 channels each at C = 1024, C/2 at C = 128) and the frames of a clip over
+// `n_tg` clusters, so that the launch fills the chip:
+//   load     each CTA stages the clip's whole [T][N][chunk] channel slice (zero beyond the clip's real actors) and its
+//            [k2][n_out][chunk] slice of the weight in shared memory ONCE (coalesced 16-byte loads, all in flight);
+//   phase 1  partial affinity-conv sums over the CTA's channels for its frames' actors: a warp owns 4 of the 3k2
+//            outputs, lanes sweep channels, __shfl_xor reductions (as before);
+//   exchange the partial sums are combined across the cluster through DISTRIBUTED SHARED MEMORY in rank order
+//            (every CTA reads all ranks' partials: identical, deterministic totals everywhere), + bias;
+//   phase 2  every CTA applies the now complete offsets / relation weights to ITS channels: softmax over the taps,
+//            detached floor, clamp-then-weight corners, all gathers served from the staged slab in shared memory.
+// Identical arithmetic per element except the association of the conv sums over channel chunks.
+// ================================================================================================
+namespace cg = cooperative_groups;
+
+__global__ void __launch_bounds__(kDinThreads)
+dynamic_infer_cluster_kernel(const float* __restrict__ x, const float* __restrict__ w_tap,
+                             const float* __restrict__ b_cat, float* __restrict__ y, int T, int N, int C, int kt, int kn,
+                             int ratio, int scale_factor, const float* __restrict__ coef_ptr, float coef_scalar,
+                             int accumulate, const int* __restrict__ n_valid, int n_tg, int chunk, int f_max) {
+  extern __shared__ float smem_f[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = static_cast<int>(cluster.block_rank());        // channel chunk
+  const int n_chunks = static_cast<int>(cluster.num_blocks());
+  const int b = blockIdx.y / n_tg, tg = blockIdx.y - b * n_tg;
+  const int t0 = (tg * T) / n_tg, t1 = ((tg + 1) * T) / n_tg;     // frames of this cluster
+  const int c0 = rank * chunk;
+  const int Nb = n_valid ? min(__ldg(n_valid + b), N) : N;
+  const int k2 = kt * kn;
+  const int n_out = scale_factor ? 3 * k2 : 2 * k2;
+  const int pt = (kt - 1) / 2 * ratio, pl = (kn - 1) / 2 * ratio;
+  const int dy0 = -(((kt - 1) * ratio + 1) / 2);
+  const int dx0 = -(((kn - 1) * ratio + 1) / 2);
+  const int ch4 = chunk >> 2;
+  float* slab = smem_f;                                            // [T][N][chunk]
+  float* wts = slab + static_cast<size_t>(T) * N * chunk;          // [k2][n_out][chunk]
+  float* part = wts + static_cast<size_t>(k2) * n_out * chunk;     // [f_max * N][n_out] this CTA's partial sums
+  float* conv_s = part + static_cast<size_t>(f_max) * N * n_out;   // [f_max * N][n_out] totals (+ bias)
+  const float* xb = x + static_cast<size_t>(b) * T * N * C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- load: the clip's channel slice and this CTA's weight slice
+  for (int i = threadIdx.x; i < T * N * ch4; i += kDinThreads) {
+    const int c4 = i % ch4, tn = i / ch4;
+    const int n = tn % N;
+    float4 v = make_float4(0, 0, 0, 0);
+    if (n < Nb) v = __ldg(reinterpret_cast<const float4*>(xb + static_cast<size_t>(tn) * C + c0) + c4);
+    reinterpret_cast<float4*>(slab)[i] = v;
+  }
+  for (int i = threadIdx.x; i < k2 * n_out * ch4; i += kDinThreads) {
+    const int c4 = i % ch4, row = i / ch4;
+    reinterpret_cast<float4*>(wts)[i] = __ldg(reinterpret_cast<const float4*>(w_tap + static_cast<size_t>(row) * C + c0) + c4);
+  }
+  __syncthreads();
+
+  // ---- phase 1: partial conv sums over this CTA's channels, frame by frame
+  for (int t = t0; t < t1; ++t) {
+    float acc[kDinMaxOutPerWarp][kDinMaxN];
+#pragma unroll
+    for (int a = 0; a < kDinMaxOutPerWarp; ++a)
+#pragma unroll
+      for (int n = 0; n < kDinMaxN; ++n) acc[a][n] = 0.0f;
+    for (int ky = 0; ky < kt; ++ky) {
+      const int tt = t + dy0 + ky * ratio;
+      if (tt < 0 || tt >= T) continue;                             // zero rows outside the clip
+      const float* xrow = slab + static_cast<size_t>(tt) * N * chunk;
+      for (int kx = 0; kx < kn; ++kx) {
+        const int dx = dx0 + kx * ratio;
+        const float* wt = wts + static_cast<size_t>(ky * kn + kx) * n_out * chunk;
+        for (int c4 = lane; c4 < ch4; c4 += 32) {
+          float4 wv[kDinMaxOutPerWarp];
+#pragma unroll
+          for (int a = 0; a < kDinMaxOutPerWarp; ++a) {
+            const int o = warp + a * kDinWarps;
+            wv[a] = (o < n_out) ? reinterpret_cast<const float4*>(wt + static_cast<size_t>(o) * chunk)[c4]
+                                : make_float4(0, 0, 0, 0);
+          }
+#pragma unroll
+          for (int n = 0; n < kDinMaxN; ++n) {
+            const int nn = n + dx;
+            if (n < Nb && nn >= 0 && nn < Nb) {
+              const float4 xv = reinterpret_cast<const float4*>(xrow + static_cast<size_t>(nn) * chunk)[c4];
+#pragma unroll
+              for (int a = 0; a < kDinMaxOutPerWarp; ++a) {
+                acc[a][n] = fmaf(wv[a].x, xv.x, acc[a][n]);
+                acc[a][n] = fmaf(wv[a].y, xv.y, acc[a][n]);
+                acc[a][n] = fmaf(wv[a].z, xv.z, acc[a][n]);
+                acc[a][n] = fmaf(wv[a].w, xv.w, acc[a][n]);
+              }
+            }
+          }
+        }
+      }
+    }
+    float* pf = part + static_cast<size_t>(t - t0) * N * n_out;
+#pragma unroll
+    for (int a = 0; a < kDinMaxOutPerWarp; ++a) {
+      const int o = warp + a * kDinWarps;
+#pragma unroll
+      for (int n = 0; n < kDinMaxN; ++n) {
+        const float v = warp_sum(acc[a][n]);
+        if (lane == 0 && o < n_out && n < Nb) pf[n * n_out + o] = v;
+      }
+    }
+  }
+
+  // ---- exchange: totals = sum over the cluster's ranks (in rank order) + bias
+  cluster.sync();
+  {
+    const int total = (t1 - t0) * N * n_out;
+    for (int i = threadIdx.x; i < total; i += kDinThreads) {
+      const int n = (i / n_out) % N;
+      if (n >= Nb) continue;
+      float s = 0.0f;
+      for (int r = 0; r < n_chunks; ++r) s += cluster.map_shared_rank(part, r)[i];
+      conv_s[i] = s + __ldg(b_cat + (i % n_out));
+    }
+  }
+  cluster.sync();                                                  // nobody overwrites / leaves while peers still read
+
+  // ---- phase 2: one warp per (frame, actor), this CTA's channels
+  const float coef = coef_ptr ? __ldg(coef_ptr) : coef_scalar;
+  const int Hp = T + 2 * pt;
+  const int Wp_b = Nb + 2 * pl;
+  const int nodes = (t1 - t0) * Nb;
+  for (int node = warp; node < nodes; node += kDinWarps) {
+    const int tf = node / Nb, n = node - tf * Nb;
+    const int t = t0 + tf;
+    const float* cs = conv_s + (static_cast<size_t>(tf) * N + n) * n_out;
+    float rel[kDinMaxK2];
+    if (scale_factor) {
+      float mx = -FLT_MAX;
+      for (int k = 0; k < k2; ++k) mx = fmaxf(mx, cs[2 * k2 + k]);
+      float den = 0.0f;
+      for (int k = 0; k < k2; ++k) { rel[k] = expf(cs[2 * k2 + k] - mx); den += rel[k]; }
+      for (int k = 0; k < k2; ++k) rel[k] = rel[k] / den;
+    } else {
+      for (int k = 0; k < k2; ++k) rel[k] = 1.0f / static_cast<float>(k2);
+    }
+    float* yp = y + ((static_cast<size_t>(b) * T + t) * N + n) * C + c0;
+    for (int c4 = lane; c4 < ch4; c4 += 32) {
+      float4 o = make_float4(0, 0, 0, 0);
+      for (int ky = 0; ky < kt; ++ky) {
+        for (int kx = 0; kx < kn; ++kx) {
+          const int k = ky * kn + kx;
+          float py = static_cast<float>(pt + t + dy0 + ky * ratio) + cs[k];
+          float px = static_cast<float>(pl + n + dx0 + kx * ratio) + cs[k2 + k];
+          float ly = floorf(py), lx = floorf(px);
+          float ry = ly + 1.0f, rx = lx + 1.0f;
+          const float my = static_cast<float>(Hp - 1), mxx = static_cast<float>(Wp_b - 1);
+          ly = fminf(fmaxf(ly, 0.0f), my); ry = fminf(fmaxf(ry, 0.0f), my); py = fminf(fmaxf(py, 0.0f), my);
+          lx = fminf(fmaxf(lx, 0.0f), mxx); rx = fminf(fmaxf(rx, 0.0f), mxx); px = fminf(fmaxf(px, 0.0f), mxx);
+          const float wly = 1.0f - fabsf(py - ly), wry = 1.0f - fabsf(py - ry);
+          const float wlx = 1.0f - fabsf(px - lx), wrx = 1.0f - fabsf(px - rx);
+          const int ily = static_cast<int>(ly) - pt, iry = static_cast<int>(ry) - pt;
+          const int ilx = static_cast<int>(lx) - pl, irx = static_cast<int>(rx) - pl;
+          auto fetch = [&](int ty, int tx) -> float4 {
+            if (ty < 0 || ty >= T || tx < 0 || tx >= Nb) return make_float4(0, 0, 0, 0);
+            return reinterpret_cast<const float4*>(slab + (static_cast<size_t>(ty) * N + tx) * chunk)[c4];
+          };
+          const float4 lt = fetch(ily, ilx), rb = fetch(iry, irx), lb = fetch(iry, ilx), rt = fetch(ily, irx);
+          const float wlt = wly * wlx, wrb = wry * wrx, wlb = wry * wlx, wrt = wly * wrx;
+          // reference order: lt + rb + lb + rt, then * relation, summed over taps (:255-258, :278)
+          const float fx = ((lt.x * wlt + rb.x * wrb) + lb.x * wlb) + rt.x * wrt;
+          const float fy = ((lt.y * wlt + rb.y * wrb) + lb.y * wlb) + rt.y * wrt;
+          const float fz = ((lt.z * wlt + rb.z * wrb) + lb.z * wlb) + rt.z * wrt;
+          const float fw = ((lt.w * wlt + rb.w * wrb) + lb.w * wlb) + rt.w * wrt;
+          o.x += fx * rel[k]; o.y += fy * rel[k]; o.z += fz * rel[k]; o.w += fw * rel[k];
+        }
+      }
+      float4* dst = reinterpret_cast<float4*>(yp) + c4;
+      if (accumulate) {
+        const float4 prev = *dst;
+        o.x = prev.x + coef * o.x; o.y = prev.y + coef * o.y; o.z = prev.z + coef * o.z; o.w = prev.w + coef * o.w;
+      } else {
+        o.x *= coef; o.y *= coef; o.z *= coef; o.w *= coef;
+      }
+      *dst = o;
+    }
+  }
+}
+
+// ================================================================================================
 // read-out: max over actors -> fc_activities -> mean over frames     (one CTA per clip)
 // ================================================================================================
 constexpr int kRoThreads = 256;
@@ -443,6 +633,45 @@ extern "C" int din_dynamic_infer_f32(const float* x, const float* w_tap, const f
   DIN_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
                   reinterpret_cast<uintptr_t>(w_tap)) & 15) == 0,
                 "din_dynamic_infer_f32: pointers must be 16-byte aligned");
+  // ---- cluster formulation (channels over the CTAs of a cluster, frames over clusters): whenever the channel count
+  //      splits into 2 / 4 / 8 chunks of a multiple of 32 channels and the staged slices fit shared memory
+  {
+    static const bool use_cluster = [] { const char* e = std::getenv("DIN_DI_CLUSTER"); return !(e && e[0] == '0'); }();
+    int n_chunks = 0;
+    for (int cand = 8; cand >= 2; cand >>= 1)
+      if (c % (cand * 32) == 0 && c / cand >= 64) { n_chunks = cand; break; }
+    if (use_cluster && n_chunks > 0) {
+      const int chunk = c / n_chunks;
+      const int sms = din_num_sms();
+      int n_tg = (2 * (sms > 0 ? sms : 148) + b * n_chunks - 1) / (b * n_chunks);     // ~2 CTAs per SM over the launch
+      if (n_tg > t) n_tg = t;
+      if (n_tg < 1) n_tg = 1;
+      auto smem_for = [&](int tg) {
+        const int f_max = (t + tg - 1) / tg;
+        return (static_cast<size_t>(t) * n * chunk + static_cast<size_t>(kt) * kn * n_out * chunk +
+                2 * static_cast<size_t>(f_max) * n * n_out) * sizeof(float);
+      };
+      while (n_tg < t && smem_for(n_tg) > 200 * 1024) ++n_tg;
+      const size_t smem_c = smem_for(n_tg);
+      if (smem_c <= 200 * 1024) {
+        const int f_max = (t + n_tg - 1) / n_tg;
+        DIN_OPT_IN_SMEM(dynamic_infer_cluster_kernel, smem_c);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(n_chunks, b * n_tg, 1);
+        cfg.blockDim = dim3(kDinThreads, 1, 1);
+        cfg.dynamicSmemBytes = smem_c;
+        cfg.stream = static_cast<cudaStream_t>(stream);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = n_chunks; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        DIN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dynamic_infer_cluster_kernel, x, w_tap, b_cat, y, t, n, c, kt, kn, ratio,
+                                          scale_factor, coef_ptr, coef_scalar, accumulate,
+                                          static_cast<const int*>(n_valid), n_tg, chunk, f_max));
+        return DIN_OK;
+      }
+    }
+  }
   const size_t smem = (static_cast<size_t>(kt) * n * c + static_cast<size_t>(n) * n_out) * sizeof(float);
   DIN_CHECK_ARG(smem <= 220 * 1024, "din_dynamic_infer_f32: kt*n*c too large for shared memory (%zu bytes)", smem);
   DIN_OPT_IN_SMEM(dynamic_infer_kernel, smem);

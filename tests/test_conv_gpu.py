@@ -212,9 +212,11 @@ def test_batched_packing_matches_single_packs_and_dgrad_filters(cuda):
                          ids=lambda v: str(v))
 def test_stem_pair_fused_equals_the_two_kernel_path(cuda, n, h, w, pool, u8):
     """conv1_1 + conv1_2 in one launch (conv1_fused_2cta_kernel: the stem computed inside conv1_2's A producer) must
-    reproduce the stand-alone stem followed by the CTA-pair convolution -- the same fp16 roundings in the same places,
-    so the comparison is on bits (one fp16 ulp is tolerated on at most 1e-5 of the elements, should a tensor-core
-    accumulation order differ between M = 128 and M = 256 instructions) -- and both match fp32 torch.  Shapes cover
+    reproduce the stand-alone stem followed by the CTA-pair convolution: conv1_1's values are bit-identical (same
+    im2col, same K order, same fp16 rounding), conv1_2's differ only in WHERE its bias joins the fp32 sum (first, on the
+    tensor core, instead of last, in the epilogue), i.e. by at most one fp16 ulp on a small fraction of the elements
+    (with the bias in the epilogue the two paths were bit-identical on all 45 M elements of these cases) -- and both
+    match fp32 torch.  Shapes cover
     ragged tiles (h % 16, w % 8 != 0), odd tile counts (an idle second CTA in the last pair), uint8 frames, 720p."""
     from din_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(11)
@@ -234,7 +236,11 @@ def test_stem_pair_fused_equals_the_two_kernel_path(cuda, n, h, w, pool, u8):
     diff = (got.float() - want.float()).abs()
     n_diff = int((diff > 0).sum())
     print(f"\n[stem pair] {n}x{h}x{w} pool={pool} u8={u8}: {n_diff} of {diff.numel()} elements differ, max |diff| {diff.max().item():.3e}")
-    assert n_diff <= 1e-5 * diff.numel() and diff.max().item() <= 2e-3 * want.float().abs().max().item()
+    # one fp16 ulp at each element's magnitude, or -- for outputs near zero, where an fp16 ulp is far below the fp32
+    # rounding of a 577-term sum of O(1) terms -- 1e-5 absolute
+    tol = (want.float().abs() * 2.0 ** -10).clamp_min(1e-5)
+    assert n_diff <= 2e-3 * diff.numel(), n_diff
+    assert bool((diff <= tol).all()), float((diff / tol).max())
     if h * w <= 128 * 128:
         xp = ((img.float().to(cuda) / 255.0) - 0.5) * 2.0
         ref = F.relu(F.conv2d(F.relu(F.conv2d(xp, w1, b1, padding=1)), w2, b2, padding=1))
