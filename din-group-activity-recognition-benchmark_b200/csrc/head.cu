@@ -365,18 +365,28 @@ dynamic_infer_cluster_kernel(const float* __restrict__ x, const float* __restric
   const float* xb = x + static_cast<size_t>(b) * T * N * C;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // ---- load: the clip's channel slice and this CTA's weight slice
+  // ---- load: the clip's channel slice and this CTA's weight slice, as asynchronous 16-byte copies (cp.async): every
+  //      copy of the CTA is in flight at once, no registers in between.  (The first version looped over __ldg + st.shared:
+  //      15 + 30 dependent L2 round trips per thread, ~35 us of the kernel's 60 us per CTA.)
   for (int i = threadIdx.x; i < T * N * ch4; i += kDinThreads) {
     const int c4 = i % ch4, tn = i / ch4;
     const int n = tn % N;
-    float4 v = make_float4(0, 0, 0, 0);
-    if (n < Nb) v = __ldg(reinterpret_cast<const float4*>(xb + static_cast<size_t>(tn) * C + c0) + c4);
-    reinterpret_cast<float4*>(slab)[i] = v;
+    float4* dst = reinterpret_cast<float4*>(slab) + i;
+    if (n < Nb) {
+      const float4* src = reinterpret_cast<const float4*>(xb + static_cast<size_t>(tn) * C + c0) + c4;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+    } else {
+      *dst = make_float4(0, 0, 0, 0);
+    }
   }
   for (int i = threadIdx.x; i < k2 * n_out * ch4; i += kDinThreads) {
     const int c4 = i % ch4, row = i / ch4;
-    reinterpret_cast<float4*>(wts)[i] = __ldg(reinterpret_cast<const float4*>(w_tap + static_cast<size_t>(row) * C + c0) + c4);
+    const float4* src = reinterpret_cast<const float4*>(w_tap + static_cast<size_t>(row) * C + c0) + c4;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(reinterpret_cast<float4*>(wts) + i)), "l"(src)
+                 : "memory");
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   // ---- phase 1: partial conv sums over this CTA's channels, frame by frame
@@ -637,9 +647,10 @@ extern "C" int din_dynamic_infer_f32(const float* x, const float* w_tap, const f
   //      splits into 2 / 4 / 8 chunks of a multiple of 32 channels and the staged slices fit shared memory
   {
     static const bool use_cluster = [] { const char* e = std::getenv("DIN_DI_CLUSTER"); return !(e && e[0] == '0'); }();
+    // 128-channel chunks: one float4 per lane per row in both phases (a 64-channel chunk leaves half of every warp idle:
+    // C = 128 split in two measured slower than the one-CTA-per-frame kernel); C = 128 runs as clusters of one CTA
     int n_chunks = 0;
-    for (int cand = 8; cand >= 2; cand >>= 1)
-      if (c % (cand * 32) == 0 && c / cand >= 64) { n_chunks = cand; break; }
+    if (c % 128 == 0 && (c / 128 == 1 || c / 128 == 2 || c / 128 == 4 || c / 128 == 8)) n_chunks = c / 128;
     if (use_cluster && n_chunks > 0) {
       const int chunk = c / n_chunks;
       const int sms = din_num_sms();

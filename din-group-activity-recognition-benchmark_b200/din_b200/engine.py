@@ -94,6 +94,9 @@ SMALL_LAUNCH_PIXELS = 148 * 128 if os.environ.get("DIN_SMALL_EXACT", "1") != "0"
 SMALL_EMBED_ROWS = 64 if os.environ.get("DIN_SMALL_EMBED_F32", "1") != "0" else 0
 
 
+_INFERENCE = [False]        # True while DinEngine.features() (the no-grad inference forward) runs a backbone plan
+
+
 class _Conv:
     """One tcgen05 convolution of the plan (weights packed fp16 [co][kh][kw][ci], fp32 bias)."""
 
@@ -120,7 +123,10 @@ class _Conv:
         return self._w
 
     def _weight_for(self, x):
-        if self.split == 2 or x.shape[0] * x.shape[1] * x.shape[2] > SMALL_LAUNCH_PIXELS * self.stride * self.stride:
+        # inference plans only: a training step re-packs every weight after the optimizer step, and packing a second
+        # (hi + lo) copy of the late layers each step cost ResNet-18's step 47 ms of packing kernels (measured)
+        if (not _INFERENCE[0] or self.split == 2
+                or x.shape[0] * x.shape[1] * x.shape[2] > SMALL_LAUNCH_PIXELS * self.stride * self.stride):
             return self.w
         if self._w_exact is None:
             self._w_exact = ops.pack_conv_weights([(self.w_src, self.bn_scale, 2, False)])[0]
@@ -607,9 +613,13 @@ class DinEngine:
             self._fm_cache = (key, torch.zeros(key, dtype=torch.float16, device=images_flat.device))
         fm = self._fm_cache[1]
         per_chunk = frames_per_chunk(self.backbone_name, F_, H, W, self.frames_per_chunk)
-        for f0 in range(0, F_, per_chunk):
-            f1 = min(F_, f0 + per_chunk)
-            self.backbone(images_flat[f0:f1], out=fm[f0:f1])      # last layer writes its slice in place
+        _INFERENCE[0] = True
+        try:
+            for f0 in range(0, F_, per_chunk):
+                f1 = min(F_, f0 + per_chunk)
+                self.backbone(images_flat[f0:f1], out=fm[f0:f1])      # last layer writes its slice in place
+        finally:
+            _INFERENCE[0] = False
         return fm
 
     def features_train(self, images_flat):
