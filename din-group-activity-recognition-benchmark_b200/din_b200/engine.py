@@ -94,6 +94,15 @@ SMALL_LAUNCH_PIXELS = 148 * 128 if os.environ.get("DIN_SMALL_EXACT", "1") != "0"
 SMALL_EMBED_ROWS = 64 if os.environ.get("DIN_SMALL_EMBED_F32", "1") != "0" else 0
 
 
+def _plan_tensor(v, device):
+    """A model tensor as the kernels want it: on the plan's device, fp32, and 16-byte aligned (the parameters of an
+    nn.DataParallel replica are slices of one coalesced broadcast buffer and start at arbitrary 4-byte offsets)."""
+    t = v.detach().to(device, torch.float32) if v.is_floating_point() else v.detach().to(device)
+    if t.data_ptr() % 16 != 0:
+        t = t.clone(memory_format=torch.contiguous_format)
+    return t
+
+
 _INFERENCE = [False]        # True while DinEngine.features() (the no-grad inference forward) runs a backbone plan
 
 
@@ -533,8 +542,7 @@ class DinEngine:
         # frames per backbone launch: bounds the activation workspace (VGG-16 at 720p: 0.27 GB per frame
         # live at once) while keeping every launch many waves long
         self.frames_per_chunk = frames_per_chunk or int(os.environ.get("DIN_FRAMES_PER_CHUNK", "0")) or None
-        sd = {k: v.detach().to(self.device, torch.float32) if v.is_floating_point() else v.detach().to(self.device)
-              for k, v in state_dict.items()}
+        sd = {k: _plan_tensor(v, self.device) for k, v in state_dict.items()}
         self.T, self.N = cfg.num_frames, cfg.num_boxes
         self.D, self.K = cfg.emb_features, cfg.crop_size[0]
         self.NFB = cfg.num_features_boxes
@@ -707,8 +715,7 @@ class BasenetEngine:
     def __init__(self, cfg, state_dict, device, dataset="volleyball", emb_name="fc_emb"):
         self.cfg, self.dataset, self.device = cfg, dataset, torch.device(device)
         self.frames_per_chunk = int(os.environ.get("DIN_FRAMES_PER_CHUNK", "0")) or None
-        sd = {k: v.detach().to(self.device, torch.float32) if v.is_floating_point() else v.detach().to(self.device)
-              for k, v in state_dict.items()}
+        sd = {k: _plan_tensor(v, self.device) for k, v in state_dict.items()}
         self.N, self.D, self.K, self.NFB = cfg.num_boxes, cfg.emb_features, cfg.crop_size[0], cfg.num_features_boxes
         self.backbone_name = "inv3" if dataset == "collective" else cfg.backbone       # base_model.py:159
         self.backbone = build_backbone_plan(self.backbone_name, sd)
