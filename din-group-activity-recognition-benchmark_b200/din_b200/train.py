@@ -1,10 +1,12 @@
-"""train.py — the stage-2 training step of the person-level head on one B200 (first slice).
+"""train.py — the stage-2 (and stage-1) training step on one B200.
 
 `forward_train` is DinEngine's forward with dropout applied and the intermediates the backward needs kept on a
-tape; `backward_head` turns d(loss)/d(logits) into gradients for every parameter after the backbone, under the
+tape; `backward_head` turns d(loss)/d(logits) into gradients for every parameter after the backbone and -- with
+cfg.train_backbone and the VGG-16 / ResNet-18 backbone -- for the backbone too (`backward_backbone`), under the
 reference's parameter names and layouts (so `optimizer.step()` in train_net_dynamic.py:220-224 works on the
-drop-in model unchanged).  Scope of this slice: the backbone is frozen (config.py:39 `train_backbone = False`);
-gradients stop at the feature map.  Host-side orchestration only: every number is produced by a kernel of
+drop-in model unchanged).  With the backbone frozen (config.py:39 `train_backbone = False`) gradients stop at the
+feature map.  A data-parallel run receives the gradients in two groups as they become final (`sink`, see
+parallel.BucketedGradientReducer).  Host-side orchestration only: every number is produced by a kernel of
 libdin_sm100.so (ops.py); torch is used for buffers, views and layout permutes.
 
 Reference graph (infer_model.py:141-234 / 1226-1319, infer_module/dynamic_infer_module.py:121-151, 407-498):
