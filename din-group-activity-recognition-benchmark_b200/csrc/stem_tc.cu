@@ -518,6 +518,483 @@ stem_tc_wide_kernel(const StemParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// ResNet-18's 7x7 stride-2 pad-3 stem as an IMPLICIT GEMM (no im2col): space-to-depth turns it into a 4x4 stride-1
+// convolution over 12 channels,
+//     out(y, x) = sum_{ty,tx in 0..3} sum_{c,dy,dx} w[c][2ty+dy][2tx+dx] * S[y+ty][x+tx][(c,dy,dx)],
+//     S[Y][X][(c,dy,dx)] = prep(in[c][2Y+dy-3][2X+dx-3])          (w index 7 = 0),
+// so ONE 16-half vector per half-resolution pixel (12 values + two bias ones + 2 zeros) serves all 16 taps: tap
+// (ty, tx)'s A operand is the same shared memory seen through a no-swizzle K-major descriptor whose start is shifted by
+// (ty * pitch + tx) rows (rows 16 bytes apart in each of the two K-chunk planes: SBO = 128, LBO = the plane size).
+// Per 128-pixel strip: 4 x 131 vectors of 12 values instead of 128 im2col rows of 147 -- the wide im2col kernel above is
+// bound by exactly that build (147 shared loads + 74 conversions + 20 stores per pixel: 8.8-9.5 ms per 320 frames at
+// 720p, 1.1 TB/s of output) --, 16 MMAs of K = 16 instead of 10.
+// ------------------------------------------------------------------------------------------------
+constexpr int kS2dPatchW = 127 * 2 + 8;          // 262 input columns per strip
+constexpr int kS2dPitch = 264;                   // even: the (dx = 0, 1) pairs are 8-byte aligned
+constexpr int kS2dRows = 24;                     // 3 channels x 8 input rows
+constexpr int kS2dVecs = 131;                    // half-resolution pixels per patch row (128 + 3)
+constexpr int kS2dVPitch = 136;                  // rows between consecutive ty in the vector array
+constexpr int kS2dVPlane = 4 * kS2dVPitch * 16;  // bytes of one K-chunk plane
+constexpr int kS2dWTap = 2048;                   // bytes of one tap's weight tile (2 planes x 64 rows x 16 B)
+constexpr size_t kS2dSmem = 128 + 2 * kS2dVPlane + 16 * kS2dWTap + 8 * 32 * kEpiPitch + 64 +
+                            static_cast<size_t>(kS2dRows) * kS2dPitch * 4;
+
+template <bool U8>
+__global__ void __launch_bounds__(kWideThreads, 2)
+stem_s2d_kernel(const StemParams p) {
+  constexpr int COUT = 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem(smem_raw, 128);
+  uint8_t* v_s = smem;                                       // vectors: 2 planes x [4 * kS2dVPitch] x 16 B
+  uint8_t* w_s = v_s + 2 * kS2dVPlane;                       // 16 taps x (2 planes x 64 rows x 16 B)
+  uint8_t* scratch = w_s + 16 * kS2dWTap;                    // 8 warps x 32 x 80 B
+  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(scratch + 8 * 32 * kEpiPitch);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  float* patch = reinterpret_cast<float*>(tmem_ptr_smem + 14);              // [24][kS2dPitch], 8-byte aligned
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- one-time: weights in tap-major [tap][plane][row][8 halfs]; bias (hi, lo) rides in columns 12, 13 of tap (0,0)
+  for (int i = tid; i < 16 * 2 * COUT; i += kWideThreads) {
+    const int o = i & 63, plane = (i >> 6) & 1, tap = i >> 7;
+    const int ty = tap >> 2, tx = tap & 3;
+    __align__(16) __half hv[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = plane * 8 + e;
+      float wv = 0.0f;
+      if (k < 12) {
+        const int c = k >> 2, ky = 2 * ty + ((k >> 1) & 1), kx = 2 * tx + (k & 1);
+        if (ky < 7 && kx < 7) wv = __ldg(p.w + ((static_cast<size_t>(o) * 3 + c) * 7 + ky) * 7 + kx);
+      } else if (k <= 13 && tap == 0 && p.bias != nullptr) {
+        const float bv = __ldg(p.bias + o);
+        const float bh = __half2float(__float2half_rn(bv));
+        wv = (k == 12) ? bh : bv - bh;
+      }
+      hv[e] = __float2half_rn(wv);
+    }
+    *reinterpret_cast<uint4*>(w_s + tap * kS2dWTap + plane * 1024 + o * 16) = *reinterpret_cast<const uint4*>(hv);
+  }
+  for (int i = tid; i < 2 * kS2dVPlane / 16; i += kWideThreads) reinterpret_cast<uint4*>(v_s)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    mbar_init(mma_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<64>(tmem_ptr_smem);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+  constexpr uint32_t idesc = umma_idesc_f16_f32(128, COUT);
+  const size_t plane_px = static_cast<size_t>(p.h) * p.w_in;
+  constexpr int kElems = (U8 ? 8 : kS2dRows) * kS2dPatchW;
+  constexpr int kIter = (kElems + kWideThreads - 1) / kWideThreads;
+
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const TileCoord cur = decode_tile(p, tile);
+    const int iy0 = cur.oy * 2 - 3;
+    const int gx0 = cur.strip * 128 * 2 - 3;
+    // ---- stage the 8 input rows x 262 columns x 3 channels (prep_images applied, 0 where the convolution pads)
+    {
+      uint32_t v[kIter];
+      bool ok[kIter];
+#pragma unroll
+      for (int u = 0; u < kIter; ++u) {
+        const int i = tid + u * kWideThreads;
+        const int r = i / kS2dPatchW, px = i - r * kS2dPatchW;
+        const int ky = U8 ? r : (r & 7);
+        const int gy = iy0 + ky, gx = gx0 + px;
+        ok[u] = i < kElems && gy >= 0 && gy < p.h && gx >= 0 && gx < p.w_in;
+        const int cy = min(max(gy, 0), p.h - 1), cx = min(max(gx, 0), p.w_in - 1);
+        if constexpr (U8) {
+          const uint8_t* q = static_cast<const uint8_t*>(p.x) + (static_cast<size_t>(cur.img) * plane_px + static_cast<size_t>(cy) * p.w_in + cx) * 3;
+          v[u] = static_cast<uint32_t>(__ldg(q)) | (static_cast<uint32_t>(__ldg(q + 1)) << 8) | (static_cast<uint32_t>(__ldg(q + 2)) << 16);
+        } else {
+          const int c = min(r >> 3, 2);
+          v[u] = __float_as_uint(__ldg(static_cast<const float*>(p.x) + (static_cast<size_t>(cur.img) * 3 + c) * plane_px +
+                                       static_cast<size_t>(cy) * p.w_in + cx));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kIter; ++u) {
+        const int i = tid + u * kWideThreads;
+        if (i < kElems) {
+          const int r = i / kS2dPatchW, px = i - r * kS2dPatchW;
+          if constexpr (U8) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+              patch[(c * 8 + r) * kS2dPitch + px] =
+                  ok[u] ? prep_value(static_cast<float>((v[u] >> (8 * c)) & 0xFFu), p.prep != 0) : 0.0f;
+          } else {
+            patch[r * kS2dPitch + px] = ok[u] ? prep_value(__uint_as_float(v[u]), p.prep != 0) : 0.0f;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- one 16-half vector per half-resolution pixel (ty, X): (c, dy, dx) values, then the two bias ones
+    for (int v = tid; v < 4 * kS2dVecs; v += kWideThreads) {
+      const int ty = v / kS2dVecs, X = v - ty * kS2dVecs;
+      uint32_t h[8];
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+          const float2 f = *reinterpret_cast<const float2*>(patch + (c * 8 + 2 * ty + dy) * kS2dPitch + 2 * X);
+          h[c * 2 + dy] = pack_half2(f.x, f.y, false);
+        }
+      h[6] = 0x3C003C00u;                                    // columns 12, 13 = 1 (bias hi / lo live in tap (0,0)'s weights)
+      h[7] = 0u;
+      uint8_t* dst = v_s + (ty * kS2dVPitch + X) * 16;
+      *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4*>(dst + kS2dVPlane) = make_uint4(h[4], h[5], h[6], h[7]);
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after_sync();
+      const uint32_t v_addr = smem_u32(v_s), w_addr = smem_u32(w_s);
+      if (elect_one()) {
+#pragma unroll
+        for (int tap = 0; tap < 16; ++tap) {
+          const uint64_t ad = desc_noswz(v_addr + ((tap >> 2) * kS2dVPitch + (tap & 3)) * 16, kS2dVPlane, 128);
+          const uint64_t bd = desc_noswz(w_addr + tap * kS2dWTap, 1024, 128);
+          umma_f16_ss(tmem_base, ad, bd, idesc, tap > 0 ? 1u : 0u);
+        }
+        umma_commit(mma_bar);
+      }
+      __syncwarp();
+    }
+    mbar_wait(mma_bar, phase);
+    phase ^= 1u;
+    tc_fence_after_sync();
+    // ---- epilogue: warp = (lane quadrant q, 32-column chunk), as stem_tc_wide_kernel
+    {
+      const int q = warp & 3, chunk = warp >> 2;
+      const int c0 = chunk * 32;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+      uint8_t* sc = scratch + warp * 32 * kEpiPitch;
+      const int unit = lane & 3;
+      __half* yrow = p.y + ((static_cast<size_t>(cur.img) * p.oh + cur.oy) * p.ow) * COUT;
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(taddr + c0, v);
+      tmem_ld_wait();
+      uint32_t hh[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        hh[j] = pack_half2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]), p.relu != 0);
+      uint4* wr = reinterpret_cast<uint4*>(sc + lane * kEpiPitch);
+#pragma unroll
+      for (int u4 = 0; u4 < 4; ++u4) wr[u4] = make_uint4(hh[4 * u4], hh[4 * u4 + 1], hh[4 * u4 + 2], hh[4 * u4 + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int src = (lane >> 2) + 8 * k;
+        const int sx = cur.strip * 128 + q * 32 + src;
+        if (sx < p.ow) {
+          const uint4 o = *reinterpret_cast<const uint4*>(sc + src * kEpiPitch + unit * 16);
+          *reinterpret_cast<uint4*>(yrow + static_cast<size_t>(sx) * COUT + c0 + unit * 8) = o;
+        }
+      }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc<64>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same implicit GEMM, warp-specialised and pipelined (the kernel above runs load -> build -> MMA -> store one after
+// the other inside a CTA and was no faster than the im2col kernel: 10.5 vs 9.7 ms per 320 frames -- both are bound by
+// that serial chain of latencies, not by the im2col build as round 1 assumed):
+//   warp 0        TMA: box {264, 8, 3} of the fp32 NCHW image ({832 B, 8} of the uint8 NHWC frame) per tile, 3 tiles
+//                 ahead (the box starts on a 16-byte boundary left of the strip: see tools/probes/tma_probe.cu);
+//   warps 2..9    build the 4 x 131 half-resolution vectors (prep_images, 0 where the convolution pads) into one of two
+//                 vector buffers;
+//   warp 1        16 tcgen05.mma (K = 16 each) per tile into one of two TMEM accumulators;
+//   warps 10..13  epilogue: TMEM -> ReLU -> fp16 -> transpose -> NHWC stores.
+// One persistent CTA per SM (155 KB of shared memory).
+// ------------------------------------------------------------------------------------------------
+constexpr int kWsThreads = 32 * 14;
+constexpr int kWsBuilders = 8;                   // warps 2..9
+constexpr int kWsEpiWarp0 = 10;                  // warps 10..13
+constexpr int kWsPatchStages = 3;
+// fp32: the 264 input columns 256*strip - 4 .. + 259 of a patch row exceed TMA's 256-element box limit, so every tile is
+// two boxes: A = columns [0, 136) and B = columns [132, 264) of that range (both start on 16-byte boundaries); the
+// (dx = 0, 1) pair of vector X sits at columns 2X + 1, 2X + 2: X <= 65 reads A, X >= 66 reads B.
+constexpr int kWsBoxA = 136, kWsBoxB = 132, kWsBoxBStart = 132, kWsSplitX = 66;
+constexpr int kWsBlockA = 3 * 8 * kWsBoxA * 4;   // 13056 bytes
+constexpr int kWsBoxU8 = 832;                    // uint8: bytes per patch row (pixels 256*strip - 16 .. + 261), loaded as
+                                                 // 208 32-bit elements (a box is at most 256 elements wide)
+constexpr int kWsPatchBytes = kWsBlockA + 3 * 8 * kWsBoxB * 4;           // 25728 (uint8: 8 * 832 = 6656)
+constexpr int kWsPatchStage = 26112;
+constexpr size_t kWsSmem = 1024 + kWsPatchStages * kWsPatchStage + 2 * 2 * kS2dVPlane + 16 * kS2dWTap + 4 * 32 * kEpiPitch + 256;
+
+template <bool U8>
+__global__ void __launch_bounds__(kWsThreads, 1)
+stem_s2d_ws_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_constant__ CUtensorMap tmap_b,
+                   const StemParams p) {
+  constexpr int COUT = 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem(smem_raw, 1024);
+  uint8_t* patch_s = smem;                                           // kWsPatchStages x raw patch
+  uint8_t* v_s = patch_s + kWsPatchStages * kWsPatchStage;           // 2 x (2 planes x [4 * kS2dVPitch] x 16 B)
+  uint8_t* w_s = v_s + 2 * 2 * kS2dVPlane;                           // 16 taps x 2 KB
+  uint8_t* scratch = w_s + 16 * kS2dWTap;                            // 4 epilogue warps x 32 x 80 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + 4 * 32 * kEpiPitch);
+  uint64_t* patch_full = bars;                    // [3]
+  uint64_t* patch_empty = patch_full + 3;         // [3]  8 builder warps
+  uint64_t* v_full = patch_empty + 3;             // [2]  8 builder warps
+  uint64_t* v_empty = v_full + 2;                 // [2]  MMA commit
+  uint64_t* acc_full = v_empty + 2;               // [2]  MMA commit
+  uint64_t* acc_empty = acc_full + 2;             // [2]  4 epilogue warps
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- one-time: weights (as stem_s2d_kernel), zeroed vector buffers, barriers, TMEM
+  for (int i = tid; i < 16 * 2 * COUT; i += kWsThreads) {
+    const int o = i & 63, plane = (i >> 6) & 1, tap = i >> 7;
+    const int ty = tap >> 2, tx = tap & 3;
+    __align__(16) __half hv[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = plane * 8 + e;
+      float wv = 0.0f;
+      if (k < 12) {
+        const int c = k >> 2, ky = 2 * ty + ((k >> 1) & 1), kx = 2 * tx + (k & 1);
+        if (ky < 7 && kx < 7) wv = __ldg(p.w + ((static_cast<size_t>(o) * 3 + c) * 7 + ky) * 7 + kx);
+      } else if (k <= 13 && tap == 0 && p.bias != nullptr) {
+        const float bv = __ldg(p.bias + o);
+        const float bh = __half2float(__float2half_rn(bv));
+        wv = (k == 12) ? bh : bv - bh;
+      }
+      hv[e] = __float2half_rn(wv);
+    }
+    *reinterpret_cast<uint4*>(w_s + tap * kS2dWTap + plane * 1024 + o * 16) = *reinterpret_cast<const uint4*>(hv);
+  }
+  for (int i = tid; i < 2 * 2 * kS2dVPlane / 16; i += kWsThreads) reinterpret_cast<uint4*>(v_s)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    tma_prefetch_desc(&tmap_img);
+    for (int s = 0; s < 3; ++s) { mbar_init(&patch_full[s], 1); mbar_init(&patch_empty[s], kWsBuilders); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&v_full[s], kWsBuilders); mbar_init(&v_empty[s], 1);
+      mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<128>(tmem_ptr_smem);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int j = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
+        const TileCoord cur = decode_tile(p, tile);
+        const int ps = j % kWsPatchStages;
+        mbar_wait_relaxed(&patch_empty[ps], ((j / kWsPatchStages) & 1) ^ 1);
+        if constexpr (U8) {
+          mbar_arrive_expect_tx(&patch_full[ps], 8u * kWsBoxU8);
+          tma_load_3d(patch_s + ps * kWsPatchStage, &tmap_img, &patch_full[ps], ((cur.strip * 256 - 16) * 3) / 4,
+                      cur.oy * 2 - 3, cur.img);
+        } else {
+          mbar_arrive_expect_tx(&patch_full[ps], static_cast<uint32_t>(kWsPatchBytes));
+          tma_load_3d(patch_s + ps * kWsPatchStage, &tmap_img, &patch_full[ps], cur.strip * 256 - 4, cur.oy * 2 - 3,
+                      cur.img * 3);
+          tma_load_3d(patch_s + ps * kWsPatchStage + kWsBlockA, &tmap_b, &patch_full[ps],
+                      cur.strip * 256 - 4 + kWsBoxBStart, cur.oy * 2 - 3, cur.img * 3);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = umma_idesc_f16_f32(128, COUT);
+    const uint32_t v_addr = smem_u32(v_s), w_addr = smem_u32(w_s);
+    int j = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
+      const int b = j & 1;
+      const uint32_t use = static_cast<uint32_t>(j >> 1);
+      mbar_wait(&v_full[b], use & 1u);
+      mbar_wait(&acc_empty[b], (use & 1u) ^ 1u);
+      tc_fence_after_sync();
+      if (leader) {
+#pragma unroll
+        for (int tap = 0; tap < 16; ++tap) {
+          const uint64_t ad = desc_noswz(v_addr + b * (2 * kS2dVPlane) + ((tap >> 2) * kS2dVPitch + (tap & 3)) * 16,
+                                         kS2dVPlane, 128);
+          const uint64_t bd = desc_noswz(w_addr + tap * kS2dWTap, 1024, 128);
+          umma_f16_ss(tmem_base + static_cast<uint32_t>(b * COUT), ad, bd, idesc, tap > 0 ? 1u : 0u);
+        }
+        umma_commit(&v_empty[b]);
+        umma_commit(&acc_full[b]);
+      }
+    }
+  } else if (warp < 2 + kWsBuilders) {
+    // ------------------------------------------------------------------ builders: one vector per half-res pixel
+    const int bt = tid - 64;                                          // 0..255
+    int j = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
+      const TileCoord cur = decode_tile(p, tile);
+      const int ps = j % kWsPatchStages, b = j & 1;
+      const uint32_t use = static_cast<uint32_t>(j >> 1);
+      mbar_wait_relaxed(&patch_full[ps], (j / kWsPatchStages) & 1);
+      mbar_wait_relaxed(&v_empty[b], (use & 1u) ^ 1u);
+      const uint8_t* patch = patch_s + ps * kWsPatchStage;
+      uint8_t* vb = v_s + b * (2 * kS2dVPlane);
+      const int iy0 = cur.oy * 2 - 3, gx0 = cur.strip * 256 - 3;      // input coordinates of (ty = 0, dy = 0) / (X = 0, dx = 0)
+      for (int v = bt; v < 4 * kS2dVecs; v += 32 * kWsBuilders) {
+        const int ty = v / kS2dVecs, X = v - ty * kS2dVecs;
+        const bool in_a = X < kWsSplitX;
+        (void)in_a;
+        bool rok[2], cok[2];
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          rok[d] = (iy0 + 2 * ty + d >= 0) && (iy0 + 2 * ty + d < p.h);
+          cok[d] = (gx0 + 2 * X + d >= 0) && (gx0 + 2 * X + d < p.w_in);
+        }
+        uint32_t h[8];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy) {
+            float f[2];
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+              float raw;
+              if constexpr (U8) raw = static_cast<float>(patch[(2 * ty + dy) * kWsBoxU8 + (13 + 2 * X + dx) * 3 + c]);
+              else raw = in_a ? reinterpret_cast<const float*>(patch)[(c * 8 + 2 * ty + dy) * kWsBoxA + 1 + 2 * X + dx]
+                              : reinterpret_cast<const float*>(patch + kWsBlockA)[(c * 8 + 2 * ty + dy) * kWsBoxB + 1 + 2 * X +
+                                                                                  dx - kWsBoxBStart];
+              f[dx] = (rok[dy] && cok[dx]) ? prep_value(raw, p.prep != 0) : 0.0f;
+            }
+            h[c * 2 + dy] = pack_half2(f[0], f[1], false);
+          }
+        h[6] = 0x3C003C00u;
+        h[7] = 0u;
+        uint8_t* dst = vb + (ty * kS2dVPitch + X) * 16;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(dst + kS2dVPlane) = make_uint4(h[4], h[5], h[6], h[7]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&patch_empty[ps]);
+        mbar_arrive(&v_full[b]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: warp e = lane quadrant e
+    const int q = warp & 3;                                           // warps 10..13 -> quadrants 2, 3, 0, 1
+    uint8_t* sc = scratch + (warp - kWsEpiWarp0) * 32 * kEpiPitch;
+    const int unit = lane & 3;
+    int j = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
+      const TileCoord cur = decode_tile(p, tile);
+      const int b = j & 1;
+      mbar_wait_relaxed(&acc_full[b], static_cast<uint32_t>(j >> 1) & 1u);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(b * COUT);
+      __half* yrow = p.y + ((static_cast<size_t>(cur.img) * p.oh + cur.oy) * p.ow) * COUT;
+#pragma unroll
+      for (int c0 = 0; c0 < COUT; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + c0, v);
+        tmem_ld_wait();
+        uint32_t hh[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          hh[k] = pack_half2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]), p.relu != 0);
+        uint4* wr = reinterpret_cast<uint4*>(sc + lane * kEpiPitch);
+#pragma unroll
+        for (int u4 = 0; u4 < 4; ++u4) wr[u4] = make_uint4(hh[4 * u4], hh[4 * u4 + 1], hh[4 * u4 + 2], hh[4 * u4 + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int src = (lane >> 2) + 8 * k;
+          const int sx = cur.strip * 128 + q * 32 + src;
+          if (sx < p.ow) {
+            const uint4 o = *reinterpret_cast<const uint4*>(sc + src * kEpiPitch + unit * 16);
+            *reinterpret_cast<uint4*>(yrow + static_cast<size_t>(sx) * COUT + c0 + unit * 8) = o;
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[b]);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<128>(tmem_base);
+  }
+}
+
+template <bool U8>
+int launch_s2d_ws(StemParams& p, cudaStream_t st) {
+  CUtensorMap timg, timg_b;
+  if (U8) {
+    // the uint8 frame as 32-bit elements (w % 16 == 0: rows are multiples of 48 bytes)
+    const uint64_t row = static_cast<uint64_t>(p.w_in) * 3;
+    const uint64_t dims[3] = {row / 4, static_cast<uint64_t>(p.h), static_cast<uint64_t>(p.n)};
+    const uint64_t strides[3] = {4, row, row * p.h};
+    const uint32_t box[3] = {kWsBoxU8 / 4, 8, 1};
+    const uint32_t es[3] = {1, 1, 1};
+    int rc = din_encode_tmap(&timg, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(p.x), dims, strides, box, es,
+                             CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc != DIN_OK) return rc;
+    timg_b = timg;
+  } else {
+    const uint64_t dims[3] = {static_cast<uint64_t>(p.w_in), static_cast<uint64_t>(p.h), static_cast<uint64_t>(p.n) * 3};
+    const uint64_t strides[3] = {4, static_cast<uint64_t>(p.w_in) * 4, static_cast<uint64_t>(p.w_in) * 4 * p.h};
+    const uint32_t es[3] = {1, 1, 1};
+    const uint32_t box_a[3] = {kWsBoxA, 8, 3}, box_b[3] = {kWsBoxB, 8, 3};
+    int rc = din_encode_tmap(&timg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(p.x), dims, strides, box_a, es,
+                             CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc != DIN_OK) return rc;
+    rc = din_encode_tmap(&timg_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(p.x), dims, strides, box_b, es,
+                         CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc != DIN_OK) return rc;
+  }
+  const int sms = din_num_sms();
+  long long grid = sms > 0 ? sms : 148;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  DIN_OPT_IN_SMEM(stem_s2d_ws_kernel<U8>, kWsSmem);
+  stem_s2d_ws_kernel<U8><<<static_cast<int>(grid), kWsThreads, kWsSmem, st>>>(timg, timg_b, p);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
+template <bool U8>
+int launch_s2d(StemParams& p, cudaStream_t st) {
+  const int sms = din_num_sms();
+  int per_sm = static_cast<int>((224 * 1024) / (kS2dSmem + 1024));
+  if (per_sm > 4) per_sm = 4;
+  if (per_sm < 1) per_sm = 1;
+  long long grid = static_cast<long long>(sms > 0 ? sms : 148) * per_sm;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  DIN_OPT_IN_SMEM(stem_s2d_kernel<U8>, kS2dSmem);
+  stem_s2d_kernel<U8><<<static_cast<int>(grid), kWideThreads, kS2dSmem, st>>>(p);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
 void fastdiv(uint32_t d, uint32_t* mul, uint32_t* shr) {
   uint32_t l = 0;
   while ((1u << l) < d) ++l;
@@ -567,7 +1044,16 @@ int launch(StemParams& p, cudaStream_t st) {
 template <bool U8>
 int dispatch(StemParams& p, int c_out, int kh, int kw, int stride, cudaStream_t st) {
   if (c_out == 64 && kh == 3 && kw == 3 && stride == 1) return launch<64, 3, 3, 1, U8>(p, st);   // VGG-16
-  if (c_out == 64 && kh == 7 && kw == 7 && stride == 2) return launch<64, 7, 7, 2, U8>(p, st);   // ResNet-18
+  if (c_out == 64 && kh == 7 && kw == 7 && stride == 2) {                                         // ResNet-18
+    // DIN_STEM_S2D=0: the im2col kernel; =1: the serial implicit-GEMM kernel; default: the pipelined one (A/B knobs)
+    const char* e = std::getenv("DIN_STEM_S2D");
+    const bool tma_ok = (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && (U8 ? p.w_in % 16 == 0 : p.w_in % 4 == 0);
+    if (p.pad == 3 && !(e && e[0] == '0')) {
+      if (tma_ok && !(e && e[0] == '1')) return launch_s2d_ws<U8>(p, st);
+      return launch_s2d<U8>(p, st);
+    }
+    return launch<64, 7, 7, 2, U8>(p, st);
+  }
   if (c_out == 32 && kh == 3 && kw == 3 && stride == 2) return launch<32, 3, 3, 2, U8>(p, st);   // Inception-v3
   return DIN_ERR_UNSUPPORTED;
 }
