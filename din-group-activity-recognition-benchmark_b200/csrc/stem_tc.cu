@@ -729,7 +729,7 @@ constexpr int kWsEpiWarp0 = 10;                  // warps 10..13
 constexpr int kWsPatchStages = 3;
 // fp32: the 264 input columns 256*strip - 4 .. + 259 of a patch row exceed TMA's 256-element box limit, so every tile is
 // two boxes: A = columns [0, 136) and B = columns [132, 264) of that range (both start on 16-byte boundaries); the
-// (dx = 0, 1) pair of vector X sits at columns 2X + 1, 2X + 2: X <= 65 reads A, X >= 66 reads B.
+// (dx = 0, 1) pair of vector X sits at columns 2X, 2X + 1 (8-byte aligned): X <= 65 reads A, X >= 66 reads B.
 constexpr int kWsBoxA = 136, kWsBoxB = 132, kWsBoxBStart = 132, kWsSplitX = 66;
 constexpr int kWsBlockA = 3 * 8 * kWsBoxA * 4;   // 13056 bytes
 constexpr int kWsBoxU8 = 832;                    // uint8: bytes per patch row (pixels 256*strip - 16 .. + 261), loaded as
@@ -769,8 +769,10 @@ stem_s2d_ws_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_co
       const int k = plane * 8 + e;
       float wv = 0.0f;
       if (k < 12) {
-        const int c = k >> 2, ky = 2 * ty + ((k >> 1) & 1), kx = 2 * tx + (k & 1);
-        if (ky < 7 && kx < 7) wv = __ldg(p.w + ((static_cast<size_t>(o) * 3 + c) * 7 + ky) * 7 + kx);
+        // columns use the space-to-depth phase -4 (pairs start on even input columns = 8-byte aligned in the patch):
+        // S[Y][X][(c,dy,dx)] = in[c][2Y+dy-3][2X+dx-4], so kx = 2*tx + dx - 1 (kx = -1 and ky = 7: zero weights)
+        const int c = k >> 2, ky = 2 * ty + ((k >> 1) & 1), kx = 2 * tx + (k & 1) - 1;
+        if (ky < 7 && kx >= 0 && kx < 7) wv = __ldg(p.w + ((static_cast<size_t>(o) * 3 + c) * 7 + ky) * 7 + kx);
       } else if (k <= 13 && tap == 0 && p.bias != nullptr) {
         const float bv = __ldg(p.bias + o);
         const float bh = __half2float(__float2half_rn(bv));
@@ -854,7 +856,7 @@ stem_s2d_ws_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_co
       mbar_wait_relaxed(&v_empty[b], (use & 1u) ^ 1u);
       const uint8_t* patch = patch_s + ps * kWsPatchStage;
       uint8_t* vb = v_s + b * (2 * kS2dVPlane);
-      const int iy0 = cur.oy * 2 - 3, gx0 = cur.strip * 256 - 3;      // input coordinates of (ty = 0, dy = 0) / (X = 0, dx = 0)
+      const int iy0 = cur.oy * 2 - 3, gx0 = cur.strip * 256 - 4;      // input coordinates of (ty = 0, dy = 0) / (X = 0, dx = 0)
       for (int v = bt; v < 4 * kS2dVecs; v += 32 * kWsBuilders) {
         const int ty = v / kS2dVecs, X = v - ty * kS2dVecs;
         const bool in_a = X < kWsSplitX;
@@ -870,16 +872,25 @@ stem_s2d_ws_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_co
         for (int c = 0; c < 3; ++c)
 #pragma unroll
           for (int dy = 0; dy < 2; ++dy) {
+            float raw[2];
+            if constexpr (U8) {
+              const uint8_t* q = patch + (2 * ty + dy) * kWsBoxU8 + (12 + 2 * X) * 3 + c;
+              raw[0] = static_cast<float>(q[0]);
+              raw[1] = static_cast<float>(q[3]);
+            } else {
+              // one aligned 8-byte load per (c, dy): lanes read consecutive pairs, no bank conflicts (with the pairs on
+              // odd columns -- phase -3 -- these were 4-byte loads at stride 2: 790 of the tile's 2430 shared-memory
+              // wavefronts were their conflicts)
+              const float* row = in_a ? reinterpret_cast<const float*>(patch) + (c * 8 + 2 * ty + dy) * kWsBoxA + 2 * X
+                                      : reinterpret_cast<const float*>(patch + kWsBlockA) + (c * 8 + 2 * ty + dy) * kWsBoxB +
+                                            2 * X - kWsBoxBStart;
+              const float2 pr = *reinterpret_cast<const float2*>(row);
+              raw[0] = pr.x;
+              raw[1] = pr.y;
+            }
             float f[2];
 #pragma unroll
-            for (int dx = 0; dx < 2; ++dx) {
-              float raw;
-              if constexpr (U8) raw = static_cast<float>(patch[(2 * ty + dy) * kWsBoxU8 + (13 + 2 * X + dx) * 3 + c]);
-              else raw = in_a ? reinterpret_cast<const float*>(patch)[(c * 8 + 2 * ty + dy) * kWsBoxA + 1 + 2 * X + dx]
-                              : reinterpret_cast<const float*>(patch + kWsBlockA)[(c * 8 + 2 * ty + dy) * kWsBoxB + 1 + 2 * X +
-                                                                                  dx - kWsBoxBStart];
-              f[dx] = (rok[dy] && cok[dx]) ? prep_value(raw, p.prep != 0) : 0.0f;
-            }
+            for (int dx = 0; dx < 2; ++dx) f[dx] = (rok[dy] && cok[dx]) ? prep_value(raw[dx], p.prep != 0) : 0.0f;
             h[c * 2 + dy] = pack_half2(f[0], f[1], false);
           }
         h[6] = 0x3C003C00u;
