@@ -63,6 +63,10 @@ WORKLOADS = {
         dict(dataset="collective", backbone="res18", image_size=(480, 720), out_size=(15, 23), emb_features=512,
              num_frames=10, num_boxes=13, lite_dim=None, ST_kernel_size=(3, 3), sampling_ratio=(1,),
              num_activities=4), 16, 254.8),
+    # the sibling model of SURVEY.md §8f rank 4: Dynamic_TCE_volleyball (context encoder prepended to DIN, C = 1536)
+    "volleyball_vgg16_tce_T10_N12_720p": (
+        dict(backbone="vgg16", image_size=(720, 1280), out_size=(22, 40), emb_features=512, num_frames=10,
+             num_boxes=12, lite_dim=None, ST_kernel_size=[(3, 3)], sampling_ratio=(1,), tce=True), 8, 5646.0),
 }
 # BASELINE.json configs[2] ("ResNet-18 lite, B=32, 8 x B200") is volleyball_res18_lite128_T10_N12_720p with
 # --global-clips 32: 32 clips per step in total, 4 per GPU at N = 8 (strong scaling); without the flag every GPU keeps
@@ -146,7 +150,9 @@ def build_model(pc, device):
     import warnings
     with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        model = (IM.Dynamic_collective if pc.dataset == "collective" else IM.Dynamic_volleyball)(cfg)
+        cls = IM.Dynamic_collective if pc.dataset == "collective" else \
+            (IM.Dynamic_TCE_volleyball if pc.tce else IM.Dynamic_volleyball)
+        model = cls(cfg)
     model.load_state_dict(sd)
     return model.to(device).eval(), sd, bb
 
@@ -509,7 +515,7 @@ def main():
 
     # supplementary: the training step (all ranks take part: its gradient all-reduce is inside the timed step)
     train_info = None
-    if not args.no_train_step and pc.backbone in ("vgg16", "res18") and pc.dataset == "volleyball":
+    if not args.no_train_step and pc.backbone in ("vgg16", "res18") and pc.dataset == "volleyball" and not pc.tce:
         train_info = train_step_info(model, pc, dev, images_d, boxes_d, min(args.train_clips, B), dist=dist)
 
     if dist is not None:

@@ -517,6 +517,106 @@ dynamic_infer_cluster_kernel(const float* __restrict__ x, const float* __restric
 }
 
 // ================================================================================================
+// Context attention of Dynamic_TCE_volleyball (TCE_STBiP_module.py:252-287, one layer of 4 heads): every actor attends
+// over the frame's feature map,
+//     a[n][px] = <q[n], x[px]>,  A = softmax_px(a),  ctx[n] = sum_px A[n][px] * x[px],   x[px] = img[px] + posbias[px]
+// with img = downsample2(feature map) (the four heads' 1x1 convolutions run as ONE tcgen05 GEMM, fp32 out) and posbias =
+// downsample2(position embedding) + bias precomputed per plan (the embedding is a constant of the map size).
+// One CTA per (frame, head): q and the attention row of every actor live in shared memory, the map streams through a
+// 32-pixel tile twice (scores, then the weighted sum); nothing but ctx is written.
+//   q, ctx: [H][M][128] (head-major, M = frames * actors);  img: [F][P][H*128] fp32;  posbias: [P][H*128] fp32.
+// ================================================================================================
+constexpr int kCtxDim = 128;
+constexpr int kCtxTile = 32;
+constexpr int kCtxThreads = 256;
+
+__global__ void __launch_bounds__(kCtxThreads)
+context_attention_kernel(const float* __restrict__ q, const float* __restrict__ img, const float* __restrict__ posbias,
+                         float* __restrict__ ctx, int F, int N, int P, int H) {
+  extern __shared__ float smem_f[];
+  const int f = blockIdx.x / H, h = blockIdx.x - f * H;
+  const int M = F * N;
+  float* qs = smem_f;                                   // [N][128]
+  float* tile = qs + N * kCtxDim;                       // [32][129]
+  float* att = tile + kCtxTile * (kCtxDim + 1);         // [N][P]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int HC = H * kCtxDim;
+  for (int i = tid; i < N * kCtxDim; i += kCtxThreads)
+    qs[i] = __ldg(q + (static_cast<size_t>(h) * M + static_cast<size_t>(f) * N) * kCtxDim + i);
+  const float* ib = img + static_cast<size_t>(f) * P * HC + h * kCtxDim;
+  const float* pb = posbias + h * kCtxDim;
+
+  auto load_tile = [&](int p0) {
+    for (int i = tid; i < kCtxTile * (kCtxDim / 4); i += kCtxThreads) {
+      const int px = i / (kCtxDim / 4), c4 = i - px * (kCtxDim / 4);
+      float4 v = make_float4(0, 0, 0, 0);
+      if (p0 + px < P) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(ib + static_cast<size_t>(p0 + px) * HC) + c4);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(pb + static_cast<size_t>(p0 + px) * HC) + c4);
+        v = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+      }
+      float* t = tile + px * (kCtxDim + 1) + 4 * c4;
+      t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+    }
+  };
+
+  // ---- pass 1: scores
+  for (int p0 = 0; p0 < P; p0 += kCtxTile) {
+    __syncthreads();
+    load_tile(p0);
+    __syncthreads();
+    for (int i = tid; i < N * kCtxTile; i += kCtxThreads) {
+      const int n = i / kCtxTile, px = i - n * kCtxTile;
+      if (p0 + px < P) {
+        const float* qq = qs + n * kCtxDim;
+        const float* xx = tile + px * (kCtxDim + 1);
+        float acc = 0.0f;
+#pragma unroll 8
+        for (int c = 0; c < kCtxDim; ++c) acc = fmaf(qq[c], xx[c], acc);
+        att[n * P + p0 + px] = acc;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- softmax over the map, one warp per actor
+  for (int n = warp; n < N; n += kCtxThreads / 32) {
+    float* a = att + n * P;
+    float mx = -FLT_MAX;
+    for (int i = lane; i < P; i += 32) mx = fmaxf(mx, a[i]);
+    mx = warp_max(mx);
+    float den = 0.0f;
+    for (int i = lane; i < P; i += 32) { const float e = expf(a[i] - mx); a[i] = e; den += e; }
+    den = warp_sum(den);
+    const float inv = 1.0f / den;
+    for (int i = lane; i < P; i += 32) a[i] *= inv;
+  }
+  // ---- pass 2: weighted sum; thread = (channel, actor parity)
+  const int c = tid & (kCtxDim - 1), n0 = tid >> 7;          // 256 threads: n0 in {0, 1}
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
+  for (int p0 = 0; p0 < P; p0 += kCtxTile) {
+    __syncthreads();
+    load_tile(p0);
+    __syncthreads();
+    const int lim = min(kCtxTile, P - p0);
+    for (int px = 0; px < lim; ++px) {
+      const float xv = tile[px * (kCtxDim + 1) + c];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int n = n0 + 2 * k;
+        if (n < N) acc[k] = fmaf(att[n * P + p0 + px], xv, acc[k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int n = n0 + 2 * k;
+    if (n < N) ctx[(static_cast<size_t>(h) * M + static_cast<size_t>(f) * N + n) * kCtxDim + c] = acc[k];
+  }
+}
+
+// ================================================================================================
 // read-out: max over actors -> fc_activities -> mean over frames     (one CTA per clip)
 // ================================================================================================
 constexpr int kRoThreads = 256;
@@ -684,7 +784,7 @@ extern "C" int din_dynamic_infer_f32(const float* x, const float* w_tap, const f
     }
   }
   const size_t smem = (static_cast<size_t>(kt) * n * c + static_cast<size_t>(n) * n_out) * sizeof(float);
-  DIN_CHECK_ARG(smem <= 220 * 1024, "din_dynamic_infer_f32: kt*n*c too large for shared memory (%zu bytes)", smem);
+  DIN_CHECK_ARG(smem <= 226 * 1024, "din_dynamic_infer_f32: kt*n*c too large for shared memory (%zu bytes)", smem);
   DIN_OPT_IN_SMEM(dynamic_infer_kernel, smem);
   dynamic_infer_kernel<<<b * t, kDinThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       x, w_tap, b_cat, y, t, n, c, kt, kn, ratio, scale_factor, coef_ptr, coef_scalar, accumulate, n_valid);
@@ -700,6 +800,24 @@ extern "C" int din_readout_f32(const float* s, const float* w, const float* bias
   const size_t smem = static_cast<size_t>(c) * sizeof(float);
   DIN_CHECK_ARG(smem <= 48 * 1024, "din_readout_f32: c=%d too large", c);
   readout_kernel<<<b, kRoThreads, smem, static_cast<cudaStream_t>(stream)>>>(s, w, bias, logits, t, n, c, a, n_valid);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
+extern "C" int din_context_attention_f32(const float* q, const float* img, const float* posbias, float* ctx, int frames,
+                                         int n, int pixels, int heads, void* stream) {
+  DIN_CHECK_ARG(q && img && posbias && ctx, "din_context_attention_f32: null pointer");
+  DIN_CHECK_ARG(frames > 0 && n > 0 && n <= 16 && pixels > 0 && heads > 0,
+                "din_context_attention_f32: bad shape frames=%d n=%d (<= 16) pixels=%d heads=%d", frames, n, pixels, heads);
+  DIN_CHECK_ARG(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(posbias) |
+                  reinterpret_cast<uintptr_t>(ctx)) & 15) == 0,
+                "din_context_attention_f32: pointers must be 16-byte aligned");
+  const size_t smem = (static_cast<size_t>(n) * kCtxDim + kCtxTile * (kCtxDim + 1) + static_cast<size_t>(n) * pixels) *
+                      sizeof(float);
+  DIN_CHECK_ARG(smem <= 200 * 1024, "din_context_attention_f32: n * pixels = %d x %d does not fit shared memory", n, pixels);
+  DIN_OPT_IN_SMEM(context_attention_kernel, smem);
+  context_attention_kernel<<<frames * heads, kCtxThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      q, img, posbias, ctx, frames, n, pixels, heads);
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;
 }

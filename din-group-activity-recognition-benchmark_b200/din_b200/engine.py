@@ -528,6 +528,71 @@ class DPIWeights:
         return ops.linear_f32(tmp, self.hidden, None, out=out, accumulate=accumulate)
 
 
+TCE_HEADS, TCE_DIM = 4, 128        # num_heads_context, num_features_context (infer_model.py:244-245)
+
+
+def _context_position_table(oh, ow, device, downscale=16.0, num_pos_feats=256, temperature=10000.0):
+    """Context_PositionEmbeddingSine(16, 512 / 2) (positional_encoding.py:67-93) as a [oh*ow, 512] table: a constant of the
+    map size, evaluated once per plan (fp32, same op order as the reference)."""
+    y = (torch.arange(1, oh + 1, dtype=torch.float32, device=device) * downscale).view(oh, 1).expand(oh, ow)
+    x = (torch.arange(1, ow + 1, dtype=torch.float32, device=device) * downscale).view(1, ow).expand(oh, ow)
+    j = torch.arange(num_pos_feats, dtype=torch.float32, device=device)
+    dim_t = temperature ** (2 * torch.div(j, 2, rounding_mode="floor") / num_pos_feats)
+    px, py = x[:, :, None] / dim_t, y[:, :, None] / dim_t
+    px = torch.stack((px[:, :, 0::2].sin(), px[:, :, 1::2].cos()), dim=3).flatten(2)
+    py = torch.stack((py[:, :, 0::2].sin(), py[:, :, 1::2].cos()), dim=3).flatten(2)
+    return torch.cat((py, px), dim=2).reshape(oh * ow, 2 * num_pos_feats).contiguous()
+
+
+class TCEWeights:
+    """The context encoding of Dynamic_TCE_volleyball (one layer, four heads; TCE_STBiP_module.py:224-310) in kernel
+    layout.  The heads' downsample2 1x1 convolutions are one tcgen05 GEMM over the feature map (N = 4 x 128, fp32 out);
+    the position embedding enters as a per-pixel additive term posbias = downsample2(pos) + bias, computed once here
+    (plan build: one-time weight preparation, like BatchNorm folding)."""
+
+    def __init__(self, sd, prefix, out_size, device):
+        H = TCE_HEADS
+        w_all = torch.cat([sd[f"{prefix}{h}.downsample2.weight"] for h in range(H)], 0)            # [512, 512, 1, 1]
+        b_all = torch.cat([sd[f"{prefix}{h}.downsample2.bias"] for h in range(H)], 0)
+        if w_all.shape[1] != 512:
+            raise ValueError("Dynamic_TCE_volleyball needs a 512-channel feature map (vgg16 / res18)")
+        self.conv = _Conv(w_all.contiguous(), None, relu=False)
+        oh, ow = out_size
+        pos = _context_position_table(oh, ow, device)
+        self.posbias = torch.addmm(b_all, pos, w_all.view(H * TCE_DIM, 512).t()).contiguous()       # [oh*ow, 512]
+        g = lambda h, n: sd[f"{prefix}{h}.{n}"].contiguous()                                        # noqa: E731
+        self.q = [(g(h, "emb_roi.weight"), g(h, "emb_roi.bias")) for h in range(H)]
+        self.ln1 = [(g(h, "layernorm1.weight"), g(h, "layernorm1.bias")) for h in range(H)]
+        self.ffn0 = [(g(h, "FFN.0.weight"), g(h, "FFN.0.bias")) for h in range(H)]
+        self.ffn3 = [(g(h, "FFN.3.weight"), g(h, "FFN.3.bias")) for h in range(H)]
+        self.ln2 = [(g(h, "layernorm2.weight"), g(h, "layernorm2.bias")) for h in range(H)]
+
+    def __call__(self, x, fm, n):
+        """x [B,T,N,NFB] fp32 person features, fm [F,OH,OW,512] fp16 feature map -> [B,T,N,NFB + 512]."""
+        B, T, N, C = x.shape
+        M, H, D = B * T * N, TCE_HEADS, TCE_DIM
+        F_, oh, ow, _ = fm.shape
+        if self.posbias.shape[0] != oh * ow:
+            raise ValueError(f"feature map {oh}x{ow} does not match cfg.out_size (position table {self.posbias.shape[0]})")
+        xf = x.reshape(M, C)
+        q = torch.empty((H, M, D), dtype=torch.float32, device=x.device)
+        for h in range(H):
+            ops.linear_f32(xf, *self.q[h], out=q[h])                                    # emb_roi (:266)
+        img = self.conv(fm, out_f32=True).view(F_, oh * ow, H * D)                       # downsample2 (:265), no bias
+        ctx = ops.context_attention(q, img, self.posbias, N)                            # :274-280
+        out = torch.empty((B, T, N, C + H * D), dtype=torch.float32, device=x.device)
+        heads = []
+        for h in range(H):
+            c1 = ops.group_layernorm(ctx[h], *self.ln1[h], n_outer=M, outer_stride=D, cols=D, pre=q[h])     # :283
+            f = ops.linear_f32(ops.linear_f32(c1, *self.ffn0[h], relu=True), *self.ffn3[h])                 # FFN :284
+            heads.append(ops.group_layernorm(f, *self.ln2[h], n_outer=M, outer_stride=D, cols=D, pre=c1))   # :285
+        # layout only: [person features | head 0 | ... | head 3] (torch.cat at :308 and infer_model.py:419)
+        out.view(M, C + H * D)[:, :C].copy_(xf)
+        for h in range(H):
+            out.view(M, C + H * D)[:, C + h * D:C + (h + 1) * D].copy_(heads[h])
+        return out
+
+
 # ------------------------------------------------------------------------------------------------
 # the whole path
 # ------------------------------------------------------------------------------------------------
@@ -535,7 +600,7 @@ class DinEngine:
     """Forward plan for Dynamic_volleyball / Dynamic_collective built from a reference-named state_dict."""
 
     def __init__(self, cfg, state_dict, device, dataset="volleyball", frames_per_chunk=None, backbone_plan=None,
-                 bn_train=False):
+                 bn_train=False, tce=False):
         """backbone_plan: a plan built earlier from the same backbone weights (a training loop with the backbone
         frozen changes only the head's weights between steps: the 14.7 M backbone weights are not re-packed)."""
         self.cfg, self.dataset, self.device = cfg, dataset, torch.device(device)
@@ -547,6 +612,10 @@ class DinEngine:
         self.D, self.K = cfg.emb_features, cfg.crop_size[0]
         self.NFB = cfg.num_features_boxes
         self.C = cfg.lite_dim if cfg.lite_dim else self.NFB
+        self.C_embed = self.C         # width of the person features embed() returns
+        self.tce = None
+        if tce:                       # Dynamic_TCE_volleyball: 4 x 128 context features per actor join the DIN input
+            self.C = self.C + TCE_HEADS * TCE_DIM
         self.backbone_name = cfg.backbone
         self.backbone = (backbone_plan if backbone_plan is not None
                          else build_backbone_plan(cfg.backbone, sd, bn_train=bn_train))
@@ -585,6 +654,8 @@ class DinEngine:
         self.fc_act = (sd["fc_activities.weight"].contiguous(), sd["fc_activities.bias"].contiguous())
         self._idx_cache = {}
         self._fm_cache = None
+        if tce:
+            self.tce = TCEWeights(sd, "multilayer_head_embfeature_context_encoding.CET.", tuple(cfg.out_size), self.device)
 
     # -- helpers ---------------------------------------------------------------------------------
     def _box_idx(self, n_frames, n_boxes):
@@ -663,9 +734,9 @@ class DinEngine:
         x = ops.group_layernorm(emb, *self.nl_emb, n_outer=M, outer_stride=self.NFB, cols=self.NFB, relu=True)
         if self.cfg.lite_dim:
             y = ops.linear_f32(x, self.point_w, self.point_b)
-            g = T * N * self.C
+            g = T * N * self.C_embed
             x = ops.group_layernorm(y, *self.point_ln, n_outer=B, outer_stride=g, cols=g, relu=True)
-        return x.view(B, T, N, self.C)
+        return x.view(B, T, N, self.C_embed)
 
     # -- forwards --------------------------------------------------------------------------------
     @torch.no_grad()
@@ -676,6 +747,8 @@ class DinEngine:
         OH, OW = self.cfg.out_size
         assert fm.shape[1:3] == (OH, OW), (tuple(fm.shape), self.cfg.out_size)          # infer_model.py:165
         x = self.embed(fm, boxes.reshape(B * T * N, 4).contiguous().float(), B, T, N)
+        if self.tce is not None:
+            x = self.tce(x, fm, N)                    # [B,T,N,C_person] -> [B,T,N,C_person + 512]  (infer_model.py:413-419)
         g_sz = T * N * self.C
         if self.hier:
             y1 = self.dpis[0](x)

@@ -749,3 +749,19 @@ def pack_flat(tensors, flat, offsets, scale=1.0):
     with _launch(f"pack_flat_{len(tensors)}", 0, 8 * total):
         check(_lib.load().din_pack_flat_f32(arr, len(tensors), _p(flat), float(scale), _stream()), "din_pack_flat_f32")
     return flat
+
+
+def context_attention(q, img, posbias, n):
+    """q [H, M, 128] fp32, img [F, P, H*128] fp32, posbias [P, H*128] fp32 -> ctx [H, M, 128] (M = F * n): per head and
+    actor, softmax attention over the frame's P map positions (din_context_attention_f32)."""
+    _need(q, torch.float32, "q")
+    _need(img, torch.float32, "img")
+    _need(posbias, torch.float32, "posbias")
+    heads, m, d = q.shape
+    frames, pixels = img.shape[0], img.shape[1]
+    assert d == 128 and img.shape[2] == heads * 128 and tuple(posbias.shape) == (pixels, heads * 128) and m == frames * n
+    ctx = torch.empty_like(q)
+    with _launch(f"context_attention_{pixels}px", 4 * m * heads * pixels * 128, 4 * (img.numel() * 2 + 2 * q.numel())):
+        check(_lib.load().din_context_attention_f32(_p(q), _p(img), _p(posbias), _p(ctx), frames, n, pixels, heads,
+                                                    _stream()), "din_context_attention_f32")
+    return ctx

@@ -81,6 +81,7 @@ class _DinTrainFn(torch.autograd.Function):
 
 class _DinModel(nn.Module):
     _dataset = None
+    _tce = False
 
     def _common_init(self, cfg, person_mat_shape, ln_shape):
         self.cfg = cfg
@@ -95,6 +96,16 @@ class _DinModel(nn.Module):
         self.nl_emb_1 = nn.LayerNorm([NFB])
         in_dim = cfg.lite_dim if cfg.lite_dim else NFB
         print_log(cfg.log_path, ("Activate" if cfg.lite_dim else "Deactivate") + " lite model inference.")
+        person_dim = in_dim
+        if self._tce:
+            # TCE module (infer_model.py:283-289): 4 heads x 128 context features join the DIN input (:292)
+            if cfg.lite_dim or N != 12 or cfg.backbone not in ("vgg16", "res18"):
+                raise NotImplementedError(
+                    "Dynamic_TCE_volleyball: the reference's context encoder takes NFB-dimensional person features "
+                    "(lite_dim must be None), asserts 12 actors (TCE_STBiP_module.py:261) and a 512-channel feature map "
+                    "(vgg16 / res18)")
+            self.multilayer_head_embfeature_context_encoding = _ContextEncoding(4, 128, NFB)
+            in_dim = in_dim + 4 * 128
         kw = dict(in_dim=in_dim, person_mat_shape=person_mat_shape, stride=cfg.stride,
                   kernel_size=cfg.ST_kernel_size, dynamic_sampling=cfg.dynamic_sampling,
                   sampling_ratio=cfg.sampling_ratio, group=cfg.group, scale_factor=cfg.scale_factor,
@@ -109,8 +120,8 @@ class _DinModel(nn.Module):
         self.dpi_nl = nn.LayerNorm(ln_shape(T, N, in_dim))
         self.dropout_global = nn.Dropout(p=cfg.train_dropout_prob)
         if cfg.lite_dim:
-            self.point_conv = nn.Conv2d(NFB, in_dim, kernel_size=1, stride=1)
-            self.point_ln = nn.LayerNorm([T, N, in_dim])
+            self.point_conv = nn.Conv2d(NFB, person_dim, kernel_size=1, stride=1)
+            self.point_ln = nn.LayerNorm([T, N, person_dim])
         self.fc_activities = nn.Linear(in_dim, cfg.num_activities)
         for m in self.modules():
             if isinstance(m, nn.Linear):
@@ -157,7 +168,7 @@ class _DinModel(nn.Module):
             plan = slot["engine"].backbone if (slot is not None and slot["bb_key"] == bb_key) else None
             with torch.cuda.device(dev):
                 eng = DinEngine(self.cfg, _pc.named_tensors(self), dev, dataset=self._dataset, backbone_plan=plan,
-                                bn_train=bn_train)
+                                bn_train=bn_train, tce=self._tce)
             slot = own._plans.put(dev, key=key, bb_key=bb_key, engine=eng)
         return slot["engine"]
 
@@ -176,6 +187,9 @@ class _DinModel(nn.Module):
                     "train mode with BatchNorm batch statistics is implemented for the ResNet-18 backbone (all of its "
                     "BatchNorm layers in train mode): freeze BN as the reference does with cfg.set_bn_eval "
                     "(train_net_dynamic.py:101-102, model.apply(set_bn_eval))")
+        if self._tce and self.training:
+            raise NotImplementedError("Dynamic_TCE_volleyball runs inference / evaluation on the sm_100a path; its "
+                                      "training step is not implemented (call model.eval())")
         eng = self.engine()
         if not self.training:
             if self._dataset == "collective":
@@ -200,6 +214,48 @@ class Dynamic_volleyball(_DinModel):
     def __init__(self, cfg):
         super().__init__()
         self._common_init(cfg, (10, 12), lambda T, N, C: [T, N, C])     # person_mat_shape hard-coded :77
+
+    def forward(self, batch_data):
+        images_in, boxes_in = batch_data
+        self._check_mode(images_in)
+        with torch.cuda.device(images_in.device):
+            scores = self._run(_as_frames(images_in), boxes_in.float())
+        return {"activities": scores}
+
+
+class _ContextHead(nn.Module):
+    """Parameter container of one EmbfeatureContextEncodingTransformer head, layer 1 (TCE_STBiP_module.py:224-250)."""
+
+    def __init__(self, dim, nfb, dropout=0.1):
+        super().__init__()
+        self.downsample2 = nn.Conv2d(512, dim, kernel_size=1, stride=1)
+        self.emb_roi = nn.Linear(nfb, dim, bias=True)
+        self.dropout = nn.Dropout(dropout)
+        self.layernorm1 = nn.LayerNorm(dim)
+        self.FFN = nn.Sequential(nn.Linear(dim, dim, bias=True), nn.ReLU(inplace=True), nn.Dropout(dropout),
+                                 nn.Linear(dim, dim, bias=True))
+        self.layernorm2 = nn.LayerNorm(dim)
+
+
+class _ContextEncoding(nn.Module):
+    """MultiHeadLayerEmbfeatureContextEncoding(heads, 1 layer, ...) (TCE_STBiP_module.py:289-310): state_dict keys
+    `CET.<h>.{downsample2, emb_roi, layernorm1, FFN.0, FFN.3, layernorm2}.{weight, bias}`.  Never called: the plan
+    (din_b200.engine.TCEWeights) runs the four heads as one tcgen05 GEMM + the context attention kernel."""
+
+    def __init__(self, heads, dim, nfb):
+        super().__init__()
+        self.CET = nn.ModuleList([_ContextHead(dim, nfb) for _ in range(heads)])
+
+
+class Dynamic_TCE_volleyball(_DinModel):
+    """reference infer_model.py:237-468: Dynamic_volleyball with the temporal-context-encoding module prepended to the
+    dynamic inference (inference / evaluation on the CUDA path)."""
+    _dataset = "volleyball"
+    _tce = True
+
+    def __init__(self, cfg):
+        super().__init__()
+        self._common_init(cfg, (10, 12), lambda T, N, C: [T, N, C])
 
     def forward(self, batch_data):
         images_in, boxes_in = batch_data
@@ -234,7 +290,6 @@ def _out_of_scope(name):
 
 
 # names the reference trainer's registry resolves at import time (train_net_dynamic.py:66-73)
-Dynamic_TCE_volleyball = _out_of_scope("Dynamic_TCE_volleyball")
 PCTDM_volleyball = _out_of_scope("PCTDM_volleyball")
 HiGCIN_volleyball = _out_of_scope("HiGCIN_volleyball")
 AT_volleyball = _out_of_scope("AT_volleyball")

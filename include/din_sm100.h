@@ -488,6 +488,17 @@ DIN_API int din_bn_bwd(const void* g, const void* z, int z_is_f32, const float* 
                const float* gamma, float* sums, void* dz, float* dbeta, float* dgamma, const float* inv_scale,
                long long rows, int c, void* stream);
 
+/* ---- Dynamic_TCE_volleyball's context encoding (infer_model.py:237-468, infer_module/TCE_STBiP_module.py:224-310) ----
+ * Every actor attends over its frame's feature map, per head:
+ *   a[n][px] = <q[n], x[px]>,  A = softmax over px,  ctx[n] = sum_px A[n][px] x[px],   x = img + posbias.
+ * q, ctx  : fp32 [heads][frames*n][128]  (emb_roi output per head / the attended context)
+ * img     : fp32 [frames][pixels][heads*128]  = the heads' downsample2 1x1 convolutions of the feature map, without bias
+ *           (one din_conv2d_nhwc_f16 with out_f32)
+ * posbias : fp32 [pixels][heads*128] = downsample2(Context_PositionEmbeddingSine table) + bias (a constant of the plan)
+ * Replaces: torch.matmul / F.softmax / torch.matmul at TCE_STBiP_module.py:274-280.  n <= 16, n*pixels*4 B <= ~130 KB. */
+DIN_API int din_context_attention_f32(const float* q, const float* img, const float* posbias, float* ctx, int frames,
+                                      int n, int pixels, int heads, void* stream);
+
 /* ---- data-parallel training: gradients -> one flat fp32 buffer (csrc/flat.cu) -----------------------------------
  * flat[dst_offset + i] = scale * src[i] for every job, ALL jobs in one launch (<= 96 per launch, more are split).
  * The flat buffer is what the step's all-reduce runs on (ncclAllReduce through torch.distributed); `scale` carries

@@ -39,6 +39,8 @@ def model_cases():
         "inv3_full": (pc("inv3", (139, 203), emb_features=1056, num_frames=2, num_boxes=4, lite_dim=None), 2),
         "collective_res18": (pc("res18", (96, 144), dataset="collective", num_frames=3, num_boxes=13,
                                 lite_dim=None, ST_kernel_size=(3, 3), num_activities=4), 3),
+        # Dynamic_TCE_volleyball (infer_model.py:237-468): context encoding prepended to DIN; N = 12 is asserted (:261)
+        "tce_vgg16": (pc("vgg16", (96, 160), num_frames=3, num_boxes=12, lite_dim=None, tce=True), 2),
     }
 
 
@@ -151,10 +153,14 @@ def main():
         return main_grads()
     if "--basenet-only" in sys.argv:
         return main_basenet()
-    main_basenet()
-    main_grads()
-    main_basenet_grads()
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None      # one whole-model fixture
+    if only is None:
+        main_basenet()
+        main_grads()
+        main_basenet_grads()
     for name, (pc, B) in model_cases().items():
+        if only is not None and name != only:
+            continue
         bb = O.build_backbone(pc.backbone)
         sd = O.make_state_dict(pc, seed=0, backbone=bb)
         batch = O.make_inputs(pc, B, seed=0)
@@ -163,6 +169,8 @@ def main():
                     "weights_checksum": checksum(sd.values()), "inputs_checksum": checksum(batch)},
                    os.path.join(OUT, f"model_{name}.pt"))
         print(name, logits[0, :4].tolist())
+    if only is not None:
+        return
     # module-level: the reference Dynamic_Person_Inference with randomised p_conv / scale_conv
     g = torch.Generator().manual_seed(42)
     for name, (kernel, ratios, T, N, beta) in {

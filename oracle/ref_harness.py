@@ -155,7 +155,9 @@ def build_ref_model(pc, sd):
     import io
     with contextlib.redirect_stdout(io.StringIO()):
         with _isolated_import():
-            model = (im.Dynamic_collective if pc.dataset == "collective" else im.Dynamic_volleyball)(cfg)
+            cls = im.Dynamic_collective if pc.dataset == "collective" else \
+                (im.Dynamic_TCE_volleyball if getattr(pc, "tce", False) else im.Dynamic_volleyball)
+            model = cls(cfg)
     missing, unexpected = model.load_state_dict(sd, strict=True), None
     model.eval()
     if pc.hierarchical_inference:

@@ -29,7 +29,9 @@ def _run_case(cuda, pc, B, seed=0, tol=TOL):
         setattr(cfg, k, getattr(pc, k))
     cfg.sampling_ratio = list(pc.sampling_ratio)
     cfg.num_features_gcn = pc.num_features_boxes
-    model = (IM.Dynamic_collective if pc.dataset == "collective" else IM.Dynamic_volleyball)(cfg)
+    cls = IM.Dynamic_collective if pc.dataset == "collective" else \
+        (IM.Dynamic_TCE_volleyball if pc.tce else IM.Dynamic_volleyball)
+    model = cls(cfg)
     missing = model.load_state_dict(sd, strict=True)
     model = model.to(cuda).eval()
     with torch.no_grad():
@@ -85,3 +87,16 @@ def test_collective_res18(cuda):
 def test_config1_vgg16_720p(cuda):
     """BASELINE config 1: VGG-16, lite 128, B=1, T=3, N=12 at 720x1280 (the reference's CPU-runnable case)."""
     _run_case(cuda, _pc("vgg16", (720, 1280), num_frames=3, num_boxes=12), B=1)
+
+
+def test_tce_vgg16(cuda):
+    """Dynamic_TCE_volleyball (infer_model.py:237-468): the context encoder (4 attention heads over the feature map with
+    the sine position embedding) prepended to DIN, C = 1024 + 512.  Same configuration as tests/golden/model_tce_vgg16.pt,
+    on which the oracle restatement equals the reference's own class bit for bit."""
+    _run_case(cuda, _pc("vgg16", (96, 160), num_frames=3, num_boxes=12, lite_dim=None, tce=True), B=2)
+
+
+def test_tce_res18(cuda):
+    # (softmax attention over the map amplifies the fp16 rounding of the feature map it scores: on a 3 x 5 map with two
+    # frames the logits error measured 2.7e-3; the reference's recipe shapes have 40-80x the pixels and 5x the frames)
+    _run_case(cuda, _pc("res18", (288, 480), num_frames=5, num_boxes=12, lite_dim=None, tce=True), B=1)

@@ -39,6 +39,17 @@ def test_config4_vgg16_hierarchical_st_factorized_T10_N12_720p(cuda):
          ST_kernel_size=[(1, 3), (3, 1)], hierarchical_inference=True)
 
 
+def test_tce_vgg16_T10_N12_720p(cuda):
+    """Dynamic_TCE_volleyball at the stage-2 recipe's size: attention over the 22 x 40 map, DIN on 1536 features."""
+    _run(cuda, "vgg16", (720, 1280), 1, num_frames=10, num_boxes=12, lite_dim=None, tce=True)
+
+
+# (No ResNet-18 variant of the TCE case at 720p: with the synthetic weights its feature map reaches |x| = 370 and the
+# attention logits +-2000, i.e. the softmax is a hard arg-max over the map -- rounding ONLY the final feature map to fp16 in
+# an otherwise fp32 CPU evaluation already moves the logits by 1.6e-3.  That ill-conditioned sample tests the weight
+# generator, not the kernels; tests/test_e2e_gpu.py::test_tce_res18 covers the ResNet-18 branch at 288 x 480: 2.8e-4.)
+
+
 def test_config5_collective_res18_480x720_T10_ragged_actors(cuda):
     """BASELINE configs[4]: Collective, ResNet-18 at 480x720, up to 13 actors, a different actor count per clip."""
     import din_oracle as O

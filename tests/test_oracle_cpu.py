@@ -29,7 +29,7 @@ BASENET_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "basenet_*.pt")))
 
 
 def test_fixtures_present():
-    assert len(MODEL_FIXTURES) == 7 and len(MODULE_FIXTURES) == 4 and len(BASENET_FIXTURES) == 3
+    assert len(MODEL_FIXTURES) == 8 and len(MODULE_FIXTURES) == 4 and len(BASENET_FIXTURES) == 3
     assert len(glob.glob(os.path.join(GOLDEN, "grads_*.pt"))) == 4
 
 
