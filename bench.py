@@ -557,7 +557,8 @@ def main():
                      "whole_path_tflops": value * gflop_per_clip / 1e3,
                      "whole_path_frac": value * gflop_per_clip / 1e3 / world / peaks["tflops_sustained"],
                      "other_kernels_ms": {k: round(v, 3) for k, v in sorted(other.items())},
-                     "per_layer_tflops": {n: round(f / (t / 1e3) / 1e12, 1) for n, (f, t, c) in per_layer.items()}},
+                     "per_layer_tflops": {n: round(f / (t / 1e3) / 1e12, 1) for n, (f, t, c) in per_layer.items()},
+                     "per_layer_ms_per_step": {n: round(t / args.steps, 3) for n, (f, t, c) in per_layer.items()}},
         "clocks": clocks.summary(),
         "gpu_launches": launches,
     }

@@ -122,7 +122,7 @@ extern "C" {
 // 2: + uint8 ingest, loss / metrics, backward entry points
 // 3: + batched weight packing, dgrad with fused ReLU backward, ResNet-18 backward helpers, batch-statistics BatchNorm
 // 4: + din_roi_align_nhwc_f16_f32out, din_tmap_cache_stats (tensor maps cached per pointer + shape)
-int din_abi_version(void) { return 4; }
+int din_abi_version(void) { return 5; }
 
 const char* din_last_error_string(void) { return g_err; }
 

@@ -62,6 +62,8 @@ struct ConvKParams {
   int th, tw, tw_log2;
   int kh, kw, stride, pad_h, pad_w;
   int n_cblk;                 // c_in / 64
+  int k16_last;               // K = 16 MMA steps that hold real channels in the LAST 64-channel block (1..4): c_in = 32 or 80
+                              // would otherwise spend half / 3 of 8 of their tensor work on TMA-zero-filled columns
   int c_in;
   int relu, out_f32, pool2;
   // A-operand staging
@@ -80,6 +82,11 @@ struct ConvKParams {
   const __half* residual;
   int res_mask;               // 0: y += residual;  1: y *= [residual > 0]  (ReLU backward fused into a dgrad convolution)
   void* y;
+  // branch-group launches (several 1x1 convolutions of one Inception block as ONE GEMM over the shared input):
+  // output columns >= split_col go to y2 (its own channel stride), columns in [norelu_lo, norelu_hi) skip the ReLU
+  // (the pool branch: its average pool + bias + ReLU run after the GEMM).  All three are multiples of 32.
+  int split_col, y2_c_stride, norelu_lo, norelu_hi;
+  void* y2;
 };
 
 constexpr int kBM = 128;
@@ -238,10 +245,11 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvKParams& p, uint32
           }
           continue;
         }
+        const bool relu_c = p.relu != 0 && !(col0 >= p.norelu_lo && col0 < p.norelu_hi);   // warp-uniform
         __half2 h[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) {   // ReLU fused into the conversion (cvt.rn.relu.f16x2.f32)
-          const uint32_t u = pack_half2(f[2 * e], f[2 * e + 1], p.relu != 0);
+          const uint32_t u = pack_half2(f[2 * e], f[2 * e + 1], relu_c);
           h[e] = *reinterpret_cast<const __half2*>(&u);
         }
         if (p.pool2) {
@@ -275,11 +283,14 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvKParams& p, uint32
         }
         __syncwarp();
         if (col0 + unit * 8 < p.c_out) {
+          const bool second = col0 >= p.split_col;                       // warp-uniform (32-column granularity)
+          __half* ybase = reinterpret_cast<__half*>(second ? p.y2 : p.y) + (second ? col0 - p.split_col : col0) + unit * 8;
+          const size_t ycs = static_cast<size_t>(second ? p.y2_c_stride : p.y_c_stride);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             if (k < n_rounds && st_valid[k]) {
               const uint4 o = *reinterpret_cast<const uint4*>(scratch + src_lane[k] * kEpiPitch + unit * 16);
-              __half* yp = reinterpret_cast<__half*>(p.y) + st_pix[k] * p.y_c_stride + col0 + unit * 8;
+              __half* yp = ybase + st_pix[k] * ycs;
               *reinterpret_cast<uint4*>(yp) = o;
             }
           }
@@ -437,9 +448,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
         uint32_t accum = 0;
+        int cb = 0;                                   // channel block of A group g (HALO: g; TAP: g % n_cblk)
         for (int g = 0; g < a_groups; ++g) {
           mbar_wait(&a_full[sa], pa);
           const uint32_t a_lo = a_lo0 + sa * a_step;
+          const int ksteps = (cb == p.n_cblk - 1) ? p.k16_last : kBK / 16;     // warp-uniform
+          if (++cb == p.n_cblk) cb = 0;
           if constexpr (TB3 > 0) {
             // static 3x3: 9 taps, halo pitch 10 rows -> tap (ky,kx) starts (ky*10 + kx) * 8 sixteen-byte units in
 #pragma unroll
@@ -455,8 +469,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                   const uint32_t bl = b_lo + static_cast<uint32_t>(tt * (kBBytes >> 4));
 #pragma unroll
                   for (int k = 0; k < kBK / 16; ++k)
-                    umma_f16_ss(d_tmem, desc64(al + 2u * k, a_hi), desc64(bl + 2u * k, b_hi), idesc,
-                                (bg == 0 && tt == 0 && k == 0) ? accum : 1u);
+                    if (k < ksteps)
+                      umma_f16_ss(d_tmem, desc64(al + 2u * k, a_hi), desc64(bl + 2u * k, b_hi), idesc,
+                                  (bg == 0 && tt == 0 && k == 0) ? accum : 1u);
                 }
                 umma_commit(&b_empty[sb]);
               }
@@ -477,8 +492,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 if (leader) {
 #pragma unroll
                   for (int k = 0; k < kBK / 16; ++k)   // +32 bytes (2 x 16-byte units) per K=16 slice
-                    umma_f16_ss(d_tmem, desc64(al + 2u * k, a_hi), desc64(b_lo + 2u * k, b_hi), idesc,
-                                (k == 0) ? accum : 1u);
+                    if (k < ksteps)
+                      umma_f16_ss(d_tmem, desc64(al + 2u * k, a_hi), desc64(b_lo + 2u * k, b_hi), idesc,
+                                  (k == 0) ? accum : 1u);
                 }
                 accum = 1;
                 if (p.split == 1 || (t & 1)) {   // the lo part re-uses the A window of its hi part
@@ -652,6 +668,7 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         for (int g = 0; g < p.n_cblk; ++g) {
           mbar_wait(&a_full[sa], pa);
           const uint32_t a_lo = a_lo0 + sa * a_step;
+          const int ksteps = (g == p.n_cblk - 1) ? p.k16_last : kBK / 16;      // warp-uniform
 #pragma unroll
           for (int bg = 0; bg < 9 / TB3; ++bg) {
             if (!p.b_resident || it == 0) mbar_wait(&b_full[sb], pb);   // resident weights arrive once
@@ -665,8 +682,9 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 const uint32_t bl = b_lo + static_cast<uint32_t>(tt * (kBHalfBytes >> 4));
 #pragma unroll
                 for (int k = 0; k < kBK / 16; ++k)
-                  umma_f16_ss_2cta(d_tmem, desc64(al + 2u * k, a_hi), desc64(bl + 2u * k, b_hi), idesc,
-                                   (bg == 0 && tt == 0 && k == 0) ? accum : 1u);
+                  if (k < ksteps)
+                    umma_f16_ss_2cta(d_tmem, desc64(al + 2u * k, a_hi), desc64(bl + 2u * k, b_hi), idesc,
+                                     (bg == 0 && tt == 0 && k == 0) ? accum : 1u);
               }
               if (!p.b_resident) umma_commit_2cta(&b_empty[sb]);
             }
@@ -1339,12 +1357,18 @@ extern "C" int din_pack_conv_weight_f16(const float* w_oihw, const float* scale,
 
 namespace {
 int conv2d_launch(const DinConvDesc* d, const void* x, const void* w_packed, const float* bias, const void* residual,
-                  int res_mask, void* y, void* stream);
+                  int res_mask, void* y, void* stream, const DinConvBranchOut* br, void* y2);
 }  // namespace
 
 extern "C" int din_conv2d_nhwc_f16(const DinConvDesc* d, const void* x, const void* w_packed, const float* bias,
                                    const void* residual, void* y, void* stream) {
-  return conv2d_launch(d, x, w_packed, bias, residual, 0, y, stream);
+  return conv2d_launch(d, x, w_packed, bias, residual, 0, y, stream, nullptr, nullptr);
+}
+
+extern "C" int din_conv2d_branches_nhwc_f16(const DinConvDesc* d, const DinConvBranchOut* br, const void* x,
+                                            const void* w_packed, const float* bias, void* y, void* y2, void* stream) {
+  DIN_CHECK_ARG(br != nullptr, "din_conv2d_branches_nhwc_f16: null branch descriptor");
+  return conv2d_launch(d, x, w_packed, bias, nullptr, 0, y, stream, br, y2);
 }
 
 namespace {
@@ -1395,12 +1419,13 @@ extern "C" int din_conv3x3_stem_pair_nhwc_f16(const void* x, int x_is_u8, const 
   DIN_CHECK_ARG(total_tiles < INT32_MAX / 2, "%s: too many tiles", who);
   p.num_tiles = static_cast<int>(total_tiles);
   p.kh = 3; p.kw = 3; p.stride = 1; p.pad_h = 1; p.pad_w = 1;
-  p.n_cblk = 1; p.c_in = kBK;
+  p.n_cblk = 1; p.c_in = kBK; p.k16_last = kBK / 16;
   p.relu = relu2; p.out_f32 = 0; p.pool2 = pool2;
   p.split = 1; p.k_part = 9 * kBK;
   p.fd_ntn = make_fastdiv(1); p.fd_tpi = make_fastdiv(p.tiles_per_img); p.fd_tx = make_fastdiv(p.tiles_x);
   p.bias = nullptr;            // conv1_2's bias is added by the kernel's bias MMA (FusedStemParams.b2)
   p.residual = nullptr; p.res_mask = 0; p.y = y;
+  p.split_col = INT32_MAX; p.y2 = nullptr; p.y2_c_stride = 0; p.norelu_lo = p.norelu_hi = 0;
   p.halo = 1; p.halo_rows = kHaloH; p.pitch_rows = kHaloW; p.per_row_loads = 0; p.use_base_offset = 0;
   p.a_stage_bytes = ((kHaloRows * 128) + 1023) & ~1023;
   p.a_tx_bytes = 0;
@@ -1463,12 +1488,12 @@ extern "C" int din_conv2d_relu_bwd_nhwc_f16(const DinConvDesc* d, const void* dz
   DIN_CHECK_ARG(y_saved != nullptr, "din_conv2d_relu_bwd_nhwc_f16: y_saved is NULL");
   DIN_CHECK_ARG(d && !d->relu && !d->pool2 && !d->out_f32,
                 "din_conv2d_relu_bwd_nhwc_f16: relu / pool2 / out_f32 must be 0 in the descriptor");
-  return conv2d_launch(d, dz, w_packed, nullptr, y_saved, 1, dx, stream);
+  return conv2d_launch(d, dz, w_packed, nullptr, y_saved, 1, dx, stream, nullptr, nullptr);
 }
 
 namespace {
 int conv2d_launch(const DinConvDesc* d, const void* x, const void* w_packed, const float* bias, const void* residual,
-                  int res_mask, void* y, void* stream) {
+                  int res_mask, void* y, void* stream, const DinConvBranchOut* br, void* y2) {
   DIN_CHECK_ARG(d && x && w_packed && y, "din_conv2d_nhwc_f16: null pointer");
   DIN_CHECK_ARG(d->n > 0 && d->h > 0 && d->w > 0, "din_conv2d_nhwc_f16: bad extent n=%d h=%d w=%d", d->n, d->h,
                 d->w);
@@ -1478,8 +1503,19 @@ int conv2d_launch(const DinConvDesc* d, const void* x, const void* w_packed, con
                 "din_conv2d_nhwc_f16: x_c_stride=%d must be >= c_in and a multiple of 8", d->x_c_stride);
   DIN_CHECK_ARG(d->c_out > 0 && d->c_out % 8 == 0 && d->c_out <= 2048,
                 "din_conv2d_nhwc_f16: c_out=%d must be a multiple of 8 and <= 2048", d->c_out);
-  DIN_CHECK_ARG(d->y_c_stride >= d->c_out && d->y_c_stride % 8 == 0,
+  DIN_CHECK_ARG(d->y_c_stride >= (br ? br->split_col : d->c_out) && d->y_c_stride % 8 == 0,
                 "din_conv2d_nhwc_f16: y_c_stride=%d must be >= c_out and a multiple of 8", d->y_c_stride);
+  if (br) {
+    DIN_CHECK_ARG(y2 && (reinterpret_cast<uintptr_t>(y2) & 15) == 0, "din_conv2d_branches_nhwc_f16: y2 must be 16-byte aligned");
+    DIN_CHECK_ARG(br->split_col > 0 && br->split_col < d->c_out && br->split_col % 32 == 0 &&
+                      br->y2_c_stride >= d->c_out - br->split_col && br->y2_c_stride % 8 == 0,
+                  "din_conv2d_branches_nhwc_f16: split_col=%d (multiple of 32 inside (0, c_out)) / y2_c_stride=%d",
+                  br->split_col, br->y2_c_stride);
+    DIN_CHECK_ARG(br->norelu_lo % 32 == 0 && br->norelu_hi % 32 == 0 && br->norelu_lo >= 0 && br->norelu_lo <= br->norelu_hi,
+                  "din_conv2d_branches_nhwc_f16: the no-ReLU column range must be multiples of 32");
+    DIN_CHECK_ARG(!d->pool2 && !d->out_f32 && !residual,
+                  "din_conv2d_branches_nhwc_f16: pool2 / out_f32 / residual are not supported");
+  }
   DIN_CHECK_ARG(d->kh >= 1 && d->kw >= 1 && d->kh * d->kw <= 49, "din_conv2d_nhwc_f16: bad filter %dx%d", d->kh,
                 d->kw);
   DIN_CHECK_ARG(d->stride == 1 || d->stride == 2, "din_conv2d_nhwc_f16: stride=%d unsupported", d->stride);
@@ -1524,10 +1560,13 @@ int conv2d_launch(const DinConvDesc* d, const void* x, const void* w_packed, con
   // N tile: the variant that wastes the fewest MMA columns; ties go to the wider tile
   int bn = 256;
   {
+    // cost of covering c_out = N tiles x (columns + a fixed per-tile share worth ~64 columns: every N tile re-reads the A
+    // operand and a narrow MMA keeps the tensor pipe less busy).  Without that share c_out = 704 (Inception's merged
+    // branch heads) ran as 11 tiles of 64 columns at 308 TFLOP/s.
     const int cand[5] = {256, 192, 128, 96, 64};
     int best_cost = INT32_MAX;
     for (int i = 0; i < 5; ++i) {
-      const int cost = ((d->c_out + cand[i] - 1) / cand[i]) * cand[i];
+      const int cost = ((d->c_out + cand[i] - 1) / cand[i]) * (cand[i] + 64);
       if (cost < best_cost) { best_cost = cost; bn = cand[i]; }
     }
   }
@@ -1540,11 +1579,14 @@ int conv2d_launch(const DinConvDesc* d, const void* x, const void* w_packed, con
   // (tensor-map extent = the real c_in) and by the packed weight's zero columns on the weight side
   p.n_cblk = (d->c_in + kBK - 1) / kBK;
   p.c_in = p.n_cblk * kBK;
+  p.k16_last = (d->c_in - (p.n_cblk - 1) * kBK + 15) / 16;
   p.relu = d->relu; p.out_f32 = d->out_f32; p.pool2 = d->pool2;
   p.split = d->w_split == 2 ? 2 : 1;
   p.k_part = d->kh * d->kw * p.c_in;
   p.fd_ntn = make_fastdiv(p.n_tiles_n); p.fd_tpi = make_fastdiv(p.tiles_per_img); p.fd_tx = make_fastdiv(p.tiles_x);
   p.bias = bias; p.residual = static_cast<const __half*>(residual); p.res_mask = res_mask; p.y = y;
+  p.split_col = br ? br->split_col : INT32_MAX; p.y2 = y2; p.y2_c_stride = br ? br->y2_c_stride : 0;
+  p.norelu_lo = br ? br->norelu_lo : 0; p.norelu_hi = br ? br->norelu_hi : 0;
 
   // A staging geometry
   uint32_t box_w, box_h;

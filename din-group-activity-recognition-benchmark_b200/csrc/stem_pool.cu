@@ -229,8 +229,12 @@ pool_fixed_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n, i
 // values are still summed in scan order, so the result is bit-identical to pool_fixed_kernel<1, 3, 1>.
 constexpr int kAvgRows = 8;
 
+// BIAS: y = (relu)(avg + bias[c]) -- the tail of an Inception pool branch whose 1x1 convolution ran before the pool
+// (din_conv2d_branches_nhwc_f16).
+template <bool BIAS>
 __global__ void __launch_bounds__(256)
-avgpool3s1_strip_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n, int h, int w, int c8, int xs8, int ys8) {
+avgpool3s1_strip_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n, int h, int w, int c8, int xs8, int ys8,
+                        const float* __restrict__ bias = nullptr, int relu = 0) {
   const int strips = (h + kAvgRows - 1) / kAvgRows;
   const size_t total = static_cast<size_t>(n) * strips * w * c8;
   const size_t i = blockIdx.x * static_cast<size_t>(256) + threadIdx.x;
@@ -252,6 +256,11 @@ avgpool3s1_strip_kernel(const __half* __restrict__ x, __half* __restrict__ y, in
     for (int kx = 0; kx < 3; ++kx) row[kx] = __ldg(base + (static_cast<size_t>(cy) * w + cx[kx]) * xs8);
     return iy >= 0 && iy < h;
   };
+  float bv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (BIAS) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * cv), b1 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * cv + 1);
+    bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+  }
   const int oy0 = strip * kAvgRows;
   oky[0] = load_row(oy0 - 1, win[0]);
   oky[1] = load_row(oy0, win[1]);
@@ -278,7 +287,14 @@ avgpool3s1_strip_kernel(const __half* __restrict__ x, __half* __restrict__ y, in
     uint4 o;
     __half2* oh2 = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) oh2[e] = __floats2half2_rn(acc[2 * e] * (1.0f / 9.0f), acc[2 * e + 1] * (1.0f / 9.0f));
+    for (int e = 0; e < 4; ++e) {
+      float a = acc[2 * e] * (1.0f / 9.0f), b = acc[2 * e + 1] * (1.0f / 9.0f);
+      if (BIAS) {
+        a += bv[2 * e]; b += bv[2 * e + 1];
+        if (relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+      }
+      oh2[e] = __floats2half2_rn(a, b);
+    }
     reinterpret_cast<uint4*>(y)[((static_cast<size_t>(img) * h + oy) * w + ox) * ys8 + cv] = o;
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) { win[0][kx] = win[1][kx]; win[1][kx] = win[2][kx]; }
@@ -287,31 +303,58 @@ avgpool3s1_strip_kernel(const __half* __restrict__ x, __half* __restrict__ y, in
   }
 }
 
-// Bilinear resize, align_corners=True (F.interpolate at infer_model.py:169), NHWC fp16, 8 channels/thread.
+// Bilinear resize, align_corners=True (F.interpolate at infer_model.py:169), NHWC fp16; torch's upsample_bilinear2d
+// arithmetic: scale = (in - 1) / (out - 1), (1-ly)*((1-lx)*a + lx*b) + ly*((1-lx)*c + lx*d).
+// One thread per (8 channels, output column, strip of kUpRows output rows): the two source rows of an
+// output row stay in registers and are re-used by the next output row (an upscale by ~2 advances the source row by 0 or
+// 1), so a strip of 8 output rows loads ~10 vectors instead of 32.  One output per thread was bound by L2 -> SM traffic
+// (4 x 16 bytes loaded per 16 bytes stored: 6.7 GB per 80 Inception-v3 frames, 1.2 ms for a 1.7 GB output).  Same
+// arithmetic per output element as the one-output-per-thread kernel it replaced: bit-identical.
+constexpr int kUpRows = 8;
+
 __global__ void __launch_bounds__(256)
-upsample_bilinear_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n, int h, int w, int c8,
-                         int xs8, int ys8, int oh, int ow) {
-  const size_t total = static_cast<size_t>(n) * oh * ow * c8;
-  // torch: scale = (in - 1) / (out - 1) for align_corners=True (0 when out == 1)
+upsample_bilinear_strip_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n, int h, int w, int c8,
+                               int xs8, int ys8, int oh, int ow) {
+  const int strips = (oh + kUpRows - 1) / kUpRows;
+  const size_t total = static_cast<size_t>(n) * strips * ow * c8;
+  const size_t i = blockIdx.x * static_cast<size_t>(256) + threadIdx.x;
+  if (i >= total) return;
   const float sy = oh > 1 ? static_cast<float>(h - 1) / static_cast<float>(oh - 1) : 0.0f;
   const float sx = ow > 1 ? static_cast<float>(w - 1) / static_cast<float>(ow - 1) : 0.0f;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int cv = static_cast<int>(i % c8);
-    size_t t = i / c8;
-    const int ox = static_cast<int>(t % ow);
-    t /= ow;
-    const int oy = static_cast<int>(t % oh);
-    const int img = static_cast<int>(t / oh);
-    const float fy = sy * static_cast<float>(oy), fx = sx * static_cast<float>(ox);
-    const int y0 = min(static_cast<int>(fy), h - 1), x0 = min(static_cast<int>(fx), w - 1);
-    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
-    const float ly = fy - static_cast<float>(y0), lx = fx - static_cast<float>(x0);
-    const uint4* base = reinterpret_cast<const uint4*>(x) + static_cast<size_t>(img) * h * w * xs8 + cv;
-    const uint4 v00 = __ldg(base + (static_cast<size_t>(y0) * w + x0) * xs8);
-    const uint4 v01 = __ldg(base + (static_cast<size_t>(y0) * w + x1) * xs8);
-    const uint4 v10 = __ldg(base + (static_cast<size_t>(y1) * w + x0) * xs8);
-    const uint4 v11 = __ldg(base + (static_cast<size_t>(y1) * w + x1) * xs8);
+  const int cv = static_cast<int>(i % c8);
+  size_t t = i / c8;
+  const int ox = static_cast<int>(t % ow);
+  t /= ow;
+  const int strip = static_cast<int>(t % strips);
+  const int img = static_cast<int>(t / strips);
+  const float fx = sx * static_cast<float>(ox);
+  const int x0 = min(static_cast<int>(fx), w - 1);
+  const int x1 = min(x0 + 1, w - 1);
+  const float lx = fx - static_cast<float>(x0);
+  const uint4* base = reinterpret_cast<const uint4*>(x) + static_cast<size_t>(img) * h * w * xs8 + cv;
+  uint4 v00 = make_uint4(0, 0, 0, 0), v01 = v00, v10 = v00, v11 = v00;
+  int cy0 = -1, cy1 = -1;
+#pragma unroll
+  for (int r = 0; r < kUpRows; ++r) {
+    const int oy = strip * kUpRows + r;
+    if (oy >= oh) break;
+    const float fy = sy * static_cast<float>(oy);
+    const int y0 = min(static_cast<int>(fy), h - 1);
+    const int y1 = min(y0 + 1, h - 1);
+    const float ly = fy - static_cast<float>(y0);
+    if (y0 != cy0) {
+      if (y0 == cy1) { v00 = v10; v01 = v11; }
+      else {
+        v00 = __ldg(base + (static_cast<size_t>(y0) * w + x0) * xs8);
+        v01 = __ldg(base + (static_cast<size_t>(y0) * w + x1) * xs8);
+      }
+      cy0 = y0;
+    }
+    if (y1 != cy1) {
+      v10 = __ldg(base + (static_cast<size_t>(y1) * w + x0) * xs8);
+      v11 = __ldg(base + (static_cast<size_t>(y1) * w + x1) * xs8);
+      cy1 = y1;
+    }
     const __half2* a = reinterpret_cast<const __half2*>(&v00);
     const __half2* b = reinterpret_cast<const __half2*>(&v01);
     const __half2* c = reinterpret_cast<const __half2*>(&v10);
@@ -322,7 +365,6 @@ upsample_bilinear_kernel(const __half* __restrict__ x, __half* __restrict__ y, i
     for (int e = 0; e < 4; ++e) {
       const float2 fa = __half22float2(a[e]), fb = __half22float2(b[e]);
       const float2 fc = __half22float2(c[e]), fd = __half22float2(d[e]);
-      // torch's upsample_bilinear2d: (1-ly)*((1-lx)*a + lx*b) + ly*((1-lx)*c + lx*d)
       const float r0 = (1.0f - ly) * ((1.0f - lx) * fa.x + lx * fb.x) + ly * ((1.0f - lx) * fc.x + lx * fd.x);
       const float r1 = (1.0f - ly) * ((1.0f - lx) * fa.y + lx * fb.y) + ly * ((1.0f - lx) * fc.y + lx * fd.y);
       oh2[e] = __floats2half2_rn(r0, r1);
@@ -403,8 +445,8 @@ static int pool_common(const char* who, int avg, const void* x, void* y, int n, 
                                                                              y_c_stride / 8, oh, ow, pad)
     else if (avg && k == 3 && stride == 1 && pad == 1) {
       const size_t strip_threads = static_cast<size_t>(n) * ((h + kAvgRows - 1) / kAvgRows) * w * (c / 8);
-      avgpool3s1_strip_kernel<<<static_cast<int>((strip_threads + 255) / 256), 256, 0, st>>>(xp, yp, n, h, w, c / 8,
-                                                                                             x_c_stride / 8, y_c_stride / 8);
+      avgpool3s1_strip_kernel<false><<<static_cast<int>((strip_threads + 255) / 256), 256, 0, st>>>(
+          xp, yp, n, h, w, c / 8, x_c_stride / 8, y_c_stride / 8);
     }
     else if (avg && k == 3 && stride == 1) DIN_POOL_FIXED(1, 3, 1);
     else if (!avg && k == 3 && stride == 2) DIN_POOL_FIXED(0, 3, 2);
@@ -455,6 +497,24 @@ extern "C" int din_avgpool2d_nhwc_f16(const void* x, void* y, int n, int h, int 
   return pool_common("din_avgpool2d_nhwc_f16", 1, x, y, n, h, w, c, x_c_stride, y_c_stride, k, stride, pad, stream);
 }
 
+extern "C" int din_avgpool3_bias_relu_nhwc_f16(const void* x, void* y, const float* bias, int n, int h, int w, int c,
+                                               int x_c_stride, int y_c_stride, int relu, void* stream) {
+  const char* who = "din_avgpool3_bias_relu_nhwc_f16";
+  DIN_CHECK_ARG(x && y && bias, "%s: null pointer", who);
+  DIN_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0,
+                "%s: bad shape n=%d h=%d w=%d c=%d (c must be a multiple of 8)", who, n, h, w, c);
+  DIN_CHECK_ARG(x_c_stride >= c && y_c_stride >= c && x_c_stride % 8 == 0 && y_c_stride % 8 == 0,
+                "%s: channel strides %d / %d must be >= c and multiples of 8", who, x_c_stride, y_c_stride);
+  DIN_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "%s: pointers must be 16-byte aligned", who);
+  const size_t strip_threads = static_cast<size_t>(n) * ((h + kAvgRows - 1) / kAvgRows) * w * (c / 8);
+  DIN_CHECK_ARG((strip_threads + 255) / 256 <= 0x7FFFFFFFull, "%s: too many blocks", who);
+  avgpool3s1_strip_kernel<true><<<static_cast<int>((strip_threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), static_cast<__half*>(y), n, h, w, c / 8, x_c_stride / 8, y_c_stride / 8, bias, relu);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
 extern "C" int din_upsample_bilinear_nhwc_f16(const void* x, void* y, int n, int h, int w, int c, int x_c_stride,
                                               int y_c_stride, int oh, int ow, void* stream) {
   DIN_CHECK_ARG(x && y, "din_upsample_bilinear_nhwc_f16: null pointer");
@@ -464,10 +524,9 @@ extern "C" int din_upsample_bilinear_nhwc_f16(const void* x, void* y, int n, int
                 "din_upsample_bilinear_nhwc_f16: channel strides must be >= c and multiples of 8");
   DIN_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
                 "din_upsample_bilinear_nhwc_f16: pointers must be 16-byte aligned");
-  const size_t total = static_cast<size_t>(n) * oh * ow * (c / 8);
-  const int sms = din_num_sms();
-  const int grid = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(sms > 0 ? sms : 148) * 16));
-  upsample_bilinear_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  const size_t total = static_cast<size_t>(n) * ((oh + kUpRows - 1) / kUpRows) * ow * (c / 8);
+  DIN_CHECK_ARG((total + 255) / 256 <= 0x7FFFFFFFull, "din_upsample_bilinear_nhwc_f16: too many blocks");
+  upsample_bilinear_strip_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(x), static_cast<__half*>(y), n, h, w, c / 8, x_c_stride / 8, y_c_stride / 8, oh, ow);
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;

@@ -24,6 +24,10 @@ class DinPackJob(C.Structure):
         "rows", "cols", "cols_padded", "kh", "kw", "split", "transposed", "reserved")]
 
 
+class DinConvBranchOut(C.Structure):
+    _fields_ = [(name, C.c_int32) for name in ("split_col", "y2_c_stride", "norelu_lo", "norelu_hi")]
+
+
 class DinFlatJob(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst_offset", C.c_longlong), ("numel", C.c_longlong)]
 
@@ -40,6 +44,8 @@ PROTOTYPES = {
     "din_stem_conv_nchw_f32": (C.c_int, [_fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_stem_conv_nhwc_u8": (C.c_int, [_vp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_conv2d_nhwc_f16": (C.c_int, [C.POINTER(DinConvDesc), _vp, _vp, _fp, _vp, _vp, _vp]),
+    "din_conv2d_branches_nhwc_f16": (C.c_int, [C.POINTER(DinConvDesc), C.POINTER(DinConvBranchOut), _vp, _vp, _fp, _vp,
+                                               _vp, _vp]),
     "din_conv3x3_stem_pair_nhwc_f16": (C.c_int, [_vp, _i, _fp, _fp, _vp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_conv2d_relu_bwd_nhwc_f16": (C.c_int, [C.POINTER(DinConvDesc), _vp, _vp, _vp, _vp, _vp]),
     "din_pack_conv_weight_f16": (C.c_int, [_fp, _fp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
@@ -51,6 +57,7 @@ PROTOTYPES = {
     "din_pack_conv_weights_f16": (C.c_int, [C.POINTER(DinPackJob), _i, _vp]),
     "din_maxpool2d_nhwc_f16": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_avgpool2d_nhwc_f16": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "din_avgpool3_bias_relu_nhwc_f16": (C.c_int, [_vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_upsample_bilinear_nhwc_f16": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_roi_align_nhwc_f16": (C.c_int, [_vp, _fp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_roi_align_nhwc_f16_f32out": (C.c_int, [_vp, _fp, _vp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

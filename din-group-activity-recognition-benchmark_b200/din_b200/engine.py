@@ -90,6 +90,10 @@ def frames_per_chunk(backbone_name, n_frames, h, w, fixed=None):
 
 FUSE_CONV1 = os.environ.get("DIN_FUSE_CONV1", "1") != "0"      # A/B knob: 0 = stand-alone stem + conv1_2
 SMALL_LAUNCH_PIXELS = 148 * 128 if os.environ.get("DIN_SMALL_EXACT", "1") != "0" else 0
+# ... except the dense GEMM (n = h = 1: fc_emb_1) above 1 GFLOP: a full batch has only 960 'pixels' (actor rows) but
+# K = 12 800 .. 27 200 -- 25-53 GFLOP, bound by weight traffic, where the second weight part doubled its time
+# (0.27 -> 0.12 ms per step for VGG-16)
+SMALL_LAUNCH_FLOPS = 1e9
 # fewer actor rows than half an MMA tile: fp32 crops + fp32 fc_emb_1 (din_linear_f32)
 SMALL_EMBED_ROWS = 64 if os.environ.get("DIN_SMALL_EMBED_F32", "1") != "0" else 0
 
@@ -134,8 +138,9 @@ class _Conv:
     def _weight_for(self, x):
         # inference plans only: a training step re-packs every weight after the optimizer step, and packing a second
         # (hi + lo) copy of the late layers each step cost ResNet-18's step 47 ms of packing kernels (measured)
-        if (not _INFERENCE[0] or self.split == 2
-                or x.shape[0] * x.shape[1] * x.shape[2] > SMALL_LAUNCH_PIXELS * self.stride * self.stride):
+        px = x.shape[0] * x.shape[1] * x.shape[2]
+        if (not _INFERENCE[0] or self.split == 2 or px > SMALL_LAUNCH_PIXELS * self.stride * self.stride
+                or (x.shape[0] == 1 and x.shape[1] == 1 and 2.0 * px * self.w_src.numel() > SMALL_LAUNCH_FLOPS)):
             return self.w
         if self._w_exact is None:
             self._w_exact = ops.pack_conv_weights([(self.w_src, self.bn_scale, 2, False)])[0]
@@ -276,8 +281,9 @@ class Res18Plan:
         self._nbt = []
 
         def bn(p):
-            if f"{p}.num_batches_tracked" in sd:
-                self._nbt.append(sd[f"{p}.num_batches_tracked"])
+            t = sd.get(f"{p}.num_batches_tracked")
+            if t is not None and all(t is not u for u in self._nbt):   # bn() runs twice per layer; a duplicate in the
+                self._nbt.append(t)                                    # _foreach_add_ list is a read-modify-write race
             return {k: sd[f"{p}.{k}"] for k in ("weight", "bias", "running_mean", "running_var")} | {"eps": 1e-5}
 
         def _fold(w, b):

@@ -54,19 +54,81 @@ class _BasicConv:
         return self.conv(x, out=out, c_in=self.c_in, x_c_offset=x_c_offset, y_c_offset=y_c_offset)
 
 
-class _InceptionA:   # Mixed_5b/5c/5d
-    def __init__(self, sd, p):
-        self.b1 = _BasicConv(sd, p + "branch1x1")
-        self.b5_1 = _BasicConv(sd, p + "branch5x5_1")
-        self.b5_2 = _BasicConv(sd, p + "branch5x5_2", pad=(2, 2))
-        self.d1 = _BasicConv(sd, p + "branch3x3dbl_1")
-        self.d2 = _BasicConv(sd, p + "branch3x3dbl_2", pad=(1, 1))
-        self.d3 = _BasicConv(sd, p + "branch3x3dbl_3", pad=(1, 1))
-        self.bp = _BasicConv(sd, p + "branch_pool")
-        self.c_in = self.b1.c_in
-        self.c_out = 64 + 64 + 96 + self.bp.c_out
+MERGE_1X1 = os.environ.get("DIN_INV3_MERGE", "1") != "0"      # A/B knob: 0 = one launch per branch convolution
+
+
+class _BranchHeads:
+    """The 1x1 convolutions that open the branches of one Inception block, as ONE GEMM over the block input (weight rows
+    stacked; ops.conv2d_branches_nhwc).  `first` (branch1x1) lands in the block's concat buffer, the others in a scratch
+    slab the branches' next convolutions read as channel slices.  The pool branch's 1x1 runs BEFORE its average pool: both
+    are linear and the pool's zero padding (count_include_pad) commutes with a bias-free 1x1, so the pool streams c_out
+    instead of c_in channels (768 -> 192, 288 -> 64); its BatchNorm shift + ReLU follow the pool.  Column order puts every
+    boundary the kernel needs (the y / y2 split, the no-ReLU range) on a multiple of 32."""
+
+    def __init__(self, sd, first, others, pool, order):
+        names = {"first": first, "pool": pool, **others}
+        parts, self.off, col = [], {}, 0
+        for key in order:
+            bn = {k: sd[f"{names[key]}.bn.{k}"] for k in ("weight", "bias", "running_mean", "running_var")}
+            bn["eps"] = 1e-3
+            w, s, b = _fold_bn(sd[f"{names[key]}.conv.weight"], bn)
+            if key == "pool":
+                self.pool_bias, b = b.contiguous().float(), torch.zeros_like(b)
+            parts.append((w, s, b))
+            self.off[key] = (col, w.shape[0])
+            col += w.shape[0]
+        assert order[0] == "first"
+        self.split_col = self.off["first"][1]
+        self.norelu = (self.off["pool"][0], self.off["pool"][0] + self.off["pool"][1])
+        assert self.split_col % 32 == 0 and self.norelu[0] % 32 == 0 and self.norelu[1] % 32 == 0
+        self.c_in, self.c_total = parts[0][0].shape[1], col
+        self.conv = _Conv(torch.cat([w for w, _, _ in parts]), torch.cat([b for _, _, b in parts]),
+                          torch.cat([s for _, s, _ in parts]), relu=True, split=_split_for(first))
+
+    def slice(self, key):
+        """(channel offset, channels) of a branch inside the scratch slab."""
+        o, c = self.off[key]
+        return o - self.split_col, c
 
     def __call__(self, x, out):
+        scratch = torch.empty(x.shape[:3] + (self.c_total - self.split_col,), dtype=torch.float16, device=x.device)
+        ops.conv2d_branches_nhwc(x, self.conv._weight_for(x), self.conv.bias, out, scratch, split_col=self.split_col,
+                                 norelu=self.norelu, c_in=self.c_in)
+        return scratch
+
+    def pool_tail(self, scratch, out, y_c_offset):
+        o, c = self.slice("pool")
+        ops.avgpool3_bias_relu_nhwc(scratch, self.pool_bias, out, c=c, x_c_offset=o, y_c_offset=y_c_offset)
+
+
+class _InceptionA:   # Mixed_5b/5c/5d
+    def __init__(self, sd, p):
+        self.b5_2 = _BasicConv(sd, p + "branch5x5_2", pad=(2, 2))
+        self.d2 = _BasicConv(sd, p + "branch3x3dbl_2", pad=(1, 1))
+        self.d3 = _BasicConv(sd, p + "branch3x3dbl_3", pad=(1, 1))
+        if MERGE_1X1:
+            # [branch1x1 64 | 3x3dbl_1 64 | pool pf | 5x5_1 48]: split at 64, pool columns start at 128
+            self.heads = _BranchHeads(sd, p + "branch1x1", {"d1": p + "branch3x3dbl_1", "s1": p + "branch5x5_1"},
+                                      p + "branch_pool", ("first", "d1", "pool", "s1"))
+            self.c_in, pf = self.heads.c_in, self.heads.off["pool"][1]
+        else:
+            self.b1 = _BasicConv(sd, p + "branch1x1")
+            self.b5_1 = _BasicConv(sd, p + "branch5x5_1")
+            self.d1 = _BasicConv(sd, p + "branch3x3dbl_1")
+            self.bp = _BasicConv(sd, p + "branch_pool")
+            self.c_in, pf = self.b1.c_in, self.bp.c_out
+        self.c_out = 64 + 64 + 96 + pf
+
+    def __call__(self, x, out):
+        if MERGE_1X1:
+            h = self.heads
+            scratch = h(x, out)                                   # branch1x1 -> out[..., 0:64]
+            o, _ = h.slice("s1")
+            self.b5_2(scratch, out=out, x_c_offset=o, y_c_offset=64)
+            o, _ = h.slice("d1")
+            self.d3(self.d2(scratch, x_c_offset=o), out=out, y_c_offset=128)
+            h.pool_tail(scratch, out, 224)
+            return out
         self.b1(x, out=out, y_c_offset=0)
         self.b5_2(self.b5_1(x), out=out, y_c_offset=64)
         self.d3(self.d2(self.d1(x)), out=out, y_c_offset=128)
@@ -91,18 +153,32 @@ class _InceptionB:   # Mixed_6a
 
 class _InceptionC:   # Mixed_6b..6e
     def __init__(self, sd, p):
-        self.b1 = _BasicConv(sd, p + "branch1x1")
-        self.s1 = _BasicConv(sd, p + "branch7x7_1")
+        if MERGE_1X1:
+            # [branch1x1 192 | 7x7_1 c7 | 7x7dbl_1 c7 | pool 192]: split at 192, pool columns start at 192 + 2 c7
+            self.heads = _BranchHeads(sd, p + "branch1x1", {"s1": p + "branch7x7_1", "d1": p + "branch7x7dbl_1"},
+                                      p + "branch_pool", ("first", "s1", "d1", "pool"))
+        else:
+            self.b1 = _BasicConv(sd, p + "branch1x1")
+            self.s1 = _BasicConv(sd, p + "branch7x7_1")
+            self.d1 = _BasicConv(sd, p + "branch7x7dbl_1")
+            self.bp = _BasicConv(sd, p + "branch_pool")
         self.s2 = _BasicConv(sd, p + "branch7x7_2", pad=(0, 3))
         self.s3 = _BasicConv(sd, p + "branch7x7_3", pad=(3, 0))
-        self.d1 = _BasicConv(sd, p + "branch7x7dbl_1")
         self.d2 = _BasicConv(sd, p + "branch7x7dbl_2", pad=(3, 0))
         self.d3 = _BasicConv(sd, p + "branch7x7dbl_3", pad=(0, 3))
         self.d4 = _BasicConv(sd, p + "branch7x7dbl_4", pad=(3, 0))
         self.d5 = _BasicConv(sd, p + "branch7x7dbl_5", pad=(0, 3))
-        self.bp = _BasicConv(sd, p + "branch_pool")
 
     def __call__(self, x, out):
+        if MERGE_1X1:
+            h = self.heads
+            scratch = h(x, out)                                   # branch1x1 -> out[..., 0:192]
+            o, _ = h.slice("s1")
+            self.s3(self.s2(scratch, x_c_offset=o), out=out, y_c_offset=192)
+            o, _ = h.slice("d1")
+            self.d5(self.d4(self.d3(self.d2(scratch, x_c_offset=o))), out=out, y_c_offset=384)
+            h.pool_tail(scratch, out, 576)
+            return out
         self.b1(x, out=out, y_c_offset=0)
         self.s3(self.s2(self.s1(x)), out=out, y_c_offset=192)
         self.d5(self.d4(self.d3(self.d2(self.d1(x)))), out=out, y_c_offset=384)

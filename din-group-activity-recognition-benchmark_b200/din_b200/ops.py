@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import DinConvDesc, check
+from ._lib import DinConvBranchOut, DinConvDesc, check
 
 
 LAUNCHES = 0      # kernels launched through this module (each C-ABI compute call launches exactly one)
@@ -145,6 +145,38 @@ def conv2d_nhwc(x, w_packed, bias=None, *, stride=1, pad=(0, 0), relu=False, res
     return out
 
 
+def conv2d_branches_nhwc(x, w_packed, bias, out, out2, *, split_col, norelu=(0, 0), relu=True, c_in=None, x_c_offset=0,
+                         y_c_offset=0, y2_c_offset=0):
+    """Several 1x1 convolutions over the same input as ONE GEMM (weight rows stacked): output columns [0, split_col) go to
+    `out` at channel y_c_offset, the rest to `out2` at y2_c_offset; columns in norelu = [lo, hi) skip the ReLU
+    (din_conv2d_branches_nhwc_f16)."""
+    _need(x, torch.float16, "x")
+    _need(w_packed, torch.float16, "w_packed")
+    _need(out, torch.float16, "out")
+    _need(out2, torch.float16, "out2")
+    _need(bias, torch.float32, "bias")
+    n, h, w, cx = x.shape
+    assert w_packed.shape[-3] == 1 and w_packed.shape[-2] == 1
+    split = 2 if w_packed.dim() == 5 else 1
+    co, ci = w_packed.shape[0], w_packed.shape[-1]
+    if c_in is None:
+        c_in = min(ci, cx - x_c_offset)
+    assert (c_in + 63) // 64 * 64 == ci and x_c_offset + c_in <= cx, (c_in, ci, cx, x_c_offset)
+    assert out.shape[:3] == (n, h, w) and out2.shape[:3] == (n, h, w)
+    assert y_c_offset + split_col <= out.shape[3] and y2_c_offset + co - split_col <= out2.shape[3]
+    d = DinConvDesc(n=n, h=h, w=w, c_in=c_in, x_c_stride=cx, c_out=co, y_c_stride=out.shape[3], kh=1, kw=1, stride=1,
+                    pad_h=0, pad_w=0, relu=int(relu), out_f32=0, pool2=0, w_split=split)
+    br = DinConvBranchOut(split_col=split_col, y2_c_stride=out2.shape[3], norelu_lo=norelu[0], norelu_hi=norelu[1])
+    flops = 2 * n * h * w * co * c_in
+    nbytes = 2 * n * h * w * (c_in + co) + 2 * co * ci
+    with _launch(f"conv1x1s1_{c_in}->{co}@{h}x{w}+branches", flops, nbytes):
+        check(_lib.load().din_conv2d_branches_nhwc_f16(
+            C.byref(d), C.byref(br), C.c_void_p(x.data_ptr() + 2 * x_c_offset), _p(w_packed), _p(bias),
+            C.c_void_p(out.data_ptr() + 2 * y_c_offset), C.c_void_p(out2.data_ptr() + 2 * y2_c_offset), _stream()),
+            "din_conv2d_branches_nhwc_f16")
+    return out, out2
+
+
 def stem_conv(x, w_oihw, bias, *, stride=1, pad=0, relu=True, prep=True):
     """Raw images (0..255) -> prep_images -> conv(+bias,+ReLU) -> NHWC fp16.
     x: fp32 NCHW [n,3,h,w] (the reference loader's tensor) or uint8 NHWC [n,h,w,3] (the decoded frame)."""
@@ -229,6 +261,22 @@ def maxpool2d_nhwc(x, k, stride, pad=0, out=None, c=None, x_c_offset=0, y_c_offs
 def avgpool2d_nhwc(x, k, stride, pad=0, out=None, c=None, x_c_offset=0, y_c_offset=0):
     """count_include_pad=True (torch default)."""
     return _pool("din_avgpool2d_nhwc_f16", x, k, stride, pad, out, c, x_c_offset, y_c_offset)
+
+
+def avgpool3_bias_relu_nhwc(x, bias, out, *, c, x_c_offset=0, y_c_offset=0, relu=True):
+    """out[..., y_c_offset : +c] = relu(avg_pool3x3 s1 p1 (x[..., x_c_offset : +c]) + bias): the tail of a pool branch whose
+    1x1 convolution ran first (conv2d_branches_nhwc)."""
+    _need(x, torch.float16, "x")
+    _need(out, torch.float16, "out")
+    _need(bias, torch.float32, "bias")
+    n, h, w, cx = x.shape
+    assert tuple(out.shape[:3]) == (n, h, w) and y_c_offset + c <= out.shape[3] and x_c_offset + c <= cx
+    assert bias.numel() == c
+    with _launch(f"avgpool3s1+bias_{c}@{h}x{w}", 0, 4 * n * c * h * w):
+        check(_lib.load().din_avgpool3_bias_relu_nhwc_f16(
+            C.c_void_p(x.data_ptr() + 2 * x_c_offset), C.c_void_p(out.data_ptr() + 2 * y_c_offset), _p(bias), n, h, w, c,
+            cx, out.shape[3], int(relu), _stream()), "din_avgpool3_bias_relu_nhwc_f16")
+    return out
 
 
 def upsample_bilinear_nhwc(x, oh, ow, out=None, c=None, x_c_offset=0, y_c_offset=0):

@@ -121,6 +121,23 @@ typedef struct DinConvDesc {
 DIN_API int din_conv2d_nhwc_f16(const DinConvDesc* desc, const void* x, const void* w_packed, const float* bias,
                         const void* residual, void* y, void* stream);
 
+/* Several convolutions that read the SAME input (the 1x1 branch heads of an Inception block: branch1x1, branch5x5_1 /
+ * branch7x7_1, branch*dbl_1 and branch_pool's 1x1, torchvision Inception{A,C}.forward under backbone.py:62-80) as ONE
+ * implicit GEMM whose weight rows are the branches' filters stacked: the input is read once, N is wide enough for the
+ * 256-column MMA, one launch instead of four.  Output columns [0, split_col) are written to y (channel stride
+ * desc.y_c_stride: the block's concat buffer), columns [split_col, c_out) to y2 (channel stride y2_c_stride: scratch that
+ * the branches' next convolutions read as channel slices).  Columns [norelu_lo, norelu_hi) skip desc.relu: the pool
+ * branch's 1x1 runs BEFORE its 3x3 average pool here (both are linear and zero padding with count_include_pad commutes
+ * with a bias-free 1x1), so the pool streams c_out instead of c_in channels; bias + ReLU follow the pool
+ * (din_avgpool3_bias_relu_nhwc_f16).  split_col, norelu_lo, norelu_hi: multiples of 32.  No pool2 / out_f32 / residual. */
+typedef struct DinConvBranchOut {
+  int32_t split_col;
+  int32_t y2_c_stride;
+  int32_t norelu_lo, norelu_hi;
+} DinConvBranchOut;
+DIN_API int din_conv2d_branches_nhwc_f16(const DinConvDesc* desc, const DinConvBranchOut* branches, const void* x,
+                                         const void* w_packed, const float* bias, void* y, void* y2, void* stream);
+
 /* VGG-16's first two layers in ONE launch (inference): conv1_1 = 3x3 pad 1 over the 3-channel image (prep_images fused,
  * bias, ReLU) computed tile by tile INSIDE the CTA-pair kernel of conv1_2 = 3x3 pad 1, 64 -> 64 channels, bias, ReLU,
  * optional fused 2x2 max-pool: conv1_1's 64-channel output (118 MB per 720p frame) never reaches HBM
@@ -186,6 +203,11 @@ DIN_API int din_maxpool2d_nhwc_f16(const void* x, void* y, int n, int h, int w, 
                                    int y_c_stride, int k, int stride, int pad, void* stream);
 DIN_API int din_avgpool2d_nhwc_f16(const void* x, void* y, int n, int h, int w, int c, int x_c_stride,
                                    int y_c_stride, int k, int stride, int pad, void* stream);
+
+/* y = relu?(avg_pool3x3(x, stride 1, pad 1, count_include_pad) + bias[c]): the tail of an Inception pool branch whose 1x1
+ * convolution ran before the pool (din_conv2d_branches_nhwc_f16).  Channel-strided like the pools above; bias fp32 [c]. */
+DIN_API int din_avgpool3_bias_relu_nhwc_f16(const void* x, void* y, const float* bias, int n, int h, int w, int c,
+                                            int x_c_stride, int y_c_stride, int relu, void* stream);
 
 /*
  * Bilinear resize with align_corners=True, NHWC fp16, [n,h,w,c] -> [n,oh,ow,c] (channel-strided buffers).

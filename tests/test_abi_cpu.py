@@ -65,7 +65,7 @@ def test_ctypes_table_matches_header():
 def test_loads_and_validates_without_gpu():
     lib = _lib()
     h = lib.load()
-    assert h.din_abi_version() == 4
+    assert h.din_abi_version() == 5
     # invalid arguments are rejected before any CUDA call, with a message
     d = lib.DinConvDesc(n=1, h=8, w=8, c_in=44, x_c_stride=48, c_out=64, y_c_stride=64, kh=3, kw=3, stride=1,
                         pad_h=1, pad_w=1, relu=1, out_f32=0, pool2=0, w_split=1)

@@ -257,3 +257,62 @@ def test_stem_pair_rejects_unaligned_widths(cuda):
     w2p = ops.pack_conv_weight(torch.zeros(64, 64, 3, 3, device=cuda))
     with pytest.raises(_lib.DinError):
         ops.stem_conv_pair(x, torch.zeros(64, 3, 3, 3, device=cuda), None, w2p, None)
+
+
+@pytest.mark.parametrize("shape", [(2, 21, 37, 192, (64, 64, 32, 48), 64, (128, 160)),      # Mixed_5b heads
+                                   (1, 11, 19, 768, (192, 160, 160, 192), 192, (512, 704)),   # Mixed_6c heads: 3 N tiles
+                                   (1, 5, 7, 288, (64, 64, 64, 48), 64, (128, 192))],
+                         ids=["5b", "6c", "5d"])
+def test_branch_group_gemm_and_pool_tail(cuda, shape):
+    """din_conv2d_branches_nhwc_f16: stacked 1x1 convolutions in one launch, two destinations, a column range without
+    ReLU; din_avgpool3_bias_relu_nhwc_f16 on that range equals conv1x1(avg_pool(x)) + bias, ReLU (the reference's
+    branch_pool order, torchvision InceptionA/C.forward) up to fp16 rounding."""
+    from din_b200 import ops
+    n, h, w, cin, widths, split_col, norelu = shape
+    g = torch.Generator(device="cpu").manual_seed(7)
+    x = torch.randn(n, h, w, cin, generator=g).to(cuda).half()
+    co = sum(widths)
+    wt = (torch.randn(co, cin, 1, 1, generator=g) * (2.0 / cin) ** 0.5).to(cuda)
+    bias = torch.randn(co, generator=g).to(cuda)
+    pool_bias = bias[norelu[0]:norelu[1]].clone()
+    bias[norelu[0]:norelu[1]] = 0
+    wp = ops.pack_conv_weight(wt)
+    out = torch.full((n, h, w, split_col + 40), 7.0, dtype=torch.float16, device=cuda)      # wider concat buffer
+    out2 = torch.full((n, h, w, co - split_col + 8), 7.0, dtype=torch.float16, device=cuda)
+    ops.conv2d_branches_nhwc(x, wp, bias, out, out2, split_col=split_col, norelu=norelu, y_c_offset=8)
+    torch.cuda.synchronize()
+    z = _ref_conv(x, _unpack(wp, cin), bias, 1, (0, 0), False)
+    ref = F.relu(z)
+    ref[..., norelu[0]:norelu[1]] = z[..., norelu[0]:norelu[1]]
+    scale = ref.abs().max().item()
+    assert (out[..., :8] == 7).all() and (out[..., 8 + split_col:] == 7).all() and (out2[..., co - split_col:] == 7).all()
+    assert (out[..., 8:8 + split_col].float() - ref[..., :split_col]).abs().max().item() <= 2e-3 * scale
+    assert (out2[..., :co - split_col].float() - ref[..., split_col:]).abs().max().item() <= 2e-3 * scale
+    # the pool branch: 1x1 first, pool + bias + ReLU after
+    c = norelu[1] - norelu[0]
+    tail = torch.zeros((n, h, w, c + 16), dtype=torch.float16, device=cuda)
+    ops.avgpool3_bias_relu_nhwc(out2, pool_bias, tail, c=c, x_c_offset=norelu[0] - split_col, y_c_offset=16)
+    torch.cuda.synchronize()
+    xp = F.avg_pool2d(x.float().permute(0, 3, 1, 2), 3, 1, 1).permute(0, 2, 3, 1).contiguous().half()
+    want = _ref_conv(xp, _unpack(wp, cin)[norelu[0]:norelu[1]], pool_bias, 1, (0, 0), True)
+    assert (tail[..., :16] == 0).all()
+    assert (tail[..., 16:].float() - want).abs().max().item() <= 3e-3 * want.abs().max().item()
+
+
+def test_inception_merged_branch_heads_match_the_per_branch_plan(cuda, monkeypatch):
+    """Inv3Plan with the branch heads merged (default) vs one launch per branch convolution (DIN_INV3_MERGE=0): the
+    multiscale maps agree to fp16 rounding (only the pool branches differ: 1x1 and average pool swapped)."""
+    import din_oracle as O
+    from din_b200 import inception
+    pc = O.PathConfig(backbone="inv3", image_size=(139, 203), out_size=O.backbone_out_size("inv3", 139, 203),
+                      emb_features=1056, num_frames=2, num_boxes=4, lite_dim=None)
+    sd = {k: v.to(cuda) for k, v in O.make_state_dict(pc, seed=3).items() if k.startswith("backbone.")}
+    images = (torch.rand(2, 3, 139, 203, generator=torch.Generator().manual_seed(5)) * 255).to(cuda)
+    maps = []
+    for merge in (True, False):
+        monkeypatch.setattr(inception, "MERGE_1X1", merge)
+        maps.append(inception.Inv3Plan(sd)(images).float())
+    torch.cuda.synchronize()
+    a, b = maps
+    assert torch.isfinite(a).all()
+    assert (a - b).abs().max().item() <= 4e-3 * b.abs().max().item(), ((a - b).abs().max().item(), b.abs().max().item())
