@@ -85,10 +85,10 @@ class _Basenet(nn.Module):
     def _check_mode(self, images):
         if not images.is_cuda:
             raise RuntimeError("the DIN hot path runs on sm_100a only: pass CUDA tensors (there is no CPU fallback)")
-        if self.training and (self._dataset != "volleyball" or self.cfg.backbone not in ("vgg16", "res18")):
+        if self.training and (self._dataset != "volleyball" or self.cfg.backbone not in ("vgg16", "res18", "inv3")):
             raise NotImplementedError(
-                "stage-1 training on the sm_100a path is implemented for Basenet_volleyball with the VGG-16 or ResNet-18 "
-                "backbone (scripts/train_volleyball_stage1.py); use model.eval() for the other configurations "
+                "stage-1 training on the sm_100a path is implemented for Basenet_volleyball with the VGG-16, ResNet-18 or "
+                "Inception-v3 backbone (scripts/train_volleyball_stage1.py); use model.eval() for Basenet_collective "
                 "(SURVEY.md §8f rank 1)")
         if self.training and any(isinstance(m, nn.modules.batchnorm._BatchNorm) and m.training
                                  for m in self.backbone.modules()):

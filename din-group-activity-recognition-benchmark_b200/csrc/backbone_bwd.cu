@@ -274,6 +274,86 @@ add_f16_kernel(const __half* __restrict__ a, const __half* __restrict__ b, __hal
   reinterpret_cast<uint4*>(y)[i] = o;
 }
 
+// dz[r, 0:c] = dy[r, 0:c] * [y[r, 0:c] > 0] over channel slices of three buffers with their own channel strides (in
+// 8-channel units): the ReLU backward of an Inception branch whose output is a slice of the block's concat buffer.
+__global__ void __launch_bounds__(256)
+relu_bwd_slice_kernel(const __half* __restrict__ y, const __half* __restrict__ dy, __half* __restrict__ dz, long long rows,
+                      int c8, int ys8, int dys8, int dzs8) {
+  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= rows * c8) return;
+  const int oc = static_cast<int>(idx % c8);
+  const long long r = idx / c8;
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(y) + r * ys8 + oc);
+  const uint4 g = __ldg(reinterpret_cast<const uint4*>(dy) + r * dys8 + oc);
+  const __half2* ha = reinterpret_cast<const __half2*>(&a);
+  const __half2* hg = reinterpret_cast<const __half2*>(&g);
+  const __half2 zero = __float2half2_rn(0.0f);
+  uint4 o;
+  __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) ho[e] = __hmul2(hg[e], __hgt2(ha[e], zero));
+  reinterpret_cast<uint4*>(dz)[r * dzs8 + oc] = o;
+}
+
+// Backward of the align_corners=True bilinear resize [n,h,w,c] -> [n,oh,ow,c] (F.interpolate at infer_model.py:169), gather
+// form: source pixel (sy, sx) collects dy from every output pixel whose forward interpolation read it, with the forward's
+// weights (same fp32 arithmetic: scale = (h-1)/(oh-1), y0 = int(scale * oy), ly = scale * oy - y0).  One thread per
+// (8 channels, source pixel); candidates are the outputs oy with y0(oy) in {sy - 1, sy}: a window of 1/scale + 2 rows.
+__global__ void __launch_bounds__(256)
+upsample_bilinear_bwd_kernel(const __half* __restrict__ dy, __half* __restrict__ dx, int n, int h, int w, int c8, int dys8,
+                             int dxs8, int oh, int ow) {
+  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= static_cast<long long>(n) * h * w * c8) return;
+  const int oc = static_cast<int>(idx % c8);
+  long long t = idx / c8;
+  const int sx = static_cast<int>(t % w);
+  t /= w;
+  const int sy = static_cast<int>(t % h);
+  const int img = static_cast<int>(t / h);
+  const float scy = oh > 1 ? static_cast<float>(h - 1) / static_cast<float>(oh - 1) : 0.0f;
+  const float scx = ow > 1 ? static_cast<float>(w - 1) / static_cast<float>(ow - 1) : 0.0f;
+  // outputs that can touch source row sy: scy * oy in (sy - 1, sy + 1)
+  int oy_lo = 0, oy_hi = oh - 1, ox_lo = 0, ox_hi = ow - 1;
+  if (scy > 0.0f) {
+    oy_lo = max(0, static_cast<int>(floorf(static_cast<float>(sy - 1) / scy)) - 1);
+    oy_hi = min(oh - 1, static_cast<int>(ceilf(static_cast<float>(sy + 1) / scy)) + 1);
+  }
+  if (scx > 0.0f) {
+    ox_lo = max(0, static_cast<int>(floorf(static_cast<float>(sx - 1) / scx)) - 1);
+    ox_hi = min(ow - 1, static_cast<int>(ceilf(static_cast<float>(sx + 1) / scx)) + 1);
+  }
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const uint4* g4 = reinterpret_cast<const uint4*>(dy) + static_cast<long long>(img) * oh * ow * dys8 + oc;
+  for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+    const float fy = scy * static_cast<float>(oy);
+    const int y0 = min(static_cast<int>(fy), h - 1), y1 = min(y0 + 1, h - 1);
+    const float ly = fy - static_cast<float>(y0);
+    const float wy = (y0 == sy ? 1.0f - ly : 0.0f) + (y1 == sy ? ly : 0.0f);
+    if (wy == 0.0f) continue;
+    for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+      const float fx = scx * static_cast<float>(ox);
+      const int x0 = min(static_cast<int>(fx), w - 1), x1 = min(x0 + 1, w - 1);
+      const float lx = fx - static_cast<float>(x0);
+      const float wx = (x0 == sx ? 1.0f - lx : 0.0f) + (x1 == sx ? lx : 0.0f);
+      if (wx == 0.0f) continue;
+      const uint4 g = __ldg(g4 + (static_cast<long long>(oy) * ow + ox) * dys8);
+      const __half2* hg = reinterpret_cast<const __half2*>(&g);
+      const float wgt = wy * wx;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(hg[e]);
+        acc[2 * e] += wgt * f.x;
+        acc[2 * e + 1] += wgt * f.y;
+      }
+    }
+  }
+  uint4 o;
+  __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) ho[e] = __floats2half2_rn(acc[2 * e], acc[2 * e + 1]);
+  reinterpret_cast<uint4*>(dx)[((static_cast<long long>(img) * h + sy) * w + sx) * dxs8 + oc] = o;
+}
+
 // Backward of MaxPool2d(3, 2, 1) fused with the ReLU before it (resnet18.relu / .maxpool):
 //   dz[iy,ix] = [x > 0] * sum over the (1, 2 or 4) windows containing (iy,ix) of  dy[window] * [(iy,ix) is the window's
 //   FIRST maximum in scan order]   (padding is -inf and never wins, as torch).
@@ -285,15 +365,21 @@ add_f16_kernel(const __half* __restrict__ a, const __half* __restrict__ b, __hal
 constexpr int kMpTileH = 8, kMpTileW = 32;
 constexpr int kMpWinH = kMpTileH / 2 + 1, kMpWinW = kMpTileW / 2 + 1;
 
+// PAD = 1: resnet18.maxpool; PAD = 0: the F.max_pool2d(3, 2) of the Inception-v3 trunk (backbone.py:50,56) and of
+// Mixed_6a's pool branch.  x / dy / dz may be channel slices of wider buffers (xs8 / dys8 / dzs8 = their channel strides
+// in 8-channel units).
+template <int PAD>
 __global__ void __launch_bounds__(256)
 maxpool3s2_relu_bwd_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, __half* __restrict__ dz, int h,
-                           int w, int c8, int oh, int ow, int tiles_x, int tiles_y) {
+                           int w, int c8, int oh, int ow, int tiles_x, int tiles_y, int xs8, int dys8, int dzs8,
+                           int accumulate) {
   extern __shared__ uint4 win_idx[];                     // [kMpWinH * kMpWinW][c8] x 8 channels (fp16 scan position)
   const int tx = blockIdx.x % tiles_x, ty = (blockIdx.x / tiles_x) % tiles_y, img = blockIdx.x / (tiles_x * tiles_y);
-  const int iy0 = ty * kMpTileH, ix0 = tx * kMpTileW, oy0 = iy0 >> 1, ox0 = ix0 >> 1;
-  const uint4* x4 = reinterpret_cast<const uint4*>(x) + static_cast<long long>(img) * h * w * c8;
-  const uint4* dy4 = reinterpret_cast<const uint4*>(dy) + static_cast<long long>(img) * oh * ow * c8;
-  uint4* dz4 = reinterpret_cast<uint4*>(dz) + static_cast<long long>(img) * h * w * c8;
+  const int iy0 = ty * kMpTileH, ix0 = tx * kMpTileW;
+  const int oy0 = (iy0 + PAD - 1) >> 1, ox0 = (ix0 + PAD - 1) >> 1;      // first window touching the patch (may be -1)
+  const uint4* x4 = reinterpret_cast<const uint4*>(x) + static_cast<long long>(img) * h * w * xs8;
+  const uint4* dy4 = reinterpret_cast<const uint4*>(dy) + static_cast<long long>(img) * oh * ow * dys8;
+  uint4* dz4 = reinterpret_cast<uint4*>(dz) + static_cast<long long>(img) * h * w * dzs8;
   const __half2 zero = __float2half2_rn(0.0f);
   const __half2 ninf = __half2half2(__ushort_as_half(static_cast<unsigned short>(0xFC00)));
 
@@ -302,20 +388,20 @@ maxpool3s2_relu_bwd_kernel(const __half* __restrict__ x, const __half* __restric
     const int oy = oy0 + wi / kMpWinW, ox = ox0 + wi % kMpWinW;
     uint4 res;
     __half2* idx = reinterpret_cast<__half2*>(&res);
-    if (oy >= oh || ox >= ow) {
+    if (oy < 0 || ox < 0 || oy >= oh || ox >= ow) {
       idx[0] = idx[1] = idx[2] = idx[3] = __float2half2_rn(-1.0f);        // no such window: matches no position
     } else {
       uint4 v[9];
 #pragma unroll
       for (int q = 0; q < 9; ++q) {                                        // all nine loads in flight, addresses clamped
-        const int yy = min(max(2 * oy - 1 + q / 3, 0), h - 1), xx = min(max(2 * ox - 1 + q % 3, 0), w - 1);
-        v[q] = __ldg(x4 + (static_cast<long long>(yy) * w + xx) * c8 + oc);
+        const int yy = min(max(2 * oy - PAD + q / 3, 0), h - 1), xx = min(max(2 * ox - PAD + q % 3, 0), w - 1);
+        v[q] = __ldg(x4 + (static_cast<long long>(yy) * w + xx) * xs8 + oc);
       }
       __half2 best[4] = {ninf, ninf, ninf, ninf};
       idx[0] = idx[1] = idx[2] = idx[3] = zero;
 #pragma unroll
       for (int q = 0; q < 9; ++q) {
-        const int yy = 2 * oy - 1 + q / 3, xx = 2 * ox - 1 + q % 3;
+        const int yy = 2 * oy - PAD + q / 3, xx = 2 * ox - PAD + q % 3;
         const bool ok = yy >= 0 && yy < h && xx >= 0 && xx < w;
         const __half2* hv = reinterpret_cast<const __half2*>(&v[q]);
         const __half2 q2 = __float2half2_rn(static_cast<float>(q));
@@ -336,17 +422,17 @@ maxpool3s2_relu_bwd_kernel(const __half* __restrict__ x, const __half* __restric
     const int oc = item % c8, pi = item / c8;
     const int iy = iy0 + pi / kMpTileW, ix = ix0 + pi % kMpTileW;
     if (iy >= h || ix >= w) continue;
-    const uint4 mine = __ldg(x4 + (static_cast<long long>(iy) * w + ix) * c8 + oc);
+    const uint4 mine = __ldg(x4 + (static_cast<long long>(iy) * w + ix) * xs8 + oc);
     const __half2* hm = reinterpret_cast<const __half2*>(&mine);
     __half2 acc[4] = {zero, zero, zero, zero};
-    for (int oy = iy >> 1; oy <= ((iy + 1) >> 1); ++oy) {                  // windows with 2*oy - 1 <= iy <= 2*oy + 1
-      if (oy >= oh) continue;
-      for (int ox = ix >> 1; ox <= ((ix + 1) >> 1); ++ox) {
-        if (ox >= ow) continue;
-        const int my_pos = (iy - (2 * oy - 1)) * 3 + (ix - (2 * ox - 1));
+    for (int oy = (iy + PAD - 1) >> 1; oy <= ((iy + PAD) >> 1); ++oy) {    // windows with 2*oy - PAD <= iy <= 2*oy - PAD + 2
+      if (oy < 0 || oy >= oh) continue;
+      for (int ox = (ix + PAD - 1) >> 1; ox <= ((ix + PAD) >> 1); ++ox) {
+        if (ox < 0 || ox >= ow) continue;
+        const int my_pos = (iy - (2 * oy - PAD)) * 3 + (ix - (2 * ox - PAD));
         const __half2 p2 = __float2half2_rn(static_cast<float>(my_pos));
         const uint4 wv = win_idx[((oy - oy0) * kMpWinW + (ox - ox0)) * c8 + oc];
-        const uint4 g = __ldg(dy4 + (static_cast<long long>(oy) * ow + ox) * c8 + oc);
+        const uint4 g = __ldg(dy4 + (static_cast<long long>(oy) * ow + ox) * dys8 + oc);
         const __half2* hw2 = reinterpret_cast<const __half2*>(&wv);
         const __half2* hg = reinterpret_cast<const __half2*>(&g);
 #pragma unroll
@@ -357,7 +443,14 @@ maxpool3s2_relu_bwd_kernel(const __half* __restrict__ x, const __half* __restric
     __half2* ho = reinterpret_cast<__half2*>(&out);
 #pragma unroll
     for (int e = 0; e < 4; ++e) ho[e] = __hmul2(acc[e], __hgt2(hm[e], zero));
-    dz4[(static_cast<long long>(iy) * w + ix) * c8 + oc] = out;
+    uint4* dst = dz4 + (static_cast<long long>(iy) * w + ix) * dzs8 + oc;
+    if (accumulate) {                                   // dz already holds another branch's gradient of the same tensor
+      const uint4 prev = *dst;
+      const __half2* hp = reinterpret_cast<const __half2*>(&prev);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) ho[e] = __hadd2(ho[e], hp[e]);
+    }
+    *dst = out;
   }
 }
 
@@ -511,15 +604,17 @@ extern "C" int din_stem_wgrad(const void* x, int x_is_u8, const void* dz, float*
                               int prep, void* stream) {
   DIN_CHECK_ARG(x && dz && dw, "din_stem_wgrad: null pointer");
   DIN_CHECK_ARG(n > 0 && h > 0 && w > 0, "din_stem_wgrad: bad extent n=%d h=%d w=%d", n, h, w);
-  DIN_CHECK_ARG(c_out == 64 && kh == kw && ((kh == 3 && stride == 1 && pad == 1) || (kh == 7 && stride == 2 && pad == 3)),
-                "din_stem_wgrad: only the VGG-16 (64 x 3x3 s1 p1) and ResNet-18 (64 x 7x7 s2 p3) stems are implemented");
+  DIN_CHECK_ARG(kh == kw && ((c_out == 64 && kh == 3 && stride == 1 && pad == 1) || (c_out == 64 && kh == 7 && stride == 2 && pad == 3) ||
+                             (c_out == 32 && kh == 3 && stride == 2 && pad == 0)),
+                "din_stem_wgrad: only the VGG-16 (64 x 3x3 s1 p1), ResNet-18 (64 x 7x7 s2 p3) and Inception-v3 (32 x 3x3 s2 p0) "
+                "stems are implemented");
   DIN_CHECK_ARG((reinterpret_cast<uintptr_t>(dz) & 15) == 0, "din_stem_wgrad: dz must be 16-byte aligned");
   {
     // production path: tensor cores (stem_tc.cu).  DIN_STEM_WGRAD_SIMT=1 keeps the CUDA-core kernel below for A/B
     // measurements -- still a kernel of this library.
     const char* e = std::getenv("DIN_STEM_WGRAD_SIMT");
-    if (!(e && e[0] == '1') || kh != 3)
-      return din_stem_wgrad_tc_launch(x, x_is_u8, dz, dw, dbias, inv_scale, n, h, w, kh, stride, pad, prep,
+    if (!(e && e[0] == '1') || kh != 3 || stride != 1)
+      return din_stem_wgrad_tc_launch(x, x_is_u8, dz, dw, dbias, inv_scale, n, h, w, c_out, kh, stride, pad, prep,
                                       static_cast<cudaStream_t>(stream));
   }
   const int sms = din_num_sms();
@@ -565,20 +660,70 @@ extern "C" int din_add_f16(const void* a, const void* b, void* y, long long coun
   return DIN_OK;
 }
 
-extern "C" int din_maxpool3s2_relu_bwd_nhwc_f16(const void* x, const void* dy, void* dz, int n, int h, int w, int c,
-                                                void* stream) {
-  DIN_CHECK_ARG(x && dy && dz, "din_maxpool3s2_relu_bwd_nhwc_f16: null pointer");
-  DIN_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "din_maxpool3s2_relu_bwd_nhwc_f16: bad shape");
-  const int oh = (h + 2 - 3) / 2 + 1, ow = (w + 2 - 3) / 2 + 1;
+extern "C" int din_relu_bwd_slice_nhwc_f16(const void* y, const void* dy, void* dz, long long rows, int c, int y_c_stride,
+                                          int dy_c_stride, int dz_c_stride, void* stream) {
+  const char* who = "din_relu_bwd_slice_nhwc_f16";
+  DIN_CHECK_ARG(y && dy && dz, "%s: null pointer", who);
+  DIN_CHECK_ARG(rows > 0 && c > 0 && c % 8 == 0 && y_c_stride >= c && dy_c_stride >= c && dz_c_stride >= c &&
+                    (y_c_stride | dy_c_stride | dz_c_stride) % 8 == 0, "%s: bad shape rows=%lld c=%d", who, rows, c);
+  DIN_CHECK_ARG(((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dz)) & 15) == 0,
+                "%s: pointers must be 16-byte aligned", who);
+  const long long total = rows * (c / 8);
+  DIN_CHECK_ARG((total + 255) / 256 <= INT32_MAX, "%s: too large", who);
+  relu_bwd_slice_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(y), static_cast<const __half*>(dy), static_cast<__half*>(dz), rows, c / 8, y_c_stride / 8,
+      dy_c_stride / 8, dz_c_stride / 8);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
+extern "C" int din_upsample_bilinear_bwd_nhwc_f16(const void* dy, void* dx, int n, int h, int w, int c, int dy_c_stride,
+                                                  int dx_c_stride, int oh, int ow, void* stream) {
+  const char* who = "din_upsample_bilinear_bwd_nhwc_f16";
+  DIN_CHECK_ARG(dy && dx, "%s: null pointer", who);
+  DIN_CHECK_ARG(n > 0 && h > 0 && w > 0 && oh > 0 && ow > 0 && c > 0 && c % 8 == 0 && dy_c_stride >= c && dx_c_stride >= c &&
+                    (dy_c_stride | dx_c_stride) % 8 == 0, "%s: bad shape", who);
+  DIN_CHECK_ARG(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0,
+                "%s: pointers must be 16-byte aligned", who);
+  const long long total = static_cast<long long>(n) * h * w * (c / 8);
+  DIN_CHECK_ARG((total + 255) / 256 <= INT32_MAX, "%s: too large", who);
+  upsample_bilinear_bwd_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(dy), static_cast<__half*>(dx), n, h, w, c / 8, dy_c_stride / 8, dx_c_stride / 8, oh, ow);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
+extern "C" int din_maxpool3s2_bwd_nhwc_f16(const void* x, const void* dy, void* dz, int n, int h, int w, int c,
+                                          int x_c_stride, int dy_c_stride, int dz_c_stride, int pad, int accumulate,
+                                          void* stream) {
+  const char* who = "din_maxpool3s2_bwd_nhwc_f16";
+  DIN_CHECK_ARG(x && dy && dz, "%s: null pointer", who);
+  DIN_CHECK_ARG(n > 0 && h >= 3 - 2 * pad && w >= 3 - 2 * pad && c > 0 && c % 8 == 0 && (pad == 0 || pad == 1), "%s: bad shape", who);
+  DIN_CHECK_ARG(x_c_stride >= c && dy_c_stride >= c && dz_c_stride >= c && (x_c_stride | dy_c_stride | dz_c_stride) % 8 == 0,
+                "%s: channel strides must be >= c and multiples of 8", who);
+  DIN_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dz)) & 15) == 0,
+                "%s: pointers must be 16-byte aligned", who);
+  const int oh = (h + 2 * pad - 3) / 2 + 1, ow = (w + 2 * pad - 3) / 2 + 1;
   const int tiles_x = (w + kMpTileW - 1) / kMpTileW, tiles_y = (h + kMpTileH - 1) / kMpTileH;
   const long long ctas = static_cast<long long>(n) * tiles_x * tiles_y;
   const size_t smem = static_cast<size_t>(kMpWinH) * kMpWinW * (c / 8) * sizeof(uint4);
-  DIN_CHECK_ARG(ctas <= INT32_MAX && smem <= 48 * 1024, "din_maxpool3s2_relu_bwd_nhwc_f16: too large (c <= 280)");
-  maxpool3s2_relu_bwd_kernel<<<static_cast<int>(ctas), 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(x), static_cast<const __half*>(dy), static_cast<__half*>(dz), h, w, c / 8, oh, ow, tiles_x,
-      tiles_y);
+  DIN_CHECK_ARG(ctas <= INT32_MAX && smem <= 48 * 1024, "%s: too large (c <= 288)", who);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (pad == 1)
+    maxpool3s2_relu_bwd_kernel<1><<<static_cast<int>(ctas), 256, smem, st>>>(
+        static_cast<const __half*>(x), static_cast<const __half*>(dy), static_cast<__half*>(dz), h, w, c / 8, oh, ow, tiles_x,
+        tiles_y, x_c_stride / 8, dy_c_stride / 8, dz_c_stride / 8, accumulate);
+  else
+    maxpool3s2_relu_bwd_kernel<0><<<static_cast<int>(ctas), 256, smem, st>>>(
+        static_cast<const __half*>(x), static_cast<const __half*>(dy), static_cast<__half*>(dz), h, w, c / 8, oh, ow, tiles_x,
+        tiles_y, x_c_stride / 8, dy_c_stride / 8, dz_c_stride / 8, accumulate);
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;
+}
+
+extern "C" int din_maxpool3s2_relu_bwd_nhwc_f16(const void* x, const void* dy, void* dz, int n, int h, int w, int c,
+                                                void* stream) {
+  return din_maxpool3s2_bwd_nhwc_f16(x, dy, dz, n, h, w, c, c, c, c, 1, 0, stream);
 }
 
 extern "C" int din_bn_gamma_grad_f16(const void* dz, const void* zsrc, const void* sub, const float* gamma,

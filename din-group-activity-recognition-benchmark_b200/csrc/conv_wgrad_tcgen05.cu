@@ -1,4 +1,5 @@
-// conv_wgrad_tcgen05.cu — weight gradient of the backbone's 3x3 stride-1 convolutions on the tcgen05 tensor cores.
+// conv_wgrad_tcgen05.cu — weight gradient of the backbones' stride-1 convolutions (1x1, 3x3, 5x5, 1x7, 7x1; any padding)
+// on the tcgen05 tensor cores.
 //
 // What autograd computes for nn.Conv2d.weight in `total_loss.backward()` (train_net_dynamic.py:220-224) when the
 // backbone is trained (scripts/train_volleyball_stage2_dynamic.py:12 `cfg.train_backbone = True`; VGG-16
@@ -11,11 +12,12 @@
 // loads (64 channels = one 128-byte swizzle row per pixel) are consumed without any transpose:
 //   * A = dZ tile: 16 x 8 output pixels x 128 output channels = two boxes {64 c, 8 w, 16 h}: K = 128 pixel rows,
 //     8-row groups 1024 B apart (SBO), the two 64-channel halves 16 KB apart (LBO);
-//   * B = the input halo rows of ONE filter row ky: {64 c, 10 w, 16 h} per 64 input channels; tap kx is the same
-//     shared memory seen through a descriptor shifted by kx rows, with SBO = the halo pitch (10 rows): the
-//     hardware applies the 128B swizzle on absolute address bits (probed for the forward kernel);
-//   * accumulators: three taps x NCI input channels = 384 (192) fp32 TMEM columns, accumulated over ALL pixel
-//     tiles the CTA owns (no per-tile epilogue); TMA zero-fill is the padding and also nulls ragged tiles.
+//   * B = the input halo rows of ONE filter row ky: {64 c, 8 + KW - 1 w, 16 h} per 64 input channels; tap kx is the
+//     same shared memory seen through a descriptor shifted by kx rows, with SBO = the halo pitch (8 + KW - 1 rows):
+//     the hardware applies the 128B swizzle on absolute address bits (probed for the forward kernel);
+//   * accumulators: KW taps x NCI input channels fp32 TMEM columns (3 x 128, 5 x 64, 7 x 64, 1 x 128), accumulated over
+//     ALL pixel tiles the CTA owns (no per-tile epilogue); TMA zero-fill is the padding, nulls ragged tiles and fills a
+//     partial last channel block (Inception-v3: c_in = 32, 48, 80, 96, 160, 288; the tensor map carries the real c_in).
 // Work unit = (128 output channels, NCI input channels, filter row ky); the pixel tiles of a unit are split over
 // several CTAs so that the grid fills the 148 SMs about twice; each CTA finishes with fp32 vector atomics into dW
 // (scaled by 1/loss-scale).  One producer warp, one MMA warp (a single elected lane issues), four epilogue warps.
@@ -37,7 +39,7 @@ struct WgradParams {
 
 constexpr int kWgThreads = 192;
 constexpr int kWgABytes = 128 * 128;       // one 64-channel half of the dZ tile: 128 pixel rows x 128 B
-constexpr int kWgBBytes = 160 * 128;       // one 64-channel block of the halo rows: 16 x 10 pixel rows x 128 B
+constexpr int wg_b_bytes(int kw) { return 16 * (8 + kw - 1) * 128; }   // one 64-channel block of the halo rows of a filter row
 constexpr int kWgMaxStages = 6;
 
 // shared-memory descriptor for an MN-major SWIZZLE_128B operand (canonical layout ((8,8,m),(8,k)) in 16-byte
@@ -59,12 +61,15 @@ __host__ __device__ constexpr uint32_t idesc_f16_f32_mn(int m, int n) {
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-template <int NCI>
+template <int NCI, int KW>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_constant__ CUtensorMap tmap_x,
                   const WgradParams p, const int n_stages) {
+  constexpr int kWgBBytes = wg_b_bytes(KW);
+  constexpr int kPitchBytes = (8 + KW - 1) * 128;         // one halo row
   constexpr int kStageBytes = 2 * kWgABytes + (NCI / 64) * kWgBBytes;
-  constexpr int kTmemCols = (3 * NCI <= 256) ? 256 : 512;
+  constexpr int kTmemCols = (KW * NCI <= 64) ? 64 : (KW * NCI <= 128) ? 128 : (KW * NCI <= 256) ? 256 : 512;
+  static_assert(KW * NCI <= 512, "accumulators exceed TMEM");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem(smem_raw, 1024);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + n_stages * kStageBytes);
@@ -135,11 +140,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
       const uint32_t sb = sa + 2 * kWgABytes;
       if (leader) {
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
+        for (int kx = 0; kx < KW; ++kx) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {            // 16 pixels (two 8-pixel tile rows) per MMA
             const uint64_t ad = desc_mn_sw128(sa + ks * 2048, kWgABytes, 1024);
-            const uint64_t bd = desc_mn_sw128(sb + kx * 128 + ks * 2560, kWgBBytes, 1280);
+            const uint64_t bd = desc_mn_sw128(sb + kx * 128 + ks * 2 * kPitchBytes, kWgBBytes, kPitchBytes);
             umma_f16_ss(tmem_base + kx * NCI, ad, bd, idesc, ks == 0 ? accum : 1u);
           }
         }
@@ -158,7 +163,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
     const int co = co0 + q * 32 + lane;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-    for (int kx = 0; kx < 3; ++kx) {
+    for (int kx = 0; kx < KW; ++kx) {
 #pragma unroll 1
       for (int c0 = 0; c0 < NCI; c0 += 32) {
         uint32_t v[32];
@@ -168,7 +173,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
           float* dst = p.dw + ((static_cast<size_t>(co) * p.kh + ky) * p.kw + kx) * p.c_in + ci0 + c0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            atomicAdd(reinterpret_cast<float4*>(dst + j),
+            if (ci0 + c0 + j < p.c_in)                  // partial last channel block (c_in is a multiple of 8)
+              atomicAdd(reinterpret_cast<float4*>(dst + j),
                       make_float4(__uint_as_float(v[j]) * scl, __uint_as_float(v[j + 1]) * scl,
                                   __uint_as_float(v[j + 2]) * scl, __uint_as_float(v[j + 3]) * scl));
           }
@@ -221,14 +227,14 @@ colsum_f16_kernel(const __half* __restrict__ dz, float* __restrict__ db, long lo
   }
 }
 
-template <int NCI>
+template <int NCI, int KW>
 int launch_wgrad(const CUtensorMap& tdz, const CUtensorMap& tx, const WgradParams& p, int grid, cudaStream_t st) {
-  constexpr int kStageBytes = 2 * kWgABytes + (NCI / 64) * kWgBBytes;
+  constexpr int kStageBytes = 2 * kWgABytes + (NCI / 64) * wg_b_bytes(KW);
   int n_stages = (220 * 1024) / kStageBytes;
   if (n_stages > 4) n_stages = 4;
   const size_t smem = static_cast<size_t>(n_stages) * kStageBytes + 1024 + (2 * kWgMaxStages + 1) * 8 + 16;
-  DIN_OPT_IN_SMEM(conv_wgrad_kernel<NCI>, smem);
-  conv_wgrad_kernel<NCI><<<grid, kWgThreads, smem, st>>>(tdz, tx, p, n_stages);
+  DIN_OPT_IN_SMEM((conv_wgrad_kernel<NCI, KW>), smem);
+  conv_wgrad_kernel<NCI, KW><<<grid, kWgThreads, smem, st>>>(tdz, tx, p, n_stages);
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;
 }
@@ -241,10 +247,11 @@ extern "C" int din_conv2d_wgrad_nhwc_f16(const void* x, const void* dz, float* d
                                          void* stream) {
   DIN_CHECK_ARG(x && dz && dw, "din_conv2d_wgrad_nhwc_f16: null pointer");
   DIN_CHECK_ARG(n > 0 && h > 0 && w > 0, "din_conv2d_wgrad_nhwc_f16: bad extent n=%d h=%d w=%d", n, h, w);
-  DIN_CHECK_ARG(kh == 3 && kw == 3, "din_conv2d_wgrad_nhwc_f16: only 3x3 stride-1 filters (got %dx%d)", kh, kw);
-  DIN_CHECK_ARG(pad_h >= 0 && pad_h <= 2 && pad_w >= 0 && pad_w <= 2, "din_conv2d_wgrad_nhwc_f16: bad padding");
-  DIN_CHECK_ARG(c_in > 0 && c_in % 64 == 0 && x_c_stride >= c_in && x_c_stride % 8 == 0,
-                "din_conv2d_wgrad_nhwc_f16: c_in=%d must be a multiple of 64 (x_c_stride=%d)", c_in, x_c_stride);
+  DIN_CHECK_ARG((kw == 1 || kw == 3 || kw == 5 || kw == 7) && kh >= 1 && kh <= 7,
+                "din_conv2d_wgrad_nhwc_f16: stride-1 filters with kw in {1,3,5,7} and kh <= 7 (got %dx%d)", kh, kw);
+  DIN_CHECK_ARG(pad_h >= 0 && pad_h < kh + 2 && pad_w >= 0 && pad_w < kw + 2, "din_conv2d_wgrad_nhwc_f16: bad padding");
+  DIN_CHECK_ARG(c_in > 0 && c_in % 8 == 0 && x_c_stride >= c_in && x_c_stride % 8 == 0,
+                "din_conv2d_wgrad_nhwc_f16: c_in=%d must be a multiple of 8 (x_c_stride=%d)", c_in, x_c_stride);
   DIN_CHECK_ARG(c_out > 0 && c_out % 8 == 0 && dz_c_stride >= c_out && dz_c_stride % 8 == 0,
                 "din_conv2d_wgrad_nhwc_f16: c_out=%d must be a multiple of 8 (dz_c_stride=%d)", c_out, dz_c_stride);
   DIN_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(dw)) & 15) == 0,
@@ -255,7 +262,7 @@ extern "C" int din_conv2d_wgrad_nhwc_f16(const void* x, const void* dz, float* d
   DIN_CHECK_ARG(sms > 0, "din_conv2d_wgrad_nhwc_f16: no CUDA device");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-  const int nci = (c_in % 128 == 0) ? 128 : 64;
+  const int nci = (c_in % 128 == 0 && kw <= 3) ? 128 : 64;        // kw * nci fp32 accumulator columns <= 512
   WgradParams p{};
   p.c_in = c_in; p.c_out = c_out; p.kh = kh; p.kw = kw; p.pad_h = pad_h; p.pad_w = pad_w;
   p.tiles_x = (ow + 7) / 8;
@@ -263,7 +270,7 @@ extern "C" int din_conv2d_wgrad_nhwc_f16(const void* x, const void* dz, float* d
   const long long tiles = static_cast<long long>(n) * p.tiles_per_img;
   DIN_CHECK_ARG(tiles < INT32_MAX, "din_conv2d_wgrad_nhwc_f16: too many tiles");
   p.num_tiles = static_cast<int>(tiles);
-  p.n_ci_blk = c_in / nci;
+  p.n_ci_blk = (c_in + nci - 1) / nci;
   const int units = ((c_out + 127) / 128) * p.n_ci_blk * kh;
   int splits = (2 * sms + units - 1) / units;
   if (splits > p.num_tiles) splits = p.num_tiles;
@@ -289,14 +296,20 @@ extern "C" int din_conv2d_wgrad_nhwc_f16(const void* x, const void* dz, float* d
                               static_cast<uint64_t>(n)};
     const uint64_t cs = static_cast<uint64_t>(x_c_stride) * 2;
     const uint64_t strides[4] = {2, cs, cs * w, cs * w * h};
-    const uint32_t box[4] = {64, 10, 16, 1};
+    const uint32_t box[4] = {64, static_cast<uint32_t>(8 + kw - 1), 16, 1};
     const uint32_t es[4] = {1, 1, 1, 1};
     int rc = din_encode_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
                              CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != DIN_OK) return rc;
   }
   const int grid = units * p.splits;
-  int rc = (nci == 128) ? launch_wgrad<128>(tdz, tx, p, grid, st) : launch_wgrad<64>(tdz, tx, p, grid, st);
+  int rc;
+  switch (kw) {
+    case 1: rc = (nci == 128) ? launch_wgrad<128, 1>(tdz, tx, p, grid, st) : launch_wgrad<64, 1>(tdz, tx, p, grid, st); break;
+    case 3: rc = (nci == 128) ? launch_wgrad<128, 3>(tdz, tx, p, grid, st) : launch_wgrad<64, 3>(tdz, tx, p, grid, st); break;
+    case 5: rc = launch_wgrad<64, 5>(tdz, tx, p, grid, st); break;
+    default: rc = launch_wgrad<64, 7>(tdz, tx, p, grid, st); break;
+  }
   if (rc != DIN_OK) return rc;
   if (dbias != nullptr) {
     DIN_CHECK_ARG(c_out <= 2048, "din_conv2d_wgrad_nhwc_f16: c_out=%d too large for the bias reduction", c_out);
@@ -307,5 +320,21 @@ extern "C" int din_conv2d_wgrad_nhwc_f16(const void* x, const void* dz, float* d
     colsum_f16_kernel<<<g, 256, 0, st>>>(static_cast<const __half*>(dz), dbias, rows, c_out, dz_c_stride, inv_scale);
     DIN_CHECK_CUDA(cudaGetLastError());
   }
+  return DIN_OK;
+}
+
+extern "C" int din_colsum_nhwc_f16(const void* dz, float* db, long long rows, int c, int c_stride, const float* inv_scale,
+                                   void* stream) {
+  const char* who = "din_colsum_nhwc_f16";
+  DIN_CHECK_ARG(dz && db, "%s: null pointer", who);
+  DIN_CHECK_ARG(rows > 0 && c > 0 && c % 8 == 0 && c <= 2048 && c_stride >= c && c_stride % 8 == 0, "%s: bad shape", who);
+  DIN_CHECK_ARG((reinterpret_cast<uintptr_t>(dz) & 15) == 0, "%s: dz must be 16-byte aligned", who);
+  const int sms = din_num_sms();
+  int g = 2 * (sms > 0 ? sms : 148);
+  const long long per = 256 / (c / 8);
+  if (static_cast<long long>(g) * per > rows) g = static_cast<int>((rows + per - 1) / per);
+  colsum_f16_kernel<<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(dz), db, rows, c, c_stride,
+                                                                     inv_scale);
+  DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;
 }

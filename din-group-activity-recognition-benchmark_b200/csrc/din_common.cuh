@@ -62,7 +62,7 @@ int din_stem_tc_launch(const void* x, int x_is_u8, const float* w, const float* 
 
 // tensor-core stem weight gradient (stem_tc.cu); arguments already validated by din_stem_wgrad
 int din_stem_wgrad_tc_launch(const void* x, int x_is_u8, const void* dz, float* dw, float* dbias, const float* inv_scale,
-                             int n, int h, int w_in, int kh, int stride, int pad, int prep, cudaStream_t st);
+                             int n, int h, int w_in, int c_out, int kh, int stride, int pad, int prep, cudaStream_t st);
 
 #ifdef __CUDACC__
 namespace din {

@@ -1108,7 +1108,7 @@ __device__ __forceinline__ uint64_t desc_mn_sw128_stem(uint32_t addr, uint32_t l
 template <int KH, int KW, int STRIDE, bool U8>
 __global__ void __launch_bounds__(kStemThreads)
 stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dz, const StemParams p, float* __restrict__ dw,
-                     float* __restrict__ db, const float* __restrict__ inv_scale) {
+                     float* __restrict__ db, const float* __restrict__ inv_scale, const int c_out) {
   using Cfg = StemCfg<64, KH, KW, STRIDE>;
   using SC = SwgCfg<KH, KW, STRIDE>;
   extern __shared__ uint8_t smem_raw[];
@@ -1198,7 +1198,7 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dz, const StemPara
   }
 
   // ---- flush: TMEM lanes 0..63 = output channels, columns = taps (kTaps = bias)
-  if (any && warp < 2) {
+  if (any && warp < 2 && warp * 32 < c_out) {               // c_out = 32 (Inception-v3): rows 32.. were zero-filled by TMA
     const float scl = inv_scale ? __ldg(inv_scale) : 1.0f;
     const int co = warp * 32 + lane;
 #pragma unroll 1
@@ -1223,7 +1223,7 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dz, const StemPara
 }
 
 template <int KH, int KW, int STRIDE, bool U8>
-int launch_stem_wgrad(const CUtensorMap& tdz, StemParams& p, float* dw, float* dbias, const float* inv_scale,
+int launch_stem_wgrad(const CUtensorMap& tdz, StemParams& p, float* dw, float* dbias, const float* inv_scale, int c_out,
                       cudaStream_t st) {
   using SC = SwgCfg<KH, KW, STRIDE>;
   const int sms = din_num_sms();
@@ -1235,7 +1235,7 @@ int launch_stem_wgrad(const CUtensorMap& tdz, StemParams& p, float* dw, float* d
   if (grid > p.num_tiles) grid = p.num_tiles;
   DIN_OPT_IN_SMEM((stem_wgrad_tc_kernel<KH, KW, STRIDE, U8>), SC::kSmem);
   stem_wgrad_tc_kernel<KH, KW, STRIDE, U8><<<static_cast<int>(grid), kStemThreads, SC::kSmem, st>>>(tdz, p, dw, dbias,
-                                                                                                  inv_scale);
+                                                                                                  inv_scale, c_out);
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;
 }
@@ -1265,9 +1265,10 @@ int din_stem_tc_launch(const void* x, int x_is_u8, const float* w, const float* 
 }
 
 // Tensor-core stem weight gradient (see stem_wgrad_tc_kernel); arguments validated by din_stem_wgrad.
-// Geometries: VGG-16 (3x3, stride 1, pad 1) and ResNet-18 (7x7, stride 2, pad 3), 64 output channels.
+// Geometries: VGG-16 (3x3, stride 1, pad 1) and ResNet-18 (7x7, stride 2, pad 3) with 64 output channels, Inception-v3
+// (3x3, stride 2, pad 0) with 32.
 int din_stem_wgrad_tc_launch(const void* x, int x_is_u8, const void* dz, float* dw, float* dbias, const float* inv_scale,
-                             int n, int h, int w_in, int kh, int stride, int pad, int prep, cudaStream_t st) {
+                             int n, int h, int w_in, int c_out, int kh, int stride, int pad, int prep, cudaStream_t st) {
   StemParams p{};
   p.x = x; p.n = n; p.h = h; p.w_in = w_in; p.pad = pad; p.prep = prep;
   p.oh = (h + 2 * pad - kh) / stride + 1;
@@ -1280,8 +1281,11 @@ int din_stem_wgrad_tc_launch(const void* x, int x_is_u8, const void* dz, float* 
   fastdiv(static_cast<uint32_t>(p.oh), &p.fo_mul, &p.fo_shr);
   CUtensorMap tdz;
   {
-    const uint64_t dims[4] = {64, static_cast<uint64_t>(p.ow), static_cast<uint64_t>(p.oh), static_cast<uint64_t>(n)};
-    const uint64_t strides[4] = {2, 128, 128ull * p.ow, 128ull * p.ow * p.oh};
+    // c_out = 32: the 64-channel box is half out of bounds -> zero-filled rows 32..63 of M
+    const uint64_t cs = 2ull * c_out;
+    const uint64_t dims[4] = {static_cast<uint64_t>(c_out), static_cast<uint64_t>(p.ow), static_cast<uint64_t>(p.oh),
+                              static_cast<uint64_t>(n)};
+    const uint64_t strides[4] = {2, cs, cs * p.ow, cs * p.ow * p.oh};
     const uint32_t box[4] = {64, 128, 1, 1};
     const uint32_t es[4] = {1, 1, 1, 1};
     int rc = din_encode_tmap(&tdz, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(dz), dims, strides, box, es,
@@ -1289,10 +1293,13 @@ int din_stem_wgrad_tc_launch(const void* x, int x_is_u8, const void* dz, float* 
     if (rc != DIN_OK) return rc;
   }
   if (kh == 3 && stride == 1)
-    return x_is_u8 ? launch_stem_wgrad<3, 3, 1, true>(tdz, p, dw, dbias, inv_scale, st)
-                   : launch_stem_wgrad<3, 3, 1, false>(tdz, p, dw, dbias, inv_scale, st);
+    return x_is_u8 ? launch_stem_wgrad<3, 3, 1, true>(tdz, p, dw, dbias, inv_scale, c_out, st)
+                   : launch_stem_wgrad<3, 3, 1, false>(tdz, p, dw, dbias, inv_scale, c_out, st);
   if (kh == 7 && stride == 2)
-    return x_is_u8 ? launch_stem_wgrad<7, 7, 2, true>(tdz, p, dw, dbias, inv_scale, st)
-                   : launch_stem_wgrad<7, 7, 2, false>(tdz, p, dw, dbias, inv_scale, st);
+    return x_is_u8 ? launch_stem_wgrad<7, 7, 2, true>(tdz, p, dw, dbias, inv_scale, c_out, st)
+                   : launch_stem_wgrad<7, 7, 2, false>(tdz, p, dw, dbias, inv_scale, c_out, st);
+  if (kh == 3 && stride == 2)                                  // Inception-v3 Conv2d_1a_3x3 (32 channels, pad 0)
+    return x_is_u8 ? launch_stem_wgrad<3, 3, 2, true>(tdz, p, dw, dbias, inv_scale, c_out, st)
+                   : launch_stem_wgrad<3, 3, 2, false>(tdz, p, dw, dbias, inv_scale, c_out, st);
   return din_set_error(DIN_ERR_UNSUPPORTED, "din_stem_wgrad: unsupported stem geometry %dx%d stride %d", kh, kh, stride);
 }

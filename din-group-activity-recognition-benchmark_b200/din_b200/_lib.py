@@ -77,6 +77,10 @@ PROTOTYPES = {
     "din_scatter2_nhwc_f16": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_add_f16": (C.c_int, [_vp, _vp, _vp, _ll, _vp]),
     "din_maxpool3s2_relu_bwd_nhwc_f16": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "din_maxpool3s2_bwd_nhwc_f16": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "din_relu_bwd_slice_nhwc_f16": (C.c_int, [_vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp]),
+    "din_upsample_bilinear_bwd_nhwc_f16": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "din_colsum_nhwc_f16": (C.c_int, [_vp, _fp, _ll, _i, _i, _fp, _vp]),
     "din_bn_gamma_grad_f16": (C.c_int, [_vp, _vp, _vp, _fp, _fp, _fp, _fp, _ll, _i, _vp]),
     "din_scale_rows_f32": (C.c_int, [_fp, _fp, _ll, _ll, _vp]),
     "din_gemm_f32": (C.c_int, [_fp, _ll, _ll, _vp, _i, _ll, _ll, _fp, _ll, _i, _i, _i, C.c_float, _i, _vp]),

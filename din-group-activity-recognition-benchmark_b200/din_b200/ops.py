@@ -579,8 +579,10 @@ def dynamic_infer_bwd(x, w_tap, b_cat, dy, dx, kernel, ratio, *, scale_factor=Tr
 # ---------------------------------------------------------------------------------------------
 # backward of the backbone (VGG-16: 3x3 stride-1 convolutions)
 # ---------------------------------------------------------------------------------------------
-def conv2d_wgrad_nhwc(x, dz, dw, dbias=None, *, pad=(1, 1), inv_scale=None, c_in=None, c_out=None):
-    """dw [c_out,3,3,c_in] fp32 (+)= sum_pixels dz (x) x_shifted;  dbias [c_out] (+)= sum_pixels dz.  Accumulates."""
+def conv2d_wgrad_nhwc(x, dz, dw, dbias=None, *, pad=(1, 1), inv_scale=None, c_in=None, c_out=None, x_c_offset=0,
+                      dz_c_offset=0):
+    """dw [c_out,kh,kw,c_in] fp32 (+)= sum_pixels dz (x) x_shifted;  dbias [c_out] (+)= sum_pixels dz.  Accumulates.
+    x / dz may be channel slices (x_c_offset / dz_c_offset) of wider NHWC buffers."""
     _need(x, torch.float16, "x")
     _need(dz, torch.float16, "dz")
     _need(dw, torch.float32, "dw")
@@ -588,14 +590,16 @@ def conv2d_wgrad_nhwc(x, dz, dw, dbias=None, *, pad=(1, 1), inv_scale=None, c_in
     co, kh, kw, ci = dw.shape
     assert dz.shape[0] == n and dz.shape[1] == h + 2 * pad[0] - kh + 1 and dz.shape[2] == w + 2 * pad[1] - kw + 1, \
         (tuple(x.shape), tuple(dz.shape))
-    assert ci <= cx and co <= dz.shape[3]
+    assert x_c_offset + ci <= cx and dz_c_offset + co <= dz.shape[3]
     if dbias is not None:
         _need(dbias, torch.float32, "dbias")
     if inv_scale is not None:
         _need(inv_scale, torch.float32, "inv_scale")
     flops = 2 * n * dz.shape[1] * dz.shape[2] * co * kh * kw * ci
     with _launch(f"wgrad{kh}x{kw}_{ci}->{co}@{dz.shape[1]}x{dz.shape[2]}", flops, 2 * (x.numel() + dz.numel())):
-        check(_lib.load().din_conv2d_wgrad_nhwc_f16(_p(x), _p(dz), _p(dw), _p(dbias), _p(inv_scale), n, h, w, ci, cx, co,
+        check(_lib.load().din_conv2d_wgrad_nhwc_f16(C.c_void_p(x.data_ptr() + 2 * x_c_offset),
+                                                    C.c_void_p(dz.data_ptr() + 2 * dz_c_offset), _p(dw), _p(dbias),
+                                                    _p(inv_scale), n, h, w, ci, cx, co,
                                                     dz.shape[3], kh, kw, pad[0], pad[1], _stream()),
               "din_conv2d_wgrad_nhwc_f16")
     return dw
@@ -650,11 +654,11 @@ def stem_wgrad(x, dz, dw, dbias, *, stride=1, pad=1, inv_scale=None, prep=True):
     _need(dz, torch.float16, "dz")
     _need(dw, torch.float32, "dw")
     n, h, w = (x.shape[0], x.shape[1], x.shape[2]) if u8 else (x.shape[0], x.shape[2], x.shape[3])
-    k = dw.shape[2]
+    k, co = dw.shape[2], dw.shape[0]
     oh, ow = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
-    assert tuple(dz.shape) == (n, oh, ow, 64) and tuple(dw.shape) == (64, 3, k, k), (tuple(dz.shape), tuple(dw.shape))
-    with _launch(f"stem_wgrad{k}x{k}", 2 * n * oh * ow * 64 * 3 * k * k, x.numel() * x.element_size() + 2 * dz.numel()):
-        check(_lib.load().din_stem_wgrad(_p(x), int(u8), _p(dz), _p(dw), _p(dbias), _p(inv_scale), n, h, w, 64, k, k,
+    assert tuple(dz.shape) == (n, oh, ow, co) and tuple(dw.shape) == (co, 3, k, k), (tuple(dz.shape), tuple(dw.shape))
+    with _launch(f"stem_wgrad{k}x{k}", 2 * n * oh * ow * co * 3 * k * k, x.numel() * x.element_size() + 2 * dz.numel()):
+        check(_lib.load().din_stem_wgrad(_p(x), int(u8), _p(dz), _p(dw), _p(dbias), _p(inv_scale), n, h, w, co, k, k,
                                          stride, pad, int(prep), _stream()), "din_stem_wgrad")
     return dw
 
@@ -695,6 +699,65 @@ def maxpool3s2_relu_bwd_nhwc(x, dy):
         check(_lib.load().din_maxpool3s2_relu_bwd_nhwc_f16(_p(x), _p(dy), _p(dz), n, h, w, c, _stream()),
               "din_maxpool3s2_relu_bwd_nhwc_f16")
     return dz
+
+
+def maxpool3s2_bwd_nhwc(x, dy, dz, *, c, pad=0, x_c_offset=0, dy_c_offset=0, dz_c_offset=0, accumulate=False):
+    """dz[..., dz_c_offset:+c] (+)= MaxPool2d(3, 2, pad) backward of dy[..., dy_c_offset:+c] routed by x[..., x_c_offset:+c]
+    (first maximum of each window), times [x > 0]."""
+    for name, t in (("x", x), ("dy", dy), ("dz", dz)):
+        _need(t, torch.float16, name)
+    n, h, w, cx = x.shape
+    oh, ow = (h + 2 * pad - 3) // 2 + 1, (w + 2 * pad - 3) // 2 + 1
+    assert tuple(dy.shape[:3]) == (n, oh, ow) and tuple(dz.shape[:3]) == (n, h, w)
+    assert x_c_offset + c <= cx and dy_c_offset + c <= dy.shape[3] and dz_c_offset + c <= dz.shape[3]
+    with _launch("maxpool3s2_bwd", 0, 2 * c * n * (2 * h * w + oh * ow)):
+        check(_lib.load().din_maxpool3s2_bwd_nhwc_f16(
+            C.c_void_p(x.data_ptr() + 2 * x_c_offset), C.c_void_p(dy.data_ptr() + 2 * dy_c_offset),
+            C.c_void_p(dz.data_ptr() + 2 * dz_c_offset), n, h, w, c, cx, dy.shape[3], dz.shape[3], pad, int(accumulate),
+            _stream()), "din_maxpool3s2_bwd_nhwc_f16")
+    return dz
+
+
+def relu_bwd_slice_nhwc(y, dy, dz, *, c, y_c_offset=0, dy_c_offset=0, dz_c_offset=0):
+    """dz[..., dz_c_offset:+c] = dy[..., dy_c_offset:+c] * [y[..., y_c_offset:+c] > 0]  (fp16 NHWC, same pixels)."""
+    for name, t in (("y", y), ("dy", dy), ("dz", dz)):
+        _need(t, torch.float16, name)
+    rows = y.numel() // y.shape[-1]
+    assert dy.numel() // dy.shape[-1] == rows == dz.numel() // dz.shape[-1]
+    assert y_c_offset + c <= y.shape[-1] and dy_c_offset + c <= dy.shape[-1] and dz_c_offset + c <= dz.shape[-1]
+    with _launch("relu_bwd_slice", 0, 6 * rows * c):
+        check(_lib.load().din_relu_bwd_slice_nhwc_f16(
+            C.c_void_p(y.data_ptr() + 2 * y_c_offset), C.c_void_p(dy.data_ptr() + 2 * dy_c_offset),
+            C.c_void_p(dz.data_ptr() + 2 * dz_c_offset), rows, c, y.shape[-1], dy.shape[-1], dz.shape[-1], _stream()),
+            "din_relu_bwd_slice_nhwc_f16")
+    return dz
+
+
+def upsample_bilinear_bwd_nhwc(dy, h, w, *, c, dy_c_offset=0, out=None):
+    """Backward of upsample_bilinear_nhwc: dy [n,oh,ow,*] (channels dy_c_offset:+c) -> dx [n,h,w,c]."""
+    _need(dy, torch.float16, "dy")
+    n, oh, ow, cy = dy.shape
+    if out is None:
+        out = torch.empty((n, h, w, c), dtype=torch.float16, device=dy.device)
+    _need(out, torch.float16, "out")
+    assert tuple(out.shape[:3]) == (n, h, w) and out.shape[3] >= c and dy_c_offset + c <= cy
+    with _launch("upsample_bwd", 0, 2 * n * c * (h * w + oh * ow)):
+        check(_lib.load().din_upsample_bilinear_bwd_nhwc_f16(C.c_void_p(dy.data_ptr() + 2 * dy_c_offset), _p(out), n, h, w, c,
+                                                             cy, out.shape[3], oh, ow, _stream()),
+              "din_upsample_bilinear_bwd_nhwc_f16")
+    return out
+
+
+def colsum_nhwc(dz, db, *, c, c_offset=0, inv_scale=None):
+    """db[0:c] += inv_scale * sum over pixels of dz[..., c_offset:+c]  (fp16 in, fp32 accumulate)."""
+    _need(dz, torch.float16, "dz")
+    _need(db, torch.float32, "db")
+    rows = dz.numel() // dz.shape[-1]
+    assert c_offset + c <= dz.shape[-1] and db.numel() == c
+    with _launch("colsum", 0, 2 * rows * c):
+        check(_lib.load().din_colsum_nhwc_f16(C.c_void_p(dz.data_ptr() + 2 * c_offset), _p(db), rows, c, dz.shape[-1],
+                                              _p(inv_scale), _stream()), "din_colsum_nhwc_f16")
+    return db
 
 
 def bn_gamma_grad(dz, zsrc, gamma, beta, dgamma, *, sub=None, inv_scale=None):

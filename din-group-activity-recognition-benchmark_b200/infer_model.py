@@ -8,11 +8,11 @@ are parameter containers and are never called.
 
 Scope: evaluation / inference forward, and the training step: `model.train()` + `loss.backward()` produce
 gradients for every parameter after the backbone through the backward kernels in csrc/head_bwd.cu, and -- with
-cfg.train_backbone = True and the VGG-16 or ResNet-18 backbone (BatchNorm in eval mode) -- for the backbone too
+cfg.train_backbone = True and the VGG-16, ResNet-18 or Inception-v3 backbone (BatchNorm in eval mode) -- for the backbone too
 (RoIAlign scatter, ReLU / max-pool backward, dgrad on the forward tcgen05 kernel, wgrad on
 csrc/conv_wgrad_tcgen05.cu, zero insertion for the stride-2 layers).
 ResNet-18 also trains with BatchNorm on batch statistics (csrc/bn_train.cu: no cfg.set_bn_eval, the reference's default).
-Training the Inception-v3 backbone, or Inception-v3 with BatchNorm on batch statistics, is not implemented and raises.
+Inception-v3 with BatchNorm on batch statistics is not implemented and raises (freeze BN as cfg.set_bn_eval does).
 """
 import collections
 
@@ -198,10 +198,10 @@ class _DinModel(nn.Module):
         if not torch.is_grad_enabled():
             return _train.forward_train(eng, images, boxes, bboxes_num, training=True)[0]
         named = _pc.trainable(self)
-        if any(n.startswith("backbone.") for n, _ in named) and self.cfg.backbone not in ("vgg16", "res18"):
+        if any(n.startswith("backbone.") for n, _ in named) and self.cfg.backbone not in ("vgg16", "res18", "inv3"):
             raise NotImplementedError(
-                f"training the backbone is implemented for VGG-16 and ResNet-18 (BatchNorm in eval mode), not "
-                f"{self.cfg.backbone!r}: set cfg.train_backbone = False (config.py:39, the stage-2 default) -- "
+                f"training the backbone is implemented for VGG-16, ResNet-18 and Inception-v3 (BatchNorm in eval mode), "
+                f"not {self.cfg.backbone!r}: set cfg.train_backbone = False (config.py:39, the stage-2 default) -- "
                 "SURVEY.md §8f rank 1")
         names = tuple(n for n, _ in named)
         return _DinTrainFn.apply(self, images, boxes, bboxes_num, names, *[p for _, p in named])

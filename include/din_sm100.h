@@ -390,16 +390,18 @@ DIN_API int din_dynamic_infer_bwd_f32(const float* x, const float* w_tap, const 
 /* ---- backward of the backbone (second slice: VGG-16) ------------------------- */
 
 /*
- * Weight (and bias) gradient of a 3x3 stride-1 convolution on the tcgen05 tensor cores:
+ * Weight (and bias) gradient of a stride-1 convolution (kw in {1, 3, 5, 7}, kh <= 7: every filter shape of the three
+ * backbones -- 1x1, 3x3, 5x5, 1x7, 7x1; any padding) on the tcgen05 tensor cores:
  *     dw[co][ky][kx][ci] += inv_scale * sum_{img,y,x} dz[img,y,x,co] * x[img, y+ky-pad_h, x+kx-pad_w, ci]
  *     dbias[co]          += inv_scale * sum_{img,y,x} dz[img,y,x,co]                      (dbias may be NULL)
  * Replaces autograd's conv2d weight/bias backward for vgg16.features.* (backbone.py:88-99) when the backbone is
  * trained (scripts/train_volleyball_stage2_dynamic.py:12).  The K dimension of this GEMM is the pixel index, so
  * both NHWC fp16 operands are consumed as MN-major UMMA tiles straight from the forward kernel's TMA boxes.
- * x  : fp16 NHWC [n, h, w, x_c_stride], channels [0, c_in) used (the conv's saved input), c_in % 64 == 0
- * dz : fp16 NHWC [n, oh, ow, dz_c_stride], oh = h + 2*pad_h - 2 (gradient w.r.t. the conv output BEFORE ReLU,
+ * x  : fp16 NHWC [n, h, w, x_c_stride], channels [0, c_in) used (the conv's saved input), c_in % 8 == 0 (a partial
+ *      last 64-channel block is zero-filled by the TMA unit: Inception-v3's 32 / 48 / 80 / 96 / 160 / 288 channels)
+ * dz : fp16 NHWC [n, oh, ow, dz_c_stride], oh = h + 2*pad_h - kh + 1 (gradient w.r.t. the conv output BEFORE ReLU,
  *      possibly multiplied by a loss scale S; then *inv_scale = 1/S, a device scalar; NULL = 1)
- * dw : fp32 [c_out][3][3][c_in] -- ACCUMULATED with atomics: zero-fill before the first call of a step (the
+ * dw : fp32 [c_out][kh][kw][c_in] -- ACCUMULATED with atomics: zero-fill before the first call of a step (the
  *      frames of a step may arrive in several calls); dbias likewise.
  */
 DIN_API int din_conv2d_wgrad_nhwc_f16(const void* x, const void* dz, float* dw, float* dbias, const float* inv_scale,
@@ -434,8 +436,9 @@ DIN_API int din_relu_pool_bwd_nhwc_f16(const void* y, const void* dy, void* dz, 
                                        void* stream);
 
 /*
- * Weight / bias gradient of the stem convolution -- VGG-16 features.0 (64 x 3 x 3x3, stride 1, pad 1) or ResNet-18
- * conv1 (64 x 3 x 7x7, stride 2, pad 3; BN folded: the caller un-folds) -- with prep_images recomputed on the raw
+ * Weight / bias gradient of the stem convolution -- VGG-16 features.0 (64 x 3 x 3x3, stride 1, pad 1), ResNet-18
+ * conv1 (64 x 3 x 7x7, stride 2, pad 3; BN folded: the caller un-folds) or Inception-v3 Conv2d_1a_3x3 (32 x 3 x 3x3,
+ * stride 2, pad 0; dw [32][3][3][3], dz [n, oh, ow, 32]) -- with prep_images recomputed on the raw
  * frames (fp32 NCHW, or uint8 NHWC when x_is_u8), on the tensor cores:
  *   dw [64][3][kh][kw] (OIHW) += inv_scale * sum_pixels dz (x) prep(x)_shifted;   dbias [64] += inv_scale * sum dz.
  * dz: fp16 NHWC [n, oh, ow, 64].  ACCUMULATES (atomics): zero-fill before the first call of a step.
@@ -466,6 +469,32 @@ DIN_API int din_add_f16(const void* a, const void* b, void* y, long long count, 
  */
 DIN_API int din_maxpool3s2_relu_bwd_nhwc_f16(const void* x, const void* dy, void* dz, int n, int h, int w, int c,
                                              void* stream);
+
+/* ---- Inception-v3 backward helpers (concat slices, 3x3/2 max-pools without padding, the multiscale resize) ---------- */
+
+/* The same routing for any MaxPool2d(3, 2, pad) with pad in {0, 1} over channel slices (x / dy / dz live in buffers with
+ * their own channel strides): F.max_pool2d(x, 3, 2) of the Inception-v3 trunk (backbone.py:50,56) and of Mixed_6a's pool
+ * branch.  x is a ReLU output everywhere in these backbones, so the x > 0 mask is the ReLU backward of the layer below.
+ * accumulate != 0: dz += (another branch already wrote its share of the same tensor's gradient).  c <= 288. */
+DIN_API int din_maxpool3s2_bwd_nhwc_f16(const void* x, const void* dy, void* dz, int n, int h, int w, int c,
+                                        int x_c_stride, int dy_c_stride, int dz_c_stride, int pad, int accumulate,
+                                        void* stream);
+
+/* dz[r, 0:c] = dy[r, 0:c] * [y[r, 0:c] > 0], rows r of three channel-strided fp16 buffers: the ReLU backward of a branch
+ * whose output is a channel slice of an Inception block's concat buffer (torch.cat backward + threshold_backward). */
+DIN_API int din_relu_bwd_slice_nhwc_f16(const void* y, const void* dy, void* dz, long long rows, int c, int y_c_stride,
+                                        int dy_c_stride, int dz_c_stride, void* stream);
+
+/* Backward of din_upsample_bilinear_nhwc_f16 (align_corners=True): dx [n,h,w,c] = sum over the outputs [n,oh,ow,c] that
+ * read each source pixel of weight * dy, gathered per source pixel with the forward's fp32 weights (no atomics).
+ * Replaces upsample_bilinear2d_backward under infer_model.py:169. */
+DIN_API int din_upsample_bilinear_bwd_nhwc_f16(const void* dy, void* dx, int n, int h, int w, int c, int dy_c_stride,
+                                               int dx_c_stride, int oh, int ow, void* stream);
+
+/* db[c] += inv_scale * sum over rows of dz[r, c] (fp16 in, fp32 atomics out; dz may be a channel slice): the bias /
+ * BatchNorm-shift gradient of a branch whose bias is applied outside its convolution (the Inception pool branches). */
+DIN_API int din_colsum_nhwc_f16(const void* dz, float* db, long long rows, int c, int c_stride, const float* inv_scale,
+                                void* stream);
 
 /*
  * Gradient of an eval-mode BatchNorm's weight when the BN is folded into its convolution (z = gamma*xhat + beta):

@@ -92,7 +92,10 @@ def main_grads():
 def main_fullgrads():
     """The whole model trained, backbone included (scripts/train_volleyball_stage2_dynamic.py:12); ResNet-18 with its
     BatchNorm layers in eval mode (config.py set_bn_eval / train_net.py:25-28)."""
-    for name in ("vgg16_lite", "res18_lite", "collective_res18"):   # the last: scripts/train_collective_stage2_dynamic.py
+    names = ("vgg16_lite", "res18_lite", "collective_res18", "inv3_full")   # the third: scripts/train_collective_stage2_dynamic.py
+    if "--missing-only" in sys.argv:
+        names = tuple(n for n in names if not os.path.exists(os.path.join(OUT, f"fullgrads_{n}.pt")))
+    for name in names:
         pc, B = model_cases()[name]
         bb = O.build_backbone(pc.backbone)
         sd = O.make_state_dict(pc, seed=0, backbone=bb)
@@ -106,6 +109,8 @@ def main_fullgrads():
         print("fullgrads", name, float(loss), len(grads))
     # BatchNorm on batch statistics (cfg.set_bn_eval = False, the default: scripts/train_collective_stage2_dynamic.py)
     for name in ("res18_lite", "collective_res18"):
+        if "--missing-only" in sys.argv and os.path.exists(os.path.join(OUT, f"bntrain_{name}.pt")):
+            continue
         pc, B = model_cases()[name]
         bb = O.build_backbone(pc.backbone)
         sd = O.make_state_dict(pc, seed=0, backbone=bb)

