@@ -77,6 +77,11 @@ PROTOTYPES = {
     "din_scatter2_nhwc_f16": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_add_f16": (C.c_int, [_vp, _vp, _vp, _ll, _vp]),
     "din_maxpool3s2_relu_bwd_nhwc_f16": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "din_resize_bilinear_u8": (C.c_int, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
+    "din_jpeg_backend": (C.c_int, []),
+    "din_jpeg_image_info": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "din_jpeg_decode_resize_u8": (C.c_int, [C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), _i, _vp, _i, _i, _vp, C.c_size_t,
+                                            _i, _vp]),
     "din_maxpool3s2_bwd_nhwc_f16": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_relu_bwd_slice_nhwc_f16": (C.c_int, [_vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp]),
     "din_upsample_bilinear_bwd_nhwc_f16": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -471,6 +471,8 @@ class Res18Plan:
         (din_scale_rows_f32), OIHW layout (permutes only)."""
         def put(conv_name, bn_name, conv, a, w_oihw):
             w_oihw = w_oihw.contiguous()
+            if w_oihw.data_ptr() == a["dw"].data_ptr():
+                w_oihw = w_oihw.clone()         # the stem's accumulator is OIHW already: never scale `acc` in place
             if not self.bn_train:
                 # folded eval-mode BatchNorm: d(gamma) = invstd * (<W, dW_folded> - mean * d(beta)), then dW = scale * dW_folded
                 ops.bn_fold_grads(conv.w_src, w_oihw, a["dbeta"], conv.bn["running_mean"], conv.bn["running_var"],

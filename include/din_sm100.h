@@ -387,6 +387,39 @@ DIN_API int din_dynamic_infer_bwd_f32(const float* x, const float* w_tap, const 
                                       const float* coef_ptr, float coef_scalar, const int32_t* n_valid,
                                       void* stream);
 
+/* ---- the loader's per-frame work on the device: JPEG decode + resize -------------------- */
+
+/*
+ * PIL-exact bilinear resize of interleaved uint8 RGB frames: src [n, h, w, 3] -> dst [n, oh, ow, 3], bit-identical to
+ * Pillow's Image.resize((ow, oh), Image.BILINEAR) (antialiased when shrinking; ImagingResample, 8 bits per channel:
+ * 22-bit fixed-point coefficients, horizontal pass into a uint8 intermediate, then the vertical pass).
+ * Replaces transforms.functional.resize(img, image_size) at volleyball.py:239 / collective.py:183.
+ * tmp: n * h * ow * 3 bytes of device scratch, needed only when both axes change (NULL otherwise).  h == oh && w == ow: a copy.
+ */
+DIN_API int din_resize_bilinear_u8(const uint8_t* src, int n, int h, int w, uint8_t* dst, int oh, int ow, uint8_t* tmp,
+                                   void* stream);
+
+/* The nvJPEG backend in use (nvjpegBackend_t: 3 = hardware engine, 2 = GPU-assisted Huffman, 0 / 1 = hybrid with CPU
+ * Huffman), -1 before the first decode.  DIN_NVJPEG_BACKEND forces one; unset: the first of 3, 2, 0 that initialises. */
+DIN_API int din_jpeg_backend(void);
+
+/* Height / width of a JPEG stream in host memory (nvjpegGetImageInfo). */
+DIN_API int din_jpeg_image_info(const unsigned char* jpeg, size_t nbytes, int* h, int* w);
+
+/*
+ * n JPEG files held in HOST memory -> frames [n, out_h, out_w, 3] uint8 on the device: nvJPEG batched decode (library
+ * code, resolved with dlopen at the first call; DIN_ERR_UNSUPPORTED when libnvjpeg.so.12 is absent) followed by
+ * din_resize_bilinear_u8 for the frames whose size differs from the target; frames already at the target size are decoded
+ * straight into `frames`.  The result is what the uint8 stems ingest (din_stem_conv_nhwc_u8, x_is_u8 of
+ * din_conv3x3_stem_pair_nhwc_f16).  Replaces Image.open + resize + np.array of volleyball.py:237-240 / collective.py:181-184.
+ * workspace: device scratch for the frames that need resizing: sum over those frames of
+ *            align256(h * w * 3) + align256(h * out_w * 3) bytes (din_jpeg_image_info gives h, w); may be NULL if none does.
+ * cpu_threads: host threads nvJPEG may use for the Huffman stage of its hybrid backend.
+ */
+DIN_API int din_jpeg_decode_resize_u8(const unsigned char* const* jpeg, const size_t* nbytes, int n, uint8_t* frames,
+                                      int out_h, int out_w, uint8_t* workspace, size_t workspace_bytes, int cpu_threads,
+                                      void* stream);
+
 /* ---- backward of the backbone (second slice: VGG-16) ------------------------- */
 
 /*

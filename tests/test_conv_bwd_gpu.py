@@ -448,3 +448,37 @@ def test_general_dgrad_filters(cuda):
         ref = x.grad.permute(0, 2, 3, 1)
         assert dx.shape == ref.shape
         assert (dx.float() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item(), (cin, cout, k)
+
+
+@pytest.mark.parametrize("shape", [(64, 32, 3, 3), (128, 64, 1, 1), (64, 3, 7, 7), (192, 160, 1, 7)], ids=str)
+def test_bn_fold_grads_matches_autograd(cuda, shape):
+    """din_bn_fold_grads_f32 + din_scale_rows_f32 in isolation: conv -> eval-mode BatchNorm, gradients of the conv weight
+    and of gamma from the gradient of the FOLDED weight, vs fp32 autograd (non-trivial running statistics, small gammas)."""
+    from din_b200 import ops
+    co, ci, kh, kw = shape
+    g = torch.Generator().manual_seed(co + kw)
+    x = torch.randn(2, ci, 9, 11, generator=g).to(cuda)
+    w = (torch.randn(co, ci, kh, kw, generator=g) * 0.1).to(cuda).requires_grad_(True)
+    gamma = (torch.rand(co, generator=g) * 1.5 + 1e-3).to(cuda).requires_grad_(True)     # down to ~1e-3: no division by gamma
+    beta = torch.randn(co, generator=g).to(cuda).requires_grad_(True)
+    mean, var = torch.randn(co, generator=g).to(cuda), (torch.rand(co, generator=g) + 0.5).to(cuda)
+    eps = 1e-3
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    y = F.batch_norm(F.conv2d(x, w, padding=(kh // 2, kw // 2)), mean, var, gamma, beta, False, 0.0, eps)
+    dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(2)).to(cuda)
+    y.backward(dy)
+    # what the CUDA path has: gradients of the folded convolution z = conv(x, scale * w) + shift
+    scale = (gamma / torch.sqrt(var + eps)).detach()
+    wf = (w.detach() * scale.view(-1, 1, 1, 1)).requires_grad_(True)
+    shift = (beta.detach() - mean * scale).requires_grad_(True)
+    (F.conv2d(x, wf, padding=(kh // 2, kw // 2)) + shift.view(1, -1, 1, 1)).backward(dy)
+    torch.backends.cudnn.allow_tf32 = old_tf32
+    dwf, dbeta = wf.grad.contiguous(), shift.grad.contiguous()
+    dgamma = torch.zeros(co, device=cuda)
+    ops.bn_fold_grads(w.detach().contiguous(), dwf, dbeta, mean, var, dgamma, eps=eps)
+    dw = ops.scale_rows(dwf.clone(), scale.contiguous())
+    torch.cuda.synchronize()
+    assert (dgamma - gamma.grad).abs().max().item() <= 2e-5 * gamma.grad.abs().max().item()
+    assert (dw - w.grad).abs().max().item() <= 2e-5 * w.grad.abs().max().item()
+    assert (dbeta - beta.grad).abs().max().item() <= 2e-5 * beta.grad.abs().max().item()

@@ -208,18 +208,20 @@ def test_stage1_training_step(cuda):
     assert all(q.grad is None for n, q in model.named_parameters() if n.startswith("backbone."))
 
 
-def test_stage1_training_step_resnet18(cuda):
-    """Basenet_volleyball with the ResNet-18 backbone (T = 1), BatchNorm in eval mode (cfg.set_bn_eval, train_net.py:83-84):
-    every gradient vs autograd over the oracle; BatchNorm on batch statistics is refused in stage 1."""
+@pytest.mark.parametrize("backbone", ["res18", "inv3"])
+def test_stage1_training_step_resnet18(cuda, backbone):
+    """Basenet_volleyball with the ResNet-18 / Inception-v3 backbone (T = 1), BatchNorm in eval mode (cfg.set_bn_eval,
+    train_net.py:83-84): every gradient vs autograd over the oracle; BatchNorm on batch statistics is refused in stage 1."""
     import base_model as BM
     import din_oracle as O
     from din_b200 import metrics
-    pc = _pc("res18", (96, 160), num_frames=1, num_boxes=4)
+    pc = _pc("res18", (96, 160), num_frames=1, num_boxes=4) if backbone == "res18" else \
+        _pc("inv3", (139, 203), emb_features=1056, num_frames=1, num_boxes=4)
     bb = O.build_backbone(pc.backbone)
     sd = O.make_basenet_state_dict(pc, seed=3, backbone=bb)
     # random-init ResNet-18 with identity BatchNorm statistics and no LayerNorm after it yields logits of +-250 (a
     # saturated softmax: an ill-conditioned gradient test); scale the embedding down to logits of a few units
-    sd["fc_emb.weight"] = sd["fc_emb.weight"] * 0.02
+    sd["fc_emb.weight"] = sd["fc_emb.weight"] * (0.02 if backbone == "res18" else 0.1)
     O.load_backbone(bb, sd)
     bb.eval()
     B = 3
@@ -250,7 +252,8 @@ def test_stage1_training_step_resnet18(cuda):
         a, b = a.detach().double().cpu().flatten(), b.detach().double().cpu().flatten()
         return float((a - b).norm() / max(float(b.norm()), 1e-30))
     worst = max(rel_l2(got[k], ref_grads[k]) for k in ref_grads)
-    print(f"\n[stage1 res18] loss {loss.item():.5f} vs {ref_loss.item():.5f}; worst rel-L2 {worst:.2e}")
+    print(f"\n[stage1 {backbone}] loss {loss.item():.5f} vs {ref_loss.item():.5f}; worst rel-L2 {worst:.2e}; "
+          f"max|logit| {activities.abs().max().item():.2f}")
     assert abs(loss.item() - ref_loss.item()) <= 2e-3 * max(1.0, abs(ref_loss.item()))
     assert worst <= 2e-1, worst
     assert rel_l2(got["fc_actions.weight"], ref_grads["fc_actions.weight"]) <= 1e-2
