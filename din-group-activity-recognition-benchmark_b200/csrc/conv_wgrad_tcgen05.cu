@@ -21,6 +21,8 @@
 // Work unit = (128 output channels, NCI input channels, filter row ky); the pixel tiles of a unit are split over
 // several CTAs so that the grid fills the 148 SMs about twice; each CTA finishes with fp32 vector atomics into dW
 // (scaled by 1/loss-scale).  One producer warp, one MMA warp (a single elected lane issues), four epilogue warps.
+#include <cstdlib>
+
 #include "din_common.cuh"
 
 namespace {
@@ -191,6 +193,145 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2, M = 256) for c_out > 128 and c_in % 128 == 0.  ncu on the one-CTA kernel: 78 % tensor
+// pipe, because a 128 x 128 x 16 MMA with two MN-major operands reads 8 KB of shared memory in its 64 cycles -- the whole
+// 128 B/clk of the SM's shared-memory pipe -- while TMA writes the next stage into the same memory.  Here the two CTAs of
+// a cluster take the two 128-channel halves of a 256-channel dZ block (M = 256) against the SAME input halo: each CTA
+// stages only ITS 64 of the 128 input channels (B is split along N across the pair), so per MMA a CTA reads 4 + 2 KB, and
+// per pixel tile it loads 52 KB instead of 72 KB.  Both CTAs run the producer for their own boxes (completion bytes land
+// on the leader's barrier), the leader's MMA warp issues, tcgen05.commit multicasts to both CTAs' barriers, every CTA
+// drains its own 128 TMEM lanes (= its output channels, all NCI x KW columns).
+// ------------------------------------------------------------------------------------------------------------------
+template <int KW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWgThreads, 1)
+conv_wgrad_2cta_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_constant__ CUtensorMap tmap_x,
+                       const WgradParams p, const int n_stages) {
+  constexpr int NCI = 128;
+  constexpr int kWgBBytes = wg_b_bytes(KW);               // this CTA's 64 input channels of the halo rows
+  constexpr int kPitchBytes = (8 + KW - 1) * 128;
+  constexpr int kStageBytes = 2 * kWgABytes + kWgBBytes;
+  constexpr int kTmemCols = (KW * NCI <= 128) ? 128 : (KW * NCI <= 256) ? 256 : 512;
+  static_assert(KW * NCI <= 512, "accumulators exceed TMEM");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem(smem_raw, 1024);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + n_stages * kStageBytes);
+  uint64_t* full = bars;                                  // used in the leader CTA only
+  uint64_t* empty = full + kWgMaxStages;
+  uint64_t* acc_full = empty + kWgMaxStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int pair = blockIdx.x >> 1;
+  const int unit = pair / p.splits;
+  const int split = pair - unit * p.splits;
+  const int ky = unit % p.kh;
+  const int blk = unit / p.kh;
+  const int ci0 = (blk % p.n_ci_blk) * NCI;
+  const int co0 = (blk / p.n_ci_blk) * 256 + rank * 128;  // this CTA's 128 output channels
+  const int t_begin = split * p.tiles_per_split;
+  const int t_end = min(p.num_tiles, t_begin + p.tiles_per_split);
+  if (t_begin >= t_end) return;                           // uniform over the pair
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_dz);
+    tma_prefetch_desc(&tmap_x);
+    for (int s = 0; s < n_stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2cta<kTmemCols>(tmem_ptr_smem);
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();                                     // the peer's barriers exist before anything signals them
+  tc_fence_after_sync();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        const int img = tile / p.tiles_per_img;
+        const int r = tile - img * p.tiles_per_img;
+        const int tyi = r / p.tiles_x, txi = r - tyi * p.tiles_x;
+        const int x0 = txi * 8, y0 = tyi * 16;
+        mbar_wait(&empty[stage], phase ^ 1u);             // own barrier: the leader's commit is multicast to both CTAs
+        uint8_t* sa = smem + stage * kStageBytes;
+        uint8_t* sb = sa + 2 * kWgABytes;
+        if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2u * static_cast<uint32_t>(kStageBytes));
+        tma_load_4d_2cta(sa, &tmap_dz, &full[stage], co0, x0, y0, img);
+        tma_load_4d_2cta(sa + kWgABytes, &tmap_dz, &full[stage], co0 + 64, x0, y0, img);
+        tma_load_4d_2cta(sb, &tmap_x, &full[stage], ci0 + rank * 64, x0 - p.pad_w, y0 + ky - p.pad_h, img);
+        if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      const bool leader = elect_one();
+      constexpr uint32_t idesc = idesc_f16_f32_mn(256, NCI);
+      const uint32_t smem0 = smem_u32(smem);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t accum = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after_sync();
+        const uint32_t sa = smem0 + stage * kStageBytes;
+        const uint32_t sb = sa + 2 * kWgABytes;
+        if (leader) {
+#pragma unroll
+          for (int kx = 0; kx < KW; ++kx) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint64_t ad = desc_mn_sw128(sa + ks * 2048, kWgABytes, 1024);
+              const uint64_t bd = desc_mn_sw128(sb + kx * 128 + ks * 2 * kPitchBytes, kWgBBytes, kPitchBytes);
+              umma_f16_ss_2cta(tmem_base + kx * NCI, ad, bd, idesc, ks == 0 ? accum : 1u);
+            }
+          }
+          umma_commit_2cta(&empty[stage]);
+        }
+        accum = 1;
+        if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+      }
+      if (leader) umma_commit_2cta(acc_full);
+    }
+  } else {
+    const int q = warp & 3;
+    mbar_wait(acc_full, 0);
+    tc_fence_after_sync();
+    const float scl = p.inv_scale ? __ldg(p.inv_scale) : 1.0f;
+    const int co = co0 + q * 32 + lane;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+    for (int kx = 0; kx < KW; ++kx) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < NCI; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + kx * NCI + c0, v);
+        tmem_ld_wait();
+        if (co < p.c_out) {
+          float* dst = p.dw + ((static_cast<size_t>(co) * p.kh + ky) * p.kw + kx) * p.c_in + ci0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            atomicAdd(reinterpret_cast<float4*>(dst + j),
+                      make_float4(__uint_as_float(v[j]) * scl, __uint_as_float(v[j + 1]) * scl,
+                                  __uint_as_float(v[j + 2]) * scl, __uint_as_float(v[j + 3]) * scl));
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();                                     // nobody leaves while the peer may still signal it
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc_2cta<kTmemCols>(tmem_base);
+  }
+}
+
 // db[c] += inv_scale * sum over pixels of dz[p][c]     (bias gradient; fp16 in, fp32 atomics out)
 __global__ void __launch_bounds__(256)
 colsum_f16_kernel(const __half* __restrict__ dz, float* __restrict__ db, long long rows, int c, int c_stride,
@@ -239,6 +380,18 @@ int launch_wgrad(const CUtensorMap& tdz, const CUtensorMap& tx, const WgradParam
   return DIN_OK;
 }
 
+template <int KW>
+int launch_wgrad_2cta(const CUtensorMap& tdz, const CUtensorMap& tx, const WgradParams& p, int grid, cudaStream_t st) {
+  constexpr int kStageBytes = 2 * kWgABytes + wg_b_bytes(KW);
+  int n_stages = (216 * 1024) / kStageBytes;
+  if (n_stages > 4) n_stages = 4;
+  const size_t smem = static_cast<size_t>(n_stages) * kStageBytes + 1024 + (2 * kWgMaxStages + 1) * 8 + 16;
+  DIN_OPT_IN_SMEM((conv_wgrad_2cta_kernel<KW>), smem);
+  conv_wgrad_2cta_kernel<KW><<<grid, kWgThreads, smem, st>>>(tdz, tx, p, n_stages);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
 }  // namespace
 
 extern "C" int din_conv2d_wgrad_nhwc_f16(const void* x, const void* dz, float* dw, float* dbias,
@@ -263,6 +416,12 @@ extern "C" int din_conv2d_wgrad_nhwc_f16(const void* x, const void* dz, float* d
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   const int nci = (c_in % 128 == 0 && kw <= 3) ? 128 : 64;        // kw * nci fp32 accumulator columns <= 512
+  // CTA pair (M = 256 output channels per MMA): see conv_wgrad_2cta_kernel.  DIN_WGRAD_2CTA=0 keeps the one-CTA kernel (A/B).
+  bool two_cta = nci == 128 && c_out > 128 && (kw == 1 || kw == 3);
+  {
+    const char* e = std::getenv("DIN_WGRAD_2CTA");
+    if (e && e[0] == '0') two_cta = false;
+  }
   WgradParams p{};
   p.c_in = c_in; p.c_out = c_out; p.kh = kh; p.kw = kw; p.pad_h = pad_h; p.pad_w = pad_w;
   p.tiles_x = (ow + 7) / 8;
@@ -271,8 +430,9 @@ extern "C" int din_conv2d_wgrad_nhwc_f16(const void* x, const void* dz, float* d
   DIN_CHECK_ARG(tiles < INT32_MAX, "din_conv2d_wgrad_nhwc_f16: too many tiles");
   p.num_tiles = static_cast<int>(tiles);
   p.n_ci_blk = (c_in + nci - 1) / nci;
-  const int units = ((c_out + 127) / 128) * p.n_ci_blk * kh;
-  int splits = (2 * sms + units - 1) / units;
+  const int co_blk = two_cta ? 256 : 128;
+  const int units = ((c_out + co_blk - 1) / co_blk) * p.n_ci_blk * kh;     // (pairs of) CTAs before the pixel split
+  int splits = ((two_cta ? sms : 2 * sms) + units - 1) / units;
   if (splits > p.num_tiles) splits = p.num_tiles;
   if (splits < 1) splits = 1;
   p.tiles_per_split = (p.num_tiles + splits - 1) / splits;
@@ -304,6 +464,9 @@ extern "C" int din_conv2d_wgrad_nhwc_f16(const void* x, const void* dz, float* d
   }
   const int grid = units * p.splits;
   int rc;
+  if (two_cta) {
+    rc = kw == 1 ? launch_wgrad_2cta<1>(tdz, tx, p, 2 * grid, st) : launch_wgrad_2cta<3>(tdz, tx, p, 2 * grid, st);
+  } else
   switch (kw) {
     case 1: rc = (nci == 128) ? launch_wgrad<128, 1>(tdz, tx, p, grid, st) : launch_wgrad<64, 1>(tdz, tx, p, grid, st); break;
     case 3: rc = (nci == 128) ? launch_wgrad<128, 3>(tdz, tx, p, grid, st) : launch_wgrad<64, 3>(tdz, tx, p, grid, st); break;
