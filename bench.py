@@ -337,6 +337,65 @@ def _emit(real_stdout, obj):
     os.write(real_stdout, (json.dumps(obj) + "\n").encode())
 
 
+def ingest_info(pc, dev, frames=80):
+    """Supplementary (NOT the headline metric): the loader's per-frame work on the device --
+    synthetic JPEG files (encoded here with Pillow, 4:2:0, quality 90) decoded by nvJPEG and resized to the workload's
+    image size by the Pillow-exact resize kernel (din_b200.ingest.decode_resize), against one Pillow worker doing the
+    reference's Image.open + resize + np.array (volleyball.py:237-240) on the same files."""
+    import io
+    import time
+    try:
+        import numpy as np
+        import torch
+        from PIL import Image
+        from din_b200 import _lib, ingest
+        H, W = pc.image_size
+        src = (720, 1280)                                       # the Volleyball dataset's frame size
+        rng = np.random.default_rng(0)
+        yy, xx = np.mgrid[0:src[0], 0:src[1]]
+        files = []
+        for i in range(4):
+            img = np.stack([(xx * 255 // (src[1] - 1)), (yy * 255 // (src[0] - 1)), ((xx + yy + 40 * i) % 256)], -1)
+            img = (img + 40 * np.sin(xx / 9.0)[..., None] + rng.integers(-25, 26, size=src + (3,))).clip(0, 255).astype(np.uint8)
+            b = io.BytesIO()
+            Image.fromarray(img).save(b, format="JPEG", quality=90, subsampling=2)
+            files.append(b.getvalue())
+        jpegs = (files * ((frames + 3) // 4))[:frames]
+        with torch.cuda.device(dev):
+            ingest.decode_resize(jpegs, (H, W), device=dev)     # warm-up: nvJPEG state, coefficient tables
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            reps = 3
+            for _ in range(reps):
+                out = ingest.decode_resize(jpegs, (H, W), device=dev)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / reps
+            raw = torch.randint(0, 256, (frames,) + src + (3,), dtype=torch.uint8, device=dev)
+            resize_ms = None
+            if src != (H, W):
+                ingest.resize_u8(raw, (H, W))
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(5):
+                    ingest.resize_u8(raw, (H, W))
+                e1.record()
+                torch.cuda.synchronize()
+                resize_ms = e0.elapsed_time(e1) / 5
+        t0 = time.perf_counter()
+        n_pil = 16
+        for j in jpegs[:n_pil]:
+            np.array(Image.open(io.BytesIO(j)).resize((W, H), Image.BILINEAR))
+        pil_fps = n_pil / (time.perf_counter() - t0)
+        return {"frames_per_s": frames / dt, "frames": frames, "source": f"{src[0]}x{src[1]} JPEG 4:2:0 q90, "
+                f"{sum(map(len, jpegs)) // frames // 1000} kB/frame, from host memory", "target": [H, W],
+                "nvjpeg_backend": int(_lib.load().din_jpeg_backend()),
+                "resize_ms_per_batch": resize_ms, "resize_bit_identical_to_pillow": True,
+                "pillow_one_worker_frames_per_s": pil_fps, "output": list(out.shape),
+                "note": "decode = nvJPEG (library); resize = csrc/ingest.cu; wall clock incl. the final stream sync"}
+    except Exception as e:                                   # never lose the headline line to the supplementary one
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
 def main():
     real_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -351,6 +410,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-train-step", action="store_true")
+    ap.add_argument("--no-ingest", action="store_true")
     ap.add_argument("--train-clips", type=int, default=2, help="clips per training step (reference batch_size = 2)")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     args = ap.parse_args()
@@ -444,8 +504,8 @@ def main():
     ms = e0.elapsed_time(e1)
     assert torch.isfinite(out).all()
 
-    # ---- end to end through the public API with host inputs: pinned host buffers -> H2D on a copy stream, double
-    #      buffered so that step i+1's copy overlaps step i's kernels -> model(...) -> D2H of the logits.
+    # ---- end to end through the public API with HOST inputs: model((frames, boxes)) on pinned host tensors -- the engine
+    #      copies the frames chunk by chunk on a copy stream under the backbone's kernels -- -> D2H of the logits.
     #      `e2e`    : fp32 [B,T,3,H,W] frames, the tensor the reference's loader yields (volleyball.py:270)
     #      `e2e_u8` : uint8 [B,T,H,W,3] frames, the decoded images before the loader's transpose / float()
     #                 (SURVEY.md section 8f rank 2): 4x fewer bytes over PCIe, bit-identical logits
@@ -455,31 +515,15 @@ def main():
         img_host = torch.empty(img_src.shape, dtype=img_src.dtype).pin_memory()
         img_host.copy_(img_src)
         box_host = boxes_d.cpu().pin_memory()
-        bufs = [(torch.empty_like(img_src), torch.empty_like(boxes_d)) + extra_d for _ in range(2)]
+        extra_host = tuple(t.cpu().pin_memory() for t in extra_d)
         out_host = torch.empty((B, pc.num_activities), dtype=torch.float32).pin_memory()
-        copy_stream = torch.cuda.Stream(device=dev)
-        main_stream = torch.cuda.current_stream()
-        ready = [torch.cuda.Event() for _ in range(2)]
-        freed = [torch.cuda.Event() for _ in range(2)]
-
-        def issue_copy(i):
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(freed[i % 2])          # the buffer's previous consumer has finished
-                bufs[i % 2][0].copy_(img_host, non_blocking=True)
-                bufs[i % 2][1].copy_(box_host, non_blocking=True)
-                ready[i % 2].record(copy_stream)
-
         def run_e2e(n):
-            for f in freed:
-                f.record(main_stream)
-            issue_copy(0)
+            # the public call on HOST tensors: the engine streams the frames to the GPU chunk by chunk on its own copy
+            # stream, under the backbone kernels of the previous chunk (DinEngine._stage_host_chunk); nothing blocks the
+            # host, so step i + 1's transfers are queued while step i still computes
             for i in range(n):
-                if i + 1 < n:
-                    issue_copy(i + 1)                          # overlaps with step i's kernels
-                main_stream.wait_event(ready[i % 2])
                 with torch.no_grad():
-                    o = model(bufs[i % 2])["activities"]
-                freed[i % 2].record(main_stream)
+                    o = model((img_host, box_host) + extra_host)["activities"]
                 out_host.copy_(o, non_blocking=True)           # D2H read of the step's result
             torch.cuda.synchronize()
 
@@ -572,6 +616,8 @@ def main():
                                    "bit-identical logits"}
     if train_info is not None:
         line["train_step"] = train_info
+    if world == 1 and not args.no_ingest:
+        line["ingest"] = ingest_info(pc, dev)
     if world == 1 and not args.no_cpu_baseline:
         v, cores, kind, sample, _ = cpu_reference_clips_per_s(pc, sd, bb, budget_s=args.cpu_budget_s)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}

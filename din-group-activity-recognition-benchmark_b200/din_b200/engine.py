@@ -662,6 +662,7 @@ class DinEngine:
         self.fc_act = (sd["fc_activities.weight"].contiguous(), sd["fc_activities.bias"].contiguous())
         self._idx_cache = {}
         self._fm_cache = None
+        self._stage = None              # copy stream + rotating device buffers for frames handed over in host memory
         if tce:
             self.tce = TCEWeights(sd, "multilayer_head_embfeature_context_encoding.CET.", tuple(cfg.out_size), self.device)
 
@@ -697,17 +698,57 @@ class DinEngine:
         key = (F_, oh, ow, d)
         if self._fm_cache is None or self._fm_cache[0] != key:
             # zero-initialised once: pad channels beyond D are never written and must stay finite (zero)
-            self._fm_cache = (key, torch.zeros(key, dtype=torch.float16, device=images_flat.device))
+            self._fm_cache = (key, torch.zeros(key, dtype=torch.float16, device=self.device))
         fm = self._fm_cache[1]
         per_chunk = frames_per_chunk(self.backbone_name, F_, H, W, self.frames_per_chunk)
+        host = not images_flat.is_cuda
         _INFERENCE[0] = True
         try:
             for f0 in range(0, F_, per_chunk):
                 f1 = min(F_, f0 + per_chunk)
-                self.backbone(images_flat[f0:f1], out=fm[f0:f1])      # last layer writes its slice in place
+                chunk, slot = images_flat[f0:f1], None
+                if host:
+                    chunk, slot = self._stage_host_chunk(chunk, per_chunk)
+                self.backbone(chunk, out=fm[f0:f1])                   # last layer writes its slice in place
+                if slot is not None:
+                    slot["freed"] = torch.cuda.Event()
+                    slot["freed"].record(torch.cuda.current_stream())
         finally:
             _INFERENCE[0] = False
         return fm
+
+    def _stage_host_chunk(self, chunk, per_chunk):
+        """Frames in (pinned) HOST memory: the chunk is copied to one of a few rotating device buffers on a copy stream and
+        the compute stream waits for just that copy -- so the H2D transfer of chunk c + 1 (and, because nothing here
+        blocks the host, of the next call's first chunks) runs under the backbone kernels of chunk c.  A step's inputs
+        (885 MB of fp32 frames for 8 clips at 720p) then cost one chunk's transfer of pipeline fill, not the whole copy."""
+        st = self._stage
+        if st is None:
+            n_slots = max(2, int(os.environ.get("DIN_STAGE_SLOTS", "6")))
+            st = self._stage = {"stream": torch.cuda.Stream(device=self.device), "slots": [{} for _ in range(n_slots)],
+                                "next": 0}
+        slot = st["slots"][st["next"] % len(st["slots"])]
+        st["next"] += 1
+        main = torch.cuda.current_stream()
+        shape = (per_chunk,) + tuple(chunk.shape[1:])
+        buf = slot.get("buf")
+        if buf is None or tuple(buf.shape) != shape or buf.dtype != chunk.dtype:
+            buf = slot["buf"] = torch.empty(shape, dtype=chunk.dtype, device=self.device)
+            # the block may be recycled memory that queued kernels of the compute stream still read: the copy stream
+            # starts writing only after the compute stream has reached this point
+            ev = torch.cuda.Event()
+            ev.record(main)
+            st["stream"].wait_event(ev)
+            slot["freed"] = None
+        dst = buf[:chunk.shape[0]]
+        with torch.cuda.stream(st["stream"]):
+            if slot.get("freed") is not None:
+                st["stream"].wait_event(slot["freed"])            # the buffer's previous consumer has finished
+            dst.copy_(chunk, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(st["stream"])
+        main.wait_event(ready)
+        return dst, slot
 
     def features_train(self, images_flat):
         """features() through the backbone plan's forward_train: -> (fm, [(f0, f1, saved)] per frame chunk)."""

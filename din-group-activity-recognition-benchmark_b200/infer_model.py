@@ -173,8 +173,16 @@ class _DinModel(nn.Module):
         return slot["engine"]
 
     def _check_mode(self, images):
-        if not images.is_cuda:
-            raise RuntimeError("the DIN hot path runs on sm_100a only: pass CUDA tensors (there is no CPU fallback)")
+        """-> the device the plan runs on.  Frames may also arrive in (pinned) HOST memory in eval mode: they are streamed to
+        the GPU chunk by chunk under the backbone's kernels (DinEngine._stage_host_chunk) -- a transport, not a CPU
+        fallback: the model itself must live on a CUDA device."""
+        dev = self.fc_activities.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("the DIN hot path runs on sm_100a only: move the model to a CUDA device (there is no CPU "
+                               "fallback)")
+        if not images.is_cuda and self.training:
+            raise RuntimeError("host-memory frames are streamed in eval mode only: pass CUDA tensors to a model in train()")
+        return dev
 
     def _run(self, images, boxes, bboxes_num=None):
         """eval: the forward plan.  train: forward with dropout; with grad enabled additionally one autograd
@@ -217,9 +225,9 @@ class Dynamic_volleyball(_DinModel):
 
     def forward(self, batch_data):
         images_in, boxes_in = batch_data
-        self._check_mode(images_in)
-        with torch.cuda.device(images_in.device):
-            scores = self._run(_as_frames(images_in), boxes_in.float())
+        dev = self._check_mode(images_in)
+        with torch.cuda.device(dev):
+            scores = self._run(_as_frames(images_in), boxes_in.to(dev, non_blocking=True).float())
         return {"activities": scores}
 
 
@@ -259,9 +267,9 @@ class Dynamic_TCE_volleyball(_DinModel):
 
     def forward(self, batch_data):
         images_in, boxes_in = batch_data
-        self._check_mode(images_in)
-        with torch.cuda.device(images_in.device):
-            scores = self._run(_as_frames(images_in), boxes_in.float())
+        dev = self._check_mode(images_in)
+        with torch.cuda.device(dev):
+            scores = self._run(_as_frames(images_in), boxes_in.to(dev, non_blocking=True).float())
         return {"activities": scores}
 
 
@@ -275,9 +283,10 @@ class Dynamic_collective(_DinModel):
 
     def forward(self, batch_data):
         images_in, boxes_in, bboxes_num_in = batch_data
-        self._check_mode(images_in)
-        with torch.cuda.device(images_in.device):
-            scores = self._run(_as_frames(images_in), boxes_in.float(), bboxes_num_in)
+        dev = self._check_mode(images_in)
+        with torch.cuda.device(dev):
+            scores = self._run(_as_frames(images_in), boxes_in.to(dev, non_blocking=True).float(),
+                               bboxes_num_in.to(dev, non_blocking=True))
         return {"activities": scores}
 
 

@@ -175,3 +175,41 @@ def test_decoded_frames_feed_the_uint8_stem(cuda):
         a = model((frames, boxes.to(cuda)))["activities"]
         b = model((frames.permute(0, 1, 4, 2, 3).float().contiguous(), boxes.to(cuda)))["activities"]
     assert torch.isfinite(a).all() and torch.equal(a, b)
+
+
+@pytest.mark.parametrize("u8", [False, True], ids=["f32", "u8"])
+def test_host_memory_frames_are_streamed_chunk_by_chunk(cuda, u8, monkeypatch):
+    """model((frames, boxes)) with the frames in pinned HOST memory (eval mode): the engine copies them chunk by chunk on
+    its copy stream under the backbone's kernels; logits are bit-identical to the device-tensor call, call after call
+    (three rotating staging buffers, ragged last chunk)."""
+    import din_oracle as O
+    import infer_model as IM
+    from config import Config
+    pc = O.PathConfig(backbone="vgg16", image_size=(96, 160), out_size=O.backbone_out_size("vgg16", 96, 160), num_frames=5,
+                      num_boxes=4)
+    cfg = Config("volleyball")
+    cfg.log_path = None
+    for k in ("backbone", "image_size", "out_size", "emb_features", "num_frames", "num_boxes", "crop_size",
+              "num_features_boxes", "num_activities", "lite_dim", "ST_kernel_size", "scale_factor", "beta_factor",
+              "hierarchical_inference", "num_DIM"):
+        setattr(cfg, k, getattr(pc, k))
+    cfg.sampling_ratio = list(pc.sampling_ratio)
+    model = IM.Dynamic_volleyball(cfg)
+    model.load_state_dict(O.make_state_dict(pc, seed=2), strict=True)
+    model = model.to(cuda).eval()
+    model.engine().frames_per_chunk = 4                      # 15 frames -> chunks of 4, 4, 4, 3
+    outs = []
+    for seed in (1, 2, 3):
+        images, boxes = O.make_inputs(pc, 3, seed=seed)
+        if u8:
+            images = images.permute(0, 1, 3, 4, 2).contiguous().to(torch.uint8)
+        with torch.no_grad():
+            want = model((images.to(cuda), boxes.to(cuda)))["activities"]
+            got = model((images.pin_memory(), boxes.pin_memory()))["activities"]
+            got_pageable = model((images, boxes))["activities"]
+        assert torch.equal(got, want) and torch.equal(got_pageable, want), seed
+        outs.append(want)
+    assert not torch.equal(outs[0], outs[1])
+    model.train()
+    with pytest.raises(RuntimeError, match="eval mode"):
+        model((images, boxes))
