@@ -198,7 +198,6 @@ def train_step_info(model, pc, dev, images_d, boxes_d, clips, steps=5, warmup=2,
         if dist is not None:
             dist.barrier()
             torch.cuda.synchronize()
-        ops.RECORDER = []
         launches0 = ops.LAUNCHES
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -206,8 +205,15 @@ def train_step_info(model, pc, dev, images_d, boxes_d, clips, steps=5, warmup=2,
             loss = step()
         e1.record()
         torch.cuda.synchronize()
-        rec, ops.RECORDER = ops.RECORDER, None
+        launches_per_step = (ops.LAUNCHES - launches0) // steps
         ms = e0.elapsed_time(e1) / steps
+        # the kernel breakdown comes from a SEPARATE, untimed pass: two CUDA events per launch cost ~0.15 ms of host time,
+        # which made the 582-launch Inception-v3 step look host-bound at 121 ms (it is 32 ms)
+        ops.RECORDER = []
+        for _ in range(steps):
+            step()
+        torch.cuda.synchronize()
+        rec, ops.RECORDER = ops.RECORDER, None
         world = 1
         if dist is not None:
             world = dist.get_world_size()
@@ -226,7 +232,7 @@ def train_step_info(model, pc, dev, images_d, boxes_d, clips, steps=5, warmup=2,
                 "allreduce": (None if reducer is None else
                               {"elements": reducer.numel, "bytes_per_step": reducer.stats["bytes"] // max(1, reducer.stats["steps"]),
                                "buckets": ["head (overlaps the backbone's backward)", "backbone"]}),
-                "backbone_trained": True, "gpu_launches_per_step": (ops.LAUNCHES - launches0) // steps,
+                "backbone_trained": True, "gpu_launches_per_step": launches_per_step,
                 "algorithmic_tflops_per_gpu": flops / (ms / 1e3) / 1e12,
                 "kernels_ms": {k: round(v, 3) for k, v in sorted(by.items(), key=lambda kv: -kv[1])[:10]},
                 "note": "forward(train) + cross-entropy + backward + SGD(lr=0) step (weights re-packed every step)"}

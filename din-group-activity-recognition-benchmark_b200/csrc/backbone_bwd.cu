@@ -154,6 +154,63 @@ relu_pool_bwd_kernel(const __half* __restrict__ y, const __half* __restrict__ dy
   reinterpret_cast<uint4*>(dz)[idx] = out;
 }
 
+// The pooled case, one thread per (2x2 window, 8 channels): the four activations of a window are loaded ONCE (the
+// pixel-per-thread form above loads them in each of the window's four threads: 6 loads per output vector, L1-bound at
+// 3.2 TB/s of algorithmic traffic), the first maximum in scan order (torch's max_pool2d index rule) takes the pooled
+// gradient if it is positive.  Windows run over ceil(h/2) x ceil(w/2): the odd last row / column lies outside every
+// pooling window and receives zeros.  Same values as relu_pool_bwd_kernel, bit for bit.
+__global__ void __launch_bounds__(256)
+relu_pool2_bwd_window_kernel(const __half* __restrict__ y, const __half* __restrict__ dy, __half* __restrict__ dz, int n, int h,
+                             int w, int c8) {
+  const int wh = (h + 1) >> 1, ww = (w + 1) >> 1, ph = h >> 1, pw = w >> 1;
+  const long long total = static_cast<long long>(n) * wh * ww * c8;
+  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int oc = static_cast<int>(idx % c8);
+  long long t = idx / c8;
+  const int px = static_cast<int>(t % ww);
+  t /= ww;
+  const int py = static_cast<int>(t % wh);
+  const int img = static_cast<int>(t / wh);
+  const uint4* y4 = reinterpret_cast<const uint4*>(y);
+  uint4* dz4 = reinterpret_cast<uint4*>(dz);
+  const long long base = ((static_cast<long long>(img) * h + 2 * py) * w + 2 * px) * c8 + oc;
+  const bool col1 = 2 * px + 1 < w, row1 = 2 * py + 1 < h;
+  if (py >= ph || px >= pw) {                                  // outside every pooling window
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    dz4[base] = z;
+    if (col1) dz4[base + c8] = z;
+    if (row1) dz4[base + static_cast<long long>(w) * c8] = z;
+    return;
+  }
+  const long long off[4] = {0, c8, static_cast<long long>(w) * c8, static_cast<long long>(w) * c8 + c8};
+  uint4 win[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) win[q] = __ldg(y4 + base + off[q]);
+  const uint4 g = __ldg(reinterpret_cast<const uint4*>(dy) + ((static_cast<long long>(img) * ph + py) * pw + px) * c8 + oc);
+  const __half2* hg = reinterpret_cast<const __half2*>(&g);
+  const __half2 zero = __float2half2_rn(0.0f);
+  uint4 out[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    __half2* ho = reinterpret_cast<__half2*>(&out[q]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __half2 me = reinterpret_cast<const __half2*>(&win[q])[e];
+      __half2 sel = __hgt2(me, zero);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const __half2 o = reinterpret_cast<const __half2*>(&win[r])[e];
+        if (r < q) sel = __hmul2(sel, __hgt2(me, o));        // strictly greater than every earlier value
+        else if (r > q) sel = __hmul2(sel, __hge2(me, o));   // >= every later one: the first maximum wins
+      }
+      ho[e] = __hmul2(hg[e], sel);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) dz4[base + off[q]] = out[q];
+}
+
 // ================================================================================================
 // Stem weight / bias gradient (3 input channels, 3x3 stride 1):
 //   dW[co][c][ky][kx] += inv_scale * sum_pixels dz[p][co] * prep(x)[c][p + tap],   db[co] += inv_scale * sum dz
@@ -593,6 +650,16 @@ extern "C" int din_relu_pool_bwd_nhwc_f16(const void* y, const void* dy, void* d
                 "din_relu_pool_bwd_nhwc_f16: pointers must be 16-byte aligned");
   const long long total = static_cast<long long>(n) * h * w * (c / 8);
   DIN_CHECK_ARG((total + 255) / 256 <= INT32_MAX, "din_relu_pool_bwd_nhwc_f16: too large");
+  {
+    const char* e = std::getenv("DIN_RELU_POOL_PIXEL");       // =1: the pixel-per-thread kernel for pooled layers too (A/B)
+    if (pool && !(e && e[0] == '1')) {
+      const long long wins = static_cast<long long>(n) * ((h + 1) / 2) * ((w + 1) / 2) * (c / 8);
+      relu_pool2_bwd_window_kernel<<<static_cast<int>((wins + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+          static_cast<const __half*>(y), static_cast<const __half*>(dy), static_cast<__half*>(dz), n, h, w, c / 8);
+      DIN_CHECK_CUDA(cudaGetLastError());
+      return DIN_OK;
+    }
+  }
   relu_pool_bwd_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(y), static_cast<const __half*>(dy), static_cast<__half*>(dz), n, h, w, c, pool);
   DIN_CHECK_CUDA(cudaGetLastError());

@@ -663,6 +663,7 @@ class DinEngine:
         self._idx_cache = {}
         self._fm_cache = None
         self._stage = None              # copy stream + rotating device buffers for frames handed over in host memory
+        self._pending_small = None      # event of the boxes / actor counts staged on the copy stream (stage_small)
         if tce:
             self.tce = TCEWeights(sd, "multilayer_head_embfeature_context_encoding.CET.", tuple(cfg.out_size), self.device)
 
@@ -715,18 +716,41 @@ class DinEngine:
                     slot["freed"].record(torch.cuda.current_stream())
         finally:
             _INFERENCE[0] = False
+        if self._pending_small is not None:                          # boxes / actor counts staged by stage_small()
+            torch.cuda.current_stream().wait_event(self._pending_small)
+            self._pending_small = None
         return fm
+
+    def _stage_state(self):
+        if self._stage is None:
+            n_slots = max(2, int(os.environ.get("DIN_STAGE_SLOTS", "3")))
+            self._stage = {"stream": torch.cuda.Stream(device=self.device), "slots": [{} for _ in range(n_slots)], "next": 0}
+        return self._stage
+
+    def stage_small(self, *tensors):
+        """Small HOST tensors of a call (boxes, actor counts) -> device, on the copy stream and BEFORE the call's frames; the
+        compute stream waits for them only after the backbone (end of features()).  Issued on the compute stream instead, a
+        1 kB H2D copy queues behind the frame transfers in the copy engine and stalls the compute stream for up to a whole
+        chunk transfer: measured 3.3 ms of idle GPU per 36 ms step (tools/probes/e2e_probe.py)."""
+        st = self._stage_state()
+        main = torch.cuda.current_stream()
+        outs = []
+        with torch.cuda.stream(st["stream"]):
+            for t in tensors:
+                o = t.to(self.device, non_blocking=True)
+                o.record_stream(main)                                # allocated on the copy stream, consumed on `main`
+                outs.append(o)
+            ev = torch.cuda.Event()
+            ev.record(st["stream"])
+        self._pending_small = ev
+        return outs
 
     def _stage_host_chunk(self, chunk, per_chunk):
         """Frames in (pinned) HOST memory: the chunk is copied to one of a few rotating device buffers on a copy stream and
         the compute stream waits for just that copy -- so the H2D transfer of chunk c + 1 (and, because nothing here
         blocks the host, of the next call's first chunks) runs under the backbone kernels of chunk c.  A step's inputs
         (885 MB of fp32 frames for 8 clips at 720p) then cost one chunk's transfer of pipeline fill, not the whole copy."""
-        st = self._stage
-        if st is None:
-            n_slots = max(2, int(os.environ.get("DIN_STAGE_SLOTS", "6")))
-            st = self._stage = {"stream": torch.cuda.Stream(device=self.device), "slots": [{} for _ in range(n_slots)],
-                                "next": 0}
+        st = self._stage_state()
         slot = st["slots"][st["next"] % len(st["slots"])]
         st["next"] += 1
         main = torch.cuda.current_stream()

@@ -184,6 +184,13 @@ class _DinModel(nn.Module):
             raise RuntimeError("host-memory frames are streamed in eval mode only: pass CUDA tensors to a model in train()")
         return dev
 
+    def _to_device(self, dev, *small):
+        """Boxes / actor counts handed over in host memory: in eval mode they travel on the engine's copy stream ahead of
+        the frames (DinEngine.stage_small); in train mode a plain copy."""
+        if self.training:
+            return [t.to(dev) for t in small]
+        return self.engine().stage_small(*small)
+
     def _run(self, images, boxes, bboxes_num=None):
         """eval: the forward plan.  train: forward with dropout; with grad enabled additionally one autograd
         node whose backward is the CUDA head backward."""
@@ -227,7 +234,9 @@ class Dynamic_volleyball(_DinModel):
         images_in, boxes_in = batch_data
         dev = self._check_mode(images_in)
         with torch.cuda.device(dev):
-            scores = self._run(_as_frames(images_in), boxes_in.to(dev, non_blocking=True).float())
+            if not boxes_in.is_cuda:
+                boxes_in, = self._to_device(dev, boxes_in)
+            scores = self._run(_as_frames(images_in), boxes_in.float())
         return {"activities": scores}
 
 
@@ -269,7 +278,9 @@ class Dynamic_TCE_volleyball(_DinModel):
         images_in, boxes_in = batch_data
         dev = self._check_mode(images_in)
         with torch.cuda.device(dev):
-            scores = self._run(_as_frames(images_in), boxes_in.to(dev, non_blocking=True).float())
+            if not boxes_in.is_cuda:
+                boxes_in, = self._to_device(dev, boxes_in)
+            scores = self._run(_as_frames(images_in), boxes_in.float())
         return {"activities": scores}
 
 
@@ -285,8 +296,9 @@ class Dynamic_collective(_DinModel):
         images_in, boxes_in, bboxes_num_in = batch_data
         dev = self._check_mode(images_in)
         with torch.cuda.device(dev):
-            scores = self._run(_as_frames(images_in), boxes_in.to(dev, non_blocking=True).float(),
-                               bboxes_num_in.to(dev, non_blocking=True))
+            if not (boxes_in.is_cuda and bboxes_num_in.is_cuda):
+                boxes_in, bboxes_num_in = self._to_device(dev, boxes_in, bboxes_num_in)
+            scores = self._run(_as_frames(images_in), boxes_in.float(), bboxes_num_in)
         return {"activities": scores}
 
 

@@ -31,6 +31,24 @@ for name, args in (("device", (img_d, box_d)), ("host", (img_h, box_h))):
         torch.cuda.synchronize()
         print(f"{name}: device {e0.elapsed_time(e1) / 8:.2f} ms/step, host call {sum(host_ms) / 8:.2f} ms/step "
               f"(min {min(host_ms):.2f}, max {max(host_ms):.2f})")
+# which kernels slow down while the copies run?
+from din_b200 import ops
+per = {}
+for name, args in (("device", (img_d, box_d)), ("host", (img_h, box_h))):
+    with torch.no_grad():
+        model(args); torch.cuda.synchronize()
+        ops.RECORDER = []
+        for _ in range(4):
+            model(args)
+        torch.cuda.synchronize()
+        rec, ops.RECORDER = ops.RECORDER, None
+    d = {}
+    for (n, f, b, a, z) in rec:
+        d[n] = d.get(n, 0.0) + a.elapsed_time(z) / 4
+    per[name] = d
+for n in per["device"]:
+    print(f"{n:50s} device {per['device'][n]:7.3f}  host {per['host'].get(n, 0):7.3f}  x{per['host'].get(n, 0) / max(per['device'][n], 1e-9):.3f}")
+print("sum", sum(per["device"].values()), sum(per["host"].values()))
 # raw copy throughput: whole tensor vs 3 chunks on a side stream
 st = torch.cuda.Stream()
 flat = img_h.reshape((-1,) + tuple(img_h.shape[2:]))
