@@ -63,7 +63,11 @@ __host__ __device__ constexpr uint32_t idesc_f16_f32_mn(int m, int n) {
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-template <int NCI, int KW>
+// PAIR64 (c_out <= 64, KW = 3): the upper 64 rows of M, otherwise zero-filled, carry a second copy of the dZ tile shifted
+// by one pixel to the left: row 64 + co of the MMA for tap kx then accumulates sum_p dZ[p - 1, co] * X[p + kx] -- tap kx + 1
+// over the pixel set shifted by one.  Two MMA groups (kx = 0, 2) instead of three produce all three taps (and a discarded
+// "tap 3"); the pixel tiles run over ceil((ow + 1) / 8) columns so that the shifted windows cover every pixel once.
+template <int NCI, int KW, bool PAIR64 = false>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_constant__ CUtensorMap tmap_x,
                   const WgradParams p, const int n_stages) {
@@ -120,7 +124,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
         uint8_t* sb = sa + 2 * kWgABytes;
         mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(kStageBytes));
         tma_load_4d(sa, &tmap_dz, &full[stage], co0, x0, y0, img);
-        tma_load_4d(sa + kWgABytes, &tmap_dz, &full[stage], co0 + 64, x0, y0, img);   // beyond c_out: zero fill
+        if constexpr (PAIR64) tma_load_4d(sa + kWgABytes, &tmap_dz, &full[stage], co0, x0 - 1, y0, img);
+        else tma_load_4d(sa + kWgABytes, &tmap_dz, &full[stage], co0 + 64, x0, y0, img);   // beyond c_out: zero fill
 #pragma unroll
         for (int c = 0; c < NCI / 64; ++c)
           tma_load_4d(sb + c * kWgBBytes, &tmap_x, &full[stage], ci0 + c * 64, x0 - p.pad_w, y0 + ky - p.pad_h, img);
@@ -142,7 +147,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
       const uint32_t sb = sa + 2 * kWgABytes;
       if (leader) {
 #pragma unroll
-        for (int kx = 0; kx < KW; ++kx) {
+        for (int kx = 0; kx < KW; kx += (PAIR64 ? 2 : 1)) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {            // 16 pixels (two 8-pixel tile rows) per MMA
             const uint64_t ad = desc_mn_sw128(sa + ks * 2048, kWgABytes, 1024);
@@ -162,17 +167,19 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
     mbar_wait(acc_full, 0);
     tc_fence_after_sync();
     const float scl = p.inv_scale ? __ldg(p.inv_scale) : 1.0f;
-    const int co = co0 + q * 32 + lane;
+    // PAIR64: TMEM lanes 64..127 (quadrants 2, 3) hold tap kx + 1 of channel lane - 64
+    const int co = PAIR64 ? co0 + (q & 1) * 32 + lane : co0 + q * 32 + lane;
+    const int tap_shift = PAIR64 ? (q >> 1) : 0;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-    for (int kx = 0; kx < KW; ++kx) {
+    for (int kx = 0; kx < KW; kx += (PAIR64 ? 2 : 1)) {
 #pragma unroll 1
       for (int c0 = 0; c0 < NCI; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + kx * NCI + c0, v);
         tmem_ld_wait();
-        if (co < p.c_out) {
-          float* dst = p.dw + ((static_cast<size_t>(co) * p.kh + ky) * p.kw + kx) * p.c_in + ci0 + c0;
+        if (co < p.c_out && kx + tap_shift < KW) {
+          float* dst = p.dw + ((static_cast<size_t>(co) * p.kh + ky) * p.kw + kx + tap_shift) * p.c_in + ci0 + c0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             if (ci0 + c0 + j < p.c_in)                  // partial last channel block (c_in is a multiple of 8)
@@ -368,14 +375,14 @@ colsum_f16_kernel(const __half* __restrict__ dz, float* __restrict__ db, long lo
   }
 }
 
-template <int NCI, int KW>
+template <int NCI, int KW, bool PAIR64 = false>
 int launch_wgrad(const CUtensorMap& tdz, const CUtensorMap& tx, const WgradParams& p, int grid, cudaStream_t st) {
   constexpr int kStageBytes = 2 * kWgABytes + (NCI / 64) * wg_b_bytes(KW);
   int n_stages = (220 * 1024) / kStageBytes;
   if (n_stages > 4) n_stages = 4;
   const size_t smem = static_cast<size_t>(n_stages) * kStageBytes + 1024 + (2 * kWgMaxStages + 1) * 8 + 16;
-  DIN_OPT_IN_SMEM((conv_wgrad_kernel<NCI, KW>), smem);
-  conv_wgrad_kernel<NCI, KW><<<grid, kWgThreads, smem, st>>>(tdz, tx, p, n_stages);
+  DIN_OPT_IN_SMEM((conv_wgrad_kernel<NCI, KW, PAIR64>), smem);
+  conv_wgrad_kernel<NCI, KW, PAIR64><<<grid, kWgThreads, smem, st>>>(tdz, tx, p, n_stages);
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;
 }
@@ -430,6 +437,17 @@ extern "C" int din_conv2d_wgrad_nhwc_f16(const void* x, const void* dz, float* d
   DIN_CHECK_ARG(tiles < INT32_MAX, "din_conv2d_wgrad_nhwc_f16: too many tiles");
   p.num_tiles = static_cast<int>(tiles);
   p.n_ci_blk = (c_in + nci - 1) / nci;
+  // c_out <= 64 with a 3x3 filter: two taps share one MMA (see PAIR64).  DIN_WGRAD_PAIR64=0: the zero-filled upper half (A/B).
+  bool pair64 = !two_cta && c_out <= 64 && kw == 3;
+  {
+    const char* e = std::getenv("DIN_WGRAD_PAIR64");
+    if (e && e[0] == '0') pair64 = false;
+  }
+  if (pair64) {                                             // the shifted windows need one more pixel column of tiles
+    p.tiles_x = (ow + 1 + 7) / 8;
+    p.tiles_per_img = p.tiles_x * ((oh + 15) / 16);
+    p.num_tiles = static_cast<int>(static_cast<long long>(n) * p.tiles_per_img);
+  }
   const int co_blk = two_cta ? 256 : 128;
   const int units = ((c_out + co_blk - 1) / co_blk) * p.n_ci_blk * kh;     // (pairs of) CTAs before the pixel split
   int splits = ((two_cta ? sms : 2 * sms) + units - 1) / units;
@@ -469,7 +487,10 @@ extern "C" int din_conv2d_wgrad_nhwc_f16(const void* x, const void* dz, float* d
   } else
   switch (kw) {
     case 1: rc = (nci == 128) ? launch_wgrad<128, 1>(tdz, tx, p, grid, st) : launch_wgrad<64, 1>(tdz, tx, p, grid, st); break;
-    case 3: rc = (nci == 128) ? launch_wgrad<128, 3>(tdz, tx, p, grid, st) : launch_wgrad<64, 3>(tdz, tx, p, grid, st); break;
+    case 3:
+      if (pair64) rc = (nci == 128) ? launch_wgrad<128, 3, true>(tdz, tx, p, grid, st) : launch_wgrad<64, 3, true>(tdz, tx, p, grid, st);
+      else rc = (nci == 128) ? launch_wgrad<128, 3>(tdz, tx, p, grid, st) : launch_wgrad<64, 3>(tdz, tx, p, grid, st);
+      break;
     case 5: rc = launch_wgrad<64, 5>(tdz, tx, p, grid, st); break;
     default: rc = launch_wgrad<64, 7>(tdz, tx, p, grid, st); break;
   }
