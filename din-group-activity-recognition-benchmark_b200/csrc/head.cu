@@ -616,6 +616,126 @@ context_attention_kernel(const float* __restrict__ q, const float* __restrict__ 
   }
 }
 
+// Backward of context_attention_kernel (autograd through torch.matmul / F.softmax / torch.matmul of
+// TCE_STBiP_module.py:274-280 when Dynamic_TCE_volleyball trains).  With x[px] = img[px] + posbias[px]:
+//     dA[n][px] = <dctx[n], x[px]>,   ds = A * (dA - sum_px A * dA),
+//     dq[n] = sum_px ds[n][px] * x[px],   dimg[px] = sum_n (ds[n][px] * q[n] + A[n][px] * dctx[n])
+// (x is both key and value, so its gradient collects both terms; posbias is a constant of the plan.)
+// One CTA per (frame, head), as the forward: scores and softmax recomputed with the forward's arithmetic, A and dA / ds for
+// all actors in shared memory, the map streamed three times through the 32-pixel tile; every output element is written by
+// exactly one thread (no atomics: deterministic).
+__global__ void __launch_bounds__(kCtxThreads)
+context_attention_bwd_kernel(const float* __restrict__ q, const float* __restrict__ img, const float* __restrict__ posbias,
+                             const float* __restrict__ dctx, const float* __restrict__ dq_add, float* __restrict__ dq,
+                             float* __restrict__ dimg, int F, int N, int P, int H) {
+  extern __shared__ float smem_f[];
+  const int f = blockIdx.x / H, h = blockIdx.x - f * H;
+  const int M = F * N;
+  float* qs = smem_f;                                   // [N][128]
+  float* gs = qs + N * kCtxDim;                         // [N][128]  dctx
+  float* tile = gs + N * kCtxDim;                       // [32][129]
+  float* att = tile + kCtxTile * (kCtxDim + 1);         // [N][P]  A
+  float* dsm = att + N * P;                             // [N][P]  dA, then ds
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int HC = H * kCtxDim;
+  const size_t row0 = (static_cast<size_t>(h) * M + static_cast<size_t>(f) * N) * kCtxDim;
+  for (int i = tid; i < N * kCtxDim; i += kCtxThreads) {
+    qs[i] = __ldg(q + row0 + i);
+    gs[i] = __ldg(dctx + row0 + i);
+  }
+  const float* ib = img + static_cast<size_t>(f) * P * HC + h * kCtxDim;
+  const float* pb = posbias + h * kCtxDim;
+  float* ob = dimg + static_cast<size_t>(f) * P * HC + h * kCtxDim;
+
+  auto load_tile = [&](int p0) {
+    for (int i = tid; i < kCtxTile * (kCtxDim / 4); i += kCtxThreads) {
+      const int px = i / (kCtxDim / 4), c4 = i - px * (kCtxDim / 4);
+      float4 v = make_float4(0, 0, 0, 0);
+      if (p0 + px < P) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(ib + static_cast<size_t>(p0 + px) * HC) + c4);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(pb + static_cast<size_t>(p0 + px) * HC) + c4);
+        v = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+      }
+      float* t = tile + px * (kCtxDim + 1) + 4 * c4;
+      t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+    }
+  };
+
+  // ---- pass 1: scores and dA (same dot products, against q and dctx)
+  for (int p0 = 0; p0 < P; p0 += kCtxTile) {
+    __syncthreads();
+    load_tile(p0);
+    __syncthreads();
+    for (int i = tid; i < N * kCtxTile; i += kCtxThreads) {
+      const int n = i / kCtxTile, px = i - n * kCtxTile;
+      if (p0 + px < P) {
+        const float* qq = qs + n * kCtxDim;
+        const float* gg = gs + n * kCtxDim;
+        const float* xx = tile + px * (kCtxDim + 1);
+        float acc = 0.0f, accg = 0.0f;
+#pragma unroll 8
+        for (int c = 0; c < kCtxDim; ++c) {
+          acc = fmaf(qq[c], xx[c], acc);
+          accg = fmaf(gg[c], xx[c], accg);
+        }
+        att[n * P + p0 + px] = acc;
+        dsm[n * P + p0 + px] = accg;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- softmax (the forward's arithmetic), then ds = A * (dA - <A, dA>), one warp per actor
+  for (int n = warp; n < N; n += kCtxThreads / 32) {
+    float* a = att + n * P;
+    float* d = dsm + n * P;
+    float mx = -FLT_MAX;
+    for (int i = lane; i < P; i += 32) mx = fmaxf(mx, a[i]);
+    mx = warp_max(mx);
+    float den = 0.0f;
+    for (int i = lane; i < P; i += 32) { const float e = expf(a[i] - mx); a[i] = e; den += e; }
+    den = warp_sum(den);
+    const float inv = 1.0f / den;
+    float dot = 0.0f;
+    for (int i = lane; i < P; i += 32) { a[i] *= inv; dot = fmaf(a[i], d[i], dot); }
+    dot = warp_sum(dot);
+    for (int i = lane; i < P; i += 32) d[i] = a[i] * (d[i] - dot);
+  }
+  // ---- pass 2: dq (thread = (channel, actor parity), as the forward's weighted sum) and dimg (thread = (pixel, channel))
+  const int c = tid & (kCtxDim - 1), n0 = tid >> 7;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
+  for (int p0 = 0; p0 < P; p0 += kCtxTile) {
+    __syncthreads();
+    load_tile(p0);
+    __syncthreads();
+    const int lim = min(kCtxTile, P - p0);
+    for (int px = 0; px < lim; ++px) {
+      const float xv = tile[px * (kCtxDim + 1) + c];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int n = n0 + 2 * k;
+        if (n < N) acc[k] = fmaf(dsm[n * P + p0 + px], xv, acc[k]);
+      }
+    }
+    for (int i = tid; i < lim * kCtxDim; i += kCtxThreads) {
+      const int px = i >> 7, cc = i & (kCtxDim - 1);
+      float o = 0.0f;
+      for (int n = 0; n < N; ++n)
+        o = fmaf(dsm[n * P + p0 + px], qs[n * kCtxDim + cc], fmaf(att[n * P + p0 + px], gs[n * kCtxDim + cc], o));
+      ob[static_cast<size_t>(p0 + px) * HC + cc] = o;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int n = n0 + 2 * k;
+    if (n < N) {                                          // dq_add: the gradient q receives through the residual of layernorm1
+      const size_t o = row0 + static_cast<size_t>(n) * kCtxDim + c;
+      dq[o] = acc[k] + (dq_add != nullptr ? __ldg(dq_add + o) : 0.0f);
+    }
+  }
+}
+
 // ================================================================================================
 // read-out: max over actors -> fc_activities -> mean over frames     (one CTA per clip)
 // ================================================================================================
@@ -800,6 +920,26 @@ extern "C" int din_readout_f32(const float* s, const float* w, const float* bias
   const size_t smem = static_cast<size_t>(c) * sizeof(float);
   DIN_CHECK_ARG(smem <= 48 * 1024, "din_readout_f32: c=%d too large", c);
   readout_kernel<<<b, kRoThreads, smem, static_cast<cudaStream_t>(stream)>>>(s, w, bias, logits, t, n, c, a, n_valid);
+  DIN_CHECK_CUDA(cudaGetLastError());
+  return DIN_OK;
+}
+
+extern "C" int din_context_attention_bwd_f32(const float* q, const float* img, const float* posbias, const float* dctx,
+                                             const float* dq_add, float* dq, float* dimg, int frames, int n, int pixels,
+                                             int heads, void* stream) {
+  const char* who = "din_context_attention_bwd_f32";
+  DIN_CHECK_ARG(q && img && posbias && dctx && dq && dimg, "%s: null pointer", who);
+  DIN_CHECK_ARG(frames > 0 && n > 0 && n <= 16 && pixels > 0 && heads > 0,
+                "%s: bad shape frames=%d n=%d (<= 16) pixels=%d heads=%d", who, frames, n, pixels, heads);
+  DIN_CHECK_ARG(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(posbias) |
+                  reinterpret_cast<uintptr_t>(dctx) | reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dimg)) & 15) == 0,
+                "%s: pointers must be 16-byte aligned", who);
+  const size_t smem = (2 * static_cast<size_t>(n) * kCtxDim + kCtxTile * (kCtxDim + 1) + 2 * static_cast<size_t>(n) * pixels) *
+                      sizeof(float);
+  DIN_CHECK_ARG(smem <= 220 * 1024, "%s: n * pixels = %d x %d does not fit shared memory", who, n, pixels);
+  DIN_OPT_IN_SMEM(context_attention_bwd_kernel, smem);
+  context_attention_bwd_kernel<<<frames * heads, kCtxThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      q, img, posbias, dctx, dq_add, dq, dimg, frames, n, pixels, heads);
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;
 }

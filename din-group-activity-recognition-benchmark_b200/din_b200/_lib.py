@@ -96,6 +96,7 @@ PROTOTYPES = {
     "din_group_layernorm_bwd_f32": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _ll, _ll, _i,
                                               _ll, _i, C.c_float, _i, _i, _vp, _vp]),
     "din_context_attention_f32": (C.c_int, [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _vp]),
+    "din_context_attention_bwd_f32": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _vp]),
     "din_pack_flat_f32": (C.c_int, [C.POINTER(DinFlatJob), _i, _fp, C.c_float, _vp]),
     "din_dynamic_infer_bwd_ws_floats": (C.c_longlong, [_i, _i, _i, _i, _i, _i, _i]),
     "din_dynamic_infer_bwd_f32": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i,

@@ -565,8 +565,10 @@ class TCEWeights:
         if w_all.shape[1] != 512:
             raise ValueError("Dynamic_TCE_volleyball needs a 512-channel feature map (vgg16 / res18)")
         self.conv = _Conv(w_all.contiguous(), None, relu=False)
+        self.w_all = w_all.view(H * TCE_DIM, 512).contiguous()                                      # fp32 [out, in]: backward
         oh, ow = out_size
         pos = _context_position_table(oh, ow, device)
+        self.pos = pos                                                                              # [oh*ow, 512]: backward
         self.posbias = torch.addmm(b_all, pos, w_all.view(H * TCE_DIM, 512).t()).contiguous()       # [oh*ow, 512]
         g = lambda h, n: sd[f"{prefix}{h}.{n}"].contiguous()                                        # noqa: E731
         self.q = [(g(h, "emb_roi.weight"), g(h, "emb_roi.bias")) for h in range(H)]

@@ -876,3 +876,18 @@ def context_attention(q, img, posbias, n):
         check(_lib.load().din_context_attention_f32(_p(q), _p(img), _p(posbias), _p(ctx), frames, n, pixels, heads,
                                                     _stream()), "din_context_attention_f32")
     return ctx
+
+
+def context_attention_bwd(q, img, posbias, dctx, dq_add=None):
+    """Backward of context_attention: -> (dq [H, M, 128] (+ dq_add), dimg [F, P, H*128])."""
+    for name, t in (("q", q), ("img", img), ("posbias", posbias), ("dctx", dctx)) + ((("dq_add", dq_add),) if dq_add is not None else ()):
+        _need(t, torch.float32, name)
+    heads, m, d = q.shape
+    frames, pixels = img.shape[0], img.shape[1]
+    n = m // frames
+    assert d == 128 and dctx.shape == q.shape and img.shape[2] == heads * 128 and m == frames * n
+    dq, dimg = torch.empty_like(q), torch.empty_like(img)
+    with _launch(f"context_attention_bwd_{pixels}px", 10 * m * heads * pixels * 128, 4 * (img.numel() * 4 + 4 * q.numel())):
+        check(_lib.load().din_context_attention_bwd_f32(_p(q), _p(img), _p(posbias), _p(dctx), _p(dq_add), _p(dq), _p(dimg),
+                                                        frames, n, pixels, heads, _stream()), "din_context_attention_bwd_f32")
+    return dq, dimg

@@ -72,7 +72,99 @@ def _dpi_backward(dpi, prefix, x, tmp, dg, dx, n_valid, grads):
         grads[prefix + "beta"] = torch.cat(dbeta)
 
 
-def forward_train(eng, images, boxes, bboxes_num=None, training=True, train_backbone=False):
+TCE_PREFIX = "multilayer_head_embfeature_context_encoding.CET."
+
+
+def _tce_forward(tce, x, fm, n, tape, training, p):
+    """TCEWeights.__call__ with the intermediates kept and the module's two dropouts applied (TCE_STBiP_module.py:280,
+    :241 -- nn.Dropout(context_dropout_ratio) on the attended features and inside the FFN)."""
+    from .engine import TCE_DIM as D, TCE_HEADS as H
+    B, T, N, C = x.shape
+    M = B * T * N
+    F_, oh, ow, _ = fm.shape
+    dev = x.device
+    xf = x.reshape(M, C)
+    q = torch.empty((H, M, D), dtype=torch.float32, device=dev)
+    for h in range(H):
+        ops.linear_f32(xf, *tce.q[h], out=q[h])
+    img = tce.conv(fm, out_f32=True).view(F_, oh * ow, H * D)
+    ctx = ops.context_attention(q, img, tce.posbias, n)
+    out = torch.empty((B, T, N, C + H * D), dtype=torch.float32, device=dev)
+    o2 = out.view(M, C + H * D)
+    o2[:, :C].copy_(xf)
+    heads = []
+    scale = 1.0 / (1.0 - p) if p < 1.0 else 0.0
+    for h in range(H):
+        m1 = _dropout_mask(ctx[h].shape, p, dev, training)
+        ctx_d = ops.scale_mask(ctx[h], m1, scale) if m1 is not None else ctx[h]
+        c1 = ops.group_layernorm(ctx_d, *tce.ln1[h], n_outer=M, outer_stride=D, cols=D, pre=q[h])
+        a = ops.linear_f32(c1, *tce.ffn0[h], relu=True)
+        m2 = _dropout_mask(a.shape, p, dev, training)
+        a_d = ops.scale_mask(a, m2, scale) if m2 is not None else a
+        f = ops.linear_f32(a_d, *tce.ffn3[h])
+        o = ops.group_layernorm(f, *tce.ln2[h], n_outer=M, outer_stride=D, cols=D, pre=c1)
+        o2[:, C + h * D:C + (h + 1) * D].copy_(o)
+        heads.append((m1, ctx_d, c1, a, m2, a_d, f))
+    tape["tce"] = {"xf": xf, "q": q, "img": img, "fm": fm, "heads": heads, "scale": scale, "C": C}
+    return out
+
+
+def _tce_backward(eng, tape, dx_full, grads, need_dfm):
+    """dx_full [M, C + 512]: gradient of the DIN input.  -> gradient of the person features [M, C]; parameter gradients
+    under the reference's names; tape['dfm_init'] = the context encoder's share of the feature-map gradient (fp32)."""
+    from .engine import TCE_DIM as D, TCE_HEADS as H
+    tce, rec = eng.tce, tape["tce"]
+    C, scale = rec["C"], rec["scale"]
+    xf, q, img = rec["xf"], rec["q"], rec["img"]
+    M = xf.shape[0]
+    dxp = dx_full[:, :C].contiguous()
+    dctx = torch.empty_like(q)
+    dq_res = torch.empty_like(q)
+    for h in range(H):
+        m1, ctx_d, c1, a, m2, a_d, f = rec["heads"][h]
+        pre = f"{TCE_PREFIX}{h}."
+        do = dx_full[:, C + h * D:C + (h + 1) * D].contiguous()
+        # layernorm2(f + c1): one gradient for both
+        df, dg2, db2 = ops.group_layernorm_bwd(f, *tce.ln2[h], do, n_outer=M, outer_stride=D, cols=D, pre=c1)
+        grads[pre + "layernorm2.weight"], grads[pre + "layernorm2.bias"] = dg2, db2
+        da_d, dw3, db3 = ops.linear_bwd(a_d, tce.ffn3[h][0], df)
+        grads[pre + "FFN.3.weight"], grads[pre + "FFN.3.bias"] = dw3, db3
+        da = ops.scale_mask(da_d, m2, scale) if m2 is not None else da_d
+        dpre = ops.relu_bwd_f32(a, da)
+        _, dw0, db0 = ops.linear_bwd(c1, tce.ffn0[h][0], dpre, dx_out=df, dx_accumulate=True)     # df += d(c1) via the FFN
+        grads[pre + "FFN.0.weight"], grads[pre + "FFN.0.bias"] = dw0, db0
+        # layernorm1(ctx_d + q): one gradient for the attended features and for q's residual
+        du, dg1, db1 = ops.group_layernorm_bwd(ctx_d, *tce.ln1[h], df, n_outer=M, outer_stride=D, cols=D, pre=q[h],
+                                               dx_out=dq_res[h])
+        grads[pre + "layernorm1.weight"], grads[pre + "layernorm1.bias"] = dg1, db1
+        if m1 is not None:
+            ops.scale_mask(du, m1, scale, out=dctx[h])
+        else:
+            dctx[h].copy_(du)
+    dq, dimg = ops.context_attention_bwd(q, img, tce.posbias, dctx, dq_add=dq_res)
+    for h in range(H):
+        pre = f"{TCE_PREFIX}{h}."
+        _, dwq, dbq = ops.linear_bwd(xf, tce.q[h][0], dq[h], dx_out=dxp, dx_accumulate=True)
+        grads[pre + "emb_roi.weight"], grads[pre + "emb_roi.bias"] = dwq, dbq
+    # downsample2 of the four heads = one 512 -> 512 GEMM over the map (the bias entered through posbias)
+    fm = rec["fm"]
+    rows = fm.shape[0] * fm.shape[1] * fm.shape[2]
+    dfm, dwd, dbd = ops.linear_bwd(fm.view(rows, fm.shape[3]), tce.w_all, dimg.view(rows, H * D), need_dx=need_dfm)
+    # downsample2 runs on context = feature map + position embedding (infer_model.py:413): the embedding's share of dW is
+    # (sum over frames of dimg)^T . pos
+    F_, P = fm.shape[0], fm.shape[1] * fm.shape[2]
+    dsum = ops.mean_axis(dimg.view(1, F_, P * H * D), 1)
+    ops.gemm_f32(dsum, tce.pos, m=H * D, n=fm.shape[3], k=P, a_strides=(1, H * D), b_strides=(fm.shape[3], 1), out=dwd,
+                 alpha=float(F_), accumulate=True)
+    for h in range(H):
+        pre = f"{TCE_PREFIX}{h}."
+        grads[pre + "downsample2.weight"] = dwd[h * D:(h + 1) * D].reshape(D, fm.shape[3], 1, 1).contiguous()
+        grads[pre + "downsample2.bias"] = dbd[h * D:(h + 1) * D].contiguous()
+    tape["dfm_init"] = dfm.view(fm.shape[0], fm.shape[1], fm.shape[2], fm.shape[3]) if need_dfm else None
+    return dxp
+
+
+def forward_train(eng, images, boxes, bboxes_num=None, training=True, train_backbone=False, tce_dropout=None):
     """-> (logits [B, A], tape).  Same kernels as DinEngine.forward_*, plus dropout and saved intermediates.
     train_backbone: additionally keep every backbone activation (VGG-16) for backward_backbone."""
     cfg = eng.cfg
@@ -104,6 +196,9 @@ def forward_train(eng, images, boxes, bboxes_num=None, training=True, train_back
             tape["ylite"] = ylite
         else:
             x = x0
+        if eng.tce is not None:                       # Dynamic_TCE_volleyball: 4 x 128 context features join the DIN input
+            p_tce = float(getattr(eng, "tce_dropout", 0.1) if tce_dropout is None else tce_dropout)
+            x = _tce_forward(eng.tce, x.view(B, T, N, eng.C_embed), fm, N, tape, training, p_tce)
         x = x.view(B, T, N, C)
         tape["x"] = x
         n_valid = None
@@ -193,8 +288,12 @@ def backward_head(eng, tape, dlogits, sink=None):
             for i, (_, dpi, xi, tmp) in enumerate(tape["dpi"]):
                 prefix = "DPI." if eng.dataset == "collective" else f"DPI.DIMlist.{i}."
                 _dpi_backward(dpi, prefix, xi, tmp, dg, dx, n_valid, grads)
-        # ---- lite branch
+        # ---- context encoder (Dynamic_TCE_volleyball): the DIN input is [person features | 4 x 128 context features]
         dx = dx.view(M, C)
+        if eng.tce is not None:
+            dx = _tce_backward(eng, tape, dx, grads, need_dfm=tape["train_backbone"])
+            C = eng.C_embed
+            g_sz = T * N * C
         if cfg.lite_dim:
             dyl, dgam, dbet = ops.group_layernorm_bwd(tape["ylite"], *eng.point_ln, dx, n_outer=B, outer_stride=g_sz,
                                                       cols=g_sz, relu=True)
@@ -230,7 +329,9 @@ def backward_backbone(eng, tape, dcrops, grads):
     `backbone.features.N.{weight,bias}` names."""
     B, T = tape["B"], tape["T"]
     N = eng.N
-    dfm = torch.zeros(tape["fm_shape"], dtype=torch.float32, device=eng.device)
+    dfm = tape.get("dfm_init")                                      # the context encoder's share (Dynamic_TCE_volleyball)
+    if dfm is None:
+        dfm = torch.zeros(tape["fm_shape"], dtype=torch.float32, device=eng.device)
     ops.roi_align_bwd(dcrops, tape["boxes"], eng._box_idx(B * T, N), dfm, eng.K, eng.K, d=eng.D_stride)
     dfm16, scale_ws = ops.grad_to_f16(dfm)
     inv_scale = scale_ws[2:3]

@@ -202,10 +202,9 @@ class _DinModel(nn.Module):
                     "train mode with BatchNorm batch statistics is implemented for the ResNet-18 backbone (all of its "
                     "BatchNorm layers in train mode): freeze BN as the reference does with cfg.set_bn_eval "
                     "(train_net_dynamic.py:101-102, model.apply(set_bn_eval))")
-        if self._tce and self.training:
-            raise NotImplementedError("Dynamic_TCE_volleyball runs inference / evaluation on the sm_100a path; its "
-                                      "training step is not implemented (call model.eval())")
         eng = self.engine()
+        if self._tce:                                       # context_dropout_ratio of the encoder (TCE_STBiP_module.py:225)
+            eng.tce_dropout = float(self.multilayer_head_embfeature_context_encoding.CET[0].dropout.p)
         if not self.training:
             if self._dataset == "collective":
                 return eng.forward_collective(images, boxes, bboxes_num)
@@ -266,7 +265,7 @@ class _ContextEncoding(nn.Module):
 
 class Dynamic_TCE_volleyball(_DinModel):
     """reference infer_model.py:237-468: Dynamic_volleyball with the temporal-context-encoding module prepended to the
-    dynamic inference (inference / evaluation on the CUDA path)."""
+    dynamic inference; trains too (scripts/train_volleyball_stage2_dynamic_tce.py): din_context_attention_bwd_f32."""
     _dataset = "volleyball"
     _tce = True
 

@@ -583,6 +583,15 @@ DIN_API int din_bn_bwd(const void* g, const void* z, int z_is_f32, const float* 
 DIN_API int din_context_attention_f32(const float* q, const float* img, const float* posbias, float* ctx, int frames,
                                       int n, int pixels, int heads, void* stream);
 
+/* Backward of din_context_attention_f32 (autograd through torch.matmul / F.softmax / torch.matmul at
+ * TCE_STBiP_module.py:274-280 when scripts/train_volleyball_stage2_dynamic_tce.py trains Dynamic_TCE_volleyball):
+ *   dq [heads][frames*n][128], dimg [frames][pixels][heads*128] (the gradient of the heads' downsample2 output: the feature map
+ *   is key AND value, both terms are summed) from dctx [heads][frames*n][128]; scores / softmax recomputed with the forward's
+ *   arithmetic; no atomics.  dq_add (or NULL): added to dq -- the gradient q also receives through layernorm1's residual. */
+DIN_API int din_context_attention_bwd_f32(const float* q, const float* img, const float* posbias, const float* dctx,
+                                          const float* dq_add, float* dq, float* dimg, int frames, int n, int pixels,
+                                          int heads, void* stream);
+
 /* ---- data-parallel training: gradients -> one flat fp32 buffer (csrc/flat.cu) -----------------------------------
  * flat[dst_offset + i] = scale * src[i] for every job, ALL jobs in one launch (<= 96 per launch, more are split).
  * The flat buffer is what the step's all-reduce runs on (ncclAllReduce through torch.distributed); `scale` carries
