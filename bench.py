@@ -565,7 +565,7 @@ def main():
 
     # supplementary: the training step (all ranks take part: its gradient all-reduce is inside the timed step)
     train_info = None
-    if not args.no_train_step and pc.backbone in ("vgg16", "res18", "inv3") and pc.dataset == "volleyball" and not pc.tce:
+    if not args.no_train_step and pc.backbone in ("vgg16", "res18", "inv3") and pc.dataset == "volleyball":
         train_info = train_step_info(model, pc, dev, images_d, boxes_d, min(args.train_clips, B), dist=dist)
 
     if dist is not None:

@@ -17,13 +17,15 @@ REF = next((p for p in ("/root/reference", os.path.join(ROOT, "oracle", "_ref", 
 
 
 @pytest.mark.skipif(REF is None, reason="reference sources not staged (python oracle/make_ref.py)")
-def test_unmodified_reference_script_trains_and_checkpoints(tmp_path, cuda):
+@pytest.mark.parametrize("script,model", [("train_volleyball_stage2_dynamic.py", "Dynamic_volleyball"),
+                                          ("train_volleyball_stage2_dynamic_tce.py", "Dynamic_TCE_volleyball")])
+def test_unmodified_reference_script_trains_and_checkpoints(tmp_path, cuda, script, model):
     """2 training steps (batch 2, T = 10, 720p, VGG-16 trained, nn.DataParallel wrap) + 1 test step + checkpoint,
-    then the checkpoint re-loaded into a fresh drop-in model."""
+    then the checkpoint re-loaded into a fresh drop-in model; the same for the TCE sibling's script."""
     env = dict(os.environ, DIN_OFFLINE="1")
     env.pop("CUDA_VISIBLE_DEVICES", None)
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "dropin_run.py"), "--ref", REF,
-                          "--workdir", str(tmp_path), "--epochs", "1", "--devices", "0"],
+                          "--workdir", str(tmp_path), "--epochs", "1", "--devices", "0", "--script", script],
                          capture_output=True, text=True, timeout=900, env=env)
     assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-3000:])
     info = json.loads(out.stdout.strip().splitlines()[-1])
@@ -31,7 +33,7 @@ def test_unmodified_reference_script_trains_and_checkpoints(tmp_path, cuda):
     assert len(info["losses"]) == 2, info                       # one 'Train' and one 'Test' epoch line
     assert all(0.0 < v < 50.0 for v in info["losses"]), info    # finite
     assert info["checkpoint"].startswith("stage2_epoch1_") and info["epochs"] == 1
-    assert info["reloaded_logits_finite"] and info["data_parallel"]
+    assert info["reloaded_logits_finite"] and info["data_parallel"] and info["model"] == model
     assert info["optimizer_state_tensors"] > 30                 # Adam state for the backbone + head parameters
 
 

@@ -34,6 +34,8 @@ def main():
     ap.add_argument("--devices", default="0")
     ap.add_argument("--train-clips", type=int, default=4)
     ap.add_argument("--test-clips", type=int, default=1)
+    ap.add_argument("--script", default="train_volleyball_stage2_dynamic.py",
+                    help="the reference experiment script under scripts/ (also: train_volleyball_stage2_dynamic_tce.py)")
     ap.add_argument("--import-only", action="store_true", help="resolve every name the trainer needs, then stop (CPU)")
     args = ap.parse_args()
     os.environ.setdefault("DIN_OFFLINE", "1")
@@ -113,7 +115,7 @@ def main():
 
     T.train_net = short_train_net
     from din_b200 import plan_cache
-    runpy.run_path(os.path.join(ref, "scripts", "train_volleyball_stage2_dynamic.py"), run_name="__main__")
+    runpy.run_path(os.path.join(ref, "scripts", args.script), run_name="__main__")
 
     cfg = seen["cfg"]
     log = open(cfg.log_path).read()
@@ -123,7 +125,9 @@ def main():
     state = torch.load(ckpts[-1], map_location="cpu")
     sd = {k[len("module."):] if k.startswith("module.") else k: v for k, v in state["state_dict"].items()}
     cfg_log, cfg.log_path = cfg.log_path, None
-    fresh = infer_model.Dynamic_volleyball(cfg)
+    cls = infer_model.Dynamic_TCE_volleyball if cfg.inference_module_name == "dynamic_tce_volleyball" else \
+        infer_model.Dynamic_volleyball
+    fresh = cls(cfg)
     fresh.load_state_dict(sd, strict=True)
     cfg.log_path = cfg_log
     fresh = fresh.cuda().eval()
@@ -133,6 +137,7 @@ def main():
     print(json.dumps({"losses": losses, "checkpoint": os.path.basename(ckpts[-1]), "epochs": state["epoch"],
                       "reloaded_logits_finite": bool(torch.isfinite(logits).all()),
                       "data_parallel": bool(cfg.use_multi_gpu), "visible_gpus": torch.cuda.device_count(),
+                      "model": cls.__name__,
                       "optimizer_state_tensors": len(state["optimizer"]["state"])}))
 
 
