@@ -60,6 +60,10 @@ int din_stem_tc_launch(const void* x, int x_is_u8, const float* w, const float* 
                        int w_in, int c_out, int kh, int kw, int stride, int pad, int relu, int prep,
                        cudaStream_t st);
 
+// ResNet-18 stem + 3x3/2 max-pool in one launch (stem_tc.cu); DIN_ERR_UNSUPPORTED for image rows TMA cannot address
+int din_stem_pool_tc_launch(const void* x, int x_is_u8, const float* w, const float* bias, void* y, int n, int h, int w_in,
+                            int prep, cudaStream_t st);
+
 // tensor-core stem weight gradient (stem_tc.cu); arguments already validated by din_stem_wgrad
 int din_stem_wgrad_tc_launch(const void* x, int x_is_u8, const void* dz, float* dw, float* dbias, const float* inv_scale,
                              int n, int h, int w_in, int c_out, int kh, int stride, int pad, int prep, cudaStream_t st);

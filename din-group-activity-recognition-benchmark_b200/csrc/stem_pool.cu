@@ -487,6 +487,19 @@ extern "C" int din_stem_conv_nhwc_u8(const uint8_t* x, const float* w, const flo
   return rc;
 }
 
+extern "C" int din_stem7x7_pool_nhwc_f16(const void* x, int x_is_u8, const float* w, const float* bias, void* y, int n,
+                                         int h, int w_in, int prep, void* stream) {
+  const char* who = "din_stem7x7_pool_nhwc_f16";
+  DIN_CHECK_ARG(x && w && y, "%s: null pointer", who);
+  DIN_CHECK_ARG(n > 0 && h >= 7 && w_in >= 7, "%s: bad extent n=%d h=%d w=%d", who, n, h, w_in);
+  DIN_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 15) == 0, "%s: y must be 16-byte aligned", who);
+  const int rc = din_stem_pool_tc_launch(x, x_is_u8, w, bias, y, n, h, w_in, prep, static_cast<cudaStream_t>(stream));
+  if (rc == DIN_ERR_UNSUPPORTED)
+    return din_set_error(DIN_ERR_UNSUPPORTED, "%s: image rows must be 16-byte multiples and x 16-byte aligned (w=%d): run "
+                         "din_stem_conv_* and din_maxpool2d_nhwc_f16 separately", who, w_in);
+  return rc;
+}
+
 extern "C" int din_maxpool2d_nhwc_f16(const void* x, void* y, int n, int h, int w, int c, int x_c_stride,
                                       int y_c_stride, int k, int stride, int pad, void* stream) {
   return pool_common("din_maxpool2d_nhwc_f16", 0, x, y, n, h, w, c, x_c_stride, y_c_stride, k, stride, pad, stream);

@@ -38,6 +38,8 @@ constexpr int kStemThreads = 128;
 constexpr int kEpiPitch = 80;            // bytes per pixel row in the store-transpose scratch
 
 struct StemParams {
+  int pool_ph, pool_pw;   // stem_s2d_ws_kernel<U8, POOL = true>: extent of the MaxPool2d(3, 2, 1) output that y holds
+  int pool_strips;        //   ceil(pool_pw / 63): strips of 63 pooled = 128 conv pixels (one overlapping)
   const void* x;          // fp32 NCHW [n,3,h,w]  or (U8) uint8 NHWC [n,h,w,3]
   const float* w; const float* bias; __half* y;
   int n, h, w_in, oh, ow, pad, relu, prep;
@@ -737,12 +739,52 @@ constexpr int kWsBoxU8 = 832;                    // uint8: bytes per patch row (
 constexpr int kWsPatchBytes = kWsBlockA + 3 * 8 * kWsBoxB * 4;           // 25728 (uint8: 8 * 832 = 6656)
 constexpr int kWsPatchStage = 26112;
 constexpr size_t kWsSmem = 1024 + kWsPatchStages * kWsPatchStage + 2 * 2 * kS2dVPlane + 16 * kS2dWTap + 4 * 32 * kEpiPitch + 256;
+// POOL: resnet18.maxpool (MaxPool2d(3, 2, 1), backbone.py:115-132) fused into the stem.  The kernel is bound by its OUTPUT
+// writes (3.2 GB per 107 frames at 720p, 3.1 TB/s of the part's ~3.95 TB/s write-only rate), and the pool throws three
+// quarters of them away: here a CTA owns a strip of 63 pooled = 128 convolution pixels (conv x = 126 * strip - 1 + r) and
+// walks the rows of one image top to bottom, its epilogue warps keep the last three ReLU'd convolution rows in a shared
+// memory ring and emit one pooled row for every second convolution row.  Padding: a ReLU output is >= 0 and every window
+// holds a real pixel, so positions outside the image enter the maximum as 0.
+constexpr int kWsPoolStride = 126;               // convolution pixels between strips (63 pooled pixels)
+constexpr int kWsRingPitch = 144;                // bytes per pixel in the ring: 128 + 16 (bank spread for 16-byte stores)
+constexpr int kWsRingRow = 128 * kWsRingPitch;
+constexpr size_t kWsPoolSmem = kWsSmem + 3 * kWsRingRow;
 
-template <bool U8>
+// iteration order of every role: POOL = false: tiles blockIdx.x, + gridDim.x, ... decoded as (img, oy, strip);
+// POOL = true: tasks (img, strip) = blockIdx.x, + gridDim.x, ..., each walked over oy = 0 .. oh - 1
+template <bool POOL>
+struct WsIter {
+  const StemParams& p;
+  int tile, oy_, task;
+  __device__ __forceinline__ WsIter(const StemParams& pp) : p(pp), tile(blockIdx.x), oy_(0), task(blockIdx.x) {}
+  __device__ __forceinline__ bool valid() const { return POOL ? task < p.n * p.pool_strips : tile < p.num_tiles; }
+  __device__ __forceinline__ TileCoord coord() const {
+    if constexpr (POOL) {
+      TileCoord t;
+      t.img = task / p.pool_strips;
+      t.strip = task - t.img * p.pool_strips;
+      t.oy = oy_;
+      return t;
+    } else {
+      return decode_tile(p, tile);
+    }
+  }
+  __device__ __forceinline__ void next() {
+    if constexpr (POOL) {
+      if (++oy_ == p.oh) { oy_ = 0; task += gridDim.x; }
+    } else {
+      tile += gridDim.x;
+    }
+  }
+};
+
+template <bool U8, bool POOL = false>
 __global__ void __launch_bounds__(kWsThreads, 1)
 stem_s2d_ws_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_constant__ CUtensorMap tmap_b,
                    const StemParams p) {
   constexpr int COUT = 64;
+  constexpr int kStripStride = POOL ? kWsPoolStride : 128;     // convolution pixels between strips
+  constexpr int kXShift = POOL ? 1 : 0;                         // the strip starts one pixel to the left of its stride
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem(smem_raw, 1024);
   uint8_t* patch_s = smem;                                           // kWsPatchStages x raw patch
@@ -757,6 +799,7 @@ stem_s2d_ws_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_co
   uint64_t* acc_full = v_empty + 2;               // [2]  MMA commit
   uint64_t* acc_empty = acc_full + 2;             // [2]  4 epilogue warps
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
+  uint8_t* ring = reinterpret_cast<uint8_t*>(bars) + 256;          // POOL: 3 convolution rows x 128 pixels x kWsRingPitch
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // ---- one-time: weights (as stem_s2d_kernel), zeroed vector buffers, barriers, TMEM
@@ -803,20 +846,22 @@ stem_s2d_ws_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_co
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int j = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
-        const TileCoord cur = decode_tile(p, tile);
+      for (WsIter<POOL> it(p); it.valid(); it.next(), ++j) {
+        const TileCoord cur = it.coord();
         const int ps = j % kWsPatchStages;
+        // input column of (X = 0, dx = 0); the box starts at the 16-byte boundary at or left of it
+        const int gx0 = (cur.strip * kStripStride - kXShift) * 2 - 4;
         mbar_wait_relaxed(&patch_empty[ps], ((j / kWsPatchStages) & 1) ^ 1);
         if constexpr (U8) {
+          const int p0 = POOL ? gx0 - (gx0 & 15) : gx0 - 12;              // first pixel of the box: a multiple of 16
           mbar_arrive_expect_tx(&patch_full[ps], 8u * kWsBoxU8);
-          tma_load_3d(patch_s + ps * kWsPatchStage, &tmap_img, &patch_full[ps], ((cur.strip * 256 - 16) * 3) / 4,
-                      cur.oy * 2 - 3, cur.img);
+          tma_load_3d(patch_s + ps * kWsPatchStage, &tmap_img, &patch_full[ps], (p0 * 3) / 4, cur.oy * 2 - 3, cur.img);
         } else {
+          const int c0 = gx0 - (POOL ? 2 : 0);                           // 252 * strip - 8: a multiple of 4 columns
           mbar_arrive_expect_tx(&patch_full[ps], static_cast<uint32_t>(kWsPatchBytes));
-          tma_load_3d(patch_s + ps * kWsPatchStage, &tmap_img, &patch_full[ps], cur.strip * 256 - 4, cur.oy * 2 - 3,
+          tma_load_3d(patch_s + ps * kWsPatchStage, &tmap_img, &patch_full[ps], c0, cur.oy * 2 - 3, cur.img * 3);
+          tma_load_3d(patch_s + ps * kWsPatchStage + kWsBlockA, &tmap_b, &patch_full[ps], c0 + kWsBoxBStart, cur.oy * 2 - 3,
                       cur.img * 3);
-          tma_load_3d(patch_s + ps * kWsPatchStage + kWsBlockA, &tmap_b, &patch_full[ps],
-                      cur.strip * 256 - 4 + kWsBoxBStart, cur.oy * 2 - 3, cur.img * 3);
         }
       }
     }
@@ -826,7 +871,7 @@ stem_s2d_ws_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_co
     constexpr uint32_t idesc = umma_idesc_f16_f32(128, COUT);
     const uint32_t v_addr = smem_u32(v_s), w_addr = smem_u32(w_s);
     int j = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
+    for (WsIter<POOL> it(p); it.valid(); it.next(), ++j) {
       const int b = j & 1;
       const uint32_t use = static_cast<uint32_t>(j >> 1);
       mbar_wait(&v_full[b], use & 1u);
@@ -848,15 +893,18 @@ stem_s2d_ws_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_co
     // ------------------------------------------------------------------ builders: one vector per half-res pixel
     const int bt = tid - 64;                                          // 0..255
     int j = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
-      const TileCoord cur = decode_tile(p, tile);
+    for (WsIter<POOL> it(p); it.valid(); it.next(), ++j) {
+      const TileCoord cur = it.coord();
       const int ps = j % kWsPatchStages, b = j & 1;
       const uint32_t use = static_cast<uint32_t>(j >> 1);
       mbar_wait_relaxed(&patch_full[ps], (j / kWsPatchStages) & 1);
       mbar_wait_relaxed(&v_empty[b], (use & 1u) ^ 1u);
       const uint8_t* patch = patch_s + ps * kWsPatchStage;
       uint8_t* vb = v_s + b * (2 * kS2dVPlane);
-      const int iy0 = cur.oy * 2 - 3, gx0 = cur.strip * 256 - 4;      // input coordinates of (ty = 0, dy = 0) / (X = 0, dx = 0)
+      // input coordinates of (ty = 0, dy = 0) / (X = 0, dx = 0)
+      const int iy0 = cur.oy * 2 - 3, gx0 = (cur.strip * kStripStride - kXShift) * 2 - 4;
+      // offset of input column gx0 inside the loaded box (see the producer)
+      const int boff = U8 ? (POOL ? (gx0 & 15) : 12) : (POOL ? 2 : 0);
       for (int v = bt; v < 4 * kS2dVecs; v += 32 * kWsBuilders) {
         const int ty = v / kS2dVecs, X = v - ty * kS2dVecs;
         const bool in_a = X < kWsSplitX;
@@ -874,16 +922,16 @@ stem_s2d_ws_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_co
           for (int dy = 0; dy < 2; ++dy) {
             float raw[2];
             if constexpr (U8) {
-              const uint8_t* q = patch + (2 * ty + dy) * kWsBoxU8 + (12 + 2 * X) * 3 + c;
+              const uint8_t* q = patch + (2 * ty + dy) * kWsBoxU8 + (boff + 2 * X) * 3 + c;
               raw[0] = static_cast<float>(q[0]);
               raw[1] = static_cast<float>(q[3]);
             } else {
               // one aligned 8-byte load per (c, dy): lanes read consecutive pairs, no bank conflicts (with the pairs on
               // odd columns -- phase -3 -- these were 4-byte loads at stride 2: 790 of the tile's 2430 shared-memory
               // wavefronts were their conflicts)
-              const float* row = in_a ? reinterpret_cast<const float*>(patch) + (c * 8 + 2 * ty + dy) * kWsBoxA + 2 * X
+              const float* row = in_a ? reinterpret_cast<const float*>(patch) + (c * 8 + 2 * ty + dy) * kWsBoxA + 2 * X + boff
                                       : reinterpret_cast<const float*>(patch + kWsBlockA) + (c * 8 + 2 * ty + dy) * kWsBoxB +
-                                            2 * X - kWsBoxBStart;
+                                            2 * X + boff - kWsBoxBStart;
               const float2 pr = *reinterpret_cast<const float2*>(row);
               raw[0] = pr.x;
               raw[1] = pr.y;
@@ -912,12 +960,65 @@ stem_s2d_ws_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_co
     uint8_t* sc = scratch + (warp - kWsEpiWarp0) * 32 * kEpiPitch;
     const int unit = lane & 3;
     int j = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++j) {
-      const TileCoord cur = decode_tile(p, tile);
+    for (WsIter<POOL> it(p); it.valid(); it.next(), ++j) {
+      const TileCoord cur = it.coord();
       const int b = j & 1;
       mbar_wait_relaxed(&acc_full[b], static_cast<uint32_t>(j >> 1) & 1u);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(b * COUT);
+      if constexpr (POOL) {
+        // this lane's convolution pixel -> the ring (zeros outside the image), then every second row one pooled row
+        const int r = q * 32 + lane;
+        const int cx = cur.strip * kWsPoolStride - 1 + r;
+        const bool inside = cx >= 0 && cx < p.ow;
+        uint8_t* dst = ring + (cur.oy % 3) * kWsRingRow + r * kWsRingPitch;
+#pragma unroll
+        for (int c0 = 0; c0 < COUT; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int u4 = 0; u4 < 4; ++u4) {
+            uint32_t hh[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              hh[k] = inside ? pack_half2(__uint_as_float(v[8 * u4 + 2 * k]), __uint_as_float(v[8 * u4 + 2 * k + 1]), true) : 0u;
+            *reinterpret_cast<uint4*>(dst + c0 * 2 + u4 * 16) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+          }
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[b]);
+        const bool last_row = cur.oy == p.oh - 1;
+        if ((cur.oy & 1) || last_row) {
+          const int py = cur.oy >> 1;                                 // rows 2 py - 1 .. 2 py + 1 (clipped to the image)
+          const int y_lo = max(2 * py - 1, 0), y_hi = min(2 * py + 1, p.oh - 1);
+          asm volatile("bar.sync 1, 128;" ::: "memory");              // the four epilogue warps: all ring rows written
+          const int et = (warp - kWsEpiWarp0) * 32 + lane;            // 0..127
+          __half* yrow = p.y + ((static_cast<size_t>(cur.img) * p.pool_ph + py) * p.pool_pw) * COUT;
+          for (int i = et; i < 63 * 8; i += 128) {
+            const int jl = i >> 3, vv = i & 7;
+            const int px = cur.strip * 63 + jl;
+            if (px < p.pool_pw) {
+              __half2 m[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) m[e] = __float2half2_rn(0.0f);
+              for (int yy = y_lo; yy <= y_hi; ++yy) {
+                const uint8_t* rr = ring + (yy % 3) * kWsRingRow + (2 * jl) * kWsRingPitch + vv * 16;
+#pragma unroll
+                for (int dxp = 0; dxp < 3; ++dxp) {
+                  const uint4 t = *reinterpret_cast<const uint4*>(rr + dxp * kWsRingPitch);
+                  const __half2* th = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) m[e] = __hmax2(m[e], th[e]);
+                }
+              }
+              *reinterpret_cast<uint4*>(yrow + static_cast<size_t>(px) * COUT + vv * 8) = *reinterpret_cast<const uint4*>(m);
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");              // ring rows may be overwritten by the next tiles
+        }
+      } else {
       __half* yrow = p.y + ((static_cast<size_t>(cur.img) * p.oh + cur.oy) * p.ow) * COUT;
 #pragma unroll
       for (int c0 = 0; c0 < COUT; c0 += 32) {
@@ -946,6 +1047,7 @@ stem_s2d_ws_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_co
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[b]);
+      }
     }
   }
 
@@ -957,7 +1059,7 @@ stem_s2d_ws_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_co
   }
 }
 
-template <bool U8>
+template <bool U8, bool POOL = false>
 int launch_s2d_ws(StemParams& p, cudaStream_t st) {
   CUtensorMap timg, timg_b;
   if (U8) {
@@ -985,9 +1087,16 @@ int launch_s2d_ws(StemParams& p, cudaStream_t st) {
   }
   const int sms = din_num_sms();
   long long grid = sms > 0 ? sms : 148;
-  if (grid > p.num_tiles) grid = p.num_tiles;
-  DIN_OPT_IN_SMEM(stem_s2d_ws_kernel<U8>, kWsSmem);
-  stem_s2d_ws_kernel<U8><<<static_cast<int>(grid), kWsThreads, kWsSmem, st>>>(timg, timg_b, p);
+  if constexpr (POOL) {
+    const long long tasks = static_cast<long long>(p.n) * p.pool_strips;
+    if (grid > tasks) grid = tasks;
+    DIN_OPT_IN_SMEM((stem_s2d_ws_kernel<U8, true>), kWsPoolSmem);
+    stem_s2d_ws_kernel<U8, true><<<static_cast<int>(grid), kWsThreads, kWsPoolSmem, st>>>(timg, timg_b, p);
+  } else {
+    if (grid > p.num_tiles) grid = p.num_tiles;
+    DIN_OPT_IN_SMEM((stem_s2d_ws_kernel<U8, false>), kWsSmem);
+    stem_s2d_ws_kernel<U8, false><<<static_cast<int>(grid), kWsThreads, kWsSmem, st>>>(timg, timg_b, p);
+  }
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;
 }
@@ -1262,6 +1371,29 @@ int din_stem_tc_launch(const void* x, int x_is_u8, const float* w, const float* 
   fastdiv(static_cast<uint32_t>(p.strips_per_row), &p.fd_mul, &p.fd_shr);
   fastdiv(static_cast<uint32_t>(p.oh), &p.fo_mul, &p.fo_shr);
   return x_is_u8 ? dispatch<true>(p, c_out, kh, kw, stride, st) : dispatch<false>(p, c_out, kh, kw, stride, st);
+}
+
+// ResNet-18's conv1 + bn1 (folded) + relu + maxpool (backbone.py:115-132) in one launch: stem_s2d_ws_kernel<U8, POOL = true>.
+// y: [n, ph, pw, 64] with ph = (oh - 1) / 2 + 1.  DIN_ERR_UNSUPPORTED when the image rows do not meet the TMA alignment (the
+// caller then runs the stem and the pool separately).
+int din_stem_pool_tc_launch(const void* x, int x_is_u8, const float* w, const float* bias, void* y, int n, int h, int w_in,
+                            int prep, cudaStream_t st) {
+  StemParams p{};
+  p.x = x; p.w = w; p.bias = bias; p.y = static_cast<__half*>(y);
+  p.n = n; p.h = h; p.w_in = w_in;
+  p.oh = (h + 6 - 7) / 2 + 1;
+  p.ow = (w_in + 6 - 7) / 2 + 1;
+  p.pad = 3; p.relu = 1; p.prep = prep;
+  p.pool_ph = (p.oh - 1) / 2 + 1;
+  p.pool_pw = (p.ow - 1) / 2 + 1;
+  p.pool_strips = (p.pool_pw + 62) / 63;
+  p.strips_per_row = p.pool_strips;
+  const long long tiles = static_cast<long long>(n) * p.oh * p.pool_strips;
+  if (tiles >= INT32_MAX) return din_set_error(DIN_ERR_INVALID_ARG, "din_stem_conv_pool: too many tiles");
+  p.num_tiles = static_cast<int>(tiles);
+  const bool tma_ok = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (x_is_u8 ? w_in % 16 == 0 : w_in % 4 == 0);
+  if (!tma_ok) return DIN_ERR_UNSUPPORTED;
+  return x_is_u8 ? launch_s2d_ws<true, true>(p, st) : launch_s2d_ws<false, true>(p, st);
 }
 
 // Tensor-core stem weight gradient (see stem_wgrad_tc_kernel); arguments validated by din_stem_wgrad.

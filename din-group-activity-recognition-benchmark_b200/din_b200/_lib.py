@@ -55,6 +55,7 @@ PROTOTYPES = {
     "din_bn_apply": (C.c_int, [_vp, _i, _fp, _fp, _vp, _vp, _ll, _i, _i, _vp]),
     "din_bn_bwd": (C.c_int, [_vp, _vp, _i, _fp, _fp, _fp, _fp, _vp, _fp, _fp, _fp, _ll, _i, _vp]),
     "din_pack_conv_weights_f16": (C.c_int, [C.POINTER(DinPackJob), _i, _vp]),
+    "din_stem7x7_pool_nhwc_f16": (C.c_int, [_vp, _i, _fp, _fp, _vp, _i, _i, _i, _i, _vp]),
     "din_maxpool2d_nhwc_f16": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_avgpool2d_nhwc_f16": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "din_avgpool3_bias_relu_nhwc_f16": (C.c_int, [_vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -89,6 +89,7 @@ def frames_per_chunk(backbone_name, n_frames, h, w, fixed=None):
 
 
 FUSE_CONV1 = os.environ.get("DIN_FUSE_CONV1", "1") != "0"      # A/B knob: 0 = stand-alone stem + conv1_2
+FUSE_STEM_POOL = os.environ.get("DIN_FUSE_STEM_POOL", "1") != "0"   # A/B knob: 0 = ResNet-18 stem and max-pool separately
 SMALL_LAUNCH_PIXELS = 148 * 128 if os.environ.get("DIN_SMALL_EXACT", "1") != "0" else 0
 # ... except the dense GEMM (n = h = 1: fc_emb_1) above 1 GFLOP: a full batch has only 960 'pixels' (actor rows) but
 # K = 12 800 .. 27 200 -- 25-53 GFLOP, bound by weight traffic, where the second weight part doubled its time
@@ -317,8 +318,13 @@ class Res18Plan:
 
     def __call__(self, images, out=None):
         assert not self.bn_train, "a batch-statistics plan only runs forward_train (DinEngine.features does that)"
-        x = self.stem(images)
-        x = ops.maxpool2d_nhwc(x, 3, 2, 1)
+        if FUSE_STEM_POOL and self.stem.relu and ops.stem_pool_supported(images):
+            # conv1 + bn1 + relu + maxpool in one launch: the half-resolution 64-channel map never reaches HBM (inference;
+            # the training forward keeps it for the backward)
+            x = ops.stem_conv_pool(images, self.stem.w, self.stem.bias, prep=True)
+        else:
+            x = self.stem(images)
+            x = ops.maxpool2d_nhwc(x, 3, 2, 1)
         last = len(self.blocks) - 1
         for i, (conv1, conv2, down) in enumerate(self.blocks):
             identity = x if down is None else down(x)
@@ -878,11 +884,15 @@ class BasenetEngine:
         self.fc_actions = (sd["fc_actions.weight"].contiguous(), sd["fc_actions.bias"].contiguous())
         self.fc_act = (sd["fc_activities.weight"].contiguous(), sd["fc_activities.bias"].contiguous())
         self._idx_cache, self._fm_cache = {}, None
+        self._stage, self._pending_small = None, None
 
     _box_idx = DinEngine._box_idx
     _flat_frames = staticmethod(DinEngine._flat_frames)
     features = DinEngine.features
     features_train = DinEngine.features_train
+    _stage_state = DinEngine._stage_state
+    _stage_host_chunk = DinEngine._stage_host_chunk
+    stage_small = DinEngine.stage_small
 
     def _states(self, images, boxes, B, T, N):
         fm = self.features(self._flat_frames(images))

@@ -203,6 +203,36 @@ def stem_conv(x, w_oihw, bias, *, stride=1, pad=0, relu=True, prep=True):
     return y
 
 
+def stem_pool_supported(x):
+    """The fused ResNet-18 stem + max-pool kernel loads image patches by TMA: rows must be 16-byte multiples."""
+    if x.data_ptr() % 16 != 0:
+        return False
+    if x.dtype == torch.uint8:
+        return x.dim() == 4 and x.shape[-1] == 3 and x.shape[2] % 16 == 0 and x.shape[1] >= 7
+    return x.dim() == 4 and x.shape[1] == 3 and x.shape[3] % 4 == 0 and x.shape[2] >= 7
+
+
+def stem_conv_pool(x, w_oihw, bias, *, prep=True):
+    """Raw images -> prep_images -> conv 7x7 stride 2 pad 3 (+bias) -> ReLU -> MaxPool2d(3, 2, 1) -> NHWC fp16 [n, ph, pw, 64],
+    one launch (din_stem7x7_pool_nhwc_f16): resnet18's conv1 / bn1 (folded) / relu / maxpool."""
+    _need(w_oihw, torch.float32, "w_oihw")
+    u8 = x.dtype == torch.uint8
+    _need(x, torch.uint8 if u8 else torch.float32, "x")
+    n, h, w = (x.shape[0], x.shape[1], x.shape[2]) if u8 else (x.shape[0], x.shape[2], x.shape[3])
+    if tuple(w_oihw.shape) != (64, 3, 7, 7):
+        raise _lib.DinError(f"stem_conv_pool: weight must be [64,3,7,7], got {tuple(w_oihw.shape)}")
+    oh, ow = (h + 6 - 7) // 2 + 1, (w + 6 - 7) // 2 + 1
+    ph, pw = (oh - 1) // 2 + 1, (ow - 1) // 2 + 1
+    y = torch.empty((n, ph, pw, 64), dtype=torch.float16, device=x.device)
+    if bias is not None:
+        _need(bias, torch.float32, "bias")
+    with _launch(f"stem7x7s2+pool_3->64@{oh}x{ow}" + ("_u8" if u8 else ""), 2 * n * oh * ow * 64 * 147,
+                 (1 if u8 else 4) * n * 3 * h * w + 2 * n * ph * pw * 64):
+        check(_lib.load().din_stem7x7_pool_nhwc_f16(_p(x), int(u8), _p(w_oihw), _p(bias), _p(y), n, h, w, int(prep), _stream()),
+              "din_stem7x7_pool_nhwc_f16")
+    return y
+
+
 def stem_pair_supported(x):
     """The fused conv1_1 + conv1_2 kernel loads image patches by TMA: rows must be 16-byte multiples."""
     if x.dtype == torch.uint8:

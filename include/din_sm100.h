@@ -191,6 +191,18 @@ typedef struct DinPackJob {
 } DinPackJob;
 DIN_API int din_pack_conv_weights_f16(const DinPackJob* jobs, int n_jobs, void* stream);
 
+/* ResNet-18's stem in ONE launch (inference): conv1 7x7 stride 2 pad 3 over the 3-channel image (prep_images fused, eval
+ * BatchNorm folded into w / bias by the caller) + ReLU + MaxPool2d(3, 2, 1) (resnet18.conv1 / bn1 / relu / maxpool,
+ * backbone.py:115-132).  The stand-alone stem is bound by its output writes and the pool discards three quarters of them:
+ * here the 64-channel half-resolution map never reaches HBM (a CTA keeps the last three convolution rows of its strip in
+ * shared memory and emits a pooled row for every second one).  Bit-identical to din_stem_conv_* followed by
+ * din_maxpool2d_nhwc_f16(k = 3, stride = 2, pad = 1).
+ * x: fp32 NCHW [n,3,h,w] raw 0..255 (w % 4 == 0) | (x_is_u8) uint8 NHWC [n,h,w,3] (w % 16 == 0); w fp32 OIHW [64,3,7,7];
+ * bias fp32 [64] or NULL; y fp16 NHWC [n, ph, pw, 64], ph = ((h + 6 - 7) / 2 + 1 - 1) / 2 + 1 (pw alike).
+ * DIN_ERR_UNSUPPORTED for other widths / unaligned x: use the two separate calls. */
+DIN_API int din_stem7x7_pool_nhwc_f16(const void* x, int x_is_u8, const float* w, const float* bias, void* y, int n, int h,
+                                      int w_in, int prep, void* stream);
+
 /*
  * Max / average pooling, NHWC fp16, over channels [0, c) of buffers with x_c_stride / y_c_stride channels
  * (so a pool can read a channel slice and write straight into a concat buffer).

@@ -316,3 +316,33 @@ def test_inception_merged_branch_heads_match_the_per_branch_plan(cuda, monkeypat
     a, b = maps
     assert torch.isfinite(a).all()
     assert (a - b).abs().max().item() <= 4e-3 * b.abs().max().item(), ((a - b).abs().max().item(), b.abs().max().item())
+
+
+@pytest.mark.parametrize("u8", [False, True], ids=["f32", "u8"])
+@pytest.mark.parametrize("n,h,w", [(2, 70, 160), (3, 73, 48), (1, 37, 16), (1, 720, 1280), (2, 480, 720), (5, 96, 272)],
+                         ids=str)
+def test_resnet_stem_with_fused_maxpool_is_bit_identical(cuda, n, h, w, u8):
+    """din_stem7x7_pool_nhwc_f16 (conv1 + folded bn1 + relu + maxpool in one launch) == din_stem_conv_* followed by
+    din_maxpool2d_nhwc_f16(3, 2, 1), bit for bit: odd / even row counts, several strips of 63 pooled pixels, several images
+    per CTA, image borders."""
+    from din_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(h * 31 + w)
+    raw = torch.randint(0, 256, (n, h, w, 3), generator=g, dtype=torch.uint8)
+    x = raw.to(cuda) if u8 else raw.permute(0, 3, 1, 2).float().contiguous().to(cuda)
+    wt = (torch.randn(64, 3, 7, 7, generator=g) * 0.05).to(cuda)
+    b = torch.randn(64, generator=g).to(cuda)
+    assert ops.stem_pool_supported(x)
+    want = ops.maxpool2d_nhwc(ops.stem_conv(x, wt, b, stride=2, pad=3, relu=True, prep=True), 3, 2, 1)
+    got = ops.stem_conv_pool(x, wt, b, prep=True)
+    torch.cuda.synchronize()
+    assert got.shape == want.shape, (tuple(got.shape), tuple(want.shape))
+    assert torch.equal(got, want), ((got.float() - want.float()).abs().max().item(),
+                                    (got != want).nonzero()[:5].tolist())
+
+
+def test_resnet_stem_pool_rejects_unaligned_rows(cuda):
+    from din_b200 import _lib, ops
+    x = torch.zeros(1, 3, 40, 50, device=cuda)                       # 50 * 4 bytes: not a 16-byte multiple
+    assert not ops.stem_pool_supported(x)
+    with pytest.raises(_lib.DinError, match="16-byte"):
+        ops.stem_conv_pool(x, torch.zeros(64, 3, 7, 7, device=cuda), None)
