@@ -18,4 +18,24 @@ for _ in range(10):
     y = ops.stem_conv(x, w, b, stride=2, pad=3)
 e1.record()
 torch.cuda.synchronize()
-print(f"DIN_STEM_TIGHT={os.environ.get('DIN_STEM_TIGHT', '0')}: {e0.elapsed_time(e1) / 10:.3f} ms per 107 frames, checksum {y.float().abs().sum().item():.6e}")
+print(f"stem alone: {e0.elapsed_time(e1) / 10:.3f} ms per 107 frames, checksum {y.float().abs().sum().item():.6e}")
+for _ in range(3):
+    z = ops.stem_conv_pool(x, w, b)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(10):
+    z = ops.stem_conv_pool(x, w, b)
+e1.record()
+torch.cuda.synchronize()
+print(f"stem + pool fused: {e0.elapsed_time(e1) / 10:.3f} ms per 107 frames, checksum {z.float().abs().sum().item():.6e}")
+xu = x.permute(0, 2, 3, 1).contiguous().to(torch.uint8)
+for fn, nm in ((lambda: ops.stem_conv(xu, w, b, stride=2, pad=3), "stem alone u8"), (lambda: ops.stem_conv_pool(xu, w, b), "fused u8")):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"{nm}: {e0.elapsed_time(e1) / 10:.3f} ms per 107 frames")
