@@ -544,7 +544,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
 conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        const ConvKParams p) {
   constexpr int kBHalfBytes = (BN / 2) * kBK * 2;            // this CTA's half of one tap's weight tile
-  constexpr int kTmemCols = (2 * BN <= 128) ? 128 : 256;
+  constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem(smem_raw, 1024);
   uint8_t* smem_a = smem;
@@ -1612,7 +1612,15 @@ int conv2d_launch(const DinConvDesc* d, const void* x, const void* w_packed, con
   const bool static3 = halo && d->kh == 3 && d->kw == 3 && p.split == 1 && !(variant >= 0 && (variant & 8));
   // CTA pair (cta_group::2, M = 256) for the narrow-N 3x3 layers: see conv_igemm_2cta_kernel.  DIN_CONV_2CTA=0
   // keeps them on the one-CTA kernel (A/B measurements).
-  bool two_cta = static3 && (bn == 64 || bn == 128) && p.n_tiles_n == 1 && p.num_tiles >= 2;
+  // bn = 192 with few input channels (Inception-v3's Conv2d_4a, 80 -> 192): the one-CTA kernel re-streams 24 KB of weights
+  // per tap for every 128-pixel tile (442 KB per tile against 2 x 23 KB of halo) and is bound by that L2 -> SM traffic;
+  // the pair halves it per CTA.  DIN_CONV_2CTA_WIDE=0 keeps it on the one-CTA kernel (A/B).
+  bool wide_pair = bn == 192 && p.n_cblk <= 2;
+  {
+    const char* e = std::getenv("DIN_CONV_2CTA_WIDE");
+    if (e && e[0] == '0') wide_pair = false;
+  }
+  bool two_cta = static3 && (bn == 64 || bn == 128 || wide_pair) && p.n_tiles_n == 1 && p.num_tiles >= 2;
   {
     const char* e = std::getenv("DIN_CONV_2CTA");
     if (e && e[0] == '0') two_cta = false;
@@ -1683,6 +1691,7 @@ int conv2d_launch(const DinConvDesc* d, const void* x, const void* w_packed, con
   if (two_cta) {
     const int pairs = (p.num_tiles + 1) / 2;
     int grid2 = 2 * (pairs < sms / 2 ? pairs : sms / 2);     // whole clusters of 2
+    if (bn == 192) return launch_conv_2cta<192, 1>(ta, tb, p, grid2, smem, st);
     return bn == 64 ? launch_conv_2cta<64, 9>(ta, tb, p, grid2, smem, st)
                     : launch_conv_2cta<128, 3>(ta, tb, p, grid2, smem, st);
   }
