@@ -719,15 +719,17 @@ stem_s2d_kernel(const StemParams p) {
 // that serial chain of latencies, not by the im2col build as round 1 assumed):
 //   warp 0        TMA: box {264, 8, 3} of the fp32 NCHW image ({832 B, 8} of the uint8 NHWC frame) per tile, 3 tiles
 //                 ahead (the box starts on a 16-byte boundary left of the strip: see tools/probes/tma_probe.cu);
-//   warps 2..9    build the 4 x 131 half-resolution vectors (prep_images, 0 where the convolution pads) into one of two
-//                 vector buffers;
+//   warps 2..17   two groups of eight build the 4 x 131 half-resolution vectors (prep_images, 0 where the convolution pads)
+//                 of alternate tiles, each group into its own vector buffer: a tile costs a group ~1200 cycles of building plus
+//                 ~850 of fence.proxy.async / barrier hand-off (per-role cycle counters), which one group alone cannot hide;
 //   warp 1        16 tcgen05.mma (K = 16 each) per tile into one of two TMEM accumulators;
-//   warps 10..13  epilogue: TMEM -> ReLU -> fp16 -> transpose -> NHWC stores.
+//   warps 18..21  epilogue: TMEM -> ReLU -> fp16 -> transpose -> NHWC stores.
 // One persistent CTA per SM (155 KB of shared memory).
 // ------------------------------------------------------------------------------------------------
-constexpr int kWsThreads = 32 * 14;
-constexpr int kWsBuilders = 8;                   // warps 2..9
-constexpr int kWsEpiWarp0 = 10;                  // warps 10..13
+constexpr int kWsThreads = 32 * 22;
+constexpr int kWsBuilders = 8;                   // builder warps per GROUP: warps 2..9 build the even tiles of a CTA, warps
+                                                 // 10..17 the odd ones (each group owns one of the two vector buffers)
+constexpr int kWsEpiWarp0 = 18;                  // warps 18..21
 constexpr int kWsPatchStages = 3;
 // fp32: the 264 input columns 256*strip - 4 .. + 259 of a patch row exceed TMA's 256-element box limit, so every tile is
 // two boxes: A = columns [0, 136) and B = columns [132, 264) of that range (both start on 16-byte boundaries); the
@@ -889,11 +891,13 @@ stem_s2d_ws_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_co
         umma_commit(&acc_full[b]);
       }
     }
-  } else if (warp < 2 + kWsBuilders) {
+  } else if (warp < 2 + 2 * kWsBuilders) {
     // ------------------------------------------------------------------ builders: one vector per half-res pixel
-    const int bt = tid - 64;                                          // 0..255
+    const int grp = (warp - 2) / kWsBuilders;                         // tiles j with (j & 1) == grp, vector buffer grp
+    const int bt = tid - 64 - grp * 32 * kWsBuilders;                 // 0..255 inside the group
     int j = 0;
     for (WsIter<POOL> it(p); it.valid(); it.next(), ++j) {
+      if ((j & 1) != grp) continue;
       const TileCoord cur = it.coord();
       const int ps = j % kWsPatchStages, b = j & 1;
       const uint32_t use = static_cast<uint32_t>(j >> 1);
