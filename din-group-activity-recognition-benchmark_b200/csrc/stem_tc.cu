@@ -719,17 +719,28 @@ stem_s2d_kernel(const StemParams p) {
 // that serial chain of latencies, not by the im2col build as round 1 assumed):
 //   warp 0        TMA: box {264, 8, 3} of the fp32 NCHW image ({832 B, 8} of the uint8 NHWC frame) per tile, 3 tiles
 //                 ahead (the box starts on a 16-byte boundary left of the strip: see tools/probes/tma_probe.cu);
-//   warps 2..17   two groups of eight build the 4 x 131 half-resolution vectors (prep_images, 0 where the convolution pads)
-//                 of alternate tiles, each group into its own vector buffer: a tile costs a group ~1200 cycles of building plus
-//                 ~850 of fence.proxy.async / barrier hand-off (per-role cycle counters), which one group alone cannot hide;
+//   builders      two groups of eight warps (six with the pool fused: 192 threads walk the 524 vectors in three trips,
+//                 exactly as 256 would) build the 4 x 131 half-resolution vectors (prep_images, 0 where the convolution
+//                 pads) of alternate tiles, each group into its own vector buffer: a tile costs a group ~1200 cycles of
+//                 building plus ~850 of fence.proxy.async / barrier hand-off (per-role cycle counters), which one group
+//                 alone cannot hide;
 //   warp 1        16 tcgen05.mma (K = 16 each) per tile into one of two TMEM accumulators;
-//   warps 18..21  epilogue: TMEM -> ReLU -> fp16 -> transpose -> NHWC stores.
-// One persistent CTA per SM (155 KB of shared memory).
+//   epilogue      TMEM -> ReLU -> fp16 -> transpose -> NHWC stores: four warps, one per TMEM lane quadrant; with the pool
+//                 fused eight (warp e reads lane quadrant e & 3 and the 32 output channels of half e >> 2: the four-warp
+//                 pool epilogue was the longest role, ~1650 of a tile's ~2100 cycles).
+// One persistent CTA per SM (164 KB of shared memory, 218 KB with the pool's ring).
 // ------------------------------------------------------------------------------------------------
 constexpr int kWsThreads = 32 * 22;
-constexpr int kWsBuilders = 8;                   // builder warps per GROUP: warps 2..9 build the even tiles of a CTA, warps
-                                                 // 10..17 the odd ones (each group owns one of the two vector buffers)
-constexpr int kWsEpiWarp0 = 18;                  // warps 18..21
+// builder warps per GROUP (the first group builds the even tiles of a CTA, the second the odd ones, each into its own
+// vector buffer) and epilogue warps: 8 + 8 + 4 without the pool (two epilogue warps per pixel would write its 128-byte
+// line as two 64-byte halves at different times: 1.25 -> 1.47 ms), 6 + 6 + 8 with it
+template <bool POOL> struct WsRoles {
+  static constexpr int kBuilders = POOL ? 6 : 8;
+  static constexpr int kEpiWarp0 = 2 + 2 * kBuilders;
+  static constexpr int kEpiWarps = POOL ? 8 : 4;
+  static_assert(kEpiWarp0 + kEpiWarps == 22 && (kEpiWarp0 & 3) == 2, "warp roles");
+};
+constexpr int kWsEpiWarps = 8;                   // scratch areas
 constexpr int kWsPatchStages = 3;
 // fp32: the 264 input columns 256*strip - 4 .. + 259 of a patch row exceed TMA's 256-element box limit, so every tile is
 // two boxes: A = columns [0, 136) and B = columns [132, 264) of that range (both start on 16-byte boundaries); the
@@ -740,7 +751,7 @@ constexpr int kWsBoxU8 = 832;                    // uint8: bytes per patch row (
                                                  // 208 32-bit elements (a box is at most 256 elements wide)
 constexpr int kWsPatchBytes = kWsBlockA + 3 * 8 * kWsBoxB * 4;           // 25728 (uint8: 8 * 832 = 6656)
 constexpr int kWsPatchStage = 26112;
-constexpr size_t kWsSmem = 1024 + kWsPatchStages * kWsPatchStage + 2 * 2 * kS2dVPlane + 16 * kS2dWTap + 4 * 32 * kEpiPitch + 256;
+constexpr size_t kWsSmem = 1024 + kWsPatchStages * kWsPatchStage + 2 * 2 * kS2dVPlane + 16 * kS2dWTap + kWsEpiWarps * 32 * kEpiPitch + 256;
 // POOL: resnet18.maxpool (MaxPool2d(3, 2, 1), backbone.py:115-132) fused into the stem.  The kernel is bound by its OUTPUT
 // writes (3.2 GB per 107 frames at 720p, 3.1 TB/s of the part's ~3.95 TB/s write-only rate), and the pool throws three
 // quarters of them away: here a CTA owns a strip of 63 pooled = 128 convolution pixels (conv x = 126 * strip - 1 + r) and
@@ -787,19 +798,21 @@ stem_s2d_ws_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_co
   constexpr int COUT = 64;
   constexpr int kStripStride = POOL ? kWsPoolStride : 128;     // convolution pixels between strips
   constexpr int kXShift = POOL ? 1 : 0;                         // the strip starts one pixel to the left of its stride
+  constexpr int kWsBuilders = WsRoles<POOL>::kBuilders, kWsEpiWarp0 = WsRoles<POOL>::kEpiWarp0;
+  constexpr int kNumEpi = WsRoles<POOL>::kEpiWarps;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem(smem_raw, 1024);
   uint8_t* patch_s = smem;                                           // kWsPatchStages x raw patch
   uint8_t* v_s = patch_s + kWsPatchStages * kWsPatchStage;           // 2 x (2 planes x [4 * kS2dVPitch] x 16 B)
   uint8_t* w_s = v_s + 2 * 2 * kS2dVPlane;                           // 16 taps x 2 KB
-  uint8_t* scratch = w_s + 16 * kS2dWTap;                            // 4 epilogue warps x 32 x 80 B
-  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + 4 * 32 * kEpiPitch);
+  uint8_t* scratch = w_s + 16 * kS2dWTap;                            // 8 epilogue warps x 32 x 80 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + kWsEpiWarps * 32 * kEpiPitch);
   uint64_t* patch_full = bars;                    // [3]
-  uint64_t* patch_empty = patch_full + 3;         // [3]  8 builder warps
-  uint64_t* v_full = patch_empty + 3;             // [2]  8 builder warps
+  uint64_t* patch_empty = patch_full + 3;         // [3]  the builder warps of one group
+  uint64_t* v_full = patch_empty + 3;             // [2]  the builder warps of one group
   uint64_t* v_empty = v_full + 2;                 // [2]  MMA commit
   uint64_t* acc_full = v_empty + 2;               // [2]  MMA commit
-  uint64_t* acc_empty = acc_full + 2;             // [2]  4 epilogue warps
+  uint64_t* acc_empty = acc_full + 2;             // [2]  8 epilogue warps
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
   uint8_t* ring = reinterpret_cast<uint8_t*>(bars) + 256;          // POOL: 3 convolution rows x 128 pixels x kWsRingPitch
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -833,7 +846,7 @@ stem_s2d_ws_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_co
     for (int s = 0; s < 3; ++s) { mbar_init(&patch_full[s], 1); mbar_init(&patch_empty[s], kWsBuilders); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&v_full[s], kWsBuilders); mbar_init(&v_empty[s], 1);
-      mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4);
+      mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kNumEpi);
     }
     fence_mbar_init();
   }
@@ -960,7 +973,8 @@ stem_s2d_ws_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_co
     }
   } else {
     // ------------------------------------------------------------------ epilogue: warp e = lane quadrant e
-    const int q = warp & 3;                                           // warps 10..13 -> quadrants 2, 3, 0, 1
+    const int q = warp & 3;                                           // warps 14..21 -> quadrants 2, 3, 0, 1, 2, 3, 0, 1
+    const int c0 = ((warp - kWsEpiWarp0) >> 2) * 32;                  // POOL: this warp's 32 output channels
     uint8_t* sc = scratch + (warp - kWsEpiWarp0) * 32 * kEpiPitch;
     const int unit = lane & 3;
     int j = 0;
@@ -976,8 +990,7 @@ stem_s2d_ws_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_co
         const int cx = cur.strip * kWsPoolStride - 1 + r;
         const bool inside = cx >= 0 && cx < p.ow;
         uint8_t* dst = ring + (cur.oy % 3) * kWsRingRow + r * kWsRingPitch;
-#pragma unroll
-        for (int c0 = 0; c0 < COUT; c0 += 32) {
+        {
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr + c0, v);
           tmem_ld_wait();
@@ -996,19 +1009,23 @@ stem_s2d_ws_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_co
         const bool last_row = cur.oy == p.oh - 1;
         if ((cur.oy & 1) || last_row) {
           const int py = cur.oy >> 1;                                 // rows 2 py - 1 .. 2 py + 1 (clipped to the image)
-          const int y_lo = max(2 * py - 1, 0), y_hi = min(2 * py + 1, p.oh - 1);
-          asm volatile("bar.sync 1, 128;" ::: "memory");              // the four epilogue warps: all ring rows written
-          const int et = (warp - kWsEpiWarp0) * 32 + lane;            // 0..127
+          asm volatile("bar.sync 1, 256;" ::: "memory");              // the eight epilogue warps: all ring rows written
+          const int et = (warp - kWsEpiWarp0) * 32 + lane;            // 0..255
           __half* yrow = p.y + ((static_cast<size_t>(cur.img) * p.pool_ph + py) * p.pool_pw) * COUT;
-          for (int i = et; i < 63 * 8; i += 128) {
+          // rows clipped INTO the image (a repeated row leaves the maximum unchanged): nine independent loads in flight
+          int slot[3];
+#pragma unroll
+          for (int d = 0; d < 3; ++d) slot[d] = min(max(2 * py - 1 + d, 0), p.oh - 1) % 3;
+          for (int i = et; i < 63 * 8; i += 32 * kNumEpi) {
             const int jl = i >> 3, vv = i & 7;
             const int px = cur.strip * 63 + jl;
             if (px < p.pool_pw) {
               __half2 m[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) m[e] = __float2half2_rn(0.0f);
-              for (int yy = y_lo; yy <= y_hi; ++yy) {
-                const uint8_t* rr = ring + (yy % 3) * kWsRingRow + (2 * jl) * kWsRingPitch + vv * 16;
+#pragma unroll
+              for (int d = 0; d < 3; ++d) {
+                const uint8_t* rr = ring + slot[d] * kWsRingRow + (2 * jl) * kWsRingPitch + vv * 16;
 #pragma unroll
                 for (int dxp = 0; dxp < 3; ++dxp) {
                   const uint4 t = *reinterpret_cast<const uint4*>(rr + dxp * kWsRingPitch);
@@ -1020,7 +1037,7 @@ stem_s2d_ws_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_co
               *reinterpret_cast<uint4*>(yrow + static_cast<size_t>(px) * COUT + vv * 8) = *reinterpret_cast<const uint4*>(m);
             }
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");              // ring rows may be overwritten by the next tiles
+          asm volatile("bar.sync 1, 256;" ::: "memory");              // ring rows may be overwritten by the next tiles
         }
       } else {
       __half* yrow = p.y + ((static_cast<size_t>(cur.img) * p.oh + cur.oy) * p.ow) * COUT;
