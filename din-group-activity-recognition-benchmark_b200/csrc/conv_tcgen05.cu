@@ -87,6 +87,8 @@ struct ConvKParams {
   // (the pool branch: its average pool + bias + ReLU run after the GEMM).  All three are multiples of 32.
   int split_col, y2_c_stride, norelu_lo, norelu_hi;
   void* y2;
+  int direct_store;           // 1: every lane stores its own pixel's 32 channels as two 256-bit stores (no transpose)
+  int res256;                 // 1: the residual's pixel rows are 32-byte aligned: two 256-bit loads per lane instead of four
 };
 
 constexpr int kBM = 128;
@@ -129,11 +131,14 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvKParams& p, uint32
     const int q = warp & 3;
     const int chunk_sel = (warp - 4) >> 2;
     uint8_t* scratch = epi_scratch + (warp - 4) * kEpiScratch;
-    // Store side of the transpose: after the scratch round-trip, lane l writes 16-byte unit (l & 3) of
-    // pixel slot (l >> 2) + 8*k (k = 0..3) — i.e. four lanes write one pixel's 64 contiguous bytes, so
-    // every global store instruction covers full 32-byte sectors (no partial-sector read-modify-write).
+    // Store side of the transpose: after the scratch round-trip, lane l writes 16-byte unit (l >> 3) of
+    // pixel slot (l & 7) + 8*k (k = 0..3) — i.e. four lanes write one pixel's 64 contiguous bytes, so
+    // every global store instruction covers full 32-byte sectors (no partial-sector read-modify-write), and the eight
+    // lanes of a quarter warp read eight different rows of the 80-byte-pitch scratch: 16-byte bank groups 0, 5, 2, 7,
+    // 4, 1, 6, 3 (with unit = l & 3 / slot = l >> 2 a quarter warp read two rows whose 64 bytes overlap in banks 0..3:
+    // every read took two wavefronts, 120 of a 64 -> 64 tile's 656 LSU wavefronts).
     // With the fused pool only 8 lanes of the warp hold a pooled pixel: one store instruction.
-    const int unit = lane & 3;
+    const int unit = lane >> 3;
     int src_lane[4];   // which lane's (= which tile pixel's) row this lane stores in round k
     int n_rounds;
     if (p.pool2) {
@@ -143,7 +148,7 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvKParams& p, uint32
       n_rounds = 1;
     } else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) src_lane[k] = (lane >> 2) + 8 * k;
+      for (int k = 0; k < 4; ++k) src_lane[k] = (lane & 7) + 8 * k;
       n_rounds = 4;
     }
     int it = 0;
@@ -187,6 +192,34 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvKParams& p, uint32
         }
       }
 
+      // the residual of this lane's pixel is requested BEFORE the wait for the accumulator (and the next chunk's right
+      // after the current one is consumed): loaded after the wait, its DRAM latency sat on the epilogue's critical path and
+      // a 64 -> 64 ResNet layer took 0.77 ms with the residual against 0.49 ms without
+      // (a lane's 64 bytes sit in a 128-byte line of their own, so every load instruction of the warp touches 32 lines:
+      // 32 cycles of the L1 tag stage each -- with four 128-bit loads per lane that was ~1000 cycles per 64 -> 64 tile on
+      // top of the ~2300 of the same layer without a residual; 256-bit loads halve it)
+      uint4 rres[4];
+      auto load_residual = [&](int c0r) {
+        const int colr = n0 + c0r;
+        if (p.residual != nullptr && valid_own && colr < p.c_out) {
+          const __half* rp = p.residual + pix_own_of() * p.y_c_stride + colr;
+          if (p.res256) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              if (colr + 16 * j < p.c_out)
+                asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                             : "=r"(rres[2 * j].x), "=r"(rres[2 * j].y), "=r"(rres[2 * j].z), "=r"(rres[2 * j].w),
+                               "=r"(rres[2 * j + 1].x), "=r"(rres[2 * j + 1].y), "=r"(rres[2 * j + 1].z),
+                               "=r"(rres[2 * j + 1].w)
+                             : "l"(rp + 16 * j));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (colr + 8 * j < p.c_out) rres[j] = __ldg(reinterpret_cast<const uint4*>(rp + 8 * j));
+          }
+        }
+      };
+      load_residual(32 * chunk_sel);
       mbar_wait_relaxed(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
@@ -210,11 +243,10 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvKParams& p, uint32
           }
         }
         if (p.residual != nullptr && valid_own) {
-          const __half* rp = p.residual + pix_own_of() * p.y_c_stride + col0;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             if (col0 + j < p.c_out) {
-              const uint4 rr = __ldg(reinterpret_cast<const uint4*>(rp + j));
+              const uint4 rr = rres[j >> 3];
               const __half2* h2 = reinterpret_cast<const __half2*>(&rr);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -229,6 +261,7 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvKParams& p, uint32
               }
             }
           }
+          if (c0 + 64 < BN) load_residual(c0 + 64);
         }
         if (p.out_f32) {
           if (p.relu) {
@@ -272,6 +305,23 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvKParams& p, uint32
 #pragma unroll
             for (int u4 = 0; u4 < 4; ++u4)
               if (col0 + u4 * 8 < p.c_out) reinterpret_cast<uint4*>(yp)[u4] = *reinterpret_cast<uint4*>(&h[4 * u4]);
+          }
+          continue;
+        }
+        if (p.direct_store) {
+          // own pixel, 64 contiguous bytes as two 256-bit stores (full sectors): no shared-memory round trip
+          if (valid_own) {
+            const bool second = col0 >= p.split_col;                     // warp-uniform (32-column granularity)
+            __half* yp = reinterpret_cast<__half*>(second ? p.y2 : p.y) + (second ? col0 - p.split_col : col0) +
+                         pix_own_of() * static_cast<size_t>(second ? p.y2_c_stride : p.y_c_stride);
+            const uint32_t* hu = reinterpret_cast<const uint32_t*>(h);
+#pragma unroll
+            for (int u8 = 0; u8 < 2; ++u8)
+              if (col0 + u8 * 16 < p.c_out)
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(yp + u8 * 16),
+                             "r"(hu[8 * u8]), "r"(hu[8 * u8 + 1]), "r"(hu[8 * u8 + 2]), "r"(hu[8 * u8 + 3]),
+                             "r"(hu[8 * u8 + 4]), "r"(hu[8 * u8 + 5]), "r"(hu[8 * u8 + 6]), "r"(hu[8 * u8 + 7])
+                             : "memory");
           }
           continue;
         }
@@ -1587,6 +1637,20 @@ int conv2d_launch(const DinConvDesc* d, const void* x, const void* w_packed, con
   p.bias = bias; p.residual = static_cast<const __half*>(residual); p.res_mask = res_mask; p.y = y;
   p.split_col = br ? br->split_col : INT32_MAX; p.y2 = y2; p.y2_c_stride = br ? br->y2_c_stride : 0;
   p.norelu_lo = br ? br->norelu_lo : 0; p.norelu_hi = br ? br->norelu_hi : 0;
+  {
+    // 256-bit per-lane stores instead of the shared-memory transpose (needs 32-byte aligned pixel rows).  The transposed
+    // store touches 8 lines per instruction, the direct one 32 (L1 tag stage), but it costs no shared-memory wavefronts, and
+    // the narrow-N layers are bound by exactly those (tensor-core operand reads + LSU share one data pipe): 64 -> 64 at
+    // 180x320 0.50 -> 0.45 ms per 107 frames, 64 -> 128 at 360x640 3.06 -> 2.31 ms per 80; at N >= 192 the two are equal
+    // within the clock noise and the transpose stays.  DIN_CONV_DIRECT_STORE=0 / 1 forces one path (A/B).
+    static const int want = [] { const char* e = std::getenv("DIN_CONV_DIRECT_STORE"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
+    const bool al = (reinterpret_cast<uintptr_t>(y) & 31) == 0 && d->y_c_stride % 16 == 0 && d->c_out % 16 == 0 &&
+                    (!br || ((reinterpret_cast<uintptr_t>(y2) & 31) == 0 && br->y2_c_stride % 16 == 0));
+    const bool on = want < 0 ? bn <= 128 : want == 1;
+    p.direct_store = (on && al && !d->pool2 && !d->out_f32) ? 1 : 0;
+    p.res256 = (residual && (reinterpret_cast<uintptr_t>(residual) & 31) == 0 && d->y_c_stride % 16 == 0 &&
+                d->c_out % 16 == 0) ? 1 : 0;
+  }
 
   // A staging geometry
   uint32_t box_w, box_h;
