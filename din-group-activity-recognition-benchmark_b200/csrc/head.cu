@@ -10,6 +10,7 @@
 //   fusion + dpi_nl           infer_model.py:203-216 (volleyball), :1298-1301 (collective)
 //   read-out                  infer_model.py:224-232 (volleyball), :1311-1313 (collective)
 #include <cfloat>
+#include <cstdio>
 #include <cstdlib>
 
 #include <cooperative_groups.h>
@@ -748,6 +749,10 @@ readout_kernel(const float* __restrict__ s, const float* __restrict__ w, const f
   __shared__ float score[64];        // A <= 64 running sum over frames
   const int b = blockIdx.x;
   const int Nb = n_valid ? min(__ldg(n_valid + b), N) : N;
+  if (Nb < 1) {   // the reference's torch.max over an empty actor axis raises (infer_model.py:1311); -FLT_MAX logits would not
+    if (threadIdx.x == 0) printf("din_readout_f32: clip %d has no valid actor\n", b);
+    __trap();
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < 64) score[threadIdx.x] = 0.0f;
   for (int t = 0; t < T; ++t) {

@@ -11,6 +11,7 @@
 // device memory until the caller reads them (once per epoch).  The same launch writes d(loss)/d(logits), the
 // seed of the backward pass.
 #include <cfloat>
+#include <cstdio>
 
 #include "din_common.cuh"
 
@@ -48,7 +49,12 @@ ce_metrics_kernel(const float* __restrict__ logits, const long long* __restrict_
     float se = 0.0f;
     for (int j = 0; j < A; ++j) se += expf(z[j] - m);
     const float lse = logf(se);                              // log_softmax_j = (z_j - m) - lse, as torch
-    const bool y_ok = y >= 0 && y < A;                       // out-of-range labels contribute nothing
+    // torch: ignore_index = -100 contributes nothing, any other label outside [0, A) is a device-side assert
+    const bool y_ok = y >= 0 && y < A;
+    if (!y_ok && y != -100) {
+      printf("din_ce_metrics_f32: label %d of sample %d is outside [0, %d)\n", y, i, A);
+      __trap();
+    }
     const float w = y_ok ? (class_weight ? class_weight[y] : 1.0f) : 0.0f;
     if (y_ok) {
       nll_w += w * -((z[y] - m) - lse);

@@ -257,3 +257,25 @@ def test_stage1_training_step_resnet18(cuda, backbone):
     assert abs(loss.item() - ref_loss.item()) <= 2e-3 * max(1.0, abs(ref_loss.item()))
     assert worst <= 2e-1, worst
     assert rel_l2(got["fc_actions.weight"], ref_grads["fc_actions.weight"]) <= 1e-2
+
+
+def test_cross_entropy_label_range(cuda):
+    """F.cross_entropy: ignore_index = -100 contributes nothing, any other label outside [0, A) is a device-side assert.
+    Same here (the assert kills the CUDA context, so that half runs in a child process)."""
+    import subprocess
+    import sys
+    from din_b200 import metrics
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn(6, 8, generator=g)
+    labels = torch.tensor([1, -100, 7, 0, -100, 3])
+    ref = F.cross_entropy(logits, labels)
+    got = metrics.cross_entropy(logits.cuda(), labels.cuda())
+    assert abs(got.item() - ref.item()) <= 1e-5 * max(1.0, abs(ref.item()))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, torch; sys.path.insert(0, %r); from din_b200 import metrics; "
+            "l = metrics.cross_entropy(torch.zeros(2, 8, device='cuda'), torch.tensor([1, 8], device='cuda')); "
+            "torch.cuda.synchronize(); print('no error', l.item())"
+            % os.path.join(root, "din-group-activity-recognition-benchmark_b200"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "no error" not in r.stdout, (r.returncode, r.stdout, r.stderr[-400:])
+    assert "outside [0, 8)" in r.stdout + r.stderr

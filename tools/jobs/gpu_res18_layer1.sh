@@ -2,11 +2,9 @@
 O=gpurun_out/l1; mkdir -p $O
 python tools/probes/res18_layer1_probe.py
 timeout 900 python -m pytest tests/test_conv_gpu.py tests/test_conv_bwd_gpu.py -m gpu -q -x -p no:cacheprovider 2>&1 | tail -3
-for m in 0 1; do
-DIN_CONV_DIRECT_STORE=$m timeout 600 python bench.py --workload volleyball_inv3_full_T10_N12_720p --no-cpu-baseline --no-train-step --no-ingest > $O/b_inv3_$m.json 2> $O/b_inv3_$m.err
+for w in volleyball_inv3_full_T10_N12_720p volleyball_res18_lite128_T10_N12_720p volleyball_vgg16_lite128_T10_N12_720p; do
+timeout 600 python bench.py --workload $w --no-cpu-baseline --no-train-step --no-ingest > $O/b_$w.json 2> $O/b_$w.err
 done
-timeout 600 python bench.py --workload volleyball_inv3_full_T10_N12_720p --no-cpu-baseline --no-train-step --no-ingest > $O/b_inv3_auto.json 2> $O/b_inv3_auto.err
-timeout 600 python bench.py --workload volleyball_res18_lite128_T10_N12_720p --no-cpu-baseline --no-train-step --no-ingest > $O/b_res18_auto.json 2> $O/b_res18_auto.err
 python - <<'PY'
 import json,glob
 for f in sorted(glob.glob('gpurun_out/l1/b_*.json')):
