@@ -39,7 +39,7 @@ constexpr int kEpiPitch = 80;            // bytes per pixel row in the store-tra
 
 struct StemParams {
   int pool_ph, pool_pw;   // stem_s2d_ws_kernel<U8, POOL = true>: extent of the MaxPool2d(3, 2, 1) output that y holds
-  int pool_strips;        //   ceil(pool_pw / 63): strips of 63 pooled = 128 conv pixels (one overlapping)
+  int pool_strips;        //   ceil(ow / 128): strips of 128 conv = 64 pooled pixels (the first one shared with the strip to the left)
   const void* x;          // fp32 NCHW [n,3,h,w]  or (U8) uint8 NHWC [n,h,w,3]
   const float* w; const float* bias; __half* y;
   int n, h, w_in, oh, ow, pad, relu, prep;
@@ -754,11 +754,15 @@ constexpr int kWsPatchStage = 26112;
 constexpr size_t kWsSmem = 1024 + kWsPatchStages * kWsPatchStage + 2 * 2 * kS2dVPlane + 16 * kS2dWTap + kWsEpiWarps * 32 * kEpiPitch + 256;
 // POOL: resnet18.maxpool (MaxPool2d(3, 2, 1), backbone.py:115-132) fused into the stem.  The kernel is bound by its OUTPUT
 // writes (3.2 GB per 107 frames at 720p, 3.1 TB/s of the part's ~3.95 TB/s write-only rate), and the pool throws three
-// quarters of them away: here a CTA owns a strip of 63 pooled = 128 convolution pixels (conv x = 126 * strip - 1 + r) and
-// walks the rows of one image top to bottom, its epilogue warps keep the last three ReLU'd convolution rows in a shared
-// memory ring and emit one pooled row for every second convolution row.  Padding: a ReLU output is >= 0 and every window
-// holds a real pixel, so positions outside the image enter the maximum as 0.
-constexpr int kWsPoolStride = 126;               // convolution pixels between strips (63 pooled pixels)
+// quarters of them away: here a CTA owns a strip of 128 convolution pixels (conv x = 128 * strip + r, the geometry of the
+// kernel without the pool) and walks the rows of one image top to bottom, its epilogue warps keep the last three ReLU'd
+// convolution rows in a shared memory ring and emit one pooled row for every second convolution row.  Pooled pixel
+// 64 * strip + jl covers ring columns 2 jl - 1 .. 2 jl + 1: jl = 1 .. 63 are complete inside the strip; jl = 0 also needs
+// the LAST column of the strip to the left, so for strip > 0 both strips fold their share into y with a 16-byte
+// red.global.max (REDG.E.MAX.F16x8) over a pixel that stem_pool_zero_kernel cleared before the launch -- exact: the maximum
+// is associative and every ReLU output is >= 0.  (First version: strips of 126 convolution = 63 complete pooled pixels, one
+// column overlapping: 1280-wide frames needed SIX strips for 5.08 strips' worth of pixels, 17 % of all tiles nearly empty.)
+// Padding: a ReLU output is >= 0 and every window holds a real pixel, so positions outside the image enter the maximum as 0.
 constexpr int kWsRingPitch = 144;                // bytes per pixel in the ring: 128 + 16 (bank spread for 16-byte stores)
 constexpr int kWsRingRow = 128 * kWsRingPitch;
 constexpr size_t kWsPoolSmem = kWsSmem + 3 * kWsRingRow;
@@ -796,8 +800,8 @@ __global__ void __launch_bounds__(kWsThreads, 1)
 stem_s2d_ws_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_constant__ CUtensorMap tmap_b,
                    const StemParams p) {
   constexpr int COUT = 64;
-  constexpr int kStripStride = POOL ? kWsPoolStride : 128;     // convolution pixels between strips
-  constexpr int kXShift = POOL ? 1 : 0;                         // the strip starts one pixel to the left of its stride
+  constexpr int kStripStride = 128;                             // convolution pixels between strips
+  constexpr int kXShift = 0;
   constexpr int kWsBuilders = WsRoles<POOL>::kBuilders, kWsEpiWarp0 = WsRoles<POOL>::kEpiWarp0;
   constexpr int kNumEpi = WsRoles<POOL>::kEpiWarps;
   extern __shared__ uint8_t smem_raw[];
@@ -868,11 +872,11 @@ stem_s2d_ws_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_co
         const int gx0 = (cur.strip * kStripStride - kXShift) * 2 - 4;
         mbar_wait_relaxed(&patch_empty[ps], ((j / kWsPatchStages) & 1) ^ 1);
         if constexpr (U8) {
-          const int p0 = POOL ? gx0 - (gx0 & 15) : gx0 - 12;              // first pixel of the box: a multiple of 16
+          const int p0 = gx0 - 12;                                         // first pixel of the box: a multiple of 16
           mbar_arrive_expect_tx(&patch_full[ps], 8u * kWsBoxU8);
           tma_load_3d(patch_s + ps * kWsPatchStage, &tmap_img, &patch_full[ps], (p0 * 3) / 4, cur.oy * 2 - 3, cur.img);
         } else {
-          const int c0 = gx0 - (POOL ? 2 : 0);                           // 252 * strip - 8: a multiple of 4 columns
+          const int c0 = gx0;                                              // 256 * strip - 4: a multiple of 4 columns
           mbar_arrive_expect_tx(&patch_full[ps], static_cast<uint32_t>(kWsPatchBytes));
           tma_load_3d(patch_s + ps * kWsPatchStage, &tmap_img, &patch_full[ps], c0, cur.oy * 2 - 3, cur.img * 3);
           tma_load_3d(patch_s + ps * kWsPatchStage + kWsBlockA, &tmap_b, &patch_full[ps], c0 + kWsBoxBStart, cur.oy * 2 - 3,
@@ -921,7 +925,7 @@ stem_s2d_ws_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_co
       // input coordinates of (ty = 0, dy = 0) / (X = 0, dx = 0)
       const int iy0 = cur.oy * 2 - 3, gx0 = (cur.strip * kStripStride - kXShift) * 2 - 4;
       // offset of input column gx0 inside the loaded box (see the producer)
-      const int boff = U8 ? (POOL ? (gx0 & 15) : 12) : (POOL ? 2 : 0);
+      const int boff = U8 ? 12 : 0;
       for (int v = bt; v < 4 * kS2dVecs; v += 32 * kWsBuilders) {
         const int ty = v / kS2dVecs, X = v - ty * kS2dVecs;
         const bool in_a = X < kWsSplitX;
@@ -987,8 +991,8 @@ stem_s2d_ws_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_co
       if constexpr (POOL) {
         // this lane's convolution pixel -> the ring (zeros outside the image), then every second row one pooled row
         const int r = q * 32 + lane;
-        const int cx = cur.strip * kWsPoolStride - 1 + r;
-        const bool inside = cx >= 0 && cx < p.ow;
+        const int cx = cur.strip * 128 + r;
+        const bool inside = cx < p.ow;
         uint8_t* dst = ring + (cur.oy % 3) * kWsRingRow + r * kWsRingPitch;
         {
           uint32_t v[32];
@@ -1016,25 +1020,36 @@ stem_s2d_ws_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_co
           int slot[3];
 #pragma unroll
           for (int d = 0; d < 3; ++d) slot[d] = min(max(2 * py - 1 + d, 0), p.oh - 1) % 3;
-          for (int i = et; i < 63 * 8; i += 32 * kNumEpi) {
+          // items 0 .. 511: pooled pixel jl = i >> 3 of the strip, 8 channels vv; items 512 .. 519: the strip's last column
+          // (r = 127) folded into pooled pixel 0 of the strip to the right
+          for (int i = et; i < 65 * 8; i += 32 * kNumEpi) {
             const int jl = i >> 3, vv = i & 7;
-            const int px = cur.strip * 63 + jl;
+            const int px = cur.strip * 64 + jl;
             if (px < p.pool_pw) {
+              const int r0 = jl == 64 ? 127 : max(2 * jl - 1, 0), r1 = jl == 64 ? 127 : 2 * jl + 1;
               __half2 m[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) m[e] = __float2half2_rn(0.0f);
 #pragma unroll
               for (int d = 0; d < 3; ++d) {
-                const uint8_t* rr = ring + slot[d] * kWsRingRow + (2 * jl) * kWsRingPitch + vv * 16;
+                const uint8_t* rr = ring + slot[d] * kWsRingRow + vv * 16;
 #pragma unroll
                 for (int dxp = 0; dxp < 3; ++dxp) {
-                  const uint4 t = *reinterpret_cast<const uint4*>(rr + dxp * kWsRingPitch);
+                  const int r = min(r0 + dxp, r1);                    // a repeated column leaves the maximum unchanged
+                  const uint4 t = *reinterpret_cast<const uint4*>(rr + r * kWsRingPitch);
                   const __half2* th = reinterpret_cast<const __half2*>(&t);
 #pragma unroll
                   for (int e = 0; e < 4; ++e) m[e] = __hmax2(m[e], th[e]);
                 }
               }
-              *reinterpret_cast<uint4*>(yrow + static_cast<size_t>(px) * COUT + vv * 8) = *reinterpret_cast<const uint4*>(m);
+              __half* dst = yrow + static_cast<size_t>(px) * COUT + vv * 8;
+              const uint4 mv = *reinterpret_cast<const uint4*>(m);
+              if (jl == 64 || (jl == 0 && cur.strip > 0))
+                asm volatile("red.global.max.noftz.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(mv.x), "r"(mv.y), "r"(mv.z),
+                             "r"(mv.w)
+                             : "memory");
+              else
+                *reinterpret_cast<uint4*>(dst) = mv;
             }
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");              // ring rows may be overwritten by the next tiles
@@ -1080,6 +1095,17 @@ stem_s2d_ws_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid_co
   }
 }
 
+// pooled pixels 64, 128, ... of every row are reduced into by two strips (red.global.max): cleared first
+__global__ void stem_pool_zero_kernel(__half* __restrict__ y, long long rows, int pool_pw, int shared_px) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // (row, shared pixel, 16-byte unit)
+  if (i >= rows * shared_px * 8) return;
+  const int vv = static_cast<int>(i & 7);
+  const long long t = i >> 3;
+  const int k = static_cast<int>(t % shared_px);
+  const long long row = t / shared_px;
+  reinterpret_cast<uint4*>(y + (row * pool_pw + 64 * (k + 1)) * 64)[vv] = make_uint4(0, 0, 0, 0);
+}
+
 template <bool U8, bool POOL = false>
 int launch_s2d_ws(StemParams& p, cudaStream_t st) {
   CUtensorMap timg, timg_b;
@@ -1111,6 +1137,11 @@ int launch_s2d_ws(StemParams& p, cudaStream_t st) {
   if constexpr (POOL) {
     const long long tasks = static_cast<long long>(p.n) * p.pool_strips;
     if (grid > tasks) grid = tasks;
+    const int shared_px = (p.pool_pw - 1) / 64;                       // pooled pixels 64 k, k >= 1
+    if (shared_px > 0) {
+      const long long rows = static_cast<long long>(p.n) * p.pool_ph, items = rows * shared_px * 8;
+      stem_pool_zero_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, st>>>(p.y, rows, p.pool_pw, shared_px);
+    }
     DIN_OPT_IN_SMEM((stem_s2d_ws_kernel<U8, true>), kWsPoolSmem);
     stem_s2d_ws_kernel<U8, true><<<static_cast<int>(grid), kWsThreads, kWsPoolSmem, st>>>(timg, timg_b, p);
   } else {
@@ -1407,7 +1438,7 @@ int din_stem_pool_tc_launch(const void* x, int x_is_u8, const float* w, const fl
   p.pad = 3; p.relu = 1; p.prep = prep;
   p.pool_ph = (p.oh - 1) / 2 + 1;
   p.pool_pw = (p.ow - 1) / 2 + 1;
-  p.pool_strips = (p.pool_pw + 62) / 63;
+  p.pool_strips = (p.ow + 127) / 128;
   p.strips_per_row = p.pool_strips;
   const long long tiles = static_cast<long long>(n) * p.oh * p.pool_strips;
   if (tiles >= INT32_MAX) return din_set_error(DIN_ERR_INVALID_ARG, "din_stem_conv_pool: too many tiles");
