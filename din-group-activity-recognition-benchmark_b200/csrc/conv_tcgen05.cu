@@ -347,9 +347,14 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvKParams& p, uint32
         }
         __syncwarp();
       }
+      // one arrival per WARP (every lane has fenced its TMEM reads before the warp barrier): with one per thread the leader's
+      // barrier took 512 arrivals per tile pair, 256 of them remote (64 -> 64: 0.458 -> 0.445 ms per 107 frames)
       tc_fence_before_sync();
-      if constexpr (TWO_CTA) mbar_arrive_cluster(&tmem_empty[acc], 0);   // the leader CTA's barrier (it issues the MMAs)
-      else mbar_arrive(&tmem_empty[acc]);
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (TWO_CTA) mbar_arrive_cluster(&tmem_empty[acc], 0);   // the leader CTA's barrier (it issues the MMAs)
+        else mbar_arrive(&tmem_empty[acc]);
+      }
     }
   }
 }
@@ -388,7 +393,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < p.n_a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < p.n_b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 32 * kNumEpiWarps); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], kNumEpiWarps); }
     fence_mbar_init();
   }
   if (warp == 3) {
@@ -622,7 +627,7 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < p.n_a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < p.n_b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 2 * 32 * kNumEpiWarps); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 2 * kNumEpiWarps); }
     fence_mbar_init();
   }
   if (warp >= 4) {
@@ -885,7 +890,7 @@ conv1_fused_2cta_kernel(const __grid_constant__ CUtensorMap tmap_img, const __gr
     for (int s = 0; s < kFusedAStages; ++s) { mbar_init(&a_full[s], 8); mbar_init(&a_empty[s], 1); }
     mbar_init(&b_full[0], 1);
     for (int a = 0; a < 2; ++a) {
-      mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 2 * 32 * kNumEpiWarps);
+      mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 2 * kNumEpiWarps);
       mbar_init(&col_full[a], 8); mbar_init(&stem_done[a], 1); mbar_init(&stem_free[a], 8);
     }
     for (int s = 0; s < kPatchStages; ++s) { mbar_init(&patch_full[s], 1); mbar_init(&patch_empty[s], 4); }
