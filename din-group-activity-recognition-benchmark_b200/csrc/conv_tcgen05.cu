@@ -220,6 +220,22 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvKParams& p, uint32
         }
       };
       load_residual(32 * chunk_sel);
+      if (p.residual != nullptr && ti + tile_step < tile_limit) {
+        // ... and the NEXT tile's residual lines are pulled into L2 now: this warp is back here ~200 cycles after its previous
+        // tile (the epilogue is the slower role of these layers), far less than a DRAM round trip, so the loads above still
+        // waited ~900 cycles per tile (per-role counters: epilogue busy 1950 cycles per tile against 1070 without a residual)
+        const int tile_n = TWO_CTA ? 2 * (ti + tile_step) + cta_rank : ti + tile_step;
+        const int mt_n = fdiv(tile_n, p.fd_ntn);
+        const int img_n = fdiv(mt_n, p.fd_tpi);
+        const int r_n = mt_n - img_n * p.tiles_per_img;
+        const int tyi_n = fdiv(r_n, p.fd_tx);
+        const int oy_n = tyi_n * p.th + (m_own >> p.tw_log2), ox_n = (r_n - tyi_n * p.tiles_x) * p.tw + (m_own & (p.tw - 1));
+        if (tile_n < p.num_tiles && oy_n < p.oh && ox_n < p.ow) {
+          const __half* rp = p.residual + ((static_cast<size_t>(img_n) * p.oh + oy_n) * p.ow + ox_n) * p.y_c_stride +
+                             (tile_n - mt_n * p.n_tiles_n) * BN;
+          for (int c0 = 32 * chunk_sel; c0 < BN; c0 += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + c0));
+        }
+      }
       mbar_wait_relaxed(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
