@@ -157,7 +157,7 @@ def build_model(pc, device):
     return model.to(device).eval(), sd, bb
 
 
-def train_step_info(model, pc, dev, images_d, boxes_d, clips, steps=5, warmup=2, dist=None):
+def train_step_info(model, pc, dev, images_d, boxes_d, clips, steps=5, warmup=4, dist=None):
     """Supplementary (NOT the headline metric): one stage-2 TRAINING step -- train-mode forward, on-device
     cross-entropy, backward through the head and the VGG-16 / ResNet-18 backbone -- on `clips` clips
     (scripts/train_volleyball_stage2_dynamic.py:42 batch_size = 2), followed by torch's SGD step with lr = 0: the update
