@@ -19,6 +19,7 @@ nl_emb_1 -> ReLU -> (point_conv -> point_ln -> ReLU) -> DPI -> fuse + dpi_nl -> 
 from __future__ import annotations
 
 import os
+import threading
 
 import torch
 
@@ -108,7 +109,15 @@ def _plan_tensor(v, device):
     return t
 
 
-_INFERENCE = [False]        # True while DinEngine.features() (the no-grad inference forward) runs a backbone plan
+class _InferenceFlag(threading.local):
+    """True while DinEngine.features() (the no-grad inference forward) runs a backbone plan -- per THREAD: nn.DataParallel
+    runs one replica per device in concurrent threads, and with a process-wide flag the replica that finished first switched
+    the other one's remaining small launches from the exact (hi + lo) weights to the single-part ones (logits 5e-4 apart from
+    the single-device result: tests/test_dropin_gpu.py::test_data_parallel_two_devices_one_plan_per_device)."""
+    on = False
+
+
+_INFERENCE = _InferenceFlag()
 
 
 class _Conv:
@@ -140,7 +149,7 @@ class _Conv:
         # inference plans only: a training step re-packs every weight after the optimizer step, and packing a second
         # (hi + lo) copy of the late layers each step cost ResNet-18's step 47 ms of packing kernels (measured)
         px = x.shape[0] * x.shape[1] * x.shape[2]
-        if (not _INFERENCE[0] or self.split == 2 or px > SMALL_LAUNCH_PIXELS * self.stride * self.stride
+        if (not _INFERENCE.on or self.split == 2 or px > SMALL_LAUNCH_PIXELS * self.stride * self.stride
                 or (x.shape[0] == 1 and x.shape[1] == 1 and 2.0 * px * self.w_src.numel() > SMALL_LAUNCH_FLOPS)):
             return self.w
         if self._w_exact is None:
@@ -711,7 +720,7 @@ class DinEngine:
         fm = self._fm_cache[1]
         per_chunk = frames_per_chunk(self.backbone_name, F_, H, W, self.frames_per_chunk)
         host = not images_flat.is_cuda
-        _INFERENCE[0] = True
+        _INFERENCE.on = True
         try:
             for f0 in range(0, F_, per_chunk):
                 f1 = min(F_, f0 + per_chunk)
@@ -723,7 +732,7 @@ class DinEngine:
                     slot["freed"] = torch.cuda.Event()
                     slot["freed"].record(torch.cuda.current_stream())
         finally:
-            _INFERENCE[0] = False
+            _INFERENCE.on = False
         if self._pending_small is not None:                          # boxes / actor counts staged by stage_small()
             torch.cuda.current_stream().wait_event(self._pending_small)
             self._pending_small = None

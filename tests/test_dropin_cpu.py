@@ -138,3 +138,17 @@ def test_plan_cache_handles_replicas_and_copies():
     assert pc.owner_of(c) is c and c._plans is not m._plans and c._plans.builds == 0
     m._plans.put(torch.device("cpu"), key=1)
     assert m._plans.builds == 1 and m._plans.get(torch.device("cpu"))["key"] == 1
+
+
+def test_inference_flag_is_per_thread():
+    """nn.DataParallel runs replicas in concurrent threads: the flag that marks the no-grad inference forward must not leak
+    from one thread into another (it selects the exact-weight copies of latency-bound launches)."""
+    import threading
+    from din_b200 import engine
+    engine._INFERENCE.on = True
+    seen = []
+    t = threading.Thread(target=lambda: seen.append(engine._INFERENCE.on))
+    t.start()
+    t.join()
+    engine._INFERENCE.on = False
+    assert seen == [False]

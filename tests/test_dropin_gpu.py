@@ -102,3 +102,15 @@ def test_data_parallel_two_devices_one_plan_per_device(cuda):
     loss = torch.nn.functional.cross_entropy(dp((images, boxes))["activities"], torch.tensor([0, 1, 2, 3], device=cuda))
     loss.backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters() if p.requires_grad)
+
+
+def test_logits_do_not_depend_on_batch_composition(cuda):
+    """A clip's logits are the same whether it runs in a batch of 4 or of 2 (what nn.DataParallel's scatter does to it; the
+    concurrent-replica side of that is test_data_parallel_two_devices_one_plan_per_device and, for the per-thread
+    inference flag, tests/test_dropin_cpu.py::test_inference_flag_is_per_thread)."""
+    model, images, boxes = _small_model(cuda)
+    model.eval()
+    with torch.no_grad():
+        want = model((images, boxes))["activities"]
+        halves = [model((images[i:i + 2].contiguous(), boxes[i:i + 2].contiguous()))["activities"] for i in (0, 2)]
+    assert torch.equal(torch.cat(halves), want)
