@@ -89,7 +89,10 @@ struct ConvKParams {
   void* y2;
   int direct_store;           // 1: every lane stores its own pixel's 32 channels as two 256-bit stores (no transpose)
   int res256;                 // 1: the residual's pixel rows are 32-byte aligned: two 256-bit loads per lane instead of four
+  int bias_tc;                // CTA-pair kernel: the bias enters the accumulator through one extra K = 16 MMA per tile
+                              // (ones x [bias_hi, bias_lo]), the epilogue adds nothing
 };
+constexpr int kBiasTcSmem = 4096 + 192 * 16 + 16;   // ones tile + bias tile of the bias MMA (+ alignment)
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;                    // fp16 elements per K step = one 128-byte swizzle row
@@ -97,6 +100,7 @@ constexpr int kNumThreads = 384;            // 4 role warps + 8 epilogue warps
 constexpr int kNumEpiWarps = 8;
 constexpr int kSmemBudget = 192 * 1024;    // operand rings; barriers and alignment slack come on top
 constexpr int kMaxStages = 16;
+constexpr size_t kSmemOptIn = kSmemBudget + 8 * 2560 + 4096 + 8192;   // dynamic shared memory the kernels opt in to (224 KB)
 
 constexpr int kEpiPitch = 80;             // bytes per pixel row in the epilogue transpose scratch (64 + 16 pad)
 constexpr int kEpiScratch = 32 * kEpiPitch;  // per epilogue warp
@@ -250,7 +254,7 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvKParams& p, uint32
         if (c0 + 64 < BN) tmem_ld_32x32b_x32(taddr + c0 + 64, v);   // prefetch this warp's next chunk
         const int col0 = n0 + c0;
         if (col0 >= p.c_out) continue;   // warp-uniform
-        if (p.bias != nullptr) {        // (the fused conv1 kernel adds its bias on the tensor core: p.bias == nullptr)
+        if (p.bias != nullptr && !p.bias_tc) {   // (bias_tc / the fused conv1 kernel: the bias was added on the tensor core)
           const float4* bs = reinterpret_cast<const float4*>(bias_s + col0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -650,6 +654,33 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     for (int c = threadIdx.x - 128; c < BN; c += 32 * kNumEpiWarps)
       bias_s[c] = (p.bias != nullptr && c < p.c_out) ? __ldg(p.bias + c) : 0.0f;
   }
+  // The bias on the tensor core (p.bias_tc): D = ones[128 x 16] x bt[BN/2 x 16]^T opens every tile's accumulation, with
+  // ones columns (1, 2^-11) against (bias_hi, bias_lo * 2^11) -- both factors normal fp16 numbers, the sum exact to ~22 bits.
+  // Per-role cycle counters on the narrow layers: an epilogue warp spent ~590 cycles per 32-column chunk between its
+  // tcgen05.ld and its stores, most of it in the eight broadcast shared-memory loads of the bias, which queue behind the
+  // tensor core's operand reads in a data pipe that is > 90 % busy; with a residual or at N = 128 the epilogue, not the MMA
+  // warp, set the tile time.  Both tiles: no-swizzle K-major, 16-byte rows, K chunk planes 2048 B (A) / BN/2 * 16 B (B) apart.
+  uint8_t* ones_s = reinterpret_cast<uint8_t*>(bias_s + BN);
+  ones_s += (16u - (smem_u32(ones_s) & 15u)) & 15u;
+  uint8_t* bt_s = ones_s + 4096;
+  if (p.bias_tc) {
+    for (int st = threadIdx.x; st < 128; st += kNumThreads) {
+      reinterpret_cast<uint4*>(ones_s)[st] = make_uint4(0x10003C00u, 0u, 0u, 0u);       // fp16 (1, 2^-11), chunk 0 of row st
+      reinterpret_cast<uint4*>(ones_s + 2048)[st] = make_uint4(0u, 0u, 0u, 0u);         // chunk 1
+    }
+    for (int st = threadIdx.x; st < BN; st += kNumThreads) {
+      const int o_local = st % (BN / 2), kc = st / (BN / 2);
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      const int o = rank * (BN / 2) + o_local;
+      if (kc == 0 && o < p.c_out) {
+        const float bv = __ldg(p.bias + o);
+        const float bh = __half2float(__float2half_rn(bv));
+        v.x = pack_half2(bh, (bv - bh) * 2048.0f, false);
+      }
+      reinterpret_cast<uint4*>(bt_s + kc * (BN / 2) * 16)[o_local] = v;
+    }
+    fence_proxy_async_smem();
+  }
   if (warp == 1) tmem_alloc_2cta<kTmemCols>(tmem_ptr_smem);
   tc_fence_before_sync();
   __syncthreads();
@@ -736,6 +767,12 @@ conv_igemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
         uint32_t accum = 0;
+        if (p.bias_tc) {
+          if (leader)
+            umma_f16_ss_2cta(d_tmem, desc_noswz(smem_u32(ones_s), 2048, 128), desc_noswz(smem_u32(bt_s), (BN / 2) * 16, 128),
+                             idesc, 0u);
+          accum = 1;
+        }
         for (int g = 0; g < p.n_cblk; ++g) {
           mbar_wait(&a_full[sa], pa);
           const uint32_t a_lo = a_lo0 + sa * a_step;
@@ -1212,7 +1249,7 @@ conv1_fused_2cta_kernel(const __grid_constant__ CUtensorMap tmap_img, const __gr
 template <int BN, int TB3>
 int launch_conv_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const ConvKParams& p, int grid, size_t smem,
                      cudaStream_t st) {
-  DIN_OPT_IN_SMEM((conv_igemm_2cta_kernel<BN, TB3>), kSmemBudget + kNumEpiWarps * kEpiScratch + 4096 + 8192);
+  DIN_OPT_IN_SMEM((conv_igemm_2cta_kernel<BN, TB3>), kSmemOptIn);
   conv_igemm_2cta_kernel<BN, TB3><<<grid, kNumThreads, smem, st>>>(ta, tb, p);
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;
@@ -1221,7 +1258,7 @@ int launch_conv_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const ConvKPa
 template <int BN, int TB3>
 int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvKParams& p, int grid, size_t smem,
                 cudaStream_t st) {
-  DIN_OPT_IN_SMEM((conv_igemm_kernel<BN, TB3>), kSmemBudget + kNumEpiWarps * kEpiScratch + 4096 + 8192);
+  DIN_OPT_IN_SMEM((conv_igemm_kernel<BN, TB3>), kSmemOptIn);
   conv_igemm_kernel<BN, TB3><<<grid, kNumThreads, smem, st>>>(ta, tb, p);
   DIN_CHECK_CUDA(cudaGetLastError());
   return DIN_OK;
@@ -1742,11 +1779,19 @@ int conv2d_launch(const DinConvDesc* d, const void* x, const void* w_packed, con
   }
   DIN_CHECK_ARG(p.n_a_stages >= 2 && (p.n_b_stages >= 2 || p.b_resident),
                 "din_conv2d_nhwc_f16: filter %dx%d does not fit shared memory", d->kh, d->kw);
-  const size_t smem = static_cast<size_t>(p.n_a_stages) * p.a_stage_bytes +
+  size_t smem = static_cast<size_t>(p.n_a_stages) * p.a_stage_bytes +
                       static_cast<size_t>(p.n_b_stages) * p.tb * b_bytes + kNumEpiWarps * kEpiScratch + 1024 /*align*/ +
                       (4 * kMaxStages + 4) * 8 + 16 + 64 * 4 /*tap offsets*/ +
                       static_cast<size_t>(p.n_tiles_n) * bn * 4 /*bias*/;
 
+  {
+    // DIN_CONV_BIAS_TC=0 keeps the bias in the epilogue of the CTA-pair kernel (A/B)
+    static const bool off = [] { const char* e = std::getenv("DIN_CONV_BIAS_TC"); return e && e[0] == '0'; }();
+    if (two_cta && bias != nullptr && !off && smem + kBiasTcSmem <= kSmemOptIn) {
+      p.bias_tc = 1;
+      smem += kBiasTcSmem;
+    }
+  }
   CUtensorMap ta, tb;
   {
     const uint64_t dims[4] = {static_cast<uint64_t>(d->c_in), static_cast<uint64_t>(d->w),
