@@ -29,15 +29,3 @@ ms = e0.elapsed_time(e1) / reps
 fl = 2 * out.numel() * ci * k * k
 by = (x.numel() + out.numel() * (2 if res is not None else 1)) * 2
 print(f"{n}x{h}x{w} {ci}->{co} k{k}{' +res' if res is not None else ''}: {ms:.3f} ms  {fl / ms / 1e9:.0f} TFLOP/s  {by / ms / 1e6:.0f} GB/s algorithmic")
-if os.environ.get("DIN_FUSED_DEBUG") == "1":       # a -DDIN_PROFILE_ROLES build of the library: per-role cycles of CTA 0
-    from din_b200 import _lib
-    L = _lib.load()
-    L.din_debug_word.restype = __import__("ctypes").c_uint
-    wd = lambda i: int(L.din_debug_word(i))
-    b36, b37 = wd(36), wd(37)
-    ops.conv2d_nhwc(x, wp, b, stride=1, pad=pad, relu=True, residual=res, out=out)
-    torch.cuda.synchronize()
-    tiles = max(wd(32), 1)
-    print(f"  CTA 0: {tiles} tiles; MMA warp per tile: total {wd(33)} cycles, wait tmem_empty {wd(34)}, wait a_full {wd(35)}, "
-          f"MMA issue {wd(38)}, commits {wd(39)}, rest {wd(33) - wd(34) - wd(35) - wd(38) - wd(39)}; epilogue warp 4 per tile: wait tmem_full {(wd(36) - b36) * 16 // tiles}, "
-          f"wait + work {(wd(37) - b37) * 16 // tiles}")
