@@ -299,10 +299,11 @@ def test_training_step_matches_oracle(cuda, name):
     kw = dict(kw)
     pc = _pc(kw.pop("backbone"), kw.pop("hw"), **kw)
     bb = O.build_backbone(pc.backbone)
-    sd = O.make_state_dict(pc, seed=0, backbone=bb)
+    seed = int(os.environ.get("DIN_TEST_SEED", "0"))         # (tolerance studies: the same test over other weights / inputs)
+    sd = O.make_state_dict(pc, seed=seed, backbone=bb)
     O.load_backbone(bb, sd)
     bb.eval()
-    batch = O.make_inputs(pc, B, seed=0)
+    batch = O.make_inputs(pc, B, seed=seed)
     labels = torch.arange(B) % pc.num_activities
     model, cfg = _model_and_cfg(cuda, pc, sd, p)
     model.keep_tape = True
@@ -347,8 +348,11 @@ def test_training_step_matches_oracle(cuda, name):
     print(f"[step {name}] logits max|Δ| {err:.2e}, loss {loss.item():.6f} vs {ref_loss.item():.6f}, worst rel-L2 {worst:.2e}")
     assert err_iso <= 1e-3 * iso_logits.abs().max().item(), ("isolated logits", err_iso)
     # TCE: the heads' downsample2 GEMM (fp16 tensor-core operands) sits between the shared feature map and the softmax of
-    # the attention, which amplifies its rounding: the encoder's gradients agree to ~1e-2 even "in isolation"
-    assert worst_iso <= (3e-2 if pc.tce else ISO_TOL), ("isolated", worst_iso)
+    # the attention, which amplifies its rounding: the encoder's gradients agree to a few 1e-2 even "in isolation", and how
+    # few depends on the realisation -- over DIN_TEST_SEED = 0..4 the worst tensor's relative L2 error was 1.3e-2, 3.8e-2,
+    # 2.3e-2, 2.5e-2, 1.9e-1 with the convolutions' bias in the epilogue and 3.6e-2, 3.4e-2, 3.6e-2, 5.8e-2, 2.6e-2 with
+    # it on the tensor core (profiles/edge_precision_study_r2.md); seed 0 is what runs here
+    assert worst_iso <= (6e-2 if pc.tce else ISO_TOL), ("isolated", worst_iso)
     assert err <= 1e-3 * ref_logits.abs().max().item(), ("logits", err)
     assert abs(loss.item() - ref_loss.item()) <= 2e-3 * max(1.0, abs(ref_loss.item()))
     # TCE: the attention softmax amplifies the fp16 backbone's rounding (emb_roi / the DIN offset convolutions: 1.1e-1)
