@@ -302,6 +302,7 @@ DIN_API int din_dynamic_infer_f32(const float* x, const float* w_tap, const floa
  * Group read-out: max over actors -> fc_activities -> mean over frames.
  * Replaces: infer_model.py:224-232 (Volleyball) and :1311-1313 (Collective, with n_valid).
  * s [b, t, n, c] fp32, w [a, c], bias [a] -> logits [b, a].   a <= 64.
+ * n_valid[i] < 1 is a device-side trap (message on stdout): the reference's torch.max over an empty actor axis raises.
  */
 DIN_API int din_readout_f32(const float* s, const float* w, const float* bias, float* logits, int b, int t,
                             int n, int c, int a, const int32_t* n_valid, void* stream);
@@ -320,7 +321,8 @@ DIN_API int din_readout_f32(const float* s, const float* w, const float* bias, f
  * conf         : int32 [a, a], conf[target][predicted] += 1 (ACCUMULATES across calls; or NULL)
  * meters       : fp64 [4] ACCUMULATING: sum(loss * b), sum(b), sum(correct), steps        (or NULL)
  * dlogits      : fp32 [b, a] = loss_scale * w[y_i] / sum w * (softmax(logits_i) - onehot(y_i))   (or NULL)
- * a <= 64.
+ * a <= 64.  labels[i] == -100 (torch's ignore_index) contributes nothing; any other label outside [0, a) is a device-side
+ * trap (message on stdout), as torch's device-side assert.
  */
 DIN_API int din_ce_metrics_f32(const float* logits, const int64_t* labels, const float* class_weight,
                                float loss_scale, float* loss, int32_t* correct, int32_t* conf, double* meters,
