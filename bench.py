@@ -13,8 +13,10 @@ Dynamic Walk -> read-out) over one batch of B clips per GPU.  Prints ONE JSON li
              region (copies are double-buffered on a side stream so they overlap the previous step)
   roofline   the dominant kernel (the tcgen05 implicit-GEMM convolution): algorithmic FLOPs of its launches
              / their CUDA-event durations, against the measured bf16 tensor peak in MEASURED_PEAKS.json
-  cpu_baseline  the CPU port of the reference path (oracle/, torch-CPU fp32, all host cores) on a bounded
-             sample of the same workload
+  cpu_baseline  the reference's own infer_model classes (staged copy oracle/_ref; else the CPU port under oracle/),
+             torch-CPU fp32, all host cores, on a bounded sample of the same workload
+  train_step (supplementary) one stage-2 training step on 2 clips per GPU, gradient all-reduce inside at N > 1:
+             ms_per_step = the MEDIAN of the timed steps (max over ranks), ms_per_step_mean and step_ms beside it
 `--impl reference` times that CPU implementation alone, on the same config / metric.
 """
 import argparse
